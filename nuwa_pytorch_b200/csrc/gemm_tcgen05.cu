@@ -1,0 +1,525 @@
+// Persistent, warp-specialised bf16 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   C[M,N] = epilogue( A[M,K] * W[N,K]^T )        A, W bf16 (K contiguous), fp32 accumulate in TMEM
+//
+// * operands are staged HBM -> shared memory by TMA (SWIZZLE_128B, 64-element K slabs),
+// * the contraction runs on the 5th-gen tensor cores: tcgen05.mma (cta_group::1, M=128, N=BN,
+//   K=16 per instruction) issued by one thread, accumulators double-buffered in TMEM so the
+//   epilogue of tile i overlaps the main loop of tile i+1,
+// * the epilogue reads TMEM with tcgen05.ld and fuses bias, LeakyReLU(0.1), GLU, GEGLU and the
+//   residual add, writing fp32 and/or bf16.
+//
+// "conv" mode turns the A operand into an implicit im2col of an NHWC bf16 activation: one M tile
+// is a (tb x th x tw) block of output pixels, each K slab is (filter tap, 64 input channels) and is
+// fetched with ONE 4-D TMA box at the tap-shifted coordinate; TMA's out-of-bounds zero fill is the
+// convolution's zero padding.  Stride-2 convolutions read one of four parity views of the input
+// (one tensor map each), so every tap is still a dense box.
+//
+// Reference ops this kernel replaces (all ATen library calls in the reference):
+//   nn.Linear  nuwa_pytorch.py:274,277,311-313,401-405,1819   nn.Conv2d  vqgan_vae.py:216-238,262-263,352-366
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nuwa {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-5 epilogue
+static constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator buffers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TileCoord {
+  int mt, nt;
+};
+// grouped raster: walk GROUP_M m-tiles for each n-tile so that concurrently resident CTAs share
+// both A and W slabs in L2.
+__device__ __forceinline__ TileCoord tile_coord(int tile, int num_m, int num_n) {
+  const int GROUP_M = 8;
+  int per_group = GROUP_M * num_n;
+  int g = tile / per_group;
+  int first_m = g * GROUP_M;
+  int gsz = min(num_m - first_m, GROUP_M);
+  int r = tile - g * per_group;
+  TileCoord c;
+  c.mt = first_m + (r % gsz);
+  c.nt = r / gsz;
+  return c;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+                    const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB);
+    if (p.conv) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmA3);
+    }
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t a_bytes = p.conv ? (uint32_t)(p.tb * p.th * p.tw * BK * 2) : (uint32_t)A_STAGE_BYTES;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(tile, p.num_m_tiles, p.num_n_tiles);
+        const int n0 = tc.nt * BN;
+        int x0 = 0, y0 = 0, b0 = 0;
+        if (p.conv) {
+          int xt = tc.mt % p.tiles_x;
+          int yt = (tc.mt / p.tiles_x) % p.tiles_y;
+          int bt = tc.mt / (p.tiles_x * p.tiles_y);
+          x0 = xt * p.tw;
+          y0 = yt * p.th;
+          b0 = bt * p.tb;
+        }
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], a_bytes + Cfg::B_STAGE_BYTES);
+          if (p.conv) {
+            int tap = kb / p.cin_blocks;
+            int cb = kb - tap * p.cin_blocks;
+            int which = p.tap_map[tap];
+            const CUtensorMap* ma = which == 0 ? &tmA0 : (which == 1 ? &tmA1 : (which == 2 ? &tmA2 : &tmA3));
+            tma_load_4d(sa, ma, &full_bar[stage], cb * BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0);
+          } else {
+            tma_load_2d(sa, &tmA0, &full_bar[stage], kb * BK, tc.mt * BM);
+          }
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in (addr >> 4) units
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above retire
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue (4 warps) ================================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool pair = (p.act == ACT_GLU || p.act == ACT_GEGLU);
+    const int n_out_total = pair ? p.N / 2 : p.N;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = tile_coord(tile, p.num_m_tiles, p.num_n_tiles);
+      const int n0 = tc.nt * BN;
+      // output row of this thread
+      long long m;
+      bool row_ok;
+      if (p.conv) {
+        int xt = tc.mt % p.tiles_x;
+        int yt = (tc.mt / p.tiles_x) % p.tiles_y;
+        int bt = tc.mt / (p.tiles_x * p.tiles_y);
+        int per_img = p.th * p.tw;
+        int bb = r / per_img;
+        int rem = r - bb * per_img;
+        int yy = rem / p.tw;
+        int xx = rem - yy * p.tw;
+        int b = bt * p.tb + bb, y = yt * p.th + yy, x = xt * p.tw + xx;
+        row_ok = (bb < p.tb) && (b < p.B) && (y < p.H) && (x < p.W);
+        m = ((long long)b * p.H + y) * p.W + x;
+      } else {
+        m = (long long)tc.mt * BM + r;
+        row_ok = m < p.M;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {
+          // all TMEM reads of this accumulator are done: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        const int nc = n0 + c * 32;
+        if (!row_ok || nc >= p.N) continue;
+        if (!pair) {
+#pragma unroll
+          for (int j0 = 0; j0 < 32; j0 += 4) {
+            const int n = nc + j0;
+            if (n >= p.N) break;
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a = __uint_as_float(v[j0 + j]);
+              if (p.bias != nullptr && n + j < p.N) a += p.bias[n + j];
+              if (p.act == ACT_LEAKY) a = leaky01(a);
+              o[j] = a;
+            }
+            if (n + 3 < p.N) {
+              if (p.residual != nullptr) {
+                const float4 rr = *reinterpret_cast<const float4*>(p.residual + m * p.ld_res + n);
+                o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+              }
+              if (p.out_f32 != nullptr)
+                *reinterpret_cast<float4*>(p.out_f32 + m * p.ld_out + n) = make_float4(o[0], o[1], o[2], o[3]);
+              if (p.out_bf16 != nullptr) {
+                uint2 pk;
+                pk.x = pack_bf16x2(o[0], o[1]);
+                pk.y = pack_bf16x2(o[2], o[3]);
+                *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_out + n) = pk;
+              }
+            } else {
+              for (int j = 0; j < 4 && n + j < p.N; ++j) {
+                float a = o[j];
+                if (p.residual != nullptr) a += p.residual[m * p.ld_res + n + j];
+                if (p.out_f32 != nullptr) p.out_f32[m * p.ld_out + n + j] = a;
+                if (p.out_bf16 != nullptr) p.out_bf16[m * p.ld_out + n + j] = __float2bfloat16(a);
+              }
+            }
+          }
+        } else {
+          // packed pair layout: within every 32 packed columns, [0,16) = value half, [16,32) = gate half
+          const int no = nc / 2;
+#pragma unroll
+          for (int j0 = 0; j0 < 16; j0 += 4) {
+            const int n = no + j0;
+            if (n >= n_out_total) break;
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a = __uint_as_float(v[j0 + j]);
+              float g = __uint_as_float(v[16 + j0 + j]);
+              if (p.bias != nullptr) {
+                a += p.bias[nc + j0 + j];
+                g += p.bias[nc + 16 + j0 + j];
+              }
+              o[j] = (p.act == ACT_GLU) ? a * sigmoid_f(g) : a * gelu_erf(g);
+            }
+            if (p.residual != nullptr) {
+              const float4 rr = *reinterpret_cast<const float4*>(p.residual + m * p.ld_res + n);
+              o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+            }
+            if (p.out_f32 != nullptr)
+              *reinterpret_cast<float4*>(p.out_f32 + m * p.ld_out + n) = make_float4(o[0], o[1], o[2], o[3]);
+            if (p.out_bf16 != nullptr) {
+              uint2 pk;
+              pk.x = pack_bf16x2(o[0], o[1]);
+              pk.y = pack_bf16x2(o[2], o[3]);
+              *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_out + n) = pk;
+            }
+          }
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  }
+  return fn;
+}
+
+// rank-2..4 bf16 tensor map, innermost box 64 elements (128 B), SWIZZLE_128B, zero OOB fill.
+static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return NUWA_ERR_DRIVER;
+  cuuint64_t gdims[4];
+  cuuint64_t gstr[3];
+  cuuint32_t gbox[4];
+  cuuint32_t estr[4];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i];
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? NUWA_OK : NUWA_ERR_INVALID;
+}
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+static int pick_bn(int num_m_tiles, int N, int force_bn) {
+  if (force_bn == 64 || force_bn == 128 || force_bn == 256) return force_bn;
+  const int sms = device_sm_count();
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    int bn = cands[i];
+    if (bn > 64 && N <= bn / 2) continue;  // too much padding
+    int tiles = num_m_tiles * ceil_div(N, bn);
+    if (tiles >= sms || bn == 64) return bn;
+  }
+  return 64;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
+        cudaSuccess)
+      return NUWA_ERR_CUDA;
+    attr_set = true;
+  }
+  p.num_n_tiles = ceil_div(p.N, BN);
+  int total = p.num_m_tiles * p.num_n_tiles;
+  int grid = total < device_sm_count() ? total : device_sm_count();
+  if (grid <= 0) return NUWA_OK;
+  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mA[0], mA[1], mA[2], mA[3], mB, p);
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+
+static int dispatch_gemm(const CUtensorMap* mA, const void* Wp, GemmParams& p, int force_bn, cudaStream_t stream) {
+  const int bn = pick_bn(p.num_m_tiles, p.N, force_bn);
+  // weight map: dims (K, N), row stride K*2 bytes, box (64, bn)
+  CUtensorMap mB;
+  uint64_t dimsB[2] = {(uint64_t)p.K, (uint64_t)p.N};
+  uint64_t strB[2] = {2, (uint64_t)p.ldw * 2};
+  uint32_t boxB[2] = {64, (uint32_t)bn};
+  int e = encode_map(&mB, Wp, 2, dimsB, strB, boxB);
+  if (e) return e;
+  if (bn == 256) return launch_gemm<256>(mA, mB, p, stream);
+  if (bn == 128) return launch_gemm<128>(mA, mB, p, stream);
+  return launch_gemm<64>(mA, mB, p, stream);
+}
+
+static bool epilogue_args_ok(const GemmParams& p) {
+  const bool pair = (p.act == ACT_GLU || p.act == ACT_GEGLU);
+  if (p.act < 0 || p.act > ACT_GEGLU) return false;
+  if (pair && (p.N % 32) != 0) return false;
+  if (p.out_f32 == nullptr && p.out_bf16 == nullptr) return false;
+  if (p.ld_out % 4 != 0) return false;
+  if (p.residual != nullptr && p.ld_res % 4 != 0) return false;
+  return true;
+}
+
+int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+              const float* residual, int ld_res, float* out_f32, void* out_bf16, int ld_out, int act, int force_bn,
+              cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return NUWA_ERR_INVALID;
+  if ((lda % 8) || (ldw % 8) || lda < K || ldw < K) return NUWA_ERR_INVALID;  // TMA: 16-byte row pitch
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) return NUWA_ERR_INVALID;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K; p.ldw = ldw;
+  p.k_blocks = ceil_div(K, BK);
+  p.num_m_tiles = ceil_div(M, BM);
+  p.bias = bias; p.residual = residual; p.ld_res = ld_res;
+  p.out_f32 = out_f32; p.out_bf16 = reinterpret_cast<bf16*>(out_bf16); p.ld_out = ld_out; p.act = act;
+  p.conv = 0;
+  if (!epilogue_args_ok(p)) return NUWA_ERR_INVALID;
+  CUtensorMap mA[4];
+  uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M};
+  uint64_t strA[2] = {2, (uint64_t)lda * 2};
+  uint32_t boxA[2] = {64, 128};
+  int e = encode_map(&mA[0], A, 2, dimsA, strA, boxA);
+  if (e) return e;
+  mA[1] = mA[0]; mA[2] = mA[0]; mA[3] = mA[0];
+  return dispatch_gemm(mA, W, p, force_bn, stream);
+}
+
+// NHWC bf16 convolution.  x: [B, Hin, Win, Cin] ; w: [Cout, KH*KW, Cin_pad] (Cin_pad = roundup(Cin,64), zero padded)
+// supported: (KH=KW=3, stride 1, pad 1), (KH=KW=1, stride 1, pad 0), (KH=KW=4, stride 2, pad 1).
+int conv2d_nhwc_bf16(const void* x, const void* w, int B, int Hin, int Win, int Cin, int Cout, int ksize, int stride,
+                     const float* bias, const float* residual, float* out_f32, void* out_bf16, int act, int force_bn,
+                     cudaStream_t stream) {
+  if (B <= 0 || Hin <= 0 || Win <= 0 || Cin <= 0 || Cout <= 0) return NUWA_ERR_INVALID;
+  if (Cin % 8) return NUWA_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(x) & 15) return NUWA_ERR_INVALID;
+  const bool k3 = (ksize == 3 && stride == 1), k1 = (ksize == 1 && stride == 1), k4 = (ksize == 4 && stride == 2);
+  if (!k3 && !k1 && !k4) return NUWA_ERR_INVALID;
+  if (k4 && ((Hin & 1) || (Win & 1))) return NUWA_ERR_INVALID;
+  const int H = k4 ? Hin / 2 : Hin, W = k4 ? Win / 2 : Win;
+  const int cin_blocks = ceil_div(Cin, BK);
+  const int ntaps = ksize * ksize;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.conv = 1;
+  p.B = B; p.H = H; p.W = W;
+  p.tw = W < 128 ? W : 128;
+  p.th = (128 / p.tw) < H ? (128 / p.tw) : H;
+  p.tb = 128 / (p.tw * p.th);
+  if (p.tb > B) p.tb = B;
+  if (p.tb < 1) p.tb = 1;
+  p.tiles_x = ceil_div(W, p.tw);
+  p.tiles_y = ceil_div(H, p.th);
+  int tiles_b = ceil_div(B, p.tb);
+  p.num_m_tiles = p.tiles_x * p.tiles_y * tiles_b;
+  p.cin_blocks = cin_blocks;
+  p.M = B * H * W;
+  p.N = Cout;
+  p.K = ntaps * cin_blocks * BK;
+  p.ldw = p.K;
+  p.k_blocks = ntaps * cin_blocks;
+  p.bias = bias; p.residual = residual;
+  const bool pair = (act == ACT_GLU || act == ACT_GEGLU);
+  p.ld_res = pair ? Cout / 2 : Cout;
+  p.ld_out = pair ? Cout / 2 : Cout;
+  p.out_f32 = out_f32; p.out_bf16 = reinterpret_cast<bf16*>(out_bf16); p.act = act;
+  if (!epilogue_args_ok(p)) return NUWA_ERR_INVALID;
+
+  CUtensorMap mA[4];
+  const uint8_t* xb = reinterpret_cast<const uint8_t*>(x);
+  if (!k4) {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
+    uint64_t str[4] = {2, (uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+    uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tb};
+    int e = encode_map(&mA[0], xb, 4, dims, str, box);
+    if (e) return e;
+    mA[1] = mA[0]; mA[2] = mA[0]; mA[3] = mA[0];
+    const int pad = k3 ? 1 : 0;
+    for (int kh = 0; kh < ksize; ++kh)
+      for (int kw = 0; kw < ksize; ++kw) {
+        int t = kh * ksize + kw;
+        p.tap_map[t] = 0;
+        p.tap_dy[t] = (int8_t)(kh - pad);
+        p.tap_dx[t] = (int8_t)(kw - pad);
+      }
+  } else {
+    // input row iy = 2*oy + kh - 1 : parity py = (kh-1)&1, half-res row = oy + floor((kh-1)/2)
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)(Win / 2), (uint64_t)(Hin / 2), (uint64_t)B};
+        uint64_t str[4] = {2, (uint64_t)2 * Cin * 2, (uint64_t)2 * Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+        uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tb};
+        int e = encode_map(&mA[py * 2 + px], xb + ((size_t)py * Win + px) * Cin * 2, 4, dims, str, box);
+        if (e) return e;
+      }
+    for (int kh = 0; kh < 4; ++kh)
+      for (int kw = 0; kw < 4; ++kw) {
+        int t = kh * 4 + kw;
+        int py = (kh - 1) & 1, px = (kw - 1) & 1;
+        p.tap_map[t] = (int8_t)(py * 2 + px);
+        p.tap_dy[t] = (int8_t)((kh - 1 - py) / 2);
+        p.tap_dx[t] = (int8_t)((kw - 1 - px) / 2);
+      }
+  }
+  return dispatch_gemm(mA, w, p, force_bn, stream);
+}
+
+}  // namespace nuwa
