@@ -32,6 +32,8 @@ const char* nuwa_strerror(int code);
 int nuwa_abi_version(void);
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 unsigned long long nuwa_launch_count(void);
+/* sizeof(nuwa_ln_params), sizeof(nuwa_attn_params), sizeof(nuwa_embed_params) -- lets a binding verify its struct mirror */
+void nuwa_struct_sizes(int* out3);
 
 /* ---- dense contraction (tcgen05) ------------------------------------------------------------
  * out[M,N] = act(A[M,K] @ W[N,K]^T + bias) + residual.   A, W bf16 with K contiguous.
@@ -53,6 +55,124 @@ int nuwa_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N,
 int nuwa_conv2d_nhwc_bf16(const void* x, const void* w, int B, int Hin, int Win, int Cin, int Cout, int ksize,
                           int stride, const float* bias, const float* residual, float* out_f32, void* out_bf16,
                           int act, int force_bn, void* stream);
+
+
+/* ---- row normalisation ------------------------------------------------------------------------
+ * nuwa_sandwich_ln: stage A (if y != NULL)   x_out = res_in + LayerNorm(y; post_w, post_b)
+ *                                            (SandwichNorm post-norm + residual: nuwa_pytorch.py:127,1175-1180;
+ *                                             reversible y1 = x1 + f(x2): reversible.py:65-66; LayerNormChan +
+ *                                             residual on NHWC rows: vqgan_vae.py:140-143,286)
+ *                   stage B (if pre_w != NULL) a_out = bf16(LayerNorm(x; pre_w, pre_b)) with the
+ *                                            ShiftVideoTokens channel shift fused as a scatter
+ *                                            (nuwa_pytorch.py:125,200-253).
+ * Rows are (b, t) with t = t0 + local index, nt rows per sample; y/res_in/x_out are dense [B*nt, D] fp32.
+ * a_out row of position t lives at a_out + b*a_bs + (t - a_t0)*a_rs ; a_npos = positions the buffer holds. */
+typedef struct {
+  const float* y;
+  const float* post_w;
+  const float* post_b;
+  const float* res_in;
+  float* x_out;
+  void* x_out_bf16;
+  const float* pre_w;
+  const float* pre_b;
+  void* a_out;
+  long long a_bs;
+  int a_rs, a_t0, a_npos;
+  int shift, fmap;
+  int t0, B, nt, D;
+  float eps;
+} nuwa_ln_params;
+int nuwa_sandwich_ln(const nuwa_ln_params* p, void* stream);
+
+/* StableLayerNorm of (a [+ b2]): LN(v / amax(v)) -- nuwa_pytorch.py:88-95 (b2: the reversible stream sum,
+ * reversible.py:142).  Writes fp32 and/or bf16. */
+int nuwa_stable_ln(const float* a, const float* b2, const float* w, const float* bias, float* out_f32, void* out_bf16,
+                   int rows, int D, void* stream);
+
+/* ---- fused attention cores -------------------------------------------------------------------
+ * q/k/v/o are bf16; element strides: *_bs per batch sample, *_rs per token row; heads are contiguous
+ * [H][dh] inside a row.  nq query positions per sample starting at absolute position t0.
+ * talk: fp32 [H][H] talking-heads matrix or NULL.  jmax = key slots per query. */
+typedef struct {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  long long q_bs, k_bs, v_bs, o_bs;
+  int q_rs, k_rs, v_rs, o_rs;
+  int B, nq, t0, H, dh;
+  float qscale;
+  const float* head_scale; /* [H] logit multiplier (exp(scale), vqgan_vae.py:275) or NULL */
+  const float* talk;
+  const float* null_k;     /* fp32 [H*dh] learned null key / value (nuwa_pytorch.py:306-307) or NULL */
+  const float* null_v;
+  const unsigned char* key_mask; /* [B][mask_bs] 1 = attend, or NULL */
+  int mask_bs;
+  const float* bias;       /* [H][bias_nq][bias_nk] additive logit bias (vqgan_vae.py:277) or NULL */
+  int bias_nq, bias_nk;
+  /* Sparse3DNA geometry (nuwa_pytorch.py:407-457) */
+  int fmap, max_frames, nv, kt, kh, kw, dt, dh_, dw, causal;
+  /* SparseCross2DNA geometry (nuwa_pytorch.py:789-792) */
+  int ck, cdil;
+  int jmax;
+} nuwa_attn_params;
+/* Sparse3DNA.forward core, nuwa_pytorch.py:490-608 (jmax = 1 + kt*kh*kw; k/v row 0 = bos, row 1+i = video token i) */
+int nuwa_attn_sparse3dna(const nuwa_attn_params* p, void* stream);
+/* Attention.forward core, nuwa_pytorch.py:339-378, and VQGanAttention core, vqgan_vae.py:275-282
+ * (jmax = nk (+1 with a null key)) */
+int nuwa_attn_dense(const nuwa_attn_params* p, void* stream);
+/* SparseCross2DNA.forward non-bos queries, nuwa_pytorch.py:851-895 (jmax = 1 + frames*ck*ck; t0 >= 1) */
+int nuwa_attn_cross2dna(const nuwa_attn_params* p, void* stream);
+
+/* ---- token level ----------------------------------------------------------------------------- */
+typedef struct {
+  float* out;             /* [B*nt, D] fp32 */
+  const long long* idx;   /* token ids, row b at idx + b*idx_bs */
+  long long idx_bs;
+  const float* table;     /* [V, D] */
+  const float* bos;       /* [D] or NULL */
+  const float* ax1;       /* axial tables (NULL = axis dropped), position p -> (p/(d2*d3), (p/d3)%d2, p%d3) */
+  const float* ax2;
+  const float* ax3;
+  int d2, d3;
+  int has_bos, t0, B, nt, D;
+} nuwa_embed_params;
+/* Embedding + AxialPositionalEmbedding + bos: nuwa_pytorch.py:1659-1709,1879-1881,1940-1944 */
+int nuwa_embed_tokens(const nuwa_embed_params* p, void* stream);
+/* rotary embedding of q,k AND v (nuwa_pytorch.py:132-153,333-335): qkv fp32 [rows,3*H*dh] -> bf16 */
+int nuwa_rotary_to_bf16(const float* qkv, void* out, const float* inv_freq, int rows, int n, int H, int dh, int rot,
+                        void* stream);
+/* F.cross_entropy mean over rows (nuwa_pytorch.py:1963); row_loss: workspace [rows] */
+int nuwa_cross_entropy_mean(const float* logits, int ld, const long long* target, float* row_loss, float* out, int rows,
+                            int V, void* stream);
+/* generate() sampling step (nuwa_pytorch.py:1901-1906,1713-1719,55-66): guidance mix, top-k, gumbel argmax.
+ * uncond may be NULL (cond_scale == 1); guided_out (optional) receives the mixed logits [B,V]. */
+int nuwa_sample_topk_gumbel(const float* cond, const float* uncond, const float* noise, long long* out,
+                            float* guided_out, int B, int V, int k, float cond_scale, float temperature, void* stream);
+
+/* ---- VQGanVAE support kernels ---------------------------------------------------------------- */
+int nuwa_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, void* stream);
+int nuwa_nhwc_to_nchw_f32(const void* in, int in_is_bf16, float* out, int B, int C, int H, int W, void* stream);
+/* im2col of the first conv (vqgan_vae.py:365): K index (kh*KS+kw)*C + c, zero padded to Kpad */
+int nuwa_im2col_nchw_f32(const float* img, void* out, int B, int C, int H, int W, int KS, int Kpad, void* stream);
+/* nn.GroupNorm(G, C) on NHWC fp32 (+LeakyReLU 0.1) (vqgan_vae.py:218,221,233,236); stats_ws: [B*G*2] floats */
+int nuwa_groupnorm_nhwc(const float* x, const float* w, const float* bias, float* stats_ws, void* out_bf16,
+                        float* out_f32, int B, int HW, int C, int G, int leaky, void* stream);
+/* nn.Upsample(scale_factor=2, bilinear, align_corners=False) (vqgan_vae.py:353) */
+int nuwa_upsample2x_nhwc_bf16(const void* in, void* out, int B, int H, int W, int C, void* stream);
+/* VQGanAttention q,k l2norm over the spatial axis (vqgan_vae.py:271-273): qkv fp32 [B,n,3*inner] -> bf16 */
+int nuwa_vae_attn_prep(const float* qkv, void* out, int B, int n, int inner, void* stream);
+/* VectorQuantize codebook arg-max (call site vqgan_vae.py:435). code: cosine -> pre-normalised codebook,
+ * euclid -> raw codebook + code_sq[Kc] = |e|^2.  out: int64 [M], first maximum wins. */
+int nuwa_vq_argmax(const float* x, const float* code, const float* code_sq, long long* out, int M, int Kc, int D,
+                   int cosine, void* stream);
+/* F.embedding / codebook[indices] (vqgan_vae.py:447, nuwa_pytorch.py:1910) */
+int nuwa_gather_rows(const float* table, const long long* idx, void* out_bf16, float* out_f32, long long M, int D,
+                     void* stream);
+/* final Conv2d(dim, channels, 1) (vqgan_vae.py:366): NHWC bf16 -> NCHW fp32, Cout <= 8 */
+int nuwa_conv1x1_nhwc_to_nchw(const void* x, const float* w, const float* bias, float* out, int B, int HW, int C,
+                              int Cout, void* stream);
 
 #ifdef __cplusplus
 }

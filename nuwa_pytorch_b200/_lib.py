@@ -12,18 +12,67 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libnuwa_b200.so")
 
 c_int, c_void_p, c_float, c_ll = ctypes.c_int, ctypes.c_void_p, ctypes.c_float, ctypes.c_longlong
+P = ctypes.POINTER
 
-# name -> argtypes (restype is int unless listed in _RESTYPES)
+
+class LnParams(ctypes.Structure):  # mirrors nuwa_ln_params
+    _fields_ = [("y", c_void_p), ("post_w", c_void_p), ("post_b", c_void_p), ("res_in", c_void_p),
+                ("x_out", c_void_p), ("x_out_bf16", c_void_p), ("pre_w", c_void_p), ("pre_b", c_void_p),
+                ("a_out", c_void_p), ("a_bs", c_ll), ("a_rs", c_int), ("a_t0", c_int), ("a_npos", c_int),
+                ("shift", c_int), ("fmap", c_int), ("t0", c_int), ("B", c_int), ("nt", c_int), ("D", c_int),
+                ("eps", c_float)]
+
+
+class AttnParams(ctypes.Structure):  # mirrors nuwa_attn_params
+    _fields_ = [("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("o", c_void_p),
+                ("q_bs", c_ll), ("k_bs", c_ll), ("v_bs", c_ll), ("o_bs", c_ll),
+                ("q_rs", c_int), ("k_rs", c_int), ("v_rs", c_int), ("o_rs", c_int),
+                ("B", c_int), ("nq", c_int), ("t0", c_int), ("H", c_int), ("dh", c_int), ("qscale", c_float),
+                ("head_scale", c_void_p), ("talk", c_void_p), ("null_k", c_void_p), ("null_v", c_void_p),
+                ("key_mask", c_void_p), ("mask_bs", c_int), ("bias", c_void_p), ("bias_nq", c_int), ("bias_nk", c_int),
+                ("fmap", c_int), ("max_frames", c_int), ("nv", c_int), ("kt", c_int), ("kh", c_int), ("kw", c_int),
+                ("dt", c_int), ("dh_", c_int), ("dw", c_int), ("causal", c_int), ("ck", c_int), ("cdil", c_int),
+                ("jmax", c_int)]
+
+
+class EmbedParams(ctypes.Structure):  # mirrors nuwa_embed_params
+    _fields_ = [("out", c_void_p), ("idx", c_void_p), ("idx_bs", c_ll), ("table", c_void_p), ("bos", c_void_p),
+                ("ax1", c_void_p), ("ax2", c_void_p), ("ax3", c_void_p), ("d2", c_int), ("d3", c_int),
+                ("has_bos", c_int), ("t0", c_int), ("B", c_int), ("nt", c_int), ("D", c_int)]
+
+
+# name -> argtypes (restype is int unless listed in _RESTYPES).  Must list EVERY symbol of include/nuwa_b200.h.
 SIGNATURES = {
     "nuwa_abi_version": [],
     "nuwa_launch_count": [],
     "nuwa_strerror": [c_int],
+    "nuwa_struct_sizes": [P(c_int)],
     "nuwa_gemm_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                        c_void_p, c_int, c_int, c_int, c_void_p],
     "nuwa_conv2d_nhwc_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "nuwa_sandwich_ln": [P(LnParams), c_void_p],
+    "nuwa_stable_ln": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "nuwa_attn_sparse3dna": [P(AttnParams), c_void_p],
+    "nuwa_attn_dense": [P(AttnParams), c_void_p],
+    "nuwa_attn_cross2dna": [P(AttnParams), c_void_p],
+    "nuwa_embed_tokens": [P(EmbedParams), c_void_p],
+    "nuwa_rotary_to_bf16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "nuwa_cross_entropy_mean": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "nuwa_sample_topk_gumbel": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                c_float, c_void_p],
+    "nuwa_nchw_f32_to_nhwc_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "nuwa_nhwc_to_nchw_f32": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "nuwa_im2col_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "nuwa_groupnorm_nhwc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                            c_int, c_void_p],
+    "nuwa_upsample2x_nhwc_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "nuwa_vae_attn_prep": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "nuwa_vq_argmax": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "nuwa_gather_rows": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
+    "nuwa_conv1x1_nhwc_to_nchw": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
 }
-_RESTYPES = {"nuwa_strerror": ctypes.c_char_p, "nuwa_launch_count": ctypes.c_ulonglong}
+_RESTYPES = {"nuwa_strerror": ctypes.c_char_p, "nuwa_launch_count": ctypes.c_ulonglong, "nuwa_struct_sizes": None}
 
 _lib = None
 
@@ -45,6 +94,11 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the symbol is not exported
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, c_int)
+        sizes = (c_int * 3)()
+        handle.nuwa_struct_sizes(sizes)
+        mine = (ctypes.sizeof(LnParams), ctypes.sizeof(AttnParams), ctypes.sizeof(EmbedParams))
+        if tuple(sizes) != mine:
+            raise NuwaB200Error(f"struct layout mismatch between include/nuwa_b200.h {tuple(sizes)} and _lib.py {mine}")
         _lib = handle
     return _lib
 
@@ -59,7 +113,8 @@ def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     if t is None:
         return None
-    assert t.is_cuda, "nuwa_pytorch_b200 kernels need CUDA tensors (there is no CPU path)"
+    if not t.is_cuda:
+        raise NuwaB200Error("nuwa_pytorch_b200 kernels need CUDA tensors (there is no CPU path)")
     return t.data_ptr()
 
 

@@ -1,0 +1,320 @@
+// Fused attention cores: neighbourhood gather / dense keys + QK^T + mask + fp32 softmax +
+// talking-heads mix across heads + PV, one kernel, nothing materialised in HBM.
+//
+// One warp owns QPW query tokens with ALL heads (the post-softmax talking-heads 1x1 conv mixes
+// probabilities across heads, nuwa_pytorch.py:556-558 / :372 / :889, so every head's row must exist
+// before any PV).  The 32 lanes split the H*dh channels (CPL per lane, 32/H lanes per head); scores
+// live in shared memory as [QPW][H][J]; K/V rows are read with 16-byte vector loads straight from
+// the bf16 q|k|v projection buffer (neighbour reuse is served by L1/L2).
+//
+// Key generators:
+//   MODE_3DNA   Sparse3DNA (nuwa_pytorch.py:459-613): bos key + (kt,kh,kw) dilated window, causal or
+//               centred; out-of-grid slots are masked, in-grid slots beyond the supplied tokens are
+//               visible ZERO keys; query 0 (bos) copies its own value (:608).
+//   MODE_DENSE  Attention (nuwa_pytorch.py:315-379): optional learned null key/value (fp32), key mask,
+//               optional additive bias + per-head logit scale (VQGanAttention, vqgan_vae.py:275-279).
+//   MODE_X2DNA  SparseCross2DNA non-bos queries (nuwa_pytorch.py:851-895): null + k x k window at the
+//               query's own (y,x) in every context frame.
+#include <float.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nuwa {
+
+enum { MODE_3DNA = 0, MODE_DENSE = 1, MODE_X2DNA = 2 };
+enum { KEY_NORMAL = 0, KEY_MASKED = 1, KEY_ZERO = 2, KEY_NULL = 3 };
+
+template <int CPL>
+__device__ __forceinline__ void load_row(const bf16* p, float (&out)[CPL]) {
+  if constexpr (CPL >= 8) {
+#pragma unroll
+    for (int i = 0; i < CPL / 8; ++i) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + i);
+      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      out[i * 8 + 0] = a.x; out[i * 8 + 1] = a.y; out[i * 8 + 2] = b.x; out[i * 8 + 3] = b.y;
+      out[i * 8 + 4] = c.x; out[i * 8 + 5] = c.y; out[i * 8 + 6] = d.x; out[i * 8 + 7] = d.y;
+    }
+  } else if constexpr (CPL == 4) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+  } else if constexpr (CPL == 2) {
+    const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p));
+    float2 a = unpack_bf16x2(u);
+    out[0] = a.x; out[1] = a.y;
+  } else {
+    out[0] = __bfloat162float(p[0]);
+  }
+}
+template <int CPL>
+__device__ __forceinline__ void load_row_f32(const float* p, float (&out)[CPL]) {
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) out[i] = __ldg(p + i);
+}
+template <int CPL>
+__device__ __forceinline__ void store_row(bf16* p, const float (&v)[CPL]) {
+  if constexpr (CPL >= 8) {
+#pragma unroll
+    for (int i = 0; i < CPL / 8; ++i) {
+      uint4 u;
+      u.x = pack_bf16x2(v[i * 8 + 0], v[i * 8 + 1]);
+      u.y = pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
+      u.z = pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]);
+      u.w = pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
+      reinterpret_cast<uint4*>(p)[i] = u;
+    }
+  } else if constexpr (CPL == 4) {
+    uint2 u;
+    u.x = pack_bf16x2(v[0], v[1]);
+    u.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = u;
+  } else if constexpr (CPL == 2) {
+    *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(v[0], v[1]);
+  } else {
+    p[0] = __float2bfloat16(v[0]);
+  }
+}
+
+// key slot j of query position t (absolute sequence index) -> kind and row in the K/V buffers
+template <int MODE>
+__device__ __forceinline__ int key_of(const AttnParams& p, int b, int t, int j, int& row) {
+  if constexpr (MODE == MODE_3DNA) {
+    if (j == 0) {
+      row = 0;  // bos key / value
+      return KEY_NORMAL;
+    }
+    const int jj = j - 1;
+    const int c = jj % p.kw, bq = (jj / p.kw) % p.kh, a = jj / (p.kw * p.kh);
+    const int T = p.fmap * p.fmap;
+    const int vt = t - 1;
+    const int f = vt / T, y = (vt % T) / p.fmap, x = vt % p.fmap;
+    const int pf = p.dt * (p.kt - 1) / 2, ph = p.dh_ * (p.kh - 1) / 2, pw = p.dw * (p.kw - 1) / 2;
+    const int Pf = p.causal ? 2 * pf : pf, Ph = p.causal ? 2 * ph : ph, Pw = p.causal ? 2 * pw : pw;
+    const int ff = f + a * p.dt - Pf, yy = y + bq * p.dh_ - Ph, xx = x + c * p.dw - Pw;
+    if (ff < 0 || ff >= p.max_frames || yy < 0 || yy >= p.fmap || xx < 0 || xx >= p.fmap) return KEY_MASKED;
+    const int idx = (ff * p.fmap + yy) * p.fmap + xx;
+    if (idx >= p.nv) return KEY_ZERO;  // zero-padded position: visible, contributes exp(0 - max), no value
+    row = 1 + idx;
+    return KEY_NORMAL;
+  } else if constexpr (MODE == MODE_DENSE) {
+    int jj = j;
+    if (p.null_k != nullptr) {
+      if (j == 0) return KEY_NULL;
+      jj = j - 1;
+    }
+    if (p.key_mask != nullptr && p.key_mask[(long long)b * p.mask_bs + jj] == 0) return KEY_MASKED;
+    row = jj;
+    return KEY_NORMAL;
+  } else {
+    if (j == 0) return KEY_NULL;
+    const int jj = j - 1;
+    const int J2 = p.ck * p.ck;
+    const int f = jj / J2, w = jj % J2;
+    const int a = w / p.ck, c = w % p.ck;
+    const int T = p.fmap * p.fmap;
+    const int i = (t - 1) % T;
+    const int y = i / p.fmap, x = i % p.fmap;
+    const int pad = p.cdil * (p.ck - 1) / 2;
+    const int yy = y + a * p.cdil - pad, xx = x + c * p.cdil - pad;
+    if (yy < 0 || yy >= p.fmap || xx < 0 || xx >= p.fmap) return KEY_MASKED;
+    const int idx = f * T + yy * p.fmap + xx;
+    if (p.key_mask != nullptr && p.key_mask[(long long)b * p.mask_bs + idx] == 0) return KEY_MASKED;
+    row = idx;
+    return KEY_NORMAL;
+  }
+}
+
+template <int MODE, int CPL, int QPW>
+__global__ void __launch_bounds__(128) attn_kernel(const AttnParams p) {
+  extern __shared__ float smem_f[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lph = 32 / p.H;            // lanes per head
+  const int h = lane / lph;            // head of this lane
+  const int sub = lane - h * lph;      // lane index inside the head group
+  const int J = p.jmax;                // key slots per query
+  float* S = smem_f + (size_t)warp * QPW * p.H * J;   // [QPW][H][J]
+  float* Wt = smem_f + (size_t)warps_per_cta * QPW * p.H * J;  // [H][H] talking-heads matrix
+  if (p.talk != nullptr) {
+    for (int i = threadIdx.x; i < p.H * p.H; i += blockDim.x) Wt[i] = p.talk[i];
+  }
+  __syncthreads();
+
+  const int groups_per_b = (p.nq + QPW - 1) / QPW;
+  const int gidx = blockIdx.x * warps_per_cta + warp;
+  if (gidx >= p.B * groups_per_b) return;
+  const int b = gidx / groups_per_b;
+  const int q0 = (gidx - b * groups_per_b) * QPW;  // first local query index of this warp
+  const int ch = lane * CPL;                        // first channel of this lane
+
+  const bf16* kb = reinterpret_cast<const bf16*>(p.k) + (long long)b * p.k_bs;
+  const bf16* vb = reinterpret_cast<const bf16*>(p.v) + (long long)b * p.v_bs;
+  const bf16* qb = reinterpret_cast<const bf16*>(p.q) + (long long)b * p.q_bs;
+  bf16* ob = reinterpret_cast<bf16*>(p.o) + (long long)b * p.o_bs;
+
+  float qf[QPW][CPL];
+  bool qok[QPW];
+#pragma unroll
+  for (int qi = 0; qi < QPW; ++qi) {
+    qok[qi] = (q0 + qi) < p.nq;
+    if (qok[qi]) {
+      load_row<CPL>(qb + (long long)(q0 + qi) * p.q_rs + ch, qf[qi]);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) qf[qi][c] *= p.qscale;
+    } else {
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) qf[qi][c] = 0.f;
+    }
+  }
+  const float hscale = p.head_scale != nullptr ? p.head_scale[h] : 1.0f;
+
+  // Sparse3DNA: the bos query attends only to itself -> output = its own value row
+  if (MODE == MODE_3DNA && (p.t0 + q0) == 0) {
+    float vv[CPL];
+    load_row<CPL>(vb + ch, vv);
+    store_row<CPL>(ob + (long long)q0 * p.o_rs + ch, vv);
+    qok[0] = false;  // (QPW == 1 for this mode)
+    if (QPW == 1) return;
+  }
+
+  // ---------------- scores ----------------
+  for (int j = 0; j < J; ++j) {
+    // key kind is query dependent only for the gather modes (QPW == 1 there)
+    int row = 0;
+    const int kind = key_of<MODE>(p, b, p.t0 + q0, j, row);
+    float part[QPW];
+    if (kind == KEY_NORMAL || kind == KEY_NULL) {
+      float kf[CPL];
+      if (kind == KEY_NULL) load_row_f32<CPL>(p.null_k + ch, kf);
+      else load_row<CPL>(kb + (long long)row * p.k_rs + ch, kf);
+#pragma unroll
+      for (int qi = 0; qi < QPW; ++qi) {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) s = fmaf(qf[qi][c], kf[c], s);
+        part[qi] = s;
+      }
+      for (int o = lph >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int qi = 0; qi < QPW; ++qi) part[qi] += __shfl_xor_sync(0xffffffffu, part[qi], o);
+      }
+    } else {
+#pragma unroll
+      for (int qi = 0; qi < QPW; ++qi) part[qi] = (kind == KEY_MASKED) ? -FLT_MAX : 0.f;
+    }
+    if (sub == 0) {
+#pragma unroll
+      for (int qi = 0; qi < QPW; ++qi) {
+        float s = part[qi];
+        if (kind != KEY_MASKED) {
+          s *= hscale;
+          if (p.bias != nullptr)
+            s += p.bias[((long long)h * p.bias_nq + (p.t0 + q0 + qi < p.bias_nq ? p.t0 + q0 + qi : 0)) * p.bias_nk + j];
+        }
+        S[(qi * p.H + h) * J + j] = s;
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---------------- fp32 softmax per (query, head) row ----------------
+#pragma unroll
+  for (int qi = 0; qi < QPW; ++qi) {
+    float* row_s = S + (qi * p.H + h) * J;
+    float m = -FLT_MAX;
+    for (int j = sub; j < J; j += lph) m = fmaxf(m, row_s[j]);
+    for (int o = lph >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int j = sub; j < J; j += lph) {
+      const float e = __expf(row_s[j] - m);
+      row_s[j] = e;
+      sum += e;
+    }
+    for (int o = lph >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    for (int j = sub; j < J; j += lph) row_s[j] *= inv;
+  }
+  __syncwarp();
+
+  // ---------------- talking heads: P'[g][j] = sum_h W[g][h] P[h][j] ----------------
+  if (p.talk != nullptr) {
+    for (int qi = 0; qi < QPW; ++qi) {
+      float* base = S + (size_t)qi * p.H * J;
+      for (int j = lane; j < J; j += 32) {
+        float pin[32];
+        for (int hh = 0; hh < p.H; ++hh) pin[hh] = base[hh * J + j];
+        for (int g = 0; g < p.H; ++g) {
+          float acc = 0.f;
+          for (int hh = 0; hh < p.H; ++hh) acc = fmaf(Wt[g * p.H + hh], pin[hh], acc);
+          base[g * J + j] = acc;
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---------------- PV ----------------
+  float acc[QPW][CPL];
+#pragma unroll
+  for (int qi = 0; qi < QPW; ++qi)
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) acc[qi][c] = 0.f;
+  for (int j = 0; j < J; ++j) {
+    int row = 0;
+    const int kind = key_of<MODE>(p, b, p.t0 + q0, j, row);
+    if (kind == KEY_MASKED || kind == KEY_ZERO) continue;
+    float vf[CPL];
+    if (kind == KEY_NULL) load_row_f32<CPL>(p.null_v + ch, vf);
+    else load_row<CPL>(vb + (long long)row * p.v_rs + ch, vf);
+#pragma unroll
+    for (int qi = 0; qi < QPW; ++qi) {
+      const float pj = S[(qi * p.H + h) * J + j];
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) acc[qi][c] = fmaf(pj, vf[c], acc[qi][c]);
+    }
+  }
+#pragma unroll
+  for (int qi = 0; qi < QPW; ++qi)
+    if (qok[qi]) store_row<CPL>(ob + (long long)(q0 + qi) * p.o_rs + ch, acc[qi]);
+}
+
+template <int MODE, int QPW>
+static int launch_attn(const AttnParams& p, cudaStream_t stream) {
+  const int inner = p.H * p.dh;
+  if (inner % 32 != 0 || (32 % p.H) != 0 || p.H > 32) return NUWA_ERR_INVALID;
+  const int cpl = inner / 32;
+  const int warps = 4;
+  const size_t smem = ((size_t)warps * QPW * p.H * p.jmax + p.H * p.H) * sizeof(float);
+  if (smem > 200 * 1024) return NUWA_ERR_INVALID;
+  const int groups = p.B * ((p.nq + QPW - 1) / QPW);
+  if (groups <= 0) return NUWA_OK;
+  const int grid = (groups + warps - 1) / warps;
+#define NUWA_LAUNCH_ATTN(CPL)                                                                                  \
+  do {                                                                                                         \
+    if (smem > 48 * 1024)                                                                                      \
+      cudaFuncSetAttribute(attn_kernel<MODE, CPL, QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    attn_kernel<MODE, CPL, QPW><<<grid, warps * 32, smem, stream>>>(p);                                        \
+  } while (0)
+  switch (cpl) {
+    case 16: NUWA_LAUNCH_ATTN(16); break;
+    case 8: NUWA_LAUNCH_ATTN(8); break;
+    case 4: NUWA_LAUNCH_ATTN(4); break;
+    case 2: NUWA_LAUNCH_ATTN(2); break;
+    case 1: NUWA_LAUNCH_ATTN(1); break;
+    default: return NUWA_ERR_INVALID;
+  }
+#undef NUWA_LAUNCH_ATTN
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+
+int attn_sparse3dna(const AttnParams& p, cudaStream_t s) { return launch_attn<MODE_3DNA, 1>(p, s); }
+int attn_dense(const AttnParams& p, cudaStream_t s) {
+  // several queries per warp amortise every K/V row load; single-query decode steps use QPW=1
+  if (p.nq >= 4) return launch_attn<MODE_DENSE, 4>(p, s);
+  return launch_attn<MODE_DENSE, 1>(p, s);
+}
+int attn_cross2dna(const AttnParams& p, cudaStream_t s) { return launch_attn<MODE_X2DNA, 1>(p, s); }
+
+}  // namespace nuwa

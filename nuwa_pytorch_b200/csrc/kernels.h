@@ -30,6 +30,10 @@ struct GemmParams {
   int8_t tap_dy[16];
 };
 
+typedef nuwa_attn_params AttnParams;
+typedef nuwa_ln_params LnParams;
+typedef nuwa_embed_params EmbedParams;
+
 int device_sm_count();
 
 // gemm_tcgen05.cu
@@ -39,5 +43,37 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
 int conv2d_nhwc_bf16(const void* x, const void* w, int B, int Hin, int Win, int Cin, int Cout, int ksize, int stride,
                      const float* bias, const float* residual, float* out_f32, void* out_bf16, int act, int force_bn,
                      cudaStream_t stream);
+
+
+// attention.cu
+int attn_sparse3dna(const AttnParams& p, cudaStream_t s);
+int attn_dense(const AttnParams& p, cudaStream_t s);
+int attn_cross2dna(const AttnParams& p, cudaStream_t s);
+// norm.cu
+int sandwich_ln(const LnParams& p, cudaStream_t stream);
+int stable_ln(const float* a, const float* b2, const float* w, const float* bias, float* out_f32, void* out_bf16,
+              int rows, int D, cudaStream_t stream);
+// token_ops.cu
+int embed_tokens(const EmbedParams& p, cudaStream_t stream);
+int rotary_to_bf16(const float* qkv, void* out, const float* inv_freq, int rows, int n, int H, int dh, int rot,
+                   cudaStream_t stream);
+int cross_entropy_mean(const float* logits, int ld, const long long* target, float* row_loss, float* out, int rows,
+                       int V, cudaStream_t stream);
+int sample_topk_gumbel(const float* cond, const float* uncond, const float* noise, long long* out, float* guided_out,
+                       int B, int V, int k, float cond_scale, float temperature, cudaStream_t stream);
+// vae_ops.cu
+int nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, cudaStream_t stream);
+int nhwc_to_nchw_f32(const void* in, int in_is_bf16, float* out, int B, int C, int H, int W, cudaStream_t stream);
+int im2col_nchw_f32(const float* img, void* out, int B, int C, int H, int W, int KS, int Kpad, cudaStream_t stream);
+int groupnorm_nhwc(const float* x, const float* w, const float* bias, float* stats_ws, void* out_bf16, float* out_f32,
+                   int B, int HW, int C, int G, int leaky, cudaStream_t stream);
+int upsample2x_nhwc_bf16(const void* in, void* out, int B, int H, int W, int C, cudaStream_t stream);
+int vae_attn_prep(const float* qkv, void* out, int B, int n, int inner, cudaStream_t stream);
+int vq_argmax(const float* x, const float* code, const float* code_sq, long long* out, int M, int Kc, int D, int cosine,
+              cudaStream_t stream);
+int gather_rows(const float* table, const long long* idx, void* out_bf16, float* out_f32, long long M, int D,
+                cudaStream_t stream);
+int conv1x1_nhwc_to_nchw(const void* x, const float* w, const float* bias, float* out, int B, int HW, int C, int Cout,
+                         cudaStream_t stream);
 
 }  // namespace nuwa

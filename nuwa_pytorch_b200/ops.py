@@ -105,3 +105,220 @@ def conv2d_nhwc(x, wp, Cin, ksize, stride=1, bias=None, residual=None, act=None,
                                        ptr(residual), ptr(out_f32), ptr(out_bf16), ACT[act], force_bn, stream())
     check(code, "nuwa_conv2d_nhwc_bf16")
     return (out, extra) if also_bf16 else out
+
+
+# ------------------------------------------------------------------------------------------------
+# norms
+# ------------------------------------------------------------------------------------------------
+def sandwich_ln(B, nt, D, *, y=None, post=None, res_in=None, x_out=None, x_out_bf16=None, pre=None, a_out=None,
+                a_bs=0, a_rs=0, a_t0=0, a_npos=0, shift=False, fmap=0, t0=0):
+    """See nuwa_sandwich_ln in include/nuwa_b200.h.  post / pre: (weight, bias) fp32 tensors or None."""
+    p = _lib.LnParams()
+    p.y, p.res_in, p.x_out, p.x_out_bf16 = ptr(y), ptr(res_in), ptr(x_out), ptr(x_out_bf16)
+    p.post_w, p.post_b = (ptr(post[0]), ptr(post[1])) if post is not None else (None, None)
+    p.pre_w, p.pre_b = (ptr(pre[0]), ptr(pre[1])) if pre is not None else (None, None)
+    p.a_out, p.a_bs, p.a_rs, p.a_t0, p.a_npos = ptr(a_out), a_bs, a_rs, a_t0, a_npos
+    p.shift, p.fmap, p.t0, p.B, p.nt, p.D, p.eps = int(bool(shift)), fmap, t0, B, nt, D, 1e-5
+    check(lib().nuwa_sandwich_ln(p, stream()), "nuwa_sandwich_ln")
+
+
+def stable_ln(a, w, b, b2=None, want_f32=True, want_bf16=False):
+    rows, D = a.numel() // a.shape[-1], a.shape[-1]
+    o32 = torch.empty_like(a) if want_f32 else None
+    o16 = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device) if want_bf16 else None
+    check(lib().nuwa_stable_ln(ptr(a), ptr(b2), ptr(w), ptr(b), ptr(o32), ptr(o16), rows, D, stream()),
+          "nuwa_stable_ln")
+    return o32, o16
+
+
+# ------------------------------------------------------------------------------------------------
+# attention cores
+# ------------------------------------------------------------------------------------------------
+def _attn_base(q, k, v, o, B, nq, t0, H, dh, q_bs, k_bs, v_bs, o_bs, q_rs, k_rs, v_rs, o_rs, talk):
+    p = _lib.AttnParams()
+    p.q, p.k, p.v, p.o = q, k, v, o
+    p.q_bs, p.k_bs, p.v_bs, p.o_bs = q_bs, k_bs, v_bs, o_bs
+    p.q_rs, p.k_rs, p.v_rs, p.o_rs = q_rs, k_rs, v_rs, o_rs
+    p.B, p.nq, p.t0, p.H, p.dh = B, nq, t0, H, dh
+    p.qscale = dh ** -0.5
+    p.talk = ptr(talk)
+    return p
+
+
+def attn_sparse3dna(qkv, o, *, B, nq, t0, npos, H, dh, talk, fmap, max_frames, nv, kernel, dilation, causal,
+                    o_bs=None):
+    """qkv: bf16 buffer (B, npos, 3*H*dh) holding q|k|v rows for positions [0, npos); queries are positions
+    [t0, t0+nq).  o: bf16 (B, nq, H*dh).  nv = number of video tokens present (positions 1..nv)."""
+    inner = H * dh
+    esz = 2
+    base = qkv.data_ptr()
+    p = _attn_base(base + t0 * 3 * inner * esz, base + inner * esz, base + 2 * inner * esz, ptr(o), B, nq, t0, H, dh,
+                   npos * 3 * inner, npos * 3 * inner, npos * 3 * inner, o_bs if o_bs is not None else nq * inner,
+                   3 * inner, 3 * inner, 3 * inner, inner, talk)
+    p.fmap, p.max_frames, p.nv = fmap, max_frames, nv
+    p.kt, p.kh, p.kw = kernel
+    p.dt, p.dh_, p.dw = dilation
+    p.causal = int(bool(causal))
+    p.jmax = 1 + kernel[0] * kernel[1] * kernel[2]
+    check(lib().nuwa_attn_sparse3dna(p, stream()), "nuwa_attn_sparse3dna")
+
+
+def attn_dense(q_ptr, k_ptr, v_ptr, o, *, B, nq, nk, H, dh, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, talk=None,
+               null_k=None, null_v=None, key_mask=None, head_scale=None, bias=None, qscale=None, t0=0):
+    p = _attn_base(q_ptr, k_ptr, v_ptr, ptr(o) if torch.is_tensor(o) else o, B, nq, t0, H, dh, q_bs, k_bs, v_bs, o_bs,
+                   q_rs, k_rs, v_rs, o_rs, talk)
+    if qscale is not None:
+        p.qscale = qscale
+    p.null_k, p.null_v = ptr(null_k), ptr(null_v)
+    if key_mask is not None:
+        assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous()
+        p.key_mask, p.mask_bs = ptr(key_mask), key_mask.shape[1]
+    p.head_scale = ptr(head_scale)
+    if bias is not None:
+        p.bias, p.bias_nq, p.bias_nk = ptr(bias), bias.shape[1], bias.shape[2]
+    p.jmax = nk + (1 if null_k is not None else 0)
+    check(lib().nuwa_attn_dense(p, stream()), "nuwa_attn_dense")
+
+
+def attn_cross2dna(q_ptr, k_ptr, v_ptr, o_ptr, *, B, nq, t0, H, dh, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs,
+                   talk, null_k, null_v, key_mask, fmap, frames, ck, cdil):
+    p = _attn_base(q_ptr, k_ptr, v_ptr, o_ptr, B, nq, t0, H, dh, q_bs, k_bs, v_bs, o_bs, q_rs, k_rs, v_rs, o_rs, talk)
+    p.null_k, p.null_v = ptr(null_k), ptr(null_v)
+    if key_mask is not None:
+        assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous()
+        p.key_mask, p.mask_bs = ptr(key_mask), key_mask.shape[1]
+    p.fmap, p.ck, p.cdil = fmap, ck, cdil
+    p.jmax = 1 + frames * ck * ck
+    check(lib().nuwa_attn_cross2dna(p, stream()), "nuwa_attn_cross2dna")
+
+
+# ------------------------------------------------------------------------------------------------
+# token level
+# ------------------------------------------------------------------------------------------------
+def embed_tokens(idx, table, *, nt, t0=0, bos=None, axials=(None, None, None), dims=(1, 1, 1)):
+    """out[b, tl] for absolute position t0+tl (see nuwa_embed_tokens).  idx: int64 (B, n_idx) contiguous."""
+    B = idx.shape[0]
+    D = table.shape[1]
+    out = torch.empty(B, nt, D, dtype=torch.float32, device=table.device)
+    p = _lib.EmbedParams()
+    p.out, p.idx, p.idx_bs, p.table, p.bos = ptr(out), ptr(idx) if idx.numel() else None, idx.stride(0), ptr(table), ptr(bos)
+    p.ax1, p.ax2, p.ax3 = (ptr(a) for a in axials)
+    p.d2, p.d3 = dims[1], dims[2]
+    p.has_bos, p.t0, p.B, p.nt, p.D = int(bos is not None), t0, B, nt, D
+    check(lib().nuwa_embed_tokens(p, stream()), "nuwa_embed_tokens")
+    return out
+
+
+def rotary_to_bf16(qkv_f32, inv_freq, n, H, dh, rot):
+    out = torch.empty(qkv_f32.shape, dtype=torch.bfloat16, device=qkv_f32.device)
+    rows = qkv_f32.shape[0]
+    check(lib().nuwa_rotary_to_bf16(ptr(qkv_f32), ptr(out), ptr(inv_freq), rows, n, H, dh, rot, stream()),
+          "nuwa_rotary_to_bf16")
+    return out
+
+
+def cross_entropy_mean(logits, target):
+    rows, V = logits.shape
+    ws = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    out = torch.empty((), dtype=torch.float32, device=logits.device)
+    check(lib().nuwa_cross_entropy_mean(ptr(logits), logits.stride(0), ptr(target), ptr(ws), ptr(out), rows, V,
+                                        stream()), "nuwa_cross_entropy_mean")
+    return out
+
+
+def sample_topk_gumbel(cond, uncond, noise, k, cond_scale, temperature, want_guided=False):
+    B, V = cond.shape
+    out = torch.empty(B, dtype=torch.int64, device=cond.device)
+    guided = torch.empty_like(cond) if want_guided else None
+    check(lib().nuwa_sample_topk_gumbel(ptr(cond), ptr(uncond), ptr(noise), ptr(out), ptr(guided), B, V, k,
+                                        float(cond_scale), float(temperature), stream()), "nuwa_sample_topk_gumbel")
+    return (out, guided) if want_guided else out
+
+
+# ------------------------------------------------------------------------------------------------
+# VAE support
+# ------------------------------------------------------------------------------------------------
+def nchw_to_nhwc_bf16(x):
+    B, C, H, W = x.shape
+    out = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=x.device)
+    check(lib().nuwa_nchw_f32_to_nhwc_bf16(ptr(x.contiguous().float()), ptr(out), B, C, H, W, stream()),
+          "nuwa_nchw_f32_to_nhwc_bf16")
+    return out
+
+
+def nhwc_to_nchw_f32(x):
+    B, H, W, C = x.shape
+    out = torch.empty(B, C, H, W, dtype=torch.float32, device=x.device)
+    check(lib().nuwa_nhwc_to_nchw_f32(ptr(x), int(x.dtype == torch.bfloat16), ptr(out), B, C, H, W, stream()),
+          "nuwa_nhwc_to_nchw_f32")
+    return out
+
+
+def im2col(img, ks, kpad):
+    B, C, H, W = img.shape
+    out = torch.empty(B * H * W, kpad, dtype=torch.bfloat16, device=img.device)
+    check(lib().nuwa_im2col_nchw_f32(ptr(img), ptr(out), B, C, H, W, ks, kpad, stream()), "nuwa_im2col_nchw_f32")
+    return out
+
+
+def pack_im2col_weight(w):
+    """(Cout, C, KS, KS) -> bf16 (Cout, Kpad) with K index (kh*KS+kw)*C + c, Kpad = roundup(KS*KS*C, 64)."""
+    cout, c, ks, _ = w.shape
+    k = ks * ks * c
+    kp = _round_up(k, 64)
+    wt = w.permute(0, 2, 3, 1).reshape(cout, k)
+    if kp != k:
+        wt = torch.cat([wt, torch.zeros(cout, kp - k, dtype=w.dtype, device=w.device)], dim=1)
+    return wt.to(torch.bfloat16).contiguous()
+
+
+def groupnorm_nhwc(x, w, b, groups, leaky=False, want_bf16=True, want_f32=False):
+    B, H, W, C = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    stats = torch.empty(B * groups * 2, dtype=torch.float32, device=x.device)
+    o16 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    o32 = torch.empty_like(x) if want_f32 else None
+    check(lib().nuwa_groupnorm_nhwc(ptr(x), ptr(w), ptr(b), ptr(stats), ptr(o16), ptr(o32), B, H * W, C, groups,
+                                    int(leaky), stream()), "nuwa_groupnorm_nhwc")
+    return o16 if not want_f32 else (o16, o32)
+
+
+def upsample2x(x):
+    B, H, W, C = x.shape
+    out = torch.empty(B, 2 * H, 2 * W, C, dtype=torch.bfloat16, device=x.device)
+    check(lib().nuwa_upsample2x_nhwc_bf16(ptr(x), ptr(out), B, H, W, C, stream()), "nuwa_upsample2x_nhwc_bf16")
+    return out
+
+
+def vae_attn_prep(qkv_f32, B, n, inner):
+    out = torch.empty(qkv_f32.shape, dtype=torch.bfloat16, device=qkv_f32.device)
+    check(lib().nuwa_vae_attn_prep(ptr(qkv_f32), ptr(out), B, n, inner, stream()), "nuwa_vae_attn_prep")
+    return out
+
+
+def vq_argmax(x, code, code_sq=None, cosine=True):
+    M, D = x.shape
+    out = torch.empty(M, dtype=torch.int64, device=x.device)
+    check(lib().nuwa_vq_argmax(ptr(x), ptr(code), ptr(code_sq), ptr(out), M, code.shape[0], D, int(cosine), stream()),
+          "nuwa_vq_argmax")
+    return out
+
+
+def gather_rows(table, idx, want_bf16=True, want_f32=False):
+    M, D = idx.numel(), table.shape[1]
+    o16 = torch.empty(M, D, dtype=torch.bfloat16, device=table.device) if want_bf16 else None
+    o32 = torch.empty(M, D, dtype=torch.float32, device=table.device) if want_f32 else None
+    check(lib().nuwa_gather_rows(ptr(table), ptr(idx.contiguous()), ptr(o16), ptr(o32), M, D, stream()),
+          "nuwa_gather_rows")
+    if want_bf16 and want_f32:
+        return o16, o32
+    return o16 if want_bf16 else o32
+
+
+def conv1x1_to_nchw(x, w, b):
+    B, H, W, C = x.shape
+    cout = w.shape[0]
+    out = torch.empty(B, cout, H, W, dtype=torch.float32, device=x.device)
+    check(lib().nuwa_conv1x1_nhwc_to_nchw(ptr(x), ptr(w), ptr(b), ptr(out), B, H * W, C, cout, stream()),
+          "nuwa_conv1x1_nhwc_to_nchw")
+    return out
