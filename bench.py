@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native NUWA hot paths.
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run, one rank/GPU)
+  python bench.py --impl reference ...                    (the reference algorithm's CPU path, oracle port)
+
+Metric (BASELINE.json): "3DNA decoder video-tokens/sec + VQGanVAE frames/sec @256^2".  The JSON line's
+`value` is VQGanVAE frames/sec on BASELINE configs[1] (dim=512, 256^2, L=4, 2 res blocks, codebook 8192,
+batch 64 per GPU: encode + VQ + decode of every frame); the 3DNA-decoder video-tokens/sec of configs[2]
+(NUWA dim 512, depth 12, 10 frames, kernel (5,3,3), dilation (1,2,4), forward loss, batch 8) rides along under
+`"decoder"`.  One "step" = one pass of the hot path over one synthetic batch.  Weights are random-init of the
+named architecture, inputs synthetic (there is no network for datasets / checkpoints).
+
+Multi-GPU: the path shards by batch with no data-path collective (inference replicas); every rank
+processes its own batch (weak scaling); timing = max over ranks between barriers.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VAE_KW = dict(dim=512, image_size=256, num_layers=4, num_resnet_blocks=2, vq_codebook_size=8192,
+              use_vgg_and_gan=False, vq_kmeans_init=False)
+VAE_BATCH = 64
+VAE_GFLOP_PER_FRAME = 2095.0  # encode 679.5 + VQ 2.15 + decode 1413.4 (2*MAC)
+DEC_VAE_KW = dict(dim=64, image_size=256, num_layers=4, vq_codebook_size=8192, vq_codebook_dim=512,
+                  use_vgg_and_gan=False, vq_kmeans_init=False)
+DEC_KW = dict(dim=512, dec_depth=12, dec_heads=8, max_video_frames=10, sparse_3dna_kernel_size=(5, 3, 3),
+              sparse_3dna_dilation=(1, 2, 4), enc_reversible=True)
+DEC_BATCH = 8
+METRIC = "VQGanVAE frames/sec @256^2 (3DNA decoder video-tokens/sec under 'decoder')"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d["bf16_tflops_sustained"],
+                    hbm_gbs=d["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.samples[0][1]), reasons=reasons,
+                    power_w_max=max(float(s[2]) for s in self.samples), samples=len(self.samples))
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_vae_frames_per_s(sd, frames, reps=1):
+    """CPU fp32 reference-algorithm VAE recon (oracle port) on `frames` frames of the cfg-2 architecture."""
+    from oracle import nuwa_oracle as O
+    spec = O.VAESpec(512, 256, num_layers=4, num_resnet_blocks=2, codebook_size=8192)
+    img = torch.randn(frames, 3, 256, 256, generator=torch.Generator().manual_seed(0))
+    best = None
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.vae_forward(img, sd, spec)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return frames / best, best
+
+
+def cpu_state_dict_vae(seed=0):
+    """Random-init weights of the cfg-2 VAE, generated on the CPU shape-by-shape (oracle/synth.py policy)."""
+    from nuwa_pytorch_b200.vqgan_vae import VQGanVAE
+    from oracle.synth import manifest_of, synth_state_dict
+    with torch.device("meta"):
+        vae = VQGanVAE(**VAE_KW)
+    man = [(k, tuple(v.shape)) for k, v in vae.state_dict().items() if v.dtype == torch.float32]
+    return synth_state_dict(man, seed)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = cpu_state_dict_vae()
+    frames = 1
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_vae_frames_per_s(sd, frames)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_vae_frames_per_s(sd, frames)
+    dt = time.perf_counter() - t0
+    fps = args.steps * frames / dt
+    line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload="VQGanVAE dim=512 image_size=256 num_layers=4 num_resnet_blocks=2 "
+                            "vq_codebook_size=8192 encode+VQ+decode (BASELINE configs[1])", batch_per_step=frames,
+                            note="reference algorithm (oracle port, PyTorch CPU fp32); the reference itself cannot be "
+                                 "imported on the GPU box (two absent third-party deps, no /root/reference)"),
+                cpu_baseline=dict(value=fps, unit="frames/s", cores=cores, kind="port",
+                                  sample=f"{frames} frame(s) of the 64-frame batch per step"),
+                e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def build_vae(dev):
+    from nuwa_pytorch_b200 import VQGanVAE
+    torch.manual_seed(0)
+    with torch.device(dev):
+        vae = VQGanVAE(**VAE_KW)
+    return vae.eval()
+
+
+def build_decoder(dev):
+    from nuwa_pytorch_b200 import NUWA, VQGanVAE
+    torch.manual_seed(0)
+    with torch.device(dev):
+        vae = VQGanVAE(**DEC_VAE_KW)
+        nuwa = NUWA(vae=vae, **DEC_KW)
+    return nuwa.eval()
+
+
+def timed(fn, steps, warmup, dist, flush):
+    """W warm-up + K timed steps between barrier+sync; CUDA events; returns max-over-ranks seconds."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        if flush is not None:
+            flush.zero_()
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sec = a.elapsed_time(b) / 1e3
+    if dist is not None:
+        t = torch.tensor([sec], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    return sec
+
+
+def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: nuwa_pytorch_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+    from nuwa_pytorch_b200 import _lib
+    pk = peaks()
+
+    # -------- VQGanVAE frames/s (configs[1]) --------
+    vae = build_vae(dev)
+    B = args.vae_batch
+    g = torch.Generator(device=dev).manual_seed(rank)
+    img = torch.randn(B, 3, 256, 256, device=dev, generator=g)
+    host_in = torch.randn(B, 3, 256, 256).pin_memory()
+    host_out = torch.empty(B, 3, 256, 256).pin_memory()
+    dev_in = torch.empty_like(img)
+
+    def step_dev():
+        return vae(img)
+
+    def step_e2e():
+        dev_in.copy_(host_in, non_blocking=True)
+        out = vae(dev_in)
+        host_out.copy_(out, non_blocking=True)
+
+    with torch.no_grad():
+        step_dev()  # builds the packed bf16 weights (one-off) outside any timed region
+        torch.cuda.synchronize()
+        launches0 = _lib.launch_count()
+        _lib.gemm_prof_enable(True)
+        with ClockSampler(local) as clocks:
+            sec = timed(step_dev, args.steps, args.warmup, dist, None)
+        n_gemm, gemm_flops, gemm_ms = _lib.gemm_prof_collect()
+        _lib.gemm_prof_enable(False)
+        launches = _lib.launch_count() - launches0
+        sec_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), dist, None)
+    fps = world * B * args.steps / sec
+    fps_e2e = world * B * args.steps / sec_e2e
+    # roofline of the dominant kernel (tcgen05 implicit-GEMM conv / GEMM): algorithmic FLOPs / summed launch time.
+    # gemm_prof counts warm-up + timed launches alike (same shapes), so the ratio is a per-launch average.
+    ach = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    peak = pk["bf16_tflops_sustained"]
+    roof = dict(bound="tensor", kernel="gemm_tcgen05_kernel (implicit-GEMM conv + GEMM)", achieved=round(ach, 1),
+                peak=peak, unit="TFLOP/s", frac=round(ach / peak, 4), traffic=None,
+                peak_source=pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                launches_per_step=n_gemm // (args.steps + args.warmup),
+                share_of_step=round((gemm_ms / (args.steps + args.warmup)) / (1e3 * sec / args.steps), 4),
+                step_level=dict(gflop_per_frame=VAE_GFLOP_PER_FRAME,
+                                achieved_tflops=round(fps / world * VAE_GFLOP_PER_FRAME / 1e3, 1),
+                                frac=round(fps / world * VAE_GFLOP_PER_FRAME / 1e3 / peak, 4)))
+    del vae, img, dev_in
+    torch.cuda.empty_cache()
+
+    # -------- 3DNA decoder video-tokens/s (configs[2], forward loss) --------
+    decoder = None
+    if not args.skip_decoder:
+        nuwa = build_decoder(dev)
+        gt = torch.Generator(device=dev).manual_seed(100 + rank)
+        text = torch.randint(1, 49408, (DEC_BATCH, 256), device=dev, generator=gt)
+        video = torch.randint(0, 8192, (DEC_BATCH, 10, 16, 16), device=dev, generator=gt)
+        h_text, h_video = text.cpu().pin_memory(), video.cpu().pin_memory()
+
+        def dstep():
+            return nuwa(text=text, video=video, return_loss=True)
+
+        def dstep_e2e():
+            t = h_text.to(dev, non_blocking=True)
+            v = h_video.to(dev, non_blocking=True)
+            return float(nuwa(text=t, video=v, return_loss=True).item())
+
+        with torch.no_grad():
+            dstep()
+            torch.cuda.synchronize()
+            l0 = _lib.launch_count()
+            dsec = timed(dstep, args.steps, args.warmup, dist, None)
+            dl = _lib.launch_count() - l0
+            dsec_e2e = timed(dstep_e2e, args.steps, 1, dist, None)
+        ntok = DEC_BATCH * 2560
+        decoder = dict(metric="3DNA decoder video-tokens/sec", value=round(world * ntok * args.steps / dsec, 1),
+                       unit="tokens/s", ms_per_step=round(1e3 * dsec / args.steps, 3),
+                       e2e=dict(value=round(world * ntok * args.steps / dsec_e2e, 1), unit="tokens/s",
+                                h2d_bytes_per_step=int(h_text.numel() * 8 + h_video.numel() * 8), d2h_bytes_per_step=4),
+                       gpu_launches=int(dl),
+                       config=dict(workload="NUWA dim=512 dec_depth=12 heads=8 max_video_frames=10 kernel (5,3,3) "
+                                   "dilation (1,2,4), forward loss incl. 6-layer text encoder + logits + CE "
+                                   "(BASELINE configs[2])", batch_per_gpu=DEC_BATCH, tokens_per_sample=2560,
+                                   backward="not included (forward loss only; autograd kernels are next-round work)"),
+                       flops=dict(mflop_per_token_fwd=104.4,
+                                  achieved_tflops=round(world * ntok * args.steps / dsec * 104.4e6 / 1e12 / world, 1)))
+        del nuwa
+
+    # -------- CPU baseline (rank 0, N == 1 only): the reference algorithm's CPU path, bounded sample --------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd = cpu_state_dict_vae()
+        v, dt = cpu_vae_frames_per_s(sd, 1)
+        cpu = dict(value=round(v, 4), unit="frames/s", cores=cores, kind="port",
+                   sample=f"1 frame of the 64-frame batch, one pass ({dt:.1f} s), PyTorch CPU fp32 oracle port of the reference")
+        del sd
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=round(fps, 2), unit="frames/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=round(1e3 * sec / args.steps, 3), higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    config=dict(workload="VQGanVAE dim=512 image_size=256 num_layers=4 num_resnet_blocks=2 "
+                                "vq_codebook_size=8192: encode + VQ + decode of every frame (BASELINE configs[1])",
+                                batch_per_gpu=B, parallelism=f"replicas x{world} (batch sharded, no collective)",
+                                l2="inputs larger than L2: 50 MB image batch, 4.4 GB bf16 weights, multi-GB activations"),
+                    e2e=dict(value=round(fps_e2e, 2), unit="frames/s", h2d_bytes_per_step=int(host_in.numel() * 4),
+                             d2h_bytes_per_step=int(host_out.numel() * 4)),
+                    gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, clocks=clocks.summary(),
+                    decoder=decoder)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--vae-batch", type=int, default=VAE_BATCH)
+    ap.add_argument("--skip-decoder", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,12 @@ unsigned long long nuwa_launch_count(void);
 /* sizeof(nuwa_ln_params), sizeof(nuwa_attn_params), sizeof(nuwa_embed_params) -- lets a binding verify its struct mirror */
 void nuwa_struct_sizes(int* out3);
 
+/* Measurement aid for bench.py's roofline: while enabled, every launch of the tcgen05 GEMM/conv kernel is
+ * bracketed by CUDA events on its launch stream.  nuwa_gemm_prof_collect (call after synchronising) returns the
+ * number of launches and their summed algorithmic FLOPs and device time, then resets the counters. */
+void nuwa_gemm_prof_enable(int on);
+int nuwa_gemm_prof_collect(double* flops, float* ms);
+
 /* ---- dense contraction (tcgen05) ------------------------------------------------------------
  * out[M,N] = act(A[M,K] @ W[N,K]^T + bias) + residual.   A, W bf16 with K contiguous.
  * Replaces nn.Linear at nuwa_pytorch.py:274,277 (FeedForward), :311-313 (Attention), :401-405

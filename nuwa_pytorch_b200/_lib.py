@@ -47,6 +47,8 @@ SIGNATURES = {
     "nuwa_launch_count": [],
     "nuwa_strerror": [c_int],
     "nuwa_struct_sizes": [P(c_int)],
+    "nuwa_gemm_prof_enable": [c_int],
+    "nuwa_gemm_prof_collect": [P(ctypes.c_double), P(c_float)],
     "nuwa_gemm_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                        c_void_p, c_int, c_int, c_int, c_void_p],
     "nuwa_conv2d_nhwc_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
@@ -72,7 +74,8 @@ SIGNATURES = {
     "nuwa_gather_rows": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "nuwa_conv1x1_nhwc_to_nchw": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
 }
-_RESTYPES = {"nuwa_strerror": ctypes.c_char_p, "nuwa_launch_count": ctypes.c_ulonglong, "nuwa_struct_sizes": None}
+_RESTYPES = {"nuwa_strerror": ctypes.c_char_p, "nuwa_launch_count": ctypes.c_ulonglong, "nuwa_struct_sizes": None,
+             "nuwa_gemm_prof_enable": None}
 
 _lib = None
 
@@ -124,3 +127,14 @@ def stream():
 
 def launch_count():
     return int(lib().nuwa_launch_count())
+
+
+def gemm_prof_enable(on):
+    lib().nuwa_gemm_prof_enable(int(bool(on)))
+
+
+def gemm_prof_collect():
+    """(launches, algorithmic FLOPs, device ms) of the tcgen05 GEMM/conv launches since enable; call after a sync."""
+    fl, ms = ctypes.c_double(0), c_float(0)
+    n = lib().nuwa_gemm_prof_collect(ctypes.byref(fl), ctypes.byref(ms))
+    return n, fl.value, ms.value

@@ -93,6 +93,9 @@ int nuwa_conv1x1_nhwc_to_nchw(const void* x, const float* w, const float* bias, 
 
 }  // extern "C"
 
+extern "C" void nuwa_gemm_prof_enable(int on) { gemm_prof_enable(on); }
+extern "C" int nuwa_gemm_prof_collect(double* flops, float* ms) { return gemm_prof_collect(flops, ms); }
+
 // sizes of the parameter structs, so a foreign-language binding can verify its mirror of the layout
 extern "C" void nuwa_struct_sizes(int* out3) {
   out3[0] = (int)sizeof(nuwa_ln_params);

@@ -17,6 +17,8 @@
 //
 // Reference ops this kernel replaces (all ATen library calls in the reference):
 //   nn.Linear  nuwa_pytorch.py:274,277,311-313,401-405,1819   nn.Conv2d  vqgan_vae.py:216-238,262-263,352-366
+#include <vector>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -374,6 +376,41 @@ static int pick_bn(int num_m_tiles, int N, int force_bn) {
   return 64;
 }
 
+// ---- optional per-launch timing of this kernel (bench.py roofline): CUDA events on the launch stream ----
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_prof_ev;  // start/stop pairs
+static size_t g_prof_used = 0;
+static double g_prof_flops = 0.0;
+static double g_cur_flops = 0.0;
+
+void gemm_prof_enable(int on) {
+  g_prof_on = on != 0;
+  g_prof_used = 0;
+  g_prof_flops = 0.0;
+}
+// Caller must have synchronised the stream(s).  Returns the number of timed launches.
+int gemm_prof_collect(double* flops, float* ms) {
+  float total = 0.f;
+  for (size_t i = 0; i + 1 < g_prof_used; i += 2) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof_ev[i], g_prof_ev[i + 1]) == cudaSuccess) total += t;
+  }
+  int n = (int)(g_prof_used / 2);
+  if (flops) *flops = g_prof_flops;
+  if (ms) *ms = total;
+  g_prof_used = 0;
+  g_prof_flops = 0.0;
+  return n;
+}
+static cudaEvent_t prof_event() {
+  if (g_prof_used == g_prof_ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_prof_ev.push_back(e);
+  }
+  return g_prof_ev[g_prof_used++];
+}
+
 template <int BN>
 static int launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -388,7 +425,12 @@ static int launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, GemmParams&
   int total = p.num_m_tiles * p.num_n_tiles;
   int grid = total < device_sm_count() ? total : device_sm_count();
   if (grid <= 0) return NUWA_OK;
+  if (g_prof_on) cudaEventRecord(prof_event(), stream);
   gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mA[0], mA[1], mA[2], mA[3], mB, p);
+  if (g_prof_on) {
+    cudaEventRecord(prof_event(), stream);
+    g_prof_flops += g_cur_flops;
+  }
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
 }
@@ -439,6 +481,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   int e = encode_map(&mA[0], A, 2, dimsA, strA, boxA);
   if (e) return e;
   mA[1] = mA[0]; mA[2] = mA[0]; mA[3] = mA[0];
+  g_cur_flops = 2.0 * (double)M * (double)N * (double)K;
   return dispatch_gemm(mA, W, p, force_bn, stream);
 }
 
@@ -519,6 +562,7 @@ int conv2d_nhwc_bf16(const void* x, const void* w, int B, int Hin, int Win, int 
         p.tap_dx[t] = (int8_t)((kw - 1 - px) / 2);
       }
   }
+  g_cur_flops = 2.0 * (double)p.M * (double)Cout * (double)(ntaps * Cin);  // algorithmic (un-padded) MACs x 2
   return dispatch_gemm(mA, w, p, force_bn, stream);
 }
 

@@ -45,6 +45,9 @@ int conv2d_nhwc_bf16(const void* x, const void* w, int B, int Hin, int Win, int 
                      cudaStream_t stream);
 
 
+void gemm_prof_enable(int on);
+int gemm_prof_collect(double* flops, float* ms);
+
 // attention.cu
 int attn_sparse3dna(const AttnParams& p, cudaStream_t s);
 int attn_dense(const AttnParams& p, cudaStream_t s);

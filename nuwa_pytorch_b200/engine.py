@@ -1,0 +1,256 @@
+"""Stack executor: walks a Transformer / ReversibleTransformer parameter container and runs it as a
+sequence of C-ABI kernel launches (no torch arithmetic).
+
+Data layout (B200-first):
+  * residual streams are fp32 [B*n, D] in HBM; every GEMM operand is bf16,
+  * one fused row kernel does  post-LayerNorm + residual add  of sub-block i  AND  pre-LayerNorm +
+    ShiftVideoTokens scatter + bf16 cast of sub-block i+1  (sandwich_ln),
+  * q|k|v live in ONE bf16 buffer [B, npos, 3*inner] written by a single fused projection GEMM; in decode
+    mode that buffer is the KV cache and the shift-scatter operand buffers are persistent, so a generate()
+    step touches only the new token's rows.
+Two execution modes: full (all n positions, teacher forced) and decode (one position, with DecodeState).
+"""
+import torch
+
+from . import ops
+
+
+def _f32(t):
+    return t.detach().float().contiguous()
+
+
+def _bf16(t):
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+class SubBlock:
+    """Packed weights + static geometry of one SandwichNorm-wrapped sub-block."""
+
+    def __init__(self, kind, sandwich, inner_mod, shift, read, write, **geom):
+        self.kind, self.shift, self.read, self.write = kind, shift, read, write
+        self.pre = (_f32(sandwich.prenorm.weight), _f32(sandwich.prenorm.bias))
+        self.post = (_f32(sandwich.postnorm.weight), _f32(sandwich.postnorm.bias))
+        self.__dict__.update(geom)
+        m = inner_mod
+        if kind in ('3dna', 'self'):
+            self.H = m.heads
+            self.inner = m.to_q.weight.shape[0]
+            self.dh = self.inner // self.H
+            self.w_qkv = _bf16(torch.cat([m.to_q.weight, m.to_kv.weight], dim=0))
+            self.w_out = _bf16(m.to_out.weight)
+            self.b_out = _f32(m.to_out.bias) if m.to_out.bias is not None else None
+            self.talk = _f32(m.talking_heads.weight.reshape(self.H, self.H))
+        if kind in ('cross', 'x2dna'):
+            self.H = m.heads
+            self.inner = m.to_q.weight.shape[0]
+            self.dh = self.inner // self.H
+            self.w_q, self.w_kv, self.w_out = _bf16(m.to_q.weight), _bf16(m.to_kv.weight), _bf16(m.to_out.weight)
+            self.talk = _f32(m.talking_heads.weight.reshape(self.H, self.H))
+        if kind in ('self', 'cross', 'x2dna'):
+            self.null_k, self.null_v = _f32(m.null_k.reshape(-1)), _f32(m.null_v.reshape(-1))
+        if kind == 'ff':
+            w1, w2 = m.net[0].weight, m.net[3].weight
+            self.ff_inner = w2.shape[1]
+            self.w1 = _bf16(ops.pack_pairs(w1.detach().float()))            # (2*ip, D) pair packed
+            ip = self.w1.shape[0] // 2
+            w2p = torch.zeros(w2.shape[0], ip, dtype=torch.float32, device=w2.device)
+            w2p[:, :self.ff_inner] = w2.detach().float()
+            self.w2 = _bf16(w2p)                                             # (D, ip), zero padded K
+
+
+class StackPack:
+    """Everything run_stack needs, built once per weight version (see pack_stack)."""
+
+    def __init__(self, subs, norm_w, norm_b, reversible, dim):
+        self.subs, self.norm_w, self.norm_b, self.reversible, self.dim = subs, norm_w, norm_b, reversible, dim
+
+
+def _signature(module):
+    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
+def pack_stack(stack):
+    """Build (or fetch the cached) StackPack of a Transformer / ReversibleTransformer container."""
+    sig = _signature(stack)
+    cached = getattr(stack, '_nuwa_pack', None)
+    if cached is not None and cached[0] == sig:
+        return cached[1]
+    dev = next(stack.parameters()).device
+    if dev.type != 'cuda':
+        raise ops._lib.NuwaB200Error('transformer stacks must live on a CUDA device (no CPU path)')
+    from .nuwa import Attention, FeedForward, ShiftVideoTokens, Sparse3DNA, SparseCross2DNA
+    subs = []
+
+    def add(sandwich, read, write):
+        fn = sandwich.fn
+        shift = False
+        if isinstance(fn, ShiftVideoTokens):
+            shift = fn.shift_space
+            assert not fn.shift_time, 'shift_time is never enabled by NUWA / NUWASketch'
+            fmap = fn.image_size
+            fn = fn.fn
+        else:
+            fmap = None
+        if isinstance(fn, Sparse3DNA):
+            assert fn.rel_pos_bias is None, 'sparse_3dna_rel_pos_bias is broken in the reference for batch > 1 (SURVEY D11)'
+            subs.append(SubBlock('3dna', sandwich, fn, shift, read, write, fmap=fn.video_shape[1],
+                                 max_frames=fn.video_shape[0], kernel=fn.kernel_size, dilation=fn.dilation,
+                                 causal=fn.causal))
+        elif isinstance(fn, SparseCross2DNA):
+            subs.append(SubBlock('x2dna', sandwich, fn, shift, read, write, fmap=fn.image_size, ck=fn.kernel_size,
+                                 cdil=fn.dilation))
+        elif isinstance(fn, Attention):
+            subs.append(SubBlock('self' if not getattr(sandwich, '_is_cross', False) else 'cross', sandwich, fn, shift,
+                                 read, write, fmap=fmap, causal=fn.causal))
+        elif isinstance(fn, FeedForward):
+            subs.append(SubBlock('ff', sandwich, fn, shift, read, write, fmap=fmap))
+        else:
+            raise TypeError(f'unsupported sub-block {type(fn)}')
+
+    reversible = hasattr(stack, 'net')
+    if not reversible:
+        for attn, cross, ff in stack.layers:
+            add(attn, 0, 0)
+            if cross is not None:
+                add(cross, 0, 0)
+            add(ff, 0, 0)
+    else:
+        for f, g in stack.layers:  # y1 = x1 + f(x2) ; y2 = x2 + g(y1)   (reversible.py:61-68)
+            add(f, 1, 0)
+            add(g, 0, 1)
+    ln = stack.norm.norm
+    pack = StackPack(subs, _f32(ln.weight), _f32(ln.bias), reversible, ln.weight.shape[0])
+    stack._nuwa_pack = (sig, pack)
+    return pack
+
+
+class DecodeState:
+    """Persistent per-stack buffers for incremental decoding of `npos` positions (bos + video tokens)."""
+
+    def __init__(self, pack, B, npos, device):
+        self.B, self.npos = B, npos
+        self.a, self.qkv, self.ctx_kv = {}, {}, {}
+        for i, s in enumerate(pack.subs):
+            if s.shift:
+                self.a[i] = torch.zeros(B, npos, pack.dim, dtype=torch.bfloat16, device=device)
+            if s.kind == '3dna':
+                self.qkv[i] = torch.zeros(B, npos, 3 * s.inner, dtype=torch.bfloat16, device=device)
+
+
+class Context:
+    """Cross-attention context: bf16 copy of the context tokens + uint8 key mask; per-layer K/V are cached."""
+
+    def __init__(self, ctx16, mask_u8):
+        self.ctx16, self.mask = ctx16, mask_u8  # (B, nk, D) bf16 ; (B, nk) uint8 or None
+        self.kv = {}
+
+    def with_mask(self, mask_u8):
+        c = Context(self.ctx16, mask_u8)
+        c.kv = self.kv  # K/V do not depend on the mask
+        return c
+
+
+def _run_sub(i, s, a, B, nt, t0, npos, D, state, context, key_mask, rotary):
+    """a: bf16 operand rows as a 2-D (B*nt, D) view (row stride may exceed D in decode mode).  Returns y fp32 (B*nt, D)."""
+    dev = a.device
+    M = B * nt
+    if s.kind == 'ff':
+        h = ops.gemm(a, s.w1, act='geglu', out_dtype=torch.bfloat16)
+        return ops.gemm(h, s.w2, out_dtype=torch.float32)
+    inner, H, dh = s.inner, s.H, s.dh
+    o = torch.empty(M, inner, dtype=torch.bfloat16, device=dev)
+    if s.kind == '3dna':
+        if state is None:
+            qkv = ops.gemm(a, s.w_qkv, out_dtype=torch.bfloat16)  # (B*n, 3*inner)
+            ops.attn_sparse3dna(qkv, o, B=B, nq=nt, t0=0, npos=nt, H=H, dh=dh, talk=s.talk, fmap=s.fmap,
+                                max_frames=s.max_frames, nv=nt - 1, kernel=s.kernel, dilation=s.dilation, causal=s.causal)
+        else:
+            cache = state.qkv[i]
+            ops.gemm(a, s.w_qkv, out=cache[:, t0, :])  # new token's q|k|v rows land in the cache
+            ops.attn_sparse3dna(cache, o, B=B, nq=1, t0=t0, npos=npos, H=H, dh=dh, talk=s.talk, fmap=s.fmap,
+                                max_frames=s.max_frames, nv=t0, kernel=s.kernel, dilation=s.dilation, causal=s.causal,
+                                o_bs=inner)
+        return ops.gemm(o, s.w_out, bias=s.b_out, out_dtype=torch.float32)
+    if s.kind == 'self':
+        assert state is None, 'dense self-attention stacks (text encoder) run in full mode only'
+        assert not s.causal, 'dense causal self-attention is not used by NUWA / NUWASketch'
+        if rotary is not None:
+            inv_freq, rot = rotary
+            qkv32 = ops.gemm(a, s.w_qkv, out_dtype=torch.float32)
+            qkv = ops.rotary_to_bf16(qkv32, inv_freq, nt, H, dh, rot)
+        else:
+            qkv = ops.gemm(a, s.w_qkv, out_dtype=torch.bfloat16)
+        base = qkv.data_ptr()
+        ops.attn_dense(base, base + inner * 2, base + 2 * inner * 2, o, B=B, nq=nt, nk=nt, H=H, dh=dh,
+                       q_bs=nt * 3 * inner, q_rs=3 * inner, k_bs=nt * 3 * inner, k_rs=3 * inner, v_bs=nt * 3 * inner,
+                       v_rs=3 * inner, o_bs=nt * inner, o_rs=inner, talk=s.talk, null_k=s.null_k, null_v=s.null_v,
+                       key_mask=key_mask)
+        return ops.gemm(o, s.w_out, out_dtype=torch.float32)
+    # ---- cross attention (dense text context or sparse 2-D nearby sketch context) ----
+    nk = context.ctx16.shape[1]
+    kv = context.kv.get(i)
+    if kv is None:
+        kv = ops.gemm(context.ctx16.view(B * nk, -1), s.w_kv, out_dtype=torch.bfloat16)  # (B*nk, 2*inner), once per call
+        context.kv[i] = kv
+    q = ops.gemm(a, s.w_q, out_dtype=torch.bfloat16)  # (B*nt, inner)
+    kb = kv.data_ptr()
+    common = dict(B=B, H=H, dh=dh, q_bs=nt * inner, q_rs=inner, k_bs=nk * 2 * inner, k_rs=2 * inner,
+                  v_bs=nk * 2 * inner, v_rs=2 * inner, o_bs=nt * inner, o_rs=inner, null_k=s.null_k, null_v=s.null_v,
+                  key_mask=context.mask)
+    if s.kind == 'cross':
+        ops.attn_dense(q.data_ptr(), kb, kb + inner * 2, o, nq=nt, nk=nk, talk=s.talk, **common)
+    else:
+        first = 0
+        if t0 == 0:  # bos query: dense over [null] + every context token, no talking heads (nuwa_pytorch.py:828-844)
+            ops.attn_dense(q.data_ptr(), kb, kb + inner * 2, o, nq=1, nk=nk, talk=None, **common)
+            first = 1
+        if nt - first > 0:
+            ops.attn_cross2dna(q.data_ptr() + first * inner * 2, kb, kb + inner * 2, o.data_ptr() + first * inner * 2,
+                               nq=nt - first, t0=t0 + first, talk=s.talk, fmap=s.fmap, frames=nk // (s.fmap * s.fmap),
+                               ck=s.ck, cdil=s.cdil, **common)
+    return ops.gemm(o, s.w_out, out_dtype=torch.float32)
+
+
+def run_stack(stack, x, *, context=None, key_mask=None, rotary=None, state=None, t0=0, want_bf16=False):
+    """Run a whole stack.  x: fp32 (B, nt, D) contiguous (nt = all positions, or 1 with a DecodeState).
+    context: Context or None; key_mask: uint8 (B, n) for dense self-attention; rotary: (inv_freq, rot_dim).
+    Returns the StableLayerNorm output fp32 (B, nt, D) [and its bf16 copy]."""
+    pack = pack_stack(stack)
+    B, nt, D = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    npos = state.npos if state is not None else nt
+    assert state is None or nt == 1
+    if pack.reversible:
+        streams = [x.view(B * nt, D).clone(), x.view(B * nt, D).clone()]  # X = [x, x]  (reversible.py:133)
+    else:
+        streams = [x.view(B * nt, D).clone()]
+    subs = pack.subs
+
+    def operand_buffer(i):
+        """bf16 operand buffer of sub-block i and its addressing for sandwich_ln stage B."""
+        s = subs[i]
+        if state is not None and s.shift:
+            buf = state.a[i]
+            return buf, dict(a_out=buf, a_bs=npos * D, a_rs=D, a_t0=0, a_npos=npos), buf[:, t0, :]
+        buf = torch.empty(B, nt, D, dtype=torch.bfloat16, device=x.device)
+        return buf, dict(a_out=buf, a_bs=nt * D, a_rs=D, a_t0=t0, a_npos=t0 + nt), buf.view(B * nt, D)
+
+    # first sub-block: pre-norm only
+    _, addr, a_view = operand_buffer(0)
+    ops.sandwich_ln(B, nt, D, res_in=streams[subs[0].read], pre=subs[0].pre, shift=subs[0].shift,
+                    fmap=subs[0].fmap or 0, t0=t0, **addr)
+    for i, s in enumerate(subs):
+        y = _run_sub(i, s, a_view, B, nt, t0, npos, D, state, context, key_mask, rotary)
+        tgt = streams[s.write]
+        if i + 1 < len(subs):
+            nxt = subs[i + 1]
+            assert nxt.read == s.write
+            _, addr, a_view = operand_buffer(i + 1)
+            ops.sandwich_ln(B, nt, D, y=y, post=s.post, res_in=tgt, x_out=tgt, pre=nxt.pre, shift=nxt.shift,
+                            fmap=nxt.fmap or 0, t0=t0, **addr)
+        else:
+            ops.sandwich_ln(B, nt, D, y=y, post=s.post, res_in=tgt, x_out=tgt, t0=t0)
+    b2 = streams[1] if pack.reversible else None
+    o32, o16 = ops.stable_ln(streams[0], pack.norm_w, pack.norm_b, b2=b2, want_f32=True, want_bf16=want_bf16)
+    o32 = o32.view(B, nt, D)
+    return (o32, o16.view(B, nt, D)) if want_bf16 else o32
