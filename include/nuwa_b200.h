@@ -122,12 +122,15 @@ typedef struct {
   /* SparseCross2DNA geometry (nuwa_pytorch.py:789-792) */
   int ck, cdil;
   int jmax;
+  int nk_dense; /* set by the library (dense tensor-core path); callers leave it 0 */
 } nuwa_attn_params;
 /* Sparse3DNA.forward core, nuwa_pytorch.py:490-608 (jmax = 1 + kt*kh*kw; k/v row 0 = bos, row 1+i = video token i) */
 int nuwa_attn_sparse3dna(const nuwa_attn_params* p, void* stream);
 /* Attention.forward core, nuwa_pytorch.py:339-378, and VQGanAttention core, vqgan_vae.py:275-282
  * (jmax = nk (+1 with a null key)) */
-int nuwa_attn_dense(const nuwa_attn_params* p, void* stream);
+int nuwa_attn_dense(const nuwa_attn_params* p, void* vt_workspace, void* stream);
+/* vt_workspace: NULL, or B*H*dh*roundup(nk,16) bf16 elements of scratch; when given and nk <= 256, dh in {32,64},
+ * H <= 8, nq >= 8 the tensor-core (mma.sync) variant runs, otherwise the generic CUDA-core kernel. */
 /* SparseCross2DNA.forward non-bos queries, nuwa_pytorch.py:851-895 (jmax = 1 + frames*ck*ck; t0 >= 1) */
 int nuwa_attn_cross2dna(const nuwa_attn_params* p, void* stream);
 

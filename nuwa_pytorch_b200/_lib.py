@@ -32,7 +32,7 @@ class AttnParams(ctypes.Structure):  # mirrors nuwa_attn_params
                 ("key_mask", c_void_p), ("mask_bs", c_int), ("bias", c_void_p), ("bias_nq", c_int), ("bias_nk", c_int),
                 ("fmap", c_int), ("max_frames", c_int), ("nv", c_int), ("kt", c_int), ("kh", c_int), ("kw", c_int),
                 ("dt", c_int), ("dh_", c_int), ("dw", c_int), ("causal", c_int), ("ck", c_int), ("cdil", c_int),
-                ("jmax", c_int)]
+                ("jmax", c_int), ("nk_dense", c_int)]
 
 
 class EmbedParams(ctypes.Structure):  # mirrors nuwa_embed_params
@@ -56,7 +56,7 @@ SIGNATURES = {
     "nuwa_sandwich_ln": [P(LnParams), c_void_p],
     "nuwa_stable_ln": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "nuwa_attn_sparse3dna": [P(AttnParams), c_void_p],
-    "nuwa_attn_dense": [P(AttnParams), c_void_p],
+    "nuwa_attn_dense": [P(AttnParams), c_void_p, c_void_p],
     "nuwa_attn_cross2dna": [P(AttnParams), c_void_p],
     "nuwa_embed_tokens": [P(EmbedParams), c_void_p],
     "nuwa_rotary_to_bf16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],

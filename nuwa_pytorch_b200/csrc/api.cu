@@ -44,7 +44,15 @@ int nuwa_stable_ln(const float* a, const float* b2, const float* w, const float*
   return stable_ln(a, b2, w, bias, out_f32, out_bf16, rows, D, S(stream));
 }
 int nuwa_attn_sparse3dna(const nuwa_attn_params* p, void* stream) { return p ? attn_sparse3dna(*p, S(stream)) : NUWA_ERR_INVALID; }
-int nuwa_attn_dense(const nuwa_attn_params* p, void* stream) { return p ? attn_dense(*p, S(stream)) : NUWA_ERR_INVALID; }
+int nuwa_attn_dense(const nuwa_attn_params* p, void* vt_workspace, void* stream) {
+  if (!p) return NUWA_ERR_INVALID;
+  if (vt_workspace != nullptr && p->nq >= 8) {
+    const int nk = p->jmax - (p->null_k != nullptr ? 1 : 0);
+    const int rc = attn_dense_mma(*p, nk, vt_workspace, S(stream));
+    if (rc != NUWA_ERR_INVALID) return rc;  // unsupported shape -> generic kernel below
+  }
+  return attn_dense(*p, S(stream));
+}
 int nuwa_attn_cross2dna(const nuwa_attn_params* p, void* stream) { return p ? attn_cross2dna(*p, S(stream)) : NUWA_ERR_INVALID; }
 int nuwa_embed_tokens(const nuwa_embed_params* p, void* stream) { return p ? embed_tokens(*p, S(stream)) : NUWA_ERR_INVALID; }
 int nuwa_rotary_to_bf16(const float* qkv, void* out, const float* inv_freq, int rows, int n, int H, int dh, int rot,

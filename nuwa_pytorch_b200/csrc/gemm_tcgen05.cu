@@ -28,6 +28,8 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-5 epilogue
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
+static constexpr int EPI_PITCH = 36;  // floats per staged row (32 + 4 pad: conflict-free float4 access)
+static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;  // one 32-row slab per epilogue warp
 
 template <int BN>
 struct GemmCfg {
@@ -35,7 +37,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator buffers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
 };
 
 struct TileCoord {
@@ -183,33 +185,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     __syncwarp();
   } else {
     // ================================ epilogue (4 warps) ================================
+    // TMEM -> registers (thread = accumulator row) -> bias/activation -> per-warp shared-memory transpose ->
+    // row-contiguous, fully coalesced global stores (8 lanes x 16 B = one 128 B line per output row segment).
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const int r = q * 32 + lane;
+    float* stg = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + q * (32 * EPI_PITCH);
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool pair = (p.act == ACT_GLU || p.act == ACT_GEGLU);
     const int n_out_total = pair ? p.N / 2 : p.N;
+    const int W = pair ? 16 : 32;            // output columns produced per 32-column accumulator chunk
+    const int lpr = W / 4;                   // lanes per output row in the store phase
+    const int rpi = 32 / lpr;                // rows per store iteration
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = tile_coord(tile, p.num_m_tiles, p.num_n_tiles);
       const int n0 = tc.nt * BN;
-      // output row of this thread
-      long long m;
-      bool row_ok;
+      int cx0 = 0, cy0 = 0, cb0 = 0;
       if (p.conv) {
-        int xt = tc.mt % p.tiles_x;
-        int yt = (tc.mt / p.tiles_x) % p.tiles_y;
-        int bt = tc.mt / (p.tiles_x * p.tiles_y);
-        int per_img = p.th * p.tw;
-        int bb = r / per_img;
-        int rem = r - bb * per_img;
-        int yy = rem / p.tw;
-        int xx = rem - yy * p.tw;
-        int b = bt * p.tb + bb, y = yt * p.th + yy, x = xt * p.tw + xx;
-        row_ok = (bb < p.tb) && (b < p.B) && (y < p.H) && (x < p.W);
-        m = ((long long)b * p.H + y) * p.W + x;
-      } else {
-        m = (long long)tc.mt * BM + r;
-        row_ok = m < p.M;
+        cx0 = (tc.mt % p.tiles_x) * p.tw;
+        cy0 = ((tc.mt / p.tiles_x) % p.tiles_y) * p.th;
+        cb0 = (tc.mt / (p.tiles_x * p.tiles_y)) * p.tb;
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -226,60 +220,67 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
         const int nc = n0 + c * 32;
-        if (!row_ok || nc >= p.N) continue;
+        if (nc >= p.N) continue;  // warp-uniform
+        // ---- phase 1: bias + activation on this thread's row, stage to shared memory ----
+        float* srow = stg + lane * EPI_PITCH;
         if (!pair) {
 #pragma unroll
           for (int j0 = 0; j0 < 32; j0 += 4) {
-            const int n = nc + j0;
-            if (n >= p.N) break;
             float o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float a = __uint_as_float(v[j0 + j]);
-              if (p.bias != nullptr && n + j < p.N) a += p.bias[n + j];
+              if (p.bias != nullptr && nc + j0 + j < p.N) a += __ldg(p.bias + nc + j0 + j);
               if (p.act == ACT_LEAKY) a = leaky01(a);
               o[j] = a;
             }
-            if (n + 3 < p.N) {
-              if (p.residual != nullptr) {
-                const float4 rr = *reinterpret_cast<const float4*>(p.residual + m * p.ld_res + n);
-                o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
-              }
-              if (p.out_f32 != nullptr)
-                *reinterpret_cast<float4*>(p.out_f32 + m * p.ld_out + n) = make_float4(o[0], o[1], o[2], o[3]);
-              if (p.out_bf16 != nullptr) {
-                uint2 pk;
-                pk.x = pack_bf16x2(o[0], o[1]);
-                pk.y = pack_bf16x2(o[2], o[3]);
-                *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_out + n) = pk;
-              }
-            } else {
-              for (int j = 0; j < 4 && n + j < p.N; ++j) {
-                float a = o[j];
-                if (p.residual != nullptr) a += p.residual[m * p.ld_res + n + j];
-                if (p.out_f32 != nullptr) p.out_f32[m * p.ld_out + n + j] = a;
-                if (p.out_bf16 != nullptr) p.out_bf16[m * p.ld_out + n + j] = __float2bfloat16(a);
-              }
-            }
+            *reinterpret_cast<float4*>(srow + j0) = make_float4(o[0], o[1], o[2], o[3]);
           }
         } else {
           // packed pair layout: within every 32 packed columns, [0,16) = value half, [16,32) = gate half
-          const int no = nc / 2;
 #pragma unroll
           for (int j0 = 0; j0 < 16; j0 += 4) {
-            const int n = no + j0;
-            if (n >= n_out_total) break;
             float o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float a = __uint_as_float(v[j0 + j]);
               float g = __uint_as_float(v[16 + j0 + j]);
               if (p.bias != nullptr) {
-                a += p.bias[nc + j0 + j];
-                g += p.bias[nc + 16 + j0 + j];
+                a += __ldg(p.bias + nc + j0 + j);
+                g += __ldg(p.bias + nc + 16 + j0 + j);
               }
               o[j] = (p.act == ACT_GLU) ? a * sigmoid_f(g) : a * gelu_erf(g);
             }
+            *reinterpret_cast<float4*>(srow + j0) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        __syncwarp();
+        // ---- phase 2: transposed read, residual add, coalesced stores ----
+        const int no = pair ? nc / 2 : nc;
+        const int c4 = (lane % lpr) * 4;
+        const int n = no + c4;
+        for (int it = 0; it < 32; it += rpi) {
+          const int rl = it + lane / lpr;  // row inside this warp's 32-row slab
+          const int r = q * 32 + rl;       // row inside the 128-row tile
+          long long m;
+          bool ok;
+          if (p.conv) {
+            const int per_img = p.th * p.tw;
+            const int bb = r / per_img;
+            const int rem = r - bb * per_img;
+            const int yy = rem / p.tw;
+            const int xx = rem - yy * p.tw;
+            const int b = cb0 + bb, y = cy0 + yy, x = cx0 + xx;
+            ok = (bb < p.tb) && (b < p.B) && (y < p.H) && (x < p.W);
+            m = ((long long)b * p.H + y) * p.W + x;
+          } else {
+            m = (long long)tc.mt * BM + r;
+            ok = m < p.M;
+          }
+          if (!ok || n >= n_out_total) continue;
+          const float4 sv = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + c4);
+          float o[4] = {sv.x, sv.y, sv.z, sv.w};
+          if (n + 3 < n_out_total) {
             if (p.residual != nullptr) {
               const float4 rr = *reinterpret_cast<const float4*>(p.residual + m * p.ld_res + n);
               o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
@@ -292,8 +293,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
               pk.y = pack_bf16x2(o[2], o[3]);
               *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_out + n) = pk;
             }
+          } else {
+            for (int j = 0; j < 4 && n + j < n_out_total; ++j) {
+              float a = o[j];
+              if (p.residual != nullptr) a += p.residual[m * p.ld_res + n + j];
+              if (p.out_f32 != nullptr) p.out_f32[m * p.ld_out + n + j] = a;
+              if (p.out_bf16 != nullptr) p.out_bf16[m * p.ld_out + n + j] = __float2bfloat16(a);
+            }
           }
         }
+        __syncwarp();  // staging buffer is reused by the next chunk
       }
       if (++acc == 2) {
         acc = 0;

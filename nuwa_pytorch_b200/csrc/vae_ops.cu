@@ -73,29 +73,40 @@ int nhwc_to_nchw_f32(const void* in, int in_is_bf16, float* out, int B, int C, i
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 im2col_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int C, int H, int W, int KS, int Kpad) {
-  const long long total = (long long)B * H * W * Kpad;
+  // one thread = 8 consecutive K entries of one output pixel -> one 16-byte store
+  const int G = Kpad / 8;
+  const long long total = (long long)B * H * W * G;
   const int pad = KS / 2;
   const int K = KS * KS * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int kk = (int)(i % Kpad);
-    const long long pix = i / Kpad;
-    float v = 0.f;
-    if (kk < K) {
-      const int c = kk % C, tap = kk / C;
-      const int kh = tap / KS, kw = tap % KS;
-      const int x = (int)(pix % W), y = (int)((pix / W) % H);
-      const long long b = pix / ((long long)W * H);
-      const int yy = y + kh - pad, xx = x + kw - pad;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = img[((b * C + c) * H + yy) * (long long)W + xx];
+    const int gk = (int)(i % G);
+    const long long pix = i / G;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H);
+    const long long b = pix / ((long long)W * H);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int kk = gk * 8 + e;
+      float val = 0.f;
+      if (kk < K) {
+        const int c = kk % C, tap = kk / C;
+        const int kh = tap / KS, kw = tap - kh * KS;
+        const int yy = y + kh - pad, xx = x + kw - pad;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(img + ((b * C + c) * H + yy) * (long long)W + xx);
+      }
+      v[e] = val;
     }
-    out[i] = __float2bfloat16(v);
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + pix * Kpad + gk * 8) = u;
   }
 }
 int im2col_nchw_f32(const float* img, void* out, int B, int C, int H, int W, int KS, int Kpad, cudaStream_t stream) {
   if (B <= 0 || C <= 0 || KS <= 0 || Kpad < KS * KS * C || (Kpad % 8)) return NUWA_ERR_INVALID;
-  const long long total = (long long)B * H * W * Kpad;
+  const long long total = (long long)B * H * W * (Kpad / 8);
   long long g = (total + 255) / 256;
-  int grid = (int)(g > 148LL * 32 ? 148LL * 32 : g);
+  int grid = (int)(g > 148LL * 64 ? 148LL * 64 : g);
   im2col_kernel<<<grid, 256, 0, stream>>>(img, reinterpret_cast<bf16*>(out), B, C, H, W, KS, Kpad);
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
@@ -107,45 +118,82 @@ int im2col_nchw_f32(const float* img, void* out, int B, int C, int H, int W, int
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512)
 gn_stats_kernel(const float* __restrict__ x, float* __restrict__ stats, int HW, int C, int G, float eps) {
+  // one CTA per (sample, group); the group's channels are a contiguous cg-wide slice of every NHWC pixel row.
   const int b = blockIdx.y, g = blockIdx.x;
   const int cg = C / G;
   const float* base = x + (long long)b * HW * C + g * cg;
-  const long long n = (long long)HW * cg;
-  // pass 1: mean
+  const double n = (double)HW * cg;
   __shared__ double red[16];
   __shared__ float s_mean;
-  double s = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const long long p = i / cg;
-    const int c = (int)(i - p * cg);
-    s += (double)base[p * C + c];
+  if (cg % 4 != 0) {
+    // narrow groups (tiny test models): scalar path, one thread does nothing clever
+    double s1 = 0.0;
+    for (long long i = threadIdx.x; i < (long long)HW * cg; i += blockDim.x) s1 += (double)base[(i / cg) * C + (i % cg)];
+    for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
+      s_mean = (float)(t / n);
+    }
+    __syncthreads();
+    const float mu = s_mean;
+    double q1 = 0.0;
+    for (long long i = threadIdx.x; i < (long long)HW * cg; i += blockDim.x) {
+      const float d = base[(i / cg) * C + (i % cg)] - mu;
+      q1 += (double)d * d;
+    }
+    for (int o = 16; o > 0; o >>= 1) q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
+      stats[((long long)b * G + g) * 2 + 0] = mu;
+      stats[((long long)b * G + g) * 2 + 1] = rsqrtf((float)(t / n) + eps);
+    }
+    return;
   }
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  const int cg4 = cg / 4;
+  const long long n4 = (long long)HW * cg4;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+    const long long p = i / cg4;
+    const int c4 = (int)(i - p * cg4);
+    const float4 v = *reinterpret_cast<const float4*>(base + p * C + c4 * 4);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  double sd = (double)s;
+  for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sd;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
-    s_mean = (float)(t / (double)n);
+    s_mean = (float)(t / n);
   }
   __syncthreads();
   const float mean = s_mean;
-  double q = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const long long p = i / cg;
-    const int c = (int)(i - p * cg);
-    const float d = base[p * C + c] - mean;
-    q += (double)d * d;
+  float q = 0.f;
+  for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+    const long long p = i / cg4;
+    const int c4 = (int)(i - p * cg4);
+    const float4 v = *reinterpret_cast<const float4*>(base + p * C + c4 * 4);
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
   }
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  double qd = (double)q;
+  for (int o = 16; o > 0; o >>= 1) qd += __shfl_xor_sync(0xffffffffu, qd, o);
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = qd;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
     stats[((long long)b * G + g) * 2 + 0] = mean;
-    stats[((long long)b * G + g) * 2 + 1] = rsqrtf((float)(t / (double)n) + eps);
+    stats[((long long)b * G + g) * 2 + 1] = rsqrtf((float)(t / n) + eps);
   }
 }
 __global__ void __launch_bounds__(256)
@@ -195,48 +243,65 @@ int groupnorm_nhwc(const float* x, const float* w, const float* bias, float* sta
 // bilinear 2x upsample, align_corners=False (vqgan_vae.py:353), NHWC bf16 -> NHWC bf16
 // src = (dst + 0.5)/2 - 0.5 clamped at 0 ; taps floor(src), floor(src)+1 (clamped) -- ATen's rule.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 lerp4_bf16x8(const uint4& a, const uint4& b, const uint4& c, const uint4& d, float wa,
+                                              float wb, float wc, float wd) {
+  const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+  const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
+  const uint32_t* pc = reinterpret_cast<const uint32_t*>(&c);
+  const uint32_t* pd = reinterpret_cast<const uint32_t*>(&d);
+  uint32_t r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fa = unpack_bf16x2(pa[j]), fb = unpack_bf16x2(pb[j]), fc = unpack_bf16x2(pc[j]), fd = unpack_bf16x2(pd[j]);
+    r[j] = pack_bf16x2(wa * fa.x + wb * fb.x + wc * fc.x + wd * fd.x, wa * fa.y + wb * fb.y + wc * fc.y + wd * fd.y);
+  }
+  return make_uint4(r[0], r[1], r[2], r[3]);
+}
+
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C) {
-  const int OH = 2 * H, OW = 2 * W;
+  // align_corners=False, scale 2: output 2i+1 = .75 in[i] + .25 in[i+1], output 2i+2 = .25 in[i] + .75 in[i+1]
+  // (indices clamped at the border).  One thread = the 2x2 output block fed by inputs (i,i+1)x(j,j+1), 8 channels:
+  // 4 loads + 4 stores of 16 bytes.  i in [-1, H-1], j in [-1, W-1].
+  const int OW = 2 * W, OH = 2 * H;
   const int C8 = C / 8;
-  const long long total = (long long)B * OH * OW * C8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    const long long pix = i / C8;
-    const int ox = (int)(pix % OW), oy = (int)((pix / OW) % OH);
-    const long long b = pix / ((long long)OW * OH);
-    float sy = ((float)oy + 0.5f) * 0.5f - 0.5f, sx = ((float)ox + 0.5f) * 0.5f - 0.5f;
-    sy = sy < 0.f ? 0.f : sy;
-    sx = sx < 0.f ? 0.f : sx;
-    const int y0 = (int)sy, x0 = (int)sx;
-    const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
-    const float ly = sy - (float)y0, lx = sx - (float)x0;
-    const float hy = 1.f - ly, hx = 1.f - lx;
+  const long long total = (long long)B * (H + 1) * (W + 1) * C8;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % C8);
+    long long r = t / C8;
+    const int j = (int)(r % (W + 1)) - 1;
+    r /= (W + 1);
+    const int i = (int)(r % (H + 1)) - 1;
+    const long long b = r / (H + 1);
+    const int i0 = i < 0 ? 0 : i, i1 = (i + 1 > H - 1) ? H - 1 : i + 1;
+    const int j0 = j < 0 ? 0 : j, j1 = (j + 1 > W - 1) ? W - 1 : j + 1;
     const bf16* base = in + b * (long long)H * W * C + c8 * 8;
-    const uint4 u00 = *reinterpret_cast<const uint4*>(base + ((long long)y0 * W + x0) * C);
-    const uint4 u01 = *reinterpret_cast<const uint4*>(base + ((long long)y0 * W + x1) * C);
-    const uint4 u10 = *reinterpret_cast<const uint4*>(base + ((long long)y1 * W + x0) * C);
-    const uint4 u11 = *reinterpret_cast<const uint4*>(base + ((long long)y1 * W + x1) * C);
-    const uint32_t* a = reinterpret_cast<const uint32_t*>(&u00);
-    const uint32_t* bq = reinterpret_cast<const uint32_t*>(&u01);
-    const uint32_t* cq = reinterpret_cast<const uint32_t*>(&u10);
-    const uint32_t* d = reinterpret_cast<const uint32_t*>(&u11);
-    uint32_t r[4];
+    const uint4 v00 = *reinterpret_cast<const uint4*>(base + ((long long)i0 * W + j0) * C);
+    const uint4 v01 = *reinterpret_cast<const uint4*>(base + ((long long)i0 * W + j1) * C);
+    const uint4 v10 = *reinterpret_cast<const uint4*>(base + ((long long)i1 * W + j0) * C);
+    const uint4 v11 = *reinterpret_cast<const uint4*>(base + ((long long)i1 * W + j1) * C);
+    bf16* ob = out + b * (long long)OH * OW * C + c8 * 8;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f00 = unpack_bf16x2(a[j]), f01 = unpack_bf16x2(bq[j]), f10 = unpack_bf16x2(cq[j]), f11 = unpack_bf16x2(d[j]);
-      const float rx = hy * (hx * f00.x + lx * f01.x) + ly * (hx * f10.x + lx * f11.x);
-      const float ry = hy * (hx * f00.y + lx * f01.y) + ly * (hx * f10.y + lx * f11.y);
-      r[j] = pack_bf16x2(rx, ry);
+    for (int dy = 0; dy < 2; ++dy) {
+      const int oy = 2 * i + 1 + dy;
+      if (oy < 0 || oy >= OH) continue;
+      const float wy0 = dy == 0 ? 0.75f : 0.25f, wy1 = 1.f - wy0;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int ox = 2 * j + 1 + dx;
+        if (ox < 0 || ox >= OW) continue;
+        const float wx0 = dx == 0 ? 0.75f : 0.25f, wx1 = 1.f - wx0;
+        *reinterpret_cast<uint4*>(ob + ((long long)oy * OW + ox) * C) =
+            lerp4_bf16x8(v00, v01, v10, v11, wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1);
+      }
     }
-    *reinterpret_cast<uint4*>(out + pix * C + c8 * 8) = make_uint4(r[0], r[1], r[2], r[3]);
   }
 }
 int upsample2x_nhwc_bf16(const void* in, void* out, int B, int H, int W, int C, cudaStream_t stream) {
   if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 8)) return NUWA_ERR_INVALID;
-  const long long total = (long long)B * 4 * H * W * (C / 8);
+  const long long total = (long long)B * (H + 1) * (W + 1) * (C / 8);
   long long g = (total + 255) / 256;
-  int grid = (int)(g > 148LL * 32 ? 148LL * 32 : g);
+  int grid = (int)(g > 148LL * 64 ? 148LL * 64 : g);
   upsample2x_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), B, H, W, C);
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
@@ -405,35 +470,49 @@ int gather_rows(const float* table, const long long* idx, void* out_bf16, float*
 __global__ void __launch_bounds__(256)
 conv1x1_to_nchw_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                        float* __restrict__ out, long long npix, int HW, int C, int Cout) {
-  const long long pix = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  extern __shared__ float w_s[];  // [Cout][C]
+  for (int i = threadIdx.x; i < Cout * C; i += blockDim.x) w_s[i] = w[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  if (pix >= npix) return;
-  float acc[8];
+  const long long wid = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long pix = wid; pix < npix; pix += nwarps) {
+    float acc[8];
 #pragma unroll
-  for (int o = 0; o < 8; ++o) acc[o] = 0.f;
-  const bf16* xr = x + pix * C;
-  for (int c = lane * 2; c < C; c += 64) {
-    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + c));
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    const bf16* xr = x + pix * C;
+    for (int c = lane * 8; c < C; c += 256) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + c);
+      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (o < Cout) {
+          const float4 wa = *reinterpret_cast<const float4*>(w_s + o * C + c);
+          const float4 wb = *reinterpret_cast<const float4*>(w_s + o * C + c + 4);
+          acc[o] += f0.x * wa.x + f0.y * wa.y + f1.x * wa.z + f1.y * wa.w + f2.x * wb.x + f2.y * wb.y + f3.x * wb.z +
+                    f3.y * wb.w;
+        }
+    }
+    const long long b = pix / HW;
+    const int p = (int)(pix - b * HW);
 #pragma unroll
     for (int o = 0; o < 8; ++o)
-      if (o < Cout) acc[o] = fmaf(v.x, w[o * C + c], fmaf(v.y, w[o * C + c + 1], acc[o]));
+      if (o < Cout) {
+        const float sres = warp_sum(acc[o]);
+        if (lane == 0) out[(b * Cout + o) * HW + p] = sres + bias[o];
+      }
   }
-  const long long b = pix / HW;
-  const int p = (int)(pix - b * HW);
-#pragma unroll
-  for (int o = 0; o < 8; ++o)
-    if (o < Cout) {
-      const float s = warp_sum(acc[o]);
-      if (lane == 0) out[(b * Cout + o) * HW + p] = s + bias[o];
-    }
 }
 int conv1x1_nhwc_to_nchw(const void* x, const float* w, const float* bias, float* out, int B, int HW, int C, int Cout,
                          cudaStream_t stream) {
-  if (B <= 0 || HW <= 0 || C <= 0 || (C & 1) || Cout <= 0 || Cout > 8) return NUWA_ERR_INVALID;
+  if (B <= 0 || HW <= 0 || C <= 0 || (C % 8) || Cout <= 0 || Cout > 8) return NUWA_ERR_INVALID;
   const long long npix = (long long)B * HW;
-  const int wpb = 8;
-  conv1x1_to_nchw_kernel<<<(unsigned)((npix + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
-      reinterpret_cast<const bf16*>(x), w, bias, out, npix, HW, C, Cout);
+  const size_t smem = (size_t)Cout * C * sizeof(float);
+  if (smem > 96 * 1024) return NUWA_ERR_INVALID;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(conv1x1_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  long long want = (npix + 7) / 8;
+  const int grid = (int)(want > 148LL * 8 ? 148LL * 8 : want);
+  conv1x1_to_nchw_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const bf16*>(x), w, bias, out, npix, HW, C, Cout);
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
 }

@@ -164,7 +164,7 @@ def attn_sparse3dna(qkv, o, *, B, nq, t0, npos, H, dh, talk, fmap, max_frames, n
 
 
 def attn_dense(q_ptr, k_ptr, v_ptr, o, *, B, nq, nk, H, dh, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, talk=None,
-               null_k=None, null_v=None, key_mask=None, head_scale=None, bias=None, qscale=None, t0=0):
+               null_k=None, null_v=None, key_mask=None, head_scale=None, bias=None, qscale=None, t0=0, use_mma=True):
     p = _attn_base(q_ptr, k_ptr, v_ptr, ptr(o) if torch.is_tensor(o) else o, B, nq, t0, H, dh, q_bs, k_bs, v_bs, o_bs,
                    q_rs, k_rs, v_rs, o_rs, talk)
     if qscale is not None:
@@ -177,7 +177,11 @@ def attn_dense(q_ptr, k_ptr, v_ptr, o, *, B, nq, nk, H, dh, q_bs, q_rs, k_bs, k_
     if bias is not None:
         p.bias, p.bias_nq, p.bias_nk = ptr(bias), bias.shape[1], bias.shape[2]
     p.jmax = nk + (1 if null_k is not None else 0)
-    check(lib().nuwa_attn_dense(p, stream()), "nuwa_attn_dense")
+    ws = None
+    if use_mma and nq >= 8 and nk <= 256 and dh in (32, 64) and H <= 8:
+        dev = o.device if torch.is_tensor(o) else torch.device('cuda')
+        ws = torch.empty(B * H * dh * _round_up(nk, 16), dtype=torch.bfloat16, device=dev)
+    check(lib().nuwa_attn_dense(p, ptr(ws), stream()), "nuwa_attn_dense")
 
 
 def attn_cross2dna(q_ptr, k_ptr, v_ptr, o_ptr, *, B, nq, t0, H, dh, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs,

@@ -1,0 +1,45 @@
+"""N>1 host logic on CPU: world_size-2 gloo process group (127.0.0.1), batch sharding + max-over-ranks timing +
+index gather, i.e. everything bench.py --gpus N does besides launching kernels."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nuwa_pytorch_b200.parallel import gather_indices, max_over_ranks, rank_slice
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    s, e = rank_slice(7, rank, world)
+    local = torch.arange(s, e, dtype=torch.int64)[:3].clone()  # 3 ids per rank (equal shapes for all_gather)
+    t = max_over_ranks(0.5 + rank, dist)
+    g = gather_indices(local, dist)
+    dist.barrier()
+    q.put((rank, (s, e), t, g.tolist()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_timing():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == (0, 4) and res[1][1] == (4, 7)          # contiguous, disjoint, covering shards
+    assert res[0][2] == res[1][2] == 1.5                         # every rank sees the slowest rank's time
+    assert res[0][3] == res[1][3] == [0, 1, 2, 4, 5, 6]          # rank-ordered gather
+
+
+def test_rank_slice_covers_everything():
+    for n in (1, 7, 64, 65):
+        for world in (1, 2, 4, 8):
+            parts = [rank_slice(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))

@@ -215,3 +215,53 @@ def test_attn_dense_core(cuda_device):
     attn = O._talking_heads(sim.softmax(-1), talk[:, :, None, None])
     ref = O._merge(attn @ vh)
     assert rel(o.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("B,nq,nk,H,dh,null,talk,bias", [(2, 37, 256, 8, 64, True, True, False), (3, 256, 256, 8, 64, False, False, True),
+                                                         (2, 50, 100, 4, 32, True, True, False)])
+def test_attn_dense_tensor_core_variant(cuda_device, B, nq, nk, H, dh, null, talk, bias):
+    """mma.sync variant vs the fp32 evaluation on identical bf16 operands, and vs the generic CUDA-core kernel."""
+    from nuwa_pytorch_b200 import ops
+    g = gen(B * 1000 + nq)
+    inner = H * dh
+    q = torch.randn(B, nq, inner, generator=g).bfloat16()
+    kv = torch.randn(B, nk, 2 * inner, generator=g).bfloat16()
+    null_k = torch.randn(H, dh, generator=g) if null else None
+    null_v = torch.randn(H, dh, generator=g) if null else None
+    tk = torch.randn(H, H, generator=g) / 2 if talk else None
+    bs = torch.randn(H, nq, nk, generator=g) if bias else None
+    hscale = torch.rand(H, generator=g) + 0.5 if bias else None
+    mask = None
+    if null:
+        mask = torch.rand(B, nk, generator=g) > 0.3
+        mask[0] = False
+    dv = lambda t: None if t is None else t.to(cuda_device).contiguous()
+    qd, kvd = dv(q), dv(kv)
+    outs = []
+    for use_mma in (True, False):
+        o = torch.zeros(B, nq, inner, dtype=torch.bfloat16, device=cuda_device)
+        ops.attn_dense(qd.data_ptr(), kvd.data_ptr(), kvd.data_ptr() + inner * 2, o, B=B, nq=nq, nk=nk, H=H, dh=dh,
+                       q_bs=nq * inner, q_rs=inner, k_bs=nk * 2 * inner, k_rs=2 * inner, v_bs=nk * 2 * inner,
+                       v_rs=2 * inner, o_bs=nq * inner, o_rs=inner, talk=dv(tk), null_k=dv(null_k), null_v=dv(null_v),
+                       key_mask=None if mask is None else dv(mask.to(torch.uint8)), head_scale=dv(hscale), bias=dv(bs),
+                       use_mma=use_mma)
+        outs.append(o.float().cpu())
+    qh = O._heads(q.float(), H) * dh ** -0.5
+    k, v = kv.float().chunk(2, -1)
+    kh, vh = O._heads(k, H), O._heads(v, H)
+    if null:
+        kh = torch.cat([null_k[None, :, None].expand(B, -1, -1, -1), kh], 2)
+        vh = torch.cat([null_v[None, :, None].expand(B, -1, -1, -1), vh], 2)
+    sim = qh @ kh.transpose(-1, -2)
+    if bias:
+        sim = sim * hscale[None, :, None, None] + bs[None]
+    if mask is not None:
+        sim = sim.masked_fill(~F.pad(mask, (1, 0), value=True)[:, None, None], O.NEG)
+    attn = sim.softmax(-1)
+    if talk:
+        attn = O._talking_heads(attn, tk[:, :, None, None])
+    ref = O._merge(attn @ vh)
+    r_mma, r_gen = rel(outs[0], ref), rel(outs[1], ref)
+    print(f"  dense attn B={B} nq={nq} nk={nk}: mma rel {r_mma:.2e}, generic rel {r_gen:.2e}")
+    assert r_gen < 4e-3      # fp32 math, one bf16 rounding of the output
+    assert r_mma < 8e-3      # additionally rounds the probabilities to bf16 for the PV tensor-core product

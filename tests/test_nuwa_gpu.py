@@ -96,7 +96,8 @@ def test_generate_runs_and_matches_oracle_sampling(cuda_device):
     for t in (0, 1, 7, 16, 25):
         lg = O.nuwa_generate_step_logits(temb, tmask, idx[:, :t].cpu(), sd, spec, 2.)
         filt = O.top_k_filter(lg, 0.9)
-        score = filt + (-torch.log(-torch.log(noise[t].cpu().clamp(min=1e-20)).clamp(min=1e-20)))
+        u = noise[t].cpu()
+        score = filt + (-torch.log((-torch.log(u.clamp(min=1e-20))).clamp(min=1e-20)))
         top2 = score.topk(2, dim=-1).values
         for b in range(2):
             if (top2[b, 0] - top2[b, 1]) > 0.3:
