@@ -6,8 +6,10 @@
 // * the contraction runs on the 5th-gen tensor cores: tcgen05.mma (cta_group::1, M=128, N=BN,
 //   K=16 per instruction) issued by one thread, accumulators double-buffered in TMEM so the
 //   epilogue of tile i overlaps the main loop of tile i+1,
-// * the epilogue reads TMEM with tcgen05.ld and fuses bias, LeakyReLU(0.1), GLU, GEGLU and the
-//   residual add, writing fp32 and/or bf16.
+// * the epilogue (8 warps, two per TMEM lane quadrant so every SM sub-partition has two warps to
+//   interleave) reads TMEM with tcgen05.ld, fuses bias, LeakyReLU(0.1), GLU, GEGLU and the residual
+//   add, transposes 32x16 slabs through shared memory and writes row-contiguous, fully coalesced
+//   fp32 and/or bf16 segments.
 //
 // "conv" mode turns the A operand into an implicit im2col of an NHWC bf16 activation: one M tile
 // is a (tb x th x tw) block of output pixels, each K slab is (filter tap, 64 input channels) and is
@@ -26,10 +28,11 @@ namespace nuwa {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-5 epilogue
+static constexpr int EPI_WARPS = 8;
+static constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-9 epilogue
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
-static constexpr int EPI_PITCH = 36;  // floats per staged row (32 + 4 pad: conflict-free float4 access)
-static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;  // one 32-row slab per epilogue warp
+static constexpr int EPI_PITCH = 20;  // floats per staged row: 16 outputs + 4 pad (conflict-free float4 access)
+static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
 
 template <int BN>
 struct GemmCfg {
@@ -58,6 +61,114 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int num_m, int num_n) 
   return c;
 }
 
+// 16 staged outputs of one accumulator row: bias + activation, written to this thread's staging row.
+//   non-pair: outputs = accumulator columns [16*h, 16*h+16) of the 32-column chunk
+//   pair    : outputs = value[0,16) combined with gate[16,32)
+template <int ACT, int HALF>
+__device__ __forceinline__ void epi_stage16(const uint32_t (&v)[32], float* srow, const float* __restrict__ bias,
+                                            int ncol /* first accumulator column of the 32-col chunk */, int N) {
+#pragma unroll
+  for (int j0 = 0; j0 < 16; j0 += 4) {
+    float o[4];
+    if constexpr (ACT == ACT_GLU || ACT == ACT_GEGLU) {
+      float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+      if (bias != nullptr) {
+        ba = __ldg(reinterpret_cast<const float4*>(bias + ncol + j0));
+        bg = __ldg(reinterpret_cast<const float4*>(bias + ncol + 16 + j0));
+      }
+      const float a[4] = {__uint_as_float(v[j0]) + ba.x, __uint_as_float(v[j0 + 1]) + ba.y,
+                          __uint_as_float(v[j0 + 2]) + ba.z, __uint_as_float(v[j0 + 3]) + ba.w};
+      const float g[4] = {__uint_as_float(v[16 + j0]) + bg.x, __uint_as_float(v[17 + j0]) + bg.y,
+                          __uint_as_float(v[18 + j0]) + bg.z, __uint_as_float(v[19 + j0]) + bg.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = (ACT == ACT_GLU) ? a[j] * sigmoid_f(g[j]) : a[j] * gelu_erf(g[j]);
+    } else {
+      const int n = ncol + 16 * HALF + j0;
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias != nullptr) {
+        if (n + 3 < N) {
+          bb = __ldg(reinterpret_cast<const float4*>(bias + n));
+        } else {
+          if (n < N) bb.x = bias[n];
+          if (n + 1 < N) bb.y = bias[n + 1];
+          if (n + 2 < N) bb.z = bias[n + 2];
+        }
+      }
+      o[0] = __uint_as_float(v[16 * HALF + j0]) + bb.x;
+      o[1] = __uint_as_float(v[16 * HALF + j0 + 1]) + bb.y;
+      o[2] = __uint_as_float(v[16 * HALF + j0 + 2]) + bb.z;
+      o[3] = __uint_as_float(v[16 * HALF + j0 + 3]) + bb.w;
+      if constexpr (ACT == ACT_LEAKY) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = leaky01(o[j]);
+      }
+    }
+    *reinterpret_cast<float4*>(srow + j0) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// Store phase of one 32-row x 16-column slab: lane -> (row = it*8 + lane/4, 4 columns), so a warp store
+// instruction covers 8 rows x 64 B (fp32) / 32 B (bf16) of contiguous output.
+__device__ __forceinline__ void epi_store16(const float* stg, int lane, const long long (&mrow)[4], unsigned okmask,
+                                            int n0, int n_out_total, const GemmParams& p) {
+  const int c4 = (lane & 3) * 4;
+  const int n = n0 + c4;
+  if (n >= n_out_total) return;
+  const bool full = n + 3 < n_out_total;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    if (!((okmask >> it) & 1u)) continue;
+    const int rl = it * 8 + (lane >> 2);
+    const float4 sv = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + c4);
+    float o[4] = {sv.x, sv.y, sv.z, sv.w};
+    const long long m = mrow[it];
+    if (full) {
+      if (p.residual != nullptr) {
+        const float4 rr = *reinterpret_cast<const float4*>(p.residual + m * p.ld_res + n);
+        o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+      }
+      if (p.out_f32 != nullptr)
+        *reinterpret_cast<float4*>(p.out_f32 + m * p.ld_out + n) = make_float4(o[0], o[1], o[2], o[3]);
+      if (p.out_bf16 != nullptr) {
+        uint2 pk;
+        pk.x = pack_bf16x2(o[0], o[1]);
+        pk.y = pack_bf16x2(o[2], o[3]);
+        *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_out + n) = pk;
+      }
+    } else {
+      for (int j = 0; j < 4 && n + j < n_out_total; ++j) {
+        float a = o[j];
+        if (p.residual != nullptr) a += p.residual[m * p.ld_res + n + j];
+        if (p.out_f32 != nullptr) p.out_f32[m * p.ld_out + n + j] = a;
+        if (p.out_bf16 != nullptr) p.out_bf16[m * p.ld_out + n + j] = __float2bfloat16(a);
+      }
+    }
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], float* stg, int lane, const long long (&mrow)[4],
+                                          unsigned okmask, int nc, int n_out_total, const GemmParams& p) {
+  float* srow = stg + lane * EPI_PITCH;
+  if constexpr (ACT == ACT_GLU || ACT == ACT_GEGLU) {
+    epi_stage16<ACT, 0>(v, srow, p.bias, nc, p.N);
+    __syncwarp();
+    epi_store16(stg, lane, mrow, okmask, nc / 2, n_out_total, p);
+    __syncwarp();
+  } else {
+    epi_stage16<ACT, 0>(v, srow, p.bias, nc, p.N);
+    __syncwarp();
+    epi_store16(stg, lane, mrow, okmask, nc, n_out_total, p);
+    __syncwarp();
+    if (nc + 16 < p.N) {  // warp-uniform
+      epi_stage16<ACT, 1>(v, srow, p.bias, nc, p.N);
+      __syncwarp();
+      epi_store16(stg, lane, mrow, okmask, nc + 16, n_out_total, p);
+      __syncwarp();
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -83,7 +194,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[a], EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -184,125 +295,75 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
     __syncwarp();
   } else {
-    // ================================ epilogue (4 warps) ================================
-    // TMEM -> registers (thread = accumulator row) -> bias/activation -> per-warp shared-memory transpose ->
-    // row-contiguous, fully coalesced global stores (8 lanes x 16 B = one 128 B line per output row segment).
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    float* stg = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + q * (32 * EPI_PITCH);
+    // ================================ epilogue (8 warps) ================================
+    const int ew = warp - 2;        // 0..7
+    const int q = warp & 3;         // TMEM lane quadrant this warp may access (hardware rule: warp id % 4)
+    const int half = ew >> 2;       // which half of the tile's column chunks this warp drains
+    constexpr int CHUNKS = BN / 32;
+    constexpr int CPW = (CHUNKS + 1) / 2;  // chunks per warp
+    float* stg = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + ew * (32 * EPI_PITCH);
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool pair = (p.act == ACT_GLU || p.act == ACT_GEGLU);
     const int n_out_total = pair ? p.N / 2 : p.N;
-    const int W = pair ? 16 : 32;            // output columns produced per 32-column accumulator chunk
-    const int lpr = W / 4;                   // lanes per output row in the store phase
-    const int rpi = 32 / lpr;                // rows per store iteration
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = tile_coord(tile, p.num_m_tiles, p.num_n_tiles);
       const int n0 = tc.nt * BN;
-      int cx0 = 0, cy0 = 0, cb0 = 0;
+      // rows this lane stores in the transposed phase: r = q*32 + it*8 + lane/4, it = 0..3
+      long long mrow[4];
+      unsigned okmask = 0;
       if (p.conv) {
-        cx0 = (tc.mt % p.tiles_x) * p.tw;
-        cy0 = ((tc.mt / p.tiles_x) % p.tiles_y) * p.th;
-        cb0 = (tc.mt / (p.tiles_x * p.tiles_y)) * p.tb;
+        const int cx0 = (tc.mt % p.tiles_x) * p.tw;
+        const int cy0 = ((tc.mt / p.tiles_x) % p.tiles_y) * p.th;
+        const int cb0 = (tc.mt / (p.tiles_x * p.tiles_y)) * p.tb;
+        const int per_img = p.th * p.tw;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int r = q * 32 + it * 8 + (lane >> 2);
+          const int bb = r / per_img;
+          const int rem = r - bb * per_img;
+          const int yy = rem / p.tw;
+          const int xx = rem - yy * p.tw;
+          const int b = cb0 + bb, y = cy0 + yy, x = cx0 + xx;
+          if ((bb < p.tb) && (b < p.B) && (y < p.H) && (x < p.W)) okmask |= 1u << it;
+          mrow[it] = ((long long)b * p.H + y) * p.W + x;
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          mrow[it] = (long long)tc.mt * BM + q * 32 + it * 8 + (lane >> 2);
+          if (mrow[it] < p.M) okmask |= 1u << it;
+        }
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
-        if (c == BN / 32 - 1) {
-          // all TMEM reads of this accumulator are done: hand the buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
+      for (int ci = 0; ci < CPW; ++ci) {
+        const int c = half * CPW + ci;
+        if (c < CHUNKS) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+          if (ci == CPW - 1 || c == CHUNKS - 1) {
+            // this warp's TMEM reads of the accumulator are done: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          const int nc = n0 + c * 32;
+          if (nc < p.N) {  // warp-uniform
+            switch (p.act) {
+              case ACT_LEAKY: epi_chunk<ACT_LEAKY>(v, stg, lane, mrow, okmask, nc, n_out_total, p); break;
+              case ACT_GLU: epi_chunk<ACT_GLU>(v, stg, lane, mrow, okmask, nc, n_out_total, p); break;
+              case ACT_GEGLU: epi_chunk<ACT_GEGLU>(v, stg, lane, mrow, okmask, nc, n_out_total, p); break;
+              default: epi_chunk<ACT_NONE>(v, stg, lane, mrow, okmask, nc, n_out_total, p); break;
+            }
+          }
+        } else if (ci == CPW - 1) {
+          // (only when CHUNKS is odd) nothing to drain in the last slot, still release the accumulator
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        const int nc = n0 + c * 32;
-        if (nc >= p.N) continue;  // warp-uniform
-        // ---- phase 1: bias + activation on this thread's row, stage to shared memory ----
-        float* srow = stg + lane * EPI_PITCH;
-        if (!pair) {
-#pragma unroll
-          for (int j0 = 0; j0 < 32; j0 += 4) {
-            float o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float a = __uint_as_float(v[j0 + j]);
-              if (p.bias != nullptr && nc + j0 + j < p.N) a += __ldg(p.bias + nc + j0 + j);
-              if (p.act == ACT_LEAKY) a = leaky01(a);
-              o[j] = a;
-            }
-            *reinterpret_cast<float4*>(srow + j0) = make_float4(o[0], o[1], o[2], o[3]);
-          }
-        } else {
-          // packed pair layout: within every 32 packed columns, [0,16) = value half, [16,32) = gate half
-#pragma unroll
-          for (int j0 = 0; j0 < 16; j0 += 4) {
-            float o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float a = __uint_as_float(v[j0 + j]);
-              float g = __uint_as_float(v[16 + j0 + j]);
-              if (p.bias != nullptr) {
-                a += __ldg(p.bias + nc + j0 + j);
-                g += __ldg(p.bias + nc + 16 + j0 + j);
-              }
-              o[j] = (p.act == ACT_GLU) ? a * sigmoid_f(g) : a * gelu_erf(g);
-            }
-            *reinterpret_cast<float4*>(srow + j0) = make_float4(o[0], o[1], o[2], o[3]);
-          }
-        }
-        __syncwarp();
-        // ---- phase 2: transposed read, residual add, coalesced stores ----
-        const int no = pair ? nc / 2 : nc;
-        const int c4 = (lane % lpr) * 4;
-        const int n = no + c4;
-        for (int it = 0; it < 32; it += rpi) {
-          const int rl = it + lane / lpr;  // row inside this warp's 32-row slab
-          const int r = q * 32 + rl;       // row inside the 128-row tile
-          long long m;
-          bool ok;
-          if (p.conv) {
-            const int per_img = p.th * p.tw;
-            const int bb = r / per_img;
-            const int rem = r - bb * per_img;
-            const int yy = rem / p.tw;
-            const int xx = rem - yy * p.tw;
-            const int b = cb0 + bb, y = cy0 + yy, x = cx0 + xx;
-            ok = (bb < p.tb) && (b < p.B) && (y < p.H) && (x < p.W);
-            m = ((long long)b * p.H + y) * p.W + x;
-          } else {
-            m = (long long)tc.mt * BM + r;
-            ok = m < p.M;
-          }
-          if (!ok || n >= n_out_total) continue;
-          const float4 sv = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + c4);
-          float o[4] = {sv.x, sv.y, sv.z, sv.w};
-          if (n + 3 < n_out_total) {
-            if (p.residual != nullptr) {
-              const float4 rr = *reinterpret_cast<const float4*>(p.residual + m * p.ld_res + n);
-              o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
-            }
-            if (p.out_f32 != nullptr)
-              *reinterpret_cast<float4*>(p.out_f32 + m * p.ld_out + n) = make_float4(o[0], o[1], o[2], o[3]);
-            if (p.out_bf16 != nullptr) {
-              uint2 pk;
-              pk.x = pack_bf16x2(o[0], o[1]);
-              pk.y = pack_bf16x2(o[2], o[3]);
-              *reinterpret_cast<uint2*>(p.out_bf16 + m * p.ld_out + n) = pk;
-            }
-          } else {
-            for (int j = 0; j < 4 && n + j < n_out_total; ++j) {
-              float a = o[j];
-              if (p.residual != nullptr) a += p.residual[m * p.ld_res + n + j];
-              if (p.out_f32 != nullptr) p.out_f32[m * p.ld_out + n + j] = a;
-              if (p.out_bf16 != nullptr) p.out_bf16[m * p.ld_out + n + j] = __float2bfloat16(a);
-            }
-          }
-        }
-        __syncwarp();  // staging buffer is reused by the next chunk
       }
       if (++acc == 2) {
         acc = 0;
@@ -423,6 +484,7 @@ static cudaEvent_t prof_event() {
 template <int BN>
 static int launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
@@ -465,6 +527,7 @@ static bool epilogue_args_ok(const GemmParams& p) {
   if (p.out_f32 == nullptr && p.out_bf16 == nullptr) return false;
   if (p.ld_out % 4 != 0) return false;
   if (p.residual != nullptr && p.ld_res % 4 != 0) return false;
+  if (p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15)) return false;
   return true;
 }
 

@@ -149,3 +149,15 @@ def test_sketch_small(cuda_device):
                  return_loss=True)
     print(f"  sketch e2e loss {loss.item():.5f} vs {fx['e2e_loss'].item():.5f}")
     assert abs(loss.item() - fx['e2e_loss'].item()) < 0.1  # token flips in the VAEs move single targets
+
+
+def test_cuda_graph_replay_matches_eager(cuda_device):
+    from nuwa_pytorch_b200.graphs import GraphedCall
+    fx, model, sd = _nuwa("nuwa_small.pt", cuda_device)
+    text, vidx = fx['text'].to(cuda_device), fx['video_indices'].to(cuda_device)
+    eager = model(text=text, video=vidx, return_loss=True).item()
+    g = GraphedCall(lambda t, v: model(text=t, video=v, return_loss=True), text, vidx)
+    assert abs(g(text, vidx).item() - eager) < 1e-6
+    vidx2 = (vidx + 7) % 64
+    eager2 = model(text=text, video=vidx2, return_loss=True).item()
+    assert abs(g(text, vidx2).item() - eager2) < 1e-6 and abs(eager2 - eager) > 1e-4
