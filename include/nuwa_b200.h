@@ -88,6 +88,14 @@ typedef struct {
   int shift, fmap;
   int t0, B, nt, D;
   float eps;
+  /* CUDA-graph decode support: when t0_ptr != NULL the position is read from device memory (t0 = *t0_ptr), so one
+   * captured decode step can be replayed for every token.  gather = 1 selects the gather form of the token shift:
+   * the complete operand row of position t is written to the dense a_out[b*a_bs + local*a_rs] (fixed address), its
+   * shifted channels being read from `shift_cache` (bf16 [B][a_npos][D], row t holds LayerNorm(x_t)[0, D/2)). */
+  const int* t0_ptr;
+  int gather;
+  void* shift_cache;
+  long long sc_bs;
 } nuwa_ln_params;
 int nuwa_sandwich_ln(const nuwa_ln_params* p, void* stream);
 
@@ -123,13 +131,14 @@ typedef struct {
   int ck, cdil;
   int jmax;
   int nk_dense; /* set by the library (dense tensor-core path); callers leave it 0 */
+  const int* t0_ptr; /* CUDA-graph decode: if non-NULL, t0 = *t0_ptr (and, for Sparse3DNA, nv = t0) */
 } nuwa_attn_params;
 /* Sparse3DNA.forward core, nuwa_pytorch.py:490-608 (jmax = 1 + kt*kh*kw; k/v row 0 = bos, row 1+i = video token i) */
 int nuwa_attn_sparse3dna(const nuwa_attn_params* p, void* stream);
 /* Attention.forward core, nuwa_pytorch.py:339-378, and VQGanAttention core, vqgan_vae.py:275-282
  * (jmax = nk (+1 with a null key)) */
 int nuwa_attn_dense(const nuwa_attn_params* p, void* vt_workspace, void* stream);
-/* vt_workspace: NULL, or B*H*dh*roundup(nk,16) bf16 elements of scratch; when given and nk <= 256, dh in {32,64},
+/* vt_workspace: NULL, or B*H*dh*roundup(nk,64) bf16 elements of scratch; when given and nk <= 256, dh in {32,64},
  * H <= 8, nq >= 8 the tensor-core (mma.sync) variant runs, otherwise the generic CUDA-core kernel. */
 /* SparseCross2DNA.forward non-bos queries, nuwa_pytorch.py:851-895 (jmax = 1 + frames*ck*ck; t0 >= 1) */
 int nuwa_attn_cross2dna(const nuwa_attn_params* p, void* stream);
@@ -146,6 +155,7 @@ typedef struct {
   const float* ax3;
   int d2, d3;
   int has_bos, t0, B, nt, D;
+  const int* t0_ptr; /* CUDA-graph decode: if non-NULL, t0 = *t0_ptr */
 } nuwa_embed_params;
 /* Embedding + AxialPositionalEmbedding + bos: nuwa_pytorch.py:1659-1709,1879-1881,1940-1944 */
 int nuwa_embed_tokens(const nuwa_embed_params* p, void* stream);
@@ -159,6 +169,15 @@ int nuwa_cross_entropy_mean(const float* logits, int ld, const long long* target
  * uncond may be NULL (cond_scale == 1); guided_out (optional) receives the mixed logits [B,V]. */
 int nuwa_sample_topk_gumbel(const float* cond, const float* uncond, const float* noise, long long* out,
                             float* guided_out, int B, int V, int k, float cond_scale, float temperature, void* stream);
+/* Same, for a captured decode step: step = *step_ptr (device); noise row = noise + step*B*V; the sampled id of sample b
+ * is written to out[b*out_bs + step] (the token sequence buffer the next step's embedding reads). */
+int nuwa_sample_topk_gumbel_at(const float* cond, const float* uncond, const float* noise, long long* out,
+                               long long out_bs, const int* step_ptr, int B, int V, int k, float cond_scale,
+                               float temperature, void* stream);
+/* Decode-step helpers: cache[b][*t_ptr][:] = row[b][:] (bf16, `width` elements; appends the new token's q|k|v to the KV
+ * cache) and *t_ptr += 1. */
+int nuwa_cache_append(const void* row, void* cache, long long cache_bs, int width, int B, const int* t_ptr, void* stream);
+int nuwa_step_increment(int* t_ptr, void* stream);
 
 /* ---- VQGanVAE support kernels ---------------------------------------------------------------- */
 int nuwa_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, void* stream);

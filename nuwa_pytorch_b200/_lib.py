@@ -20,7 +20,7 @@ class LnParams(ctypes.Structure):  # mirrors nuwa_ln_params
                 ("x_out", c_void_p), ("x_out_bf16", c_void_p), ("pre_w", c_void_p), ("pre_b", c_void_p),
                 ("a_out", c_void_p), ("a_bs", c_ll), ("a_rs", c_int), ("a_t0", c_int), ("a_npos", c_int),
                 ("shift", c_int), ("fmap", c_int), ("t0", c_int), ("B", c_int), ("nt", c_int), ("D", c_int),
-                ("eps", c_float)]
+                ("eps", c_float), ("t0_ptr", c_void_p), ("gather", c_int), ("shift_cache", c_void_p), ("sc_bs", c_ll)]
 
 
 class AttnParams(ctypes.Structure):  # mirrors nuwa_attn_params
@@ -32,13 +32,13 @@ class AttnParams(ctypes.Structure):  # mirrors nuwa_attn_params
                 ("key_mask", c_void_p), ("mask_bs", c_int), ("bias", c_void_p), ("bias_nq", c_int), ("bias_nk", c_int),
                 ("fmap", c_int), ("max_frames", c_int), ("nv", c_int), ("kt", c_int), ("kh", c_int), ("kw", c_int),
                 ("dt", c_int), ("dh_", c_int), ("dw", c_int), ("causal", c_int), ("ck", c_int), ("cdil", c_int),
-                ("jmax", c_int), ("nk_dense", c_int)]
+                ("jmax", c_int), ("nk_dense", c_int), ("t0_ptr", c_void_p)]
 
 
 class EmbedParams(ctypes.Structure):  # mirrors nuwa_embed_params
     _fields_ = [("out", c_void_p), ("idx", c_void_p), ("idx_bs", c_ll), ("table", c_void_p), ("bos", c_void_p),
                 ("ax1", c_void_p), ("ax2", c_void_p), ("ax3", c_void_p), ("d2", c_int), ("d3", c_int),
-                ("has_bos", c_int), ("t0", c_int), ("B", c_int), ("nt", c_int), ("D", c_int)]
+                ("has_bos", c_int), ("t0", c_int), ("B", c_int), ("nt", c_int), ("D", c_int), ("t0_ptr", c_void_p)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES).  Must list EVERY symbol of include/nuwa_b200.h.
@@ -63,6 +63,10 @@ SIGNATURES = {
     "nuwa_cross_entropy_mean": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "nuwa_sample_topk_gumbel": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                 c_float, c_void_p],
+    "nuwa_sample_topk_gumbel_at": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_float,
+                                   c_float, c_void_p],
+    "nuwa_cache_append": [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
+    "nuwa_step_increment": [c_void_p, c_void_p],
     "nuwa_nchw_f32_to_nhwc_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "nuwa_nhwc_to_nchw_f32": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "nuwa_im2col_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],

@@ -67,6 +67,15 @@ int nuwa_sample_topk_gumbel(const float* cond, const float* uncond, const float*
                             float* guided_out, int B, int V, int k, float cond_scale, float temperature, void* stream) {
   return sample_topk_gumbel(cond, uncond, noise, out, guided_out, B, V, k, cond_scale, temperature, S(stream));
 }
+int nuwa_sample_topk_gumbel_at(const float* cond, const float* uncond, const float* noise, long long* out,
+                               long long out_bs, const int* step_ptr, int B, int V, int k, float cond_scale,
+                               float temperature, void* stream) {
+  return sample_topk_gumbel_at(cond, uncond, noise, out, out_bs, step_ptr, B, V, k, cond_scale, temperature, S(stream));
+}
+int nuwa_cache_append(const void* row, void* cache, long long cache_bs, int width, int B, const int* t_ptr, void* stream) {
+  return cache_append(row, cache, cache_bs, width, B, t_ptr, S(stream));
+}
+int nuwa_step_increment(int* t_ptr, void* stream) { return step_increment(t_ptr, S(stream)); }
 int nuwa_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, void* stream) {
   return nchw_f32_to_nhwc_bf16(in, out, B, C, H, W, S(stream));
 }

@@ -78,7 +78,7 @@ __device__ __forceinline__ void store_row(bf16* p, const float (&v)[CPL]) {
 
 // key slot j of query position t (absolute sequence index) -> kind and row in the K/V buffers
 template <int MODE>
-__device__ __forceinline__ int key_of(const AttnParams& p, int b, int t, int j, int& row) {
+__device__ __forceinline__ int key_of(const AttnParams& p, int b, int t, int nv, int j, int& row) {
   if constexpr (MODE == MODE_3DNA) {
     if (j == 0) {
       row = 0;  // bos key / value
@@ -94,7 +94,7 @@ __device__ __forceinline__ int key_of(const AttnParams& p, int b, int t, int j, 
     const int ff = f + a * p.dt - Pf, yy = y + bq * p.dh_ - Ph, xx = x + c * p.dw - Pw;
     if (ff < 0 || ff >= p.max_frames || yy < 0 || yy >= p.fmap || xx < 0 || xx >= p.fmap) return KEY_MASKED;
     const int idx = (ff * p.fmap + yy) * p.fmap + xx;
-    if (idx >= p.nv) return KEY_ZERO;  // zero-padded position: visible, contributes exp(0 - max), no value
+    if (idx >= nv) return KEY_ZERO;  // zero-padded position: visible, contributes exp(0 - max), no value
     row = 1 + idx;
     return KEY_NORMAL;
   } else if constexpr (MODE == MODE_DENSE) {
@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnParams p) {
   const int J = p.jmax;                // key slots per query
   float* S = smem_f + (size_t)warp * QPW * p.H * J;   // [QPW][H][J]
   float* Wt = smem_f + (size_t)warps_per_cta * QPW * p.H * J;  // [H][H] talking-heads matrix
+  int* keys = reinterpret_cast<int*>(Wt + p.H * p.H) + warp * J;  // per-warp key list: (kind << 28) | row
   if (p.talk != nullptr) {
     for (int i = threadIdx.x; i < p.H * p.H; i += blockDim.x) Wt[i] = p.talk[i];
   }
@@ -170,7 +171,9 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnParams p) {
   const float hscale = p.head_scale != nullptr ? p.head_scale[h] : 1.0f;
 
   // Sparse3DNA: the bos query attends only to itself -> output = its own value row
-  if (MODE == MODE_3DNA && (p.t0 + q0) == 0) {
+  const int t0 = p.t0_ptr != nullptr ? __ldg(p.t0_ptr) : p.t0;  // device-side position for graph-replayed decode steps
+  const int nv = (p.t0_ptr != nullptr && MODE == MODE_3DNA) ? t0 : p.nv;
+  if (MODE == MODE_3DNA && (t0 + q0) == 0) {
     float vv[CPL];
     load_row<CPL>(vb + ch, vv);
     store_row<CPL>(ob + (long long)q0 * p.o_rs + ch, vv);
@@ -178,11 +181,20 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnParams p) {
     if (QPW == 1) return;
   }
 
+  // key list once per warp (the index arithmetic is ~40 integer ops per slot: do it on one lane per slot instead of
+  // on all 32 lanes per slot, twice).  Key kind is query dependent only for the gather modes (QPW == 1 there).
+  for (int j = lane; j < J; j += 32) {
+    int row = 0;
+    const int kind = key_of<MODE>(p, b, t0 + q0, nv, j, row);
+    keys[j] = (kind << 28) | row;
+  }
+  __syncwarp();
+
   // ---------------- scores ----------------
   for (int j = 0; j < J; ++j) {
-    // key kind is query dependent only for the gather modes (QPW == 1 there)
-    int row = 0;
-    const int kind = key_of<MODE>(p, b, p.t0 + q0, j, row);
+    const int kj = keys[j];
+    const int row = kj & 0x0FFFFFFF;
+    const int kind = kj >> 28;
     float part[QPW];
     if (kind == KEY_NORMAL || kind == KEY_NULL) {
       float kf[CPL];
@@ -210,7 +222,7 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnParams p) {
         if (kind != KEY_MASKED) {
           s *= hscale;
           if (p.bias != nullptr)
-            s += p.bias[((long long)h * p.bias_nq + (p.t0 + q0 + qi < p.bias_nq ? p.t0 + q0 + qi : 0)) * p.bias_nk + j];
+            s += p.bias[((long long)h * p.bias_nq + (t0 + q0 + qi < p.bias_nq ? t0 + q0 + qi : 0)) * p.bias_nk + j];
         }
         S[(qi * p.H + h) * J + j] = s;
       }
@@ -261,8 +273,9 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnParams p) {
 #pragma unroll
     for (int c = 0; c < CPL; ++c) acc[qi][c] = 0.f;
   for (int j = 0; j < J; ++j) {
-    int row = 0;
-    const int kind = key_of<MODE>(p, b, p.t0 + q0, j, row);
+    const int kj = keys[j];
+    const int row = kj & 0x0FFFFFFF;
+    const int kind = kj >> 28;
     if (kind == KEY_MASKED || kind == KEY_ZERO) continue;
     float vf[CPL];
     if (kind == KEY_NULL) load_row_f32<CPL>(p.null_v + ch, vf);
@@ -285,7 +298,7 @@ static int launch_attn(const AttnParams& p, cudaStream_t stream) {
   if (inner % 32 != 0 || (32 % p.H) != 0 || p.H > 32) return NUWA_ERR_INVALID;
   const int cpl = inner / 32;
   const int warps = 4;
-  const size_t smem = ((size_t)warps * QPW * p.H * p.jmax + p.H * p.H) * sizeof(float);
+  const size_t smem = ((size_t)warps * QPW * p.H * p.jmax + p.H * p.H + (size_t)warps * p.jmax) * sizeof(float);
   if (smem > 200 * 1024) return NUWA_ERR_INVALID;
   const int groups = p.B * ((p.nq + QPW - 1) / QPW);
   if (groups <= 0) return NUWA_OK;

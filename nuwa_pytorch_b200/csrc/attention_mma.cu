@@ -7,10 +7,15 @@
 //            the learned null key is an exact fp32 side column; P_w -> shared memory as bf16
 //   phase 2  talking heads: P'[g] = sum_h W[g][h] P[h] mixes the heads in shared memory
 //   phase 3  O_w = P'_w V_w (+ P'_null * null_v), bf16 out
-// Operand fragments are read straight from global/L2 with 32-bit loads in the m16n8k16 fragment layout
-// (K rows are d-contiguous; V is consumed through a transposed copy vT[b][h][d][j] produced by
-// kv_transpose_kernel), so no shared-memory staging of K/V is needed; K/V of a sample are shared by all
-// its query tiles and stay L2 resident.
+//
+// Operand fragments come straight from global/L2 (K/V of a sample are shared by all its query tiles and stay
+// L2 resident).  A contraction does not care about the order of its index, so the contraction index is
+// PERMUTED such that everything one lane feeds into the 4 k-steps of an m16n8k16 group is 32 contiguous
+// bytes: lane t of a quad owns d in [DH/4*t, DH/4*(t+1)) for QK^T and keys [64*blk+16t, +16) for PV
+// (k-step s, fragment slots {2t,2t+1,2t+8,2t+9}  <->  owned index 4s+{0,1,2,3}).  Loads are therefore
+// 16-byte vectors covering whole 128-byte rows per quad instead of scattered 4-byte words.
+// V is consumed through a transposed copy vT[b][h][d][j] (kv_transpose_kernel).
+//
 // This is the legacy mma.sync tensor path on purpose: tiles are 16 x 8, far below a tcgen05 128-row atom, and
 // the talking-heads mix forces all heads of a query tile to be resident at once (8 x 257 probabilities per
 // query), which caps the query tile at 16-32 rows.
@@ -21,14 +26,29 @@
 
 namespace nuwa {
 
-static constexpr int MMA_MAXKT = 16;  // 16-key steps -> nk <= 256
+static constexpr int MMA_MAXKB = 4;   // 64-key blocks -> nk <= 256
 static constexpr int MMA_QT = 16;     // queries per CTA
 
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// 2*KS consecutive 32-bit words (= 4*KS bf16) from a 16-byte aligned address
+template <int KS>
+__device__ __forceinline__ void load_words(const bf16* p, uint32_t (&w)[2 * KS]) {
+  if constexpr (KS == 4) {
+    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    w[0] = u0.x; w[1] = u0.y; w[2] = u0.z; w[3] = u0.w;
+    w[4] = u1.x; w[5] = u1.y; w[6] = u1.z; w[7] = u1.w;
+  } else {
+    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(p));
+    w[0] = u0.x; w[1] = u0.y; w[2] = u0.z; w[3] = u0.w;
+  }
 }
 
 // vT[b][h][d][jp] = v[b][j][h*dh + d]  (zero padded to jp keys)
@@ -47,62 +67,59 @@ kv_transpose_kernel(const bf16* __restrict__ v, long long v_bs, int v_rs, bf16* 
 
 template <int DH>
 __global__ void __launch_bounds__(256, 1) attn_dense_mma_kernel(const AttnParams p, const bf16* __restrict__ vT, int jp) {
-  constexpr int KS = DH / 16;  // k-steps of the QK^T contraction
-  constexpr int ND = DH / 8;   // output n-tiles of PV
+  constexpr int KS = DH / 16;   // k-steps of the QK^T contraction
+  constexpr int ND = DH / 8;    // output n-tiles of PV
+  constexpr int SPAN = DH / 4;  // d values owned by one lane of a quad
   extern __shared__ __align__(16) uint8_t smem_mma[];
   const int H = p.H;
-  const int PSTR = jp + 8;  // bf16 row pitch of P (bank-conflict-free fragment reads)
-  bf16* P = reinterpret_cast<bf16*>(smem_mma);                                   // [H][16][PSTR]
+  const int PSTR = jp + 4;  // bf16 row pitch of P: 64-bit fragment reads are bank-conflict free
+  bf16* P = reinterpret_cast<bf16*>(smem_mma);                                        // [H][16][PSTR]
   float* Pnull = reinterpret_cast<float*>(smem_mma + (size_t)H * MMA_QT * PSTR * 2);  // [H][16]
-  float* Wt = Pnull + H * MMA_QT;                                                // [H][H]
+  float* Wt = Pnull + H * MMA_QT;                                                     // [H][H]
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int tiles_per_b = (p.nq + MMA_QT - 1) / MMA_QT;
   const int b = blockIdx.x / tiles_per_b;
   const int q0 = (blockIdx.x - b * tiles_per_b) * MMA_QT;
   const int nk = p.nk_dense;
-  const int nkt = jp / 16;
+  const int nkb = jp / 64;  // 64-key blocks
   const bool has_null = p.null_k != nullptr;
   if (p.talk != nullptr)
     for (int i = threadIdx.x; i < H * H; i += blockDim.x) Wt[i] = p.talk[i];
 
-  const bf16* qb = reinterpret_cast<const bf16*>(p.q) + (long long)b * p.q_bs + w * DH;
-  const bf16* kb = reinterpret_cast<const bf16*>(p.k) + (long long)b * p.k_bs + w * DH;
+  const bf16* qb = reinterpret_cast<const bf16*>(p.q) + (long long)b * p.q_bs + w * DH + SPAN * t;
+  const bf16* kb = reinterpret_cast<const bf16*>(p.k) + (long long)b * p.k_bs + w * DH + SPAN * t;
   const int r0 = q0 + g, r1 = q0 + g + 8;
   const bool ok0 = r0 < p.nq, ok1 = r1 < p.nq;
 
   // ---------------- phase 1: scores + softmax (warp w = head w) ----------------
-  uint32_t qa[KS][4];
+  uint32_t qa0[2 * KS], qa1[2 * KS];  // rows r0 / r1, this lane's d span
 #pragma unroll
-  for (int ks = 0; ks < KS; ++ks) {
-    const int d0 = ks * 16 + 2 * t;
-    qa[ks][0] = ok0 ? *reinterpret_cast<const uint32_t*>(qb + (long long)r0 * p.q_rs + d0) : 0u;
-    qa[ks][1] = ok1 ? *reinterpret_cast<const uint32_t*>(qb + (long long)r1 * p.q_rs + d0) : 0u;
-    qa[ks][2] = ok0 ? *reinterpret_cast<const uint32_t*>(qb + (long long)r0 * p.q_rs + d0 + 8) : 0u;
-    qa[ks][3] = ok1 ? *reinterpret_cast<const uint32_t*>(qb + (long long)r1 * p.q_rs + d0 + 8) : 0u;
-  }
-  float s[2 * MMA_MAXKT][4];
+  for (int i = 0; i < 2 * KS; ++i) qa0[i] = qa1[i] = 0u;
+  if (ok0) load_words<KS>(qb + (long long)r0 * p.q_rs, qa0);
+  if (ok1) load_words<KS>(qb + (long long)r1 * p.q_rs, qa1);
+
+  float s[8 * MMA_MAXKB][4];
 #pragma unroll
-  for (int nt = 0; nt < 2 * MMA_MAXKT; ++nt) {
+  for (int nt = 0; nt < 8 * MMA_MAXKB; ++nt) {
     s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-    if (nt < 2 * nkt) {
+    if (nt < 8 * nkb) {
       const int j = nt * 8 + g;  // key row this lane feeds into the B fragment
-      const bf16* krow = kb + (long long)(j < nk ? j : 0) * p.k_rs;
+      uint32_t kw[2 * KS];
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 2 * t);
-        uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 2 * t + 8);
-        if (j >= nk) { b0 = 0u; b1 = 0u; }
-        mma_bf16_16816(s[nt], qa[ks], b0, b1);
-      }
+      for (int i = 0; i < 2 * KS; ++i) kw[i] = 0u;
+      if (j < nk) load_words<KS>(kb + (long long)j * p.k_rs, kw);
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        mma_bf16_16816(s[nt], qa0[2 * ks], qa1[2 * ks], qa0[2 * ks + 1], qa1[2 * ks + 1], kw[2 * ks], kw[2 * ks + 1]);
     }
   }
   const float hs = p.qscale * (p.head_scale != nullptr ? p.head_scale[w] : 1.0f);
   const unsigned char* km = p.key_mask != nullptr ? p.key_mask + (long long)b * p.mask_bs : nullptr;
   float m0 = -FLT_MAX, m1 = -FLT_MAX;
 #pragma unroll
-  for (int nt = 0; nt < 2 * MMA_MAXKT; ++nt) {
-    if (nt < 2 * nkt) {
+  for (int nt = 0; nt < 8 * MMA_MAXKB; ++nt) {
+    if (nt < 8 * nkb) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = nt * 8 + 2 * t + (e & 1);
@@ -117,17 +134,15 @@ __global__ void __launch_bounds__(256, 1) attn_dense_mma_kernel(const AttnParams
       m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
     }
   }
-  // exact fp32 null-key logit (always visible): partial dot over this lane's d values, quad reduce
+  // exact fp32 null-key logit (always visible): partial dot over this lane's d span, quad reduce
   float sn0 = 0.f, sn1 = 0.f;
   if (has_null) {
-    const float* nkp = p.null_k + w * DH;
+    const float* nkp = p.null_k + w * DH + SPAN * t;
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      const int d0 = ks * 16 + 2 * t;
-      const float2 a0 = unpack_bf16x2(qa[ks][0]), a1 = unpack_bf16x2(qa[ks][1]);
-      const float2 a2 = unpack_bf16x2(qa[ks][2]), a3 = unpack_bf16x2(qa[ks][3]);
-      sn0 += a0.x * nkp[d0] + a0.y * nkp[d0 + 1] + a2.x * nkp[d0 + 8] + a2.y * nkp[d0 + 9];
-      sn1 += a1.x * nkp[d0] + a1.y * nkp[d0 + 1] + a3.x * nkp[d0 + 8] + a3.y * nkp[d0 + 9];
+    for (int i = 0; i < 2 * KS; ++i) {
+      const float2 a0 = unpack_bf16x2(qa0[i]), a1 = unpack_bf16x2(qa1[i]);
+      sn0 += a0.x * nkp[2 * i] + a0.y * nkp[2 * i + 1];
+      sn1 += a1.x * nkp[2 * i] + a1.y * nkp[2 * i + 1];
     }
     sn0 += __shfl_xor_sync(0xffffffffu, sn0, 1); sn0 += __shfl_xor_sync(0xffffffffu, sn0, 2);
     sn1 += __shfl_xor_sync(0xffffffffu, sn1, 1); sn1 += __shfl_xor_sync(0xffffffffu, sn1, 2);
@@ -139,8 +154,8 @@ __global__ void __launch_bounds__(256, 1) attn_dense_mma_kernel(const AttnParams
   m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
   float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-  for (int nt = 0; nt < 2 * MMA_MAXKT; ++nt) {
-    if (nt < 2 * nkt) {
+  for (int nt = 0; nt < 8 * MMA_MAXKB; ++nt) {
+    if (nt < 8 * nkb) {
       s[nt][0] = __expf(s[nt][0] - m0); s[nt][1] = __expf(s[nt][1] - m0);
       s[nt][2] = __expf(s[nt][2] - m1); s[nt][3] = __expf(s[nt][3] - m1);
       l0 += s[nt][0] + s[nt][1];
@@ -159,8 +174,8 @@ __global__ void __launch_bounds__(256, 1) attn_dense_mma_kernel(const AttnParams
   const float i0 = 1.0f / l0, i1 = 1.0f / l1;
   bf16* Pw = P + (size_t)w * MMA_QT * PSTR;
 #pragma unroll
-  for (int nt = 0; nt < 2 * MMA_MAXKT; ++nt) {
-    if (nt < 2 * nkt) {
+  for (int nt = 0; nt < 8 * MMA_MAXKB; ++nt) {
+    if (nt < 8 * nkb) {
       *reinterpret_cast<uint32_t*>(Pw + (size_t)g * PSTR + nt * 8 + 2 * t) = pack_bf16x2(s[nt][0] * i0, s[nt][1] * i0);
       *reinterpret_cast<uint32_t*>(Pw + (size_t)(g + 8) * PSTR + nt * 8 + 2 * t) = pack_bf16x2(s[nt][2] * i1, s[nt][3] * i1);
     }
@@ -201,23 +216,26 @@ __global__ void __launch_bounds__(256, 1) attn_dense_mma_kernel(const AttnParams
     __syncthreads();
   }
 
-  // ---------------- phase 3: O_w = P'_w V_w ----------------
+  // ---------------- phase 3: O_w = P'_w V_w  (keys contracted in lane-owned 16-key spans) ----------------
   float o[ND][4];
 #pragma unroll
   for (int nd = 0; nd < ND; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
-  const bf16* vtb = vT + ((long long)b * H + w) * DH * jp;
-  for (int kt = 0; kt < nkt; ++kt) {
-    uint32_t a[4];
-    a[0] = *reinterpret_cast<const uint32_t*>(Pw + (size_t)g * PSTR + kt * 16 + 2 * t);
-    a[1] = *reinterpret_cast<const uint32_t*>(Pw + (size_t)(g + 8) * PSTR + kt * 16 + 2 * t);
-    a[2] = *reinterpret_cast<const uint32_t*>(Pw + (size_t)g * PSTR + kt * 16 + 2 * t + 8);
-    a[3] = *reinterpret_cast<const uint32_t*>(Pw + (size_t)(g + 8) * PSTR + kt * 16 + 2 * t + 8);
+  const bf16* vtb = vT + ((long long)b * H + w) * DH * jp + 16 * t;
+  for (int blk = 0; blk < nkb; ++blk) {
+    // A fragments of the 4 k-steps of this 64-key block: P'[row][64 blk + 16 t + 4 s + {0,1 | 2,3}]
+    uint2 pa0[4], pa1[4];
+#pragma unroll
+    for (int sidx = 0; sidx < 4; ++sidx) {
+      pa0[sidx] = *reinterpret_cast<const uint2*>(Pw + (size_t)g * PSTR + blk * 64 + 16 * t + 4 * sidx);
+      pa1[sidx] = *reinterpret_cast<const uint2*>(Pw + (size_t)(g + 8) * PSTR + blk * 64 + 16 * t + 4 * sidx);
+    }
 #pragma unroll
     for (int nd = 0; nd < ND; ++nd) {
-      const bf16* vrow = vtb + (long long)(nd * 8 + g) * jp + kt * 16 + 2 * t;
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vrow);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vrow + 8);
-      mma_bf16_16816(o[nd], a, b0, b1);
+      uint32_t vw[8];
+      load_words<4>(vtb + (long long)(nd * 8 + g) * jp + blk * 64, vw);
+#pragma unroll
+      for (int sidx = 0; sidx < 4; ++sidx)
+        mma_bf16_16816(o[nd], pa0[sidx].x, pa1[sidx].x, pa0[sidx].y, pa1[sidx].y, vw[2 * sidx], vw[2 * sidx + 1]);
     }
   }
   bf16* ob = reinterpret_cast<bf16*>(p.o) + (long long)b * p.o_bs + w * DH;
@@ -237,11 +255,13 @@ __global__ void __launch_bounds__(256, 1) attn_dense_mma_kernel(const AttnParams
 }
 
 // Returns NUWA_ERR_INVALID when the shape is outside this kernel's envelope (caller falls back to the
-// generic CUDA-core attention kernel).  vT_ws: workspace of B*H*dh*roundup(nk,16) bf16.
+// generic CUDA-core attention kernel).  vT_ws: workspace of B*H*dh*roundup(nk,64) bf16.
 int attn_dense_mma(const AttnParams& p, int nk, void* vT_ws, cudaStream_t stream) {
-  if (p.H > 8 || (p.dh != 64 && p.dh != 32) || nk <= 0 || nk > 16 * MMA_MAXKT || vT_ws == nullptr) return NUWA_ERR_INVALID;
-  if ((p.q_rs & 1) || (p.k_rs & 1) || (p.o_rs & 1)) return NUWA_ERR_INVALID;
-  const int jp = (nk + 15) / 16 * 16;
+  if (p.H > 8 || (p.dh != 64 && p.dh != 32) || nk <= 0 || nk > 64 * MMA_MAXKB || vT_ws == nullptr) return NUWA_ERR_INVALID;
+  // 16-byte vector loads of q / k rows
+  if ((p.q_rs % 8) || (p.k_rs % 8) || (p.q_bs % 8) || (p.k_bs % 8) || (p.o_rs & 1)) return NUWA_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(p.q) & 15) || (reinterpret_cast<uintptr_t>(p.k) & 15)) return NUWA_ERR_INVALID;
+  const int jp = (nk + 63) / 64 * 64;
   bf16* vT = reinterpret_cast<bf16*>(vT_ws);
   const long long total = (long long)p.B * p.H * p.dh * jp;
   int tgrid = (int)((total + 255) / 256);
@@ -251,7 +271,7 @@ int attn_dense_mma(const AttnParams& p, int nk, void* vT_ws, cudaStream_t stream
   NUWA_CHECK_LAUNCH();
   AttnParams q = p;
   q.nk_dense = nk;
-  const size_t smem = (size_t)p.H * MMA_QT * (jp + 8) * 2 + (size_t)p.H * MMA_QT * 4 + (size_t)p.H * p.H * 4;
+  const size_t smem = (size_t)p.H * MMA_QT * (jp + 4) * 2 + (size_t)p.H * MMA_QT * 4 + (size_t)p.H * p.H * 4;
   const int grid = p.B * ((p.nq + MMA_QT - 1) / MMA_QT);
   if (p.dh == 64) {
     if (smem > 48 * 1024)

@@ -65,6 +65,11 @@ int cross_entropy_mean(const float* logits, int ld, const long long* target, flo
                        int V, cudaStream_t stream);
 int sample_topk_gumbel(const float* cond, const float* uncond, const float* noise, long long* out, float* guided_out,
                        int B, int V, int k, float cond_scale, float temperature, cudaStream_t stream);
+int sample_topk_gumbel_at(const float* cond, const float* uncond, const float* noise, long long* out, long long out_bs,
+                          const int* step_ptr, int B, int V, int k, float cond_scale, float temperature,
+                          cudaStream_t stream);
+int cache_append(const void* row, void* cache, long long cache_bs, int width, int B, const int* t_ptr, cudaStream_t stream);
+int step_increment(int* t_ptr, cudaStream_t stream);
 // vae_ops.cu
 int nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, cudaStream_t stream);
 int nhwc_to_nchw_f32(const void* in, int in_is_bf16, float* out, int B, int C, int H, int W, cudaStream_t stream);

@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256) sandwich_ln_kernel(const LnParams p) {
   if (warp >= rows) return;
   const int b = warp / p.nt;
   const int tl = warp - b * p.nt;
-  const int t = p.t0 + tl;
+  const int t0 = p.t0_ptr != nullptr ? __ldg(p.t0_ptr) : p.t0;
+  const int t = t0 + tl;
   const int D = p.D;
   // number of float4 this lane owns: channels c = (lane + 32*i)*4
   int nv = 0;
@@ -107,6 +108,40 @@ __global__ void __launch_bounds__(256) sandwich_ln_kernel(const LnParams p) {
     if (col < p.fmap - 1 && t + 1 < p.a_npos) dst_w = t + 1;
   }
   bf16* abase = reinterpret_cast<bf16*>(p.a_out) + (long long)b * p.a_bs;
+  if (p.gather) {
+    // decode form (one CUDA graph replayed per token): fixed-address dense operand row; the shifted channels of
+    // position t were produced when positions t - fmap / t - 1 were decoded and wait in shift_cache.
+    bf16* sc = reinterpret_cast<bf16*>(p.shift_cache) + (long long)b * p.sc_bs;
+    const bool shifted = p.shift && t >= 1;
+    int src_h = -1, src_w = -1;
+    if (shifted) {
+      const int T = p.fmap * p.fmap;
+      const int pos = (t - 1) % T;
+      const int row = pos / p.fmap, col = pos - row * p.fmap;
+      if (row > 0) src_h = t - p.fmap;
+      if (col > 0) src_w = t - 1;
+    }
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv) {
+        const int c = (lane + 32 * i) * 4;
+        const float4 w = *reinterpret_cast<const float4*>(p.pre_w + c);
+        const float4 bb = *reinterpret_cast<const float4*>(p.pre_b + c);
+        uint2 pk;
+        pk.x = pack_bf16x2((v[i].x - mean) * rstd * w.x + bb.x, (v[i].y - mean) * rstd * w.y + bb.y);
+        pk.y = pack_bf16x2((v[i].z - mean) * rstd * w.z + bb.z, (v[i].w - mean) * rstd * w.w + bb.w);
+        uint2 outv = pk;
+        if (p.shift && c < 2 * q4) {
+          if (t < p.a_npos) *reinterpret_cast<uint2*>(sc + (long long)t * D + c) = pk;  // for the tokens to come
+          if (shifted) {
+            const int src = c < q4 ? src_h : src_w;
+            outv = src >= 0 ? *reinterpret_cast<const uint2*>(sc + (long long)src * D + c) : make_uint2(0u, 0u);
+          }
+        }
+        *reinterpret_cast<uint2*>(abase + (long long)tl * p.a_rs + c) = outv;
+      }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i)
     if (i < nv) {

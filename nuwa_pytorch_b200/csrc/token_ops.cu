@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.nt) return;
   const int b = row / p.nt, tl = row - b * p.nt;
-  const int t = p.t0 + tl;
+  const int t = (p.t0_ptr != nullptr ? __ldg(p.t0_ptr) : p.t0) + tl;
   float* out = p.out + (long long)row * p.D;
   if (p.has_bos && t == 0) {
     for (int c = lane * 4; c < p.D; c += 128)
@@ -156,13 +156,18 @@ __device__ __forceinline__ uint32_t f2ord(float f) {  // order-preserving float 
 __global__ void __launch_bounds__(256)
 sample_kernel(const float* __restrict__ cond, const float* __restrict__ uncond, const float* __restrict__ noise,
               long long* __restrict__ out, float* __restrict__ guided_out, int V, int k, float cond_scale,
-              float temperature) {
+              float temperature, const int* __restrict__ step_ptr, long long out_bs) {
   extern __shared__ float sl[];  // V guided logits
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_prefix, s_remaining;
   __shared__ float s_val[8];
   __shared__ int s_idx[8];
   const int b = blockIdx.x;
+  if (step_ptr != nullptr) {  // graph-replayed decode step: this step's noise slab and output column
+    const int step = __ldg(step_ptr);
+    noise += (long long)step * gridDim.x * V;
+    out += (long long)b * out_bs + step - b;  // so that out[b] below lands on out0[b*out_bs + step]
+  }
   const float* c = cond + (long long)b * V;
   const float* u = uncond ? uncond + (long long)b * V : nullptr;
   for (int i = threadIdx.x; i < V; i += blockDim.x) {
@@ -228,7 +233,47 @@ int sample_topk_gumbel(const float* cond, const float* uncond, const float* nois
   const size_t smem = (size_t)V * sizeof(float);
   if (smem > 200 * 1024) return NUWA_ERR_INVALID;
   if (smem > 48 * 1024) cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  sample_kernel<<<B, 256, smem, stream>>>(cond, uncond, noise, out, guided_out, V, k, cond_scale, temperature);
+  sample_kernel<<<B, 256, smem, stream>>>(cond, uncond, noise, out, guided_out, V, k, cond_scale, temperature, nullptr, 0);
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+
+int sample_topk_gumbel_at(const float* cond, const float* uncond, const float* noise, long long* out, long long out_bs,
+                          const int* step_ptr, int B, int V, int k, float cond_scale, float temperature,
+                          cudaStream_t stream) {
+  if (B <= 0 || V <= 0 || k <= 0 || k > V || step_ptr == nullptr) return NUWA_ERR_INVALID;
+  const size_t smem = (size_t)V * sizeof(float);
+  if (smem > 200 * 1024) return NUWA_ERR_INVALID;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  sample_kernel<<<B, 256, smem, stream>>>(cond, uncond, noise, out, nullptr, V, k, cond_scale, temperature, step_ptr, out_bs);
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+
+// cache[b][*t][0:width] = row[b][0:width]   (bf16; appends the decoded token's q|k|v to the KV cache)
+__global__ void __launch_bounds__(256)
+cache_append_kernel(const bf16* __restrict__ row, bf16* __restrict__ cache, long long cache_bs, int width, int B,
+                    const int* __restrict__ t_ptr) {
+  const int t = __ldg(t_ptr);
+  const int w8 = width / 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * w8; i += gridDim.x * blockDim.x) {
+    const int b = i / w8, c = (i - b * w8) * 8;
+    *reinterpret_cast<uint4*>(cache + (long long)b * cache_bs + (long long)t * width + c) =
+        *reinterpret_cast<const uint4*>(row + (long long)b * width + c);
+  }
+}
+int cache_append(const void* row, void* cache, long long cache_bs, int width, int B, const int* t_ptr, cudaStream_t stream) {
+  if (B <= 0 || width <= 0 || (width % 8) || t_ptr == nullptr) return NUWA_ERR_INVALID;
+  const int n = B * (width / 8);
+  cache_append_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(row), reinterpret_cast<bf16*>(cache),
+                                                            cache_bs, width, B, t_ptr);
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+__global__ void step_increment_kernel(int* t) { *t += 1; }
+int step_increment(int* t_ptr, cudaStream_t stream) {
+  if (t_ptr == nullptr) return NUWA_ERR_INVALID;
+  step_increment_kernel<<<1, 1, 0, stream>>>(t_ptr);
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
 }

@@ -127,8 +127,10 @@ def pack_stack(stack):
 class DecodeState:
     """Persistent per-stack buffers for incremental decoding of `npos` positions (bos + video tokens)."""
 
-    def __init__(self, pack, B, npos, device):
+    def __init__(self, pack, B, npos, device, t_dev=None):
         self.B, self.npos = B, npos
+        # current position as a device-side int32 scalar (shared by the two sweeps of a generate step)
+        self.t_dev = t_dev if t_dev is not None else torch.zeros(1, dtype=torch.int32, device=device)
         self.a, self.qkv, self.ctx_kv = {}, {}, {}
         for i, s in enumerate(pack.subs):
             if s.shift:
@@ -150,6 +152,16 @@ class Context:
         return c
 
 
+def prime_context(stack, context):
+    """Project the context to K/V for every cross-attention sub-block now (they are constant over a generate() call),
+    so that a decode step allocates nothing context dependent and can be captured in a CUDA graph."""
+    pack = pack_stack(stack)
+    B, nk = context.ctx16.shape[:2]
+    for i, s in enumerate(pack.subs):
+        if s.kind in ('cross', 'x2dna') and i not in context.kv:
+            context.kv[i] = ops.gemm(context.ctx16.view(B * nk, -1), s.w_kv, out_dtype=torch.bfloat16)
+
+
 def _run_sub(i, s, a, B, nt, t0, npos, D, state, context, key_mask, rotary):
     """a: bf16 operand rows as a 2-D (B*nt, D) view (row stride may exceed D in decode mode).  Returns y fp32 (B*nt, D)."""
     dev = a.device
@@ -165,11 +177,13 @@ def _run_sub(i, s, a, B, nt, t0, npos, D, state, context, key_mask, rotary):
             ops.attn_sparse3dna(qkv, o, B=B, nq=nt, t0=0, npos=nt, H=H, dh=dh, talk=s.talk, fmap=s.fmap,
                                 max_frames=s.max_frames, nv=nt - 1, kernel=s.kernel, dilation=s.dilation, causal=s.causal)
         else:
+            # decode step: every address is position independent (the position lives in state.t_dev on the device),
+            # so the whole step can be captured once in a CUDA graph and replayed per token
             cache = state.qkv[i]
-            ops.gemm(a, s.w_qkv, out=cache[:, t0, :])  # new token's q|k|v rows land in the cache
-            ops.attn_sparse3dna(cache, o, B=B, nq=1, t0=t0, npos=npos, H=H, dh=dh, talk=s.talk, fmap=s.fmap,
-                                max_frames=s.max_frames, nv=t0, kernel=s.kernel, dilation=s.dilation, causal=s.causal,
-                                o_bs=inner)
+            row = ops.gemm(a, s.w_qkv, out_dtype=torch.bfloat16)     # (B, 3*inner): the new token's q|k|v
+            ops.cache_append(row, cache, state.t_dev)                 # KV cache row t
+            ops.attn_sparse3dna_decode(row, cache, o, state.t_dev, B=B, npos=npos, H=H, dh=dh, talk=s.talk, fmap=s.fmap,
+                                       max_frames=s.max_frames, kernel=s.kernel, dilation=s.dilation, causal=s.causal)
         return ops.gemm(o, s.w_out, bias=s.b_out, out_dtype=torch.float32)
     if s.kind == 'self':
         assert state is None, 'dense self-attention stacks (text encoder) run in full mode only'
@@ -226,13 +240,18 @@ def run_stack(stack, x, *, context=None, key_mask=None, rotary=None, state=None,
         streams = [x.view(B * nt, D).clone()]
     subs = pack.subs
 
+    t_dev = state.t_dev if state is not None else None
+
     def operand_buffer(i):
         """bf16 operand buffer of sub-block i and its addressing for sandwich_ln stage B."""
         s = subs[i]
-        if state is not None and s.shift:
-            buf = state.a[i]
-            return buf, dict(a_out=buf, a_bs=npos * D, a_rs=D, a_t0=0, a_npos=npos), buf[:, t0, :]
         buf = torch.empty(B, nt, D, dtype=torch.bfloat16, device=x.device)
+        if state is not None:
+            # decode: dense fixed-address operand row; the token shift is a gather from the persistent shift cache
+            addr = dict(a_out=buf, a_bs=D, a_rs=D, a_t0=0, a_npos=npos, gather=True, t_dev=t_dev)
+            if s.shift:
+                addr.update(shift_cache=state.a[i], sc_bs=npos * D)
+            return buf, addr, buf.view(B, D)
         return buf, dict(a_out=buf, a_bs=nt * D, a_rs=D, a_t0=t0, a_npos=t0 + nt), buf.view(B * nt, D)
 
     # first sub-block: pre-norm only
@@ -249,7 +268,7 @@ def run_stack(stack, x, *, context=None, key_mask=None, rotary=None, state=None,
             ops.sandwich_ln(B, nt, D, y=y, post=s.post, res_in=tgt, x_out=tgt, pre=nxt.pre, shift=nxt.shift,
                             fmap=nxt.fmap or 0, t0=t0, **addr)
         else:
-            ops.sandwich_ln(B, nt, D, y=y, post=s.post, res_in=tgt, x_out=tgt, t0=t0)
+            ops.sandwich_ln(B, nt, D, y=y, post=s.post, res_in=tgt, x_out=tgt, t0=t0, t_dev=t_dev)
     b2 = streams[1] if pack.reversible else None
     o32, o16 = ops.stable_ln(streams[0], pack.norm_w, pack.norm_b, b2=b2, want_f32=True, want_bf16=want_bf16)
     o32 = o32.view(B, nt, D)

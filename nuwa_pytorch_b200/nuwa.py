@@ -317,10 +317,10 @@ def _top_k_count(num_logits, thres):
 # shared decoder logic of NUWA and NUWASketch
 # ------------------------------------------------------------------------------------------------
 class _VideoDecoderMixin:
-    def _embed_video(self, indices, nt, t0=0):
+    def _embed_video(self, indices, nt, t0=0, t_dev=None):
         """bos + image_embedding + axial positions for positions [t0, t0+nt)  (:1940-1944 / :1879-1881)."""
         return ops.embed_tokens(indices.contiguous(), self.image_embedding.embed.weight.detach().float().contiguous(),
-                                nt=nt, t0=t0, bos=self.video_bos.detach().float().contiguous(),
+                                nt=nt, t0=t0, t_dev=t_dev, bos=self.video_bos.detach().float().contiguous(),
                                 axials=self.video_pos_emb.tables(), dims=self.video_pos_emb.full_shape)
 
     def _logits_weight(self):
@@ -343,8 +343,11 @@ class _VideoDecoderMixin:
 
     @torch.no_grad()
     def _generate_indices(self, context, batch, *, num_frames, filter_thres, temperature, cond_scale, noise=None,
-                          return_step_logits=False):
-        """Autoregressive loop (:1858-1908 / :2455-2505), one token per step, KV-cached."""
+                          return_step_logits=False, use_graph=True):
+        """Autoregressive loop (:1858-1908 / :2455-2505), one token per step, KV-cached.
+
+        Incremental mode keeps the position in a device scalar, so ONE decode step (both guidance sweeps, sampling,
+        position increment) is captured in a CUDA graph and replayed for every token (dense-context decoders)."""
         dev = self.video_bos.device
         T = self.video_fmap_size ** 2
         total = T * num_frames
@@ -353,39 +356,63 @@ class _VideoDecoderMixin:
         k = _top_k_count(V, filter_thres)
         video_indices = torch.zeros(batch, total, dtype=torch.int64, device=dev)
         pack = engine.pack_stack(self.video_transformer)
-        incremental = total <= max_tokens
-        if incremental:
-            st_c = engine.DecodeState(pack, batch, total, dev)
-            st_u = engine.DecodeState(pack, batch, total, dev) if cond_scale != 1 else None
         uncond_ctx = context.with_mask(torch.zeros_like(context.mask)) if cond_scale != 1 else None
         w_log = self._logits_weight()
         step_logits = []
-        for ind in range(total):
-            if incremental:
-                x = self._embed_video(video_indices, 1, t0=ind)
+        if total <= max_tokens:
+            t_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            st_c = engine.DecodeState(pack, batch, total, dev, t_dev)
+            st_u = engine.DecodeState(pack, batch, total, dev, t_dev) if cond_scale != 1 else None
+            engine.prime_context(self.video_transformer, context)
+            noise_all = noise if noise is not None else torch.rand(total, batch, V, device=dev)
+            noise_all = noise_all.contiguous()
+
+            def step(ind):
+                x = self._embed_video(video_indices, 1, t0=ind, t_dev=t_dev)
                 y32, y16 = engine.run_stack(self.video_transformer, x, context=context, state=st_c, t0=ind, want_bf16=True)
                 logits = ops.gemm(y16.view(batch, -1), w_log, out_dtype=torch.float32)
                 ulogits = None
                 if cond_scale != 1:
                     # the reference feeds the conditional sweep's OUTPUT to the second sweep
-                    _, u16 = engine.run_stack(self.video_transformer, y32, context=uncond_ctx, state=st_u, t0=ind, want_bf16=True)
+                    _, u16 = engine.run_stack(self.video_transformer, y32, context=uncond_ctx, state=st_u, t0=ind,
+                                              want_bf16=True)
                     ulogits = ops.gemm(u16.view(batch, -1), w_log, out_dtype=torch.float32)
+                if return_step_logits:
+                    step_logits.append(logits if ulogits is None else ulogits + (logits - ulogits) * cond_scale)
+                ops.sample_topk_gumbel_at(logits, ulogits, noise_all, video_indices, t_dev, k, cond_scale, temperature)
+                ops.step_increment(t_dev)
+
+            graphable = use_graph and not return_step_logits and all(s.kind != 'x2dna' for s in pack.subs)
+            if graphable and total > 2:
+                step(0)  # eager warm-up: sizes every kernel's attributes / workspaces; its writes are redone by replay 0
+                t_dev.zero_()
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    step(0)
+                for _ in range(total):
+                    graph.replay()
             else:
-                # look-back window beyond max_video_frames (:1873-1877): positions shift every frame, so the window is
-                # re-evaluated in full (reference semantics; rare path)
-                window = video_indices[:, :ind]
-                if ind > max_tokens:
-                    cur = ind % T
-                    lookback = (self.max_video_frames - (0 if cur == 0 else 1)) * T + cur
-                    window = window[:, -lookback:]
-                n = window.shape[1] + 1
-                x = self._embed_video(window, n)
-                y32, y16 = engine.run_stack(self.video_transformer, x, context=context, want_bf16=True)
-                logits = ops.gemm(y16[:, -1].contiguous(), w_log, out_dtype=torch.float32)
-                ulogits = None
-                if cond_scale != 1:
-                    _, u16 = engine.run_stack(self.video_transformer, y32, context=uncond_ctx, want_bf16=True)
-                    ulogits = ops.gemm(u16[:, -1].contiguous(), w_log, out_dtype=torch.float32)
+                for ind in range(total):
+                    step(ind)
+            return (video_indices, step_logits) if return_step_logits else video_indices
+
+        for ind in range(total):
+            # look-back window beyond max_video_frames (:1873-1877): positions shift every frame, so the window is
+            # re-evaluated in full each step (reference semantics; rare path, only when num_frames > max_video_frames)
+            window = video_indices[:, :ind]
+            if ind > max_tokens:
+                cur = ind % T
+                lookback = (self.max_video_frames - (0 if cur == 0 else 1)) * T + cur
+                window = window[:, -lookback:]
+            n = window.shape[1] + 1
+            x = self._embed_video(window, n)
+            y32, y16 = engine.run_stack(self.video_transformer, x, context=context, want_bf16=True)
+            logits = ops.gemm(y16[:, -1].contiguous(), w_log, out_dtype=torch.float32)
+            ulogits = None
+            if cond_scale != 1:
+                _, u16 = engine.run_stack(self.video_transformer, y32, context=uncond_ctx, want_bf16=True)
+                ulogits = ops.gemm(u16[:, -1].contiguous(), w_log, out_dtype=torch.float32)
             u = noise[ind] if noise is not None else torch.rand(batch, V, device=dev)
             res = ops.sample_topk_gumbel(logits, ulogits, u, k, cond_scale, temperature, want_guided=return_step_logits)
             if return_step_logits:
@@ -490,12 +517,12 @@ class NUWA(nn.Module, _VideoDecoderMixin):
     @torch.no_grad()
     @_eval_decorator
     def generate(self, *, text, filter_thres=0.9, temperature=1., decode_max_batchsize=10, cond_scale=2., num_frames=None,
-                 _noise=None, _return_indices=False):
+                 _noise=None, _return_indices=False, _use_graph=True):
         batch = text.shape[0]
         context = self._text_context(text, text != 0)
         num_frames = num_frames if _exists(num_frames) else self.max_video_frames
         idx = self._generate_indices(context, batch, num_frames=num_frames, filter_thres=filter_thres,
-                                     temperature=temperature, cond_scale=cond_scale, noise=_noise)
+                                     temperature=temperature, cond_scale=cond_scale, noise=_noise, use_graph=_use_graph)
         if _return_indices:
             return idx
         return self._indices_to_video(idx, decode_max_batchsize)
@@ -607,7 +634,7 @@ class NUWASketch(nn.Module, _VideoDecoderMixin):
         context = self._sketch_context(sketch, sketch_mask)
         num_frames = num_frames if _exists(num_frames) else self.max_video_frames
         idx = self._generate_indices(context, batch, num_frames=num_frames, filter_thres=filter_thres,
-                                     temperature=temperature, cond_scale=cond_scale, noise=_noise)
+                                     temperature=temperature, cond_scale=cond_scale, noise=_noise, use_graph=_use_graph)
         if _return_indices:
             return idx
         return self._indices_to_video(idx, decode_max_batchsize)

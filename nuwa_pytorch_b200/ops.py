@@ -111,9 +111,12 @@ def conv2d_nhwc(x, wp, Cin, ksize, stride=1, bias=None, residual=None, act=None,
 # norms
 # ------------------------------------------------------------------------------------------------
 def sandwich_ln(B, nt, D, *, y=None, post=None, res_in=None, x_out=None, x_out_bf16=None, pre=None, a_out=None,
-                a_bs=0, a_rs=0, a_t0=0, a_npos=0, shift=False, fmap=0, t0=0):
-    """See nuwa_sandwich_ln in include/nuwa_b200.h.  post / pre: (weight, bias) fp32 tensors or None."""
+                a_bs=0, a_rs=0, a_t0=0, a_npos=0, shift=False, fmap=0, t0=0, t_dev=None, gather=False, shift_cache=None,
+                sc_bs=0):
+    """See nuwa_sandwich_ln in include/nuwa_b200.h.  post / pre: (weight, bias) fp32 tensors or None.
+    t_dev: int32 device scalar holding the position (graph-replayed decode); gather: decode form of the shift."""
     p = _lib.LnParams()
+    p.t0_ptr, p.gather, p.shift_cache, p.sc_bs = ptr(t_dev), int(bool(gather)), ptr(shift_cache), sc_bs
     p.y, p.res_in, p.x_out, p.x_out_bf16 = ptr(y), ptr(res_in), ptr(x_out), ptr(x_out_bf16)
     p.post_w, p.post_b = (ptr(post[0]), ptr(post[1])) if post is not None else (None, None)
     p.pre_w, p.pre_b = (ptr(pre[0]), ptr(pre[1])) if pre is not None else (None, None)
@@ -163,6 +166,40 @@ def attn_sparse3dna(qkv, o, *, B, nq, t0, npos, H, dh, talk, fmap, max_frames, n
     check(lib().nuwa_attn_sparse3dna(p, stream()), "nuwa_attn_sparse3dna")
 
 
+def attn_sparse3dna_decode(q_row, cache, o, t_dev, *, B, npos, H, dh, talk, fmap, max_frames, kernel, dilation, causal):
+    """Graph-replayable decode step: q_row (B, 3*H*dh) bf16 holds the new token's q|k|v (its k|v must already be in
+    `cache` (B, npos, 3*H*dh)); the position is read from the int32 device scalar t_dev."""
+    inner = H * dh
+    base = cache.data_ptr()
+    p = _attn_base(q_row.data_ptr(), base + inner * 2, base + 2 * inner * 2, ptr(o), B, 1, 0, H, dh, 3 * inner,
+                   npos * 3 * inner, npos * 3 * inner, inner, 3 * inner, 3 * inner, 3 * inner, inner, talk)
+    p.t0_ptr = ptr(t_dev)
+    p.fmap, p.max_frames, p.nv = fmap, max_frames, 0
+    p.kt, p.kh, p.kw = kernel
+    p.dt, p.dh_, p.dw = dilation
+    p.causal = int(bool(causal))
+    p.jmax = 1 + kernel[0] * kernel[1] * kernel[2]
+    check(lib().nuwa_attn_sparse3dna(p, stream()), "nuwa_attn_sparse3dna")
+
+
+def cache_append(row, cache, t_dev):
+    """cache[b, *t_dev, :] = row[b, :]  (bf16)."""
+    B, npos, width = cache.shape
+    check(lib().nuwa_cache_append(ptr(row), ptr(cache), npos * width, width, B, ptr(t_dev), stream()), "nuwa_cache_append")
+
+
+def step_increment(t_dev):
+    check(lib().nuwa_step_increment(ptr(t_dev), stream()), "nuwa_step_increment")
+
+
+def sample_topk_gumbel_at(cond, uncond, noise_all, out_seq, t_dev, k, cond_scale, temperature):
+    """noise_all: (steps, B, V) fp32; out_seq: (B, steps) int64; the step index is read from t_dev on the device."""
+    B, V = cond.shape
+    check(lib().nuwa_sample_topk_gumbel_at(ptr(cond), ptr(uncond), ptr(noise_all), ptr(out_seq), out_seq.stride(0),
+                                           ptr(t_dev), B, V, k, float(cond_scale), float(temperature), stream()),
+          "nuwa_sample_topk_gumbel_at")
+
+
 def attn_dense(q_ptr, k_ptr, v_ptr, o, *, B, nq, nk, H, dh, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, talk=None,
                null_k=None, null_v=None, key_mask=None, head_scale=None, bias=None, qscale=None, t0=0, use_mma=True):
     p = _attn_base(q_ptr, k_ptr, v_ptr, ptr(o) if torch.is_tensor(o) else o, B, nq, t0, H, dh, q_bs, k_bs, v_bs, o_bs,
@@ -180,7 +217,7 @@ def attn_dense(q_ptr, k_ptr, v_ptr, o, *, B, nq, nk, H, dh, q_bs, q_rs, k_bs, k_
     ws = None
     if use_mma and nq >= 8 and nk <= 256 and dh in (32, 64) and H <= 8:
         dev = o.device if torch.is_tensor(o) else torch.device('cuda')
-        ws = torch.empty(B * H * dh * _round_up(nk, 16), dtype=torch.bfloat16, device=dev)
+        ws = torch.empty(B * H * dh * _round_up(nk, 64), dtype=torch.bfloat16, device=dev)
     check(lib().nuwa_attn_dense(p, ptr(ws), stream()), "nuwa_attn_dense")
 
 
@@ -199,7 +236,7 @@ def attn_cross2dna(q_ptr, k_ptr, v_ptr, o_ptr, *, B, nq, t0, H, dh, q_bs, q_rs, 
 # ------------------------------------------------------------------------------------------------
 # token level
 # ------------------------------------------------------------------------------------------------
-def embed_tokens(idx, table, *, nt, t0=0, bos=None, axials=(None, None, None), dims=(1, 1, 1)):
+def embed_tokens(idx, table, *, nt, t0=0, bos=None, axials=(None, None, None), dims=(1, 1, 1), t_dev=None):
     """out[b, tl] for absolute position t0+tl (see nuwa_embed_tokens).  idx: int64 (B, n_idx) contiguous."""
     B = idx.shape[0]
     D = table.shape[1]
@@ -209,6 +246,7 @@ def embed_tokens(idx, table, *, nt, t0=0, bos=None, axials=(None, None, None), d
     p.ax1, p.ax2, p.ax3 = (ptr(a) for a in axials)
     p.d2, p.d3 = dims[1], dims[2]
     p.has_bos, p.t0, p.B, p.nt, p.D = int(bos is not None), t0, B, nt, D
+    p.t0_ptr = ptr(t_dev)
     check(lib().nuwa_embed_tokens(p, stream()), "nuwa_embed_tokens")
     return out
 

@@ -66,6 +66,8 @@ def test_nuwa_rev_forward_and_incremental_generate_logits(cuda_device):
     w = model._logits_weight()
     worst = 0.0
     for t in range(41):
+        st_c.t_dev.fill_(t)  # decode kernels read the position from device memory
+        st_u.t_dev.fill_(t)
         x = model._embed_video(seq, 1, t0=t)
         y32, y16 = engine.run_stack(model.video_transformer, x, context=context, state=st_c, t0=t, want_bf16=True)
         lc = ops.gemm(y16.view(2, -1), w, out_dtype=torch.float32)
@@ -86,6 +88,9 @@ def test_generate_runs_and_matches_oracle_sampling(cuda_device):
     noise = torch.rand(32, 2, 64, generator=g).to(cuda_device)
     idx = model.generate(text=text, num_frames=2, _noise=noise, _return_indices=True)
     assert idx.shape == (2, 32) and idx.dtype == torch.int64 and int(idx.max()) < 64
+    # the CUDA-graph replayed decode loop and the eager loop are the same computation
+    idx_eager = model.generate(text=text, num_frames=2, _noise=noise, _return_indices=True, _use_graph=False)
+    assert torch.equal(idx, idx_eager)
     video = model.generate(text=text, num_frames=2, _noise=noise)
     assert video.shape == (2, 2, 3, 64, 64) and torch.isfinite(video).all()
     # replay on the oracle with the SAME sampled prefix: each step's sampled token must be the oracle's choice
