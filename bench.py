@@ -306,7 +306,49 @@ def run_ours(args):
                                    backward="not included (forward loss only; autograd kernels are next-round work)"),
                        flops=dict(mflop_per_token_fwd=104.4,
                                   achieved_tflops=round(world * ntok * args.steps / dsec * 104.4e6 / 1e12 / world, 1)))
-        del nuwa
+        del nuwa, graphed
+        torch.cuda.empty_cache()
+
+    # -------- generate() (configs[3]): depth-64 reversible decoder, 5 frames = 1280 AR steps, KV-cached, --------
+    # -------- one CUDA-graph replay per token (both guidance sweeps + sampling inside the graph)          --------
+    generate = None
+    if not args.skip_generate:
+        from nuwa_pytorch_b200 import NUWA, VQGanVAE
+        torch.manual_seed(0)
+        with torch.device(dev):
+            gvae = VQGanVAE(**DEC_VAE_KW)
+            gnuwa = NUWA(vae=gvae, **{**DEC_KW, "dec_depth": 64, "dec_reversible": True}).eval()
+        gt = torch.Generator(device=dev).manual_seed(200 + rank)
+        gtext = torch.randint(1, 49408, (DEC_BATCH, 256), device=dev, generator=gt)
+        frames = args.gen_frames
+        with torch.no_grad():
+            gnuwa.generate(text=gtext, num_frames=1, _return_indices=True)  # warm-up (packs weights)
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c = torch.cuda.Event(enable_timing=True)
+            a.record()
+            idx = gnuwa.generate(text=gtext, num_frames=frames, _return_indices=True)
+            b.record()
+            vid = gnuwa._indices_to_video(idx, 10)
+            c.record()
+            torch.cuda.synchronize()
+        t_ar, t_dec = a.elapsed_time(b) / 1e3, b.elapsed_time(c) / 1e3
+        if dist is not None:
+            tt = torch.tensor([t_ar, t_dec], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_ar, t_dec = float(tt[0]), float(tt[1])
+        ntok = DEC_BATCH * frames * 256
+        generate = dict(metric="generate(): sampled video-tokens/sec (AR loop) and decoded frames/sec",
+                        tokens_per_s=round(world * ntok / t_ar, 1), ms_per_token_step=round(1e3 * t_ar / (frames * 256), 3),
+                        vae_decode_frames_per_s=round(world * DEC_BATCH * frames / t_dec, 1),
+                        config=dict(workload="NUWA dim=512 dec_depth=64 dec_reversible=True, generate(num_frames=%d), "
+                                    "cond_scale=2 (two sweeps per token, SURVEY D8), filter_thres=0.9 (BASELINE configs[3])"
+                                    % frames, batch_per_gpu=DEC_BATCH, steps=frames * 256, video_shape=list(vid.shape),
+                                    launch="KV-cached incremental decode, one CUDA graph replay per token"))
+        del gnuwa, gvae, idx, vid
+        torch.cuda.empty_cache()
 
     # -------- CPU baseline (rank 0, N == 1 only): the reference algorithm's CPU path, bounded sample --------
     cpu = None
@@ -329,7 +371,7 @@ def run_ours(args):
                     e2e=dict(value=round(fps_e2e, 2), unit="frames/s", h2d_bytes_per_step=int(host_in.numel() * 4),
                              d2h_bytes_per_step=int(host_out.numel() * 4)),
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, clocks=clocks.summary(),
-                    decoder=decoder)
+                    decoder=decoder, generate=generate)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -343,6 +385,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--vae-batch", type=int, default=VAE_BATCH)
     ap.add_argument("--skip-decoder", action="store_true")
+    ap.add_argument("--skip-generate", action="store_true")
+    ap.add_argument("--gen-frames", type=int, default=5)
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -322,12 +322,185 @@ static int launch_attn(const AttnParams& p, cudaStream_t stream) {
   return NUWA_OK;
 }
 
-int attn_sparse3dna(const AttnParams& p, cudaStream_t s) { return launch_attn<MODE_3DNA, 1>(p, s); }
+int attn_decode_sparse3dna(const AttnParams& p, cudaStream_t s);
+int attn_decode_dense(const AttnParams& p, cudaStream_t s);
+int attn_decode_cross2dna(const AttnParams& p, cudaStream_t s);
+
+int attn_sparse3dna(const AttnParams& p, cudaStream_t s) {
+  if (p.nq == 1) {
+    const int rc = attn_decode_sparse3dna(p, s);
+    if (rc != NUWA_ERR_INVALID) return rc;
+  }
+  return launch_attn<MODE_3DNA, 1>(p, s);
+}
 int attn_dense(const AttnParams& p, cudaStream_t s) {
   // several queries per warp amortise every K/V row load; single-query decode steps use QPW=1
   if (p.nq >= 4) return launch_attn<MODE_DENSE, 4>(p, s);
+  if (p.nq == 1) {
+    const int rc = attn_decode_dense(p, s);
+    if (rc != NUWA_ERR_INVALID) return rc;
+  }
   return launch_attn<MODE_DENSE, 1>(p, s);
 }
-int attn_cross2dna(const AttnParams& p, cudaStream_t s) { return launch_attn<MODE_X2DNA, 1>(p, s); }
+int attn_cross2dna(const AttnParams& p, cudaStream_t s) {
+  if (p.nq == 1) {
+    const int rc = attn_decode_cross2dna(p, s);
+    if (rc != NUWA_ERR_INVALID) return rc;
+  }
+  return launch_attn<MODE_X2DNA, 1>(p, s);
+}
+
+}  // namespace nuwa
+
+// ================================================================================================
+// Decode-step attention (one query position per sample): the single-query problem has no query
+// parallelism, so the KEYS are spread over the lanes instead -- lane j scores key j with the whole
+// head vector in registers, the softmax is a warp reduction, the talking-heads mix goes through
+// shared memory, and PV gives every lane dh/32 output channels with coalesced V row reads.
+// grid = B, block = 32*H (warp = head).  Used by generate() (Sparse3DNA / dense / cross-2DNA).
+// ================================================================================================
+namespace nuwa {
+
+template <int MODE, int DH>
+__global__ void __launch_bounds__(256) attn_decode_kernel(const AttnParams p) {
+  extern __shared__ float smem_d[];
+  const int H = p.H, J = p.jmax;
+  float* P = smem_d;                                  // [H][J]
+  float* Wt = P + (size_t)H * J;                      // [H][H]
+  int* keys = reinterpret_cast<int*>(Wt + H * H);     // [J]
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const int t0 = p.t0_ptr != nullptr ? __ldg(p.t0_ptr) : p.t0;
+  const int nv = (p.t0_ptr != nullptr && MODE == MODE_3DNA) ? t0 : p.nv;
+  const bf16* kb = reinterpret_cast<const bf16*>(p.k) + (long long)b * p.k_bs;
+  const bf16* vb = reinterpret_cast<const bf16*>(p.v) + (long long)b * p.v_bs;
+  const bf16* qb = reinterpret_cast<const bf16*>(p.q) + (long long)b * p.q_bs;
+  bf16* ob = reinterpret_cast<bf16*>(p.o) + (long long)b * p.o_bs;
+  constexpr int DPL = DH / 32;  // output channels per lane
+  if (MODE == MODE_3DNA && t0 == 0) {  // bos attends only to itself
+    for (int c = threadIdx.x; c < H * DH; c += blockDim.x) ob[c] = vb[c];
+    return;
+  }
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    int row = 0;
+    const int kind = key_of<MODE>(p, b, t0, nv, j, row);
+    keys[j] = (kind << 28) | row;
+  }
+  if (p.talk != nullptr)
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) Wt[i] = p.talk[i];
+  __syncthreads();
+  // ---- scores: lane j <-> key j ----
+  float qf[DH];
+  {
+    const bf16* qh = qb + w * DH;
+#pragma unroll
+    for (int i = 0; i < DH / 8; ++i) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(qh) + i);
+      const float2 a = unpack_bf16x2(u.x), bq = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      qf[i * 8 + 0] = a.x; qf[i * 8 + 1] = a.y; qf[i * 8 + 2] = bq.x; qf[i * 8 + 3] = bq.y;
+      qf[i * 8 + 4] = c.x; qf[i * 8 + 5] = c.y; qf[i * 8 + 6] = d.x; qf[i * 8 + 7] = d.y;
+    }
+  }
+  const float hs = p.qscale * (p.head_scale != nullptr ? p.head_scale[w] : 1.0f);
+  float* Pw = P + (size_t)w * J;
+  float m = -FLT_MAX;
+  for (int j = lane; j < J; j += 32) {
+    const int kj = keys[j];
+    const int row = kj & 0x0FFFFFFF, kind = kj >> 28;
+    float s;
+    if (kind == KEY_NORMAL) {
+      const bf16* kr = kb + (long long)row * p.k_rs + w * DH;
+      s = 0.f;
+#pragma unroll
+      for (int i = 0; i < DH / 8; ++i) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(kr) + i);
+        const float2 a = unpack_bf16x2(u.x), bq = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        s += qf[i * 8 + 0] * a.x + qf[i * 8 + 1] * a.y + qf[i * 8 + 2] * bq.x + qf[i * 8 + 3] * bq.y +
+             qf[i * 8 + 4] * c.x + qf[i * 8 + 5] * c.y + qf[i * 8 + 6] * d.x + qf[i * 8 + 7] * d.y;
+      }
+      s *= hs;
+    } else if (kind == KEY_NULL) {
+      const float* nk = p.null_k + w * DH;
+      s = 0.f;
+#pragma unroll
+      for (int i = 0; i < DH; ++i) s += qf[i] * __ldg(nk + i);
+      s *= hs;
+    } else {
+      s = (kind == KEY_MASKED) ? -FLT_MAX : 0.f;
+    }
+    if (kind != KEY_MASKED && p.bias != nullptr) s += p.bias[((long long)w * p.bias_nq + (t0 < p.bias_nq ? t0 : 0)) * p.bias_nk + j];
+    Pw[j] = s;
+    m = fmaxf(m, s);
+  }
+  m = warp_max(m);
+  float l = 0.f;
+  for (int j = lane; j < J; j += 32) {
+    const float e = __expf(Pw[j] - m);
+    Pw[j] = e;
+    l += e;
+  }
+  l = warp_sum(l);
+  const float inv = 1.0f / l;
+  for (int j = lane; j < J; j += 32) Pw[j] *= inv;
+  __syncthreads();
+  // ---- talking heads ----
+  if (p.talk != nullptr) {
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+      float pin[8];
+      for (int h = 0; h < H; ++h) pin[h] = P[(size_t)h * J + j];
+      for (int g = 0; g < H; ++g) {
+        float a = 0.f;
+        for (int h = 0; h < H; ++h) a = fmaf(Wt[g * H + h], pin[h], a);
+        P[(size_t)g * J + j] = a;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- PV: lane owns DPL consecutive output channels of head w ----
+  float acc[DPL];
+#pragma unroll
+  for (int c = 0; c < DPL; ++c) acc[c] = 0.f;
+  const int ch = w * DH + lane * DPL;
+#pragma unroll 4
+  for (int j = 0; j < J; ++j) {
+    const int kj = keys[j];
+    const int row = kj & 0x0FFFFFFF, kind = kj >> 28;
+    if (kind == KEY_MASKED || kind == KEY_ZERO) continue;
+    const float pj = Pw[j];
+    if (kind == KEY_NULL) {
+#pragma unroll
+      for (int c = 0; c < DPL; ++c) acc[c] = fmaf(pj, __ldg(p.null_v + ch + c), acc[c]);
+    } else {
+      float vf[DPL];
+      load_row<DPL>(vb + (long long)row * p.v_rs + ch, vf);
+#pragma unroll
+      for (int c = 0; c < DPL; ++c) acc[c] = fmaf(pj, vf[c], acc[c]);
+    }
+  }
+  store_row<DPL>(ob + ch, acc);
+}
+
+template <int MODE>
+static int launch_attn_decode(const AttnParams& p, cudaStream_t stream) {
+  if (p.nq != 1 || p.H > 8 || (p.dh != 64 && p.dh != 32)) return NUWA_ERR_INVALID;
+  if ((p.k_rs % 8) || (p.q_rs % 8) || (p.k_bs % 8) || (p.q_bs % 8)) return NUWA_ERR_INVALID;
+  const size_t smem = ((size_t)p.H * p.jmax + p.H * p.H + p.jmax) * sizeof(float);
+  if (smem > 200 * 1024) return NUWA_ERR_INVALID;
+  if (p.dh == 64) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(attn_decode_kernel<MODE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attn_decode_kernel<MODE, 64><<<p.B, 32 * p.H, smem, stream>>>(p);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(attn_decode_kernel<MODE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attn_decode_kernel<MODE, 32><<<p.B, 32 * p.H, smem, stream>>>(p);
+  }
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+
+int attn_decode_sparse3dna(const AttnParams& p, cudaStream_t s) { return launch_attn_decode<MODE_3DNA>(p, s); }
+int attn_decode_dense(const AttnParams& p, cudaStream_t s) { return launch_attn_decode<MODE_DENSE>(p, s); }
+int attn_decode_cross2dna(const AttnParams& p, cudaStream_t s) { return launch_attn_decode<MODE_X2DNA>(p, s); }
 
 }  // namespace nuwa

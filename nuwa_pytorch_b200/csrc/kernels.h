@@ -40,6 +40,9 @@ int device_sm_count();
 int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
               const float* residual, int ld_res, float* out_f32, void* out_bf16, int ld_out, int act, int force_bn,
               cudaStream_t stream);
+int gemm_skinny(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                const float* residual, int ld_res, float* out_f32, void* out_bf16, int ld_out, int act,
+                cudaStream_t stream);  // gemm_skinny.cu
 int conv2d_nhwc_bf16(const void* x, const void* w, int B, int Hin, int Win, int Cin, int Cout, int ksize, int stride,
                      const float* bias, const float* residual, float* out_f32, void* out_bf16, int act, int force_bn,
                      cudaStream_t stream);

@@ -1,0 +1,79 @@
+"""Decode-step kernels (skinny-M GEMM, lane-per-key attention): same results as the batch kernels / fp32 math."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import nuwa_oracle as O
+from tests.helpers import gen, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K", [(8, 512, 512), (8, 1536, 512), (3, 8192, 512), (32, 512, 1376), (1, 64, 136)])
+def test_skinny_gemm_plain(cuda_device, M, N, K):
+    from nuwa_pytorch_b200 import ops
+    g = gen(M + N + K)
+    a = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    ref = a.float() @ w.float().t() + bias + res
+    out = ops.gemm(a.to(cuda_device), w.to(cuda_device), bias=bias.to(cuda_device), residual=res.to(cuda_device),
+                   out_dtype=torch.float32)
+    assert rel(out, ref) < 1e-5
+    # the tensor-core kernel (forced) agrees
+    out_tc = ops.gemm(a.to(cuda_device), w.to(cuda_device), bias=bias.to(cuda_device), residual=res.to(cuda_device),
+                      out_dtype=torch.float32, force_bn=64)
+    assert rel(out_tc, ref) < 1e-5
+
+
+def test_skinny_gemm_geglu_and_strided_rows(cuda_device):
+    from nuwa_pytorch_b200 import ops
+    g = gen(5)
+    M, K, inner = 8, 512, 1365
+    buf = torch.randn(M, 7, K, generator=g).bfloat16().to(cuda_device)
+    a = buf[:, 3, :]  # rows strided by 7*K, as the decode path reads cache rows
+    w = (torch.randn(2 * inner, K, generator=g) / K ** 0.5).bfloat16()
+    wp = ops.pack_pairs(w.to(cuda_device))
+    out = ops.gemm(a, wp, act='geglu', out_dtype=torch.bfloat16)
+    h = a.float().cpu() @ w.float().t()
+    ref = h[:, :inner] * F.gelu(h[:, inner:])
+    assert rel(out.float()[:, :inner], ref) < 4e-3
+    assert out[:, inner:].float().abs().max().item() == 0.0  # zero padded tail columns
+
+
+def test_decode_attention_matches_batch_kernels(cuda_device):
+    """nq == 1 dispatches to the lane-per-key kernel; it must agree with the warp-per-query kernel on the same
+    position (Sparse3DNA causal window and dense null-key attention)."""
+    from nuwa_pytorch_b200 import ops
+    g = gen(6)
+    B, H, dh, fmap, maxf = 3, 8, 64, 4, 3
+    inner = H * dh
+    n = 1 + 2 * 16 + 7
+    qkv = torch.randn(B, n, 3 * inner, generator=g).bfloat16().to(cuda_device)
+    talk = (torch.randn(H, H, generator=g) / 2).to(cuda_device)
+    full = torch.empty(B, n, inner, dtype=torch.bfloat16, device=cuda_device)
+    geom = dict(H=H, dh=dh, talk=talk, fmap=fmap, max_frames=maxf, kernel=(5, 3, 3), dilation=(2, 2, 2), causal=True)
+    ops.attn_sparse3dna(qkv, full, B=B, nq=n, t0=0, npos=n, nv=n - 1, **geom)
+    for t in (0, 1, 17, n - 1):
+        o = torch.empty(B, 1, inner, dtype=torch.bfloat16, device=cuda_device)
+        t_dev = torch.tensor([t], dtype=torch.int32, device=cuda_device)
+        ops.attn_sparse3dna_decode(qkv[:, t, :].contiguous(), qkv, o, t_dev, B=B, npos=n, **geom)
+        assert rel(o[:, 0].float(), full[:, t].float()) < 1e-2, t
+    # dense with null key, mask, talking heads
+    nk = 50
+    q = torch.randn(B, 1, inner, generator=g).bfloat16().to(cuda_device)
+    kv = torch.randn(B, nk, 2 * inner, generator=g).bfloat16().to(cuda_device)
+    null_k, null_v = torch.randn(H * dh, generator=g).to(cuda_device), torch.randn(H * dh, generator=g).to(cuda_device)
+    mask = (torch.rand(B, nk, generator=g) > 0.3)
+    mask[0] = False
+    o1 = torch.empty(B, 1, inner, dtype=torch.bfloat16, device=cuda_device)
+    ops.attn_dense(q.data_ptr(), kv.data_ptr(), kv.data_ptr() + inner * 2, o1, B=B, nq=1, nk=nk, H=H, dh=dh, q_bs=inner,
+                   q_rs=inner, k_bs=nk * 2 * inner, k_rs=2 * inner, v_bs=nk * 2 * inner, v_rs=2 * inner, o_bs=inner,
+                   o_rs=inner, talk=talk, null_k=null_k, null_v=null_v, key_mask=mask.to(torch.uint8).to(cuda_device))
+    qh = O._heads(q.float().cpu(), H) * dh ** -0.5
+    k, v = kv.float().cpu().chunk(2, -1)
+    kh = torch.cat([null_k.cpu().view(1, H, 1, dh).expand(B, -1, -1, -1), O._heads(k, H)], 2)
+    vh = torch.cat([null_v.cpu().view(1, H, 1, dh).expand(B, -1, -1, -1), O._heads(v, H)], 2)
+    sim = (qh @ kh.transpose(-1, -2)).masked_fill(~F.pad(mask, (1, 0), value=True)[:, None, None], O.NEG)
+    attn = O._talking_heads(sim.softmax(-1), talk.cpu()[:, :, None, None])
+    assert rel(o1.float(), O._merge(attn @ vh)) < 4e-3
