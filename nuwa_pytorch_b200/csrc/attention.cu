@@ -456,35 +456,53 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const AttnParams p) {
     }
     __syncthreads();
   }
-  // ---- PV: lane owns DPL consecutive output channels of head w ----
-  float acc[DPL];
+  // ---- PV: the keys stay spread over the lanes (every lane streams whole V rows of ITS keys with independent
+  //      16-byte loads -> full memory-level parallelism), then a shared-memory reduction folds the 32 partial
+  //      head vectors and gives lane l the output channels [l*DPL, (l+1)*DPL) ----
+  float acc[DH];
 #pragma unroll
-  for (int c = 0; c < DPL; ++c) acc[c] = 0.f;
-  const int ch = w * DH + lane * DPL;
-#pragma unroll 4
-  for (int j = 0; j < J; ++j) {
+  for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+  for (int j = lane; j < J; j += 32) {
     const int kj = keys[j];
     const int row = kj & 0x0FFFFFFF, kind = kj >> 28;
     if (kind == KEY_MASKED || kind == KEY_ZERO) continue;
     const float pj = Pw[j];
     if (kind == KEY_NULL) {
+      const float* nvp = p.null_v + w * DH;
 #pragma unroll
-      for (int c = 0; c < DPL; ++c) acc[c] = fmaf(pj, __ldg(p.null_v + ch + c), acc[c]);
+      for (int c = 0; c < DH; ++c) acc[c] = fmaf(pj, __ldg(nvp + c), acc[c]);
     } else {
-      float vf[DPL];
-      load_row<DPL>(vb + (long long)row * p.v_rs + ch, vf);
+      const bf16* vr = vb + (long long)row * p.v_rs + w * DH;
 #pragma unroll
-      for (int c = 0; c < DPL; ++c) acc[c] = fmaf(pj, vf[c], acc[c]);
+      for (int i = 0; i < DH / 8; ++i) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(vr) + i);
+        const float2 a = unpack_bf16x2(u.x), bq = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        acc[i * 8 + 0] = fmaf(pj, a.x, acc[i * 8 + 0]); acc[i * 8 + 1] = fmaf(pj, a.y, acc[i * 8 + 1]);
+        acc[i * 8 + 2] = fmaf(pj, bq.x, acc[i * 8 + 2]); acc[i * 8 + 3] = fmaf(pj, bq.y, acc[i * 8 + 3]);
+        acc[i * 8 + 4] = fmaf(pj, c2.x, acc[i * 8 + 4]); acc[i * 8 + 5] = fmaf(pj, c2.y, acc[i * 8 + 5]);
+        acc[i * 8 + 6] = fmaf(pj, d.x, acc[i * 8 + 6]); acc[i * 8 + 7] = fmaf(pj, d.y, acc[i * 8 + 7]);
+      }
     }
   }
-  store_row<DPL>(ob + ch, acc);
+  float* red = reinterpret_cast<float*>(keys + J) + (size_t)w * 32 * (DH + 1);  // [32 lanes][DH + 1]
+#pragma unroll
+  for (int c = 0; c < DH; ++c) red[lane * (DH + 1) + c] = acc[c];
+  __syncwarp();
+  float outv[DPL];
+#pragma unroll
+  for (int c = 0; c < DPL; ++c) {
+    float sum = 0.f;
+    for (int l = 0; l < 32; ++l) sum += red[l * (DH + 1) + lane * DPL + c];
+    outv[c] = sum;
+  }
+  store_row<DPL>(ob + w * DH + lane * DPL, outv);
 }
 
 template <int MODE>
 static int launch_attn_decode(const AttnParams& p, cudaStream_t stream) {
   if (p.nq != 1 || p.H > 8 || (p.dh != 64 && p.dh != 32)) return NUWA_ERR_INVALID;
   if ((p.k_rs % 8) || (p.q_rs % 8) || (p.k_bs % 8) || (p.q_bs % 8)) return NUWA_ERR_INVALID;
-  const size_t smem = ((size_t)p.H * p.jmax + p.H * p.H + p.jmax) * sizeof(float);
+  const size_t smem = ((size_t)p.H * p.jmax + p.H * p.H + p.jmax + (size_t)p.H * 32 * (p.dh + 1)) * sizeof(float);
   if (smem > 200 * 1024) return NUWA_ERR_INVALID;
   if (p.dh == 64) {
     if (smem > 48 * 1024)

@@ -26,6 +26,19 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__
   bf16* As = reinterpret_cast<bf16*>(smem_sk);  // [M][Kp], Kp = K rounded up to 8
   const int Kp = (K + 7) & ~7;
   const int k8 = Kp / 8;
+  // issue this warp's first weight loads BEFORE staging A, so the two DRAM/L2 latencies overlap
+  const bool pair_ = (act == ACT_GLU || act == ACT_GEGLU);
+  const int n_out_ = pair_ ? N / 2 : N;
+  const int col_ = blockIdx.x * SK_WARPS + (threadIdx.x >> 5);
+  uint4 pre_w = make_uint4(0u, 0u, 0u, 0u), pre_g = pre_w;
+  {
+    const int c = (threadIdx.x & 31) * 8;
+    if (col_ < n_out_ && c + 8 <= K) {
+      const int wr = pair_ ? (col_ / 16) * 32 + (col_ % 16) : col_;
+      pre_w = __ldg(reinterpret_cast<const uint4*>(W + (long long)wr * ldw + c));
+      if (pair_) pre_g = __ldg(reinterpret_cast<const uint4*>(W + (long long)(wr + 16) * ldw + c));
+    }
+  }
   for (int i = threadIdx.x; i < M * k8; i += blockDim.x) {
     const int r = i / k8, c = (i - r * k8) * 8;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -54,7 +67,10 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__
     for (int r = 0; r < SK_MR; ++r) acc[r] = accg[r] = 0.f;
     for (int c = lane * 8; c < Kp; c += 256) {
       uint4 wv = make_uint4(0u, 0u, 0u, 0u), wg = wv;
-      if (c + 8 <= K) {
+      if (c == lane * 8 && c + 8 <= K) {
+        wv = pre_w;  // prefetched above
+        wg = pre_g;
+      } else if (c + 8 <= K) {
         wv = __ldg(reinterpret_cast<const uint4*>(w0 + c));
         if (pair) wg = __ldg(reinterpret_cast<const uint4*>(w1 + c));
       } else {
