@@ -134,7 +134,10 @@ typedef struct {
   const int* t0_ptr; /* CUDA-graph decode: if non-NULL, t0 = *t0_ptr (and, for Sparse3DNA, nv = t0) */
 } nuwa_attn_params;
 /* Sparse3DNA.forward core, nuwa_pytorch.py:490-608 (jmax = 1 + kt*kh*kw; k/v row 0 = bos, row 1+i = video token i) */
-int nuwa_attn_sparse3dna(const nuwa_attn_params* p, void* stream);
+int nuwa_attn_sparse3dna(const nuwa_attn_params* p, void* vt_workspace, void* stream);
+/* vt_workspace: NULL, or B*H*dh*roundup(nv,16) bf16 elements of scratch; when given and the call is a full causal
+ * pass over a 16-wide token grid (t0 == 0, nq == nv + 1, dh in {32,64}, H <= 8) the tensor-core kernel
+ * (attention_3dna_tc.cu) runs, otherwise the generic gather kernel. */
 /* Attention.forward core, nuwa_pytorch.py:339-378, and VQGanAttention core, vqgan_vae.py:275-282
  * (jmax = nk (+1 with a null key)) */
 int nuwa_attn_dense(const nuwa_attn_params* p, void* vt_workspace, void* stream);

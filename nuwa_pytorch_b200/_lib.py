@@ -55,7 +55,7 @@ SIGNATURES = {
                               c_void_p, c_void_p, c_int, c_int, c_void_p],
     "nuwa_sandwich_ln": [P(LnParams), c_void_p],
     "nuwa_stable_ln": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
-    "nuwa_attn_sparse3dna": [P(AttnParams), c_void_p],
+    "nuwa_attn_sparse3dna": [P(AttnParams), c_void_p, c_void_p],
     "nuwa_attn_dense": [P(AttnParams), c_void_p, c_void_p],
     "nuwa_attn_cross2dna": [P(AttnParams), c_void_p],
     "nuwa_embed_tokens": [P(EmbedParams), c_void_p],

@@ -43,7 +43,14 @@ int nuwa_stable_ln(const float* a, const float* b2, const float* w, const float*
                    int rows, int D, void* stream) {
   return stable_ln(a, b2, w, bias, out_f32, out_bf16, rows, D, S(stream));
 }
-int nuwa_attn_sparse3dna(const nuwa_attn_params* p, void* stream) { return p ? attn_sparse3dna(*p, S(stream)) : NUWA_ERR_INVALID; }
+int nuwa_attn_sparse3dna(const nuwa_attn_params* p, void* vt_workspace, void* stream) {
+  if (!p) return NUWA_ERR_INVALID;
+  if (vt_workspace != nullptr) {
+    const int rc = attn_3dna_tc(*p, vt_workspace, S(stream));
+    if (rc != NUWA_ERR_INVALID) return rc;  // outside the tensor-core kernel's envelope -> generic kernel
+  }
+  return attn_sparse3dna(*p, S(stream));
+}
 int nuwa_attn_dense(const nuwa_attn_params* p, void* vt_workspace, void* stream) {
   if (!p) return NUWA_ERR_INVALID;
   if (vt_workspace != nullptr && p->nq >= 8) {

@@ -535,8 +535,10 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
               const float* residual, int ld_res, float* out_f32, void* out_bf16, int ld_out, int act, int force_bn,
               cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return NUWA_ERR_INVALID;
-  if (M <= 32 && force_bn == 0)  // decode-step products: weight-streaming bound, see gemm_skinny.cu
-    return gemm_skinny(A, lda, W, ldw, M, N, K, bias, residual, ld_res, out_f32, out_bf16, ld_out, act, stream);
+  if (M <= 32 && force_bn == 0) {  // decode-step products: weight-streaming bound, see gemm_skinny.cu
+    const int rc = gemm_skinny(A, lda, W, ldw, M, N, K, bias, residual, ld_res, out_f32, out_bf16, ld_out, act, stream);
+    if (rc != NUWA_ERR_INVALID) return rc;  // shapes outside its envelope fall through to the tensor-core kernel
+  }
   if ((lda % 8) || (ldw % 8) || lda < K || ldw < K) return NUWA_ERR_INVALID;  // TMA: 16-byte row pitch
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) return NUWA_ERR_INVALID;
   GemmParams p;

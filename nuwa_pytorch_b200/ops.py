@@ -149,7 +149,7 @@ def _attn_base(q, k, v, o, B, nq, t0, H, dh, q_bs, k_bs, v_bs, o_bs, q_rs, k_rs,
 
 
 def attn_sparse3dna(qkv, o, *, B, nq, t0, npos, H, dh, talk, fmap, max_frames, nv, kernel, dilation, causal,
-                    o_bs=None):
+                    o_bs=None, use_tc=True):
     """qkv: bf16 buffer (B, npos, 3*H*dh) holding q|k|v rows for positions [0, npos); queries are positions
     [t0, t0+nq).  o: bf16 (B, nq, H*dh).  nv = number of video tokens present (positions 1..nv)."""
     inner = H * dh
@@ -163,7 +163,10 @@ def attn_sparse3dna(qkv, o, *, B, nq, t0, npos, H, dh, talk, fmap, max_frames, n
     p.dt, p.dh_, p.dw = dilation
     p.causal = int(bool(causal))
     p.jmax = 1 + kernel[0] * kernel[1] * kernel[2]
-    check(lib().nuwa_attn_sparse3dna(p, stream()), "nuwa_attn_sparse3dna")
+    ws = None
+    if use_tc and causal and fmap == 16 and t0 == 0 and nq == nv + 1 and dh in (32, 64) and H <= 8:
+        ws = torch.empty(B * H * dh * _round_up(nv, 16), dtype=torch.bfloat16, device=qkv.device)
+    check(lib().nuwa_attn_sparse3dna(p, ptr(ws), stream()), "nuwa_attn_sparse3dna")
 
 
 def attn_sparse3dna_decode(q_row, cache, o, t_dev, *, B, npos, H, dh, talk, fmap, max_frames, kernel, dilation, causal):
@@ -179,7 +182,7 @@ def attn_sparse3dna_decode(q_row, cache, o, t_dev, *, B, npos, H, dh, talk, fmap
     p.dt, p.dh_, p.dw = dilation
     p.causal = int(bool(causal))
     p.jmax = 1 + kernel[0] * kernel[1] * kernel[2]
-    check(lib().nuwa_attn_sparse3dna(p, stream()), "nuwa_attn_sparse3dna")
+    check(lib().nuwa_attn_sparse3dna(p, None, stream()), "nuwa_attn_sparse3dna")
 
 
 def cache_append(row, cache, t_dev):

@@ -77,3 +77,26 @@ def test_decode_attention_matches_batch_kernels(cuda_device):
     sim = (qh @ kh.transpose(-1, -2)).masked_fill(~F.pad(mask, (1, 0), value=True)[:, None, None], O.NEG)
     attn = O._talking_heads(sim.softmax(-1), talk.cpu()[:, :, None, None])
     assert rel(o1.float(), O._merge(attn @ vh)) < 4e-3
+
+
+@pytest.mark.parametrize("H,dh,kernel,dil,nv", [(8, 64, (5, 3, 3), 1, 768), (8, 64, (5, 3, 3), 2, 768), (8, 64, (5, 3, 3), 4, 1024),
+                                                (8, 64, (5, 3, 3), 2, 601), (2, 32, (3, 3, 3), 3, 530), (4, 64, (3, 5, 1), 1, 256)])
+def test_sparse3dna_tensor_core_kernel_matches_gather_kernel(cuda_device, H, dh, kernel, dil, nv):
+    """attention_3dna_tc.cu (banded 16x16 MMA blocks) vs the generic gather kernel on identical bf16 q|k|v."""
+    from nuwa_pytorch_b200 import ops
+    g = gen(H * 1000 + nv + dil)
+    B, fmap, maxf = 2, 16, 5
+    inner = H * dh
+    n = nv + 1
+    qkv = torch.randn(B, n, 3 * inner, generator=g).bfloat16().to(cuda_device)
+    talk = (torch.randn(H, H, generator=g) / 2).to(cuda_device)
+    geom = dict(B=B, nq=n, t0=0, npos=n, H=H, dh=dh, talk=talk, fmap=fmap, max_frames=maxf, nv=nv, kernel=kernel,
+                dilation=(dil,) * 3, causal=True)
+    o_ref = torch.zeros(B, n, inner, dtype=torch.bfloat16, device=cuda_device)
+    o_tc = torch.zeros(B, n, inner, dtype=torch.bfloat16, device=cuda_device)
+    ops.attn_sparse3dna(qkv, o_ref, use_tc=False, **geom)
+    ops.attn_sparse3dna(qkv, o_tc, use_tc=True, **geom)
+    r = rel(o_tc.float(), o_ref.float())
+    print(f"  3dna tc vs gather H={H} dh={dh} k={kernel} d={dil} nv={nv}: rel {r:.2e}")
+    assert torch.equal(o_tc[:, 0], o_ref[:, 0])  # bos row: its own value
+    assert r < 8e-3  # probabilities are rounded to bf16 for the tensor-core PV

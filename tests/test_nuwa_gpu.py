@@ -156,6 +156,38 @@ def test_sketch_small(cuda_device):
     assert abs(loss.item() - fx['e2e_loss'].item()) < 0.1  # token flips in the VAEs move single targets
 
 
+def test_sketch_generate_incremental_matches_teacher_forced(cuda_device):
+    """NUWASketch.generate (KV-cached decode incl. the sparse 2-D cross attention) against a teacher-forced full pass
+    of the same model on the sampled sequence: the guided logits of every step must agree."""
+    from nuwa_pytorch_b200 import NUWASketch, VQGanVAE, engine, ops
+    from oracle.synth import manifest_of, synth_state_dict
+    fx = golden("sketch_small.pt")
+    vae, svae = VQGanVAE(**fx['vae_kwargs']), VQGanVAE(**fx['sketch_vae_kwargs'])
+    vae.load_state_dict(synth_state_dict(manifest_of(vae.state_dict()), fx['vae_seed']), strict=False)
+    svae.load_state_dict(synth_state_dict(manifest_of(svae.state_dict()), fx['sketch_vae_seed']), strict=False)
+    model, sd = _load(NUWASketch(vae=vae, sketch_vae=svae, **fx['kwargs']), fx, cuda_device)
+    sketch = torch.randn(2, 3, 5, 64, 64, generator=gen(fx['e2e_sketch_seed'])).to(cuda_device)
+    smask = torch.ones(2, 3, dtype=torch.bool, device=cuda_device)
+    noise = torch.rand(32, 2, 64, generator=gen(77)).to(cuda_device)
+    video = model.generate(sketch=sketch, sketch_mask=smask, num_frames=2, _noise=noise)
+    assert video.shape == (2, 2, 3, 64, 64) and torch.isfinite(video).all()
+    ctx = model._sketch_context(sketch, smask)
+    idx, step_logits = model._generate_indices(ctx, 2, num_frames=2, filter_thres=0.9, temperature=1., cond_scale=2.,
+                                               noise=noise, return_step_logits=True)
+    # teacher-forced: full-sequence passes (conditional, then the D8 second sweep on its output)
+    x = model._embed_video(idx, 32)
+    y32, y16 = engine.run_stack(model.video_transformer, x, context=ctx, want_bf16=True)
+    w = model._logits_weight()
+    lc = ops.gemm(y16.view(64, -1), w, out_dtype=torch.float32).view(2, 32, -1)
+    unc = ctx.with_mask(torch.zeros_like(ctx.mask))
+    _, u16 = engine.run_stack(model.video_transformer, y32, context=unc, want_bf16=True)
+    lu = ops.gemm(u16.view(64, -1), w, out_dtype=torch.float32).view(2, 32, -1)
+    guided = lu + (lc - lu) * 2.0
+    worst = max(rel(step_logits[t], guided[:, t]) for t in range(32))
+    print(f"  sketch generate: worst step-vs-teacher-forced guided-logit rel {worst:.3e}")
+    assert worst < 2e-2
+
+
 def test_cuda_graph_replay_matches_eager(cuda_device):
     from nuwa_pytorch_b200.graphs import GraphedCall
     fx, model, sd = _nuwa("nuwa_small.pt", cuda_device)
