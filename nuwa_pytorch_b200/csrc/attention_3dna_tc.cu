@@ -133,27 +133,40 @@ __global__ void __launch_bounds__(TC_WARPS * 32) attn_3dna_tc_kernel(const AttnP
         Ph[(g + 8) * TC_PITCH] = c[2] * p.qscale;
       }
     }
-    for (int a = 0; a < kt; ++a) {
-      const int ff = f - (kt - 1 - a) * p.dt;
-      if (ff < 0) continue;
-      for (int bq = 0; bq < kh; ++bq) {
-        const int yy = y - (kh - 1 - bq) * p.dh_;
-        if (yy < 0) continue;
-        const long long krow = 1 + (long long)(ff * TC_W + yy) * TC_W;  // sequence row of key x' = 0
-        uint32_t k0[2 * KS], k1[2 * KS];
+    // software-pipelined over the kt*kh (frame, row) blocks: the K fragments of block i+1 are in flight while
+    // block i is multiplied (the loop is a chain of L2 latencies otherwise)
+    const int nblk = kt * kh;
+    uint32_t kc0[2 * KS], kc1[2 * KS], kn0[2 * KS], kn1[2 * KS];
+    auto block_geom = [&](int idx, int& ff, int& yy) {
+      const int a = idx / kh, bq = idx - a * kh;
+      ff = f - (kt - 1 - a) * p.dt;
+      yy = y - (kh - 1 - bq) * p.dh_;
+      return ff >= 0 && yy >= 0;
+    };
+    auto load_block = [&](int idx, uint32_t (&d0)[2 * KS], uint32_t (&d1)[2 * KS]) {
 #pragma unroll
-        for (int i = 0; i < 2 * KS; ++i) k0[i] = k1[i] = 0u;
-        // (only the partial last row of a sequence can have key columns beyond the supplied tokens; they are
-        //  never inside a causal window, but they must not be read)
-        if (krow + g <= p.nv) ld_words<KS>(kh_ + (krow + g) * p.k_rs, k0);
-        if (krow + g + 8 <= p.nv) ld_words<KS>(kh_ + (krow + g + 8) * p.k_rs, k1);
+      for (int i = 0; i < 2 * KS; ++i) d0[i] = d1[i] = 0u;
+      int ff, yy;
+      if (idx < nblk && block_geom(idx, ff, yy)) {
+        const long long krow = 1 + (long long)(ff * TC_W + yy) * TC_W;  // sequence row of key x' = 0
+        // (only the partial last row of a sequence can have key columns beyond the supplied tokens; they are never
+        //  inside a causal window, but they must not be read)
+        if (krow + g <= p.nv) ld_words<KS>(kh_ + (krow + g) * p.k_rs, d0);
+        if (krow + g + 8 <= p.nv) ld_words<KS>(kh_ + (krow + g + 8) * p.k_rs, d1);
+      }
+    };
+    load_block(0, kc0, kc1);
+    for (int idx = 0; idx < nblk; ++idx) {
+      load_block(idx + 1, kn0, kn1);
+      int ff, yy;
+      if (block_geom(idx, ff, yy)) {
         float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          mma16816(c0, qa0[2 * ks], qa1[2 * ks], qa0[2 * ks + 1], qa1[2 * ks + 1], k0[2 * ks], k0[2 * ks + 1]);
-          mma16816(c1, qa0[2 * ks], qa1[2 * ks], qa0[2 * ks + 1], qa1[2 * ks + 1], k1[2 * ks], k1[2 * ks + 1]);
+          mma16816(c0, qa0[2 * ks], qa1[2 * ks], qa0[2 * ks + 1], qa1[2 * ks + 1], kc0[2 * ks], kc0[2 * ks + 1]);
+          mma16816(c1, qa0[2 * ks], qa1[2 * ks], qa0[2 * ks + 1], qa1[2 * ks + 1], kc1[2 * ks], kc1[2 * ks + 1]);
         }
-        const int sbase = 1 + (a * kh + bq) * kw;
+        const int sbase = 1 + idx * kw;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int x = (e < 2) ? g : g + 8;
@@ -161,6 +174,8 @@ __global__ void __launch_bounds__(TC_WARPS * 32) attn_3dna_tc_kernel(const AttnP
           if (cidx[4 + e] >= 0) Ph[x * TC_PITCH + sbase + cidx[4 + e]] = c1[e] * p.qscale;
         }
       }
+#pragma unroll
+      for (int i = 0; i < 2 * KS; ++i) { kc0[i] = kn0[i]; kc1[i] = kn1[i]; }
     }
   }
   __syncwarp();
@@ -205,19 +220,34 @@ __global__ void __launch_bounds__(TC_WARPS * 32) attn_3dna_tc_kernel(const AttnP
 #pragma unroll
     for (int nd = 0; nd < ND; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
     const bf16* vth = vT + ((long long)b * H + h) * DH * npad + 4 * t;
-    for (int a = 0; a < kt; ++a) {
-      const int ff = f - (kt - 1 - a) * p.dt;
-      if (ff < 0) continue;
-      for (int bq = 0; bq < kh; ++bq) {
-        const int yy = y - (kh - 1 - bq) * p.dh_;
-        if (yy < 0) continue;
-        const int sbase = 1 + (a * kh + bq) * kw;
+    const int nblk = kt * kh;
+    uint2 vc[ND], vn[ND];
+    auto block_geom = [&](int idx, int& ff, int& yy) {
+      const int a = idx / kh, bq = idx - a * kh;
+      ff = f - (kt - 1 - a) * p.dt;
+      yy = y - (kh - 1 - bq) * p.dh_;
+      return ff >= 0 && yy >= 0;
+    };
+    auto load_v = [&](int idx, uint2 (&dst)[ND]) {
+      int ff, yy;
+      const bool ok = idx < nblk && block_geom(idx, ff, yy);
+      const int kbase = ok ? (ff * TC_W + yy) * TC_W : 0;  // video index of key x' = 0
+#pragma unroll
+      for (int nd = 0; nd < ND; ++nd)
+        dst[nd] = ok ? __ldg(reinterpret_cast<const uint2*>(vth + (long long)(nd * 8 + g) * npad + kbase)) : make_uint2(0u, 0u);
+    };
+    load_v(0, vc);
+    for (int idx = 0; idx < nblk; ++idx) {
+      load_v(idx + 1, vn);
+      int ff, yy;
+      if (block_geom(idx, ff, yy)) {
+        const int sbase = 1 + idx * kw;
         // A fragment: rows x = g / g+8, contraction slots <-> keys x' = 4t + {0,1 | 2,3}
         float av[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int x = (i & 1) ? g + 8 : g;     // i: (pair index << 1) | row-half ... see packing below
-          const int xp = 4 * t + (i >> 1);       // key column 4t + 0..3
+          const int x = (i & 1) ? g + 8 : g;
+          const int xp = 4 * t + (i >> 1);  // key column 4t + 0..3
           const int delta = x - xp;
           float val = 0.f;
           if (delta >= 0 && delta % p.dw == 0 && delta / p.dw <= kw - 1) val = Ph[x * TC_PITCH + sbase + kw - 1 - delta / p.dw];
@@ -228,13 +258,11 @@ __global__ void __launch_bounds__(TC_WARPS * 32) attn_3dna_tc_kernel(const AttnP
         const uint32_t a1 = pack_bf16x2(av[1], av[3]);  // row g+8, keys 4t, 4t+1
         const uint32_t a2 = pack_bf16x2(av[4], av[6]);  // row g,   keys 4t+2, 4t+3
         const uint32_t a3 = pack_bf16x2(av[5], av[7]);  // row g+8, keys 4t+2, 4t+3
-        const int kbase = (ff * TC_W + yy) * TC_W;      // video index of key x' = 0
 #pragma unroll
-        for (int nd = 0; nd < ND; ++nd) {
-          const uint2 vv = __ldg(reinterpret_cast<const uint2*>(vth + (long long)(nd * 8 + g) * npad + kbase));
-          mma16816(o[nd], a0, a1, a2, a3, vv.x, vv.y);
-        }
+        for (int nd = 0; nd < ND; ++nd) mma16816(o[nd], a0, a1, a2, a3, vc[nd].x, vc[nd].y);
       }
+#pragma unroll
+      for (int nd = 0; nd < ND; ++nd) vc[nd] = vn[nd];
     }
     // bos value (slot 0) + store
     const float pb0 = Ph[g * TC_PITCH], pb1 = Ph[(g + 8) * TC_PITCH];

@@ -629,7 +629,7 @@ class NUWASketch(nn.Module, _VideoDecoderMixin):
     @torch.no_grad()
     @_eval_decorator
     def generate(self, *, sketch, sketch_mask=None, filter_thres=0.9, temperature=1., decode_max_batchsize=10,
-                 cond_scale=2., num_frames=None, _noise=None, _return_indices=False):
+                 cond_scale=2., num_frames=None, _noise=None, _return_indices=False, _use_graph=True):
         batch = sketch.shape[0]
         context = self._sketch_context(sketch, sketch_mask)
         num_frames = num_frames if _exists(num_frames) else self.max_video_frames
