@@ -105,11 +105,28 @@ __global__ void __launch_bounds__(TC_WARPS * 32) attn_3dna_tc_kernel(const AttnP
       if (delta >= 0 && delta % p.dw == 0 && delta / p.dw <= kw - 1) c = kw - 1 - delta / p.dw;
       cidx[nt * 4 + e] = c;
     }
+  // same for the A fragment of the PV blocks: entry i <-> (x = g + 8*(i&1), key column 4t + (i>>1))
+  int aidx[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int x = (i & 1) ? g + 8 : g;
+    const int delta = x - (4 * t + (i >> 1));
+    int c = -1;
+    if (delta >= 0 && delta % p.dw == 0 && delta / p.dw <= kw - 1) c = kw - 1 - delta / p.dw;
+    aidx[i] = c;
+  }
+  // (frame,row) blocks of this query row: video index of key column 0, or -1 when the block is outside the grid
+  int* blk_tab = reinterpret_cast<int*>(smem_tc + (size_t)TC_WARPS * H * TC_W * TC_PITCH) + warp * 32;
+  if (lane < kt * kh) {
+    const int a = lane / kh, bq = lane - a * kh;
+    const int ff = f - (kt - 1 - a) * p.dt, yy = y - (kh - 1 - bq) * p.dh_;
+    blk_tab[lane] = (ff >= 0 && yy >= 0) ? (ff * TC_W + yy) * TC_W : -1;
+  }
   const bool ok0 = vbase + g < p.nv, ok1 = vbase + g + 8 < p.nv;  // query validity (partial last row)
 
   // ---------------- phase 1: scores of every head into P[h][x][slot] ----------------
   for (int i = lane; i < H * TC_W * TC_PITCH; i += 32) P[i] = -FLT_MAX;  // masked unless written
-  __syncwarp();
+  __syncwarp();  // (also publishes blk_tab)
   for (int h = 0; h < H; ++h) {
     uint32_t qa0[2 * KS], qa1[2 * KS];
 #pragma unroll
@@ -137,18 +154,12 @@ __global__ void __launch_bounds__(TC_WARPS * 32) attn_3dna_tc_kernel(const AttnP
     // block i is multiplied (the loop is a chain of L2 latencies otherwise)
     const int nblk = kt * kh;
     uint32_t kc0[2 * KS], kc1[2 * KS], kn0[2 * KS], kn1[2 * KS];
-    auto block_geom = [&](int idx, int& ff, int& yy) {
-      const int a = idx / kh, bq = idx - a * kh;
-      ff = f - (kt - 1 - a) * p.dt;
-      yy = y - (kh - 1 - bq) * p.dh_;
-      return ff >= 0 && yy >= 0;
-    };
     auto load_block = [&](int idx, uint32_t (&d0)[2 * KS], uint32_t (&d1)[2 * KS]) {
 #pragma unroll
       for (int i = 0; i < 2 * KS; ++i) d0[i] = d1[i] = 0u;
-      int ff, yy;
-      if (idx < nblk && block_geom(idx, ff, yy)) {
-        const long long krow = 1 + (long long)(ff * TC_W + yy) * TC_W;  // sequence row of key x' = 0
+      const int kv0 = idx < nblk ? blk_tab[idx] : -1;
+      if (kv0 >= 0) {
+        const long long krow = 1 + (long long)kv0;  // sequence row of key x' = 0
         // (only the partial last row of a sequence can have key columns beyond the supplied tokens; they are never
         //  inside a causal window, but they must not be read)
         if (krow + g <= p.nv) ld_words<KS>(kh_ + (krow + g) * p.k_rs, d0);
@@ -158,8 +169,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32) attn_3dna_tc_kernel(const AttnP
     load_block(0, kc0, kc1);
     for (int idx = 0; idx < nblk; ++idx) {
       load_block(idx + 1, kn0, kn1);
-      int ff, yy;
-      if (block_geom(idx, ff, yy)) {
+      if (blk_tab[idx] >= 0) {
         float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
@@ -198,15 +208,14 @@ __global__ void __launch_bounds__(TC_WARPS * 32) attn_3dna_tc_kernel(const AttnP
 
   // ---------------- talking heads: P'[g][x][j] = sum_h W[g][h] P[h][x][j] ----------------
   if (p.talk != nullptr) {
-    float Wr[64];
-    for (int i = 0; i < H * H; ++i) Wr[i] = __ldg(p.talk + i);
+    const float* Wr = p.talk;  // 64 floats, L1-resident broadcast reads
     for (int i = lane; i < TC_W * J; i += 32) {
       const int x = i / J, j = i - x * J;
       float pin[8];
       for (int h = 0; h < H; ++h) pin[h] = P[((size_t)h * TC_W + x) * TC_PITCH + j];
       for (int gh = 0; gh < H; ++gh) {
         float acc = 0.f;
-        for (int h = 0; h < H; ++h) acc = fmaf(Wr[gh * H + h], pin[h], acc);
+        for (int h = 0; h < H; ++h) acc = fmaf(__ldg(Wr + gh * H + h), pin[h], acc);
         P[((size_t)gh * TC_W + x) * TC_PITCH + j] = acc;
       }
     }
@@ -222,16 +231,10 @@ __global__ void __launch_bounds__(TC_WARPS * 32) attn_3dna_tc_kernel(const AttnP
     const bf16* vth = vT + ((long long)b * H + h) * DH * npad + 4 * t;
     const int nblk = kt * kh;
     uint2 vc[ND], vn[ND];
-    auto block_geom = [&](int idx, int& ff, int& yy) {
-      const int a = idx / kh, bq = idx - a * kh;
-      ff = f - (kt - 1 - a) * p.dt;
-      yy = y - (kh - 1 - bq) * p.dh_;
-      return ff >= 0 && yy >= 0;
-    };
     auto load_v = [&](int idx, uint2 (&dst)[ND]) {
-      int ff, yy;
-      const bool ok = idx < nblk && block_geom(idx, ff, yy);
-      const int kbase = ok ? (ff * TC_W + yy) * TC_W : 0;  // video index of key x' = 0
+      const int kv0 = idx < nblk ? blk_tab[idx] : -1;
+      const bool ok = kv0 >= 0;
+      const int kbase = ok ? kv0 : 0;  // video index of key x' = 0
 #pragma unroll
       for (int nd = 0; nd < ND; ++nd)
         dst[nd] = ok ? __ldg(reinterpret_cast<const uint2*>(vth + (long long)(nd * 8 + g) * npad + kbase)) : make_uint2(0u, 0u);
@@ -239,19 +242,14 @@ __global__ void __launch_bounds__(TC_WARPS * 32) attn_3dna_tc_kernel(const AttnP
     load_v(0, vc);
     for (int idx = 0; idx < nblk; ++idx) {
       load_v(idx + 1, vn);
-      int ff, yy;
-      if (block_geom(idx, ff, yy)) {
+      if (blk_tab[idx] >= 0) {
         const int sbase = 1 + idx * kw;
         // A fragment: rows x = g / g+8, contraction slots <-> keys x' = 4t + {0,1 | 2,3}
         float av[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int x = (i & 1) ? g + 8 : g;
-          const int xp = 4 * t + (i >> 1);  // key column 4t + 0..3
-          const int delta = x - xp;
-          float val = 0.f;
-          if (delta >= 0 && delta % p.dw == 0 && delta / p.dw <= kw - 1) val = Ph[x * TC_PITCH + sbase + kw - 1 - delta / p.dw];
-          av[i] = val;
+          av[i] = aidx[i] >= 0 ? Ph[x * TC_PITCH + sbase + aidx[i]] : 0.f;
         }
         // av[2k + half] = P'(x = g + 8*half, key 4t + k)
         const uint32_t a0 = pack_bf16x2(av[0], av[2]);  // row g,   keys 4t, 4t+1
@@ -287,7 +285,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32) attn_3dna_tc_kernel(const AttnP
 int attn_3dna_tc(const AttnParams& p, void* vT_ws, cudaStream_t stream) {
   if (!p.causal || p.fmap != TC_W || p.t0 != 0 || p.t0_ptr != nullptr || vT_ws == nullptr) return NUWA_ERR_INVALID;
   if (p.H > 8 || (p.dh != 64 && p.dh != 32) || p.nq != p.nv + 1 || p.nv <= 0) return NUWA_ERR_INVALID;
-  if (1 + p.kt * p.kh * p.kw > TC_MAXJ || p.dt <= 0 || p.dh_ <= 0 || p.dw <= 0) return NUWA_ERR_INVALID;
+  if (p.kt * p.kh > 32 || 1 + p.kt * p.kh * p.kw > TC_MAXJ || p.dt <= 0 || p.dh_ <= 0 || p.dw <= 0) return NUWA_ERR_INVALID;
   if ((p.q_rs % 8) || (p.k_rs % 8) || (p.q_bs % 8) || (p.k_bs % 8) || (p.o_rs & 1)) return NUWA_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(p.q) & 15) || (reinterpret_cast<uintptr_t>(p.k) & 15)) return NUWA_ERR_INVALID;
   const int npad = (p.nv + 15) / 16 * 16;
@@ -297,7 +295,7 @@ int attn_3dna_tc(const AttnParams& p, void* vT_ws, cudaStream_t stream) {
                                                   p.nv, npad);
   NUWA_CHECK_LAUNCH();
   const int rows = p.B * ((p.nv + TC_W - 1) / TC_W);
-  const size_t smem = (size_t)TC_WARPS * p.H * TC_W * TC_PITCH * sizeof(float);
+  const size_t smem = (size_t)TC_WARPS * p.H * TC_W * TC_PITCH * sizeof(float) + TC_WARPS * 32 * sizeof(int);
   const int grid = (rows + TC_WARPS - 1) / TC_WARPS;
   if (p.dh == 64) {
     if (smem > 48 * 1024)

@@ -149,9 +149,12 @@ def _attn_base(q, k, v, o, B, nq, t0, H, dh, q_bs, k_bs, v_bs, o_bs, q_rs, k_rs,
 
 
 def attn_sparse3dna(qkv, o, *, B, nq, t0, npos, H, dh, talk, fmap, max_frames, nv, kernel, dilation, causal,
-                    o_bs=None, use_tc=True):
+                    o_bs=None, use_tc=False):
     """qkv: bf16 buffer (B, npos, 3*H*dh) holding q|k|v rows for positions [0, npos); queries are positions
-    [t0, t0+nq).  o: bf16 (B, nq, H*dh).  nv = number of video tokens present (positions 1..nv)."""
+    [t0, t0+nq).  o: bf16 (B, nq, H*dh).  nv = number of video tokens present (positions 1..nv).
+    use_tc selects the banded tensor-core kernel (attention_3dna_tc.cu); measured 253-296 us vs 158-234 us for the
+    gather kernel at the cfg-3 shape (profiles/r01_attn3dna_perf.json), so it is opt-in until its softmax / mix
+    phases move off the CUDA cores."""
     inner = H * dh
     esz = 2
     base = qkv.data_ptr()
