@@ -73,26 +73,38 @@ int nhwc_to_nchw_f32(const void* in, int in_is_bf16, float* out, int B, int C, i
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 im2col_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int C, int H, int W, int KS, int Kpad) {
-  // one thread = 8 consecutive K entries of one output pixel -> one 16-byte store
-  const int G = Kpad / 8;
-  const long long total = (long long)B * H * W * G;
+  // one thread = 8 consecutive K entries of one output pixel -> one 16-byte store.  The (dy, dx, c) of every K entry
+  // comes from a per-CTA table (no integer division in the hot loop).
+  extern __shared__ int lut[];  // [Kpad]: ((dy + 64) << 20) | ((dx + 64) << 10) | c ,  -1 for the zero padding
   const int pad = KS / 2;
   const int K = KS * KS * C;
+  for (int kk = threadIdx.x; kk < Kpad; kk += blockDim.x) {
+    int v = -1;
+    if (kk < K) {
+      const int c = kk % C, tap = kk / C;
+      const int kh = tap / KS, kw = tap - kh * KS;
+      v = ((kh - pad + 64) << 20) | ((kw - pad + 64) << 10) | c;
+    }
+    lut[kk] = v;
+  }
+  __syncthreads();
+  const int G = Kpad / 8;
+  const long long total = (long long)B * H * W * G;
+  const long long HW = (long long)H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int gk = (int)(i % G);
     const long long pix = i / G;
     const int x = (int)(pix % W), y = (int)((pix / W) % H);
-    const long long b = pix / ((long long)W * H);
+    const long long b = pix / HW;
+    const float* base = img + b * C * HW;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int kk = gk * 8 + e;
+      const int l = lut[gk * 8 + e];
       float val = 0.f;
-      if (kk < K) {
-        const int c = kk % C, tap = kk / C;
-        const int kh = tap / KS, kw = tap - kh * KS;
-        const int yy = y + kh - pad, xx = x + kw - pad;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(img + ((b * C + c) * H + yy) * (long long)W + xx);
+      if (l >= 0) {
+        const int yy = y + ((l >> 20) & 1023) - 64, xx = x + ((l >> 10) & 1023) - 64, c = l & 1023;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(base + c * HW + (long long)yy * W + xx);
       }
       v[e] = val;
     }
@@ -107,7 +119,8 @@ int im2col_nchw_f32(const float* img, void* out, int B, int C, int H, int W, int
   const long long total = (long long)B * H * W * (Kpad / 8);
   long long g = (total + 255) / 256;
   int grid = (int)(g > 148LL * 64 ? 148LL * 64 : g);
-  im2col_kernel<<<grid, 256, 0, stream>>>(img, reinterpret_cast<bf16*>(out), B, C, H, W, KS, Kpad);
+  if (C > 1023 || KS > 63) return NUWA_ERR_INVALID;
+  im2col_kernel<<<grid, 256, Kpad * sizeof(int), stream>>>(img, reinterpret_cast<bf16*>(out), B, C, H, W, KS, Kpad);
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
 }
@@ -351,19 +364,20 @@ int vae_attn_prep(const float* qkv, void* out, int B, int n, int inner, cudaStre
 // CTA = 64 tokens x (all codes in steps of 64); 256 threads, 4x4 register tile each; running best per
 // thread, then a warp-shuffle arg-max across the 16 threads that share a token; first maximum wins.
 // ------------------------------------------------------------------------------------------------
-static constexpr int VQ_TM = 64, VQ_TN = 64, VQ_TK = 32;
+static constexpr int VQ_TM = 64, VQ_TN = 128, VQ_TK = 16;
 
 __global__ void __launch_bounds__(256)
 vq_argmax_kernel(const float* __restrict__ x, const float* __restrict__ code, const float* __restrict__ code_sq,
                  long long* __restrict__ out, int M, int Kc, int D, int cosine) {
-  __shared__ float xs[VQ_TK][VQ_TM + 1];
-  __shared__ float cs[VQ_TK][VQ_TN + 1];
+  // CTA = 64 tokens x (all codes, 128 per step); 256 threads = 16 (token groups of 4) x 16 (code groups of 8):
+  // 32 FMA per 3 shared-memory 128-bit loads.
+  __shared__ __align__(16) float xs[VQ_TK][VQ_TM + 4];
+  __shared__ __align__(16) float cs[VQ_TK][VQ_TN + 4];
   __shared__ float xnorm[VQ_TM];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;  // tx: code sub-tile, ty: token sub-tile
   const int m0 = blockIdx.x * VQ_TM;
-  // per-token scale: 1/max(|x|,eps) for cosine, |x|^2 for euclid
-  if (tid < VQ_TM) {
+  if (tid < VQ_TM) {  // per-token scale: 1/max(|x|,eps) for cosine, |x|^2 for euclid
     const int m = m0 + tid;
     float s = 0.f;
     if (m < M)
@@ -376,49 +390,52 @@ vq_argmax_kernel(const float* __restrict__ x, const float* __restrict__ code, co
 #pragma unroll
   for (int i = 0; i < 4; ++i) { best[i] = -FLT_MAX; besti[i] = 0x7fffffff; }
   for (int n0 = 0; n0 < Kc; n0 += VQ_TN) {
-    float acc[4][4];
+    float acc[4][8];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     for (int k0 = 0; k0 < D; k0 += VQ_TK) {
-      // load tiles (coalesced along D)
+      // x tile: 64 x 16, code tile: 128 x 16 (coalesced along D)
       for (int i = tid; i < VQ_TM * VQ_TK; i += 256) {
         const int r = i / VQ_TK, k = i % VQ_TK;
         const int m = m0 + r;
         float v = (m < M && k0 + k < D) ? x[(long long)m * D + k0 + k] : 0.f;
         if (cosine) v *= xnorm[r];
         xs[k][r] = v;
+      }
+      for (int i = tid; i < VQ_TN * VQ_TK; i += 256) {
+        const int r = i / VQ_TK, k = i % VQ_TK;
         const int cn = n0 + r;
         cs[k][r] = (cn < Kc && k0 + k < D) ? code[(long long)cn * D + k0 + k] : 0.f;
       }
       __syncthreads();
-#pragma unroll 8
+#pragma unroll
       for (int k = 0; k < VQ_TK; ++k) {
-        float a[4], bq[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = xs[k][ty * 4 + i];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bq[j] = cs[k][tx * 4 + j];
+        const float4 a4 = *reinterpret_cast<const float4*>(&xs[k][ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&cs[k][tx * 8]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&cs[k][tx * 8 + 4]);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float bq[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bq[j], acc[i][j]);
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bq[j], acc[i][j]);
       }
       __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int cn = n0 + tx * 4 + j;
+      for (int j = 0; j < 8; ++j) {
+        const int cn = n0 + tx * 8 + j;
         if (cn >= Kc) continue;
         float s = acc[i][j];
         if (!cosine) s = -(xnorm[ty * 4 + i] - 2.0f * s + code_sq[cn]);
         if (s > best[i] || (s == best[i] && cn < besti[i])) { best[i] = s; besti[i] = cn; }
       }
   }
-  // arg-max across the 16 lanes (tx) that hold the same tokens: lanes [0,16) and [16,32) of a warp are 2 ty values
+  // arg-max across the 16 lanes (tx) that hold the same tokens: a warp = 2 token groups x 16 code groups
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     for (int o = 8; o > 0; o >>= 1) {
@@ -467,9 +484,72 @@ int gather_rows(const float* table, const long long* idx, void* out_bf16, float*
 // One warp per pixel: lanes stride the input channels, Cout (<= 8) accumulators, warp-shuffle reduce.
 // HBM-bound: reads the activation once.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_c1(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                       uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// out[b][o][p] = sum_c x[b][p][c] w[o][c] + bias[o],  Cout <= 8, C % 64 == 0.
+// One warp = 16 pixels per step: m16n8k16 with the output channels as the (padded) N = 8; the contraction index is
+// permuted so that lane t of a quad owns channels [64 blk + 16 t, +16) -> two 16-byte loads per pixel row and block.
+// HBM bound: the activation is read exactly once.
 __global__ void __launch_bounds__(256)
 conv1x1_to_nchw_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                        float* __restrict__ out, long long npix, int HW, int C, int Cout) {
+  extern __shared__ __align__(16) uint8_t smem_c1[];
+  bf16* ws = reinterpret_cast<bf16*>(smem_c1);  // [8][C] bf16 (rows >= Cout are zero)
+  for (int i = threadIdx.x; i < 8 * C; i += blockDim.x) {
+    const int o = i / C, c = i - o * C;
+    ws[i] = __float2bfloat16(o < Cout ? w[o * C + c] : 0.f);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const long long wid = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long ntiles = (npix + 15) / 16;
+  const int nblk = C / 64;
+  for (long long tile = wid; tile < ntiles; tile += nwarps) {
+    const long long p0 = tile * 16 + g, p1 = p0 + 8;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int blk = 0; blk < nblk; ++blk) {
+      uint4 r0a = make_uint4(0u, 0u, 0u, 0u), r0b = r0a, r1a = r0a, r1b = r0a;
+      const int c0 = blk * 64 + 16 * t;
+      if (p0 < npix) {
+        r0a = __ldg(reinterpret_cast<const uint4*>(x + p0 * C + c0));
+        r0b = __ldg(reinterpret_cast<const uint4*>(x + p0 * C + c0) + 1);
+      }
+      if (p1 < npix) {
+        r1a = __ldg(reinterpret_cast<const uint4*>(x + p1 * C + c0));
+        r1b = __ldg(reinterpret_cast<const uint4*>(x + p1 * C + c0) + 1);
+      }
+      const uint32_t a_r0[8] = {r0a.x, r0a.y, r0a.z, r0a.w, r0b.x, r0b.y, r0b.z, r0b.w};
+      const uint32_t a_r1[8] = {r1a.x, r1a.y, r1a.z, r1a.w, r1b.x, r1b.y, r1b.z, r1b.w};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        // B fragment: output channel g, channels c0 + 4 ks + {0,1 | 2,3}
+        const uint2 bw = *reinterpret_cast<const uint2*>(ws + (long long)g * C + c0 + 4 * ks);
+        mma_c1(acc, a_r0[2 * ks], a_r1[2 * ks], a_r0[2 * ks + 1], a_r1[2 * ks + 1], bw.x, bw.y);
+      }
+    }
+    // acc[0],acc[1] = (pixel p0, o = 2t, 2t+1) ; acc[2],acc[3] = (pixel p1, ...)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int o = 2 * t + (e & 1);
+      const long long pp = (e < 2) ? p0 : p1;
+      if (o < Cout && pp < npix) {
+        const long long b = pp / HW;
+        out[(b * Cout + o) * HW + (pp - b * HW)] = acc[e] + bias[o];
+      }
+    }
+  }
+}
+// generic fallback (C % 8 == 0, fp32 weights in shared memory): one warp per pixel
+__global__ void __launch_bounds__(256)
+conv1x1_to_nchw_scalar_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                              float* __restrict__ out, long long npix, int HW, int C, int Cout) {
   extern __shared__ float w_s[];  // [Cout][C]
   for (int i = threadIdx.x; i < Cout * C; i += blockDim.x) w_s[i] = w[i];
   __syncthreads();
@@ -507,10 +587,22 @@ int conv1x1_nhwc_to_nchw(const void* x, const float* w, const float* bias, float
                          cudaStream_t stream) {
   if (B <= 0 || HW <= 0 || C <= 0 || (C % 8) || Cout <= 0 || Cout > 8) return NUWA_ERR_INVALID;
   const long long npix = (long long)B * HW;
-  const size_t smem = (size_t)Cout * C * sizeof(float);
+  if (C % 64) {
+    const size_t smem = (size_t)Cout * C * sizeof(float);
+    if (smem > 96 * 1024) return NUWA_ERR_INVALID;
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(conv1x1_to_nchw_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long long want = (npix + 7) / 8;
+    const int grid = (int)(want > 148LL * 8 ? 148LL * 8 : want);
+    conv1x1_to_nchw_scalar_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const bf16*>(x), w, bias, out, npix, HW, C,
+                                                                Cout);
+    NUWA_CHECK_LAUNCH();
+    return NUWA_OK;
+  }
+  const size_t smem = (size_t)8 * C * sizeof(bf16);
   if (smem > 96 * 1024) return NUWA_ERR_INVALID;
   if (smem > 48 * 1024) cudaFuncSetAttribute(conv1x1_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  long long want = (npix + 7) / 8;
+  long long want = ((npix + 15) / 16 + 7) / 8;
   const int grid = (int)(want > 148LL * 8 ? 148LL * 8 : want);
   conv1x1_to_nchw_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const bf16*>(x), w, bias, out, npix, HW, C, Cout);
   NUWA_CHECK_LAUNCH();

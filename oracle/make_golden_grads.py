@@ -1,0 +1,68 @@
+"""TEST INFRASTRUCTURE ONLY.  Golden GRADIENTS of the training step `loss = nuwa(text=, video=, return_loss=True);
+loss.backward()` (SURVEY §8d cfg3 timed region), produced by the UNMODIFIED reference imported from /root/reference
+(build container only) on the `nuwa_small` / `nuwa_rev_small` fixtures' weights and inputs, and used to pin the autograd
+of the oracle restatement (oracle/nuwa_oracle.py) -- which in turn is the checker for the CUDA backward path.
+
+    python -m oracle.make_golden_grads      # writes tests/golden/nuwa_small_grads.pt, nuwa_rev_small_grads.pt
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import nuwa_oracle as O  # noqa: E402
+from oracle.ref_import import import_reference  # noqa: E402
+from oracle.synth import synth_state_dict  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def oracle_grads(fx, spec, sd):
+    """Autograd through the functional oracle; returns {state-dict key: grad} for every float leaf that got one."""
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and not k.startswith('vae.')}
+    full = dict(sd)
+    full.update(leaves)
+    _, loss = O.nuwa_logits(fx['text'], fx['video_indices'].reshape(fx['text'].shape[0], -1), full, spec)
+    loss.backward()
+    return loss.detach(), {k: v.grad for k, v in leaves.items() if v.grad is not None}
+
+
+def main():
+    NP, VQ = import_reference()
+    for name, spec_kw in (("nuwa_small", dict(dec_depth=3, kernel=(5, 3, 3), dilation=(1, 2, 4))),
+                          ("nuwa_rev_small", dict(dec_depth=2, dec_reversible=True, kernel=3, dilation=2))):
+        fx = torch.load(os.path.join(OUT, name + ".pt"))
+        vae = VQ.VQGanVAE(**fx['vae_kwargs']).eval()
+        nuwa = NP.NUWA(vae=vae, **fx['kwargs'])
+        sd = synth_state_dict(fx['manifest'], fx['seed'])
+        nuwa.load_state_dict(sd, strict=False)
+        nuwa.train()
+        loss = nuwa(text=fx['text'], video=fx['video_indices'], return_loss=True, cond_dropout_prob=0.)
+        loss.backward()
+        assert abs(loss.item() - fx['loss'].item()) < 1e-6
+        grads = {k: p.grad.clone() for k, p in nuwa.named_parameters() if p.grad is not None}
+        assert not any(k.startswith('vae.') for k in grads)
+        spec = O.NUWASpec(64, 4, 3, 64, text_enc_dim_head=32, text_enc_depth=2, text_enc_heads=2, dec_heads=2, **spec_kw)
+        oloss, og = oracle_grads(fx, spec, sd)
+        assert abs(oloss.item() - loss.item()) < 1e-6
+        worst = 0.
+        for k, g in grads.items():
+            assert k in og, k
+            worst = max(worst, rel(og[k], g))
+            if rel(og[k], g) > 2e-4:
+                print('  MISMATCH', k, rel(og[k], g))
+        print(f"{name}: {len(grads)} gradient tensors, oracle-vs-reference worst rel {worst:.2e}")
+        assert worst < 2e-4
+        path = os.path.join(OUT, name + "_grads.pt")
+        torch.save(dict(loss=loss.detach(), grads=grads), path)
+        print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+if __name__ == "__main__":
+    main()

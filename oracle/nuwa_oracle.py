@@ -552,6 +552,12 @@ def axial_pos_emb(sd, prefix, shape):
     return pos.reshape(-1, pos.shape[-1])
 
 
+def frac_gradient(x, frac=0.2):
+    """Embedding.forward's gradient scaling -- nuwa_pytorch.py:1666-1670 (value unchanged, gradient x frac;
+    embed_gradient_frac defaults to 0.2, :1741 / :2314)."""
+    return x * frac + x.detach() * (1 - frac) if frac != 1. else x
+
+
 class NUWASpec:
     def __init__(self, dim, fmap, max_video_frames, num_image_tokens, text_enc_depth=6, text_enc_heads=8,
                  dec_depth=6, dec_heads=8, dec_reversible=False, enc_reversible=True, kernel=3, dilation=1,
@@ -569,7 +575,7 @@ class NUWASpec:
 def nuwa_embed_text(text, sd, spec):
     """NUWA.embed_text -- nuwa_pytorch.py:1821-1839 (rotary position embedding, text_rotary_pos_emb=True)."""
     mask = text != 0
-    tok = sd['text_embedding.embed.weight'][text]
+    tok = frac_gradient(sd['text_embedding.embed.weight'][text])
     inv = sd.get('text_rotary_pos_emb.inv_freq')
     if inv is None:  # buffer of RotaryEmbedding(dim=min(32, dim_head)) -- nuwa_pytorch.py:135,1769
         rd = min(32, spec.text_dim_head)
@@ -594,7 +600,7 @@ def nuwa_logits(text, frame_indices, sd, spec, return_loss=True, context_mask_ov
     idx_in = frame_indices[:, :-1] if return_loss else frame_indices
     b, n = idx_in.shape
     pos = axial_pos_emb(sd, 'video_pos_emb', spec.video_shape)
-    x = sd['image_embedding.embed.weight'][idx_in] + pos[:n]
+    x = frac_gradient(sd['image_embedding.embed.weight'][idx_in]) + pos[:n]
     x = torch.cat([sd['video_bos'][None, None].expand(b, 1, -1), x], dim=1)
     x = transformer(x, _sub(sd, 'video_transformer'), spec.dec, context=text_emb, context_mask=text_mask)
     logits = x @ sd['to_logits.weight'].t()
@@ -663,7 +669,7 @@ def sketch_embed(sketch_indices, sketch_mask_frames, sd, spec):
     b, f = sketch_indices.shape[:2]
     idx = sketch_indices.reshape(b, -1)
     n = idx.shape[1]
-    tok = sd['sketch_embedding.embed.weight'][idx] + axial_pos_emb(sd, 'sketch_pos_emb', spec.sketch_shape)[:n]
+    tok = frac_gradient(sd['sketch_embedding.embed.weight'][idx]) + axial_pos_emb(sd, 'sketch_pos_emb', spec.sketch_shape)[:n]
     if sketch_mask_frames is not None:
         mask = sketch_mask_frames[:, :, None].expand(b, f, n // f).reshape(b, n)
     else:
@@ -678,7 +684,7 @@ def sketch_logits(sketch_indices, sketch_mask_frames, frame_indices, sd, spec, r
     idx_in = frame_indices[:, :-1] if return_loss else frame_indices
     b, n = idx_in.shape
     pos = axial_pos_emb(sd, 'video_pos_emb', spec.video_shape)
-    x = sd['image_embedding.embed.weight'][idx_in] + pos[:n]
+    x = frac_gradient(sd['image_embedding.embed.weight'][idx_in]) + pos[:n]
     x = torch.cat([sd['video_bos'][None, None].expand(b, 1, -1), x], dim=1)
     x = transformer(x, _sub(sd, 'video_transformer'), spec.dec, context=ctx, context_mask=cmask)
     logits = x @ sd['to_logits.weight'].t()

@@ -52,11 +52,14 @@ def test_layout_and_first_conv(cuda_device):
 def test_conv1x1_to_nchw(cuda_device):
     from nuwa_pytorch_b200 import ops
     g = gen(4)
-    x = torch.randn(2, 7, 6, 64, generator=g).bfloat16()
-    w, b = torch.randn(3, 64, generator=g) / 8, torch.randn(3, generator=g)
-    out = ops.conv1x1_to_nchw(x.to(cuda_device), w.to(cuda_device), b.to(cuda_device))
-    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w[:, :, None, None], b)
-    assert rel(out, ref) < 1e-5
+    # C % 64 == 0 -> tensor-core kernel (weights rounded to bf16); otherwise the fp32-weight warp-per-pixel kernel
+    for C, cout in ((64, 3), (128, 3), (512, 8), (40, 3), (8, 1)):
+        x = torch.randn(2, 7, 6, C, generator=g).bfloat16()
+        w, b = torch.randn(cout, C, generator=g) / 8, torch.randn(cout, generator=g)
+        out = ops.conv1x1_to_nchw(x.to(cuda_device), w.to(cuda_device), b.to(cuda_device))
+        w_eff = w.bfloat16().float() if C % 64 == 0 else w
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w_eff[:, :, None, None], b)
+        assert rel(out, ref) < 1e-5, (C, cout)
 
 
 def test_sandwich_ln_shift_scatter(cuda_device):

@@ -77,6 +77,11 @@ def test_vq_argmax_bit_exact_at_op_boundary(cuda_device):
     want = O.vq_lookup(x, code, True)
     assert got[5].item() == 17
     assert (got == want).float().mean().item() > 0.999  # fp32 sum-order differences can only flip ~1e-7 near-ties
+    # ragged everything: tokens, codes and feature dim all off the tile sizes (64 / 128 / 16)
+    code = torch.randn(131, 20, generator=g)
+    x = torch.randn(70, 20, generator=g)
+    got = ops.vq_argmax(x.to(cuda_device), code.to(cuda_device), code.pow(2).sum(-1).to(cuda_device), cosine=False).cpu()
+    assert torch.equal(got, O.vq_lookup(x, code, False))
 
 
 def test_vae_small_l4_video_paths(cuda_device):
