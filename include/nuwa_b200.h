@@ -205,6 +205,138 @@ int nuwa_gather_rows(const float* table, const long long* idx, void* out_bf16, f
 int nuwa_conv1x1_nhwc_to_nchw(const void* x, const float* w, const float* bias, float* out, int B, int HW, int C,
                               int Cout, void* stream);
 
+/* =================================================================================================
+ * Training (backward) entry points -- the gradient of `loss = nuwa(text=, video=, return_loss=True); loss.backward()`
+ * (nuwa_pytorch.py:1917-1964; the reference obtains it from ATen autograd, reversible.py:70-123 for the reversible
+ * stacks).  Same conventions as above; gradient accumulators are fp32 and are ADDED to unless stated.
+ * ================================================================================================= */
+
+/* out_f32[M,N] += A[M,K] @ W[N,K]^T with the contraction split over up to `splits` work items per output tile (fp32
+ * atomics).  The weight-gradient GEMMs dW = dY^T X have a small output and a long contraction (K = tokens). */
+int nuwa_gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out_f32,
+                          int ld_out, int splits, int force_bn, void* stream);
+
+/* Batched small GEMM on mma.sync (attention backward products), see csrc/bgemm.cu.
+ *   C[i1][i2] (M x N) = alpha * A(M x K) * B(K x N)  (+ C if accumulate; fp32 C only)
+ *   A(m,k) = a_trans ? A[k*lda + m] : A[m*lda + k] ;  B(k,n) = b_trans ? B[k*ldb + n] : B[n*ldb + k]   (bf16)
+ * batch offsets (elements): i1*x_s1 + i2*x_s2.  lda/ldb and the batch strides must be multiples of 8. */
+typedef struct {
+  const void* A;
+  const void* B;
+  void* C;
+  int M, N, K;
+  int a_trans, b_trans;
+  long long lda, ldb, ldc;
+  int batch1, batch2;
+  long long a_s1, a_s2, b_s1, b_s2, c_s1, c_s2;
+  float alpha;
+  int c_bf16, accumulate;
+} nuwa_bgemm_params;
+int nuwa_bgemm(const nuwa_bgemm_params* p, void* stream);
+
+/* LayerNorm / StableLayerNorm backward of rows (b, t), nt rows per sample (nn.LayerNorm in SandwichNorm,
+ * nuwa_pytorch.py:112-128; StableLayerNorm :88-95).  dout is fp32 or bf16 (exactly one non-NULL).  unshift = 1: the
+ * normalised row went through ShiftVideoTokens (:200-253) before its consumer, so the upstream gradient of the first /
+ * second channel quarter is read from the row one grid-row below / one column right (zero at the borders).
+ * x (+ x2): the forward input of the norm; stable = 1: LN(x / amax(x)).  Outputs: dx as bf16 and/or fp32 (dx_f32 and
+ * dx2_f32 are accumulated into when accumulate = 1).  part: [ln_bwd_grid(rows)][3][D] fp32 per-CTA partial sums of
+ * dweight, dbias and colsum(dx); reduce with nuwa_reduce_partials. */
+typedef struct {
+  int rows, nt, D;
+  const float* dout_f32;
+  const void* dout_bf16;
+  int unshift, fmap;
+  const float* x;
+  const float* x2;
+  int stable;
+  const float* w;
+  float eps;
+  void* dx_bf16;
+  float* dx_f32;
+  float* dx2_f32;
+  int accumulate;
+  float* part;
+} nuwa_lnbwd_params;
+int nuwa_ln_bwd_grid(int rows);
+int nuwa_ln_bwd(const nuwa_lnbwd_params* p, void* stream);
+/* o0[c] += sum_p part[p][0][c], o1 <- [1], o2 <- [2]  (NULL outputs skipped) */
+int nuwa_reduce_partials(const float* part, int nparts, int D, float* o0, float* o1, float* o2, void* stream);
+
+/* bf16 [R][ld_in] -> [C][ld_out] */
+int nuwa_transpose_bf16(const void* in, long long ld_in, void* out, long long ld_out, int R, int C, void* stream);
+
+/* GEGLU (nuwa_pytorch.py:255-258) on the pair-packed pre-activation h [M][2*ip] (see NUWA_ACT_GEGLU): g [M][ip] and its
+ * backward dh [M][2*ip] from dg [M][ip] */
+int nuwa_geglu_fwd(const void* h, void* g, long long M, int ip, void* stream);
+int nuwa_geglu_bwd(const void* dg, const void* h, void* dh, long long M, int ip, void* stream);
+
+/* d mean-cross-entropy / d logits (F.cross_entropy, nuwa_pytorch.py:1963): bf16 dlogits = (softmax - onehot) * (*gscale) / rows;
+ * gscale: device scalar (the incoming grad_output) or NULL = 1 */
+int nuwa_ce_bwd(const float* logits, int ld, const long long* target, const float* gscale, void* dlogits, int ld_out,
+                int rows, int V, void* stream);
+
+/* Embedding (+frac_gradient, nuwa_pytorch.py:1659-1671), AxialPositionalEmbedding (:1693-1709) and bos backward */
+typedef struct {
+  const float* dx;        /* [B*nt][D] */
+  const long long* idx;
+  long long idx_bs;
+  float* dtable;          /* [V][D] += frac * dx */
+  float* dbos;            /* [D] or NULL */
+  float* dax1;
+  float* dax2;
+  float* dax3;
+  int d2, d3;
+  int has_bos, B, nt, D;
+  float frac;
+} nuwa_embed_bwd_params;
+int nuwa_embed_bwd(const nuwa_embed_bwd_params* p, void* stream);
+
+/* inverse rotation of the gradient of the rotated q|k|v (nuwa_pytorch.py:149-153): fp32 in, bf16 out */
+int nuwa_rotary_bwd_to_bf16(const float* dqkv, void* out, const float* inv_freq, int rows, int n, int H, int dh, int rot,
+                            void* stream);
+
+/* dst[map[r]][0:cols] (+)= src[r][0:cols] (map NULL = identity; negative = skip): un-packs padded / pair-packed gradients */
+int nuwa_add_rows_f32(float* dst, long long ld_dst, const float* src, long long ld_src, const int* map, int rows, int cols,
+                      int accumulate, void* stream);
+
+/* ---- attention backward --------------------------------------------------------------------
+ * Shared row kernel: softmax + talking-heads forward/backward on materialised logits.
+ *   S, dPp fp32 [B][H][nq][jp] (logits incl. scale and masks; dPp = dO V^T) -> Pp (= P', bf16), dS (bf16, x out_scale),
+ *   dtalk[H][H] += sum dPp[g] P[h].   J valid slots per row, pad slots of the outputs are zeroed. */
+typedef struct {
+  const float* S;
+  const float* dPp;
+  void* Pp;
+  void* dS;
+  const float* talk; /* [H][H] or NULL (identity) */
+  float* dtalk;      /* [H][H] or NULL */
+  int B, H, nq, J, jp;
+  float out_scale;
+} nuwa_attn_rows_params;
+int nuwa_attn_bwd_rows(const nuwa_attn_rows_params* p, void* stream);
+/* dense attention (nuwa_pytorch.py:339-378): K / V with the learned null slot prepended, zero padded to jp rows */
+int nuwa_kv_full_build(const void* k, const void* v, long long kv_bs, int kv_rs, const float* null_k, const float* null_v,
+                       void* kfull, void* vfull, int B, int nk, int jp, int inner, void* stream);
+int nuwa_kv_full_split(const float* dkfull, const float* dvfull, float* dnull_k, float* dnull_v, void* dk16, void* dv16,
+                       float* dk32, float* dv32, long long o_bs, int o_rs, int B, int nk, int jp, int inner, void* stream);
+int nuwa_mask_scores(float* S, const unsigned char* mask, int mask_bs, int B, int H, int nq, int jp, int nk, int has_null,
+                     void* stream);
+/* Sparse3DNA (nuwa_pytorch.py:490-608): p describes the NON-bos queries (p.t0 >= 1, p.q = first such row) */
+int nuwa_attn3dna_bwd_scores(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp,
+                             int jp, void* stream);
+int nuwa_attn3dna_bwd_dq(const nuwa_attn_params* p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs,
+                         void* stream);
+int nuwa_attn3dna_bwd_dkdv(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, const void* dS,
+                           const void* Pp, int jp, void* dk, void* dv, long long dkv_bs, int dkv_rs, void* stream);
+/* slot 0 (bos key / null key): out_k[b] += sum_q dS[b,h,q,0] q[b,q] ; out_v[b] += sum_q Pp[b,h,q,0] dO[b,q] */
+int nuwa_attn_bwd_first_key(const void* q, long long q_bs, int q_rs, const void* dO, long long do_bs, int do_rs,
+                            const void* dS, const void* Pp, int jp, int B, int H, int dh, int nq, float* out_k,
+                            float* out_v, long long ok_bs, void* stream);
+int nuwa_attn3dna_bwd_first_key_finalize(const float* tmp_k, const float* tmp_v, const void* dO_bos, long long do_bs,
+                                         void* dqkv, long long dqkv_bs, int inner, int B, void* stream);
+/* sizeof of the five backward parameter structs (bgemm, lnbwd, embed_bwd, attn_rows, -) for binding checks */
+void nuwa_struct_sizes_bwd(int* out4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,32 @@ class EmbedParams(ctypes.Structure):  # mirrors nuwa_embed_params
                 ("has_bos", c_int), ("t0", c_int), ("B", c_int), ("nt", c_int), ("D", c_int), ("t0_ptr", c_void_p)]
 
 
+class BgemmParams(ctypes.Structure):  # mirrors nuwa_bgemm_params
+    _fields_ = [("A", c_void_p), ("B", c_void_p), ("C", c_void_p), ("M", c_int), ("N", c_int), ("K", c_int),
+                ("a_trans", c_int), ("b_trans", c_int), ("lda", c_ll), ("ldb", c_ll), ("ldc", c_ll),
+                ("batch1", c_int), ("batch2", c_int), ("a_s1", c_ll), ("a_s2", c_ll), ("b_s1", c_ll), ("b_s2", c_ll),
+                ("c_s1", c_ll), ("c_s2", c_ll), ("alpha", c_float), ("c_bf16", c_int), ("accumulate", c_int)]
+
+
+class LnBwdParams(ctypes.Structure):  # mirrors nuwa_lnbwd_params
+    _fields_ = [("rows", c_int), ("nt", c_int), ("D", c_int), ("dout_f32", c_void_p), ("dout_bf16", c_void_p),
+                ("unshift", c_int), ("fmap", c_int), ("x", c_void_p), ("x2", c_void_p), ("stable", c_int),
+                ("w", c_void_p), ("eps", c_float), ("dx_bf16", c_void_p), ("dx_f32", c_void_p), ("dx2_f32", c_void_p),
+                ("accumulate", c_int), ("part", c_void_p)]
+
+
+class EmbedBwdParams(ctypes.Structure):  # mirrors nuwa_embed_bwd_params
+    _fields_ = [("dx", c_void_p), ("idx", c_void_p), ("idx_bs", c_ll), ("dtable", c_void_p), ("dbos", c_void_p),
+                ("dax1", c_void_p), ("dax2", c_void_p), ("dax3", c_void_p), ("d2", c_int), ("d3", c_int),
+                ("has_bos", c_int), ("B", c_int), ("nt", c_int), ("D", c_int), ("frac", c_float)]
+
+
+class AttnRowsParams(ctypes.Structure):  # mirrors nuwa_attn_rows_params
+    _fields_ = [("S", c_void_p), ("dPp", c_void_p), ("Pp", c_void_p), ("dS", c_void_p), ("talk", c_void_p),
+                ("dtalk", c_void_p), ("B", c_int), ("H", c_int), ("nq", c_int), ("J", c_int), ("jp", c_int),
+                ("out_scale", c_float)]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES).  Must list EVERY symbol of include/nuwa_b200.h.
 SIGNATURES = {
     "nuwa_abi_version": [],
@@ -77,9 +103,36 @@ SIGNATURES = {
     "nuwa_vq_argmax": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "nuwa_gather_rows": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "nuwa_conv1x1_nhwc_to_nchw": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    # ---- training (backward) ----
+    "nuwa_gemm_bf16_splitk": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+    "nuwa_bgemm": [P(BgemmParams), c_void_p],
+    "nuwa_ln_bwd_grid": [c_int],
+    "nuwa_ln_bwd": [P(LnBwdParams), c_void_p],
+    "nuwa_reduce_partials": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "nuwa_transpose_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p],
+    "nuwa_geglu_fwd": [c_void_p, c_void_p, c_ll, c_int, c_void_p],
+    "nuwa_geglu_bwd": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
+    "nuwa_ce_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "nuwa_embed_bwd": [P(EmbedBwdParams), c_void_p],
+    "nuwa_rotary_bwd_to_bf16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "nuwa_add_rows_f32": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p],
+    "nuwa_attn_bwd_rows": [P(AttnRowsParams), c_void_p],
+    "nuwa_kv_full_build": [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                           c_int, c_void_p],
+    "nuwa_kv_full_split": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int,
+                           c_int, c_int, c_int, c_int, c_void_p],
+    "nuwa_mask_scores": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "nuwa_attn3dna_bwd_scores": [P(AttnParams), c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    "nuwa_attn3dna_bwd_dq": [P(AttnParams), c_void_p, c_int, c_void_p, c_ll, c_int, c_void_p],
+    "nuwa_attn3dna_bwd_dkdv": [P(AttnParams), c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll,
+                               c_int, c_void_p],
+    "nuwa_attn_bwd_first_key": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p],
+    "nuwa_attn3dna_bwd_first_key_finalize": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p],
+    "nuwa_struct_sizes_bwd": [P(c_int)],
 }
 _RESTYPES = {"nuwa_strerror": ctypes.c_char_p, "nuwa_launch_count": ctypes.c_ulonglong, "nuwa_struct_sizes": None,
-             "nuwa_gemm_prof_enable": None}
+             "nuwa_gemm_prof_enable": None, "nuwa_struct_sizes_bwd": None}
 
 _lib = None
 
@@ -106,6 +159,11 @@ def lib():
         mine = (ctypes.sizeof(LnParams), ctypes.sizeof(AttnParams), ctypes.sizeof(EmbedParams))
         if tuple(sizes) != mine:
             raise NuwaB200Error(f"struct layout mismatch between include/nuwa_b200.h {tuple(sizes)} and _lib.py {mine}")
+        sizes = (c_int * 4)()
+        handle.nuwa_struct_sizes_bwd(sizes)
+        mine = tuple(ctypes.sizeof(c) for c in (BgemmParams, LnBwdParams, EmbedBwdParams, AttnRowsParams))
+        if tuple(sizes) != mine:
+            raise NuwaB200Error(f"backward struct layout mismatch: include/nuwa_b200.h {tuple(sizes)} vs _lib.py {mine}")
         _lib = handle
     return _lib
 

@@ -126,3 +126,80 @@ extern "C" void nuwa_struct_sizes(int* out3) {
   out3[1] = (int)sizeof(nuwa_attn_params);
   out3[2] = (int)sizeof(nuwa_embed_params);
 }
+
+// ---------------- training (backward) entry points ----------------
+extern "C" {
+int nuwa_gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out_f32,
+                          int ld_out, int splits, int force_bn, void* stream) {
+  return gemm_bf16(A, lda, W, ldw, M, N, K, nullptr, nullptr, 0, out_f32, nullptr, ld_out, ACT_NONE, force_bn, S(stream),
+                   splits < 2 ? 2 : splits);
+}
+int nuwa_bgemm(const nuwa_bgemm_params* p, void* stream) { return p ? bgemm(*p, S(stream)) : NUWA_ERR_INVALID; }
+int nuwa_ln_bwd_grid(int rows) { return ln_bwd_grid(rows); }
+int nuwa_ln_bwd(const nuwa_lnbwd_params* p, void* stream) { return p ? ln_bwd(*p, S(stream)) : NUWA_ERR_INVALID; }
+int nuwa_reduce_partials(const float* part, int nparts, int D, float* o0, float* o1, float* o2, void* stream) {
+  return reduce_partials(part, nparts, D, o0, o1, o2, S(stream));
+}
+int nuwa_transpose_bf16(const void* in, long long ld_in, void* out, long long ld_out, int R, int C, void* stream) {
+  return transpose_bf16(in, ld_in, out, ld_out, R, C, S(stream));
+}
+int nuwa_geglu_fwd(const void* h, void* g, long long M, int ip, void* stream) { return geglu_fwd(h, g, M, ip, S(stream)); }
+int nuwa_geglu_bwd(const void* dg, const void* h, void* dh, long long M, int ip, void* stream) {
+  return geglu_bwd(dg, h, dh, M, ip, S(stream));
+}
+int nuwa_ce_bwd(const float* logits, int ld, const long long* target, const float* gscale, void* dlogits, int ld_out,
+                int rows, int V, void* stream) {
+  return ce_bwd(logits, ld, target, gscale, dlogits, ld_out, rows, V, S(stream));
+}
+int nuwa_embed_bwd(const nuwa_embed_bwd_params* p, void* stream) { return p ? embed_bwd(*p, S(stream)) : NUWA_ERR_INVALID; }
+int nuwa_rotary_bwd_to_bf16(const float* dqkv, void* out, const float* inv_freq, int rows, int n, int H, int dh, int rot,
+                            void* stream) {
+  return rotary_bwd_to_bf16(dqkv, out, inv_freq, rows, n, H, dh, rot, S(stream));
+}
+int nuwa_add_rows_f32(float* dst, long long ld_dst, const float* src, long long ld_src, const int* map, int rows, int cols,
+                      int accumulate, void* stream) {
+  return add_rows_f32(dst, ld_dst, src, ld_src, map, rows, cols, accumulate, S(stream));
+}
+int nuwa_attn_bwd_rows(const nuwa_attn_rows_params* p, void* stream) {
+  return p ? attn_bwd_rows(*p, S(stream)) : NUWA_ERR_INVALID;
+}
+int nuwa_kv_full_build(const void* k, const void* v, long long kv_bs, int kv_rs, const float* null_k, const float* null_v,
+                       void* kfull, void* vfull, int B, int nk, int jp, int inner, void* stream) {
+  return kv_full_build(k, v, kv_bs, kv_rs, null_k, null_v, kfull, vfull, B, nk, jp, inner, S(stream));
+}
+int nuwa_kv_full_split(const float* dkfull, const float* dvfull, float* dnull_k, float* dnull_v, void* dk16, void* dv16,
+                       float* dk32, float* dv32, long long o_bs, int o_rs, int B, int nk, int jp, int inner, void* stream) {
+  return kv_full_split(dkfull, dvfull, dnull_k, dnull_v, dk16, dv16, dk32, dv32, o_bs, o_rs, B, nk, jp, inner, S(stream));
+}
+int nuwa_mask_scores(float* Sc, const unsigned char* mask, int mask_bs, int B, int H, int nq, int jp, int nk, int has_null,
+                     void* stream) {
+  return mask_scores(Sc, mask, mask_bs, B, H, nq, jp, nk, has_null, S(stream));
+}
+int nuwa_attn3dna_bwd_scores(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* Sc, float* dPp,
+                             int jp, void* stream) {
+  return p ? attn3dna_bwd_scores(*p, dO, do_bs, do_rs, Sc, dPp, jp, S(stream)) : NUWA_ERR_INVALID;
+}
+int nuwa_attn3dna_bwd_dq(const nuwa_attn_params* p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs,
+                         void* stream) {
+  return p ? attn3dna_bwd_dq(*p, dS, jp, dq, dq_bs, dq_rs, S(stream)) : NUWA_ERR_INVALID;
+}
+int nuwa_attn3dna_bwd_dkdv(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, const void* dS,
+                           const void* Pp, int jp, void* dk, void* dv, long long dkv_bs, int dkv_rs, void* stream) {
+  return p ? attn3dna_bwd_dkdv(*p, dO, do_bs, do_rs, dS, Pp, jp, dk, dv, dkv_bs, dkv_rs, S(stream)) : NUWA_ERR_INVALID;
+}
+int nuwa_attn_bwd_first_key(const void* q, long long q_bs, int q_rs, const void* dO, long long do_bs, int do_rs,
+                            const void* dS, const void* Pp, int jp, int B, int H, int dh, int nq, float* out_k,
+                            float* out_v, long long ok_bs, void* stream) {
+  return attn_bwd_first_key(q, q_bs, q_rs, dO, do_bs, do_rs, dS, Pp, jp, B, H, dh, nq, out_k, out_v, ok_bs, S(stream));
+}
+int nuwa_attn3dna_bwd_first_key_finalize(const float* tmp_k, const float* tmp_v, const void* dO_bos, long long do_bs,
+                                         void* dqkv, long long dqkv_bs, int inner, int B, void* stream) {
+  return attn3dna_bwd_first_key_finalize(tmp_k, tmp_v, dO_bos, do_bs, dqkv, dqkv_bs, inner, B, S(stream));
+}
+void nuwa_struct_sizes_bwd(int* out4) {
+  out4[0] = (int)sizeof(nuwa_bgemm_params);
+  out4[1] = (int)sizeof(nuwa_lnbwd_params);
+  out4[2] = (int)sizeof(nuwa_embed_bwd_params);
+  out4[3] = (int)sizeof(nuwa_attn_rows_params);
+}
+}

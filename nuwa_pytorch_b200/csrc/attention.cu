@@ -522,3 +522,313 @@ int attn_decode_dense(const AttnParams& p, cudaStream_t s) { return launch_attn_
 int attn_decode_cross2dna(const AttnParams& p, cudaStream_t s) { return launch_attn_decode<MODE_X2DNA>(p, s); }
 
 }  // namespace nuwa
+
+// ================================================================================================
+// Backward of the gather attentions (Sparse3DNA / SparseCross2DNA), see backward.cu for the shared row kernel.
+//   gather_scores : per query, S[h][j] = qscale q.k_j (masked slots -FLT_MAX, zero keys 0) and dP'[h][j] = dO.v_j
+//   gather_dq     : dq = sum_j dS[h][j] k_j               (dS already carries qscale)
+//   gather_dkdv   : key-centric -- every key row sums over the queries whose window contains it (inverse of key_of),
+//                   no atomics, deterministic
+//   first_key     : slot 0 (bos key of Sparse3DNA / null key of SparseCross2DNA) is seen by every query: column reduction
+// Score / probability tensors are [B][H][nq][jp] with nq = the non-bos queries (absolute positions t0 .. t0+nq-1).
+// ================================================================================================
+namespace nuwa {
+
+template <int MODE, int CPL>
+__global__ void __launch_bounds__(128) gather_scores_kernel(const AttnParams p, const bf16* __restrict__ dO, long long do_bs,
+                                                            int do_rs, float* __restrict__ S, float* __restrict__ dPp, int jp) {
+  extern __shared__ float smem_g[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int lph = 32 / p.H, h = lane / lph, sub = lane - h * lph;
+  const int J = p.jmax;
+  float* Ss = smem_g + (size_t)warp * (2 * p.H * J + J);  // [H][J] scores, [H][J] dP', [J] keys
+  float* Ds = Ss + p.H * J;
+  int* keys = reinterpret_cast<int*>(Ds + p.H * J);
+  const long long gidx = blockIdx.x * (long long)wpb + warp;
+  if (gidx >= (long long)p.B * p.nq) return;
+  const int b = (int)(gidx / p.nq), ql = (int)(gidx - (long long)b * p.nq);
+  const int t = p.t0 + ql;
+  const int ch = lane * CPL;
+  const bf16* kb = reinterpret_cast<const bf16*>(p.k) + (long long)b * p.k_bs;
+  const bf16* vb = reinterpret_cast<const bf16*>(p.v) + (long long)b * p.v_bs;
+  float qf[CPL], df[CPL];
+  load_row<CPL>(reinterpret_cast<const bf16*>(p.q) + (long long)b * p.q_bs + (long long)ql * p.q_rs + ch, qf);
+  load_row<CPL>(dO + (long long)b * do_bs + (long long)ql * do_rs + ch, df);
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) qf[c] *= p.qscale;
+  for (int j = lane; j < J; j += 32) {
+    int row = 0;
+    const int kind = key_of<MODE>(p, b, t, p.nv, j, row);
+    keys[j] = (kind << 28) | row;
+  }
+  __syncwarp();
+  for (int j = 0; j < J; ++j) {
+    const int kj = keys[j];
+    const int row = kj & 0x0FFFFFFF, kind = kj >> 28;
+    float s, d = 0.f;
+    if (kind == KEY_NORMAL || kind == KEY_NULL) {
+      float kf[CPL], vf[CPL];
+      if (kind == KEY_NULL) {
+        load_row_f32<CPL>(p.null_k + ch, kf);
+        load_row_f32<CPL>(p.null_v + ch, vf);
+      } else {
+        load_row<CPL>(kb + (long long)row * p.k_rs + ch, kf);
+        load_row<CPL>(vb + (long long)row * p.v_rs + ch, vf);
+      }
+      s = 0.f;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        s = fmaf(qf[c], kf[c], s);
+        d = fmaf(df[c], vf[c], d);
+      }
+      for (int o = lph >> 1; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+      }
+    } else {
+      s = (kind == KEY_MASKED) ? -FLT_MAX : 0.f;
+    }
+    if (sub == 0) {
+      Ss[h * J + j] = s;
+      Ds[h * J + j] = d;
+    }
+  }
+  __syncwarp();
+  for (int hh = 0; hh < p.H; ++hh) {
+    const long long o = (((long long)b * p.H + hh) * p.nq + ql) * jp;
+    for (int j = lane; j < J; j += 32) {
+      S[o + j] = Ss[hh * J + j];
+      dPp[o + j] = Ds[hh * J + j];
+    }
+  }
+}
+
+template <int MODE, int CPL>
+__global__ void __launch_bounds__(128) gather_dq_kernel(const AttnParams p, const bf16* __restrict__ dS, int jp,
+                                                        bf16* __restrict__ dq, long long dq_bs, int dq_rs) {
+  extern __shared__ float smem_g[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int lph = 32 / p.H, h = lane / lph;
+  const int J = p.jmax;
+  float* Ds = smem_g + (size_t)warp * (p.H * J + J);
+  int* keys = reinterpret_cast<int*>(Ds + p.H * J);
+  const long long gidx = blockIdx.x * (long long)wpb + warp;
+  if (gidx >= (long long)p.B * p.nq) return;
+  const int b = (int)(gidx / p.nq), ql = (int)(gidx - (long long)b * p.nq);
+  const int t = p.t0 + ql;
+  const int ch = lane * CPL;
+  const bf16* kb = reinterpret_cast<const bf16*>(p.k) + (long long)b * p.k_bs;
+  for (int j = lane; j < J; j += 32) {
+    int row = 0;
+    const int kind = key_of<MODE>(p, b, t, p.nv, j, row);
+    keys[j] = (kind << 28) | row;
+  }
+  for (int hh = 0; hh < p.H; ++hh) {
+    const long long o = (((long long)b * p.H + hh) * p.nq + ql) * jp;
+    for (int j = lane; j < J; j += 32) Ds[hh * J + j] = __bfloat162float(dS[o + j]);
+  }
+  __syncwarp();
+  float acc[CPL];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
+  for (int j = 0; j < J; ++j) {
+    const int kj = keys[j];
+    const int row = kj & 0x0FFFFFFF, kind = kj >> 28;
+    if (kind != KEY_NORMAL && kind != KEY_NULL) continue;
+    float kf[CPL];
+    if (kind == KEY_NULL) load_row_f32<CPL>(p.null_k + ch, kf);
+    else load_row<CPL>(kb + (long long)row * p.k_rs + ch, kf);
+    const float w = Ds[h * J + j];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) acc[c] = fmaf(w, kf[c], acc[c]);
+  }
+  store_row<CPL>(dq + (long long)b * dq_bs + (long long)ql * dq_rs + ch, acc);
+}
+
+// Sparse3DNA key-centric pass: key row r (video token r-1) <- queries (f,y,x) = key - offset*dil + P  (inverse of key_of)
+template <int CPL>
+__global__ void __launch_bounds__(128)
+gather_dkdv_3dna_kernel(const AttnParams p, const bf16* __restrict__ dO, long long do_bs, int do_rs,
+                        const bf16* __restrict__ dS, const bf16* __restrict__ Pp, int jp, bf16* __restrict__ dk,
+                        bf16* __restrict__ dv, long long dkv_bs, int dkv_rs) {
+  extern __shared__ float smem_g[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int lph = 32 / p.H, h = lane / lph;
+  const int J = p.jmax;
+  int* inv = reinterpret_cast<int*>(smem_g) + (size_t)warp * J;  // (query local index << 8) | slot, or -1
+  const long long gidx = blockIdx.x * (long long)wpb + warp;
+  if (gidx >= (long long)p.B * p.nv) return;
+  const int b = (int)(gidx / p.nv), kidx = (int)(gidx - (long long)b * p.nv);  // video token index of this key
+  const int T = p.fmap * p.fmap;
+  const int kf_ = kidx / T, ky = (kidx % T) / p.fmap, kx = kidx % p.fmap;
+  const int pf = p.dt * (p.kt - 1) / 2, ph = p.dh_ * (p.kh - 1) / 2, pw = p.dw * (p.kw - 1) / 2;
+  const int Pf = p.causal ? 2 * pf : pf, Ph = p.causal ? 2 * ph : ph, Pw = p.causal ? 2 * pw : pw;
+  for (int jj = lane; jj < J - 1; jj += 32) {
+    const int c = jj % p.kw, bq = (jj / p.kw) % p.kh, a = jj / (p.kw * p.kh);
+    const int qf_ = kf_ - a * p.dt + Pf, qy = ky - bq * p.dh_ + Ph, qx = kx - c * p.dw + Pw;
+    int e = -1;
+    if (qf_ >= 0 && qf_ < p.max_frames && qy >= 0 && qy < p.fmap && qx >= 0 && qx < p.fmap) {
+      const int qidx = (qf_ * p.fmap + qy) * p.fmap + qx;  // video token index of the query; its position is 1 + qidx
+      const int ql = 1 + qidx - p.t0;
+      if (ql >= 0 && ql < p.nq) e = (ql << 8) | (jj + 1);
+    }
+    inv[jj] = e;
+  }
+  __syncwarp();
+  const int ch = lane * CPL;
+  const bf16* qb = reinterpret_cast<const bf16*>(p.q) + (long long)b * p.q_bs;
+  const bf16* dob = dO + (long long)b * do_bs;
+  float ak[CPL], av[CPL];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) ak[c] = av[c] = 0.f;
+  const long long hb = ((long long)b * p.H + h) * p.nq;
+  for (int jj = 0; jj < J - 1; ++jj) {
+    const int e = inv[jj];
+    if (e < 0) continue;
+    const int ql = e >> 8, j = e & 255;
+    const float ws = __bfloat162float(dS[(hb + ql) * jp + j]);
+    const float wp = __bfloat162float(Pp[(hb + ql) * jp + j]);
+    float qv[CPL], dv_[CPL];
+    load_row<CPL>(qb + (long long)ql * p.q_rs + ch, qv);
+    load_row<CPL>(dob + (long long)ql * do_rs + ch, dv_);
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      ak[c] = fmaf(ws, qv[c], ak[c]);
+      av[c] = fmaf(wp, dv_[c], av[c]);
+    }
+  }
+  const long long o = (long long)b * dkv_bs + (long long)(1 + kidx) * dkv_rs + ch;
+  store_row<CPL>(dk + o, ak);
+  store_row<CPL>(dv + o, av);
+}
+
+// slot-0 key (seen by every query): out_k[b][c] += sum_q dS[b][h][q][0] Q[b][q][c] ; out_v[b][c] += sum_q P'[..][0] dO[b][q][c]
+// grid (chunks, B), block = inner threads; ok_bs = 0 accumulates all samples into one vector (learned null key).
+__global__ void __launch_bounds__(1024)
+first_key_kernel(const bf16* __restrict__ q, long long q_bs, int q_rs, const bf16* __restrict__ dO, long long do_bs, int do_rs,
+                 const bf16* __restrict__ dS, const bf16* __restrict__ Pp, int jp, int H, int dh, int nq, int chunk,
+                 float* __restrict__ out_k, float* __restrict__ out_v, long long ok_bs) {
+  const int b = blockIdx.y, c = threadIdx.x, h = c / dh;
+  const int q0 = blockIdx.x * chunk, q1 = min(nq, q0 + chunk);
+  float ak = 0.f, av = 0.f;
+  const long long hb = ((long long)b * H + h) * nq;
+  for (int ql = q0; ql < q1; ++ql) {
+    const float ws = __bfloat162float(dS[(hb + ql) * jp]);
+    const float wp = __bfloat162float(Pp[(hb + ql) * jp]);
+    ak = fmaf(ws, __bfloat162float(q[(long long)b * q_bs + (long long)ql * q_rs + c]), ak);
+    av = fmaf(wp, __bfloat162float(dO[(long long)b * do_bs + (long long)ql * do_rs + c]), av);
+  }
+  atomicAdd(out_k + (long long)b * ok_bs + c, ak);
+  atomicAdd(out_v + (long long)b * ok_bs + c, av);
+}
+// Sparse3DNA row 0 of d(q|k|v): dq = 0 (the bos query copies its value, :608), dk = tmp_k, dv = tmp_v + dO[bos]
+__global__ void __launch_bounds__(256)
+first_key_finalize_kernel(const float* __restrict__ tmp_k, const float* __restrict__ tmp_v, const bf16* __restrict__ dO_bos,
+                          long long do_bs, bf16* __restrict__ dqkv, long long dqkv_bs, int inner, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * inner) return;
+  const int b = i / inner, c = i - b * inner;
+  bf16* o = dqkv + (long long)b * dqkv_bs;
+  o[c] = __float2bfloat16(0.f);
+  o[inner + c] = __float2bfloat16(tmp_k[(long long)b * inner + c]);
+  o[2 * inner + c] = __float2bfloat16(tmp_v[(long long)b * inner + c] + __bfloat162float(dO_bos[(long long)b * do_bs + c]));
+}
+
+#define NUWA_CPL_SWITCH(cpl, CALL)      \
+  switch (cpl) {                        \
+    case 16: { CALL(16); } break;       \
+    case 8: { CALL(8); } break;         \
+    case 4: { CALL(4); } break;         \
+    case 2: { CALL(2); } break;         \
+    case 1: { CALL(1); } break;         \
+    default: return NUWA_ERR_INVALID;   \
+  }
+
+template <int MODE>
+static int launch_gather_scores(const AttnParams& p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp, int jp,
+                                cudaStream_t stream) {
+  const int inner = p.H * p.dh;
+  if (inner % 32 != 0 || (32 % p.H) != 0 || p.H > 32 || jp < p.jmax) return NUWA_ERR_INVALID;
+  const int cpl = inner / 32, warps = 4;
+  const size_t smem = (size_t)warps * (2 * p.H * p.jmax + p.jmax) * sizeof(float);
+  if (smem > 200 * 1024) return NUWA_ERR_INVALID;
+  const long long groups = (long long)p.B * p.nq;
+  if (groups <= 0) return NUWA_OK;
+  const unsigned grid = (unsigned)((groups + warps - 1) / warps);
+#define CALL(C)                                                                                                      \
+  if (smem > 48 * 1024)                                                                                              \
+    cudaFuncSetAttribute(gather_scores_kernel<MODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+  gather_scores_kernel<MODE, C><<<grid, warps * 32, smem, stream>>>(p, reinterpret_cast<const bf16*>(dO), do_bs, do_rs, S, dPp, jp)
+  NUWA_CPL_SWITCH(cpl, CALL)
+#undef CALL
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+template <int MODE>
+static int launch_gather_dq(const AttnParams& p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs,
+                            cudaStream_t stream) {
+  const int inner = p.H * p.dh;
+  if (inner % 32 != 0 || (32 % p.H) != 0 || p.H > 32 || jp < p.jmax) return NUWA_ERR_INVALID;
+  const int cpl = inner / 32, warps = 4;
+  const size_t smem = (size_t)warps * (p.H * p.jmax + p.jmax) * sizeof(float);
+  if (smem > 200 * 1024) return NUWA_ERR_INVALID;
+  const long long groups = (long long)p.B * p.nq;
+  if (groups <= 0) return NUWA_OK;
+  const unsigned grid = (unsigned)((groups + warps - 1) / warps);
+#define CALL(C)                                                                                                  \
+  if (smem > 48 * 1024)                                                                                          \
+    cudaFuncSetAttribute(gather_dq_kernel<MODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+  gather_dq_kernel<MODE, C><<<grid, warps * 32, smem, stream>>>(p, reinterpret_cast<const bf16*>(dS), jp,        \
+                                                                 reinterpret_cast<bf16*>(dq), dq_bs, dq_rs)
+  NUWA_CPL_SWITCH(cpl, CALL)
+#undef CALL
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+
+int attn3dna_bwd_scores(const AttnParams& p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp, int jp,
+                        cudaStream_t s) {
+  return launch_gather_scores<MODE_3DNA>(p, dO, do_bs, do_rs, S, dPp, jp, s);
+}
+int attn3dna_bwd_dq(const AttnParams& p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs, cudaStream_t s) {
+  return launch_gather_dq<MODE_3DNA>(p, dS, jp, dq, dq_bs, dq_rs, s);
+}
+int attn3dna_bwd_dkdv(const AttnParams& p, const void* dO, long long do_bs, int do_rs, const void* dS, const void* Pp, int jp,
+                      void* dk, void* dv, long long dkv_bs, int dkv_rs, cudaStream_t stream) {
+  const int inner = p.H * p.dh;
+  if (inner % 32 != 0 || (32 % p.H) != 0 || p.H > 32 || p.jmax > 255 || p.nv <= 0) return NUWA_ERR_INVALID;
+  const int cpl = inner / 32, warps = 4;
+  const size_t smem = (size_t)warps * p.jmax * sizeof(int);
+  const long long groups = (long long)p.B * p.nv;
+  const unsigned grid = (unsigned)((groups + warps - 1) / warps);
+#define CALL(C)                                                                                                      \
+  gather_dkdv_3dna_kernel<C><<<grid, warps * 32, smem, stream>>>(                                                    \
+      p, reinterpret_cast<const bf16*>(dO), do_bs, do_rs, reinterpret_cast<const bf16*>(dS),                         \
+      reinterpret_cast<const bf16*>(Pp), jp, reinterpret_cast<bf16*>(dk), reinterpret_cast<bf16*>(dv), dkv_bs, dkv_rs)
+  NUWA_CPL_SWITCH(cpl, CALL)
+#undef CALL
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+int attn_bwd_first_key(const void* q, long long q_bs, int q_rs, const void* dO, long long do_bs, int do_rs, const void* dS,
+                       const void* Pp, int jp, int B, int H, int dh, int nq, float* out_k, float* out_v, long long ok_bs,
+                       cudaStream_t stream) {
+  const int inner = H * dh;
+  if (inner > 1024 || inner <= 0 || B <= 0 || nq <= 0) return NUWA_ERR_INVALID;
+  const int chunk = 64;
+  dim3 grid(ceil_div(nq, chunk), B);
+  first_key_kernel<<<grid, inner, 0, stream>>>(reinterpret_cast<const bf16*>(q), q_bs, q_rs, reinterpret_cast<const bf16*>(dO),
+                                               do_bs, do_rs, reinterpret_cast<const bf16*>(dS),
+                                               reinterpret_cast<const bf16*>(Pp), jp, H, dh, nq, chunk, out_k, out_v, ok_bs);
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+int attn3dna_bwd_first_key_finalize(const float* tmp_k, const float* tmp_v, const void* dO_bos, long long do_bs, void* dqkv,
+                                    long long dqkv_bs, int inner, int B, cudaStream_t stream) {
+  first_key_finalize_kernel<<<ceil_div(B * inner, 256), 256, 0, stream>>>(tmp_k, tmp_v, reinterpret_cast<const bf16*>(dO_bos),
+                                                                          do_bs, reinterpret_cast<bf16*>(dqkv), dqkv_bs, inner, B);
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+
+}  // namespace nuwa

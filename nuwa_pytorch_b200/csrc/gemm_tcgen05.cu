@@ -122,6 +122,14 @@ __device__ __forceinline__ void epi_store16(const float* stg, int lane, const lo
     const float4 sv = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + c4);
     float o[4] = {sv.x, sv.y, sv.z, sv.w};
     const long long m = mrow[it];
+    if (p.atomic_out) {  // split-K partial product: out += (fp32 reduction in L2)
+      if (full) {
+        atomicAdd(reinterpret_cast<float4*>(p.out_f32 + m * p.ld_out + n), make_float4(o[0], o[1], o[2], o[3]));
+      } else {
+        for (int j = 0; j < 4 && n + j < n_out_total; ++j) atomicAdd(p.out_f32 + m * p.ld_out + n + j, o[j]);
+      }
+      continue;
+    }
     if (full) {
       if (p.residual != nullptr) {
         const float4 rr = *reinterpret_cast<const float4*>(p.residual + m * p.ld_res + n);
@@ -185,7 +193,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int total_items = p.num_m_tiles * p.num_n_tiles * p.splits;  // split-K: `splits` work items per output tile
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -222,7 +230,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t a_bytes = p.conv ? (uint32_t)(p.tb * p.th * p.tw * BK * 2) : (uint32_t)A_STAGE_BYTES;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int tile = item / p.splits, sp = item - tile * p.splits;
+        const int kb0 = sp * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         const TileCoord tc = tile_coord(tile, p.num_m_tiles, p.num_n_tiles);
         const int n0 = tc.nt * BN;
         int x0 = 0, y0 = 0, b0 = 0;
@@ -234,7 +244,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           y0 = yt * p.th;
           b0 = bt * p.tb;
         }
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
@@ -265,11 +275,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int sp = item % p.splits;
+        const int kb0 = sp * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -278,7 +290,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in (addr >> 4) units
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above retire
           if (++stage == Cfg::STAGES) {
@@ -306,8 +318,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     uint32_t acc_phase = 0;
     const bool pair = (p.act == ACT_GLU || p.act == ACT_GEGLU);
     const int n_out_total = pair ? p.N / 2 : p.N;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord(tile, p.num_m_tiles, p.num_n_tiles);
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const TileCoord tc = tile_coord(item / p.splits, p.num_m_tiles, p.num_n_tiles);
       const int n0 = tc.nt * BN;
       // rows this lane stores in the transposed phase: r = q*32 + it*8 + lane/4, it = 0..3
       long long mrow[4];
@@ -493,7 +505,16 @@ static int launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, GemmParams&
     attr_set = true;
   }
   p.num_n_tiles = ceil_div(p.N, BN);
-  int total = p.num_m_tiles * p.num_n_tiles;
+  if (p.splits <= 1) { p.splits = 1; p.kb_per_split = p.k_blocks; }
+  if (p.splits > 1) {  // as many work items as keep every SM busy, every split non-empty
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    int want = ceil_div(2 * device_sm_count(), tiles);
+    if (want > p.splits) want = p.splits;
+    if (want > p.k_blocks) want = p.k_blocks;
+    p.kb_per_split = ceil_div(p.k_blocks, want < 1 ? 1 : want);
+    p.splits = ceil_div(p.k_blocks, p.kb_per_split);
+  }
+  int total = p.num_m_tiles * p.num_n_tiles * p.splits;
   int grid = total < device_sm_count() ? total : device_sm_count();
   if (grid <= 0) return NUWA_OK;
   if (g_prof_on) cudaEventRecord(prof_event(), stream);
@@ -533,9 +554,11 @@ static bool epilogue_args_ok(const GemmParams& p) {
 
 int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
               const float* residual, int ld_res, float* out_f32, void* out_bf16, int ld_out, int act, int force_bn,
-              cudaStream_t stream) {
+              cudaStream_t stream, int splits) {
   if (M <= 0 || N <= 0 || K <= 0) return NUWA_ERR_INVALID;
-  if (M <= 32 && force_bn == 0) {  // decode-step products: weight-streaming bound, see gemm_skinny.cu
+  if (splits > 1 && (bias != nullptr || residual != nullptr || out_bf16 != nullptr || act != ACT_NONE || out_f32 == nullptr))
+    return NUWA_ERR_INVALID;  // split-K accumulates raw partial products into out_f32
+  if (M <= 32 && force_bn == 0 && splits <= 1) {  // decode-step products: weight-streaming bound, see gemm_skinny.cu
     const int rc = gemm_skinny(A, lda, W, ldw, M, N, K, bias, residual, ld_res, out_f32, out_bf16, ld_out, act, stream);
     if (rc != NUWA_ERR_INVALID) return rc;  // shapes outside its envelope fall through to the tensor-core kernel
   }
@@ -549,6 +572,8 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   p.bias = bias; p.residual = residual; p.ld_res = ld_res;
   p.out_f32 = out_f32; p.out_bf16 = reinterpret_cast<bf16*>(out_bf16); p.ld_out = ld_out; p.act = act;
   p.conv = 0;
+  p.splits = splits > 1 ? splits : 1;
+  p.atomic_out = splits > 1 ? 1 : 0;  // out_f32 += A W^T even when a single split turns out to be enough
   if (!epilogue_args_ok(p)) return NUWA_ERR_INVALID;
   CUtensorMap mA[4];
   uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M};

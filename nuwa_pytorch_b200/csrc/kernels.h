@@ -28,6 +28,8 @@ struct GemmParams {
   int8_t tap_map[16];
   int8_t tap_dx[16];
   int8_t tap_dy[16];
+  // split-K (weight-gradient GEMMs: small output, long contraction): item = tile * splits + split
+  int splits, kb_per_split, atomic_out;
 };
 
 typedef nuwa_attn_params AttnParams;
@@ -39,7 +41,7 @@ int device_sm_count();
 // gemm_tcgen05.cu
 int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
               const float* residual, int ld_res, float* out_f32, void* out_bf16, int ld_out, int act, int force_bn,
-              cudaStream_t stream);
+              cudaStream_t stream, int splits = 1);
 int gemm_skinny(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                 const float* residual, int ld_res, float* out_f32, void* out_bf16, int ld_out, int act,
                 cudaStream_t stream);  // gemm_skinny.cu
@@ -88,5 +90,42 @@ int gather_rows(const float* table, const long long* idx, void* out_bf16, float*
                 cudaStream_t stream);
 int conv1x1_nhwc_to_nchw(const void* x, const float* w, const float* bias, float* out, int B, int HW, int C, int Cout,
                          cudaStream_t stream);
+
+
+// bgemm.cu
+int bgemm(const nuwa_bgemm_params& p, cudaStream_t stream);
+// backward.cu
+int ln_bwd_grid(int rows);
+int ln_bwd(const nuwa_lnbwd_params& p, cudaStream_t stream);
+int reduce_partials(const float* part, int nparts, int D, float* o0, float* o1, float* o2, cudaStream_t stream);
+int transpose_bf16(const void* in, long long ld_in, void* out, long long ld_out, int R, int C, cudaStream_t stream);
+int geglu_fwd(const void* h, void* g, long long M, int ip, cudaStream_t stream);
+int geglu_bwd(const void* dg, const void* h, void* dh, long long M, int ip, cudaStream_t stream);
+int ce_bwd(const float* logits, int ld, const long long* target, const float* gscale, void* dlogits, int ld_out, int rows,
+           int V, cudaStream_t stream);
+int embed_bwd(const nuwa_embed_bwd_params& p, cudaStream_t stream);
+int rotary_bwd_to_bf16(const float* dqkv, void* out, const float* inv_freq, int rows, int n, int H, int dh, int rot,
+                       cudaStream_t stream);
+int add_rows_f32(float* dst, long long ld_dst, const float* src, long long ld_src, const int* map, int rows, int cols,
+                 int accumulate, cudaStream_t stream);
+int attn_bwd_rows(const nuwa_attn_rows_params& p, cudaStream_t stream);
+int kv_full_build(const void* k, const void* v, long long kv_bs, int kv_rs, const float* null_k, const float* null_v,
+                  void* kfull, void* vfull, int B, int nk, int jp, int inner, cudaStream_t stream);
+int kv_full_split(const float* dkfull, const float* dvfull, float* dnull_k, float* dnull_v, void* dk16, void* dv16,
+                  float* dk32, float* dv32, long long o_bs, int o_rs, int B, int nk, int jp, int inner,
+                  cudaStream_t stream);
+int mask_scores(float* S, const unsigned char* mask, int mask_bs, int B, int H, int nq, int jp, int nk, int has_null,
+                cudaStream_t stream);
+// attention.cu (gather-attention backward)
+int attn3dna_bwd_scores(const AttnParams& p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp, int jp,
+                        cudaStream_t s);
+int attn3dna_bwd_dq(const AttnParams& p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs, cudaStream_t s);
+int attn3dna_bwd_dkdv(const AttnParams& p, const void* dO, long long do_bs, int do_rs, const void* dS, const void* Pp, int jp,
+                      void* dk, void* dv, long long dkv_bs, int dkv_rs, cudaStream_t stream);
+int attn_bwd_first_key(const void* q, long long q_bs, int q_rs, const void* dO, long long do_bs, int do_rs, const void* dS,
+                       const void* Pp, int jp, int B, int H, int dh, int nq, float* out_k, float* out_v, long long ok_bs,
+                       cudaStream_t stream);
+int attn3dna_bwd_first_key_finalize(const float* tmp_k, const float* tmp_v, const void* dO_bos, long long do_bs, void* dqkv,
+                                    long long dqkv_bs, int inner, int B, cudaStream_t stream);
 
 }  // namespace nuwa

@@ -28,7 +28,8 @@ class SubBlock:
 
     def __init__(self, kind, sandwich, inner_mod, shift, read, write, **geom):
         self.kind, self.shift, self.read, self.write = kind, shift, read, write
-        self.pre = (_f32(sandwich.prenorm.weight), _f32(sandwich.prenorm.bias))
+        self.sandwich, self.mod = sandwich, inner_mod  # parameter owners (train.py maps gradients back to them)
+        self.pre =(_f32(sandwich.prenorm.weight), _f32(sandwich.prenorm.bias))
         self.post = (_f32(sandwich.postnorm.weight), _f32(sandwich.postnorm.bias))
         self.__dict__.update(geom)
         m = inner_mod

@@ -540,6 +540,10 @@ class NUWA(nn.Module, _VideoDecoderMixin):
         if self.training and cond_dropout_prob > 0:  # condition dropout (:1946-1950)
             uncond = torch.zeros((batch,), device=device).float().uniform_(0, 1) < cond_dropout_prob
             text_mask = text_mask & ~uncond[:, None]
+        if return_loss and torch.is_grad_enabled() and any(p.requires_grad for p in self.to_logits.parameters()):
+            # training step: CUDA forward with a tape + CUDA backward behind one autograd node (train.py)
+            from . import train
+            return train.nuwa_training_loss(self, text, frame_indices, text_mask.to(torch.uint8).contiguous())
         with torch.no_grad():
             # NB: the text encoder sees the un-dropped mask, the decoder the dropped one (reference order :1927-1950)
             context = self._text_context(text, text != 0).with_mask(text_mask.to(torch.uint8).contiguous())

@@ -1,0 +1,362 @@
+"""Training step of the NUWA decoder path: `loss = nuwa(text=, video=, return_loss=True); loss.backward()`
+(nuwa_pytorch.py:1917-1964; SURVEY §8d cfg 3) as hand-written CUDA forward + backward behind ONE autograd node.
+
+Layout (B200-first): activations needed by the backward are simply kept (a cfg-3 step saves ~7 GB of 180 GB), so
+nothing is recomputed except cheap row statistics; the reversible stacks (reversible.py:54-123) are differentiated
+through the same saved-activation tape -- algebraically the gradient the reference obtains by reconstructing
+activations, without its extra forward pass.  Every weight gradient is accumulated in fp32 inside one flat buffer
+(one memset, one optional NCCL all-reduce per bucket, see parallel.py); the views handed to autograd alias it.
+
+Per sub-block  x' = x + LN_post(fn(shift(LN_pre(x_r)))):
+    dy   = LN_post backward of the stream gradient                     (ln_bwd, bf16 out; bias grad = column sum)
+    da   = fn backward (GEMM dgrad on tcgen05, weight grads as split-K tcgen05 GEMMs over transposed operands,
+           attention backward kernels)
+    G_r += LN_pre backward of da through the inverse token shift        (ln_bwd, accumulate)
+"""
+import torch
+
+from . import engine, ops, ops_bwd
+from .ops_bwd import _round_up
+
+
+class GradStore:
+    """fp32 gradient accumulators of a fixed parameter list, carved out of one flat zero-initialised buffer."""
+
+    def __init__(self, params):
+        self.params = list(params)
+        dev = self.params[0].device
+        sizes = [_round_up(p.numel(), 4) for p in self.params]  # 16-byte aligned views (vectorised atomics / float4)
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + s)
+        self.flat = torch.zeros(self.offsets[-1], dtype=torch.float32, device=dev)
+        self.index = {id(p): i for i, p in enumerate(self.params)}
+
+    def __call__(self, p):
+        i = self.index.get(id(p))
+        if i is None:
+            return None
+        return self.flat[self.offsets[i]:self.offsets[i] + p.numel()].view(p.shape)
+
+    def view2d(self, p, rows):
+        g = self(p)
+        return None if g is None else g.view(rows, -1)
+
+    def grads(self):
+        return [self(p) for p in self.params]
+
+
+def _bw(s):
+    """Transposed bf16 weight copies for the dgrad GEMMs (built once per weight version, cached on the SubBlock)."""
+    if getattr(s, '_bw', None) is None:
+        t = ops_bwd.transpose
+        bw = {}
+        if s.kind in ('3dna', 'self'):
+            bw['w_qkv_t'], bw['w_out_t'] = t(s.w_qkv).contiguous(), t(s.w_out).contiguous()
+        elif s.kind in ('cross', 'x2dna'):
+            bw['w_q_t'], bw['w_kv_t'], bw['w_out_t'] = t(s.w_q).contiguous(), t(s.w_kv).contiguous(), t(s.w_out).contiguous()
+        elif s.kind == 'ff':
+            bw['w1_t'], bw['w2_t'] = t(s.w1).contiguous(), t(s.w2).contiguous()
+            inner, ip = s.ff_inner, s.w1.shape[0] // 2
+            # packed row r of w1 -> row of net[0].weight (value rows [0, inner), gate rows [inner, 2*inner)), -1 = padding
+            r = torch.arange(2 * ip)
+            blk, j = r // 32, r % 32
+            col = blk * 16 + (j % 16)
+            src = torch.where(j < 16, col, col + inner)
+            src = torch.where(col < inner, src, torch.full_like(src, -1))
+            bw['w1_map'] = src.to(torch.int32).to(s.w1.device)
+        s._bw = bw
+    return s._bw
+
+
+# ------------------------------------------------------------------------------------------------
+# forward with tape
+# ------------------------------------------------------------------------------------------------
+def _sub_forward(i, s, a, B, nt, rec, context, key_mask, rotary):
+    """a: bf16 (B*nt, D).  Returns y fp32 (B*nt, D); stores what the backward needs in rec."""
+    M = B * nt
+    dev = a.device
+    if s.kind == 'ff':
+        rec['h'] = ops.gemm(a, s.w1, out_dtype=torch.bfloat16)          # pair-packed pre-activation (M, 2*ip)
+        rec['g'] = ops_bwd.geglu_fwd(rec['h'])
+        return ops.gemm(rec['g'], s.w2, out_dtype=torch.float32)
+    inner, H, dh = s.inner, s.H, s.dh
+    o = torch.empty(M, inner, dtype=torch.bfloat16, device=dev)
+    rec['o'] = o
+    if s.kind == '3dna':
+        qkv = ops.gemm(a, s.w_qkv, out_dtype=torch.bfloat16)
+        rec['qkv'] = qkv
+        ops.attn_sparse3dna(qkv, o, B=B, nq=nt, t0=0, npos=nt, H=H, dh=dh, talk=s.talk, fmap=s.fmap,
+                            max_frames=s.max_frames, nv=nt - 1, kernel=s.kernel, dilation=s.dilation, causal=s.causal)
+        return ops.gemm(o, s.w_out, bias=s.b_out, out_dtype=torch.float32)
+    if s.kind == 'self':
+        assert not s.causal
+        if rotary is not None:
+            inv_freq, rot = rotary
+            qkv = ops.rotary_to_bf16(ops.gemm(a, s.w_qkv, out_dtype=torch.float32), inv_freq, nt, H, dh, rot)
+        else:
+            qkv = ops.gemm(a, s.w_qkv, out_dtype=torch.bfloat16)
+        rec['qkv'] = qkv
+        base = qkv.data_ptr()
+        ops.attn_dense(base, base + inner * 2, base + 2 * inner * 2, o, B=B, nq=nt, nk=nt, H=H, dh=dh,
+                       q_bs=nt * 3 * inner, q_rs=3 * inner, k_bs=nt * 3 * inner, k_rs=3 * inner, v_bs=nt * 3 * inner,
+                       v_rs=3 * inner, o_bs=nt * inner, o_rs=inner, talk=s.talk, null_k=s.null_k, null_v=s.null_v,
+                       key_mask=key_mask)
+        return ops.gemm(o, s.w_out, out_dtype=torch.float32)
+    if s.kind == 'cross':
+        nk = context.ctx16.shape[1]
+        kv = ops.gemm(context.ctx16.view(B * nk, -1), s.w_kv, out_dtype=torch.bfloat16)
+        q = ops.gemm(a, s.w_q, out_dtype=torch.bfloat16)
+        rec['q'], rec['kv'] = q, kv
+        kb = kv.data_ptr()
+        ops.attn_dense(q.data_ptr(), kb, kb + inner * 2, o, B=B, nq=nt, nk=nk, H=H, dh=dh, q_bs=nt * inner, q_rs=inner,
+                       k_bs=nk * 2 * inner, k_rs=2 * inner, v_bs=nk * 2 * inner, v_rs=2 * inner, o_bs=nt * inner,
+                       o_rs=inner, talk=s.talk, null_k=s.null_k, null_v=s.null_v, key_mask=context.mask)
+        return ops.gemm(o, s.w_out, out_dtype=torch.float32)
+    raise NotImplementedError(f"training path of sub-block kind '{s.kind}' (SparseCross2DNA) is not built yet")
+
+
+def stack_forward(stack, x, *, context=None, key_mask=None, rotary=None):
+    """Teacher-forced pass of a whole stack that keeps the tape.  x: fp32 (B, nt, D).
+    Returns (out fp32 (B,nt,D), out bf16, tape)."""
+    pack = engine.pack_stack(stack)
+    B, nt, D = x.shape
+    M = B * nt
+    x2d = x.view(M, D)
+    streams = [x2d, x2d] if pack.reversible else [x2d]   # X = [x, x]  (reversible.py:133)
+    subs = pack.subs
+    tape = dict(B=B, nt=nt, D=D, recs=[], context=context, key_mask=key_mask, rotary=rotary)
+
+    def operand():
+        return torch.empty(B, nt, D, dtype=torch.bfloat16, device=x.device)
+
+    a = operand()
+    ops.sandwich_ln(B, nt, D, res_in=streams[subs[0].read], pre=subs[0].pre, shift=subs[0].shift, fmap=subs[0].fmap or 0,
+                    a_out=a, a_bs=nt * D, a_rs=D, a_t0=0, a_npos=nt)
+    for i, s in enumerate(subs):
+        rec = dict(x_read=streams[s.read], a=a.view(M, D))
+        y = _sub_forward(i, s, rec['a'], B, nt, rec, context, key_mask, rotary)
+        rec['y'] = y
+        new = torch.empty(M, D, dtype=torch.float32, device=x.device)
+        if i + 1 < len(subs):
+            nxt = subs[i + 1]
+            assert nxt.read == s.write
+            a = operand()
+            ops.sandwich_ln(B, nt, D, y=y, post=s.post, res_in=streams[s.write], x_out=new, pre=nxt.pre, shift=nxt.shift,
+                            fmap=nxt.fmap or 0, a_out=a, a_bs=nt * D, a_rs=D, a_t0=0, a_npos=nt)
+        else:
+            ops.sandwich_ln(B, nt, D, y=y, post=s.post, res_in=streams[s.write], x_out=new)
+        streams[s.write] = new
+        tape['recs'].append(rec)
+    tape['final'] = (streams[0], streams[1] if pack.reversible else None)
+    o32, o16 = ops.stable_ln(streams[0], pack.norm_w, pack.norm_b, b2=tape['final'][1], want_f32=True, want_bf16=True)
+    return o32.view(B, nt, D), o16.view(B, nt, D), tape
+
+
+# ------------------------------------------------------------------------------------------------
+# backward
+# ------------------------------------------------------------------------------------------------
+def _wgrad(dyT, a16_T, dst):
+    if dst is not None:
+        ops_bwd.gemm_splitk(dyT, a16_T, dst)
+
+
+def _sub_backward(i, s, rec, dy16, B, nt, g, tape, dctx):
+    """dy16: bf16 (M, D) gradient of the sub-block output y.  Returns da fp32 (M, D)."""
+    bw = _bw(s)
+    M = B * nt
+    T = ops_bwd.transpose
+    dyT = T(dy16)
+    aT = T(rec['a'])
+    if s.kind == 'ff':
+        m = s.mod
+        D = dy16.shape[1]
+        ip = s.w1.shape[0] // 2
+        dg = ops.gemm(dy16, bw['w2_t'], out_dtype=torch.bfloat16)                     # (M, ip)
+        w2g = g(m.net[3].weight)
+        if w2g is not None:
+            tmp = torch.zeros(D, ip, dtype=torch.float32, device=dy16.device)
+            ops_bwd.gemm_splitk(dyT, T(rec['g']), tmp)
+            ops_bwd.add_rows(w2g, tmp, cols=s.ff_inner)
+        dh = ops_bwd.geglu_bwd(dg, rec['h'])                                         # (M, 2*ip) pair packed
+        w1g = g(m.net[0].weight)
+        if w1g is not None:
+            tmp = torch.zeros(2 * ip, D, dtype=torch.float32, device=dy16.device)
+            ops_bwd.gemm_splitk(T(dh), aT, tmp)
+            ops_bwd.add_rows(w1g, tmp, row_map=bw['w1_map'])
+        return ops.gemm(dh, bw['w1_t'], out_dtype=torch.float32)
+    m = s.mod
+    inner, H, dh_ = s.inner, s.H, s.dh
+    do = ops.gemm(dy16, bw['w_out_t'], out_dtype=torch.bfloat16)                      # (M, inner)
+    _wgrad(dyT, T(rec['o']), g(m.to_out.weight))
+    dtalk = g(m.talking_heads.weight)
+    dtalk = dtalk.view(H, H) if dtalk is not None else torch.zeros(H, H, device=dy16.device)
+    if s.kind == '3dna':
+        dqkv = ops_bwd.attn_sparse3dna_bwd(rec['qkv'], do, B=B, n=nt, H=H, dh=dh_, talk=s.talk, dtalk=dtalk, fmap=s.fmap,
+                                           max_frames=s.max_frames, kernel=s.kernel, dilation=s.dilation, causal=s.causal)
+        dqkv = dqkv.view(M, 3 * inner)
+    elif s.kind == 'self':
+        qkv = rec['qkv']
+        base = qkv.data_ptr()
+        rotary = tape['rotary']
+        dnk, dnv = g(m.null_k), g(m.null_v)
+        dnk = dnk.view(-1) if dnk is not None else torch.zeros(inner, device=do.device)
+        dnv = dnv.view(-1) if dnv is not None else torch.zeros(inner, device=do.device)
+        out_dtype = torch.float32 if rotary is not None else torch.bfloat16
+        esz = 4 if rotary is not None else 2
+        dq_all = torch.empty(M, 3 * inner, dtype=out_dtype, device=do.device)
+        ops_bwd.attn_dense_bwd(base, base + inner * 2, base + 2 * inner * 2, do.view(B, nt, inner), B=B, nq=nt, nk=nt, H=H,
+                               dh=dh_, q_bs=nt * 3 * inner, q_rs=3 * inner, kv_bs=nt * 3 * inner, kv_rs=3 * inner,
+                               talk=s.talk, dtalk=dtalk, null_k=s.null_k, null_v=s.null_v, dnull_k=dnk, dnull_v=dnv,
+                               key_mask=tape['key_mask'], dq_out=(dq_all, dq_all.data_ptr()), dq_bs=nt * 3 * inner,
+                               dq_rs=3 * inner, dk_ptr=dq_all.data_ptr() + inner * esz,
+                               dv_ptr=dq_all.data_ptr() + 2 * inner * esz, dkv_bs=nt * 3 * inner, dkv_rs=3 * inner,
+                               out_f32=rotary is not None)
+        dqkv = ops_bwd.rotary_bwd_to_bf16(dq_all, rotary[0], nt, H, dh_, rotary[1]) if rotary is not None else dq_all
+    elif s.kind == 'cross':
+        ctx = tape['context']
+        nk = ctx.ctx16.shape[1]
+        q, kv = rec['q'], rec['kv']
+        dnk, dnv = g(m.null_k), g(m.null_v)
+        dnk = dnk.view(-1) if dnk is not None else torch.zeros(inner, device=do.device)
+        dnv = dnv.view(-1) if dnv is not None else torch.zeros(inner, device=do.device)
+        dq = torch.empty(M, inner, dtype=torch.bfloat16, device=do.device)
+        dkv = torch.empty(B * nk, 2 * inner, dtype=torch.bfloat16, device=do.device)
+        kb = kv.data_ptr()
+        ops_bwd.attn_dense_bwd(q.data_ptr(), kb, kb + inner * 2, do.view(B, nt, inner), B=B, nq=nt, nk=nk, H=H, dh=dh_,
+                               q_bs=nt * inner, q_rs=inner, kv_bs=nk * 2 * inner, kv_rs=2 * inner, talk=s.talk, dtalk=dtalk,
+                               null_k=s.null_k, null_v=s.null_v, dnull_k=dnk, dnull_v=dnv, key_mask=ctx.mask, dq_out=dq,
+                               dq_bs=nt * inner, dq_rs=inner, dk_ptr=dkv.data_ptr(), dv_ptr=dkv.data_ptr() + inner * 2,
+                               dkv_bs=nk * 2 * inner, dkv_rs=2 * inner, out_f32=False)
+        _wgrad(T(dq), aT, g(m.to_q.weight))
+        if dctx is not None:
+            if getattr(ctx, 'ctx16_T', None) is None:
+                ctx.ctx16_T = T(ctx.ctx16.view(B * nk, -1))
+            _wgrad(T(dkv), ctx.ctx16_T, g(m.to_kv.weight))
+            ops.gemm(dkv, bw['w_kv_t'], residual=dctx, out=dctx)                      # dctx += dkv @ W_kv
+        return ops.gemm(dq, bw['w_q_t'], out_dtype=torch.float32)
+    else:
+        raise NotImplementedError(s.kind)
+    dqkvT = T(dqkv)
+    _wgrad(dqkvT[:inner], aT, g(m.to_q.weight))
+    _wgrad(dqkvT[inner:], aT, g(m.to_kv.weight))
+    return ops.gemm(dqkv, bw['w_qkv_t'], out_dtype=torch.float32)
+
+
+def stack_backward(stack, tape, dout, g, dctx=None):
+    """dout: fp32 (B*nt, D) gradient of the stack output (after its StableLayerNorm).  g: GradStore.
+    dctx: fp32 (B*nk, D) accumulator for the gradient w.r.t. the cross-attention context (or None).
+    Returns the gradient w.r.t. the stack input, fp32 (B*nt, D)."""
+    pack = engine.pack_stack(stack)
+    B, nt, D = tape['B'], tape['nt'], tape['D']
+    M = B * nt
+    dev = dout.device
+    ln = stack.norm.norm
+    G = [torch.empty(M, D, dtype=torch.float32, device=dev) for _ in range(2 if pack.reversible else 1)]
+    f0, f1 = tape['final']
+    ops_bwd.ln_bwd(dout, f0, pack.norm_w, nt=nt, dw=g(ln.weight), db=g(ln.bias), x2=f1, stable=True, dx_f32=G[0],
+                   dx2_f32=G[1] if pack.reversible else None)
+    for i in range(len(pack.subs) - 1, -1, -1):
+        s, rec = pack.subs[i], tape['recs'][i]
+        sw = s.sandwich
+        bias = getattr(s.mod, 'to_out', None)
+        bias = bias.bias if (bias is not None and getattr(bias, 'bias', None) is not None) else None
+        dy16 = ops_bwd.ln_bwd(G[s.write], rec['y'], s.post[0], nt=nt, dw=g(sw.postnorm.weight), db=g(sw.postnorm.bias),
+                              dcol=g(bias) if bias is not None else None, dx_bf16=True)
+        da = _sub_backward(i, s, rec, dy16, B, nt, g, tape, dctx)
+        ops_bwd.ln_bwd(da, rec['x_read'], s.pre[0], nt=nt, dw=g(sw.prenorm.weight), db=g(sw.prenorm.bias), unshift=s.shift,
+                       fmap=s.fmap or 0, dx_f32=G[s.read], accumulate=True)
+        tape['recs'][i] = None  # free the saved activations of this sub-block
+    if pack.reversible:
+        ops_bwd.add_rows(G[0], G[1])  # both streams start as x
+    return G[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# NUWA training step as one autograd node
+# ------------------------------------------------------------------------------------------------
+class NuwaStep:
+    """Forward (with tape) and backward of NUWA.forward(return_loss=True) for one batch."""
+
+    def __init__(self, model, text, frame_indices, text_mask_dec):
+        self.model, self.text, self.idx, self.mask_dec = model, text.contiguous(), frame_indices.contiguous(), text_mask_dec
+        self.params = [p for n, p in model.named_parameters() if p.requires_grad and not n.startswith('vae.')]
+
+    def forward(self):
+        m = self.model
+        text, idx = self.text, self.idx
+        B, N = idx.shape
+        axials, dims = (None, None, None), (1, 1, 1)
+        if m.text_abs_pos_emb is not None:
+            axials = (m.text_abs_pos_emb.embed.weight.detach().float().contiguous(), None, None)
+            dims = (text.shape[1], 1, 1)
+        tokens = ops.embed_tokens(text, m.text_embedding.embed.weight.detach().float().contiguous(), nt=text.shape[1],
+                                  axials=axials, dims=dims)
+        rotary = None
+        if m.text_rotary_pos_emb is not None:
+            rotary = (m.text_rotary_pos_emb.inv_freq.float().contiguous(), m.text_rotary_pos_emb.dim)
+        km = (text != 0).to(torch.uint8).contiguous()
+        _, e16, self.tape_text = stack_forward(m.text_transformer, tokens, key_mask=km, rotary=rotary)
+        self.context = engine.Context(e16, self.mask_dec)
+        x = m._embed_video(idx, N)
+        _, y16, self.tape_dec = stack_forward(m.video_transformer, x, context=self.context)
+        self.y16 = y16.view(B * N, -1)
+        self.logits = ops.gemm(self.y16, m._logits_weight(), out_dtype=torch.float32)
+        self.targets = idx.reshape(-1).contiguous()
+        return ops.cross_entropy_mean(self.logits, self.targets)
+
+    def backward(self, gout, reducer=None):
+        m = self.model
+        g = GradStore(self.params)
+        B, N = self.idx.shape
+        D = self.y16.shape[1]
+        gscale = gout.detach().to(torch.float32).reshape(1).contiguous()
+        dlogits = ops_bwd.ce_bwd(self.logits, self.targets, gscale)
+        self.logits = None
+        w_t = ops_bwd.transpose(m._logits_weight()).contiguous()                    # (D, V)
+        dy = ops_bwd.linear_bwd(dlogits, self.y16, w_t, g(m.to_logits.weight))
+        del dlogits
+        nk = self.context.ctx16.shape[1]
+        dctx = torch.zeros(B * nk, D, dtype=torch.float32, device=dy.device)
+        dx = stack_backward(m.video_transformer, self.tape_dec, dy, g, dctx)
+        frac = m.image_embedding.frac_gradient if m.training else 1.0
+        pe = m.video_pos_emb
+        dax, ax = [], 1
+        for length in pe.full_shape:
+            if length > 1:
+                dax.append(g(getattr(pe, f'axial{ax}')))
+                ax += 1
+            else:
+                dax.append(None)
+        ops_bwd.embed_bwd(dx, self.idx, g(m.image_embedding.embed.weight), nt=N, frac=frac, dbos=g(m.video_bos),
+                          daxials=tuple(dax), dims=pe.full_shape)
+        dtok = stack_backward(m.text_transformer, self.tape_text, dctx, g)
+        frac_t = m.text_embedding.frac_gradient if m.training else 1.0
+        dpos = (None, None, None)
+        if m.text_abs_pos_emb is not None:
+            dpos = (g(m.text_abs_pos_emb.embed.weight), None, None)
+        ops_bwd.embed_bwd(dtok, self.text, g(m.text_embedding.embed.weight), nt=self.text.shape[1], frac=frac_t,
+                          daxials=dpos, dims=(self.text.shape[1], 1, 1))
+        self.tape_dec = self.tape_text = None
+        if reducer is not None:
+            reducer(g.flat)
+        return g.grads()
+
+
+class _StepFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, step, *params):
+        ctx.step = step
+        with torch.no_grad():
+            return step.forward()
+
+    @staticmethod
+    def backward(ctx, gout):
+        with torch.no_grad():
+            grads = ctx.step.backward(gout, getattr(ctx.step.model, '_grad_reducer', None))
+        return (None, *grads)
+
+
+def nuwa_training_loss(model, text, frame_indices, text_mask_dec):
+    step = NuwaStep(model, text, frame_indices, text_mask_dec)
+    return _StepFn.apply(step, *step.params)

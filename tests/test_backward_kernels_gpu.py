@@ -1,0 +1,244 @@
+"""Unit parity of the training (backward) kernels, through the C-ABI, against torch autograd on the CPU oracle math."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import nuwa_oracle as O
+from tests.helpers import gen, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _pad8(t):
+    """(R, C) -> same values inside a buffer whose row pitch is a multiple of 8 (garbage-free zero pad)."""
+    R, C = t.shape
+    buf = torch.zeros(R, (C + 7) // 8 * 8, dtype=t.dtype, device=t.device)
+    buf[:, :C] = t
+    return buf
+
+
+@pytest.mark.parametrize("at,bt", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_bgemm_all_orientations(cuda_device, at, bt):
+    from nuwa_pytorch_b200 import ops_bwd
+    g = gen(10 + at * 2 + bt)
+    b1, b2, M, N, K = 2, 3, 70, 50, 45
+    A = torch.randn(b1, b2, M, K, generator=g).bfloat16()
+    Bm = torch.randn(b1, b2, K, N, generator=g).bfloat16()
+    ref = 0.5 * (A.float() @ Bm.float())
+    a_store = (A.transpose(-1, -2) if at else A).contiguous()           # (.., K, M) or (.., M, K)
+    b_store = (Bm if bt else Bm.transpose(-1, -2)).contiguous()          # (.., K, N) or (.., N, K)
+    a_dev = _pad8(a_store.reshape(-1, a_store.shape[-1])).to(cuda_device)
+    b_dev = _pad8(b_store.reshape(-1, b_store.shape[-1])).to(cuda_device)
+    lda, ldb = a_dev.shape[1], b_dev.shape[1]
+    ra, rb = a_store.shape[-2], b_store.shape[-2]
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 4e-3)):
+        C = torch.full((b1, b2, M, N), 7.0, dtype=dtype, device=cuda_device)
+        ops_bwd.bgemm(a_dev, b_dev, C, M=M, N=N, K=K, a_trans=at, b_trans=bt, lda=lda, ldb=ldb, ldc=N, batch1=b1,
+                      batch2=b2, a_s=(b2 * ra * lda, ra * lda), b_s=(b2 * rb * ldb, rb * ldb), c_s=(b2 * M * N, M * N),
+                      alpha=0.5)
+        assert rel(C.float(), ref) < tol, (at, bt, dtype)
+    C = torch.ones(b1, b2, M, N, device=cuda_device)
+    ops_bwd.bgemm(a_dev, b_dev, C, M=M, N=N, K=K, a_trans=at, b_trans=bt, lda=lda, ldb=ldb, ldc=N, batch1=b1, batch2=b2,
+                  a_s=(b2 * ra * lda, ra * lda), b_s=(b2 * rb * ldb, rb * ldb), c_s=(b2 * M * N, M * N), alpha=0.5,
+                  accumulate=True)
+    assert rel(C, ref + 1) < 1e-5
+
+
+def test_transpose_and_splitk_gemm(cuda_device):
+    from nuwa_pytorch_b200 import ops_bwd
+    g = gen(20)
+    x = torch.randn(203, 77, generator=g).bfloat16()
+    xt = ops_bwd.transpose(x.to(cuda_device))
+    assert xt.shape == (77, 203) and torch.equal(xt.cpu(), x.t())
+    for (M, N, K) in ((512, 192, 5000), (96, 40, 333), (1536, 512, 20480 // 4)):
+        a = torch.randn(M, K, generator=g).bfloat16()
+        w = torch.randn(N, K, generator=g).bfloat16()
+        a_d, w_d = _pad8(a).to(cuda_device)[:, :K], _pad8(w).to(cuda_device)[:, :K]
+        out = torch.ones(M, N, device=cuda_device)
+        ops_bwd.gemm_splitk(a_d, w_d, out)
+        ref = a.float() @ w.float().t() + 1
+        assert rel(out, ref) < 2e-5, (M, N, K)
+
+
+@pytest.mark.parametrize("D", [64, 512, 1024])
+def test_ln_bwd_plain_shift_stable(cuda_device, D):
+    from nuwa_pytorch_b200 import ops_bwd
+    g = gen(30 + D)
+    B, fmap = 2, 4
+    n = 1 + 2 * 16 + 5
+    dv = lambda t: t.to(cuda_device).contiguous()
+    x = torch.randn(B, n, D, generator=g) * 1.5 + 0.3
+    w, b = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    dout = torch.randn(B, n, D, generator=g)
+    # ---- plain LayerNorm, fp32 upstream gradient, accumulate into an existing gradient ----
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    F.layer_norm(xr, (D,), wr, br).backward(dout)
+    dw, db, dcol = (torch.ones(D, device=cuda_device) for _ in range(3))
+    acc = torch.ones(B * n, D, device=cuda_device)
+    d16 = ops_bwd.ln_bwd(dv(dout.view(-1, D)), dv(x.view(-1, D)), dv(w), nt=n, dw=dw, db=db, dcol=dcol, dx_bf16=True,
+                         dx_f32=acc, accumulate=True)
+    assert rel(acc - 1, xr.grad.view(-1, D)) < 1e-5 and rel(d16.float(), xr.grad.view(-1, D)) < 4e-3
+    assert rel(dw - 1, wr.grad) < 1e-5 and rel(db - 1, br.grad) < 1e-5
+    assert rel(dcol - 1, xr.grad.sum((0, 1))) < 1e-4
+    # ---- pre-norm of a ShiftVideoTokens block: bf16 upstream gradient of the shifted operand ----
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    da = dout.bfloat16()
+    O.shift_video_tokens(F.layer_norm(xr, (D,), wr, br), fmap).backward(da.float())
+    dw, db = torch.zeros(D, device=cuda_device), torch.zeros(D, device=cuda_device)
+    dx = torch.zeros(B * n, D, device=cuda_device)
+    ops_bwd.ln_bwd(dv(da.view(-1, D)), dv(x.view(-1, D)), dv(w), nt=n, dw=dw, db=db, unshift=True, fmap=fmap, dx_f32=dx)
+    assert rel(dx, xr.grad.view(-1, D)) < 1e-5 and rel(dw, wr.grad) < 1e-5 and rel(db, br.grad) < 1e-5
+    # ---- StableLayerNorm of the sum of two streams ----
+    x2 = torch.randn(B, n, D, generator=g)
+    xr, x2r, wr, br = (t.clone().requires_grad_() for t in (x, x2, w, b))
+    O.stable_layer_norm(xr + x2r, wr, br).backward(dout)
+    dw, db = torch.zeros(D, device=cuda_device), torch.zeros(D, device=cuda_device)
+    d1, d2 = torch.zeros(B * n, D, device=cuda_device), torch.zeros(B * n, D, device=cuda_device)
+    ops_bwd.ln_bwd(dv(dout.view(-1, D)), dv(x.view(-1, D)), dv(w), nt=n, dw=dw, db=db, x2=dv(x2.view(-1, D)), stable=True,
+                   dx_f32=d1, dx2_f32=d2)
+    assert rel(d1, xr.grad.view(-1, D)) < 1e-4 and torch.equal(d1, d2)  # x / amax(x) amplifies fp32 rounding
+    assert rel(dw, wr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+
+
+def test_geglu_ce_embed_rotary_bwd(cuda_device):
+    from nuwa_pytorch_b200 import ops, ops_bwd
+    g = gen(40)
+    dv = lambda t: t.to(cuda_device).contiguous()
+    # ---- GEGLU on the pair-packed layout ----
+    M, inner = 37, 170
+    h = torch.randn(M, 2 * inner, generator=g)
+    hp = ops.pack_pairs(h.t().contiguous()).t().contiguous().bfloat16()    # (M, 2*ip) packed columns
+    ip = hp.shape[1] // 2
+    gk = ops_bwd.geglu_fwd(dv(hp))
+    hq = hp.float()
+    unpack = ops.pack_pairs(torch.arange(2 * inner, dtype=torch.float32)[:, None]).view(-1).long()  # packed col -> source col
+    hsrc = torch.zeros(M, 2 * inner)
+    valid = torch.ones(2 * ip, dtype=torch.bool)
+    pad_cols = ops.pack_pairs(torch.ones(2 * inner, 1)).view(-1) == 0
+    valid[pad_cols] = False
+    hsrc[:, unpack[valid]] = hq[:, valid]
+    hr = hsrc.clone().requires_grad_()
+    a, gt = hr.chunk(2, -1)
+    ref = a * F.gelu(gt)
+    assert rel(gk.float()[:, :inner], ref) < 4e-3 and gk[:, inner:].float().abs().max().item() == 0
+    dg = torch.zeros(M, ip)
+    dg[:, :inner] = torch.randn(M, inner, generator=g)
+    dg = dg.bfloat16()
+    ref.backward(dg.float()[:, :inner])
+    dh = ops_bwd.geglu_bwd(dv(dg), dv(hp)).float().cpu()
+    got = torch.zeros(M, 2 * inner)
+    got[:, unpack[valid]] = dh[:, valid]
+    assert rel(got, hr.grad) < 6e-3
+    # ---- cross entropy ----
+    rows, V = 19, 300
+    logits = (torch.randn(rows, V, generator=g) * 3).requires_grad_()
+    tgt = torch.randint(0, V, (rows,), generator=g)
+    (F.cross_entropy(logits, tgt) * 0.25).backward()
+    dl = ops_bwd.ce_bwd(dv(logits.detach()), dv(tgt), gscale=torch.tensor([0.25], device=cuda_device))
+    assert rel(dl.float(), logits.grad) < 4e-3
+    # ---- embedding / axial positions / bos ----
+    D, Fr, hh = 32, 3, 4
+    table, bos = torch.randn(50, D, generator=g).requires_grad_(), torch.randn(D, generator=g).requires_grad_()
+    a1, a2, a3 = (torch.randn(s, D, generator=g).requires_grad_() for s in (Fr, hh, hh))
+    idx = torch.randint(0, 50, (2, 40), generator=g)
+    pos = (a1[:, None, None] + a2[None, :, None] + a3[None, None, :]).reshape(-1, D)
+    x = torch.cat([bos[None, None].expand(2, 1, D), O.frac_gradient(table[idx], 0.2) + pos[:40]], dim=1)
+    dx = torch.randn(2, 41, D, generator=g)
+    x.backward(dx)
+    dt, dbos = torch.zeros(50, D, device=cuda_device), torch.zeros(D, device=cuda_device)
+    dax = tuple(torch.zeros(s, D, device=cuda_device) for s in (Fr, hh, hh))
+    ops_bwd.embed_bwd(dv(dx), dv(idx), dt, nt=41, frac=0.2, dbos=dbos, daxials=dax, dims=(Fr, hh, hh))
+    assert rel(dt, table.grad) < 1e-5 and rel(dbos, bos.grad) < 1e-5
+    for got_, want in zip(dax, (a1, a2, a3)):
+        assert rel(got_, want.grad) < 1e-5
+    # ---- rotary ----
+    B, n, H, dh, rot = 2, 9, 2, 32, 32
+    inv = 1. / (10000 ** (torch.arange(0, rot, 2).float() / rot))
+    t = torch.randn(3, B, H, n, dh, generator=g).requires_grad_()
+    y = O.apply_rotary(O.rotary_freqs(inv, n), t)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    to_rows = lambda u: u.permute(1, 3, 0, 2, 4).reshape(B * n, -1)  # (B*n, 3*H*dh)
+    got = ops_bwd.rotary_bwd_to_bf16(dv(to_rows(dy)), dv(inv), n, H, dh, rot)
+    assert rel(got.float(), to_rows(t.grad)) < 4e-3
+
+
+@pytest.mark.parametrize("causal,kernel,dil,n,H,dh", [(True, (5, 3, 3), 1, 49, 2, 32), (True, (5, 3, 3), 2, 40, 2, 32),
+                                                       (True, (3, 3, 3), 4, 49, 8, 64), (False, (3, 3, 3), 1, 33, 2, 32),
+                                                       (False, (3, 5, 3), 2, 49, 4, 16)])
+def test_attn_sparse3dna_bwd(cuda_device, causal, kernel, dil, n, H, dh):
+    from nuwa_pytorch_b200 import ops, ops_bwd
+    g = gen(50 + n + dil)
+    B, fmap, maxf = 2, 4, 3
+    inner = H * dh
+    qkv = torch.randn(B, n, 3 * inner, generator=g).bfloat16()
+    talk = torch.randn(H, H, generator=g) / 2
+    do = torch.randn(B, n, inner, generator=g).bfloat16()
+    eye, z = torch.eye(inner), torch.zeros(inner, inner)
+    x = qkv.float().clone().requires_grad_()
+    tk = talk.clone().requires_grad_()
+    p = {'to_q.weight': torch.cat([eye, z, z], 1), 'to_kv.weight': torch.cat([torch.cat([z, eye, z], 1), torch.cat([z, z, eye], 1)]),
+         'talking_heads.weight': tk[:, :, None, None], 'to_out.weight': eye, 'to_out.bias': torch.zeros(inner)}
+    out = O.sparse3dna(x, p, H, (maxf, fmap, fmap), kernel, (dil,) * 3, causal)
+    out.backward(do.float())
+    # forward consistency of the saved q|k|v with the product kernel, then the backward
+    o = torch.empty(B, n, inner, dtype=torch.bfloat16, device=cuda_device)
+    geom = dict(H=H, dh=dh, fmap=fmap, max_frames=maxf, kernel=kernel, dilation=(dil,) * 3, causal=causal)
+    ops.attn_sparse3dna(qkv.to(cuda_device), o, B=B, nq=n, t0=0, npos=n, nv=n - 1, talk=talk.to(cuda_device), **geom)
+    assert rel(o.float(), out) < 1e-2
+    dtalk = torch.zeros(H, H, device=cuda_device)
+    dqkv = ops_bwd.attn_sparse3dna_bwd(qkv.to(cuda_device), do.to(cuda_device), B=B, n=n, talk=talk.to(cuda_device),
+                                       dtalk=dtalk, **geom)
+    r = rel(dqkv.float(), x.grad)
+    print(f"  3dna bwd causal={causal} k={kernel} d={dil} n={n}: dqkv rel {r:.2e}, dtalk rel {rel(dtalk, tk.grad):.2e}")
+    assert r < 1.5e-2 and rel(dtalk, tk.grad) < 1.5e-2
+    for part, name in ((slice(0, inner), 'dq'), (slice(inner, 2 * inner), 'dk'), (slice(2 * inner, 3 * inner), 'dv')):
+        assert rel(dqkv.float()[..., part], x.grad[..., part]) < 2e-2, name
+
+
+@pytest.mark.parametrize("B,nq,nk,H,dh,null,masked", [(2, 37, 12, 2, 32, True, True), (3, 70, 50, 8, 64, True, False),
+                                                       (2, 16, 16, 4, 16, False, True)])
+def test_attn_dense_bwd(cuda_device, B, nq, nk, H, dh, null, masked):
+    from nuwa_pytorch_b200 import ops_bwd
+    g = gen(60 + nq)
+    inner = H * dh
+    q = torch.randn(B, nq, inner, generator=g).bfloat16()
+    kv = torch.randn(B, nk, 2 * inner, generator=g).bfloat16()
+    do = torch.randn(B, nq, inner, generator=g).bfloat16()
+    talk = torch.randn(H, H, generator=g) / 2
+    null_k, null_v = torch.randn(inner, generator=g), torch.randn(inner, generator=g)
+    mask = torch.rand(B, nk, generator=g) > 0.3 if masked else None
+    if masked:
+        mask[0] = False
+        if not null:
+            mask[:, 0] = True
+    qr, kvr, tk, nkr, nvr = (t.float().clone().requires_grad_() for t in (q, kv, talk, null_k.bfloat16(), null_v.bfloat16()))
+    qh = O._heads(qr, H) * dh ** -0.5
+    k, v = kvr.chunk(2, -1)
+    kh, vh = O._heads(k, H), O._heads(v, H)
+    if null:
+        kh = torch.cat([nkr.view(1, H, 1, dh).expand(B, -1, -1, -1), kh], 2)
+        vh = torch.cat([nvr.view(1, H, 1, dh).expand(B, -1, -1, -1), vh], 2)
+    sim = qh @ kh.transpose(-1, -2)
+    if masked:
+        m = F.pad(mask, (1, 0), value=True) if null else mask
+        sim = sim.masked_fill(~m[:, None, None], O.NEG)
+    attn = O._talking_heads(sim.softmax(-1), tk[:, :, None, None])
+    O._merge(attn @ vh).backward(do.float())
+    dv_ = lambda t: t.to(cuda_device).contiguous()
+    qd, kvd, dod = dv_(q), dv_(kv), dv_(do)
+    dq = torch.empty(B, nq, inner, dtype=torch.bfloat16, device=cuda_device)
+    dkv = torch.empty(B, nk, 2 * inner, dtype=torch.bfloat16, device=cuda_device)
+    dtalk = torch.zeros(H, H, device=cuda_device)
+    dnk, dnv = (torch.zeros(inner, device=cuda_device), torch.zeros(inner, device=cuda_device)) if null else (None, None)
+    ops_bwd.attn_dense_bwd(qd.data_ptr(), kvd.data_ptr(), kvd.data_ptr() + inner * 2, dod, B=B, nq=nq, nk=nk, H=H, dh=dh,
+                           q_bs=nq * inner, q_rs=inner, kv_bs=nk * 2 * inner, kv_rs=2 * inner, talk=dv_(talk), dtalk=dtalk,
+                           null_k=dv_(null_k) if null else None, null_v=dv_(null_v) if null else None, dnull_k=dnk,
+                           dnull_v=dnv, key_mask=dv_(mask.to(torch.uint8)) if masked else None, dq_out=dq,
+                           dq_bs=nq * inner, dq_rs=inner, dk_ptr=dkv.data_ptr(), dv_ptr=dkv.data_ptr() + inner * 2,
+                           dkv_bs=nk * 2 * inner, dkv_rs=2 * inner, out_f32=False)
+    assert rel(dq.float(), qr.grad) < 1.5e-2
+    assert rel(dkv.float(), kvr.grad) < 1.5e-2
+    assert rel(dtalk, tk.grad) < 1.5e-2
+    if null:
+        assert rel(dnk, nkr.grad) < 1.5e-2 and rel(dnv, nvr.grad) < 1.5e-2

@@ -1,0 +1,66 @@
+"""Training step (forward + backward) of NUWA through the CUDA path vs the gradients of the UNMODIFIED reference
+(tests/golden/*_grads.pt, written by oracle/make_golden_grads.py from `loss.backward()` of the reference).
+
+Tolerance: bf16 tensor-core operands with fp32 accumulation on the CUDA side against fp32 end to end in the
+reference; gradients are compared per parameter tensor by relative L2 (GRAD_TOL) and over the concatenation of all of
+them (GRAD_TOL_ALL)."""
+import pytest
+import torch
+
+from tests.helpers import golden, rel, synth
+
+pytestmark = pytest.mark.gpu
+GRAD_TOL = 6e-2
+GRAD_TOL_ALL = 2.5e-2
+GRAD_TOL_TINY = 0.15
+
+
+def _train_model(name, dev):
+    from nuwa_pytorch_b200 import NUWA, VQGanVAE
+    fx = golden(name)
+    vae = VQGanVAE(**fx['vae_kwargs'])
+    model = NUWA(vae=vae, **fx['kwargs'])
+    missing, unexpected = model.load_state_dict(synth(fx), strict=False)
+    assert not unexpected
+    return fx, model.to(dev).train()
+
+
+@pytest.mark.parametrize("name", ["nuwa_small", "nuwa_rev_small"])
+def test_nuwa_loss_backward_matches_reference_gradients(cuda_device, name):
+    fx, model = _train_model(name + ".pt", cuda_device)
+    gold = golden(name + "_grads.pt")
+    text, vidx = fx['text'].to(cuda_device), fx['video_indices'].to(cuda_device)
+    loss = model(text=text, video=vidx, return_loss=True, cond_dropout_prob=0.)
+    assert loss.requires_grad and abs(loss.item() - gold['loss'].item()) < 2e-2
+    loss.backward()
+    params = dict(model.named_parameters())
+    worst, num, den, bad = (0., None), 0., 0., []
+    for k, gref in gold['grads'].items():
+        p = params[k]
+        assert p.grad is not None, k
+        r = rel(p.grad, gref)
+        if r > worst[0]:
+            worst = (r, k)
+        num += (p.grad.double().cpu() - gref.double()).pow(2).sum().item()
+        den += gref.double().pow(2).sum().item()
+        # the (heads x heads) talking-heads gradients are sums with heavy cancellation over every (query, key) pair:
+        # the fp32 oracle itself only reproduces the reference to 1e-4 there, bf16 operands cost ~3 decimal digits more
+        bad = bad + [(k, r)] if r > (GRAD_TOL_TINY if gref.numel() <= 64 else GRAD_TOL) else bad
+    total = (num / den) ** 0.5
+    print(f"  {name}: {len(gold['grads'])} gradient tensors, worst rel {worst[0]:.3e} ({worst[1]}), all-params rel {total:.3e}")
+    assert not bad, bad
+    assert total < GRAD_TOL_ALL
+    assert all(p.grad is None for k, p in params.items() if k.startswith('vae.'))  # the frozen VAE copy gets no gradient
+
+
+def test_backward_scales_with_grad_output_and_accumulates(cuda_device):
+    fx, model = _train_model("nuwa_small.pt", cuda_device)
+    text, vidx = fx['text'].to(cuda_device), fx['video_indices'].to(cuda_device)
+    model(text=text, video=vidx, return_loss=True, cond_dropout_prob=0.).backward()
+    g1 = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    # gradient accumulation as NUWATrainer does it (train_nuwa.py:247-251): (loss / 2).backward() twice more
+    for _ in range(2):
+        (model(text=text, video=vidx, return_loss=True, cond_dropout_prob=0.) / 2).backward()
+    for k, p in model.named_parameters():
+        if p.grad is not None and g1[k].abs().max() > 0:
+            assert rel(p.grad, 2 * g1[k]) < 2e-3, k  # split-K / atomic summation order is the only difference
