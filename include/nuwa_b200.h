@@ -239,8 +239,8 @@ int nuwa_bgemm(const nuwa_bgemm_params* p, void* stream);
  * normalised row went through ShiftVideoTokens (:200-253) before its consumer, so the upstream gradient of the first /
  * second channel quarter is read from the row one grid-row below / one column right (zero at the borders).
  * x (+ x2): the forward input of the norm; stable = 1: LN(x / amax(x)).  Outputs: dx as bf16 and/or fp32 (dx_f32 and
- * dx2_f32 are accumulated into when accumulate = 1).  part: [ln_bwd_grid(rows)][3][D] fp32 per-CTA partial sums of
- * dweight, dbias and colsum(dx); reduce with nuwa_reduce_partials. */
+ * dx2_f32 are accumulated into when accumulate = 1).  The affine-parameter gradients are reduced per CTA and added to
+ * dw / db / dcol with fp32 atomics. */
 typedef struct {
   int rows, nt, D;
   const float* dout_f32;
@@ -255,7 +255,9 @@ typedef struct {
   float* dx_f32;
   float* dx2_f32;
   int accumulate;
-  float* part;
+  float* dw;   /* [D] += sum_rows dout * xhat   (NULL = skip) */
+  float* db;   /* [D] += sum_rows dout */
+  float* dcol; /* [D] += sum_rows dx            (bias gradient of the layer that produced x) */
 } nuwa_lnbwd_params;
 int nuwa_ln_bwd_grid(int rows);
 int nuwa_ln_bwd(const nuwa_lnbwd_params* p, void* stream);
@@ -312,6 +314,8 @@ typedef struct {
   float* dtalk;      /* [H][H] or NULL */
   int B, H, nq, J, jp;
   float out_scale;
+  const unsigned char* key_mask; /* dense attention: [B][mask_bs], 0 = key (slot - has_null) is masked; or NULL */
+  int mask_bs, has_null;
 } nuwa_attn_rows_params;
 int nuwa_attn_bwd_rows(const nuwa_attn_rows_params* p, void* stream);
 /* dense attention (nuwa_pytorch.py:339-378): K / V with the learned null slot prepended, zero padded to jp rows */

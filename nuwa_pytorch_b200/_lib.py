@@ -52,7 +52,7 @@ class LnBwdParams(ctypes.Structure):  # mirrors nuwa_lnbwd_params
     _fields_ = [("rows", c_int), ("nt", c_int), ("D", c_int), ("dout_f32", c_void_p), ("dout_bf16", c_void_p),
                 ("unshift", c_int), ("fmap", c_int), ("x", c_void_p), ("x2", c_void_p), ("stable", c_int),
                 ("w", c_void_p), ("eps", c_float), ("dx_bf16", c_void_p), ("dx_f32", c_void_p), ("dx2_f32", c_void_p),
-                ("accumulate", c_int), ("part", c_void_p)]
+                ("accumulate", c_int), ("dw", c_void_p), ("db", c_void_p), ("dcol", c_void_p)]
 
 
 class EmbedBwdParams(ctypes.Structure):  # mirrors nuwa_embed_bwd_params
@@ -64,7 +64,7 @@ class EmbedBwdParams(ctypes.Structure):  # mirrors nuwa_embed_bwd_params
 class AttnRowsParams(ctypes.Structure):  # mirrors nuwa_attn_rows_params
     _fields_ = [("S", c_void_p), ("dPp", c_void_p), ("Pp", c_void_p), ("dS", c_void_p), ("talk", c_void_p),
                 ("dtalk", c_void_p), ("B", c_int), ("H", c_int), ("nq", c_int), ("J", c_int), ("jp", c_int),
-                ("out_scale", c_float)]
+                ("out_scale", c_float), ("key_mask", c_void_p), ("mask_bs", c_int), ("has_null", c_int)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES).  Must list EVERY symbol of include/nuwa_b200.h.

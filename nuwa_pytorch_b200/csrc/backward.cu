@@ -24,8 +24,8 @@ namespace nuwa {
 // =================================================================================================
 // LayerNorm backward
 // =================================================================================================
-template <int MAXV>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const nuwa_lnbwd_params p) {
+template <int MAXV, bool COLSUM>
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const nuwa_lnbwd_params p) {
   extern __shared__ float sm_part[];  // [3][D] CTA partial sums
   const int D = p.D;
   for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) sm_part[i] = 0.f;
@@ -37,33 +37,67 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const nuwa_lnbwd_params p) 
 #pragma unroll
   for (int i = 0; i < MAXV; ++i)
     if ((lane + 32 * i) * 4 < D) nv = i + 1;
-  float4 aw[MAXV], ab[MAXV], ac[MAXV], w4[MAXV];
+  float4 aw[MAXV], ab[MAXV], ac[COLSUM ? MAXV : 1];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    aw[i] = ab[i] = ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    w4[i] = (i < nv) ? *reinterpret_cast<const float4*>(p.w + (lane + 32 * i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int i = 0; i < MAXV; ++i) aw[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < (COLSUM ? MAXV : 1); ++i) ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int q4 = D / 4;
   const float invD = 1.0f / (float)D;
   for (long long row = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); row < p.rows; row += nwarps) {
     const int b = (int)(row / p.nt), t = (int)(row - (long long)b * p.nt);
     const long long roff = row * D;
-    // ---- input row, statistics ----
-    float4 v[MAXV];
-    float mx = -FLT_MAX;
+    // ---- upstream gradient rows (through the inverse token shift when the normalised row fed a shifted sub-block) ----
+    int src_h = t, src_w = t;  // rows the first / second channel quarter of the normalised row went to
+    bool ok_h = true, ok_w = true;
+    if (p.unshift && t >= 1) {
+      const int T = p.fmap * p.fmap;
+      const int pos = (t - 1) % T;
+      const int gr = pos / p.fmap, gc = pos - gr * p.fmap;
+      ok_h = (gr < p.fmap - 1) && (t + p.fmap < p.nt);
+      ok_w = (gc < p.fmap - 1) && (t + 1 < p.nt);
+      src_h = t + p.fmap;
+      src_w = t + 1;
+    }
+    // ---- all loads of the row first (memory-level parallelism), then the reductions ----
+    float4 v[MAXV], g[MAXV];
 #pragma unroll
     for (int i = 0; i < MAXV; ++i)
       if (i < nv) {
         const int c = (lane + 32 * i) * 4;
         v[i] = *reinterpret_cast<const float4*>(p.x + roff + c);
-        if (p.x2 != nullptr) {
-          const float4 u = *reinterpret_cast<const float4*>(p.x2 + roff + c);
+        int sr = t;
+        bool ok = true;
+        if (p.unshift && t >= 1 && c < 2 * q4) {
+          sr = c < q4 ? src_h : src_w;
+          ok = c < q4 ? ok_h : ok_w;
+        }
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+          const long long so = ((long long)b * p.nt + sr) * D + c;
+          if (p.dout_f32 != nullptr) d = *reinterpret_cast<const float4*>(p.dout_f32 + so);
+          else {
+            const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p.dout_bf16) + so);
+            const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+            d = make_float4(lo.x, lo.y, hi.x, hi.y);
+          }
+        }
+        g[i] = d;
+      }
+    if (p.x2 != nullptr) {
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+          const float4 u = *reinterpret_cast<const float4*>(p.x2 + roff + (lane + 32 * i) * 4);
           v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
         }
-        mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
-      }
+    }
     float inv_mx = 1.0f;
     if (p.stable) {
+      float mx = -FLT_MAX;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i)
+        if (i < nv) mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
       mx = warp_max(mx);
       inv_mx = 1.0f / mx;
 #pragma unroll
@@ -83,48 +117,18 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const nuwa_lnbwd_params p) 
         qv += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
       }
     const float rstd = rsqrtf(warp_sum(qv) * invD + p.eps);
-    // ---- upstream gradient (through the inverse token shift when the normalised row fed a shifted sub-block) ----
-    int src_h = t, src_w = t;  // rows the first / second channel quarter of the normalised row went to
-    bool ok_h = true, ok_w = true;
-    if (p.unshift && t >= 1) {
-      const int T = p.fmap * p.fmap;
-      const int pos = (t - 1) % T;
-      const int gr = pos / p.fmap, gc = pos - gr * p.fmap;
-      ok_h = (gr < p.fmap - 1) && (t + p.fmap < p.nt);
-      ok_w = (gc < p.fmap - 1) && (t + 1 < p.nt);
-      src_h = t + p.fmap;
-      src_w = t + 1;
-    }
-    float4 g[MAXV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i)
       if (i < nv) {
-        const int c = (lane + 32 * i) * 4;
-        int sr = t;
-        bool ok = true;
-        if (p.unshift && t >= 1 && c < 2 * q4) {
-          sr = c < q4 ? src_h : src_w;
-          ok = c < q4 ? ok_h : ok_w;
-        }
-        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) {
-          const long long so = ((long long)b * p.nt + sr) * D + c;
-          if (p.dout_f32 != nullptr) d = *reinterpret_cast<const float4*>(p.dout_f32 + so);
-          else {
-            const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p.dout_bf16) + so);
-            const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
-            d = make_float4(lo.x, lo.y, hi.x, hi.y);
-          }
-        }
-        g[i] = d;
-        // xhat = v * rstd
-        v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;
-        const float gx = d.x * w4[i].x, gy = d.y * w4[i].y, gz = d.z * w4[i].z, gw = d.w * w4[i].w;
-        s1 += gx + gy + gz + gw;
-        s2 += gx * v[i].x + gy * v[i].y + gz * v[i].z + gw * v[i].w;
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.w + (lane + 32 * i) * 4));
+        const float4 d = g[i];
+        v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
         aw[i].x += d.x * v[i].x; aw[i].y += d.y * v[i].y; aw[i].z += d.z * v[i].z; aw[i].w += d.w * v[i].w;
         ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+        g[i].x = d.x * w4.x; g[i].y = d.y * w4.y; g[i].z = d.z * w4.z; g[i].w = d.w * w4.w;  // dout * w
+        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        s2 += g[i].x * v[i].x + g[i].y * v[i].y + g[i].z * v[i].z + g[i].w * v[i].w;
       }
     const float m1 = warp_sum(s1) * invD, m2 = warp_sum(s2) * invD;
     const float k = rstd * inv_mx;
@@ -133,11 +137,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const nuwa_lnbwd_params p) 
       if (i < nv) {
         const int c = (lane + 32 * i) * 4;
         float4 dx;
-        dx.x = k * (g[i].x * w4[i].x - m1 - v[i].x * m2);
-        dx.y = k * (g[i].y * w4[i].y - m1 - v[i].y * m2);
-        dx.z = k * (g[i].z * w4[i].z - m1 - v[i].z * m2);
-        dx.w = k * (g[i].w * w4[i].w - m1 - v[i].w * m2);
-        ac[i].x += dx.x; ac[i].y += dx.y; ac[i].z += dx.z; ac[i].w += dx.w;
+        dx.x = k * (g[i].x - m1 - v[i].x * m2);
+        dx.y = k * (g[i].y - m1 - v[i].y * m2);
+        dx.z = k * (g[i].z - m1 - v[i].z * m2);
+        dx.w = k * (g[i].w - m1 - v[i].w * m2);
+        if (COLSUM) { ac[i].x += dx.x; ac[i].y += dx.y; ac[i].z += dx.z; ac[i].w += dx.w; }
         if (p.dx_bf16 != nullptr) {
           uint2 pk;
           pk.x = pack_bf16x2(dx.x, dx.y);
@@ -158,8 +162,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const nuwa_lnbwd_params p) 
         }
       }
   }
-  // ---- CTA partial sums ----
-  if (p.part != nullptr) {
+  // ---- parameter gradients: CTA reduction in shared memory, then one fp32 atomic per (CTA, channel) ----
+  if (p.dw != nullptr || p.db != nullptr || p.dcol != nullptr) {
 #pragma unroll
     for (int i = 0; i < MAXV; ++i)
       if (i < nv) {
@@ -168,18 +172,23 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const nuwa_lnbwd_params p) 
         atomicAdd(&sm_part[c + 2], aw[i].z); atomicAdd(&sm_part[c + 3], aw[i].w);
         atomicAdd(&sm_part[D + c + 0], ab[i].x); atomicAdd(&sm_part[D + c + 1], ab[i].y);
         atomicAdd(&sm_part[D + c + 2], ab[i].z); atomicAdd(&sm_part[D + c + 3], ab[i].w);
-        atomicAdd(&sm_part[2 * D + c + 0], ac[i].x); atomicAdd(&sm_part[2 * D + c + 1], ac[i].y);
-        atomicAdd(&sm_part[2 * D + c + 2], ac[i].z); atomicAdd(&sm_part[2 * D + c + 3], ac[i].w);
+        if (COLSUM) {
+          atomicAdd(&sm_part[2 * D + c + 0], ac[i].x); atomicAdd(&sm_part[2 * D + c + 1], ac[i].y);
+          atomicAdd(&sm_part[2 * D + c + 2], ac[i].z); atomicAdd(&sm_part[2 * D + c + 3], ac[i].w);
+        }
       }
     __syncthreads();
-    float* dst = p.part + (long long)blockIdx.x * 3 * D;
-    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) dst[i] = sm_part[i];
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      if (p.dw != nullptr) atomicAdd(p.dw + i, sm_part[i]);
+      if (p.db != nullptr) atomicAdd(p.db + i, sm_part[D + i]);
+      if (COLSUM && p.dcol != nullptr) atomicAdd(p.dcol + i, sm_part[2 * D + i]);
+    }
   }
 }
 
 int ln_bwd_grid(int rows) {
-  const int want = ceil_div(rows, 8 * 4);  // >= 4 rows per warp so that the partial-sum traffic stays small
-  const int cap = device_sm_count() * 4;
+  const int want = ceil_div(rows, 8 * 4);  // >= 4 rows per warp amortise the parameter-gradient reduction
+  const int cap = device_sm_count() * 2;
   return want < 1 ? 1 : (want > cap ? cap : want);
 }
 
@@ -190,8 +199,14 @@ int ln_bwd(const nuwa_lnbwd_params& p, cudaStream_t stream) {
   if (p.unshift && p.fmap <= 0) return NUWA_ERR_INVALID;
   const int grid = ln_bwd_grid(p.rows);
   const size_t smem = (size_t)3 * p.D * sizeof(float);
-  if (p.D <= 512) ln_bwd_kernel<4><<<grid, 256, smem, stream>>>(p);
-  else ln_bwd_kernel<8><<<grid, 256, smem, stream>>>(p);
+  const bool cs = p.dcol != nullptr;
+  if (p.D <= 512) {
+    if (cs) ln_bwd_kernel<4, true><<<grid, 256, smem, stream>>>(p);
+    else ln_bwd_kernel<4, false><<<grid, 256, smem, stream>>>(p);
+  } else {
+    if (cs) ln_bwd_kernel<8, true><<<grid, 256, smem, stream>>>(p);
+    else ln_bwd_kernel<8, false><<<grid, 256, smem, stream>>>(p);
+  }
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
 }
@@ -604,8 +619,164 @@ __global__ void __launch_bounds__(128) attn_bwd_rows_kernel(const nuwa_attn_rows
     for (int i = threadIdx.x; i < H * H; i += blockDim.x) atomicAdd(p.dtalk + i, dW_cta[i]);
   }
 }
+// Register-resident variant: lane l owns the key slots j = l + 32 i (i < NJ) of ALL heads, so the softmax statistics are
+// warp shuffles (the H reductions are independent -> instruction-level parallelism), the talking-heads mixes are pure
+// register FMAs, and nothing but the H x H mixing matrix lives in shared memory.  J <= 32 * NJ.
+template <int H, int NJ>
+__global__ void __launch_bounds__(128, 2) attn_bwd_rows_reg_kernel(const nuwa_attn_rows_params p) {
+  __shared__ __align__(16) float Wt[H * H];
+  __shared__ float dW_cta[H * H];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int J = p.J, jp = p.jp;
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+    Wt[i] = p.talk != nullptr ? p.talk[i] : ((i / H) == (i % H) ? 1.0f : 0.0f);
+    dW_cta[i] = 0.f;
+  }
+  __syncthreads();
+  float dW[H * H];
+#pragma unroll
+  for (int i = 0; i < H * H; ++i) dW[i] = 0.f;
+  const long long nrows = (long long)p.B * p.nq;
+  const long long hs = (long long)p.nq * jp;  // head stride
+  bf16* Pp = reinterpret_cast<bf16*>(p.Pp);
+  bf16* dS = reinterpret_cast<bf16*>(p.dS);
+  for (long long r = blockIdx.x * (long long)wpb + warp; r < nrows; r += (long long)gridDim.x * wpb) {
+    const int b = (int)(r / p.nq), q = (int)(r - (long long)b * p.nq);
+    const long long base = ((long long)b * H * p.nq + q) * jp;
+    float P[H][NJ], G[H][NJ];
+    bool live[NJ];
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const int j = lane + 32 * i;
+      live[i] = j < J;
+      if (live[i] && p.key_mask != nullptr) {
+        const int key = j - p.has_null;
+        if (key >= 0 && p.key_mask[(long long)b * p.mask_bs + key] == 0) live[i] = false;
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        P[h][i] = live[i] ? p.S[base + h * hs + j] : -FLT_MAX;
+        G[h][i] = live[i] ? p.dPp[base + h * hs + j] : 0.f;
+      }
+    }
+    // ---- softmax of every head ----
+    float m[H], sum[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      m[h] = P[h][0];
+#pragma unroll
+      for (int i = 1; i < NJ; ++i) m[h] = fmaxf(m[h], P[h][i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int h = 0; h < H; ++h) m[h] = fmaxf(m[h], __shfl_xor_sync(0xffffffffu, m[h], o));
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      sum[h] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        P[h][i] = live[i] ? __expf(P[h][i] - m[h]) : 0.f;
+        sum[h] += P[h][i];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int h = 0; h < H; ++h) sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], o);
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float inv = 1.0f / sum[h];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) P[h][i] *= inv;
+    }
+    // ---- talking heads forward (P' -> HBM), backward (dP = W^T dP'), dW accumulation; then P .* dP row sums ----
+    float dot[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) dot[h] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const int j = lane + 32 * i;
+      float dp[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) dp[h] = 0.f;
+#pragma unroll
+      for (int g = 0; g < H; ++g) {
+        float wrow[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) wrow[h] = Wt[g * H + h];
+        const float dpp = G[g][i];
+        float a = 0.f;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          a = fmaf(wrow[h], P[h][i], a);
+          dp[h] = fmaf(wrow[h], dpp, dp[h]);
+          dW[g * H + h] = fmaf(dpp, P[h][i], dW[g * H + h]);
+        }
+        if (j < jp) Pp[base + g * hs + j] = __float2bfloat16(a);
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        G[h][i] = dp[h];
+        dot[h] = fmaf(P[h][i], dp[h], dot[h]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int h = 0; h < H; ++h) dot[h] += __shfl_xor_sync(0xffffffffu, dot[h], o);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const int j = lane + 32 * i;
+      if (j < jp) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) dS[base + h * hs + j] = __float2bfloat16(P[h][i] * (G[h][i] - dot[h]) * p.out_scale);
+      }
+    }
+  }
+  if (p.dtalk != nullptr) {
+#pragma unroll
+    for (int i = 0; i < H * H; ++i) {
+      const float v = warp_sum(dW[i]);
+      if (lane == 0) atomicAdd(&dW_cta[i], v);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) atomicAdd(p.dtalk + i, dW_cta[i]);
+  }
+}
+
+template <int H>
+static bool launch_rows_reg(const nuwa_attn_rows_params& p, int grid, cudaStream_t stream) {
+  const int nj = ceil_div(p.J, 32);
+  if (nj <= 1) attn_bwd_rows_reg_kernel<H, 1><<<grid, 128, 0, stream>>>(p);
+  else if (nj <= 2) attn_bwd_rows_reg_kernel<H, 2><<<grid, 128, 0, stream>>>(p);
+  else if (nj <= 4) attn_bwd_rows_reg_kernel<H, 4><<<grid, 128, 0, stream>>>(p);
+  else if (nj <= 9 && H * 9 <= 72) attn_bwd_rows_reg_kernel<H, 9><<<grid, 128, 0, stream>>>(p);
+  else return false;
+  return true;
+}
+
 int attn_bwd_rows(const nuwa_attn_rows_params& p, cudaStream_t stream) {
   if (p.B <= 0 || p.nq <= 0 || p.J <= 0 || p.jp < p.J) return NUWA_ERR_INVALID;
+  {
+    const long long nrows = (long long)p.B * p.nq;
+    long long want = (nrows + 4 * 8 - 1) / (4 * 8);  // >= 8 rows per warp amortise the dW reduction
+    const long long cap = (long long)device_sm_count() * 2;
+    const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    bool ok = false;
+    switch (p.H) {
+      case 8: ok = launch_rows_reg<8>(p, grid, stream); break;
+      case 4: ok = launch_rows_reg<4>(p, grid, stream); break;
+      case 2: ok = launch_rows_reg<2>(p, grid, stream); break;
+      case 1: ok = launch_rows_reg<1>(p, grid, stream); break;
+      default: break;
+    }
+    if (ok) {
+      NUWA_CHECK_LAUNCH();
+      return NUWA_OK;
+    }
+  }
+  if (p.key_mask != nullptr) return NUWA_ERR_INVALID;  // the shared-memory fallback expects masks folded into S
   const int wpb = 4;
   const size_t smem = ((size_t)wpb * 2 * p.H * p.jp + p.H * p.H) * sizeof(float);
   if (smem > 200 * 1024) return NUWA_ERR_INVALID;

@@ -90,16 +90,8 @@ def ln_bwd(dout, x, w, *, nt, dw=None, db=None, dcol=None, x2=None, stable=False
     p.x, p.x2, p.stable, p.w, p.eps = ptr(x), ptr(x2), int(bool(stable)), ptr(w), 1e-5
     out16 = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device) if dx_bf16 else None
     p.dx_bf16, p.dx_f32, p.dx2_f32, p.accumulate = ptr(out16), ptr(dx_f32), ptr(dx2_f32), int(bool(accumulate))
-    need_part = dw is not None or db is not None or dcol is not None
-    part = None
-    if need_part:
-        nparts = lib().nuwa_ln_bwd_grid(rows)
-        part = torch.empty(nparts, 3, D, dtype=torch.float32, device=x.device)
-        p.part = ptr(part)
+    p.dw, p.db, p.dcol = ptr(dw), ptr(db), ptr(dcol)
     check(lib().nuwa_ln_bwd(p, stream()), "nuwa_ln_bwd")
-    if need_part:
-        check(lib().nuwa_reduce_partials(ptr(part), part.shape[0], D, ptr(dw), ptr(db), ptr(dcol), stream()),
-              "nuwa_reduce_partials")
     return out16
 
 
@@ -155,12 +147,14 @@ def add_rows(dst, src, row_map=None, cols=None, accumulate=True):
 # ------------------------------------------------------------------------------------------------
 # attention backward
 # ------------------------------------------------------------------------------------------------
-def _rows(S, dPp, talk, dtalk, B, H, nq, J, jp, out_scale):
+def _rows(S, dPp, talk, dtalk, B, H, nq, J, jp, out_scale, key_mask=None, has_null=0):
     Pp = torch.empty(B, H, nq, jp, dtype=torch.bfloat16, device=S.device)
     dS = torch.empty(B, H, nq, jp, dtype=torch.bfloat16, device=S.device)
     p = _lib.AttnRowsParams()
     p.S, p.dPp, p.Pp, p.dS, p.talk, p.dtalk = ptr(S), ptr(dPp), ptr(Pp), ptr(dS), ptr(talk), ptr(dtalk)
     p.B, p.H, p.nq, p.J, p.jp, p.out_scale = B, H, nq, J, jp, float(out_scale)
+    if key_mask is not None:
+        p.key_mask, p.mask_bs, p.has_null = ptr(key_mask), key_mask.stride(0), int(has_null)
     check(lib().nuwa_attn_bwd_rows(p, stream()), "nuwa_attn_bwd_rows")
     return Pp, dS
 
@@ -228,12 +222,9 @@ def attn_dense_bwd(q_ptr, k_ptr, v_ptr, do, *, B, nq, nk, H, dh, q_bs, q_rs, kv_
     full_s = (jp * inner, dh)
     bgemm(q_ptr, kfull, S, M=nq, N=jp, K=dh, a_trans=0, b_trans=0, lda=q_rs, ldb=inner, ldc=jp, batch1=B, batch2=H,
           a_s=(q_bs, dh), b_s=full_s, c_s=sc, alpha=scale)
-    if key_mask is not None:
-        check(lib().nuwa_mask_scores(ptr(S), ptr(key_mask), key_mask.stride(0), B, H, nq, jp, nk, has_null, stream()),
-              "nuwa_mask_scores")
     bgemm(do, vfull, dPp, M=nq, N=jp, K=dh, a_trans=0, b_trans=0, lda=inner, ldb=inner, ldc=jp, batch1=B, batch2=H,
           a_s=(nq * inner, dh), b_s=full_s, c_s=sc)
-    Pp, dS = _rows(S, dPp, talk, dtalk, B, H, nq, J, jp, scale)
+    Pp, dS = _rows(S, dPp, talk, dtalk, B, H, nq, J, jp, scale, key_mask=key_mask, has_null=has_null)  # mask fused
     del S, dPp
     # dQ = dS K
     bgemm(dS, kfull, dq_out, M=nq, N=dh, K=jp, a_trans=0, b_trans=1, lda=jp, ldb=inner, ldc=dq_rs, batch1=B, batch2=H,
