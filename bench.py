@@ -306,7 +306,57 @@ def run_ours(args):
                                    backward="not included (forward loss only; autograd kernels are next-round work)"),
                        flops=dict(mflop_per_token_fwd=104.4,
                                   achieved_tflops=round(world * ntok * args.steps / dsec * 104.4e6 / 1e12 / world, 1)))
-        del nuwa, graphed
+        del graphed
+        # ---- training step of the same config: forward loss + backward (SURVEY §8d cfg 3 timed region) ----
+        from nuwa_pytorch_b200.graphs import GraphedTrainStep
+        from nuwa_pytorch_b200.parallel import GradAllReduce
+        nuwa.train()
+        tparams = [p for n, p in nuwa.named_parameters() if not n.startswith('vae.')]
+
+        def loss_fn(t, v):
+            return nuwa(text=t, video=v, return_loss=True)  # default cond_dropout_prob = 0.2, as NUWATrainer calls it
+
+        def eager_step(t, v):
+            for p in tparams:
+                p.grad = None
+            loss = loss_fn(t, v)
+            loss.backward()
+            return loss
+
+        eager_step(text, video)
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        eager_step(text, video)
+        tl = _lib.launch_count() - l0
+        if world == 1:
+            tstepper = GraphedTrainStep(loss_fn, tparams, text, video)
+            launch_mode = "one CUDA graph replay per step (forward + backward, GraphedTrainStep)"
+        else:
+            nuwa._grad_reducer = GradAllReduce(dist)  # the ONE collective: fp32 gradient all-reduce (mean) over NCCL
+            tstepper = eager_step
+            launch_mode = "eager launches; per-sub-block NCCL all-reduce of the flat gradient buffer overlapping the backward"
+
+        def tstep():
+            return tstepper(text, video)
+
+        def tstep_e2e():
+            return float(tstepper(h_text.to(dev, non_blocking=True), h_video.to(dev, non_blocking=True)).item())
+
+        tsec = timed(tstep, args.steps, args.warmup, dist, None)
+        tsec_e2e = timed(tstep_e2e, args.steps, 1, dist, None)
+        gnorm = float(torch.sqrt(sum((p.grad.float() ** 2).sum() for p in tparams if p.grad is not None)))
+        decoder["train"] = dict(
+            metric="3DNA decoder video-tokens/sec, forward loss + backward", value=round(world * ntok * args.steps / tsec, 1),
+            unit="tokens/s", ms_per_step=round(1e3 * tsec / args.steps, 3),
+            e2e=dict(value=round(world * ntok * args.steps / tsec_e2e, 1), unit="tokens/s",
+                     h2d_bytes_per_step=int(h_text.numel() * 8 + h_video.numel() * 8), d2h_bytes_per_step=4),
+            gpu_launches=int(tl), launch=launch_mode, grad_norm=round(gnorm, 5),
+            collective=None if world == 1 else "all_reduce(AVG) of %.1f M fp32 gradients per step" % (
+                sum(p.numel() for p in tparams) / 1e6),
+            flops=dict(mflop_per_token_fwd_bwd=3 * 104.4,
+                       achieved_tflops=round(ntok * args.steps / tsec * 3 * 104.4e6 / 1e12, 1)))
+        decoder["config"]["backward"] = "see 'train' (same model and batch, loss.backward() included)"
+        del nuwa, tstepper
         torch.cuda.empty_cache()
 
     # -------- generate() (configs[3]): depth-64 reversible decoder, 5 frames = 1280 AR steps, KV-cached, --------

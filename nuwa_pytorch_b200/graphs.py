@@ -32,3 +32,37 @@ class GraphedCall:
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.static_outputs
+
+
+class GraphedTrainStep:
+    """Whole-step capture of `loss = fn(*inputs); loss.backward()`: one graph replay runs the CUDA forward, the CUDA
+    backward and the writes of every `p.grad` (static buffers owned by the graph's memory pool; each replay overwrites
+    them, so accumulate / apply the gradients before the next replay)."""
+
+    def __init__(self, fn, params, *example_inputs, warmup=3):
+        self.params = [p for p in params if p.requires_grad]
+        self.static_inputs = [t.clone() for t in example_inputs]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):  # packs weights, sets kernel attributes, warms the allocator outside the capture
+                for p in self.params:
+                    p.grad = None
+                fn(*self.static_inputs).backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for p in self.params:
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        # capture on the warm-up stream: autograd binds each parameter's AccumulateGrad node to the stream it was created
+        # on, and a node that outlived an earlier eager step on another stream would invalidate the capture
+        with torch.cuda.graph(self.graph, stream=side):
+            self.loss = fn(*self.static_inputs)
+            self.loss.backward()
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_inputs, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -1,7 +1,8 @@
-"""Multi-GPU plumbing of the hot path.  The path shards by batch with NO data-path collective (inference
-replicas): each rank owns a contiguous slice of the samples.  The only reductions are the
-benchmark's max-over-ranks timing and (for callers that want the outputs in one place) an optional gather
-outside any timed region."""
+"""Multi-GPU plumbing of the hot path.  The path shards by batch: each rank owns a contiguous
+slice of the samples.  Inference (VAE, generate) has NO data-path collective -- only the benchmark's max-over-ranks
+timing and an optional gather outside any timed region.  Training has exactly ONE: the gradient all-reduce
+(sum -> mean) of the flat fp32 gradient buffer, issued per finished sub-block so that NCCL over NVLink overlaps the
+rest of the backward (GradAllReduce)."""
 import torch
 
 
@@ -28,3 +29,51 @@ def gather_indices(local_idx, dist=None):
     out = [torch.empty_like(local_idx) for _ in range(dist.get_world_size())]
     dist.all_gather(out, local_idx.contiguous())
     return torch.cat(out, dim=0)
+
+
+class GradAllReduce:
+    """Data-parallel gradient averaging over the flat fp32 gradient buffer of train.GradStore.
+
+    `ready(lo, hi)` launches an asynchronous all-reduce of flat[lo:hi] as soon as the backward has finished writing
+    that range (the collective runs on the backend's own stream and overlaps the remaining backward kernels);
+    `finish()` reduces whatever was not announced and waits for everything.  NCCL averages in the collective
+    (ReduceOp.AVG); backends without AVG (gloo, used by the CPU tests) sum and scale."""
+
+    def __init__(self, dist, group=None, max_bucket_elems=32 * 1024 * 1024):
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group) if dist is not None and dist.is_initialized() else 1
+        self.max_bucket = max_bucket_elems
+        self.avg = self.world > 1 and dist.get_backend(group) == "nccl"
+        self.flat, self.done, self.handles = None, [], []
+
+    def begin(self, flat):
+        self.flat, self.done, self.handles = flat, [], []
+
+    def _launch(self, lo, hi):
+        d = self.dist
+        for s in range(lo, hi, self.max_bucket):
+            chunk = self.flat[s:min(hi, s + self.max_bucket)]
+            op = d.ReduceOp.AVG if self.avg else d.ReduceOp.SUM
+            self.handles.append((d.all_reduce(chunk, op=op, group=self.group, async_op=True), chunk))
+
+    def ready(self, lo, hi):
+        if self.world == 1 or hi <= lo:
+            return
+        self.done.append((lo, hi))
+        self._launch(lo, hi)
+
+    def finish(self):
+        if self.world == 1:
+            return
+        pos = 0
+        for lo, hi in sorted(self.done):  # complement of the announced ranges
+            if lo > pos:
+                self._launch(pos, lo)
+            pos = max(pos, hi)
+        if pos < self.flat.numel():
+            self._launch(pos, self.flat.numel())
+        for h, chunk in self.handles:
+            h.wait()
+            if not self.avg:
+                chunk.div_(self.world)
+        self.handles = []

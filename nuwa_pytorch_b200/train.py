@@ -45,6 +45,13 @@ class GradStore:
     def grads(self):
         return [self(p) for p in self.params]
 
+    def span(self, params):
+        """[lo, hi) of the flat buffer covering `params` (contiguous when they are consecutive in the parameter list)."""
+        ids = [self.index[id(p)] for p in params if id(p) in self.index]
+        if not ids:
+            return 0, 0
+        return self.offsets[min(ids)], self.offsets[max(ids) + 1]
+
 
 def _bw(s):
     """Transposed bf16 weight copies for the dgrad GEMMs (built once per weight version, cached on the SubBlock)."""
@@ -243,7 +250,7 @@ def _sub_backward(i, s, rec, dy16, B, nt, g, tape, dctx):
     return ops.gemm(dqkv, bw['w_qkv_t'], out_dtype=torch.float32)
 
 
-def stack_backward(stack, tape, dout, g, dctx=None):
+def stack_backward(stack, tape, dout, g, dctx=None, on_done=None):
     """dout: fp32 (B*nt, D) gradient of the stack output (after its StableLayerNorm).  g: GradStore.
     dctx: fp32 (B*nk, D) accumulator for the gradient w.r.t. the cross-attention context (or None).
     Returns the gradient w.r.t. the stack input, fp32 (B*nt, D)."""
@@ -267,6 +274,8 @@ def stack_backward(stack, tape, dout, g, dctx=None):
         ops_bwd.ln_bwd(da, rec['x_read'], s.pre[0], nt=nt, dw=g(sw.prenorm.weight), db=g(sw.prenorm.bias), unshift=s.shift,
                        fmap=s.fmap or 0, dx_f32=G[s.read], accumulate=True)
         tape['recs'][i] = None  # free the saved activations of this sub-block
+        if on_done is not None:
+            on_done(s)  # every gradient of this sub-block's parameters is final (data-parallel all-reduce can start)
     if pack.reversible:
         ops_bwd.add_rows(G[0], G[1])  # both streams start as x
     return G[0]
@@ -308,6 +317,10 @@ class NuwaStep:
     def backward(self, gout, reducer=None):
         m = self.model
         g = GradStore(self.params)
+        on_done = None
+        if reducer is not None:
+            reducer.begin(g.flat)
+            on_done = lambda s: reducer.ready(*g.span(list(s.sandwich.parameters())))  # noqa: E731
         B, N = self.idx.shape
         D = self.y16.shape[1]
         gscale = gout.detach().to(torch.float32).reshape(1).contiguous()
@@ -318,7 +331,7 @@ class NuwaStep:
         del dlogits
         nk = self.context.ctx16.shape[1]
         dctx = torch.zeros(B * nk, D, dtype=torch.float32, device=dy.device)
-        dx = stack_backward(m.video_transformer, self.tape_dec, dy, g, dctx)
+        dx = stack_backward(m.video_transformer, self.tape_dec, dy, g, dctx, on_done)
         frac = m.image_embedding.frac_gradient if m.training else 1.0
         pe = m.video_pos_emb
         dax, ax = [], 1
@@ -339,7 +352,7 @@ class NuwaStep:
                           daxials=dpos, dims=(self.text.shape[1], 1, 1))
         self.tape_dec = self.tape_text = None
         if reducer is not None:
-            reducer(g.flat)
+            reducer.finish()
         return g.grads()
 
 

@@ -43,3 +43,35 @@ def test_rank_slice_covers_everything():
             parts = [rank_slice(n, r, world) for r in range(world)]
             assert parts[0][0] == 0 and parts[-1][1] == n
             assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+
+
+def _reducer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nuwa_pytorch_b200.parallel import GradAllReduce
+    flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)      # rank-dependent "gradients"
+    red = GradAllReduce(dist, max_bucket_elems=128)                   # small buckets: exercises the chunking
+    red.begin(flat)
+    red.ready(700, 900)   # ranges become final in backward order, with holes that finish() must cover
+    red.ready(300, 700)
+    red.ready(0, 0)
+    red.finish()
+    q.put((rank, flat.tolist()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_allreduce_mean():
+    """The one collective of the training path: every element of the flat gradient buffer ends up as the mean over
+    ranks exactly once, whatever order the ranges were announced in."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = (torch.arange(1000, dtype=torch.float32) * 1.5).tolist()   # mean of x*1 and x*2
+    assert res[0][1] == want and res[1][1] == want

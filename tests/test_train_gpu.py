@@ -64,3 +64,28 @@ def test_backward_scales_with_grad_output_and_accumulates(cuda_device):
     for k, p in model.named_parameters():
         if p.grad is not None and g1[k].abs().max() > 0:
             assert rel(p.grad, 2 * g1[k]) < 2e-3, k  # split-K / atomic summation order is the only difference
+
+
+def test_whole_step_cuda_graph_matches_eager(cuda_device):
+    """bench.py replays the training step (forward + backward) from one CUDA graph: same loss and gradients as eager."""
+    from nuwa_pytorch_b200.graphs import GraphedTrainStep
+    fx, model = _train_model("nuwa_small.pt", cuda_device)
+    text, vidx = fx['text'].to(cuda_device), fx['video_indices'].to(cuda_device)
+    params = [p for n, p in model.named_parameters() if not n.startswith('vae.')]
+    fn = lambda t, v: model(text=t, video=v, return_loss=True, cond_dropout_prob=0.)  # noqa: E731
+    eager_loss = fn(text, vidx)
+    eager_loss.backward()
+    eager = [p.grad.clone() if p.grad is not None else None for p in params]
+    eager_loss = eager_loss.detach()  # drop the eager autograd graph (and its stream-bound AccumulateGrad nodes)
+    step = GraphedTrainStep(fn, params, text, vidx)
+    for _ in range(2):
+        loss = step(text, vidx)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - eager_loss.item()) < 1e-5
+    for p, e in zip(params, eager):
+        if e is not None and e.abs().max() > 0:
+            assert rel(p.grad, e) < 2e-3  # atomic summation order only
+    # new inputs through the static buffers
+    vidx2 = (vidx + 1) % 64
+    l2 = step(text, vidx2).item()
+    assert abs(l2 - fn(text, vidx2).item()) < 1e-4
