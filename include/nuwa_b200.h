@@ -332,6 +332,14 @@ int nuwa_attn3dna_bwd_dq(const nuwa_attn_params* p, const void* dS, int jp, void
                          void* stream);
 int nuwa_attn3dna_bwd_dkdv(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, const void* dS,
                            const void* Pp, int jp, void* dk, void* dv, long long dkv_bs, int dkv_rs, void* stream);
+/* SparseCross2DNA non-bos queries (nuwa_pytorch.py:851-895): same three passes; nk = context tokens; base_k / base_v
+ * (fp32 [B][nk] rows with strides base_bs / base_rs, or NULL) is added to the key gradients (the dense bos query's part) */
+int nuwa_attnx2_bwd_scores(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp,
+                           int jp, void* stream);
+int nuwa_attnx2_bwd_dq(const nuwa_attn_params* p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs, void* stream);
+int nuwa_attnx2_bwd_dkdv(const nuwa_attn_params* p, int nk, const void* dO, long long do_bs, int do_rs, const void* dS,
+                         const void* Pp, int jp, const float* base_k, const float* base_v, long long base_bs, int base_rs,
+                         void* dk, void* dv, long long dkv_bs, int dkv_rs, void* stream);
 /* slot 0 (bos key / null key): out_k[b] += sum_q dS[b,h,q,0] q[b,q] ; out_v[b] += sum_q Pp[b,h,q,0] dO[b,q] */
 int nuwa_attn_bwd_first_key(const void* q, long long q_bs, int q_rs, const void* dO, long long do_bs, int do_rs,
                             const void* dS, const void* Pp, int jp, int B, int H, int dh, int nq, float* out_k,

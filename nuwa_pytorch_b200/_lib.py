@@ -126,6 +126,10 @@ SIGNATURES = {
     "nuwa_attn3dna_bwd_dq": [P(AttnParams), c_void_p, c_int, c_void_p, c_ll, c_int, c_void_p],
     "nuwa_attn3dna_bwd_dkdv": [P(AttnParams), c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll,
                                c_int, c_void_p],
+    "nuwa_attnx2_bwd_scores": [P(AttnParams), c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    "nuwa_attnx2_bwd_dq": [P(AttnParams), c_void_p, c_int, c_void_p, c_ll, c_int, c_void_p],
+    "nuwa_attnx2_bwd_dkdv": [P(AttnParams), c_int, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll,
+                             c_int, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "nuwa_attn_bwd_first_key": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p],
     "nuwa_attn3dna_bwd_first_key_finalize": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p],

@@ -196,6 +196,20 @@ int nuwa_attn3dna_bwd_first_key_finalize(const float* tmp_k, const float* tmp_v,
                                          void* dqkv, long long dqkv_bs, int inner, int B, void* stream) {
   return attn3dna_bwd_first_key_finalize(tmp_k, tmp_v, dO_bos, do_bs, dqkv, dqkv_bs, inner, B, S(stream));
 }
+int nuwa_attnx2_bwd_scores(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* Sc, float* dPp,
+                           int jp, void* stream) {
+  return p ? attnx2_bwd_scores(*p, dO, do_bs, do_rs, Sc, dPp, jp, S(stream)) : NUWA_ERR_INVALID;
+}
+int nuwa_attnx2_bwd_dq(const nuwa_attn_params* p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs, void* stream) {
+  return p ? attnx2_bwd_dq(*p, dS, jp, dq, dq_bs, dq_rs, S(stream)) : NUWA_ERR_INVALID;
+}
+int nuwa_attnx2_bwd_dkdv(const nuwa_attn_params* p, int nk, const void* dO, long long do_bs, int do_rs, const void* dS,
+                         const void* Pp, int jp, const float* base_k, const float* base_v, long long base_bs, int base_rs,
+                         void* dk, void* dv, long long dkv_bs, int dkv_rs, void* stream) {
+  return p ? attnx2_bwd_dkdv(*p, nk, dO, do_bs, do_rs, dS, Pp, jp, base_k, base_v, base_bs, base_rs, dk, dv, dkv_bs, dkv_rs,
+                             S(stream))
+           : NUWA_ERR_INVALID;
+}
 void nuwa_struct_sizes_bwd(int* out4) {
   out4[0] = (int)sizeof(nuwa_bgemm_params);
   out4[1] = (int)sizeof(nuwa_lnbwd_params);

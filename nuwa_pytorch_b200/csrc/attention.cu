@@ -810,6 +810,85 @@ int attn3dna_bwd_dkdv(const AttnParams& p, const void* dO, long long do_bs, int 
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
 }
+// SparseCross2DNA key-centric pass: context key (f_s, yy, xx) <- queries at (y, x) = key - offset*dil + pad in EVERY video
+// frame (inverse of key_of<MODE_X2DNA>).  base_k / base_v (fp32, optional): the dense bos-query contribution, added in.
+template <int CPL>
+__global__ void __launch_bounds__(128)
+gather_dkdv_x2dna_kernel(const AttnParams p, int nk, const bf16* __restrict__ dO, long long do_bs, int do_rs,
+                         const bf16* __restrict__ dS, const bf16* __restrict__ Pp, int jp, const float* __restrict__ base_k,
+                         const float* __restrict__ base_v, long long base_bs, int base_rs, bf16* __restrict__ dk,
+                         bf16* __restrict__ dv, long long dkv_bs, int dkv_rs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int lph = 32 / p.H, h = lane / lph;
+  const long long gidx = blockIdx.x * (long long)wpb + warp;
+  if (gidx >= (long long)p.B * nk) return;
+  const int b = (int)(gidx / nk), kidx = (int)(gidx - (long long)b * nk);
+  const int T = p.fmap * p.fmap;
+  const int fs = kidx / T, ky = (kidx % T) / p.fmap, kx = kidx % p.fmap;
+  const int pad = p.cdil * (p.ck - 1) / 2;
+  const int J2 = p.ck * p.ck;
+  const int ch = lane * CPL;
+  const bf16* qb = reinterpret_cast<const bf16*>(p.q) + (long long)b * p.q_bs;
+  const bf16* dob = dO + (long long)b * do_bs;
+  float ak[CPL], av[CPL];
+  if (base_k != nullptr) {
+    load_row_f32<CPL>(base_k + (long long)b * base_bs + (long long)kidx * base_rs + ch, ak);
+    load_row_f32<CPL>(base_v + (long long)b * base_bs + (long long)kidx * base_rs + ch, av);
+  } else {
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) ak[c] = av[c] = 0.f;
+  }
+  const long long hb = ((long long)b * p.H + h) * p.nq;
+  for (int w = 0; w < J2; ++w) {
+    const int a = w / p.ck, c = w - a * p.ck;
+    const int qy = ky - a * p.cdil + pad, qx = kx - c * p.cdil + pad;
+    if (qy < 0 || qy >= p.fmap || qx < 0 || qx >= p.fmap) continue;
+    const int j = 1 + fs * J2 + w;
+    for (int ql = qy * p.fmap + qx + 1 - p.t0; ql < p.nq; ql += T) {  // the same (y, x) in every video frame
+      if (ql < 0) continue;
+      const float ws = __bfloat162float(dS[(hb + ql) * jp + j]);
+      const float wp = __bfloat162float(Pp[(hb + ql) * jp + j]);
+      float qv[CPL], dv_[CPL];
+      load_row<CPL>(qb + (long long)ql * p.q_rs + ch, qv);
+      load_row<CPL>(dob + (long long)ql * do_rs + ch, dv_);
+#pragma unroll
+      for (int cc = 0; cc < CPL; ++cc) {
+        ak[cc] = fmaf(ws, qv[cc], ak[cc]);
+        av[cc] = fmaf(wp, dv_[cc], av[cc]);
+      }
+    }
+  }
+  const long long o = (long long)b * dkv_bs + (long long)kidx * dkv_rs + ch;
+  store_row<CPL>(dk + o, ak);
+  store_row<CPL>(dv + o, av);
+}
+
+int attnx2_bwd_scores(const AttnParams& p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp, int jp,
+                      cudaStream_t s) {
+  return launch_gather_scores<MODE_X2DNA>(p, dO, do_bs, do_rs, S, dPp, jp, s);
+}
+int attnx2_bwd_dq(const AttnParams& p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs, cudaStream_t s) {
+  return launch_gather_dq<MODE_X2DNA>(p, dS, jp, dq, dq_bs, dq_rs, s);
+}
+int attnx2_bwd_dkdv(const AttnParams& p, int nk, const void* dO, long long do_bs, int do_rs, const void* dS, const void* Pp,
+                    int jp, const float* base_k, const float* base_v, long long base_bs, int base_rs, void* dk, void* dv,
+                    long long dkv_bs, int dkv_rs, cudaStream_t stream) {
+  const int inner = p.H * p.dh;
+  if (inner % 32 != 0 || (32 % p.H) != 0 || p.H > 32 || nk <= 0 || p.fmap <= 0 || (nk % (p.fmap * p.fmap)) != 0)
+    return NUWA_ERR_INVALID;
+  const int cpl = inner / 32, warps = 4;
+  const long long groups = (long long)p.B * nk;
+  const unsigned grid = (unsigned)((groups + warps - 1) / warps);
+#define CALL(C)                                                                                                         \
+  gather_dkdv_x2dna_kernel<C><<<grid, warps * 32, 0, stream>>>(                                                         \
+      p, nk, reinterpret_cast<const bf16*>(dO), do_bs, do_rs, reinterpret_cast<const bf16*>(dS),                        \
+      reinterpret_cast<const bf16*>(Pp), jp, base_k, base_v, base_bs, base_rs, reinterpret_cast<bf16*>(dk),             \
+      reinterpret_cast<bf16*>(dv), dkv_bs, dkv_rs)
+  NUWA_CPL_SWITCH(cpl, CALL)
+#undef CALL
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
 int attn_bwd_first_key(const void* q, long long q_bs, int q_rs, const void* dO, long long do_bs, int do_rs, const void* dS,
                        const void* Pp, int jp, int B, int H, int dh, int nq, float* out_k, float* out_v, long long ok_bs,
                        cudaStream_t stream) {

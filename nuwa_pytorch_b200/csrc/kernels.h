@@ -122,6 +122,12 @@ int attn3dna_bwd_scores(const AttnParams& p, const void* dO, long long do_bs, in
 int attn3dna_bwd_dq(const AttnParams& p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs, cudaStream_t s);
 int attn3dna_bwd_dkdv(const AttnParams& p, const void* dO, long long do_bs, int do_rs, const void* dS, const void* Pp, int jp,
                       void* dk, void* dv, long long dkv_bs, int dkv_rs, cudaStream_t stream);
+int attnx2_bwd_scores(const AttnParams& p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp, int jp,
+                      cudaStream_t s);
+int attnx2_bwd_dq(const AttnParams& p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs, cudaStream_t s);
+int attnx2_bwd_dkdv(const AttnParams& p, int nk, const void* dO, long long do_bs, int do_rs, const void* dS, const void* Pp,
+                    int jp, const float* base_k, const float* base_v, long long base_bs, int base_rs, void* dk, void* dv,
+                    long long dkv_bs, int dkv_rs, cudaStream_t stream);
 int attn_bwd_first_key(const void* q, long long q_bs, int q_rs, const void* dO, long long do_bs, int do_rs, const void* dS,
                        const void* Pp, int jp, int B, int H, int dh, int nq, float* out_k, float* out_v, long long ok_bs,
                        cudaStream_t stream);

@@ -650,8 +650,19 @@ class NUWASketch(nn.Module, _VideoDecoderMixin):
         frames = video.shape[1]
         assert sketch_image_size == self.image_size, 'sketch image size must be equal'
         assert sketch_frames <= self.sketch_max_video_frames, 'sketch frames must be less than max sketch video frames'
+        train_path = return_loss and torch.is_grad_enabled() and self.to_logits.weight.requires_grad
         with torch.no_grad():
-            context = self._sketch_context(sketch, sketch_mask)
+            if not train_path:
+                context = self._sketch_context(sketch, sketch_mask)
+            else:  # training step (train.py): keep the sketch token ids, the sketch encoder runs with a tape
+                if _exists(sketch_mask):
+                    assert sketch_mask.shape[:2] == (batch, sketch_frames), 'sketch mask must be in shape of (batch x frame)'
+                sketch_indices = self.sketch_vae.get_video_indices(sketch)
+                per_frame = sketch_indices[0, 0].numel()
+                tok_mask = (sketch_mask[:, :, None].expand(batch, sketch_frames, per_frame).reshape(batch, -1)
+                            if _exists(sketch_mask) else
+                            torch.ones((batch, sketch_frames * per_frame), dtype=torch.bool, device=sketch.device))
+                tok_mask = tok_mask.to(torch.uint8).contiguous()
         assert frames == self.max_video_frames, f'you must give the full video frames ({self.max_video_frames}) during training'
         frame_indices = self.vae.get_video_indices(video).reshape(batch, -1)
         if self.training and cond_dropout_prob > 0:
@@ -661,5 +672,8 @@ class NUWASketch(nn.Module, _VideoDecoderMixin):
                 raise TypeError("unsupported operand type(s) for *=: 'NoneType' and 'Tensor'")
             uncond = torch.zeros((batch,), device=sketch.device).float().uniform_(0, 1) < cond_dropout_prob
             sketch_mask *= ~uncond[:, None]
+        if train_path:
+            from . import train
+            return train.sketch_training_loss(self, sketch_indices, tok_mask, frame_indices)
         with torch.no_grad():
             return self._decoder_logits(frame_indices, context, return_loss)

@@ -239,3 +239,52 @@ def attn_dense_bwd(q_ptr, k_ptr, v_ptr, do, *, B, nq, nk, H, dh, q_bs, q_rs, kv_
     k16, v16, k32, v32 = (None, None, dk_ptr, dv_ptr) if out_f32 else (dk_ptr, dv_ptr, None, None)
     check(lib().nuwa_kv_full_split(ptr(dkfull), ptr(dvfull), ptr(dnull_k), ptr(dnull_v), k16, v16, k32, v32, dkv_bs, dkv_rs,
                                    B, nk, jp, inner, stream()), "nuwa_kv_full_split")
+
+
+def attn_cross2dna_bwd(q, kv, do, *, B, n, nk, H, dh, talk, dtalk, null_k, null_v, dnull_k, dnull_v, key_mask, fmap, ck, cdil):
+    """Backward of the SparseCross2DNA core over a full teacher-forced pass (nuwa_pytorch.py:794-901): position 0 (bos) is a
+    dense query over [null] + every context token WITHOUT talking heads (:828-844), positions 1.. attend to the null key
+    and the ck x ck window at their own (y, x) in every context frame (:851-895).
+    q: bf16 (B, n, inner); kv: bf16 (B, nk, 2*inner); do: bf16 (B, n, inner).  Returns dq (B, n, inner), dkv (B, nk, 2*inner)
+    bf16; adds to dtalk, dnull_k, dnull_v."""
+    inner = H * dh
+    dev = q.device
+    dq = torch.empty(B, n, inner, dtype=torch.bfloat16, device=dev)
+    dkv = torch.empty(B, nk, 2 * inner, dtype=torch.bfloat16, device=dev)
+    kb = kv.data_ptr()
+    # ---- bos query: dense, fp32 key gradients kept as the base of the key-centric pass ----
+    base = torch.empty(B, nk, 2 * inner, dtype=torch.float32, device=dev)
+    do0 = do[:, 0].contiguous().view(B, 1, inner)
+    attn_dense_bwd(q.data_ptr(), kb, kb + inner * 2, do0, B=B, nq=1, nk=nk, H=H, dh=dh, q_bs=n * inner, q_rs=inner,
+                   kv_bs=nk * 2 * inner, kv_rs=2 * inner, talk=None, dtalk=None, null_k=null_k, null_v=null_v,
+                   dnull_k=dnull_k, dnull_v=dnull_v, key_mask=key_mask, dq_out=(dq, dq.data_ptr()), dq_bs=n * inner,
+                   dq_rs=inner, dk_ptr=base.data_ptr(), dv_ptr=base.data_ptr() + inner * 4, dkv_bs=nk * 2 * inner,
+                   dkv_rs=2 * inner, out_f32=True)
+    nq = n - 1
+    if nq <= 0:
+        dkv.copy_(base)
+        return dq, dkv
+    frames = nk // (fmap * fmap)
+    J = 1 + frames * ck * ck
+    jp = _round_up(J, 8)
+    p = ops._attn_base(q.data_ptr() + inner * 2, kb, kb + inner * 2, None, B, nq, 1, H, dh, n * inner, nk * 2 * inner,
+                       nk * 2 * inner, 0, inner, 2 * inner, 2 * inner, inner, talk)
+    p.null_k, p.null_v = ptr(null_k), ptr(null_v)
+    if key_mask is not None:
+        p.key_mask, p.mask_bs = ptr(key_mask), key_mask.shape[1]
+    p.fmap, p.ck, p.cdil, p.jmax = fmap, ck, cdil, J
+    S = torch.empty(B, H, nq, jp, dtype=torch.float32, device=dev)
+    dPp = torch.empty(B, H, nq, jp, dtype=torch.float32, device=dev)
+    do_q = do.data_ptr() + inner * 2
+    check(lib().nuwa_attnx2_bwd_scores(p, do_q, n * inner, inner, ptr(S), ptr(dPp), jp, stream()), "nuwa_attnx2_bwd_scores")
+    Pp, dS = _rows(S, dPp, talk, dtalk, B, H, nq, J, jp, dh ** -0.5)  # masks already folded into S by the gather
+    check(lib().nuwa_attnx2_bwd_dq(p, ptr(dS), jp, dq.data_ptr() + inner * 2, n * inner, inner, stream()),
+          "nuwa_attnx2_bwd_dq")
+    check(lib().nuwa_attnx2_bwd_dkdv(p, nk, do_q, n * inner, inner, ptr(dS), ptr(Pp), jp, ptr(base),
+                                     base.data_ptr() + inner * 4, nk * 2 * inner, 2 * inner, dkv.data_ptr(),
+                                     dkv.data_ptr() + inner * 2, nk * 2 * inner, 2 * inner, stream()),
+          "nuwa_attnx2_bwd_dkdv")
+    check(lib().nuwa_attn_bwd_first_key(q.data_ptr() + inner * 2, n * inner, inner, do_q, n * inner, inner, ptr(dS),
+                                        ptr(Pp), jp, B, H, dh, nq, ptr(dnull_k), ptr(dnull_v), 0, stream()),
+          "nuwa_attn_bwd_first_key")
+    return dq, dkv

@@ -120,7 +120,22 @@ def _sub_forward(i, s, a, B, nt, rec, context, key_mask, rotary):
                        k_bs=nk * 2 * inner, k_rs=2 * inner, v_bs=nk * 2 * inner, v_rs=2 * inner, o_bs=nt * inner,
                        o_rs=inner, talk=s.talk, null_k=s.null_k, null_v=s.null_v, key_mask=context.mask)
         return ops.gemm(o, s.w_out, out_dtype=torch.float32)
-    raise NotImplementedError(f"training path of sub-block kind '{s.kind}' (SparseCross2DNA) is not built yet")
+    if s.kind == 'x2dna':
+        nk = context.ctx16.shape[1]
+        kv = ops.gemm(context.ctx16.view(B * nk, -1), s.w_kv, out_dtype=torch.bfloat16)
+        q = ops.gemm(a, s.w_q, out_dtype=torch.bfloat16)
+        rec['q'], rec['kv'] = q, kv
+        kb = kv.data_ptr()
+        common = dict(B=B, H=H, dh=dh, q_bs=nt * inner, q_rs=inner, k_bs=nk * 2 * inner, k_rs=2 * inner,
+                      v_bs=nk * 2 * inner, v_rs=2 * inner, o_bs=nt * inner, o_rs=inner, null_k=s.null_k, null_v=s.null_v,
+                      key_mask=context.mask)
+        # bos query: dense over [null] + every context token, no talking heads (nuwa_pytorch.py:828-844)
+        ops.attn_dense(q.data_ptr(), kb, kb + inner * 2, o, nq=1, nk=nk, talk=None, **common)
+        if nt > 1:
+            ops.attn_cross2dna(q.data_ptr() + inner * 2, kb, kb + inner * 2, o.data_ptr() + inner * 2, nq=nt - 1, t0=1,
+                               talk=s.talk, fmap=s.fmap, frames=nk // (s.fmap * s.fmap), ck=s.ck, cdil=s.cdil, **common)
+        return ops.gemm(o, s.w_out, out_dtype=torch.float32)
+    raise NotImplementedError(s.kind)
 
 
 def stack_forward(stack, x, *, context=None, key_mask=None, rotary=None):
@@ -220,21 +235,29 @@ def _sub_backward(i, s, rec, dy16, B, nt, g, tape, dctx):
                                dv_ptr=dq_all.data_ptr() + 2 * inner * esz, dkv_bs=nt * 3 * inner, dkv_rs=3 * inner,
                                out_f32=rotary is not None)
         dqkv = ops_bwd.rotary_bwd_to_bf16(dq_all, rotary[0], nt, H, dh_, rotary[1]) if rotary is not None else dq_all
-    elif s.kind == 'cross':
+    elif s.kind in ('cross', 'x2dna'):
         ctx = tape['context']
         nk = ctx.ctx16.shape[1]
         q, kv = rec['q'], rec['kv']
         dnk, dnv = g(m.null_k), g(m.null_v)
         dnk = dnk.view(-1) if dnk is not None else torch.zeros(inner, device=do.device)
         dnv = dnv.view(-1) if dnv is not None else torch.zeros(inner, device=do.device)
-        dq = torch.empty(M, inner, dtype=torch.bfloat16, device=do.device)
-        dkv = torch.empty(B * nk, 2 * inner, dtype=torch.bfloat16, device=do.device)
-        kb = kv.data_ptr()
-        ops_bwd.attn_dense_bwd(q.data_ptr(), kb, kb + inner * 2, do.view(B, nt, inner), B=B, nq=nt, nk=nk, H=H, dh=dh_,
-                               q_bs=nt * inner, q_rs=inner, kv_bs=nk * 2 * inner, kv_rs=2 * inner, talk=s.talk, dtalk=dtalk,
-                               null_k=s.null_k, null_v=s.null_v, dnull_k=dnk, dnull_v=dnv, key_mask=ctx.mask, dq_out=dq,
-                               dq_bs=nt * inner, dq_rs=inner, dk_ptr=dkv.data_ptr(), dv_ptr=dkv.data_ptr() + inner * 2,
-                               dkv_bs=nk * 2 * inner, dkv_rs=2 * inner, out_f32=False)
+        if s.kind == 'cross':
+            dq = torch.empty(M, inner, dtype=torch.bfloat16, device=do.device)
+            dkv = torch.empty(B * nk, 2 * inner, dtype=torch.bfloat16, device=do.device)
+            kb = kv.data_ptr()
+            ops_bwd.attn_dense_bwd(q.data_ptr(), kb, kb + inner * 2, do.view(B, nt, inner), B=B, nq=nt, nk=nk, H=H, dh=dh_,
+                                   q_bs=nt * inner, q_rs=inner, kv_bs=nk * 2 * inner, kv_rs=2 * inner, talk=s.talk,
+                                   dtalk=dtalk, null_k=s.null_k, null_v=s.null_v, dnull_k=dnk, dnull_v=dnv,
+                                   key_mask=ctx.mask, dq_out=dq, dq_bs=nt * inner, dq_rs=inner, dk_ptr=dkv.data_ptr(),
+                                   dv_ptr=dkv.data_ptr() + inner * 2, dkv_bs=nk * 2 * inner, dkv_rs=2 * inner,
+                                   out_f32=False)
+        else:
+            dq, dkv = ops_bwd.attn_cross2dna_bwd(q.view(B, nt, inner), kv.view(B, nk, 2 * inner), do.view(B, nt, inner), B=B,
+                                                 n=nt, nk=nk, H=H, dh=dh_, talk=s.talk, dtalk=dtalk, null_k=s.null_k,
+                                                 null_v=s.null_v, dnull_k=dnk, dnull_v=dnv, key_mask=ctx.mask, fmap=s.fmap,
+                                                 ck=s.ck, cdil=s.cdil)
+            dq, dkv = dq.view(M, inner), dkv.view(B * nk, 2 * inner)
         _wgrad(T(dq), aT, g(m.to_q.weight))
         if dctx is not None:
             if getattr(ctx, 'ctx16_T', None) is None:
@@ -372,4 +395,78 @@ class _StepFn(torch.autograd.Function):
 
 def nuwa_training_loss(model, text, frame_indices, text_mask_dec):
     step = NuwaStep(model, text, frame_indices, text_mask_dec)
+    return _StepFn.apply(step, *step.params)
+
+
+# ------------------------------------------------------------------------------------------------
+# NUWASketch training step (nuwa_pytorch.py:2514-2571): sketch tokens -> sketch encoder -> decoder with SparseCross2DNA
+# ------------------------------------------------------------------------------------------------
+class SketchStep(NuwaStep):
+    def __init__(self, model, sketch_indices, tok_mask_u8, frame_indices):
+        self.model, self.sidx, self.tok_mask, self.idx = model, sketch_indices, tok_mask_u8, frame_indices.contiguous()
+        self.params = [p for n, p in model.named_parameters()
+                       if p.requires_grad and not n.startswith('vae.') and not n.startswith('sketch_vae.')]
+
+    def forward(self):
+        m = self.model
+        idx = self.idx
+        B, N = idx.shape
+        sflat = self.sidx.reshape(B, -1).contiguous()
+        self.sflat = sflat
+        ns = sflat.shape[1]
+        tokens = ops.embed_tokens(sflat, m.sketch_embedding.embed.weight.detach().float().contiguous(), nt=ns,
+                                  axials=m.sketch_pos_emb.tables(), dims=m.sketch_pos_emb.full_shape)
+        _, e16, self.tape_ctx = stack_forward(m.sketch_transformer, tokens, key_mask=self.tok_mask)
+        self.context = engine.Context(e16, self.tok_mask)
+        x = m._embed_video(idx, N)
+        _, y16, self.tape_dec = stack_forward(m.video_transformer, x, context=self.context)
+        self.y16 = y16.view(B * N, -1)
+        self.logits = ops.gemm(self.y16, m._logits_weight(), out_dtype=torch.float32)
+        self.targets = idx.reshape(-1).contiguous()
+        return ops.cross_entropy_mean(self.logits, self.targets)
+
+    def backward(self, gout, reducer=None):
+        m = self.model
+        g = GradStore(self.params)
+        on_done = None
+        if reducer is not None:
+            reducer.begin(g.flat)
+            on_done = lambda s: reducer.ready(*g.span(list(s.sandwich.parameters())))  # noqa: E731
+        B, N = self.idx.shape
+        D = self.y16.shape[1]
+        gscale = gout.detach().to(torch.float32).reshape(1).contiguous()
+        dlogits = ops_bwd.ce_bwd(self.logits, self.targets, gscale)
+        self.logits = None
+        w_t = ops_bwd.transpose(m._logits_weight()).contiguous()
+        dy = ops_bwd.linear_bwd(dlogits, self.y16, w_t, g(m.to_logits.weight))
+        del dlogits
+        nk = self.context.ctx16.shape[1]
+        dctx = torch.zeros(B * nk, D, dtype=torch.float32, device=dy.device)
+        dx = stack_backward(m.video_transformer, self.tape_dec, dy, g, dctx, on_done)
+
+        def axial_grads(pe):
+            out, ax = [], 1
+            for length in pe.full_shape:
+                if length > 1:
+                    out.append(g(getattr(pe, f'axial{ax}')))
+                    ax += 1
+                else:
+                    out.append(None)
+            return tuple(out)
+
+        frac = m.image_embedding.frac_gradient if m.training else 1.0
+        ops_bwd.embed_bwd(dx, self.idx, g(m.image_embedding.embed.weight), nt=N, frac=frac, dbos=g(m.video_bos),
+                          daxials=axial_grads(m.video_pos_emb), dims=m.video_pos_emb.full_shape)
+        dtok = stack_backward(m.sketch_transformer, self.tape_ctx, dctx, g)
+        frac_s = m.sketch_embedding.frac_gradient if m.training else 1.0
+        ops_bwd.embed_bwd(dtok, self.sflat, g(m.sketch_embedding.embed.weight), nt=self.sflat.shape[1], frac=frac_s,
+                          daxials=axial_grads(m.sketch_pos_emb), dims=m.sketch_pos_emb.full_shape)
+        self.tape_dec = self.tape_ctx = None
+        if reducer is not None:
+            reducer.finish()
+        return g.grads()
+
+
+def sketch_training_loss(model, sketch_indices, tok_mask_u8, frame_indices):
+    step = SketchStep(model, sketch_indices, tok_mask_u8, frame_indices)
     return _StepFn.apply(step, *step.params)

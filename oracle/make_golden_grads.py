@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import nuwa_oracle as O  # noqa: E402
 from oracle.ref_import import import_reference  # noqa: E402
-from oracle.synth import synth_state_dict  # noqa: E402
+from oracle.synth import manifest_of, synth_state_dict  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -62,6 +62,43 @@ def main():
         path = os.path.join(OUT, name + "_grads.pt")
         torch.save(dict(loss=loss.detach(), grads=grads), path)
         print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+    # ---------------- NUWASketch (cfg-5 shape of path: 3DNA sketch encoder, SparseCross2DNA decoder), end to end ----------
+    fx = torch.load(os.path.join(OUT, "sketch_small.pt"))
+    vae = VQ.VQGanVAE(**fx['vae_kwargs']).eval()
+    vae.load_state_dict(synth_state_dict(manifest_of(vae.state_dict()), fx['vae_seed']), strict=False)
+    svae = VQ.VQGanVAE(**fx['sketch_vae_kwargs']).eval()
+    svae.load_state_dict(synth_state_dict(manifest_of(svae.state_dict()), fx['sketch_vae_seed']), strict=False)
+    sk = NP.NUWASketch(vae=vae, sketch_vae=svae, **fx['kwargs'])
+    sd = synth_state_dict(fx['manifest'], fx['seed'])
+    sk.load_state_dict(sd, strict=False)
+    sk.train()
+    g = lambda seed: torch.Generator().manual_seed(seed)  # noqa: E731
+    sketch = torch.randn(2, 3, 5, 64, 64, generator=g(fx['e2e_sketch_seed']))
+    video = torch.randn(2, 3, 3, 64, 64, generator=g(fx['e2e_video_seed']))
+    smask = torch.ones(2, 3, dtype=torch.bool)
+    loss = sk(sketch=sketch, sketch_mask=smask.clone(), video=video, return_loss=True, cond_dropout_prob=0.)
+    loss.backward()
+    assert abs(loss.item() - fx['e2e_loss'].item()) < 1e-6
+    grads = {k: p.grad.clone() for k, p in sk.named_parameters() if p.grad is not None}
+    assert not any(k.startswith('vae.') or k.startswith('sketch_vae.') for k in grads)
+    with torch.no_grad():
+        sidx = sk.sketch_vae.get_video_indices(sketch)
+        fi = sk.vae.get_video_indices(video).reshape(2, -1)
+    spec = O.SketchSpec(64, 4, 3, 3, 64, sketch_enc_depth=2, sketch_enc_heads=2, sketch_enc_use_sparse_3dna=True,
+                        dec_depth=3, dec_heads=2, kernel=(5, 3, 3), dilation=(1, 2), cross_dilation=2)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.is_floating_point() and not k.startswith('vae.') and not k.startswith('sketch_vae.')}
+    full = dict(sd)
+    full.update(leaves)
+    _, oloss = O.sketch_logits(sidx, smask, fi, full, spec)
+    oloss.backward()
+    worst = max(rel(leaves[k].grad, gr) for k, gr in grads.items())
+    print(f"sketch_small: {len(grads)} gradient tensors, oracle-vs-reference worst rel {worst:.2e}")
+    assert worst < 2e-4 and abs(oloss.item() - loss.item()) < 1e-6
+    path = os.path.join(OUT, "sketch_small_grads.pt")
+    torch.save(dict(loss=loss.detach(), grads=grads), path)
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
 if __name__ == "__main__":

@@ -242,3 +242,39 @@ def test_attn_dense_bwd(cuda_device, B, nq, nk, H, dh, null, masked):
     assert rel(dtalk, tk.grad) < 1.5e-2
     if null:
         assert rel(dnk, nkr.grad) < 1.5e-2 and rel(dnv, nvr.grad) < 1.5e-2
+
+
+@pytest.mark.parametrize("n,frames,ck,cdil,H,dh,masked", [(49, 3, 3, 1, 2, 32, True), (40, 2, 3, 2, 2, 32, False),
+                                                           (33, 1, 5, 1, 8, 64, True), (1, 2, 3, 1, 2, 32, True)])
+def test_attn_cross2dna_bwd(cuda_device, n, frames, ck, cdil, H, dh, masked):
+    """SparseCross2DNA core backward (dense bos query + windowed queries + null key) vs autograd on the oracle."""
+    from nuwa_pytorch_b200 import ops_bwd
+    g = gen(70 + n + ck)
+    B, fmap = 2, 4
+    inner, nk = H * dh, frames * 16
+    q = torch.randn(B, n, inner, generator=g).bfloat16()
+    kv = torch.randn(B, nk, 2 * inner, generator=g).bfloat16()
+    do = torch.randn(B, n, inner, generator=g).bfloat16()
+    talk = torch.randn(H, H, generator=g) / 2
+    null_k, null_v = torch.randn(inner, generator=g).bfloat16().float(), torch.randn(inner, generator=g).bfloat16().float()
+    mask = torch.rand(B, nk, generator=g) > 0.3 if masked else None
+    if masked:
+        mask[0, :16] = False
+    eye = torch.eye(inner)
+    qr, kvr, tk, nkr, nvr = (t.float().clone().requires_grad_() for t in (q, kv, talk, null_k, null_v))
+    p = {'to_q.weight': eye, 'to_kv.weight': torch.eye(2 * inner), 'to_out.weight': eye,
+         'talking_heads.weight': tk[:, :, None, None, None], 'null_k': nkr.view(H, 1, dh), 'null_v': nvr.view(H, 1, dh)}
+    out = O.sparse_cross2dna(qr, p, H, kvr, mask, fmap, ck, cdil)
+    out.backward(do.float())
+    dv_ = lambda t: t.to(cuda_device).contiguous()
+    dtalk = torch.zeros(H, H, device=cuda_device)
+    dnk, dnv = torch.zeros(inner, device=cuda_device), torch.zeros(inner, device=cuda_device)
+    dq, dkv = ops_bwd.attn_cross2dna_bwd(dv_(q), dv_(kv), dv_(do), B=B, n=n, nk=nk, H=H, dh=dh, talk=dv_(talk), dtalk=dtalk,
+                                         null_k=dv_(null_k), null_v=dv_(null_v), dnull_k=dnk, dnull_v=dnv,
+                                         key_mask=dv_(mask.to(torch.uint8)) if masked else None, fmap=fmap, ck=ck, cdil=cdil)
+    print(f"  x2dna bwd n={n} frames={frames} ck={ck} d={cdil}: dq {rel(dq.float(), qr.grad):.2e} dkv "
+          f"{rel(dkv.float(), kvr.grad):.2e} dnull {rel(dnk, nkr.grad):.2e}/{rel(dnv, nvr.grad):.2e}")
+    assert rel(dq.float(), qr.grad) < 1.5e-2 and rel(dkv.float(), kvr.grad) < 1.5e-2
+    assert rel(dnk, nkr.grad) < 1.5e-2 and rel(dnv, nvr.grad) < 1.5e-2
+    if n > 1:
+        assert rel(dtalk, tk.grad) < 1.5e-2
