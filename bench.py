@@ -359,6 +359,55 @@ def run_ours(args):
         del nuwa, tstepper
         torch.cuda.empty_cache()
 
+        # ---- NUWASketch training step (BASELINE configs[4]): 12-layer 3DNA sketch encoder over 3 sketch frames, ----
+        # ---- 24-layer decoder with SparseCross2DNA, batch 4 per GPU, float sketch + video through both VAEs     ----
+        if not args.skip_sketch:
+            from nuwa_pytorch_b200 import NUWASketch, VQGanVAE
+            torch.manual_seed(0)
+            with torch.device(dev):
+                svae = VQGanVAE(**{**DEC_VAE_KW, "channels": 5})
+                vvae = VQGanVAE(**DEC_VAE_KW)
+                sk = NUWASketch(vae=vvae, sketch_vae=svae, dim=512, image_size=256, sketch_enc_depth=12,
+                                sketch_max_video_frames=3, sketch_enc_use_sparse_3dna=True, max_video_frames=10, dec_depth=24,
+                                sparse_3dna_kernel_size=(5, 3, 3), sparse_3dna_dilation=(1, 2, 4)).train()
+            SB = 4
+            gs = torch.Generator(device=dev).manual_seed(300 + rank)
+            sketch = torch.randn(SB, 3, 5, 256, 256, device=dev, generator=gs)
+            svideo = torch.randn(SB, 10, 3, 256, 256, device=dev, generator=gs)
+            smask = torch.ones(SB, 3, dtype=torch.bool, device=dev)
+            h_sketch, h_svideo = sketch.cpu().pin_memory(), svideo.cpu().pin_memory()
+            sparams = [p for n, p in sk.named_parameters() if not n.startswith('vae.') and not n.startswith('sketch_vae.')]
+            if world > 1:
+                sk._grad_reducer = GradAllReduce(dist)
+
+            def sk_step(s_, v_):
+                for p in sparams:
+                    p.grad = None
+                loss = sk(sketch=s_, sketch_mask=smask.clone(), video=v_, return_loss=True)
+                loss.backward()
+                return loss
+
+            sk_step(sketch, svideo)
+            torch.cuda.synchronize()
+            l0 = _lib.launch_count()
+            sk_step(sketch, svideo)
+            sl = _lib.launch_count() - l0
+            ssec = timed(lambda: sk_step(sketch, svideo), args.steps, args.warmup, dist, None)
+            ssec_e2e = timed(lambda: float(sk_step(h_sketch.to(dev, non_blocking=True), h_svideo.to(dev, non_blocking=True)).item()),
+                             args.steps, 1, dist, None)
+            stok = SB * 2560
+            decoder["sketch_train"] = dict(
+                metric="NUWASketch video-tokens/sec, forward loss + backward (incl. both VAE encodes)",
+                value=round(world * stok * args.steps / ssec, 1), unit="tokens/s", ms_per_step=round(1e3 * ssec / args.steps, 3),
+                e2e=dict(value=round(world * stok * args.steps / ssec_e2e, 1), unit="tokens/s",
+                         h2d_bytes_per_step=int(h_sketch.numel() * 4 + h_svideo.numel() * 4), d2h_bytes_per_step=4),
+                gpu_launches=int(sl), launch="eager launches" + ("" if world == 1 else " + overlapped NCCL gradient all-reduce"),
+                config=dict(workload="NUWASketch dim=512 sketch_enc_depth=12 (Sparse3DNA) sketch_max_video_frames=3 dec_depth=24 "
+                            "(Sparse3DNA + SparseCross2DNA) max_video_frames=10, loss.backward() (BASELINE configs[4])",
+                            batch_per_gpu=SB, tokens_per_sample=2560, context_tokens=768))
+            del sk, svae, vvae
+            torch.cuda.empty_cache()
+
     # -------- generate() (configs[3]): depth-64 reversible decoder, 5 frames = 1280 AR steps, KV-cached, --------
     # -------- one CUDA-graph replay per token (both guidance sweeps + sampling inside the graph)          --------
     generate = None
@@ -434,6 +483,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--vae-batch", type=int, default=VAE_BATCH)
+    ap.add_argument("--skip-sketch", action="store_true", help="skip the NUWASketch training leg")
     ap.add_argument("--skip-decoder", action="store_true")
     ap.add_argument("--skip-generate", action="store_true")
     ap.add_argument("--gen-frames", type=int, default=5)

@@ -224,7 +224,11 @@ def attn_dense_bwd(q_ptr, k_ptr, v_ptr, do, *, B, nq, nk, H, dh, q_bs, q_rs, kv_
           a_s=(q_bs, dh), b_s=full_s, c_s=sc, alpha=scale)
     bgemm(do, vfull, dPp, M=nq, N=jp, K=dh, a_trans=0, b_trans=0, lda=inner, ldb=inner, ldc=jp, batch1=B, batch2=H,
           a_s=(nq * inner, dh), b_s=full_s, c_s=sc)
-    Pp, dS = _rows(S, dPp, talk, dtalk, B, H, nq, J, jp, scale, key_mask=key_mask, has_null=has_null)  # mask fused
+    fuse_mask = J <= 288  # the register-resident row kernel applies the key mask itself; the wide fallback wants it in S
+    if key_mask is not None and not fuse_mask:
+        check(lib().nuwa_mask_scores(ptr(S), ptr(key_mask), key_mask.stride(0), B, H, nq, jp, nk, has_null, stream()),
+              "nuwa_mask_scores")
+    Pp, dS = _rows(S, dPp, talk, dtalk, B, H, nq, J, jp, scale, key_mask=key_mask if fuse_mask else None, has_null=has_null)
     del S, dPp
     # dQ = dS K
     bgemm(dS, kfull, dq_out, M=nq, N=dh, K=jp, a_trans=0, b_trans=1, lda=jp, ldb=inner, ldc=dq_rs, batch1=B, batch2=H,

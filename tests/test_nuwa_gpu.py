@@ -192,9 +192,11 @@ def test_cuda_graph_replay_matches_eager(cuda_device):
     from nuwa_pytorch_b200.graphs import GraphedCall
     fx, model, sd = _nuwa("nuwa_small.pt", cuda_device)
     text, vidx = fx['text'].to(cuda_device), fx['video_indices'].to(cuda_device)
-    eager = model(text=text, video=vidx, return_loss=True).item()
+    with torch.no_grad():  # the inference path (with autograd enabled, forward() takes the training path of train.py)
+        eager = model(text=text, video=vidx, return_loss=True).item()
     g = GraphedCall(lambda t, v: model(text=t, video=v, return_loss=True), text, vidx)
     assert abs(g(text, vidx).item() - eager) < 1e-6
     vidx2 = (vidx + 7) % 64
-    eager2 = model(text=text, video=vidx2, return_loss=True).item()
+    with torch.no_grad():
+        eager2 = model(text=text, video=vidx2, return_loss=True).item()
     assert abs(g(text, vidx2).item() - eager2) < 1e-6 and abs(eager2 - eager) > 1e-4
