@@ -123,3 +123,22 @@ def test_topk_gumbel():
     u = torch.rand(3, 100, generator=gen(6))
     s = O.gumbel_argmax(f, u)
     assert all(f[i, s[i]] > float('-inf') for i in range(3))
+
+
+def test_oracle_autograd_matches_reference_gradients():
+    """The oracle is also the checker of the CUDA backward: its autograd must reproduce the gradients the UNMODIFIED
+    reference produced for `loss.backward()` (tests/golden/*_grads.pt, oracle/make_golden_grads.py)."""
+    import torch
+    from tests.helpers import golden, nuwa_spec_from_kwargs, rel, synth
+    for name in ("nuwa_small", "nuwa_rev_small"):
+        fx, gold = golden(name + ".pt"), golden(name + "_grads.pt")
+        sd = synth(fx)
+        spec = nuwa_spec_from_kwargs(fx['kwargs'], fx['vae_kwargs'])
+        leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and not k.startswith('vae.')}
+        full = dict(sd)
+        full.update(leaves)
+        _, loss = O.nuwa_logits(fx['text'], fx['video_indices'].reshape(2, -1), full, spec)
+        loss.backward()
+        assert abs(loss.item() - gold['loss'].item()) < 1e-5
+        worst = max(rel(leaves[k].grad, g) for k, g in gold['grads'].items())
+        assert worst < 3e-4, (name, worst)
