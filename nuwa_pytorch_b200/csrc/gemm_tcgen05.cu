@@ -32,7 +32,9 @@ static constexpr int EPI_WARPS = 8;
 static constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-9 epilogue
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
 static constexpr int EPI_PITCH = 20;  // floats per staged row: 16 outputs + 4 pad (conflict-free float4 access)
-static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
+static constexpr int EPI_SLAB = 4096;  // per epilogue warp: 32 rows x 128 B TMA-store slab (the transposing path uses 2.5 KB of it)
+static constexpr int EPI_BYTES = EPI_WARPS * EPI_SLAB;
+static constexpr int BAR_BYTES = 1024;  // barrier block; keeps the slabs 1024-byte aligned (SWIZZLE_128B TMA stores)
 
 template <int BN>
 struct GemmCfg {
@@ -40,7 +42,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator buffers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + EPI_BYTES;
 };
 
 struct TileCoord {
@@ -181,7 +183,8 @@ template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
-                    const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                    const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -209,6 +212,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
+    if (p.tma_out) tma_prefetch_desc(&tmC);
     if (p.conv) {
       tma_prefetch_desc(&tmA1);
       tma_prefetch_desc(&tmA2);
@@ -313,7 +317,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const int half = ew >> 2;       // which half of the tile's column chunks this warp drains
     constexpr int CHUNKS = BN / 32;
     constexpr int CPW = (CHUNKS + 1) / 2;  // chunks per warp
-    float* stg = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + ew * (32 * EPI_PITCH);
+    uint8_t* slab = smem + Cfg::STAGES * Cfg::STAGE_BYTES + BAR_BYTES + ew * EPI_SLAB;
+    float* stg = reinterpret_cast<float*>(slab);
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool pair = (p.act == ACT_GLU || p.act == ACT_GEGLU);
@@ -364,7 +369,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
           }
           const int nc = n0 + c * 32;
-          if (nc < p.N) {  // warp-uniform
+          if (p.tma_out && nc < p.N) {
+            // ---- TMA-store epilogue: this lane's accumulator row (32 columns) -> bias / LeakyReLU -> swizzled slab row,
+            //      one elected lane hands the 32 x 32 slab to the TMA unit (bounds are clipped by the tensor map; split-K
+            //      partial products use the fp32 reduce-add form) ----
+            if (lane == 0) tma_store_wait_read0();  // the previous store has finished reading the slab
+            __syncwarp();
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nc + j < p.N) o[j] += __ldg(p.bias + nc + j);
+            }
+            if (p.act == ACT_LEAKY) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = leaky01(o[j]);
+            }
+            if (p.out_f32 != nullptr) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                *reinterpret_cast<float4*>(slab + lane * 128 + ((k ^ (lane & 7)) << 4)) =
+                    make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint4 u;
+                u.x = pack_bf16x2(o[8 * k], o[8 * k + 1]); u.y = pack_bf16x2(o[8 * k + 2], o[8 * k + 3]);
+                u.z = pack_bf16x2(o[8 * k + 4], o[8 * k + 5]); u.w = pack_bf16x2(o[8 * k + 6], o[8 * k + 7]);
+                *reinterpret_cast<uint4*>(slab + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = u;
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int m0 = tc.mt * BM + q * 32;
+              if (p.tma_out == 2) tma_reduce_add_2d(&tmC, slab, nc, m0);
+              else tma_store_2d(&tmC, slab, nc, m0);
+              tma_store_commit();
+            }
+          } else if (nc < p.N) {  // warp-uniform
             switch (p.act) {
               case ACT_LEAKY: epi_chunk<ACT_LEAKY>(v, stg, lane, mrow, okmask, nc, n_out_total, p); break;
               case ACT_GLU: epi_chunk<ACT_GLU>(v, stg, lane, mrow, okmask, nc, n_out_total, p); break;
@@ -382,6 +427,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         acc_phase ^= 1;
       }
     }
+    if (p.tma_out && lane == 0) tma_store_wait0();  // all bulk stores of this warp are complete before the CTA exits
   }
 
   tc_fence_before();
@@ -415,7 +461,8 @@ static PFN_encodeTiled get_encode_fn() {
 
 // rank-2..4 bf16 tensor map, innermost box 64 elements (128 B), SWIZZLE_128B, zero OOB fill.
 static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box) {
+                      const uint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                      CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return NUWA_ERR_DRIVER;
   cuuint64_t gdims[4];
@@ -428,8 +475,8 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64
     estr[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i];
   }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(map, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? NUWA_OK : NUWA_ERR_INVALID;
 }
@@ -494,7 +541,8 @@ static cudaEvent_t prof_event() {
 }
 
 template <int BN>
-static int launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, const CUtensorMap& mC, GemmParams& p,
+                       cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
   static bool attr_set = false;
@@ -518,7 +566,7 @@ static int launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, GemmParams&
   int grid = total < device_sm_count() ? total : device_sm_count();
   if (grid <= 0) return NUWA_OK;
   if (g_prof_on) cudaEventRecord(prof_event(), stream);
-  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mA[0], mA[1], mA[2], mA[3], mB, p);
+  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mA[0], mA[1], mA[2], mA[3], mB, mC, p);
   if (g_prof_on) {
     cudaEventRecord(prof_event(), stream);
     g_prof_flops += g_cur_flops;
@@ -536,9 +584,29 @@ static int dispatch_gemm(const CUtensorMap* mA, const void* Wp, GemmParams& p, i
   uint32_t boxB[2] = {64, (uint32_t)bn};
   int e = encode_map(&mB, Wp, 2, dimsB, strB, boxB);
   if (e) return e;
-  if (bn == 256) return launch_gemm<256>(mA, mB, p, stream);
-  if (bn == 128) return launch_gemm<128>(mA, mB, p, stream);
-  return launch_gemm<64>(mA, mB, p, stream);
+  // Output through TMA stores (32 x 32 slabs) when the epilogue is "bias + optional LeakyReLU" of a plain GEMM with one
+  // 16-byte aligned output: removes the per-element address / bounds / transposition instructions that made small-K
+  // shapes epilogue-issue bound.  Split-K partial products use the fp32 reduce-add form instead of atomics.
+  CUtensorMap mC = mB;
+  p.tma_out = 0;
+  {
+    const bool one_out = (p.out_f32 != nullptr) != (p.out_bf16 != nullptr);
+    const bool f32 = p.out_f32 != nullptr;
+    const void* outp = f32 ? (const void*)p.out_f32 : (const void*)p.out_bf16;
+    const size_t esz = f32 ? 4 : 2;
+    if (!p.conv && p.residual == nullptr && one_out && (p.act == ACT_NONE || p.act == ACT_LEAKY) &&
+        (reinterpret_cast<uintptr_t>(outp) & 15) == 0 && ((size_t)p.ld_out * esz) % 16 == 0 && (!p.atomic_out || f32)) {
+      uint64_t dimsC[2] = {(uint64_t)p.N, (uint64_t)p.M};
+      uint64_t strC[2] = {esz, (uint64_t)p.ld_out * esz};
+      uint32_t boxC[2] = {32, 32};
+      if (encode_map(&mC, outp, 2, dimsC, strC, boxC, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                     f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B) == NUWA_OK)
+        p.tma_out = p.atomic_out ? 2 : 1;
+    }
+  }
+  if (bn == 256) return launch_gemm<256>(mA, mB, mC, p, stream);
+  if (bn == 128) return launch_gemm<128>(mA, mB, mC, p, stream);
+  return launch_gemm<64>(mA, mB, mC, p, stream);
 }
 
 static bool epilogue_args_ok(const GemmParams& p) {

@@ -30,6 +30,7 @@ struct GemmParams {
   int8_t tap_dy[16];
   // split-K (weight-gradient GEMMs: small output, long contraction): item = tile * splits + split
   int splits, kb_per_split, atomic_out;
+  int tma_out;  // 0: per-thread stores, 1: TMA tile stores, 2: TMA fp32 reduce-add (split-K)
 };
 
 typedef nuwa_attn_params AttnParams;
