@@ -53,6 +53,10 @@ int nuwa_attn_sparse3dna(const nuwa_attn_params* p, void* vt_workspace, void* st
 }
 int nuwa_attn_dense(const nuwa_attn_params* p, void* vt_workspace, void* stream) {
   if (!p) return NUWA_ERR_INVALID;
+  if (p->nq >= 16) {  // 8 x 64 heads, learned null key / mask / talking heads: two-pass 64-query tensor-core kernel
+    const int rc = attn_dense_x64(*p, p->jmax - (p->null_k != nullptr ? 1 : 0), S(stream));
+    if (rc != NUWA_ERR_INVALID) return rc;
+  }
   if (vt_workspace != nullptr && p->nq >= 8) {
     const int nk = p->jmax - (p->null_k != nullptr ? 1 : 0);
     const int rc = attn_dense_mma(*p, nk, vt_workspace, S(stream));

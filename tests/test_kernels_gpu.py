@@ -268,3 +268,48 @@ def test_attn_dense_tensor_core_variant(cuda_device, B, nq, nk, H, dh, null, tal
     print(f"  dense attn B={B} nq={nq} nk={nk}: mma rel {r_mma:.2e}, generic rel {r_gen:.2e}")
     assert r_gen < 4e-3      # fp32 math, one bf16 rounding of the output
     assert r_mma < 8e-3      # additionally rounds the probabilities to bf16 for the PV tensor-core product
+
+
+@pytest.mark.parametrize("B,nq,nk,null,talk,masked", [(2, 100, 256, True, True, True), (1, 64, 50, True, True, False),
+                                                       (3, 16, 12, False, True, True), (2, 257, 77, True, False, True),
+                                                       (1, 2560, 256, True, True, True)])
+def test_attn_dense_x64_two_pass_kernel(cuda_device, B, nq, nk, null, talk, masked):
+    """attention_x64.cu (8 heads x 64, 64-query tiles, statistics pass + register talking-heads mix) vs the oracle math."""
+    from nuwa_pytorch_b200 import ops
+    g = gen(300 + nq + nk)
+    H, dh = 8, 64
+    inner = H * dh
+    q = torch.randn(B, nq, inner, generator=g).bfloat16()
+    kv = torch.randn(B, nk, 2 * inner, generator=g).bfloat16()
+    tk = torch.randn(H, H, generator=g) / 2 if talk else None
+    null_k, null_v = (torch.randn(inner, generator=g), torch.randn(inner, generator=g)) if null else (None, None)
+    mask = None
+    if masked:
+        mask = torch.rand(B, nk, generator=g) > 0.3
+        mask[0, :nk // 2] = False
+        if not null:
+            mask[:, -1] = True
+    qh = O._heads(q.float(), H) * dh ** -0.5
+    k, v = kv.float().chunk(2, -1)
+    kh, vh = O._heads(k, H), O._heads(v, H)
+    if null:
+        kh = torch.cat([null_k.view(1, H, 1, dh).expand(B, -1, -1, -1), kh], 2)
+        vh = torch.cat([null_v.view(1, H, 1, dh).expand(B, -1, -1, -1), vh], 2)
+    sim = qh @ kh.transpose(-1, -2)
+    if masked:
+        mm = F.pad(mask, (1, 0), value=True) if null else mask
+        sim = sim.masked_fill(~mm[:, None, None], O.NEG)
+    attn = sim.softmax(-1)
+    if talk:
+        attn = O._talking_heads(attn, tk[:, :, None, None])
+    ref = O._merge(attn @ vh)
+    dv = lambda t_: t_.to(cuda_device).contiguous() if t_ is not None else None
+    qd, kvd = dv(q), dv(kv)
+    o = torch.zeros(B, nq, inner, dtype=torch.bfloat16, device=cuda_device)
+    ops.attn_dense(qd.data_ptr(), kvd.data_ptr(), kvd.data_ptr() + inner * 2, o, B=B, nq=nq, nk=nk, H=H, dh=dh,
+                   q_bs=nq * inner, q_rs=inner, k_bs=nk * 2 * inner, k_rs=2 * inner, v_bs=nk * 2 * inner, v_rs=2 * inner,
+                   o_bs=nq * inner, o_rs=inner, talk=dv(tk), null_k=dv(null_k), null_v=dv(null_v),
+                   key_mask=dv(mask.to(torch.uint8)) if masked else None)
+    r = rel(o.float(), ref)
+    print(f"  x64 dense attention B={B} nq={nq} nk={nk}: rel {r:.2e}")
+    assert r < 6e-3  # probabilities are rounded to bf16 for the tensor-core P'V, output stored as bf16
