@@ -11,10 +11,11 @@
 //           holds the same (query, key) slots for every head), feed the mixed probabilities straight back into the
 //           tensor cores as the A operand of P'V.
 //
-// CTA = 64 queries of one sample, 8 warps: warp = (16-query tile, half of the output heads).  Both warps of a tile compute
-// the logits of all 8 heads (the mix needs them) but accumulate only their 4 output heads (128 accumulator registers).
-// Q (once) and K / V chunks (double buffered cp.async) are staged in shared memory and read with ldmatrix; the learned
-// null key stays an exact fp32 side column as in the reference.
+// CTA = 64 queries of one sample, 16 warps: warp = (16-query tile, pair of heads).  A warp computes the logits of its two
+// heads, publishes the normalised probabilities (bf16) to the three other warps of its tile through shared memory (named
+// barrier per tile), mixes all 8 heads for its two OUTPUT heads and accumulates their P'V (64 accumulator registers, so
+// 16 warps fit an SM and hide the ldmatrix / mma latencies).  Q (once) and 16-key K / V chunks (double buffered cp.async)
+// are staged in shared memory and read with ldmatrix; the learned null key stays an exact fp32 side column.
 #include <float.h>
 
 #include "common.cuh"
@@ -25,9 +26,12 @@ namespace nuwa {
 namespace {
 
 constexpr int XQ = 64;        // queries per CTA
-constexpr int XK = 32;        // keys per staged chunk
+constexpr int XK = 16;        // keys per staged chunk (one m16n8k16 contraction step of P'V)
 constexpr int XH = 8, XD = 64, XC = XH * XD;
 constexpr int XP = XC + 8;    // bf16 row pitch (1040 B): conflict-free ldmatrix rows
+constexpr int XS = 3;         // cp.async stages of the K / V chunk ring
+constexpr int XT = 512;       // threads: 16 warps = 4 query tiles x 4 head pairs
+constexpr int EXP = 16 + 2;   // bf16 pitch of one exchanged probability row (16 keys), padded against bank conflicts
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
@@ -53,6 +57,9 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // rows [r0, r0+nrows) of a (row-strided) bf16 matrix with XC columns -> dst[row][XP]; rows >= limit are zero filled
 __device__ __forceinline__ void stage_rows(bf16* dst, const bf16* src, long long row_stride, int r0, int nrows, int limit) {
@@ -63,12 +70,30 @@ __device__ __forceinline__ void stage_rows(bf16* dst, const bf16* src, long long
   }
 }
 
-__global__ void __launch_bounds__(256, 1) attn_dense_x64_kernel(const AttnParams p, int nk) {
+// logits of heads h0, h0+1 of this warp's 16 queries against the 16 staged keys: s[head][8-key block][c-fragment]
+__device__ __forceinline__ void scores2(const bf16* Qs, const bf16* Kc, int rbase, int h0, int l8, int id, float (&s)[2][2][4]) {
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) s[hh][blk][0] = s[hh][blk][1] = s[hh][blk][2] = s[hh][blk][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t qa[4], kb[4];
+      ldsm4(qa, Qs + (rbase + l8 + 8 * (id & 1)) * XP + (h0 + hh) * XD + ks * 16 + 8 * (id >> 1));
+      ldsm4(kb, Kc + (l8 + 8 * (id >> 1)) * XP + (h0 + hh) * XD + ks * 16 + 8 * (id & 1));
+      mma16816(s[hh][0], qa, kb[0], kb[1]);
+      mma16816(s[hh][1], qa, kb[2], kb[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(XT, 1) attn_dense_x64_kernel(const AttnParams p, int nk) {
   extern __shared__ __align__(16) uint8_t smem_x[];
   bf16* Qs = reinterpret_cast<bf16*>(smem_x);                 // [XQ][XP]
-  bf16* Ks = Qs + XQ * XP;                                    // [2][XK][XP]
-  bf16* Vs = Ks + 2 * XK * XP;                                // [2][XK][XP]
-  float* Wt = reinterpret_cast<float*>(Vs + 2 * XK * XP);     // [8][8]
+  bf16* Ks = Qs + XQ * XP;                                    // [XS][XK][XP]
+  bf16* Vs = Ks + XS * XK * XP;                               // [XS][XK][XP]
+  bf16* Ex = Vs + XS * XK * XP;                                // [2][4 tiles][8 heads][16 rows][EXP] normalised probabilities
+  float* Wt = reinterpret_cast<float*>(Ex + 2 * 4 * XH * 16 * EXP);  // [8][8]
   float* nullk = Wt + 64;                                     // [512]
   float* nullv = nullk + XC;                                  // [512]
   float* st_m = nullv + XC;                                   // [XQ][8] row max
@@ -76,7 +101,7 @@ __global__ void __launch_bounds__(256, 1) attn_dense_x64_kernel(const AttnParams
   float* st_sn = st_il + XQ * XH;                             // [XQ][8] null-key logit
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = warp >> 1, part = warp & 1;
+  const int qt = warp >> 2, hp = warp & 3, h0 = hp * 2;       // query tile, head pair
   const int g = lane >> 2, t = lane & 3, id = lane >> 3, l8 = lane & 7;
   const int tiles = (p.nq + XQ - 1) / XQ;
   const int b = blockIdx.x / tiles, q0 = (blockIdx.x - b * tiles) * XQ;
@@ -89,9 +114,14 @@ __global__ void __launch_bounds__(256, 1) attn_dense_x64_kernel(const AttnParams
   const float scale = p.qscale;
 
   // ---- prologue: Q tile + first K chunk in flight, small fp32 tables by plain loads ----
+  // cp.async pipeline, XS stages, prefetch distance XS - 1: iteration c waits for chunk c, ONE barrier, then refills the
+  // stage chunk c - 1 just vacated with chunk c + XS - 1 (a commit every iteration keeps the group count uniform)
   stage_rows(Qs, qg, p.q_rs, q0, XQ, p.nq);
-  stage_rows(Ks, kg, p.k_rs, 0, XK, nk);
-  cp_async_commit();
+#pragma unroll
+  for (int pc = 0; pc < XS - 1; ++pc) {
+    if (pc < nchunks) stage_rows(Ks + pc * XK * XP, kg, p.k_rs, pc * XK, XK, nk);
+    cp_async_commit();
+  }
   for (int i = threadIdx.x; i < 64; i += blockDim.x) Wt[i] = p.talk != nullptr ? p.talk[i] : ((i >> 3) == (i & 7) ? 1.f : 0.f);
   for (int i = threadIdx.x; i < XC; i += blockDim.x) {
     nullk[i] = has_null ? p.null_k[i] : 0.f;
@@ -99,69 +129,48 @@ __global__ void __launch_bounds__(256, 1) attn_dense_x64_kernel(const AttnParams
   }
   const int rbase = qt * 16;  // this warp's 16 query rows inside the tile
 
-  // =========================== pass 1: softmax statistics of heads part*4 .. part*4+3 ===========================
-  float m[4][2], l[4][2];
+  // =========================== pass 1: softmax statistics of heads h0, h0 + 1 ===========================
+  float m[2][2], l[2][2];
 #pragma unroll
-  for (int hh = 0; hh < 4; ++hh) m[hh][0] = m[hh][1] = -FLT_MAX, l[hh][0] = l[hh][1] = 0.f;
+  for (int hh = 0; hh < 2; ++hh) m[hh][0] = m[hh][1] = -FLT_MAX, l[hh][0] = l[hh][1] = 0.f;
   for (int c = 0; c < nchunks; ++c) {
-    if (c + 1 < nchunks) {
-      stage_rows(Ks + ((c + 1) & 1) * XK * XP, kg, p.k_rs, (c + 1) * XK, XK, nk);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    cp_async_wait<XS - 2>();
     __syncthreads();
-    const bf16* Kc = Ks + (c & 1) * XK * XP;
-    bool ok[2][2][2];  // [16-key group][8-key block][column]
+    if (c + XS - 1 < nchunks) stage_rows(Ks + ((c + XS - 1) % XS) * XK * XP, kg, p.k_rs, (c + XS - 1) * XK, XK, nk);
+    cp_async_commit();
+    float s[2][2][4];
+    scores2(Qs, Ks + (c % XS) * XK * XP, rbase, h0, l8, id, s);
+    bool ok[2][2];  // [8-key block][column]
 #pragma unroll
-    for (int n16 = 0; n16 < 2; ++n16)
+    for (int blk = 0; blk < 2; ++blk)
 #pragma unroll
-      for (int blk = 0; blk < 2; ++blk)
+      for (int e = 0; e < 2; ++e) {
+        const int j = c * XK + blk * 8 + 2 * t + e;
+        ok[blk][e] = j < nk && (km == nullptr || km[j] != 0);
+      }
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = c * XK + n16 * 16 + blk * 8 + 2 * t + e;
-          ok[n16][blk][e] = j < nk && (km == nullptr || km[j] != 0);
-        }
+    for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-    for (int hh = 0; hh < 4; ++hh) {
-      const int h = part * 4 + hh;
-      uint32_t qa[4][4];
+      for (int r = 0; r < 2; ++r) {  // row g (r = 0) / g + 8 (r = 1)
+        float v[4];
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) ldsm4(qa[ks], Qs + (rbase + l8 + 8 * (id & 1)) * XP + h * XD + ks * 16 + 8 * (id >> 1));
+        for (int blk = 0; blk < 2; ++blk)
 #pragma unroll
-      for (int n16 = 0; n16 < 2; ++n16) {
-        float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint32_t kb[4];
-          ldsm4(kb, Kc + (n16 * 16 + l8 + 8 * (id >> 1)) * XP + h * XD + ks * 16 + 8 * (id & 1));
-          mma16816(s[0], qa[ks], kb[0], kb[1]);
-          mma16816(s[1], qa[ks], kb[2], kb[3]);
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {  // row g (r = 0) / g + 8 (r = 1)
-          float v[4];
-#pragma unroll
-          for (int blk = 0; blk < 2; ++blk)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) v[blk * 2 + e] = ok[n16][blk][e] ? s[blk][r * 2 + e] * scale : -FLT_MAX;
-          const float bm = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
-          const float mn = fmaxf(m[hh][r], bm);
-          if (mn > -FLT_MAX) {
-            l[hh][r] = l[hh][r] * __expf(m[hh][r] - mn) + __expf(v[0] - mn) + __expf(v[1] - mn) + __expf(v[2] - mn) +
-                       __expf(v[3] - mn);
-            m[hh][r] = mn;
-          }
+          for (int e = 0; e < 2; ++e) v[blk * 2 + e] = ok[blk][e] ? s[hh][blk][r * 2 + e] * scale : -FLT_MAX;
+        const float mn = fmaxf(m[hh][r], fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])));
+        if (mn > -FLT_MAX) {
+          l[hh][r] = l[hh][r] * __expf(m[hh][r] - mn) + __expf(v[0] - mn) + __expf(v[1] - mn) + __expf(v[2] - mn) +
+                     __expf(v[3] - mn);
+          m[hh][r] = mn;
         }
       }
-    }
-    __syncthreads();  // everyone is done with buffer (c & 1) before chunk c + 2 lands in it
   }
+  cp_async_wait<0>();
+  __syncthreads();  // every warp is done with the K stages of pass 1
   // ---- combine the four lanes of a quad, fold in the exact fp32 null-key logit, publish ----
 #pragma unroll
-  for (int hh = 0; hh < 4; ++hh) {
-    const int h = part * 4 + hh;
+  for (int hh = 0; hh < 2; ++hh) {
+    const int h = h0 + hh;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       float mm = m[hh][r], ll = l[hh][r];
@@ -184,121 +193,121 @@ __global__ void __launch_bounds__(256, 1) attn_dense_x64_kernel(const AttnParams
         ll = ll * __expf(mm - mn) + __expf(sn - mn);
         mm = mn;
       }
+      m[hh][r] = mm;
+      l[hh][r] = ll > 0.f ? 1.0f / ll : 0.f;  // from here on: 1 / row sum
       if (t == 0) {
         const int row = rbase + g + 8 * r;
         st_m[row * XH + h] = mm;
-        st_il[row * XH + h] = ll > 0.f ? 1.0f / ll : 0.f;
+        st_il[row * XH + h] = l[hh][r];
         st_sn[row * XH + h] = sn;
       }
     }
   }
-  // first K / V chunk of pass 2 (buffers are free: the loop above ended with a barrier)
-  stage_rows(Ks, kg, p.k_rs, 0, XK, nk);
-  stage_rows(Vs, vg, p.v_rs, 0, XK, nk);
-  cp_async_commit();
-  __syncthreads();  // statistics of all heads visible
-
-  // =========================== pass 2: normalise, mix heads, P'V for output heads part*4 .. +3 ===========================
-  float O[4][8][4];
+  // first K / V chunks of pass 2 (the stages are free: barrier above)
 #pragma unroll
-  for (int go = 0; go < 4; ++go)
+  for (int pc = 0; pc < XS - 1; ++pc) {
+    if (pc < nchunks) {
+      stage_rows(Ks + pc * XK * XP, kg, p.k_rs, pc * XK, XK, nk);
+      stage_rows(Vs + pc * XK * XP, vg, p.v_rs, pc * XK, XK, nk);
+    }
+    cp_async_commit();
+  }
+
+  // =========================== pass 2: normalise, exchange, mix heads, P'V for output heads h0, h0 + 1 ===========================
+  float O[2][8][4];
+#pragma unroll
+  for (int go = 0; go < 2; ++go)
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) O[go][nt][0] = O[go][nt][1] = O[go][nt][2] = O[go][nt][3] = 0.f;
+  float wmix[2][8];
   for (int c = 0; c < nchunks; ++c) {
-    if (c + 1 < nchunks) {
-      stage_rows(Ks + ((c + 1) & 1) * XK * XP, kg, p.k_rs, (c + 1) * XK, XK, nk);
-      stage_rows(Vs + ((c + 1) & 1) * XK * XP, vg, p.v_rs, (c + 1) * XK, XK, nk);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
+    cp_async_wait<XS - 2>();
+    __syncthreads();  // chunk c visible to all; everyone finished chunk c - 1 (its stage is refilled next, and the exchange
+                      // buffer of chunk c - 2 may be overwritten)
+    if (c + XS - 1 < nchunks) {
+      stage_rows(Ks + ((c + XS - 1) % XS) * XK * XP, kg, p.k_rs, (c + XS - 1) * XK, XK, nk);
+      stage_rows(Vs + ((c + XS - 1) % XS) * XK * XP, vg, p.v_rs, (c + XS - 1) * XK, XK, nk);
     }
-    __syncthreads();
-    const bf16* Kc = Ks + (c & 1) * XK * XP;
-    const bf16* Vc = Vs + (c & 1) * XK * XP;
-#pragma unroll 1
-    for (int n16 = 0; n16 < 2; ++n16) {
-      bool ok[2][2];
+    cp_async_commit();
+    if (c == 0) {  // Wt was written before the first barrier of pass 1
+#pragma unroll
+      for (int go = 0; go < 2; ++go)
+#pragma unroll
+        for (int h = 0; h < 8; ++h) wmix[go][h] = Wt[(h0 + go) * 8 + h];
+    }
+    const bf16* Vc = Vs + (c % XS) * XK * XP;
+    float s[2][2][4];
+    scores2(Qs, Ks + (c % XS) * XK * XP, rbase, h0, l8, id, s);
+    // ---- normalised probabilities of my two heads -> exchange buffer (bf16) ----
+    bf16* ex = Ex + ((c & 1) * 4 + qt) * XH * 16 * EXP;
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+      bool ok[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = c * XK + blk * 8 + 2 * t + e;
+        ok[e] = j < nk && (km == nullptr || km[j] != 0);
+      }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float p0 = ok[0] ? __expf(s[hh][blk][r * 2] * scale - m[hh][r]) * l[hh][r] : 0.f;
+          const float p1 = ok[1] ? __expf(s[hh][blk][r * 2 + 1] * scale - m[hh][r]) * l[hh][r] : 0.f;
+          *reinterpret_cast<uint32_t*>(ex + ((h0 + hh) * 16 + g + 8 * r) * EXP + blk * 8 + 2 * t) = pack_bf16x2(p0, p1);
+        }
+    }
+    bar_sync_named(1 + qt, 128);  // the four warps of this query tile have published all 8 heads
+    // ---- talking heads: mix the 8 heads for my two output heads, straight into the A fragments of P'V ----
+    float mix[2][2][4];
+#pragma unroll
+    for (int go = 0; go < 2; ++go)
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) mix[go][blk][0] = mix[go][blk][1] = mix[go][blk][2] = mix[go][blk][3] = 0.f;
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
 #pragma unroll
       for (int blk = 0; blk < 2; ++blk)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = c * XK + n16 * 16 + blk * 8 + 2 * t + e;
-          ok[blk][e] = j < nk && (km == nullptr || km[j] != 0);
-        }
-      // ---- normalised probabilities of all 8 heads for this 16-key group ----
-      float P[8][2][4];
+        for (int r = 0; r < 2; ++r) {
+          const float2 pv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(ex + (h * 16 + g + 8 * r) * EXP + blk * 8 + 2 * t));
 #pragma unroll
-      for (int h = 0; h < 8; ++h) {
-#pragma unroll
-        for (int blk = 0; blk < 2; ++blk) P[h][blk][0] = P[h][blk][1] = P[h][blk][2] = P[h][blk][3] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint32_t qa[4], kb[4];
-          ldsm4(qa, Qs + (rbase + l8 + 8 * (id & 1)) * XP + h * XD + ks * 16 + 8 * (id >> 1));
-          ldsm4(kb, Kc + (n16 * 16 + l8 + 8 * (id >> 1)) * XP + h * XD + ks * 16 + 8 * (id & 1));
-          mma16816(P[h][0], qa, kb[0], kb[1]);
-          mma16816(P[h][1], qa, kb[2], kb[3]);
-        }
-        const float m0 = st_m[(rbase + g) * XH + h], m1 = st_m[(rbase + g + 8) * XH + h];
-        const float i0 = st_il[(rbase + g) * XH + h], i1 = st_il[(rbase + g + 8) * XH + h];
-#pragma unroll
-        for (int blk = 0; blk < 2; ++blk)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            P[h][blk][e] = ok[blk][e] ? __expf(P[h][blk][e] * scale - m0) * i0 : 0.f;
-            P[h][blk][2 + e] = ok[blk][e] ? __expf(P[h][blk][2 + e] * scale - m1) * i1 : 0.f;
+          for (int go = 0; go < 2; ++go) {
+            mix[go][blk][r * 2] = fmaf(wmix[go][h], pv.x, mix[go][blk][r * 2]);
+            mix[go][blk][r * 2 + 1] = fmaf(wmix[go][h], pv.y, mix[go][blk][r * 2 + 1]);
           }
-      }
-      // ---- talking heads in registers, packed straight into the A fragments of P'V ----
-#pragma unroll
-      for (int go = 0; go < 4; ++go) {
-        const float* wrow = Wt + (part * 4 + go) * 8;
-        float mix[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-        for (int h = 0; h < 8; ++h) {
-          const float wv = wrow[h];
-#pragma unroll
-          for (int blk = 0; blk < 2; ++blk)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) mix[blk][e] = fmaf(wv, P[h][blk][e], mix[blk][e]);
         }
-        uint32_t pa[4];
-        pa[0] = pack_bf16x2(mix[0][0], mix[0][1]);  // row g    , keys 2t, 2t+1
-        pa[1] = pack_bf16x2(mix[0][2], mix[0][3]);  // row g + 8
-        pa[2] = pack_bf16x2(mix[1][0], mix[1][1]);  // row g    , keys 8 + 2t ..
-        pa[3] = pack_bf16x2(mix[1][2], mix[1][3]);  // row g + 8
-        const int hg = part * 4 + go;
 #pragma unroll
-        for (int ntp = 0; ntp < 4; ++ntp) {
-          uint32_t vb[4];
-          ldsm4t(vb, Vc + (n16 * 16 + l8 + 8 * (id & 1)) * XP + hg * XD + ntp * 16 + 8 * (id >> 1));
-          mma16816(O[go][ntp * 2], pa, vb[0], vb[1]);
-          mma16816(O[go][ntp * 2 + 1], pa, vb[2], vb[3]);
-        }
+    for (int go = 0; go < 2; ++go) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(mix[go][0][0], mix[go][0][1]);  // row g    , keys 2t, 2t+1
+      pa[1] = pack_bf16x2(mix[go][0][2], mix[go][0][3]);  // row g + 8
+      pa[2] = pack_bf16x2(mix[go][1][0], mix[go][1][1]);  // row g    , keys 8 + 2t ..
+      pa[3] = pack_bf16x2(mix[go][1][2], mix[go][1][3]);  // row g + 8
+#pragma unroll
+      for (int ntp = 0; ntp < 4; ++ntp) {
+        uint32_t vb[4];
+        ldsm4t(vb, Vc + (l8 + 8 * (id & 1)) * XP + (h0 + go) * XD + ntp * 16 + 8 * (id >> 1));
+        mma16816(O[go][ntp * 2], pa, vb[0], vb[1]);
+        mma16816(O[go][ntp * 2 + 1], pa, vb[2], vb[3]);
       }
     }
-    __syncthreads();
   }
 
   // ---- null value (fp32), store ----
   bf16* ob = reinterpret_cast<bf16*>(p.o) + (long long)b * p.o_bs;
-  float pn[2][8];
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
-#pragma unroll
-    for (int h = 0; h < 8; ++h) {
-      const int row = rbase + g + 8 * r;
-      pn[r][h] = has_null ? __expf(st_sn[row * XH + h] - st_m[row * XH + h]) * st_il[row * XH + h] : 0.f;
-    }
-#pragma unroll
-  for (int go = 0; go < 4; ++go) {
-    const int hg = part * 4 + go;
+  for (int go = 0; go < 2; ++go) {
+    const int hg = h0 + go;
     float pm[2] = {0.f, 0.f};
+    if (has_null) {
 #pragma unroll
-    for (int h = 0; h < 8; ++h) {
-      pm[0] = fmaf(Wt[hg * 8 + h], pn[0][h], pm[0]);
-      pm[1] = fmaf(Wt[hg * 8 + h], pn[1][h], pm[1]);
+      for (int r = 0; r < 2; ++r) {
+        const int row = rbase + g + 8 * r;
+#pragma unroll
+        for (int h = 0; h < 8; ++h)
+          pm[r] = fmaf(wmix[go][h], __expf(st_sn[row * XH + h] - st_m[row * XH + h]) * st_il[row * XH + h], pm[r]);
+      }
     }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -325,7 +334,7 @@ int attn_dense_x64(const AttnParams& p, int nk, cudaStream_t stream) {
     return NUWA_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(p.q) & 15) || (reinterpret_cast<uintptr_t>(p.k) & 15) || (reinterpret_cast<uintptr_t>(p.v) & 15))
     return NUWA_ERR_INVALID;
-  const size_t smem = (size_t)(XQ + 4 * XK) * XP * 2 + (64 + 2 * XC + 3 * XQ * XH) * sizeof(float);
+  const size_t smem = (size_t)(XQ + 2 * XS * XK) * XP * 2 + (size_t)2 * 4 * XH * 16 * EXP * 2 + (64 + 2 * XC + 3 * XQ * XH) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(attn_dense_x64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -333,7 +342,7 @@ int attn_dense_x64(const AttnParams& p, int nk, cudaStream_t stream) {
     attr = true;
   }
   const int grid = p.B * ((p.nq + XQ - 1) / XQ);
-  attn_dense_x64_kernel<<<grid, 256, smem, stream>>>(p, nk);
+  attn_dense_x64_kernel<<<grid, XT, smem, stream>>>(p, nk);
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
 }
