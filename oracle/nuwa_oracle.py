@@ -576,11 +576,15 @@ def nuwa_embed_text(text, sd, spec):
     """NUWA.embed_text -- nuwa_pytorch.py:1821-1839 (rotary position embedding, text_rotary_pos_emb=True)."""
     mask = text != 0
     tok = frac_gradient(sd['text_embedding.embed.weight'][text])
-    inv = sd.get('text_rotary_pos_emb.inv_freq')
-    if inv is None:  # buffer of RotaryEmbedding(dim=min(32, dim_head)) -- nuwa_pytorch.py:135,1769
-        rd = min(32, spec.text_dim_head)
-        inv = 1. / (10000 ** (torch.arange(0, rd, 2).float() / rd))
-    rot = rotary_freqs(inv, text.shape[1])
+    if 'text_abs_pos_emb.embed.weight' in sd:  # text_rotary_pos_emb=False: learned absolute positions -- :1829-1831
+        tok = tok + sd['text_abs_pos_emb.embed.weight'][:text.shape[1]]
+        rot = None
+    else:
+        inv = sd.get('text_rotary_pos_emb.inv_freq')
+        if inv is None:  # buffer of RotaryEmbedding(dim=min(32, dim_head)) -- nuwa_pytorch.py:135,1769
+            rd = min(32, spec.text_dim_head)
+            inv = 1. / (10000 ** (torch.arange(0, rd, 2).float() / rd))
+        rot = rotary_freqs(inv, text.shape[1])
     emb = transformer(tok, _sub(sd, 'text_transformer'), spec.text, mask=mask, rotary=rot)
     return emb, mask
 

@@ -144,3 +144,48 @@ def test_nuwa_sketch_loss_backward_matches_reference_gradients(cuda_device):
     print(f"  sketch_small: {len(gold['grads'])} gradient tensors, worst rel {worst[0]:.3e} ({worst[1]}), all-params rel {total:.3e}")
     assert not bad, bad
     assert total < GRAD_TOL_ALL
+
+
+def _compare_grads(model, gold_grads, label):
+    params = dict(model.named_parameters())
+    worst, num, den, bad = (0., None), 0., 0., []
+    for k, gref in gold_grads.items():
+        p = params[k]
+        assert p.grad is not None, k
+        r = rel(p.grad, gref)
+        worst = max(worst, (r, k))
+        num += (p.grad.double().cpu() - gref.double()).pow(2).sum().item()
+        den += gref.double().pow(2).sum().item()
+        if r > (GRAD_TOL_TINY if gref.numel() <= 64 else GRAD_TOL):
+            bad.append((k, r))
+    total = (num / den) ** 0.5
+    print(f"  {label}: {len(gold_grads)} gradient tensors, worst rel {worst[0]:.3e} ({worst[1]}), all-params rel {total:.3e}")
+    assert not bad, bad
+    assert total < GRAD_TOL_ALL
+
+
+def test_training_variants_match_reference_gradients(cuda_device):
+    """Code paths the main fixtures do not reach: learned absolute text positions + 4 heads x 16 (NUWA), and a dense
+    (non-3DNA) sketch encoder + reversible decoder with SparseCross2DNA + a masked sketch frame (NUWASketch)."""
+    from nuwa_pytorch_b200 import NUWA, NUWASketch, VQGanVAE, train
+    from oracle.synth import synth_state_dict
+    var = golden("train_variants.pt")
+    a = var['nuwa_abs_pos']
+    model = NUWA(vae=VQGanVAE(**a['vae_kwargs']), **a['kwargs'])
+    _, unexpected = model.load_state_dict(synth_state_dict(a['manifest'], a['seed']), strict=False)
+    assert not unexpected
+    model = model.to(cuda_device).train()
+    loss = model(text=a['text'].to(cuda_device), video=a['video_indices'].to(cuda_device), return_loss=True, cond_dropout_prob=0.)
+    assert abs(loss.item() - a['loss'].item()) < 2e-2
+    loss.backward()
+    _compare_grads(model, a['grads'], 'nuwa_abs_pos')
+    b = var['sketch_dense_rev']
+    sk = NUWASketch(vae=VQGanVAE(**b['vae_kwargs']), sketch_vae=VQGanVAE(**b['sketch_vae_kwargs']), **b['kwargs'])
+    _, unexpected = sk.load_state_dict(synth_state_dict(b['manifest'], b['seed']), strict=False)
+    assert not unexpected
+    sk = sk.to(cuda_device).train()
+    tok_mask = b['sketch_mask'][:, :, None].expand(2, 2, 16).reshape(2, -1).to(torch.uint8).contiguous().to(cuda_device)
+    loss = train.sketch_training_loss(sk, b['sketch_indices'].to(cuda_device), tok_mask, b['frame_indices'].to(cuda_device))
+    assert abs(loss.item() - b['loss'].item()) < 2e-2
+    loss.backward()
+    _compare_grads(sk, b['grads'], 'sketch_dense_rev')
