@@ -182,6 +182,69 @@ int nuwa_sample_topk_gumbel_at(const float* cond, const float* uncond, const flo
 int nuwa_cache_append(const void* row, void* cache, long long cache_bs, int width, int B, const int* t_ptr, void* stream);
 int nuwa_step_increment(int* t_ptr, void* stream);
 
+/* ---- persistent decode step (generate()) -------------------------------------------------------
+ * ONE cooperative kernel launch runs a whole Transformer / ReversibleTransformer stack for the single new position
+ * *t_ptr of every sample (nuwa_pytorch.py:1168-1182, :1289-1295 and reversible.py:61-68,132-142 restricted to one
+ * token, over SandwichNorm :112-128, ShiftVideoTokens :200-253, Sparse3DNA :459-613, Attention :315-379, FeedForward
+ * :255-286, StableLayerNorm :88-95; optionally to_logits :1819).  It replaces the ~15 launches per layer of the
+ * per-kernel decode path; see csrc/decode_stack.cu.  All pointers are device pointers; `subs` is a DEVICE array. */
+#define NUWA_DEC_3DNA 0
+#define NUWA_DEC_CROSS 1
+#define NUWA_DEC_FF 2
+typedef struct {
+  int kind;           /* NUWA_DEC_* */
+  int shift;          /* ShiftVideoTokens (space) wraps the block */
+  int read, write;    /* residual stream read / updated: 0,0 (plain) or f: 1,0 / g: 0,1 (reversible.py:65-68) */
+  const float* pre_w; /* SandwichNorm prenorm / postnorm affine parameters, fp32 [D] */
+  const float* pre_b;
+  const float* post_w;
+  const float* post_b;
+  const void* w_a;    /* bf16: 3DNA to_q|to_kv [3*inner][D]; cross to_q [inner][D]; FF net.0 pair packed [2*ip][D] */
+  const void* w_b;    /* bf16: to_out [D][inner]; FF net.3 [D][ip] (zero padded K) */
+  const float* b_out; /* Sparse3DNA to_out bias [D] or NULL */
+  const float* talk;  /* talking-heads matrix fp32 [H][H] (attention kinds) */
+  const float* null_k;/* cross attention learned null key / value, fp32 [H*dh] */
+  const float* null_v;
+  void* cache;        /* 3DNA: bf16 q|k|v cache [B][npos][3*inner] (row t is WRITTEN); cross: bf16 k|v of the context
+                         [B][nk][2*inner] */
+  void* shift_cache;  /* bf16 [B][npos][D]: pre-norm rows of earlier positions (row t is written) or NULL */
+  int ip;             /* FF: padded inner width */
+  int reserved;
+} nuwa_decode_sub;
+typedef struct {
+  const nuwa_decode_sub* subs;
+  int nsubs;
+  int B, D, H, dh, npos, reversible;
+  int fmap, max_frames, kt, kh, kw, dt, dh_, dw, causal; /* Sparse3DNA geometry shared by all 3DNA sub-blocks */
+  int nk;                        /* context tokens of the cross attention (0 if none) */
+  const unsigned char* key_mask; /* [B][mask_bs], 1 = attend (context_mask), or NULL */
+  int mask_bs;
+  const int* t_ptr;              /* position of the new token (device scalar) */
+  const float* x_in;             /* [B][D] fp32: embedded token (or the previous sweep's output) */
+  const float* norm_w;           /* final StableLayerNorm */
+  const float* norm_b;
+  float* out_f32;                /* [B][D] normalised output, fp32 and / or bf16 (either may be NULL) */
+  void* out_bf16;
+  const void* w_logits;          /* bf16 [V][D] or NULL */
+  int V;
+  float* logits;                 /* [B][V] fp32 */
+  /* scratch, all owned by the caller */
+  float* y;                      /* [B][D] fp32 */
+  void* act;                     /* bf16 [B][kmax] */
+  void* actq;                    /* bf16 [B][H*dh] */
+  float* scores;                 /* fp32 [B][H][nk+1] (cross attention) */
+  unsigned int* barrier;         /* 2 words, zero before the FIRST launch; the kernel leaves them zero */
+  int kmax;                      /* max(D, H*dh, every ip) */
+  int jmax;                      /* set by the library */
+  int split_small, split_ff;     /* K slices per output column of the D x inner / D x ip products: 1, 2 or 4 (0 = default) */
+  int max_ctas;                  /* 0 = one CTA per SM */
+} nuwa_decode_params;
+/* cooperative = 1: cudaLaunchCooperativeKernel (co-residency guaranteed by the driver); 0: plain launch with
+ * grid <= SM count.  Returns NUWA_ERR_INVALID for shapes outside the kernel's envelope (B > 16, D > 1024, ...). */
+int nuwa_decode_stack(const nuwa_decode_params* p, int cooperative, void* stream);
+/* sizeof(nuwa_decode_sub), sizeof(nuwa_decode_params) */
+void nuwa_struct_sizes_decode(int* out2);
+
 /* ---- VQGanVAE support kernels ---------------------------------------------------------------- */
 int nuwa_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, void* stream);
 int nuwa_nhwc_to_nchw_f32(const void* in, int in_is_bf16, float* out, int B, int C, int H, int W, void* stream);

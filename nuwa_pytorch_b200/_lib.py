@@ -67,6 +67,27 @@ class AttnRowsParams(ctypes.Structure):  # mirrors nuwa_attn_rows_params
                 ("out_scale", c_float), ("key_mask", c_void_p), ("mask_bs", c_int), ("has_null", c_int)]
 
 
+class DecodeSub(ctypes.Structure):  # mirrors nuwa_decode_sub
+    _fields_ = [("kind", c_int), ("shift", c_int), ("read", c_int), ("write", c_int),
+                ("pre_w", c_void_p), ("pre_b", c_void_p), ("post_w", c_void_p), ("post_b", c_void_p),
+                ("w_a", c_void_p), ("w_b", c_void_p), ("b_out", c_void_p), ("talk", c_void_p),
+                ("null_k", c_void_p), ("null_v", c_void_p), ("cache", c_void_p), ("shift_cache", c_void_p),
+                ("ip", c_int), ("reserved", c_int)]
+
+
+class DecodeParams(ctypes.Structure):  # mirrors nuwa_decode_params
+    _fields_ = [("subs", c_void_p), ("nsubs", c_int),
+                ("B", c_int), ("D", c_int), ("H", c_int), ("dh", c_int), ("npos", c_int), ("reversible", c_int),
+                ("fmap", c_int), ("max_frames", c_int), ("kt", c_int), ("kh", c_int), ("kw", c_int),
+                ("dt", c_int), ("dh_", c_int), ("dw", c_int), ("causal", c_int),
+                ("nk", c_int), ("key_mask", c_void_p), ("mask_bs", c_int),
+                ("t_ptr", c_void_p), ("x_in", c_void_p), ("norm_w", c_void_p), ("norm_b", c_void_p),
+                ("out_f32", c_void_p), ("out_bf16", c_void_p), ("w_logits", c_void_p), ("V", c_int),
+                ("logits", c_void_p), ("y", c_void_p), ("act", c_void_p), ("actq", c_void_p), ("scores", c_void_p),
+                ("barrier", c_void_p), ("kmax", c_int), ("jmax", c_int), ("split_small", c_int), ("split_ff", c_int),
+                ("max_ctas", c_int)]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES).  Must list EVERY symbol of include/nuwa_b200.h.
 SIGNATURES = {
     "nuwa_abi_version": [],
@@ -93,6 +114,8 @@ SIGNATURES = {
                                    c_float, c_void_p],
     "nuwa_cache_append": [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
     "nuwa_step_increment": [c_void_p, c_void_p],
+    "nuwa_decode_stack": [P(DecodeParams), c_int, c_void_p],
+    "nuwa_struct_sizes_decode": [P(c_int)],
     "nuwa_nchw_f32_to_nhwc_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "nuwa_nhwc_to_nchw_f32": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "nuwa_im2col_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
@@ -136,7 +159,7 @@ SIGNATURES = {
     "nuwa_struct_sizes_bwd": [P(c_int)],
 }
 _RESTYPES = {"nuwa_strerror": ctypes.c_char_p, "nuwa_launch_count": ctypes.c_ulonglong, "nuwa_struct_sizes": None,
-             "nuwa_gemm_prof_enable": None, "nuwa_struct_sizes_bwd": None}
+             "nuwa_gemm_prof_enable": None, "nuwa_struct_sizes_bwd": None, "nuwa_struct_sizes_decode": None}
 
 _lib = None
 
@@ -168,6 +191,11 @@ def lib():
         mine = tuple(ctypes.sizeof(c) for c in (BgemmParams, LnBwdParams, EmbedBwdParams, AttnRowsParams))
         if tuple(sizes) != mine:
             raise NuwaB200Error(f"backward struct layout mismatch: include/nuwa_b200.h {tuple(sizes)} vs _lib.py {mine}")
+        sizes = (c_int * 2)()
+        handle.nuwa_struct_sizes_decode(sizes)
+        mine = (ctypes.sizeof(DecodeSub), ctypes.sizeof(DecodeParams))
+        if tuple(sizes) != mine:
+            raise NuwaB200Error(f"decode struct layout mismatch: include/nuwa_b200.h {tuple(sizes)} vs _lib.py {mine}")
         _lib = handle
     return _lib
 

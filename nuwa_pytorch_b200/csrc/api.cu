@@ -87,6 +87,13 @@ int nuwa_cache_append(const void* row, void* cache, long long cache_bs, int widt
   return cache_append(row, cache, cache_bs, width, B, t_ptr, S(stream));
 }
 int nuwa_step_increment(int* t_ptr, void* stream) { return step_increment(t_ptr, S(stream)); }
+int nuwa_decode_stack(const nuwa_decode_params* p, int cooperative, void* stream) {
+  return p ? decode_stack(*p, cooperative, S(stream)) : NUWA_ERR_INVALID;
+}
+void nuwa_struct_sizes_decode(int* out2) {
+  out2[0] = (int)sizeof(nuwa_decode_sub);
+  out2[1] = (int)sizeof(nuwa_decode_params);
+}
 int nuwa_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, void* stream) {
   return nchw_f32_to_nhwc_bf16(in, out, B, C, H, W, S(stream));
 }

@@ -78,6 +78,8 @@ int sample_topk_gumbel_at(const float* cond, const float* uncond, const float* n
                           cudaStream_t stream);
 int cache_append(const void* row, void* cache, long long cache_bs, int width, int B, const int* t_ptr, cudaStream_t stream);
 int step_increment(int* t_ptr, cudaStream_t stream);
+// decode_stack.cu
+int decode_stack(const nuwa_decode_params& p, int cooperative, cudaStream_t stream);
 // vae_ops.cu
 int nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, cudaStream_t stream);
 int nhwc_to_nchw_f32(const void* in, int in_is_bf16, float* out, int B, int C, int H, int W, cudaStream_t stream);

@@ -10,9 +10,12 @@ Data layout (B200-first):
     step touches only the new token's rows.
 Two execution modes: full (all n positions, teacher forced) and decode (one position, with DecodeState).
 """
+import ctypes
+import os
+
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 def _f32(t):
@@ -274,3 +277,113 @@ def run_stack(stack, x, *, context=None, key_mask=None, rotary=None, state=None,
     o32, o16 = ops.stable_ln(streams[0], pack.norm_w, pack.norm_b, b2=b2, want_f32=True, want_bf16=want_bf16)
     o32 = o32.view(B, nt, D)
     return (o32, o16.view(B, nt, D)) if want_bf16 else o32
+
+
+# ------------------------------------------------------------------------------------------------
+# persistent decode step: the whole stack of one token step in ONE cooperative kernel (csrc/decode_stack.cu)
+# ------------------------------------------------------------------------------------------------
+_DEC_KIND = {'3dna': 0, 'cross': 1, 'ff': 2}
+
+
+class FusedDecode:
+    """Descriptor table + scratch for `nuwa_decode_stack` over one DecodeState.  `supported()` tells whether the stack
+    fits the kernel's envelope (Sparse3DNA / dense cross-attention / FeedForward sub-blocks with one geometry,
+    B <= 16, D <= 1024); other stacks (NUWASketch's sparse 2-D cross attention) keep the per-kernel decode path."""
+
+    @staticmethod
+    def supported(pack, B, context):
+        if os.environ.get('NUWA_DECODE_FUSED', '1') == '0' or B > 16 or pack.dim % 16 or pack.dim > 1024:
+            return False
+        geo, heads = set(), set()
+        for s in pack.subs:
+            if s.kind not in _DEC_KIND:
+                return False
+            if s.kind == '3dna':
+                geo.add((s.fmap, s.max_frames, tuple(s.kernel), tuple(s.dilation), bool(s.causal)))
+                if s.b_out is None:
+                    return False
+            if s.kind == 'ff' and s.shift and s.fmap is None:
+                return False
+            if s.kind != 'ff':
+                heads.add((s.H, s.dh))
+            if s.kind == 'cross' and context is None:
+                return False
+        if len(geo) != 1 or len(heads) != 1:
+            return False
+        H, dh = next(iter(heads))
+        return H <= 16 and dh % 8 == 0 and H * dh <= 1024
+
+    def __init__(self, pack, state, context, w_logits=None):
+        dev = state.t_dev.device
+        B, npos, D = state.B, state.npos, pack.dim
+        self.pack, self.state, self.context = pack, state, context
+        subs = (_lib.DecodeSub * len(pack.subs))()
+        kmax, H, dh = D, None, None
+        shift_fmap = None
+        for i, s in enumerate(pack.subs):
+            d = subs[i]
+            d.kind, d.shift, d.read, d.write = _DEC_KIND[s.kind], int(bool(s.shift)), s.read, s.write
+            d.pre_w, d.pre_b, d.post_w, d.post_b = (t.data_ptr() for t in (*s.pre, *s.post))
+            if s.shift:
+                d.shift_cache = state.a[i].data_ptr()
+                shift_fmap = s.fmap
+            if s.kind == '3dna':
+                H, dh = s.H, s.dh
+                d.w_a, d.w_b, d.b_out, d.talk = s.w_qkv.data_ptr(), s.w_out.data_ptr(), s.b_out.data_ptr(), s.talk.data_ptr()
+                d.cache = state.qkv[i].data_ptr()
+                geom = s
+            elif s.kind == 'cross':
+                H, dh = s.H, s.dh
+                d.w_a, d.w_b, d.talk = s.w_q.data_ptr(), s.w_out.data_ptr(), s.talk.data_ptr()
+                d.null_k, d.null_v = s.null_k.data_ptr(), s.null_v.data_ptr()
+                d.cache = context.kv[i].data_ptr()
+            else:
+                d.w_a, d.w_b, d.ip = s.w1.data_ptr(), s.w2.data_ptr(), s.w1.shape[0] // 2
+                kmax = max(kmax, d.ip)
+        inner = H * dh
+        kmax = max(kmax, inner)
+        raw = bytes(subs)
+        self.subs_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        nk = context.ctx16.shape[1] if context is not None else 0
+        self.out_f32 = torch.empty(B, 1, D, dtype=torch.float32, device=dev)
+        self.out_bf16 = torch.empty(B, 1, D, dtype=torch.bfloat16, device=dev)
+        self.y = torch.empty(B, D, dtype=torch.float32, device=dev)
+        self.act = torch.empty(B, kmax, dtype=torch.bfloat16, device=dev)
+        self.actq = torch.empty(B, inner, dtype=torch.bfloat16, device=dev)
+        self.scores = torch.empty(B, H, nk + 1, dtype=torch.float32, device=dev)
+        self.barrier = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.w_logits = w_logits
+        self.logits = torch.empty(B, w_logits.shape[0], dtype=torch.float32, device=dev) if w_logits is not None else None
+        p = _lib.DecodeParams()
+        p.subs, p.nsubs = self.subs_dev.data_ptr(), len(pack.subs)
+        p.B, p.D, p.H, p.dh, p.npos, p.reversible = B, D, H, dh, npos, int(pack.reversible)
+        p.fmap, p.max_frames = geom.fmap, geom.max_frames
+        p.kt, p.kh, p.kw = geom.kernel
+        p.dt, p.dh_, p.dw = geom.dilation
+        p.causal = int(bool(geom.causal))
+        assert shift_fmap is None or shift_fmap == geom.fmap
+        p.nk = nk
+        if context is not None and context.mask is not None:
+            p.key_mask, p.mask_bs = context.mask.data_ptr(), context.mask.shape[1]
+        p.t_ptr = state.t_dev.data_ptr()
+        p.norm_w, p.norm_b = pack.norm_w.data_ptr(), pack.norm_b.data_ptr()
+        p.out_f32, p.out_bf16 = self.out_f32.data_ptr(), self.out_bf16.data_ptr()
+        if w_logits is not None:
+            p.w_logits, p.V, p.logits = w_logits.data_ptr(), w_logits.shape[0], self.logits.data_ptr()
+        p.y, p.act, p.actq, p.scores = self.y.data_ptr(), self.act.data_ptr(), self.actq.data_ptr(), self.scores.data_ptr()
+        p.barrier = self.barrier.data_ptr()
+        p.kmax = kmax
+        p.split_small = int(os.environ.get('NUWA_DECODE_SPLIT_SMALL', '0'))
+        p.split_ff = int(os.environ.get('NUWA_DECODE_SPLIT_FF', '0'))
+        p.max_ctas = int(os.environ.get('NUWA_DECODE_MAX_CTAS', '0'))
+        self.params = p
+        self.cooperative = int(os.environ.get('NUWA_DECODE_COOP', '1'))
+
+    def run(self, x):
+        """x: fp32 (B, 1, D) contiguous.  Returns (normalised output fp32 (B,1,D), logits (B,V) or None); both are
+        persistent buffers of this plan, overwritten by the next call."""
+        assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() == self.state.B * self.pack.dim
+        self.params.x_in = x.data_ptr()
+        _lib.check(_lib.lib().nuwa_decode_stack(ctypes.byref(self.params), self.cooperative, _lib.stream()),
+                   "nuwa_decode_stack")
+        return self.out_f32, self.logits

@@ -343,7 +343,7 @@ class _VideoDecoderMixin:
 
     @torch.no_grad()
     def _generate_indices(self, context, batch, *, num_frames, filter_thres, temperature, cond_scale, noise=None,
-                          return_step_logits=False, use_graph=True):
+                          return_step_logits=False, use_graph=True, use_fused=True):
         """Autoregressive loop (:1858-1908 / :2455-2505), one token per step, KV-cached.
 
         Incremental mode keeps the position in a device scalar, so ONE decode step (both guidance sweeps, sampling,
@@ -367,18 +367,30 @@ class _VideoDecoderMixin:
             noise_all = noise if noise is not None else torch.rand(total, batch, V, device=dev)
             noise_all = noise_all.contiguous()
 
+            fused = use_fused and engine.FusedDecode.supported(pack, batch, context)
+            if fused:
+                # whole stack + to_logits of one token step in ONE persistent kernel per sweep (csrc/decode_stack.cu)
+                plan_c = engine.FusedDecode(pack, st_c, context, w_log)
+                plan_u = engine.FusedDecode(pack, st_u, uncond_ctx, w_log) if cond_scale != 1 else None
+
             def step(ind):
                 x = self._embed_video(video_indices, 1, t0=ind, t_dev=t_dev)
-                y32, y16 = engine.run_stack(self.video_transformer, x, context=context, state=st_c, t0=ind, want_bf16=True)
-                logits = ops.gemm(y16.view(batch, -1), w_log, out_dtype=torch.float32)
                 ulogits = None
-                if cond_scale != 1:
-                    # the reference feeds the conditional sweep's OUTPUT to the second sweep
-                    _, u16 = engine.run_stack(self.video_transformer, y32, context=uncond_ctx, state=st_u, t0=ind,
-                                              want_bf16=True)
-                    ulogits = ops.gemm(u16.view(batch, -1), w_log, out_dtype=torch.float32)
+                if fused:
+                    y32, logits = plan_c.run(x)
+                    if cond_scale != 1:
+                        _, ulogits = plan_u.run(y32)  # second sweep consumes the first sweep's OUTPUT
+                else:
+                    y32, y16 = engine.run_stack(self.video_transformer, x, context=context, state=st_c, t0=ind,
+                                                want_bf16=True)
+                    logits = ops.gemm(y16.view(batch, -1), w_log, out_dtype=torch.float32)
+                    if cond_scale != 1:
+                        # the reference feeds the conditional sweep's OUTPUT to the second sweep
+                        _, u16 = engine.run_stack(self.video_transformer, y32, context=uncond_ctx, state=st_u, t0=ind,
+                                                  want_bf16=True)
+                        ulogits = ops.gemm(u16.view(batch, -1), w_log, out_dtype=torch.float32)
                 if return_step_logits:
-                    step_logits.append(logits if ulogits is None else ulogits + (logits - ulogits) * cond_scale)
+                    step_logits.append(logits.clone() if ulogits is None else ulogits + (logits - ulogits) * cond_scale)
                 ops.sample_topk_gumbel_at(logits, ulogits, noise_all, video_indices, t_dev, k, cond_scale, temperature)
                 ops.step_increment(t_dev)
 
@@ -517,12 +529,13 @@ class NUWA(nn.Module, _VideoDecoderMixin):
     @torch.no_grad()
     @_eval_decorator
     def generate(self, *, text, filter_thres=0.9, temperature=1., decode_max_batchsize=10, cond_scale=2., num_frames=None,
-                 _noise=None, _return_indices=False, _use_graph=True):
+                 _noise=None, _return_indices=False, _use_graph=True, _use_fused=True):
         batch = text.shape[0]
         context = self._text_context(text, text != 0)
         num_frames = num_frames if _exists(num_frames) else self.max_video_frames
         idx = self._generate_indices(context, batch, num_frames=num_frames, filter_thres=filter_thres,
-                                     temperature=temperature, cond_scale=cond_scale, noise=_noise, use_graph=_use_graph)
+                                     temperature=temperature, cond_scale=cond_scale, noise=_noise, use_graph=_use_graph,
+                                     use_fused=_use_fused)
         if _return_indices:
             return idx
         return self._indices_to_video(idx, decode_max_batchsize)
