@@ -209,13 +209,16 @@ typedef struct {
                          [B][nk][2*inner] */
   void* shift_cache;  /* bf16 [B][npos][D]: pre-norm rows of earlier positions (row t is written) or NULL */
   int ip;             /* FF: padded inner width */
+  int kt, kh, kw;     /* Sparse3DNA window (nuwa_pytorch.py:407-422); kernel and dilation are per-layer settings */
+  int dt, dh_, dw;    /* (sparse_3dna_kernel_size / sparse_3dna_dilation are cast to one value per layer, :1097-1100) */
   int reserved;
 } nuwa_decode_sub;
 typedef struct {
   const nuwa_decode_sub* subs;
   int nsubs;
   int B, D, H, dh, npos, reversible;
-  int fmap, max_frames, kt, kh, kw, dt, dh_, dw, causal; /* Sparse3DNA geometry shared by all 3DNA sub-blocks */
+  int fmap, max_frames, causal; /* Sparse3DNA token grid shared by all 3DNA sub-blocks */
+  int j3max;                    /* max over the 3DNA sub-blocks of 1 + kt*kh*kw */
   int nk;                        /* context tokens of the cross attention (0 if none) */
   const unsigned char* key_mask; /* [B][mask_bs], 1 = attend (context_mask), or NULL */
   int mask_bs;
@@ -238,6 +241,12 @@ typedef struct {
   int jmax;                      /* set by the library */
   int split_small, split_ff;     /* K slices per output column of the D x inner / D x ip products: 1, 2 or 4 (0 = default) */
   int max_ctas;                  /* 0 = one CTA per SM */
+  /* measurement aids (tools/decode_phase_profile.py): prof != NULL makes CTA prof_cta record (tag, clock64) pairs at
+   * every phase boundary (room for 2 * (12 * nsubs + 8) values); debug_flags bit 0/1/2 skip the norms / skinny
+   * products / attention (timing experiments only: the result is then meaningless) */
+  long long* prof;
+  int prof_cta;
+  int debug_flags;
 } nuwa_decode_params;
 /* cooperative = 1: cudaLaunchCooperativeKernel (co-residency guaranteed by the driver); 0: plain launch with
  * grid <= SM count.  Returns NUWA_ERR_INVALID for shapes outside the kernel's envelope (B > 16, D > 1024, ...). */
@@ -409,6 +418,35 @@ int nuwa_attn_bwd_first_key(const void* q, long long q_bs, int q_rs, const void*
                             float* out_v, long long ok_bs, void* stream);
 int nuwa_attn3dna_bwd_first_key_finalize(const float* tmp_k, const float* tmp_v, const void* dO_bos, long long do_bs,
                                          void* dqkv, long long dqkv_bs, int inner, int B, void* stream);
+/* ---- trainer step: clip_grad_norm_ + AdamW + zero_grad over flat fp32 buffers ---------------------------------
+ * Replaces train_nuwa.py:256-258 (torch.nn.utils.clip_grad_norm_; optim.step(); optim.zero_grad()) with the optimizer of
+ * optimizer.py:11-31 (AdamW, no weight decay on parameters with ndim < 2).  See csrc/optim.cu. */
+/* out[0] (+)= sum x[i]^2, deterministic two-stage reduction; partials: nparts floats of scratch (grid = nparts CTAs) */
+int nuwa_sqnorm_f32(const float* x, long long n, float* partials, int nparts, float* out, int accumulate, void* stream);
+typedef struct {
+  long long offset;   /* first element of the chunk in the flat buffers (multiple of 4) */
+  int len;            /* elements; a chunk never crosses a parameter boundary */
+  int weight_decay;   /* 1: decoupled weight decay applies (parameter ndim >= 2) */
+} nuwa_opt_chunk;
+typedef struct {
+  float* p;           /* parameters   (flat fp32, layout of train.GradStore) */
+  float* g;           /* gradients    (same layout; zeroed afterwards when zero_grad = 1) */
+  float* m;           /* exp_avg */
+  float* v;           /* exp_avg_sq */
+  const nuwa_opt_chunk* chunks; /* DEVICE array, one CTA per chunk */
+  int nchunks;
+  float lr, beta1, beta2, eps, weight_decay;
+  float max_norm;      /* clip_grad_norm_ threshold; <= 0 or sqnorm == NULL: no clipping */
+  float grad_scale;    /* gradients are multiplied by this first (1 / grad_accum_every) */
+  const float* sqnorm; /* device scalar: sum of squares of the UNscaled gradient buffer (nuwa_sqnorm_f32) */
+  int step;            /* 1-based optimizer step, used when step_ptr == NULL */
+  const int* step_ptr; /* device-side step counter (CUDA-graph replay) or NULL */
+  int zero_grad;
+} nuwa_adamw_params;
+int nuwa_adamw_step(const nuwa_adamw_params* a, void* stream);
+/* sizeof(nuwa_opt_chunk), sizeof(nuwa_adamw_params) */
+void nuwa_struct_sizes_optim(int* out2);
+
 /* sizeof of the five backward parameter structs (bgemm, lnbwd, embed_bwd, attn_rows, -) for binding checks */
 void nuwa_struct_sizes_bwd(int* out4);
 

@@ -72,20 +72,31 @@ class DecodeSub(ctypes.Structure):  # mirrors nuwa_decode_sub
                 ("pre_w", c_void_p), ("pre_b", c_void_p), ("post_w", c_void_p), ("post_b", c_void_p),
                 ("w_a", c_void_p), ("w_b", c_void_p), ("b_out", c_void_p), ("talk", c_void_p),
                 ("null_k", c_void_p), ("null_v", c_void_p), ("cache", c_void_p), ("shift_cache", c_void_p),
-                ("ip", c_int), ("reserved", c_int)]
+                ("ip", c_int), ("kt", c_int), ("kh", c_int), ("kw", c_int), ("dt", c_int), ("dh_", c_int), ("dw", c_int),
+                ("reserved", c_int)]
 
 
 class DecodeParams(ctypes.Structure):  # mirrors nuwa_decode_params
     _fields_ = [("subs", c_void_p), ("nsubs", c_int),
                 ("B", c_int), ("D", c_int), ("H", c_int), ("dh", c_int), ("npos", c_int), ("reversible", c_int),
-                ("fmap", c_int), ("max_frames", c_int), ("kt", c_int), ("kh", c_int), ("kw", c_int),
-                ("dt", c_int), ("dh_", c_int), ("dw", c_int), ("causal", c_int),
+                ("fmap", c_int), ("max_frames", c_int), ("causal", c_int), ("j3max", c_int),
                 ("nk", c_int), ("key_mask", c_void_p), ("mask_bs", c_int),
                 ("t_ptr", c_void_p), ("x_in", c_void_p), ("norm_w", c_void_p), ("norm_b", c_void_p),
                 ("out_f32", c_void_p), ("out_bf16", c_void_p), ("w_logits", c_void_p), ("V", c_int),
                 ("logits", c_void_p), ("y", c_void_p), ("act", c_void_p), ("actq", c_void_p), ("scores", c_void_p),
                 ("barrier", c_void_p), ("kmax", c_int), ("jmax", c_int), ("split_small", c_int), ("split_ff", c_int),
-                ("max_ctas", c_int)]
+                ("max_ctas", c_int), ("prof", c_void_p), ("prof_cta", c_int), ("debug_flags", c_int)]
+
+
+class OptChunk(ctypes.Structure):  # mirrors nuwa_opt_chunk
+    _fields_ = [("offset", c_ll), ("len", c_int), ("weight_decay", c_int)]
+
+
+class AdamWParams(ctypes.Structure):  # mirrors nuwa_adamw_params
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("chunks", c_void_p),
+                ("nchunks", c_int), ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
+                ("weight_decay", c_float), ("max_norm", c_float), ("grad_scale", c_float), ("sqnorm", c_void_p),
+                ("step", c_int), ("step_ptr", c_void_p), ("zero_grad", c_int)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES).  Must list EVERY symbol of include/nuwa_b200.h.
@@ -116,6 +127,9 @@ SIGNATURES = {
     "nuwa_step_increment": [c_void_p, c_void_p],
     "nuwa_decode_stack": [P(DecodeParams), c_int, c_void_p],
     "nuwa_struct_sizes_decode": [P(c_int)],
+    "nuwa_sqnorm_f32": [c_void_p, c_ll, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "nuwa_adamw_step": [P(AdamWParams), c_void_p],
+    "nuwa_struct_sizes_optim": [P(c_int)],
     "nuwa_nchw_f32_to_nhwc_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "nuwa_nhwc_to_nchw_f32": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "nuwa_im2col_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
@@ -159,9 +173,12 @@ SIGNATURES = {
     "nuwa_struct_sizes_bwd": [P(c_int)],
 }
 _RESTYPES = {"nuwa_strerror": ctypes.c_char_p, "nuwa_launch_count": ctypes.c_ulonglong, "nuwa_struct_sizes": None,
-             "nuwa_gemm_prof_enable": None, "nuwa_struct_sizes_bwd": None, "nuwa_struct_sizes_decode": None}
+             "nuwa_gemm_prof_enable": None, "nuwa_struct_sizes_bwd": None, "nuwa_struct_sizes_decode": None, "nuwa_struct_sizes_optim": None}
 
 _lib = None
+# bumped by code that rewrites parameter storage behind autograd's back (optim.FusedAdamW): part of every packed-weight
+# cache key next to (data_ptr, _version)
+WEIGHTS_EPOCH = [0]
 
 
 class NuwaB200Error(RuntimeError):
@@ -196,6 +213,10 @@ def lib():
         mine = (ctypes.sizeof(DecodeSub), ctypes.sizeof(DecodeParams))
         if tuple(sizes) != mine:
             raise NuwaB200Error(f"decode struct layout mismatch: include/nuwa_b200.h {tuple(sizes)} vs _lib.py {mine}")
+        handle.nuwa_struct_sizes_optim(sizes)
+        mine = (ctypes.sizeof(OptChunk), ctypes.sizeof(AdamWParams))
+        if tuple(sizes) != mine:
+            raise NuwaB200Error(f"optimizer struct layout mismatch: include/nuwa_b200.h {tuple(sizes)} vs _lib.py {mine}")
         _lib = handle
     return _lib
 

@@ -90,6 +90,14 @@ int nuwa_step_increment(int* t_ptr, void* stream) { return step_increment(t_ptr,
 int nuwa_decode_stack(const nuwa_decode_params* p, int cooperative, void* stream) {
   return p ? decode_stack(*p, cooperative, S(stream)) : NUWA_ERR_INVALID;
 }
+int nuwa_sqnorm_f32(const float* x, long long n, float* partials, int nparts, float* out, int accumulate, void* stream) {
+  return sqnorm_f32(x, n, partials, nparts, out, accumulate, S(stream));
+}
+int nuwa_adamw_step(const nuwa_adamw_params* a, void* stream) { return a ? adamw_step(*a, S(stream)) : NUWA_ERR_INVALID; }
+void nuwa_struct_sizes_optim(int* out2) {
+  out2[0] = (int)sizeof(nuwa_opt_chunk);
+  out2[1] = (int)sizeof(nuwa_adamw_params);
+}
 void nuwa_struct_sizes_decode(int* out2) {
   out2[0] = (int)sizeof(nuwa_decode_sub);
   out2[1] = (int)sizeof(nuwa_decode_params);

@@ -44,7 +44,7 @@ enum { DK_NORMAL = 0, DK_MASKED = 1, DK_ZERO = 2, DK_NULL = 3 };
 // shared-memory layout (same arithmetic on host and device)
 // ------------------------------------------------------------------------------------------------
 struct DsLayout {
-  int streams, act, red, S, pm, keys, qs, wt, part, outs, total;
+  int streams, act, red, S, pm, keys, qs, wt, part, outs, lnp, shs, desc, total;
 };
 __host__ __device__ inline int ds_align16(int x) { return (x + 15) & ~15; }
 __host__ __device__ inline DsLayout ds_layout(int B, int D, int kmax, int H, int dh, int jmax) {
@@ -60,6 +60,9 @@ __host__ __device__ inline DsLayout ds_layout(int B, int D, int kmax, int H, int
   L.wt = o;      o += ds_align16(H * H * 4);              // talking-heads matrix
   L.part = o;    o += ds_align16(DS_THREADS * 2 * 4);     // PV partial sums
   L.outs = o;    o += ds_align16(H * dh * 4);             // attention output, fp32
+  L.lnp = o;     o += ds_align16(4 * D * 4);              // post_w, post_b, pre_w, pre_b of the coming norms (cp.async)
+  L.shs = o;     o += ds_align16(B * (D / 2) * 2);        // shifted channel halves of the ShiftVideoTokens gather
+  L.desc = o;    o += 3 * ds_align16((int)sizeof(nuwa_decode_sub));  // previous / current / next sub-block descriptor
   L.total = o;
   return L;
 }
@@ -83,8 +86,8 @@ __device__ __forceinline__ void grid_barrier(GridBar& g) {
   __syncthreads();
   if (threadIdx.x == 0) {
     g.target += g.nblocks;
-    __threadfence();
-    atomicAdd(g.count, 1u);
+    // release: everything this CTA wrote (ordered before by the CTA barrier) is visible to whoever acquires the count
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(g.count) : "memory");
     long long t0 = 0;
     unsigned spins = 0;
     while (ld_acquire_u32(g.count) < g.target) {
@@ -93,10 +96,15 @@ __device__ __forceinline__ void grid_barrier(GridBar& g) {
       // watchdog: a protocol bug becomes a launch error instead of a hung GPU (~2 s)
       if (spins > 4096u && (spins & 4095u) == 0u && (clock64() - t0) > 4000000000LL) __trap();
     }
-    __threadfence();
   }
   __syncthreads();
 }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // skinny products:  out[b][col] = sum_k As[b][k] * W[row(col)][k]      (As bf16 in shared memory)
@@ -264,31 +272,70 @@ __device__ __forceinline__ void ds_row_stats(const float4 (&v)[DS_LNV], int nv, 
   rstd = rsqrtf(q / (float)D + 1e-5f);
 }
 
+// Requested BEFORE the barrier that precedes the norms (cp.async, L2 -> shared memory, no registers held):
+// lnp[0..1] = post-norm weight / bias of `prev`, lnp[2..3] = pre-norm weight / bias of `cur` (w2 / b2 when cur is
+// NULL: the final StableLayerNorm), shs[b][0:D/2] = the two shifted channel quarters of ShiftVideoTokens, taken from
+// the pre-norm rows of positions t - fmap and t - 1 (zeros at the grid border).
+__device__ __forceinline__ void prefetch_norms(const DecParams& p, const DecSub* prev, const DecSub* cur, const float* w2,
+                                               const float* b2, int t, float* lnp, bf16* shs) {
+  const int D = p.D, D4 = D / 4;
+  for (int i = threadIdx.x; i < 4 * D4; i += DS_THREADS) {
+    const int arr = i / D4, k = i - arr * D4;
+    const float* src = arr == 0 ? (prev ? prev->post_w : nullptr)
+                     : arr == 1 ? (prev ? prev->post_b : nullptr)
+                     : arr == 2 ? (cur ? cur->pre_w : w2)
+                                : (cur ? cur->pre_b : b2);
+    if (src != nullptr) cp_async16(lnp + arr * D + k * 4, src + k * 4);
+  }
+  if (cur != nullptr && cur->shift && t >= 1) {
+    const int T = p.fmap * p.fmap;
+    const int pos = (t - 1) % T;
+    const int row = pos / p.fmap, col = pos - row * p.fmap;
+    const int src_h = row > 0 ? t - p.fmap : -1, src_w = col > 0 ? t - 1 : -1;
+    const int q4 = D / 4, qp = D / 32;  // 16-byte pieces per channel quarter (bf16)
+    const bf16* sc = reinterpret_cast<const bf16*>(cur->shift_cache);
+    for (int i = threadIdx.x; i < p.B * 2 * qp; i += DS_THREADS) {
+      const int b = i / (2 * qp), r = i - b * 2 * qp;
+      const int quarter = r / qp, k = r - quarter * qp;
+      const int src = quarter == 0 ? src_h : src_w;
+      bf16* dst = shs + b * (D / 2) + quarter * q4 + k * 8;
+      if (src >= 0) cp_async16(dst, sc + ((long long)b * p.npos + src) * D + quarter * q4 + k * 8);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  cp_async_commit();
+}
+
 // prev != NULL:  streams[prev->write] += LayerNorm_post(y)        (SandwichNorm tail + residual)
 // cur  != NULL:  As = bf16(LayerNorm_pre(streams[cur->read])) with the ShiftVideoTokens gather
+// Needs prefetch_norms(prev, cur) to have been issued; waits for it here.
 __device__ __forceinline__ void ln_prologue(const DecParams& p, const DecSub* prev, const DecSub* cur, int t, float* streams,
-                                            bf16* As, int lda_s, int warp, int lane) {
+                                            bf16* As, int lda_s, const float* lnp, const bf16* shs, int warp, int lane) {
   const int D = p.D, B = p.B;
-  if (warp < B) {
-    const int b = warp;
-    int nv = 0;
+  float4 v[DS_LNV];
+  int nv = 0;
+#pragma unroll
+  for (int i = 0; i < DS_LNV; ++i)
+    if ((lane + 32 * i) * 4 < D) nv = i + 1;
+  if (warp < B && prev != nullptr) {  // the only loads that had to wait for the barrier
 #pragma unroll
     for (int i = 0; i < DS_LNV; ++i)
-      if ((lane + 32 * i) * 4 < D) nv = i + 1;
-    float4 v[DS_LNV];
+      if (i < nv) v[i] = __ldcg(reinterpret_cast<const float4*>(p.y + (long long)warp * D + (lane + 32 * i) * 4));
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (warp < B) {
+    const int b = warp;
     if (prev != nullptr) {
       float* st = streams + ((long long)prev->write * B + b) * D;
-#pragma unroll
-      for (int i = 0; i < DS_LNV; ++i)
-        if (i < nv) v[i] = __ldcg(reinterpret_cast<const float4*>(p.y + (long long)b * D + (lane + 32 * i) * 4));
       float mean, rstd;
       ds_row_stats(v, nv, D, mean, rstd);
 #pragma unroll
       for (int i = 0; i < DS_LNV; ++i)
         if (i < nv) {
           const int c = (lane + 32 * i) * 4;
-          const float4 w = __ldg(reinterpret_cast<const float4*>(prev->post_w + c));
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(prev->post_b + c));
+          const float4 w = *reinterpret_cast<const float4*>(lnp + c);
+          const float4 bb = *reinterpret_cast<const float4*>(lnp + D + c);
           const float4 r = *reinterpret_cast<const float4*>(st + c);
           v[i].x = (v[i].x - mean) * rstd * w.x + bb.x + r.x;
           v[i].y = (v[i].y - mean) * rstd * w.y + bb.y + r.y;
@@ -308,21 +355,13 @@ __device__ __forceinline__ void ln_prologue(const DecParams& p, const DecSub* pr
       ds_row_stats(v, nv, D, mean, rstd);
       const int q4 = D / 4;
       const bool shifted = cur->shift && t >= 1;
-      int src_h = -1, src_w = -1;
-      if (shifted) {
-        const int T = p.fmap * p.fmap;
-        const int pos = (t - 1) % T;
-        const int row = pos / p.fmap, col = pos - row * p.fmap;
-        if (row > 0) src_h = t - p.fmap;
-        if (col > 0) src_w = t - 1;
-      }
       bf16* sc = cur->shift ? reinterpret_cast<bf16*>(cur->shift_cache) + (long long)b * p.npos * D : nullptr;
 #pragma unroll
       for (int i = 0; i < DS_LNV; ++i)
         if (i < nv) {
           const int c = (lane + 32 * i) * 4;
-          const float4 w = __ldg(reinterpret_cast<const float4*>(cur->pre_w + c));
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(cur->pre_b + c));
+          const float4 w = *reinterpret_cast<const float4*>(lnp + 2 * D + c);
+          const float4 bb = *reinterpret_cast<const float4*>(lnp + 3 * D + c);
           uint2 pk;
           pk.x = pack_bf16x2((v[i].x - mean) * rstd * w.x + bb.x, (v[i].y - mean) * rstd * w.y + bb.y);
           pk.y = pack_bf16x2((v[i].z - mean) * rstd * w.z + bb.z, (v[i].w - mean) * rstd * w.w + bb.w);
@@ -330,10 +369,7 @@ __device__ __forceinline__ void ln_prologue(const DecParams& p, const DecSub* pr
           if (cur->shift && c < 2 * q4) {
             // every CTA holds the same value; CTA 0 publishes it for the tokens to come
             if (blockIdx.x == 0 && t < p.npos) *reinterpret_cast<uint2*>(sc + (long long)t * D + c) = pk;
-            if (shifted) {
-              const int src = c < q4 ? src_h : src_w;
-              outv = src >= 0 ? *reinterpret_cast<const uint2*>(sc + (long long)src * D + c) : make_uint2(0u, 0u);
-            }
+            if (shifted) outv = *reinterpret_cast<const uint2*>(shs + b * (D / 2) + c);
           }
           *reinterpret_cast<uint2*>(As + b * lda_s + c) = outv;
         }
@@ -342,9 +378,10 @@ __device__ __forceinline__ void ln_prologue(const DecParams& p, const DecSub* pr
   __syncthreads();
 }
 
-// final StableLayerNorm of streams[0] (+ streams[1]) -> out_f32 / out_bf16 (CTA 0) and As (every CTA, for the logits)
-__device__ __forceinline__ void stable_ln_rows(const DecParams& p, const float* streams, bf16* As, int lda_s, int warp,
-                                               int lane) {
+// final StableLayerNorm of streams[0] (+ streams[1]) -> out_f32 / out_bf16 (CTA 0) and As (every CTA, for the logits);
+// weight / bias in lnp[2..3]
+__device__ __forceinline__ void stable_ln_rows(const DecParams& p, const float* streams, bf16* As, int lda_s,
+                                               const float* lnp, int warp, int lane) {
   const int D = p.D, B = p.B;
   if (warp < B) {
     const int b = warp;
@@ -374,8 +411,8 @@ __device__ __forceinline__ void stable_ln_rows(const DecParams& p, const float* 
     for (int i = 0; i < DS_LNV; ++i)
       if (i < nv) {
         const int c = (lane + 32 * i) * 4;
-        const float4 ww = __ldg(reinterpret_cast<const float4*>(p.norm_w + c));
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.norm_b + c));
+        const float4 ww = *reinterpret_cast<const float4*>(lnp + 2 * D + c);
+        const float4 bb = *reinterpret_cast<const float4*>(lnp + 3 * D + c);
         float4 o;
         o.x = (v[i].x - mean) * rstd * ww.x + bb.x;
         o.y = (v[i].y - mean) * rstd * ww.y + bb.y;
@@ -397,16 +434,16 @@ __device__ __forceinline__ void stable_ln_rows(const DecParams& p, const float* 
 // ------------------------------------------------------------------------------------------------
 // attention pieces (one query row per sample)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int key3dna(const DecParams& p, int t, int nv, int j, int& row) {
+__device__ __forceinline__ int key3dna(const DecParams& p, const DecSub& s, int t, int nv, int j, int& row) {
   if (j == 0) { row = 0; return DK_NORMAL; }
   const int jj = j - 1;
-  const int c = jj % p.kw, bq = (jj / p.kw) % p.kh, a = jj / (p.kw * p.kh);
+  const int c = jj % s.kw, bq = (jj / s.kw) % s.kh, a = jj / (s.kw * s.kh);
   const int T = p.fmap * p.fmap;
   const int vt = t - 1;
   const int f = vt / T, y = (vt % T) / p.fmap, x = vt % p.fmap;
-  const int pf = p.dt * (p.kt - 1) / 2, ph = p.dh_ * (p.kh - 1) / 2, pw = p.dw * (p.kw - 1) / 2;
+  const int pf = s.dt * (s.kt - 1) / 2, ph = s.dh_ * (s.kh - 1) / 2, pw = s.dw * (s.kw - 1) / 2;
   const int Pf = p.causal ? 2 * pf : pf, Ph = p.causal ? 2 * ph : ph, Pw = p.causal ? 2 * pw : pw;
-  const int ff = f + a * p.dt - Pf, yy = y + bq * p.dh_ - Ph, xx = x + c * p.dw - Pw;
+  const int ff = f + a * s.dt - Pf, yy = y + bq * s.dh_ - Ph, xx = x + c * s.dw - Pw;
   if (ff < 0 || ff >= p.max_frames || yy < 0 || yy >= p.fmap || xx < 0 || xx >= p.fmap) return DK_MASKED;
   const int idx = (ff * p.fmap + yy) * p.fmap + xx;
   if (idx >= nv) return DK_ZERO;
@@ -414,7 +451,15 @@ __device__ __forceinline__ int key3dna(const DecParams& p, int t, int nv, int j,
   return DK_NORMAL;
 }
 
-// scores of heads [0, nh) (pointers already offset to the first head): S[hl*J + j]
+__device__ __forceinline__ float dot8q(const float* q, const uint4& u) {
+  const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  const float4 q0 = *reinterpret_cast<const float4*>(q), q1 = *reinterpret_cast<const float4*>(q + 4);
+  return q0.x * a.x + q0.y * a.y + q0.z * b2.x + q0.w * b2.y + q1.x * c.x + q1.y * c.y + q1.z * d.x + q1.w * d.y;
+}
+
+// scores of heads [0, nh) (pointers already offset to the first head): S[hl*J + j].  DH8 = dh / 8 as a compile-time
+// constant puts every 16-byte load of a key row in flight at once (0 = runtime head width).
+template <int DH8>
 __device__ __forceinline__ void attn_scores(const float* qs, const int* keys, const bf16* kbase, int k_rs,
                                             const float* null_k, int nh, int dh, int J, float* S) {
   for (int item = threadIdx.x; item < nh * J; item += DS_THREADS) {
@@ -424,13 +469,16 @@ __device__ __forceinline__ void attn_scores(const float* qs, const int* keys, co
     const float* q = qs + hl * dh;
     float s;
     if (kind == DK_NORMAL) {
-      const bf16* kr = kbase + (long long)row * k_rs + hl * dh;
+      const uint4* kr = reinterpret_cast<const uint4*>(kbase + (long long)row * k_rs + hl * dh);
       s = 0.f;
-      for (int i = 0; i < dh / 8; ++i) {
-        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(kr) + i);
-        const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-        const float4 q0 = *reinterpret_cast<const float4*>(q + i * 8), q1 = *reinterpret_cast<const float4*>(q + i * 8 + 4);
-        s += q0.x * a.x + q0.y * a.y + q0.z * b2.x + q0.w * b2.y + q1.x * c.x + q1.y * c.y + q1.z * d.x + q1.w * d.y;
+      if (DH8 > 0) {
+        uint4 u[DH8 > 0 ? DH8 : 1];
+#pragma unroll
+        for (int i = 0; i < DH8; ++i) u[i] = __ldcg(kr + i);
+#pragma unroll
+        for (int i = 0; i < DH8; ++i) s += dot8q(q + i * 8, u[i]);
+      } else {
+        for (int i = 0; i < dh / 8; ++i) s += dot8q(q + i * 8, __ldcg(kr + i));
       }
     } else if (kind == DK_NULL) {
       const float* nk = null_k + hl * dh;
@@ -462,7 +510,8 @@ __device__ __forceinline__ void attn_softmax(float* S, int nh, int J, int warp, 
   }
 }
 
-// out[hl*dh + c] = sum_j P[hl*J + j] * V[row_j][hl*dh + c]   for heads [0, nh) (vbase / null_v offset to the first head)
+// out[hl*dh + c] = sum_j P[hl*J + j] * V[row_j][hl*dh + c]   for heads [0, nh) (vbase / null_v offset to the first head).
+// Branch-free key loop (masked / zero / null keys load row 0 with weight 0) so that the unrolled loads overlap.
 __device__ __forceinline__ void attn_pv(const float* P, const int* keys, const bf16* vbase, int v_rs, const float* null_v,
                                         int nh, int dh, int J, float* part, float* outs) {
   const int npairs = nh * dh / 2;
@@ -471,22 +520,37 @@ __device__ __forceinline__ void attn_pv(const float* P, const int* keys, const b
   if (kg < KG) {
     const int hl = cp / (dh / 2), c2 = cp - hl * (dh / 2);
     const float* Ph = P + hl * J;
+    const bf16* vcol = vbase + hl * dh + 2 * c2;
     float ax = 0.f, ay = 0.f;
-#pragma unroll 4
-    for (int j = kg; j < J; j += KG) {
-      const int kj = keys[j];
-      const int row = kj & 0x0FFFFFFF, kind = kj >> 28;
-      if (kind == DK_NORMAL) {
-        const uint32_t u = __ldcg(reinterpret_cast<const unsigned int*>(vbase + (long long)row * v_rs + hl * dh + 2 * c2));
-        const float2 v = unpack_bf16x2(u);
-        const float pj = Ph[j];
-        ax = fmaf(pj, v.x, ax);
-        ay = fmaf(pj, v.y, ay);
-      } else if (kind == DK_NULL) {
-        const float pj = Ph[j];
-        ax = fmaf(pj, __ldg(null_v + hl * dh + 2 * c2), ax);
-        ay = fmaf(pj, __ldg(null_v + hl * dh + 2 * c2 + 1), ay);
+    int j = kg;
+    for (; j + 7 * KG < J; j += 8 * KG) {
+      uint32_t u[8];
+      float pj[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int kj = keys[j + k * KG];
+        const bool normal = (kj >> 28) == DK_NORMAL;
+        u[k] = __ldcg(reinterpret_cast<const unsigned int*>(vcol + (long long)(normal ? (kj & 0x0FFFFFFF) : 0) * v_rs));
+        pj[k] = normal ? Ph[j + k * KG] : 0.f;
       }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float2 v = unpack_bf16x2(u[k]);
+        ax = fmaf(pj[k], v.x, ax);
+        ay = fmaf(pj[k], v.y, ay);
+      }
+    }
+    for (; j < J; j += KG) {
+      const int kj = keys[j];
+      if ((kj >> 28) == DK_NORMAL) {
+        const float2 v = unpack_bf16x2(__ldcg(reinterpret_cast<const unsigned int*>(vcol + (long long)(kj & 0x0FFFFFFF) * v_rs)));
+        ax = fmaf(Ph[j], v.x, ax);
+        ay = fmaf(Ph[j], v.y, ay);
+      }
+    }
+    if (kg == 0 && (keys[0] >> 28) == DK_NULL) {  // the learned null key / value is slot 0
+      ax = fmaf(Ph[0], __ldg(null_v + hl * dh + 2 * c2), ax);
+      ay = fmaf(Ph[0], __ldg(null_v + hl * dh + 2 * c2 + 1), ay);
     }
     part[(kg * npairs + cp) * 2 + 0] = ax;
     part[(kg * npairs + cp) * 2 + 1] = ay;
@@ -504,9 +568,37 @@ __device__ __forceinline__ void attn_pv(const float* P, const int* keys, const b
   __syncthreads();
 }
 
+__device__ __forceinline__ void attn_scores_any(const float* qs, const int* keys, const bf16* kbase, int k_rs,
+                                                const float* null_k, int nh, int dh, int J, float* S) {
+  if (dh == 64) attn_scores<8>(qs, keys, kbase, k_rs, null_k, nh, dh, J, S);
+  else if (dh == 32) attn_scores<4>(qs, keys, kbase, k_rs, null_k, nh, dh, J, S);
+  else attn_scores<0>(qs, keys, kbase, k_rs, null_k, nh, dh, J, S);
+}
+
+// key list of the dense cross attention: slot 0 = learned null key, slot 1 + i = context token i (masked by key_mask)
+__device__ __forceinline__ void cross_keys(const DecParams& p, int b, int J, int* keys) {
+  for (int j = threadIdx.x; j < J; j += DS_THREADS) {
+    int kd = DK_NULL, row = 0;
+    if (j > 0) {
+      row = j - 1;
+      kd = (p.key_mask != nullptr && p.key_mask[(long long)b * p.mask_bs + row] == 0) ? DK_MASKED : DK_NORMAL;
+    }
+    keys[j] = (kd << 28) | row;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+#define DS_STAMP(id)                                                            \
+  do {                                                                          \
+    if (p.prof != nullptr && blockIdx.x == p.prof_cta && threadIdx.x == 0) {   \
+      p.prof[2 * nstamp] = (long long)(si * 16 + (id));                         \
+      p.prof[2 * nstamp + 1] = clock64();                                       \
+      ++nstamp;                                                                 \
+    }                                                                           \
+  } while (0)
+
 __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecParams p) {
   extern __shared__ __align__(16) uint8_t ds_smem[];
   const int B = p.B, D = p.D, H = p.H, dh = p.dh, inner = H * dh;
@@ -521,27 +613,41 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
   float* Wt = reinterpret_cast<float*>(ds_smem + L.wt);
   float* part = reinterpret_cast<float*>(ds_smem + L.part);
   float* outs = reinterpret_cast<float*>(ds_smem + L.outs);
+  float* lnp = reinterpret_cast<float*>(ds_smem + L.lnp);
+  bf16* shs = reinterpret_cast<bf16*>(ds_smem + L.shs);
+  constexpr int DESC_STRIDE = (sizeof(DecSub) + 15) & ~15;
+  constexpr int DESC_WORDS = sizeof(DecSub) / 4;
   const int lda_s = p.kmax;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gwarp = blockIdx.x * DS_WARPS + warp;
   const int total_warps = gridDim.x * DS_WARPS;
   const int t = __ldg(p.t_ptr);
   const float qscale = rsqrtf((float)dh);
+  const int dbg = p.debug_flags;
   GridBar bar{p.barrier, gridDim.x, 0u};
   bf16* act = reinterpret_cast<bf16*>(p.act);
   bf16* actq = reinterpret_cast<bf16*>(p.actq);
+  int nstamp = 0;
+  int si = 0;
 
-  // X = x (plain) or [x, x] (reversible.py:133)
+  // X = x (plain) or [x, x] (reversible.py:133); descriptor of the first sub-block
   for (int i = threadIdx.x; i < B * D; i += DS_THREADS) {
     const float v = __ldg(p.x_in + i);
     streams[i] = v;
     if (p.reversible) streams[B * D + i] = v;
   }
+  if (threadIdx.x < DESC_WORDS)
+    reinterpret_cast<uint32_t*>(ds_smem + L.desc)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(p.subs) + threadIdx.x);
   __syncthreads();
+  DS_STAMP(0);
 
   const DecSub* prev = nullptr;
-  for (int si = 0; si < p.nsubs; ++si) {
-    const DecSub* s = p.subs + si;
+  for (si = 0; si < p.nsubs; ++si) {
+    const DecSub* s = reinterpret_cast<const DecSub*>(ds_smem + L.desc + (si % 3) * DESC_STRIDE);
+    // descriptor of the NEXT sub-block: requested now, parked in shared memory after the first barrier wait
+    uint32_t next_word = 0;
+    const bool has_next = si + 1 < p.nsubs && threadIdx.x < DESC_WORDS;
+    if (has_next) next_word = __ldg(reinterpret_cast<const uint32_t*>(p.subs + si + 1) + threadIdx.x);
     const int kind = s->kind;
     WPre wp;
     // ---- phase 1: (post-norm + residual of the previous sub-block,) pre-norm, first product ----
@@ -553,33 +659,43 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
     const bf16* Wb = reinterpret_cast<const bf16*>(s->w_b);
     if (kind == NUWA_DEC_FF) gemv_prefetch<true>(wp, Wa, D, N1, D, S1, gwarp, lane);
     else gemv_prefetch<false>(wp, Wa, D, N1, D, S1, gwarp, lane);
+    prefetch_norms(p, prev, s, nullptr, nullptr, t, lnp, shs);
+    DS_STAMP(1);
     if (prev != nullptr) grid_barrier(bar);  // y of the previous sub-block is complete
-    ln_prologue(p, prev, s, t, streams, As, lda_s, warp, lane);
+    DS_STAMP(2);
+    if (has_next)
+      reinterpret_cast<uint32_t*>(ds_smem + L.desc + ((si + 1) % 3) * DESC_STRIDE)[threadIdx.x] = next_word;
+    if (!(dbg & 1)) ln_prologue(p, prev, s, t, streams, As, lda_s, lnp, shs, warp, lane);
+    else { cp_async_wait_all(); __syncthreads(); }
+    DS_STAMP(3);
     if (kind == NUWA_DEC_3DNA) {
       // q|k|v of the new token go straight into row t of the cache
       bf16* cache = reinterpret_cast<bf16*>(s->cache);
       GemvOut o{nullptr, cache + (long long)t * 3 * inner, (long long)p.npos * 3 * inner, nullptr};
-      gemv_run<false>(wp, Wa, D, N1, D, S1, As, lda_s, B, red, o, gwarp, total_warps, warp, lane);
+      if (!(dbg & 2)) gemv_run<false>(wp, Wa, D, N1, D, S1, As, lda_s, B, red, o, gwarp, total_warps, warp, lane);
       gemv_prefetch<false>(wp, Wb, inner, D, inner, p.split_small, gwarp, lane);
+      for (int i = threadIdx.x; i < H * H; i += DS_THREADS) Wt[i] = __ldg(s->talk + i);
+      DS_STAMP(4);
       grid_barrier(bar);
+      DS_STAMP(5);
       // ---- phase 2: attention, one CTA per sample (all heads: talking heads mix across heads) ----
+      if (!(dbg & 4))
       for (int b = blockIdx.x; b < B; b += gridDim.x) {
         const bf16* cb = cache + (long long)b * p.npos * 3 * inner;
         if (t == 0) {  // bos attends only to itself (:499,608)
           for (int c = threadIdx.x; c < inner; c += DS_THREADS) act[(long long)b * inner + c] = __ldcg(cb + 2 * inner + c);
           continue;
         }
-        const int J = 1 + p.kt * p.kh * p.kw;
+        const int J = 1 + s->kt * s->kh * s->kw;
         for (int j = threadIdx.x; j < J; j += DS_THREADS) {
           int row = 0;
-          const int kd = key3dna(p, t, t, j, row);
+          const int kd = key3dna(p, *s, t, t, j, row);
           keys[j] = (kd << 28) | row;
         }
         for (int c = threadIdx.x; c < inner; c += DS_THREADS)
           qs[c] = __bfloat162float(__ldcg(cb + (long long)t * 3 * inner + c)) * qscale;
-        for (int i = threadIdx.x; i < H * H; i += DS_THREADS) Wt[i] = __ldg(s->talk + i);
         __syncthreads();
-        attn_scores(qs, keys, cb + inner, 3 * inner, nullptr, H, dh, J, Ss);
+        attn_scores_any(qs, keys, cb + inner, 3 * inner, nullptr, H, dh, J, Ss);
         __syncthreads();
         attn_softmax(Ss, H, J, warp, lane);
         __syncthreads();
@@ -597,49 +713,44 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
         for (int c = threadIdx.x; c < inner; c += DS_THREADS) act[(long long)b * inner + c] = __float2bfloat16(outs[c]);
         __syncthreads();
       }
+      DS_STAMP(6);
       grid_barrier(bar);
+      DS_STAMP(7);
       // ---- phase 3: to_out (+ bias) ----
       stage_act(As, lda_s, act, inner, B, inner);
       GemvOut o3{p.y, nullptr, (long long)D, s->b_out};
-      gemv_run<false>(wp, Wb, inner, D, inner, p.split_small, As, lda_s, B, red, o3, gwarp, total_warps, warp, lane);
+      if (!(dbg & 2)) gemv_run<false>(wp, Wb, inner, D, inner, p.split_small, As, lda_s, B, red, o3, gwarp, total_warps, warp, lane);
+      DS_STAMP(12);
     } else if (kind == NUWA_DEC_CROSS) {
       GemvOut o{nullptr, actq, (long long)inner, nullptr};
-      gemv_run<false>(wp, Wa, D, N1, D, S1, As, lda_s, B, red, o, gwarp, total_warps, warp, lane);
+      if (!(dbg & 2)) gemv_run<false>(wp, Wa, D, N1, D, S1, As, lda_s, B, red, o, gwarp, total_warps, warp, lane);
       gemv_prefetch<false>(wp, Wb, inner, D, inner, p.split_small, gwarp, lane);
+      DS_STAMP(4);
       grid_barrier(bar);
+      DS_STAMP(5);
       const int J = p.nk + 1;
       const bf16* kv = reinterpret_cast<const bf16*>(s->cache);
       // ---- phase 2a: scores of one (sample, head) per CTA ----
+      if (!(dbg & 4))
       for (int w = blockIdx.x; w < B * H; w += gridDim.x) {
         const int b = w / H, h = w - b * H;
-        for (int j = threadIdx.x; j < J; j += DS_THREADS) {
-          int kd = DK_NULL, row = 0;
-          if (j > 0) {
-            row = j - 1;
-            kd = (p.key_mask != nullptr && p.key_mask[(long long)b * p.mask_bs + row] == 0) ? DK_MASKED : DK_NORMAL;
-          }
-          keys[j] = (kd << 28) | row;
-        }
+        cross_keys(p, b, J, keys);
         for (int c = threadIdx.x; c < dh; c += DS_THREADS)
           qs[c] = __bfloat162float(__ldcg(actq + (long long)b * inner + h * dh + c)) * qscale;
         __syncthreads();
-        attn_scores(qs, keys, kv + (long long)b * p.nk * 2 * inner + h * dh, 2 * inner, s->null_k + h * dh, 1, dh, J, Ss);
+        attn_scores_any(qs, keys, kv + (long long)b * p.nk * 2 * inner + h * dh, 2 * inner, s->null_k + h * dh, 1, dh, J, Ss);
         __syncthreads();
         for (int j = threadIdx.x; j < J; j += DS_THREADS) p.scores[((long long)b * H + h) * J + j] = Ss[j];
         __syncthreads();
       }
+      DS_STAMP(6);
       grid_barrier(bar);
+      DS_STAMP(7);
       // ---- phase 2b: softmax of every head of the sample, talking-heads row g, PV of head g ----
+      if (!(dbg & 4))
       for (int w = blockIdx.x; w < B * H; w += gridDim.x) {
         const int b = w / H, g = w - b * H;
-        for (int j = threadIdx.x; j < J; j += DS_THREADS) {
-          int kd = DK_NULL, row = 0;
-          if (j > 0) {
-            row = j - 1;
-            kd = (p.key_mask != nullptr && p.key_mask[(long long)b * p.mask_bs + row] == 0) ? DK_MASKED : DK_NORMAL;
-          }
-          keys[j] = (kd << 28) | row;
-        }
+        cross_keys(p, b, J, keys);
         for (int i = threadIdx.x; i < H * J; i += DS_THREADS) Ss[i] = __ldcg(p.scores + (long long)b * H * J + i);
         for (int i = threadIdx.x; i < H; i += DS_THREADS) Wt[i] = __ldg(s->talk + g * H + i);
         __syncthreads();
@@ -656,19 +767,25 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
         for (int c = threadIdx.x; c < dh; c += DS_THREADS) act[(long long)b * inner + g * dh + c] = __float2bfloat16(outs[c]);
         __syncthreads();
       }
+      DS_STAMP(8);
       grid_barrier(bar);
+      DS_STAMP(9);
       stage_act(As, lda_s, act, inner, B, inner);
       GemvOut o3{p.y, nullptr, (long long)D, nullptr};
-      gemv_run<false>(wp, Wb, inner, D, inner, p.split_small, As, lda_s, B, red, o3, gwarp, total_warps, warp, lane);
+      if (!(dbg & 2)) gemv_run<false>(wp, Wb, inner, D, inner, p.split_small, As, lda_s, B, red, o3, gwarp, total_warps, warp, lane);
+      DS_STAMP(12);
     } else {
       // GEGLU product: value/gate pairs -> a * gelu(g) (:255-258)
       GemvOut o{nullptr, act, (long long)s->ip, nullptr};
-      gemv_run<true>(wp, Wa, D, N1, D, S1, As, lda_s, B, red, o, gwarp, total_warps, warp, lane);
+      if (!(dbg & 2)) gemv_run<true>(wp, Wa, D, N1, D, S1, As, lda_s, B, red, o, gwarp, total_warps, warp, lane);
       gemv_prefetch<false>(wp, Wb, s->ip, D, s->ip, p.split_ff, gwarp, lane);
+      DS_STAMP(4);
       grid_barrier(bar);
+      DS_STAMP(5);
       stage_act(As, lda_s, act, s->ip, B, s->ip);
       GemvOut o3{p.y, nullptr, (long long)D, nullptr};
-      gemv_run<false>(wp, Wb, s->ip, D, s->ip, p.split_ff, As, lda_s, B, red, o3, gwarp, total_warps, warp, lane);
+      if (!(dbg & 2)) gemv_run<false>(wp, Wb, s->ip, D, s->ip, p.split_ff, As, lda_s, B, red, o3, gwarp, total_warps, warp, lane);
+      DS_STAMP(12);
     }
     prev = s;
   }
@@ -676,13 +793,16 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
   WPre wl;
   const bf16* Wl = reinterpret_cast<const bf16*>(p.w_logits);
   if (Wl != nullptr) gemv_prefetch<false>(wl, Wl, D, p.V, D, 1, gwarp, lane);
+  prefetch_norms(p, prev, nullptr, p.norm_w, p.norm_b, t, lnp, shs);
   grid_barrier(bar);
-  ln_prologue(p, prev, nullptr, t, streams, As, lda_s, warp, lane);
-  stable_ln_rows(p, streams, As, lda_s, warp, lane);
+  DS_STAMP(13);
+  ln_prologue(p, prev, nullptr, t, streams, As, lda_s, lnp, shs, warp, lane);
+  stable_ln_rows(p, streams, As, lda_s, lnp, warp, lane);
   if (Wl != nullptr) {
     GemvOut ol{p.logits, nullptr, (long long)p.V, nullptr};
     gemv_run<false>(wl, Wl, D, p.V, D, 1, As, lda_s, B, red, ol, gwarp, total_warps, warp, lane);
   }
+  DS_STAMP(14);
   // ---- leave: the last CTA out resets the barrier words for the next launch ----
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -693,6 +813,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
       p.barrier[1] = 0u;
       __threadfence();
     }
+    if (p.prof != nullptr && blockIdx.x == p.prof_cta) p.prof[2 * nstamp] = -1;
   }
 }
 
@@ -703,15 +824,15 @@ int decode_stack(const DecParams& p_in, int cooperative, cudaStream_t stream) {
   DecParams p = p_in;
   if (p.subs == nullptr || p.nsubs <= 0 || p.B <= 0 || p.B > 16 || p.t_ptr == nullptr || p.barrier == nullptr)
     return NUWA_ERR_INVALID;
-  if (p.D % 16 != 0 || p.D > 1024 || p.H <= 0 || p.H > 16 || p.dh % 8 != 0 || p.H * p.dh > 1024 || (p.H * p.dh) % 8 != 0)
+  if (p.D % 32 != 0 || p.D > 1024 || p.H <= 0 || p.H > 16 || p.dh % 8 != 0 || p.H * p.dh > 1024 || (p.H * p.dh) % 8 != 0)
     return NUWA_ERR_INVALID;
   if (p.kmax < p.D || p.kmax < p.H * p.dh || p.kmax % 8 != 0) return NUWA_ERR_INVALID;
   if (p.x_in == nullptr || p.y == nullptr || p.act == nullptr || p.actq == nullptr || p.norm_w == nullptr ||
       p.norm_b == nullptr)
     return NUWA_ERR_INVALID;
   if (p.w_logits != nullptr && (p.logits == nullptr || p.V <= 0)) return NUWA_ERR_INVALID;
-  const int j3 = 1 + p.kt * p.kh * p.kw;
-  p.jmax = j3 > p.nk + 1 ? j3 : p.nk + 1;
+  if (p.j3max < 1 || p.j3max > 4096) return NUWA_ERR_INVALID;
+  p.jmax = p.j3max > p.nk + 1 ? p.j3max : p.nk + 1;
   if (p.nk > 0 && p.scores == nullptr) return NUWA_ERR_INVALID;
   if (p.split_small != 1 && p.split_small != 2 && p.split_small != 4) p.split_small = 2;
   if (p.split_ff != 1 && p.split_ff != 2 && p.split_ff != 4) p.split_ff = 4;

@@ -80,6 +80,9 @@ int cache_append(const void* row, void* cache, long long cache_bs, int width, in
 int step_increment(int* t_ptr, cudaStream_t stream);
 // decode_stack.cu
 int decode_stack(const nuwa_decode_params& p, int cooperative, cudaStream_t stream);
+// optim.cu
+int sqnorm_f32(const float* x, long long n, float* partials, int nparts, float* out, int accumulate, cudaStream_t stream);
+int adamw_step(const nuwa_adamw_params& a, cudaStream_t stream);
 // vae_ops.cu
 int nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, cudaStream_t stream);
 int nhwc_to_nchw_f32(const void* in, int in_is_bf16, float* out, int B, int C, int H, int W, cudaStream_t stream);

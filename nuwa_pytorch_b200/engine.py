@@ -70,7 +70,7 @@ class StackPack:
 
 
 def _signature(module):
-    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+    return (_lib.WEIGHTS_EPOCH[0],) + tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
 
 
 def pack_stack(stack):
@@ -292,14 +292,14 @@ class FusedDecode:
 
     @staticmethod
     def supported(pack, B, context):
-        if os.environ.get('NUWA_DECODE_FUSED', '1') == '0' or B > 16 or pack.dim % 16 or pack.dim > 1024:
+        if os.environ.get('NUWA_DECODE_FUSED', '1') == '0' or B > 16 or pack.dim % 32 or pack.dim > 1024:
             return False
         geo, heads = set(), set()
         for s in pack.subs:
             if s.kind not in _DEC_KIND:
                 return False
             if s.kind == '3dna':
-                geo.add((s.fmap, s.max_frames, tuple(s.kernel), tuple(s.dilation), bool(s.causal)))
+                geo.add((s.fmap, s.max_frames, bool(s.causal)))  # kernel / dilation may differ per layer
                 if s.b_out is None:
                     return False
             if s.kind == 'ff' and s.shift and s.fmap is None:
@@ -319,7 +319,7 @@ class FusedDecode:
         self.pack, self.state, self.context = pack, state, context
         subs = (_lib.DecodeSub * len(pack.subs))()
         kmax, H, dh = D, None, None
-        shift_fmap = None
+        shift_fmap, j3max = None, 1
         for i, s in enumerate(pack.subs):
             d = subs[i]
             d.kind, d.shift, d.read, d.write = _DEC_KIND[s.kind], int(bool(s.shift)), s.read, s.write
@@ -331,6 +331,9 @@ class FusedDecode:
                 H, dh = s.H, s.dh
                 d.w_a, d.w_b, d.b_out, d.talk = s.w_qkv.data_ptr(), s.w_out.data_ptr(), s.b_out.data_ptr(), s.talk.data_ptr()
                 d.cache = state.qkv[i].data_ptr()
+                d.kt, d.kh, d.kw = s.kernel
+                d.dt, d.dh_, d.dw = s.dilation
+                j3max = max(j3max, 1 + s.kernel[0] * s.kernel[1] * s.kernel[2])
                 geom = s
             elif s.kind == 'cross':
                 H, dh = s.H, s.dh
@@ -357,10 +360,7 @@ class FusedDecode:
         p = _lib.DecodeParams()
         p.subs, p.nsubs = self.subs_dev.data_ptr(), len(pack.subs)
         p.B, p.D, p.H, p.dh, p.npos, p.reversible = B, D, H, dh, npos, int(pack.reversible)
-        p.fmap, p.max_frames = geom.fmap, geom.max_frames
-        p.kt, p.kh, p.kw = geom.kernel
-        p.dt, p.dh_, p.dw = geom.dilation
-        p.causal = int(bool(geom.causal))
+        p.fmap, p.max_frames, p.causal, p.j3max = geom.fmap, geom.max_frames, int(bool(geom.causal)), j3max
         assert shift_fmap is None or shift_fmap == geom.fmap
         p.nk = nk
         if context is not None and context.mask is not None:
@@ -376,6 +376,7 @@ class FusedDecode:
         p.split_small = int(os.environ.get('NUWA_DECODE_SPLIT_SMALL', '0'))
         p.split_ff = int(os.environ.get('NUWA_DECODE_SPLIT_FF', '0'))
         p.max_ctas = int(os.environ.get('NUWA_DECODE_MAX_CTAS', '0'))
+        p.debug_flags = int(os.environ.get('NUWA_DECODE_DEBUG', '0'))
         self.params = p
         self.cooperative = int(os.environ.get('NUWA_DECODE_COOP', '1'))
 

@@ -325,7 +325,7 @@ class _VideoDecoderMixin:
 
     def _logits_weight(self):
         w = self.to_logits.weight
-        key = (w.data_ptr(), w._version)
+        key = (w.data_ptr(), w._version, ops._lib.WEIGHTS_EPOCH[0])
         if getattr(self, '_logits_cache', (None,))[0] != key:
             self._logits_cache = (key, w.detach().to(torch.bfloat16).contiguous())
         return self._logits_cache[1]
