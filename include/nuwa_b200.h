@@ -239,7 +239,8 @@ typedef struct {
   unsigned int* barrier;         /* 2 words, zero before the FIRST launch; the kernel leaves them zero */
   int kmax;                      /* max(D, H*dh, every ip) */
   int jmax;                      /* set by the library */
-  int split_small, split_ff;     /* K slices per output column of the D x inner / D x ip products: 1, 2 or 4 (0 = default) */
+  int split_small, split_ff, split_logits; /* K slices (1 or 7 = worker warps per CTA; 0 = default) per 16-row tile of the
+                                  D- / inner-wide products, the FF-out product and the logits product */
   int max_ctas;                  /* 0 = one CTA per SM */
   /* measurement aids (tools/decode_phase_profile.py): prof != NULL makes CTA prof_cta record (tag, clock64) pairs at
    * every phase boundary (room for 2 * (12 * nsubs + 8) values); debug_flags bit 0/1/2 skip the norms / skinny

@@ -84,7 +84,7 @@ class DecodeParams(ctypes.Structure):  # mirrors nuwa_decode_params
                 ("t_ptr", c_void_p), ("x_in", c_void_p), ("norm_w", c_void_p), ("norm_b", c_void_p),
                 ("out_f32", c_void_p), ("out_bf16", c_void_p), ("w_logits", c_void_p), ("V", c_int),
                 ("logits", c_void_p), ("y", c_void_p), ("act", c_void_p), ("actq", c_void_p), ("scores", c_void_p),
-                ("barrier", c_void_p), ("kmax", c_int), ("jmax", c_int), ("split_small", c_int), ("split_ff", c_int),
+                ("barrier", c_void_p), ("kmax", c_int), ("jmax", c_int), ("split_small", c_int), ("split_ff", c_int), ("split_logits", c_int),
                 ("max_ctas", c_int), ("prof", c_void_p), ("prof_cta", c_int), ("debug_flags", c_int)]
 
 

@@ -6,15 +6,20 @@
 // microseconds of work on M = batch rows; as separate launches (even replayed from a CUDA graph) the step
 // is bound by launch + dependency latency (~7.6 us per node, 14.6 ms per token), 60x above the time the
 // 806 MB of bf16 weights need to stream from HBM.  Here the chip stays resident: 148 CTAs x 16 warps,
-// phases separated by a device-wide barrier (one L2 atomic + acquire spin), and
+// phases separated by a device-wide barrier, and everything that does not depend on the previous phase is
+// REQUESTED BEFORE the barrier so that the HBM latency (~1.3 us) hides behind it:
 //   * the residual streams live in EVERY CTA's shared memory (each CTA redundantly applies the post-norm +
-//     residual + pre-norm of the B rows, so no extra barrier and no HBM round trip for the streams),
-//   * every skinny product (q|k|v, q, GEGLU, out, FF-out, logits) is spread as (column, K-slice) tasks over
-//     all warps of the chip; the weights of a warp's first task are requested BEFORE it waits at the
-//     barrier, so the HBM latency of the weight stream is hidden behind the barrier,
-//   * the new token's q|k|v go straight into the KV cache row (no append kernel), the ShiftVideoTokens
-//     gather reads the persistent pre-norm cache, cross attention is split over (sample, head) CTAs in two
-//     phases (scores | softmax + talking-heads row + PV) so that no SM streams more than one head.
+//     residual + pre-norm of the B rows: no extra barrier, no HBM round trip for the streams),
+//   * skinny products (q|k|v, q, GEGLU, out, FF-out, logits) run on the tensor cores: mma.sync m16n8k16 with
+//     the 16 weight rows as M and the <= 8 batch rows as N (a CUDA-core version was ISSUE bound: ~1000
+//     instructions per output column); a warp owns a (16-row tile, K-slice) task, its weight fragments are
+//     16-byte loads issued before the barrier wait (the contraction index is permuted identically for both
+//     operands so that a lane's fragment is 8 contiguous bf16), partial tiles are reduced through smem,
+//   * K/V rows of earlier tokens (3DNA window) and the context K/V head slices (cross attention) stream into
+//     shared memory with cp.async two barriers ahead of their use; norm parameters, to_out bias,
+//     talking-heads matrices, shifted channel quarters and the next sub-block's descriptor likewise,
+//   * the new token's q|k|v go straight into the KV cache row (no append kernel); cross attention is split
+//     over (sample, head) CTAs in two phases (scores | softmax + talking-heads row + PV).
 // Rounding points are those of the per-kernel path (bf16 GEMM operands / q,k,v,o / GEGLU output, fp32
 // accumulation, norms and streams), so both paths agree to fp32 summation order.
 //
@@ -32,11 +37,18 @@ namespace nuwa {
 typedef nuwa_decode_sub DecSub;
 typedef nuwa_decode_params DecParams;
 
-static constexpr int DS_THREADS = 512;
+static constexpr int DS_THREADS = 256;  // 8 warps, 1 CTA / SM: up to 255 registers per thread (prefetched weight fragments)
 static constexpr int DS_WARPS = DS_THREADS / 32;
-static constexpr int DS_MR = 8;      // rows accumulated per pass of a skinny product
-static constexpr int DS_MAXC = 2;    // prefetched 16-byte weight chunks per lane and weight row
-static constexpr int DS_LNV = 8;     // float4 per lane in the row norms -> D <= 1024
+static constexpr int DS_LNV = 8;      // float4 per lane in the row norms -> D <= 1024
+static constexpr int DS_SMEM_MAX = 225 * 1024;
+// Warp DS_WWARPS (the last one) is the "sync warp": it signals and polls the device-wide barrier and therefore never
+// has loads in flight when it arrives -- a release fence waits for the issuing warp's outstanding loads, so a thread
+// that prefetches weights would serialise every barrier behind its own prefetch (HBM latency; measured >= 1 us per
+// barrier).  The sync warp takes no product tasks and issues no cp.async / register prefetches; it does share the
+// post-barrier work (norm rows, staging, attention), whose loads complete before the next arrival.
+static constexpr int DS_WWARPS = DS_WARPS - 1;
+static constexpr int DS_WORK = DS_WWARPS * 32;
+__device__ __forceinline__ int ds_wtid() { return threadIdx.x < DS_WORK ? (int)threadIdx.x : (1 << 28); }
 
 enum { DK_NORMAL = 0, DK_MASKED = 1, DK_ZERO = 2, DK_NULL = 3 };
 
@@ -44,25 +56,36 @@ enum { DK_NORMAL = 0, DK_MASKED = 1, DK_ZERO = 2, DK_NULL = 3 };
 // shared-memory layout (same arithmetic on host and device)
 // ------------------------------------------------------------------------------------------------
 struct DsLayout {
-  int streams, act, red, S, pm, keys, qs, wt, part, outs, lnp, shs, desc, total;
+  int streams, act, red, S, pm, keys, ckeys, qs, wt, part, outs, lnp, bias, shs, nullkv, desc, kvs, kv_rs3, kv_rsx, total;
 };
 __host__ __device__ inline int ds_align16(int x) { return (x + 15) & ~15; }
-__host__ __device__ inline DsLayout ds_layout(int B, int D, int kmax, int H, int dh, int jmax) {
+__host__ __device__ inline DsLayout ds_layout(int B, int D, int kmax, int H, int dh, int j3max, int nk) {
   DsLayout L;
+  const int nt = (B + 7) / 8;
+  const int jmax = j3max > nk + 1 ? j3max : nk + 1;
   int o = 0;
-  L.streams = o; o += ds_align16(2 * B * D * 4);          // fp32 [2][B][D]
-  L.act = o;     o += ds_align16(B * kmax * 2);           // bf16 [B][kmax] operand rows of the current product
-  L.red = o;     o += ds_align16(DS_WARPS * 2 * DS_MR * 4);  // K-slice partial sums
-  L.S = o;       o += ds_align16(H * jmax * 4);           // scores / probabilities [H][J]
-  L.pm = o;      o += ds_align16(jmax * 4);               // mixed probabilities of one head
-  L.keys = o;    o += ds_align16(jmax * 4);               // key list: (kind << 28) | row
-  L.qs = o;      o += ds_align16(H * dh * 4);             // scaled query, fp32
-  L.wt = o;      o += ds_align16(H * H * 4);              // talking-heads matrix
-  L.part = o;    o += ds_align16(DS_THREADS * 2 * 4);     // PV partial sums
-  L.outs = o;    o += ds_align16(H * dh * 4);             // attention output, fp32
-  L.lnp = o;     o += ds_align16(4 * D * 4);              // post_w, post_b, pre_w, pre_b of the coming norms (cp.async)
-  L.shs = o;     o += ds_align16(B * (D / 2) * 2);        // shifted channel halves of the ShiftVideoTokens gather
-  L.desc = o;    o += 3 * ds_align16((int)sizeof(nuwa_decode_sub));  // previous / current / next sub-block descriptor
+  L.streams = o; o += ds_align16(2 * B * D * 4);            // fp32 [2][B][D]
+  L.act = o;     o += ds_align16(B * kmax * 2);             // bf16 [B][kmax] operand rows of the current product
+  L.red = o;     o += ds_align16(DS_WARPS * 2 * nt * 128 * 4);  // partial 16 x 8 tiles of the K slices (value | gate)
+  L.S = o;       o += ds_align16(H * jmax * 4);             // scores / probabilities [H][J]
+  L.pm = o;      o += ds_align16(jmax * 4);                 // mixed probabilities of one head
+  L.keys = o;    o += ds_align16(j3max * 4);                // 3DNA key list of this sub-block: (kind << 28) | row
+  L.ckeys = o;   o += ds_align16((nk + 1) * 4);             // cross-attention key list of this CTA's sample (whole launch)
+  L.qs = o;      o += ds_align16(H * dh * 4);               // scaled query, fp32
+  L.wt = o;      o += ds_align16(H * H * 4);                // talking-heads matrix
+  L.part = o;    o += ds_align16(DS_THREADS * 2 * 4);       // PV partial sums
+  L.outs = o;    o += ds_align16(H * dh * 4);               // attention output, fp32
+  L.lnp = o;     o += ds_align16(4 * D * 4);                // post_w, post_b, pre_w, pre_b of the coming norms (cp.async)
+  L.bias = o;    o += ds_align16(D * 4);                    // to_out bias of the current Sparse3DNA sub-block
+  L.shs = o;     o += ds_align16(B * (D / 2) * 2);          // shifted channel quarters of the ShiftVideoTokens gather
+  L.nullkv = o;  o += ds_align16(2 * dh * 4);               // learned null key / value of this CTA's head, fp32
+  L.desc = o;    o += 4 * ds_align16((int)sizeof(nuwa_decode_sub));  // previous / current / next / next-but-one descriptor
+  // staged K | V rows: 3DNA window of one sample (all heads) or the context head slices of one (sample, head);
+  // row strides padded by 16 bytes so that lanes reading consecutive rows hit different banks
+  L.kv_rs3 = H * dh * 2 + 16;
+  L.kv_rsx = dh * 2 + 16;
+  const int kv3 = 2 * j3max * L.kv_rs3, kvx = nk > 0 ? 2 * nk * L.kv_rsx : 0;
+  L.kvs = o;     o += ds_align16(kv3 > kvx ? kv3 : kvx);
   L.total = o;
   return L;
 }
@@ -84,7 +107,7 @@ struct GridBar {
 
 __device__ __forceinline__ void grid_barrier(GridBar& g) {
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == DS_WORK) {  // lane 0 of the sync warp
     g.target += g.nblocks;
     // release: everything this CTA wrote (ordered before by the CTA barrier) is visible to whoever acquires the count
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(g.count) : "memory");
@@ -104,139 +127,172 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// wait until at most N of the most recently committed groups are still pending
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// skinny products:  out[b][col] = sum_k As[b][k] * W[row(col)][k]      (As bf16 in shared memory)
-// task = (column, K-slice); the S slices of a column sit in consecutive warps of one CTA.
+// skinny products on mma.sync:  out[n][tile*16 + r] = sum_k W[tile*16 + r][k] * As[n][k]
+//   A operand = 16 weight rows, B operand = batch rows (N = 8 per MMA), fp32 accumulators.
+//   k-block = 32 contraction indices; lane (g = lane/4, tg = lane%4) owns the 8 contiguous k [32*kb + 8*tg, +8) of weight
+//   rows g and g+8 (one 16-byte load each) and of batch row g (one 16-byte shared-memory load): the two MMAs of a
+//   k-block consume the .x/.y and .z/.w halves, i.e. the same permutation of k on both operands.
+//   task = (tile, K-slice); the S slices of a tile sit in consecutive worker warps of one CTA (S = 1 or DS_WWARPS).
 // ------------------------------------------------------------------------------------------------
-struct WPre {
-  uint4 v[DS_MAXC];
-  uint4 g[DS_MAXC];
-};
-
-__device__ __forceinline__ float dot8f(const uint4& a, const uint4& w) {
-  const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-  const float2 w0 = unpack_bf16x2(w.x), w1 = unpack_bf16x2(w.y), w2 = unpack_bf16x2(w.z), w3 = unpack_bf16x2(w.w);
-  return a0.x * w0.x + a0.y * w0.y + a1.x * w1.x + a1.y * w1.y + a2.x * w2.x + a2.y * w2.y + a3.x * w3.x + a3.y * w3.y;
+__device__ __forceinline__ void mma_bf16_16x8x16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                 uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ int gemv_slice(int K, int S) { return ((K + S - 1) / S + 7) & ~7; }
+template <int KB, bool PAIR>
+struct WPre {
+  uint4 a[KB][2];
+  uint4 g[PAIR ? KB : 1][2];
+};
 
 struct GemvOut {
   float* f32;        // fp32 output or NULL
   bf16* b16;         // bf16 output or NULL
   long long ld;      // row stride (elements)
-  const float* bias; // per output column or NULL
+  const float* bias; // per output column (shared memory) or NULL
 };
 
-template <bool PAIR>
-__device__ __forceinline__ void gemv_prefetch(WPre& w, const bf16* __restrict__ W, int ldw, int N, int K, int S,
-                                              int gwarp, int lane) {
+struct GemvTask {
+  int tile, kb0, kb1;
+  bool active;
+};
+__device__ __forceinline__ GemvTask gemv_task(int task, int ntiles, int K, int S) {
+  GemvTask t;
+  t.active = task < ntiles * S;
+  t.tile = t.active ? task / S : 0;
+  const int ks = t.active ? task - t.tile * S : 0;
+  const int nkb = (K + 31) >> 5, per = (nkb + S - 1) / S;
+  t.kb0 = ks * per;
+  t.kb1 = min(nkb, t.kb0 + per);
+  return t;
+}
+
+template <int KB, bool PAIR>
+__device__ __forceinline__ void gemv_prefetch(WPre<KB, PAIR>& w, const bf16* __restrict__ W, int ldw, int ntiles, int K,
+                                              int S, int gwarp, int lane) {
+  const GemvTask t = gemv_task(gwarp, ntiles, K, S);
+  const int g = lane >> 2, tg = lane & 3;
+  const bf16* w0 = W + (long long)(t.tile * (PAIR ? 32 : 16) + g) * ldw + 8 * tg;
 #pragma unroll
-  for (int i = 0; i < DS_MAXC; ++i) {
-    w.v[i] = make_uint4(0u, 0u, 0u, 0u);
-    w.g[i] = make_uint4(0u, 0u, 0u, 0u);
-  }
-  if (gwarp >= N * S) return;
-  const int col = gwarp / S, ks = gwarp - col * S;
-  const int slice = gemv_slice(K, S);
-  const int k0 = ks * slice, k1 = min(K, k0 + slice);
-  const int row = PAIR ? (col / 16) * 32 + (col % 16) : col;
-  const bf16* w0 = W + (long long)row * ldw;
-#pragma unroll
-  for (int i = 0; i < DS_MAXC; ++i) {
-    const int c = k0 + (lane + 32 * i) * 8;
-    if (c < k1) {
-      w.v[i] = __ldg(reinterpret_cast<const uint4*>(w0 + c));
-      if (PAIR) w.g[i] = __ldg(reinterpret_cast<const uint4*>(w0 + (long long)16 * ldw + c));
+  for (int i = 0; i < KB; ++i) {
+    const int kb = t.kb0 + i;
+    const bool valid = t.active && kb < t.kb1 && kb * 32 + 8 * tg < K;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    w.a[i][0] = valid ? __ldg(reinterpret_cast<const uint4*>(w0 + kb * 32)) : z;
+    w.a[i][1] = valid ? __ldg(reinterpret_cast<const uint4*>(w0 + (long long)8 * ldw + kb * 32)) : z;
+    if (PAIR) {
+      w.g[i][0] = valid ? __ldg(reinterpret_cast<const uint4*>(w0 + (long long)16 * ldw + kb * 32)) : z;
+      w.g[i][1] = valid ? __ldg(reinterpret_cast<const uint4*>(w0 + (long long)24 * ldw + kb * 32)) : z;
     }
   }
 }
 
-// All threads of the CTA must call this (it contains __syncthreads when S > 1).
-template <bool PAIR>
-__device__ __forceinline__ void gemv_run(const WPre& wp, const bf16* __restrict__ W, int ldw, int N, int K, int S,
-                                         const bf16* As, int lda_s, int B, float* red, const GemvOut& o, int gwarp,
-                                         int total_warps, int warp, int lane) {
-  const int ntasks = N * S;
-  const int rounds = (ntasks + total_warps - 1) / total_warps;
-  const int slice = gemv_slice(K, S);
+__device__ __forceinline__ void gemv_emit(const GemvOut& o, int tile, int e, float v, float gt, bool pair, int B,
+                                          int ncols) {
+  const int nt = e >> 7, ln = (e & 127) >> 2, r = e & 3;
+  const int row = (ln >> 2) + ((r & 2) ? 8 : 0);
+  const int n = nt * 8 + 2 * (ln & 3) + (r & 1);
+  const int col = tile * 16 + row;
+  if (n >= B || col >= ncols) return;
+  if (pair) v = v * gelu_erf(gt);
+  else if (o.bias != nullptr) v += o.bias[col];
+  if (o.f32 != nullptr) o.f32[(long long)n * o.ld + col] = v;
+  if (o.b16 != nullptr) o.b16[(long long)n * o.ld + col] = __float2bfloat16(v);
+}
+
+// All threads of the CTA must call this (it contains __syncthreads when S > 1).  ncols = valid output columns.
+template <int NT, int KB, bool PAIR>
+__device__ __forceinline__ void gemv_run(const WPre<KB, PAIR>& wp, const bf16* __restrict__ W, int ldw, int ntiles,
+                                         int ncols, int K, int S, const bf16* As, int lda_s, int B, float* red,
+                                         const GemvOut& o, int gwarp, int total_warps, int warp, int lane) {
+  const int rounds = (ntiles * S + total_warps - 1) / total_warps;
+  const int g = lane >> 2, tg = lane & 3;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   for (int r = 0; r < rounds; ++r) {
-    const int task = gwarp + r * total_warps;
-    const bool active = task < ntasks;
-    const int col = active ? task / S : 0, ks = active ? task - col * S : 0;
-    const int k0 = ks * slice, k1 = min(K, k0 + slice);
-    const int row = PAIR ? (col / 16) * 32 + (col % 16) : col;
-    const bf16* w0 = W + (long long)row * ldw;
-    for (int m0 = 0; m0 < B; m0 += DS_MR) {
-      float acc[DS_MR], accg[DS_MR];
+    const GemvTask t = gemv_task(gwarp + r * total_warps, ntiles, K, S);
+    float c[NT][4], cg[PAIR ? NT : 1][4];
 #pragma unroll
-      for (int b = 0; b < DS_MR; ++b) acc[b] = accg[b] = 0.f;
-      if (active) {
+    for (int n = 0; n < NT; ++n)
 #pragma unroll
-        for (int i = 0; i < DS_MAXC; ++i) {  // chunks whose weights were requested before the barrier (round 0)
-          const int c = k0 + (lane + 32 * i) * 8;
-          if (c < k1) {
-            uint4 wv = wp.v[i], wg = wp.g[i];
-            if (r != 0) {
-              wv = __ldg(reinterpret_cast<const uint4*>(w0 + c));
-              if (PAIR) wg = __ldg(reinterpret_cast<const uint4*>(w0 + (long long)16 * ldw + c));
-            }
+      for (int k = 0; k < 4; ++k) {
+        c[n][k] = 0.f;
+        if (PAIR) cg[n][k] = 0.f;
+      }
+    if (t.active) {
+      const bf16* w0 = W + (long long)(t.tile * (PAIR ? 32 : 16) + g) * ldw + 8 * tg;
+      auto step = [&](const uint4& a0, const uint4& a1, const uint4& g0, const uint4& g1, int kk) {
 #pragma unroll
-            for (int b = 0; b < DS_MR; ++b)
-              if (m0 + b < B) {
-                const uint4 av = *reinterpret_cast<const uint4*>(As + (m0 + b) * lda_s + c);
-                acc[b] += dot8f(av, wv);
-                if (PAIR) accg[b] += dot8f(av, wg);
-              }
+        for (int n = 0; n < NT; ++n) {
+          const int row = n * 8 + g;
+          const uint4 av = (row < B && kk < K) ? *reinterpret_cast<const uint4*>(As + row * lda_s + kk) : z;
+          mma_bf16_16x8x16(c[n], a0.x, a1.x, a0.y, a1.y, av.x, av.y);
+          mma_bf16_16x8x16(c[n], a0.z, a1.z, a0.w, a1.w, av.z, av.w);
+          if (PAIR) {
+            mma_bf16_16x8x16(cg[n], g0.x, g1.x, g0.y, g1.y, av.x, av.y);
+            mma_bf16_16x8x16(cg[n], g0.z, g1.z, g0.w, g1.w, av.z, av.w);
           }
         }
-        for (int c = k0 + (lane + 32 * DS_MAXC) * 8; c < k1; c += 256) {  // longer slices: stream the rest
-          const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w0 + c));
-          uint4 wg = make_uint4(0u, 0u, 0u, 0u);
-          if (PAIR) wg = __ldg(reinterpret_cast<const uint4*>(w0 + (long long)16 * ldw + c));
+      };
+      if (r == 0) {
 #pragma unroll
-          for (int b = 0; b < DS_MR; ++b)
-            if (m0 + b < B) {
-              const uint4 av = *reinterpret_cast<const uint4*>(As + (m0 + b) * lda_s + c);
-              acc[b] += dot8f(av, wv);
-              if (PAIR) accg[b] += dot8f(av, wg);
-            }
-        }
+        for (int i = 0; i < KB; ++i)
+          if (t.kb0 + i < t.kb1) step(wp.a[i][0], wp.a[i][1], wp.g[PAIR ? i : 0][0], wp.g[PAIR ? i : 0][1], (t.kb0 + i) * 32 + 8 * tg);
       }
-      float mine = 0.f, mineg = 0.f;
-#pragma unroll
-      for (int b = 0; b < DS_MR; ++b) {
-        const float v = warp_sum(acc[b]);
-        const float g = PAIR ? warp_sum(accg[b]) : 0.f;
-        if (lane == b) { mine = v; mineg = g; }
-      }
-      if (S > 1) {
-        if (lane < DS_MR) {
-          red[(warp * 2 + 0) * DS_MR + lane] = mine;
-          red[(warp * 2 + 1) * DS_MR + lane] = mineg;
-        }
-        __syncthreads();
-        if (ks == 0 && lane < DS_MR) {
-          for (int s2 = 1; s2 < S; ++s2) {
-            mine += red[((warp + s2) * 2 + 0) * DS_MR + lane];
-            mineg += red[((warp + s2) * 2 + 1) * DS_MR + lane];
-          }
-        }
-        __syncthreads();
-      }
-      if (active && ks == 0 && lane < DS_MR && m0 + lane < B) {
-        const long long m = m0 + lane;
-        float v = mine;
+      for (int kb = t.kb0 + (r == 0 ? KB : 0); kb < t.kb1; ++kb) {  // beyond the prefetched blocks / later rounds
+        const int kk = kb * 32 + 8 * tg;
+        const bool valid = kk < K;
+        const uint4 a0 = valid ? __ldg(reinterpret_cast<const uint4*>(w0 + kb * 32)) : z;
+        const uint4 a1 = valid ? __ldg(reinterpret_cast<const uint4*>(w0 + (long long)8 * ldw + kb * 32)) : z;
+        uint4 g0 = z, g1 = z;
         if (PAIR) {
-          v = v * gelu_erf(mineg);
-        } else if (o.bias != nullptr) {
-          v += __ldg(o.bias + col);
+          g0 = valid ? __ldg(reinterpret_cast<const uint4*>(w0 + (long long)16 * ldw + kb * 32)) : z;
+          g1 = valid ? __ldg(reinterpret_cast<const uint4*>(w0 + (long long)24 * ldw + kb * 32)) : z;
         }
-        if (o.f32 != nullptr) o.f32[m * o.ld + col] = v;
-        if (o.b16 != nullptr) o.b16[m * o.ld + col] = __float2bfloat16(v);
+        step(a0, a1, g0, g1, kk);
       }
+    }
+    if (S == 1) {
+      if (t.active) {
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) gemv_emit(o, t.tile, n * 128 + lane * 4 + k, c[n][k], PAIR ? cg[n][k] : 0.f, PAIR, B, ncols);
+      }
+    } else {
+      // partial tiles -> shared memory: red[warp][value|gate][NT*128]
+      if (warp < DS_WWARPS) {
+        float* mine = red + (size_t)warp * 2 * NT * 128;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          *reinterpret_cast<float4*>(mine + n * 128 + lane * 4) = make_float4(c[n][0], c[n][1], c[n][2], c[n][3]);
+          if (PAIR) *reinterpret_cast<float4*>(mine + NT * 128 + n * 128 + lane * 4) = make_float4(cg[n][0], cg[n][1], cg[n][2], cg[n][3]);
+        }
+      }
+      __syncthreads();
+      const int tiles_here = DS_WWARPS / S;  // tiles of this CTA in this round
+      const int first_task = blockIdx.x * DS_WWARPS + r * total_warps;
+      for (int idx = threadIdx.x; idx < tiles_here * NT * 128; idx += DS_THREADS) {
+        const int tl = idx / (NT * 128), e = idx - tl * NT * 128;
+        const int task0 = first_task + tl * S;
+        if (task0 < ntiles * S) {
+          float v = 0.f, gt = 0.f;
+          for (int s2 = 0; s2 < S; ++s2) {
+            const float* src = red + (size_t)(tl * S + s2) * 2 * NT * 128;
+            v += src[e];
+            if (PAIR) gt += src[NT * 128 + e];
+          }
+          gemv_emit(o, task0 / S, e, v, gt, PAIR, B, ncols);
+        }
+      }
+      __syncthreads();
     }
   }
 }
@@ -272,14 +328,14 @@ __device__ __forceinline__ void ds_row_stats(const float4 (&v)[DS_LNV], int nv, 
   rstd = rsqrtf(q / (float)D + 1e-5f);
 }
 
-// Requested BEFORE the barrier that precedes the norms (cp.async, L2 -> shared memory, no registers held):
+// Requested well before the barrier that precedes the norms (cp.async, L2 -> shared memory, no registers held):
 // lnp[0..1] = post-norm weight / bias of `prev`, lnp[2..3] = pre-norm weight / bias of `cur` (w2 / b2 when cur is
-// NULL: the final StableLayerNorm), shs[b][0:D/2] = the two shifted channel quarters of ShiftVideoTokens, taken from
-// the pre-norm rows of positions t - fmap and t - 1 (zeros at the grid border).
+// NULL: the final StableLayerNorm), shs[b][0:D/2] = the two shifted channel quarters of ShiftVideoTokens, taken from the pre-norm rows of positions t - fmap and t - 1 (zeros at the grid border).
+// Commits exactly one cp.async group.
 __device__ __forceinline__ void prefetch_norms(const DecParams& p, const DecSub* prev, const DecSub* cur, const float* w2,
                                                const float* b2, int t, float* lnp, bf16* shs) {
   const int D = p.D, D4 = D / 4;
-  for (int i = threadIdx.x; i < 4 * D4; i += DS_THREADS) {
+  for (int i = ds_wtid(); i < 4 * D4; i += DS_WORK) {
     const int arr = i / D4, k = i - arr * D4;
     const float* src = arr == 0 ? (prev ? prev->post_w : nullptr)
                      : arr == 1 ? (prev ? prev->post_b : nullptr)
@@ -294,7 +350,7 @@ __device__ __forceinline__ void prefetch_norms(const DecParams& p, const DecSub*
     const int src_h = row > 0 ? t - p.fmap : -1, src_w = col > 0 ? t - 1 : -1;
     const int q4 = D / 4, qp = D / 32;  // 16-byte pieces per channel quarter (bf16)
     const bf16* sc = reinterpret_cast<const bf16*>(cur->shift_cache);
-    for (int i = threadIdx.x; i < p.B * 2 * qp; i += DS_THREADS) {
+    for (int i = ds_wtid(); i < p.B * 2 * qp; i += DS_WORK) {
       const int b = i / (2 * qp), r = i - b * 2 * qp;
       const int quarter = r / qp, k = r - quarter * qp;
       const int src = quarter == 0 ? src_h : src_w;
@@ -308,7 +364,7 @@ __device__ __forceinline__ void prefetch_norms(const DecParams& p, const DecSub*
 
 // prev != NULL:  streams[prev->write] += LayerNorm_post(y)        (SandwichNorm tail + residual)
 // cur  != NULL:  As = bf16(LayerNorm_pre(streams[cur->read])) with the ShiftVideoTokens gather
-// Needs prefetch_norms(prev, cur) to have been issued; waits for it here.
+// The norm parameters (prefetch_norms) must be the OLDEST pending cp.async group but one.
 __device__ __forceinline__ void ln_prologue(const DecParams& p, const DecSub* prev, const DecSub* cur, int t, float* streams,
                                             bf16* As, int lda_s, const float* lnp, const bf16* shs, int warp, int lane) {
   const int D = p.D, B = p.B;
@@ -317,16 +373,17 @@ __device__ __forceinline__ void ln_prologue(const DecParams& p, const DecSub* pr
 #pragma unroll
   for (int i = 0; i < DS_LNV; ++i)
     if ((lane + 32 * i) * 4 < D) nv = i + 1;
-  if (warp < B && prev != nullptr) {  // the only loads that had to wait for the barrier
+  auto load_y = [&](int b) {
 #pragma unroll
     for (int i = 0; i < DS_LNV; ++i)
-      if (i < nv) v[i] = __ldcg(reinterpret_cast<const float4*>(p.y + (long long)warp * D + (lane + 32 * i) * 4));
-  }
-  cp_async_wait_all();
+      if (i < nv) v[i] = __ldcg(reinterpret_cast<const float4*>(p.y + (long long)b * D + (lane + 32 * i) * 4));
+  };
+  if (warp < B && prev != nullptr) load_y(warp);  // the only loads that had to wait for the barrier
+  cp_async_wait<1>();
   __syncthreads();
-  if (warp < B) {
-    const int b = warp;
+  for (int b = warp; b < B; b += DS_WARPS) {
     if (prev != nullptr) {
+      if (b != warp) load_y(b);
       float* st = streams + ((long long)prev->write * B + b) * D;
       float mean, rstd;
       ds_row_stats(v, nv, D, mean, rstd);
@@ -383,8 +440,7 @@ __device__ __forceinline__ void ln_prologue(const DecParams& p, const DecSub* pr
 __device__ __forceinline__ void stable_ln_rows(const DecParams& p, const float* streams, bf16* As, int lda_s,
                                                const float* lnp, int warp, int lane) {
   const int D = p.D, B = p.B;
-  if (warp < B) {
-    const int b = warp;
+  for (int b = warp; b < B; b += DS_WARPS) {
     float4 v[DS_LNV];
     int nv = 0;
     float mx = -FLT_MAX;
@@ -432,7 +488,7 @@ __device__ __forceinline__ void stable_ln_rows(const DecParams& p, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// attention pieces (one query row per sample)
+// attention pieces (one query row per sample); K / V rows are read from shared memory
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int key3dna(const DecParams& p, const DecSub& s, int t, int nv, int j, int& row) {
   if (j == 0) { row = 0; return DK_NORMAL; }
@@ -457,33 +513,21 @@ __device__ __forceinline__ float dot8q(const float* q, const uint4& u) {
   return q0.x * a.x + q0.y * a.y + q0.z * b2.x + q0.w * b2.y + q1.x * c.x + q1.y * c.y + q1.z * d.x + q1.w * d.y;
 }
 
-// scores of heads [0, nh) (pointers already offset to the first head): S[hl*J + j].  DH8 = dh / 8 as a compile-time
-// constant puts every 16-byte load of a key row in flight at once (0 = runtime head width).
-template <int DH8>
-__device__ __forceinline__ void attn_scores(const float* qs, const int* keys, const bf16* kbase, int k_rs,
-                                            const float* null_k, int nh, int dh, int J, float* S) {
+// scores of heads [0, nh): S[hl*J + j] = q[hl] . K_j[hl]; key slot j is staged at Ks + j * rs (bytes); null_k fp32 (smem)
+__device__ __forceinline__ void attn_scores(const float* qs, const int* keys, const uint8_t* Ks, int rs, const float* null_k,
+                                            int nh, int dh, int J, float* S) {
   for (int item = threadIdx.x; item < nh * J; item += DS_THREADS) {
     const int hl = item / J, j = item - hl * J;
-    const int kj = keys[j];
-    const int row = kj & 0x0FFFFFFF, kind = kj >> 28;
+    const int kind = keys[j] >> 28;
     const float* q = qs + hl * dh;
     float s;
     if (kind == DK_NORMAL) {
-      const uint4* kr = reinterpret_cast<const uint4*>(kbase + (long long)row * k_rs + hl * dh);
+      const uint4* kr = reinterpret_cast<const uint4*>(Ks + (size_t)j * rs + hl * dh * 2);
       s = 0.f;
-      if (DH8 > 0) {
-        uint4 u[DH8 > 0 ? DH8 : 1];
-#pragma unroll
-        for (int i = 0; i < DH8; ++i) u[i] = __ldcg(kr + i);
-#pragma unroll
-        for (int i = 0; i < DH8; ++i) s += dot8q(q + i * 8, u[i]);
-      } else {
-        for (int i = 0; i < dh / 8; ++i) s += dot8q(q + i * 8, __ldcg(kr + i));
-      }
+      for (int i = 0; i < dh / 8; ++i) s += dot8q(q + i * 8, kr[i]);
     } else if (kind == DK_NULL) {
-      const float* nk = null_k + hl * dh;
       s = 0.f;
-      for (int i = 0; i < dh; ++i) s += q[i] * __ldg(nk + i);
+      for (int i = 0; i < dh; ++i) s += q[i] * null_k[hl * dh + i];
     } else {
       s = (kind == DK_MASKED) ? -FLT_MAX : 0.f;
     }
@@ -510,9 +554,8 @@ __device__ __forceinline__ void attn_softmax(float* S, int nh, int J, int warp, 
   }
 }
 
-// out[hl*dh + c] = sum_j P[hl*J + j] * V[row_j][hl*dh + c]   for heads [0, nh) (vbase / null_v offset to the first head).
-// Branch-free key loop (masked / zero / null keys load row 0 with weight 0) so that the unrolled loads overlap.
-__device__ __forceinline__ void attn_pv(const float* P, const int* keys, const bf16* vbase, int v_rs, const float* null_v,
+// out[hl*dh + c] = sum_j P[hl*J + j] * V_j[hl*dh + c]   for heads [0, nh); V slot j staged at Vs + j * rs (bytes)
+__device__ __forceinline__ void attn_pv(const float* P, const int* keys, const uint8_t* Vs, int rs, const float* null_v,
                                         int nh, int dh, int J, float* part, float* outs) {
   const int npairs = nh * dh / 2;
   const int KG = DS_THREADS / npairs;  // key groups (>= 1: H*dh <= 1024)
@@ -520,37 +563,19 @@ __device__ __forceinline__ void attn_pv(const float* P, const int* keys, const b
   if (kg < KG) {
     const int hl = cp / (dh / 2), c2 = cp - hl * (dh / 2);
     const float* Ph = P + hl * J;
-    const bf16* vcol = vbase + hl * dh + 2 * c2;
+    const uint8_t* vcol = Vs + (hl * dh + 2 * c2) * 2;
     float ax = 0.f, ay = 0.f;
-    int j = kg;
-    for (; j + 7 * KG < J; j += 8 * KG) {
-      uint32_t u[8];
-      float pj[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int kj = keys[j + k * KG];
-        const bool normal = (kj >> 28) == DK_NORMAL;
-        u[k] = __ldcg(reinterpret_cast<const unsigned int*>(vcol + (long long)(normal ? (kj & 0x0FFFFFFF) : 0) * v_rs));
-        pj[k] = normal ? Ph[j + k * KG] : 0.f;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float2 v = unpack_bf16x2(u[k]);
-        ax = fmaf(pj[k], v.x, ax);
-        ay = fmaf(pj[k], v.y, ay);
-      }
-    }
-    for (; j < J; j += KG) {
-      const int kj = keys[j];
-      if ((kj >> 28) == DK_NORMAL) {
-        const float2 v = unpack_bf16x2(__ldcg(reinterpret_cast<const unsigned int*>(vcol + (long long)(kj & 0x0FFFFFFF) * v_rs)));
+#pragma unroll 4
+    for (int j = kg; j < J; j += KG) {
+      const int kind = keys[j] >> 28;
+      if (kind == DK_NORMAL) {
+        const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vcol + (size_t)j * rs));
         ax = fmaf(Ph[j], v.x, ax);
         ay = fmaf(Ph[j], v.y, ay);
+      } else if (kind == DK_NULL) {
+        ax = fmaf(Ph[j], null_v[hl * dh + 2 * c2], ax);
+        ay = fmaf(Ph[j], null_v[hl * dh + 2 * c2 + 1], ay);
       }
-    }
-    if (kg == 0 && (keys[0] >> 28) == DK_NULL) {  // the learned null key / value is slot 0
-      ax = fmaf(Ph[0], __ldg(null_v + hl * dh + 2 * c2), ax);
-      ay = fmaf(Ph[0], __ldg(null_v + hl * dh + 2 * c2 + 1), ay);
     }
     part[(kg * npairs + cp) * 2 + 0] = ax;
     part[(kg * npairs + cp) * 2 + 1] = ay;
@@ -568,23 +593,64 @@ __device__ __forceinline__ void attn_pv(const float* P, const int* keys, const b
   __syncthreads();
 }
 
-__device__ __forceinline__ void attn_scores_any(const float* qs, const int* keys, const bf16* kbase, int k_rs,
-                                                const float* null_k, int nh, int dh, int J, float* S) {
-  if (dh == 64) attn_scores<8>(qs, keys, kbase, k_rs, null_k, nh, dh, J, S);
-  else if (dh == 32) attn_scores<4>(qs, keys, kbase, k_rs, null_k, nh, dh, J, S);
-  else attn_scores<0>(qs, keys, kbase, k_rs, null_k, nh, dh, J, S);
-}
-
-// key list of the dense cross attention: slot 0 = learned null key, slot 1 + i = context token i (masked by key_mask)
-__device__ __forceinline__ void cross_keys(const DecParams& p, int b, int J, int* keys) {
-  for (int j = threadIdx.x; j < J; j += DS_THREADS) {
-    int kd = DK_NULL, row = 0;
-    if (j > 0) {
-      row = j - 1;
-      kd = (p.key_mask != nullptr && p.key_mask[(long long)b * p.mask_bs + row] == 0) ? DK_MASKED : DK_NORMAL;
+// K / V prefetch of a sub-block's attention (cp.async; consumed two barriers later).  Commits exactly one group.
+//   3DNA:  CTA b < B stages the window rows of sample b that earlier steps wrote (row t, the new token, comes later)
+//   cross: CTA w < B*H stages the context K and V slices of its (sample, head), the head's null key / value
+//   both:  the talking-heads matrix; 3DNA (every CTA): the to_out bias
+__device__ __forceinline__ void prefetch_kv(const DecParams& p, const DecSub* s, const DsLayout& L, uint8_t* smem, int t) {
+  const int H = p.H, dh = p.dh, inner = H * dh;
+  if (s->kind == NUWA_DEC_3DNA) {
+    if (s->b_out != nullptr)  // every CTA adds the to_out bias in phase 3
+      for (int i = ds_wtid(); i < p.D / 4; i += DS_WORK) cp_async16(smem + L.bias + i * 16, s->b_out + i * 4);
+    if ((int)blockIdx.x < p.B && t > 0) {
+      const int b = blockIdx.x;
+      int* keys = reinterpret_cast<int*>(smem + L.keys);
+      const int J = 1 + s->kt * s->kh * s->kw;
+      for (int j = threadIdx.x; j < J; j += DS_THREADS) {
+        int row = 0;
+        const int kd = key3dna(p, *s, t, t, j, row);
+        keys[j] = (kd << 28) | row;
+      }
+      __syncthreads();
+      const bf16* cb = reinterpret_cast<const bf16*>(s->cache) + (long long)b * p.npos * 3 * inner;
+      uint8_t* Ks = smem + L.kvs;
+      uint8_t* Vs = Ks + (size_t)J * L.kv_rs3;
+      const int pieces = inner / 8;  // 16-byte pieces per row
+      for (int i = ds_wtid(); i < J * 2 * pieces; i += DS_WORK) {
+        const int j = i / (2 * pieces), r = i - j * 2 * pieces;
+        const int kv = r / pieces, k = r - kv * pieces;
+        const int kj = keys[j];
+        const int row = kj & 0x0FFFFFFF;
+        if ((kj >> 28) == DK_NORMAL && row != t)
+          cp_async16((kv ? Vs : Ks) + (size_t)j * L.kv_rs3 + k * 16, cb + (long long)row * 3 * inner + (1 + kv) * inner + k * 8);
+      }
+      for (int i = ds_wtid(); i < H * H / 4; i += DS_WORK)
+        cp_async16(smem + L.wt + i * 16, s->talk + i * 4);
     }
-    keys[j] = (kd << 28) | row;
+  } else if (s->kind == NUWA_DEC_CROSS) {
+    if ((int)blockIdx.x < p.B * H) {
+      const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+      const int* ckeys = reinterpret_cast<const int*>(smem + L.ckeys);
+      const bf16* kv = reinterpret_cast<const bf16*>(s->cache) + (long long)b * p.nk * 2 * inner + h * dh;
+      uint8_t* Ks = smem + L.kvs;
+      uint8_t* Vs = Ks + (size_t)p.nk * L.kv_rsx;
+      const int pieces = dh / 8;
+      for (int i = ds_wtid(); i < p.nk * 2 * pieces; i += DS_WORK) {
+        const int row = i / (2 * pieces), r = i - row * 2 * pieces;
+        const int sel = r / pieces, k = r - sel * pieces;
+        if ((ckeys[row + 1] >> 28) == DK_NORMAL)
+          cp_async16((sel ? Vs : Ks) + (size_t)row * L.kv_rsx + k * 16, kv + (long long)row * 2 * inner + sel * inner + k * 8);
+      }
+      float* nkv = reinterpret_cast<float*>(smem + L.nullkv);
+      for (int i = ds_wtid(); i < 2 * (dh / 4); i += DS_WORK) {
+        const int sel = i / (dh / 4), k = i - sel * (dh / 4);
+        cp_async16(nkv + sel * dh + k * 4, (sel ? s->null_v : s->null_k) + h * dh + k * 4);
+      }
+      for (int i = ds_wtid(); i < H * H / 4; i += DS_WORK)
+        cp_async16(smem + L.wt + i * 16, s->talk + i * 4);
+    }
   }
+  cp_async_commit();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -599,210 +665,249 @@ __device__ __forceinline__ void cross_keys(const DecParams& p, int b, int J, int
     }                                                                           \
   } while (0)
 
+template <int NT>
 __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecParams p) {
   extern __shared__ __align__(16) uint8_t ds_smem[];
   const int B = p.B, D = p.D, H = p.H, dh = p.dh, inner = H * dh;
-  const DsLayout L = ds_layout(B, D, p.kmax, H, dh, p.jmax);
+  const DsLayout L = ds_layout(B, D, p.kmax, H, dh, p.j3max, p.nk);
   float* streams = reinterpret_cast<float*>(ds_smem + L.streams);
   bf16* As = reinterpret_cast<bf16*>(ds_smem + L.act);
   float* red = reinterpret_cast<float*>(ds_smem + L.red);
   float* Ss = reinterpret_cast<float*>(ds_smem + L.S);
   float* Pm = reinterpret_cast<float*>(ds_smem + L.pm);
   int* keys = reinterpret_cast<int*>(ds_smem + L.keys);
+  int* ckeys = reinterpret_cast<int*>(ds_smem + L.ckeys);
   float* qs = reinterpret_cast<float*>(ds_smem + L.qs);
   float* Wt = reinterpret_cast<float*>(ds_smem + L.wt);
   float* part = reinterpret_cast<float*>(ds_smem + L.part);
   float* outs = reinterpret_cast<float*>(ds_smem + L.outs);
   float* lnp = reinterpret_cast<float*>(ds_smem + L.lnp);
   bf16* shs = reinterpret_cast<bf16*>(ds_smem + L.shs);
+  float* nullkv = reinterpret_cast<float*>(ds_smem + L.nullkv);
+  uint8_t* kvs = ds_smem + L.kvs;
   constexpr int DESC_STRIDE = (sizeof(DecSub) + 15) & ~15;
   constexpr int DESC_WORDS = sizeof(DecSub) / 4;
   const int lda_s = p.kmax;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gwarp = blockIdx.x * DS_WARPS + warp;
-  const int total_warps = gridDim.x * DS_WARPS;
+  const int gwarp = warp < DS_WWARPS ? blockIdx.x * DS_WWARPS + warp : (1 << 28);  // the sync warp takes no tasks
+  const int total_warps = gridDim.x * DS_WWARPS;
   const int t = __ldg(p.t_ptr);
   const float qscale = rsqrtf((float)dh);
   const int dbg = p.debug_flags;
+  const int S16 = p.split_small;  // K slices of the D- / inner-wide products
   GridBar bar{p.barrier, gridDim.x, 0u};
   bf16* act = reinterpret_cast<bf16*>(p.act);
   bf16* actq = reinterpret_cast<bf16*>(p.actq);
   int nstamp = 0;
   int si = 0;
 
-  // X = x (plain) or [x, x] (reversible.py:133); descriptor of the first sub-block
+  // X = x (plain) or [x, x] (reversible.py:133); descriptors of the first two sub-blocks; cross-attention key list
   for (int i = threadIdx.x; i < B * D; i += DS_THREADS) {
     const float v = __ldg(p.x_in + i);
     streams[i] = v;
     if (p.reversible) streams[B * D + i] = v;
   }
-  if (threadIdx.x < DESC_WORDS)
+  if (threadIdx.x < DESC_WORDS) {
     reinterpret_cast<uint32_t*>(ds_smem + L.desc)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(p.subs) + threadIdx.x);
+    if (p.nsubs > 1)
+      reinterpret_cast<uint32_t*>(ds_smem + L.desc + DESC_STRIDE)[threadIdx.x] =
+          __ldg(reinterpret_cast<const uint32_t*>(p.subs + 1) + threadIdx.x);
+  }
+  if (p.nk > 0 && (int)blockIdx.x < B * H) {
+    const int b = blockIdx.x / H;
+    for (int j = threadIdx.x; j <= p.nk; j += DS_THREADS) {
+      int kd = DK_NULL, row = 0;
+      if (j > 0) {
+        row = j - 1;
+        kd = (p.key_mask != nullptr && p.key_mask[(long long)b * p.mask_bs + row] == 0) ? DK_MASKED : DK_NORMAL;
+      }
+      ckeys[j] = (kd << 28) | row;
+    }
+  }
   __syncthreads();
+  {
+    const DecSub* s0 = reinterpret_cast<const DecSub*>(ds_smem + L.desc);
+    prefetch_norms(p, nullptr, s0, nullptr, nullptr, t, lnp, shs);
+  }
   DS_STAMP(0);
 
   const DecSub* prev = nullptr;
   for (si = 0; si < p.nsubs; ++si) {
-    const DecSub* s = reinterpret_cast<const DecSub*>(ds_smem + L.desc + (si % 3) * DESC_STRIDE);
-    // descriptor of the NEXT sub-block: requested now, parked in shared memory after the first barrier wait
+    const DecSub* s = reinterpret_cast<const DecSub*>(ds_smem + L.desc + (si % 4) * DESC_STRIDE);
+    const DecSub* nxt = si + 1 < p.nsubs ? reinterpret_cast<const DecSub*>(ds_smem + L.desc + ((si + 1) % 4) * DESC_STRIDE) : nullptr;
+    // descriptor of sub-block si + 2: requested now, parked in shared memory after the first barrier wait
     uint32_t next_word = 0;
-    const bool has_next = si + 1 < p.nsubs && threadIdx.x < DESC_WORDS;
-    if (has_next) next_word = __ldg(reinterpret_cast<const uint32_t*>(p.subs + si + 1) + threadIdx.x);
+    const bool has_next2 = si + 2 < p.nsubs && threadIdx.x < DESC_WORDS;  // worker warps 0-1
+    if (has_next2) next_word = __ldg(reinterpret_cast<const uint32_t*>(p.subs + si + 2) + threadIdx.x);
     const int kind = s->kind;
-    WPre wp;
-    // ---- phase 1: (post-norm + residual of the previous sub-block,) pre-norm, first product ----
-    int N1, S1;
-    if (kind == NUWA_DEC_3DNA) { N1 = 3 * inner; S1 = 1; }
-    else if (kind == NUWA_DEC_CROSS) { N1 = inner; S1 = p.split_small; }
-    else { N1 = s->ip; S1 = 1; }
     const bf16* Wa = reinterpret_cast<const bf16*>(s->w_a);
     const bf16* Wb = reinterpret_cast<const bf16*>(s->w_b);
-    if (kind == NUWA_DEC_FF) gemv_prefetch<true>(wp, Wa, D, N1, D, S1, gwarp, lane);
-    else gemv_prefetch<false>(wp, Wa, D, N1, D, S1, gwarp, lane);
-    prefetch_norms(p, prev, s, nullptr, nullptr, t, lnp, shs);
-    DS_STAMP(1);
-    if (prev != nullptr) grid_barrier(bar);  // y of the previous sub-block is complete
-    DS_STAMP(2);
-    if (has_next)
-      reinterpret_cast<uint32_t*>(ds_smem + L.desc + ((si + 1) % 3) * DESC_STRIDE)[threadIdx.x] = next_word;
-    if (!(dbg & 1)) ln_prologue(p, prev, s, t, streams, As, lda_s, lnp, shs, warp, lane);
-    else { cp_async_wait_all(); __syncthreads(); }
-    DS_STAMP(3);
+    // cp.async groups in commit order: norms(si) [during si-1], kv(si) [top of si], norms(si+1) [after the norms of si];
+    // each consumer waits with wait_group 1 = everything but the most recent group
+    auto phase1 = [&]() {
+      prefetch_kv(p, s, L, ds_smem, t);
+      DS_STAMP(1);
+      if (prev != nullptr) grid_barrier(bar);  // y of the previous sub-block is complete
+      DS_STAMP(2);
+      if (has_next2)
+        reinterpret_cast<uint32_t*>(ds_smem + L.desc + ((si + 2) % 4) * DESC_STRIDE)[threadIdx.x] = next_word;
+      if (!(dbg & 1)) ln_prologue(p, prev, s, t, streams, As, lda_s, lnp, shs, warp, lane);
+      else { cp_async_wait<1>(); __syncthreads(); }
+      // norm parameters of the NEXT sub-block (or of the final StableLayerNorm): >= two barriers ahead of their use
+      prefetch_norms(p, s, nxt, p.norm_w, p.norm_b, t, lnp, shs);
+      DS_STAMP(3);
+    };
     if (kind == NUWA_DEC_3DNA) {
+      WPre<1, false> wa;
+      gemv_prefetch(wa, Wa, D, 3 * inner / 16, D, S16, gwarp, lane);
+      phase1();
       // q|k|v of the new token go straight into row t of the cache
       bf16* cache = reinterpret_cast<bf16*>(s->cache);
       GemvOut o{nullptr, cache + (long long)t * 3 * inner, (long long)p.npos * 3 * inner, nullptr};
-      if (!(dbg & 2)) gemv_run<false>(wp, Wa, D, N1, D, S1, As, lda_s, B, red, o, gwarp, total_warps, warp, lane);
-      gemv_prefetch<false>(wp, Wb, inner, D, inner, p.split_small, gwarp, lane);
-      for (int i = threadIdx.x; i < H * H; i += DS_THREADS) Wt[i] = __ldg(s->talk + i);
+      if (!(dbg & 2)) gemv_run<NT>(wa, Wa, D, 3 * inner / 16, 3 * inner, D, S16, As, lda_s, B, red, o, gwarp, total_warps, warp, lane);
+      WPre<1, false> wb;
+      gemv_prefetch(wb, Wb, inner, D / 16, inner, S16, gwarp, lane);
       DS_STAMP(4);
       grid_barrier(bar);
       DS_STAMP(5);
       // ---- phase 2: attention, one CTA per sample (all heads: talking heads mix across heads) ----
-      if (!(dbg & 4))
-      for (int b = blockIdx.x; b < B; b += gridDim.x) {
+      if (!(dbg & 4) && (int)blockIdx.x < B) {
+        const int b = blockIdx.x;
         const bf16* cb = cache + (long long)b * p.npos * 3 * inner;
         if (t == 0) {  // bos attends only to itself (:499,608)
           for (int c = threadIdx.x; c < inner; c += DS_THREADS) act[(long long)b * inner + c] = __ldcg(cb + 2 * inner + c);
-          continue;
-        }
-        const int J = 1 + s->kt * s->kh * s->kw;
-        for (int j = threadIdx.x; j < J; j += DS_THREADS) {
-          int row = 0;
-          const int kd = key3dna(p, *s, t, t, j, row);
-          keys[j] = (kd << 28) | row;
-        }
-        for (int c = threadIdx.x; c < inner; c += DS_THREADS)
-          qs[c] = __bfloat162float(__ldcg(cb + (long long)t * 3 * inner + c)) * qscale;
-        __syncthreads();
-        attn_scores_any(qs, keys, cb + inner, 3 * inner, nullptr, H, dh, J, Ss);
-        __syncthreads();
-        attn_softmax(Ss, H, J, warp, lane);
-        __syncthreads();
-        for (int j = threadIdx.x; j < J; j += DS_THREADS) {  // talking heads (:556-558)
-          float pin[16];
-          for (int h = 0; h < H; ++h) pin[h] = Ss[h * J + j];
-          for (int g = 0; g < H; ++g) {
-            float a = 0.f;
-            for (int h = 0; h < H; ++h) a = fmaf(Wt[g * H + h], pin[h], a);
-            Ss[g * J + j] = a;
+        } else {
+          const int J = 1 + s->kt * s->kh * s->kw;
+          uint8_t* Ks = kvs;
+          uint8_t* Vs = kvs + (size_t)J * L.kv_rs3;
+          // the new token's own q, and its k / v into their window slot(s)
+          for (int c = threadIdx.x; c < inner; c += DS_THREADS)
+            qs[c] = __bfloat162float(__ldcg(cb + (long long)t * 3 * inner + c)) * qscale;
+          const int pieces = inner / 8;
+          for (int i = threadIdx.x; i < J * 2 * pieces; i += DS_THREADS) {
+            const int j = i / (2 * pieces), r = i - j * 2 * pieces;
+            const int kv = r / pieces, k = r - kv * pieces;
+            const int kj = keys[j];
+            if ((kj >> 28) == DK_NORMAL && (kj & 0x0FFFFFFF) == t)
+              *reinterpret_cast<uint4*>((kv ? Vs : Ks) + (size_t)j * L.kv_rs3 + k * 16) =
+                  __ldcg(reinterpret_cast<const uint4*>(cb + (long long)t * 3 * inner + (1 + kv) * inner + k * 8));
           }
+          cp_async_wait<1>();
+          __syncthreads();
+          attn_scores(qs, keys, Ks, L.kv_rs3, nullptr, H, dh, J, Ss);
+          __syncthreads();
+          attn_softmax(Ss, H, J, warp, lane);
+          __syncthreads();
+          for (int j = threadIdx.x; j < J; j += DS_THREADS) {  // talking heads (:556-558)
+            float pin[16];
+            for (int h = 0; h < H; ++h) pin[h] = Ss[h * J + j];
+            for (int g = 0; g < H; ++g) {
+              float a = 0.f;
+              for (int h = 0; h < H; ++h) a = fmaf(Wt[g * H + h], pin[h], a);
+              Ss[g * J + j] = a;
+            }
+          }
+          __syncthreads();
+          attn_pv(Ss, keys, Vs, L.kv_rs3, nullptr, H, dh, J, part, outs);
+          for (int c = threadIdx.x; c < inner; c += DS_THREADS) act[(long long)b * inner + c] = __float2bfloat16(outs[c]);
         }
-        __syncthreads();
-        attn_pv(Ss, keys, cb + 2 * inner, 3 * inner, nullptr, H, dh, J, part, outs);
-        for (int c = threadIdx.x; c < inner; c += DS_THREADS) act[(long long)b * inner + c] = __float2bfloat16(outs[c]);
-        __syncthreads();
       }
       DS_STAMP(6);
       grid_barrier(bar);
       DS_STAMP(7);
       // ---- phase 3: to_out (+ bias) ----
+      cp_async_wait<1>();  // the bias (kv group); made visible by the CTA barrier inside stage_act
       stage_act(As, lda_s, act, inner, B, inner);
-      GemvOut o3{p.y, nullptr, (long long)D, s->b_out};
-      if (!(dbg & 2)) gemv_run<false>(wp, Wb, inner, D, inner, p.split_small, As, lda_s, B, red, o3, gwarp, total_warps, warp, lane);
+      GemvOut o3{p.y, nullptr, (long long)D, s->b_out != nullptr ? reinterpret_cast<const float*>(ds_smem + L.bias) : nullptr};
+      if (!(dbg & 2)) gemv_run<NT>(wb, Wb, inner, D / 16, D, inner, S16, As, lda_s, B, red, o3, gwarp, total_warps, warp, lane);
       DS_STAMP(12);
     } else if (kind == NUWA_DEC_CROSS) {
+      WPre<1, false> wa;
+      gemv_prefetch(wa, Wa, D, inner / 16, D, S16, gwarp, lane);
+      phase1();
       GemvOut o{nullptr, actq, (long long)inner, nullptr};
-      if (!(dbg & 2)) gemv_run<false>(wp, Wa, D, N1, D, S1, As, lda_s, B, red, o, gwarp, total_warps, warp, lane);
-      gemv_prefetch<false>(wp, Wb, inner, D, inner, p.split_small, gwarp, lane);
+      if (!(dbg & 2)) gemv_run<NT>(wa, Wa, D, inner / 16, inner, D, S16, As, lda_s, B, red, o, gwarp, total_warps, warp, lane);
+      WPre<1, false> wb;
+      gemv_prefetch(wb, Wb, inner, D / 16, inner, S16, gwarp, lane);
       DS_STAMP(4);
       grid_barrier(bar);
       DS_STAMP(5);
       const int J = p.nk + 1;
-      const bf16* kv = reinterpret_cast<const bf16*>(s->cache);
+      // slot j >= 1 of the key list is context row j - 1, staged at row j - 1 of Ks / Vs: shift the bases by one row
+      const uint8_t* Ks = kvs - L.kv_rsx;
+      const uint8_t* Vs = kvs + (size_t)p.nk * L.kv_rsx - L.kv_rsx;
+      const bool mine = (int)blockIdx.x < B * H;
+      const int b = blockIdx.x / H, h = blockIdx.x - b * H;
       // ---- phase 2a: scores of one (sample, head) per CTA ----
-      if (!(dbg & 4))
-      for (int w = blockIdx.x; w < B * H; w += gridDim.x) {
-        const int b = w / H, h = w - b * H;
-        cross_keys(p, b, J, keys);
+      if (!(dbg & 4) && mine) {
         for (int c = threadIdx.x; c < dh; c += DS_THREADS)
           qs[c] = __bfloat162float(__ldcg(actq + (long long)b * inner + h * dh + c)) * qscale;
+        cp_async_wait<1>();
         __syncthreads();
-        attn_scores_any(qs, keys, kv + (long long)b * p.nk * 2 * inner + h * dh, 2 * inner, s->null_k + h * dh, 1, dh, J, Ss);
+        attn_scores(qs, ckeys, Ks, L.kv_rsx, nullkv, 1, dh, J, Ss);
         __syncthreads();
         for (int j = threadIdx.x; j < J; j += DS_THREADS) p.scores[((long long)b * H + h) * J + j] = Ss[j];
-        __syncthreads();
       }
       DS_STAMP(6);
       grid_barrier(bar);
       DS_STAMP(7);
-      // ---- phase 2b: softmax of every head of the sample, talking-heads row g, PV of head g ----
-      if (!(dbg & 4))
-      for (int w = blockIdx.x; w < B * H; w += gridDim.x) {
-        const int b = w / H, g = w - b * H;
-        cross_keys(p, b, J, keys);
+      // ---- phase 2b: softmax of every head of the sample, talking-heads row h, PV of head h ----
+      if (!(dbg & 4) && mine) {
         for (int i = threadIdx.x; i < H * J; i += DS_THREADS) Ss[i] = __ldcg(p.scores + (long long)b * H * J + i);
-        for (int i = threadIdx.x; i < H; i += DS_THREADS) Wt[i] = __ldg(s->talk + g * H + i);
         __syncthreads();
         attn_softmax(Ss, H, J, warp, lane);
         __syncthreads();
         for (int j = threadIdx.x; j < J; j += DS_THREADS) {  // :372
           float a = 0.f;
-          for (int h = 0; h < H; ++h) a = fmaf(Wt[h], Ss[h * J + j], a);
+          for (int hh = 0; hh < H; ++hh) a = fmaf(Wt[h * H + hh], Ss[hh * J + j], a);
           Pm[j] = a;
         }
         __syncthreads();
-        attn_pv(Pm, keys, kv + (long long)b * p.nk * 2 * inner + inner + g * dh, 2 * inner, s->null_v + g * dh, 1, dh, J,
-                part, outs);
-        for (int c = threadIdx.x; c < dh; c += DS_THREADS) act[(long long)b * inner + g * dh + c] = __float2bfloat16(outs[c]);
-        __syncthreads();
+        attn_pv(Pm, ckeys, Vs, L.kv_rsx, nullkv + dh, 1, dh, J, part, outs);
+        for (int c = threadIdx.x; c < dh; c += DS_THREADS) act[(long long)b * inner + h * dh + c] = __float2bfloat16(outs[c]);
       }
       DS_STAMP(8);
       grid_barrier(bar);
       DS_STAMP(9);
       stage_act(As, lda_s, act, inner, B, inner);
       GemvOut o3{p.y, nullptr, (long long)D, nullptr};
-      if (!(dbg & 2)) gemv_run<false>(wp, Wb, inner, D, inner, p.split_small, As, lda_s, B, red, o3, gwarp, total_warps, warp, lane);
+      if (!(dbg & 2)) gemv_run<NT>(wb, Wb, inner, D / 16, D, inner, S16, As, lda_s, B, red, o3, gwarp, total_warps, warp, lane);
       DS_STAMP(12);
     } else {
-      // GEGLU product: value/gate pairs -> a * gelu(g) (:255-258)
-      GemvOut o{nullptr, act, (long long)s->ip, nullptr};
-      if (!(dbg & 2)) gemv_run<true>(wp, Wa, D, N1, D, S1, As, lda_s, B, red, o, gwarp, total_warps, warp, lane);
-      gemv_prefetch<false>(wp, Wb, s->ip, D, s->ip, p.split_ff, gwarp, lane);
+      // GEGLU product: value / gate tile pairs -> a * gelu(g) (:255-258)
+      const int ip = s->ip;
+      WPre<1, true> wa;
+      gemv_prefetch(wa, Wa, D, ip / 16, D, S16, gwarp, lane);
+      phase1();
+      GemvOut o{nullptr, act, (long long)ip, nullptr};
+      if (!(dbg & 2)) gemv_run<NT>(wa, Wa, D, ip / 16, ip, D, S16, As, lda_s, B, red, o, gwarp, total_warps, warp, lane);
+      WPre<7, false> wb;
+      gemv_prefetch(wb, Wb, ip, D / 16, ip, p.split_ff, gwarp, lane);
       DS_STAMP(4);
       grid_barrier(bar);
       DS_STAMP(5);
-      stage_act(As, lda_s, act, s->ip, B, s->ip);
+      stage_act(As, lda_s, act, ip, B, ip);
       GemvOut o3{p.y, nullptr, (long long)D, nullptr};
-      if (!(dbg & 2)) gemv_run<false>(wp, Wb, s->ip, D, s->ip, p.split_ff, As, lda_s, B, red, o3, gwarp, total_warps, warp, lane);
+      if (!(dbg & 2)) gemv_run<NT>(wb, Wb, ip, D / 16, D, ip, p.split_ff, As, lda_s, B, red, o3, gwarp, total_warps, warp, lane);
       DS_STAMP(12);
     }
     prev = s;
   }
   // ---- tail: last post-norm + residual, StableLayerNorm, logits ----
-  WPre wl;
+  WPre<3, false> wl;
   const bf16* Wl = reinterpret_cast<const bf16*>(p.w_logits);
-  if (Wl != nullptr) gemv_prefetch<false>(wl, Wl, D, p.V, D, 1, gwarp, lane);
-  prefetch_norms(p, prev, nullptr, p.norm_w, p.norm_b, t, lnp, shs);
+  if (Wl != nullptr) gemv_prefetch(wl, Wl, D, (p.V + 15) / 16, D, p.split_logits, gwarp, lane);
+  cp_async_commit();  // (empty) keeps the group order of ln_prologue: norms = oldest pending group but one
   grid_barrier(bar);
   DS_STAMP(13);
   ln_prologue(p, prev, nullptr, t, streams, As, lda_s, lnp, shs, warp, lane);
   stable_ln_rows(p, streams, As, lda_s, lnp, warp, lane);
   if (Wl != nullptr) {
     GemvOut ol{p.logits, nullptr, (long long)p.V, nullptr};
-    gemv_run<false>(wl, Wl, D, p.V, D, 1, As, lda_s, B, red, ol, gwarp, total_warps, warp, lane);
+    gemv_run<NT>(wl, Wl, D, (p.V + 15) / 16, p.V, D, p.split_logits, As, lda_s, B, red, ol, gwarp, total_warps, warp, lane);
   }
   DS_STAMP(14);
+  cp_async_wait<0>();
   // ---- leave: the last CTA out resets the barrier words for the next launch ----
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -820,42 +925,49 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static bool valid_split(int s) { return s == 1 || s == DS_WWARPS; }
+
 int decode_stack(const DecParams& p_in, int cooperative, cudaStream_t stream) {
   DecParams p = p_in;
   if (p.subs == nullptr || p.nsubs <= 0 || p.B <= 0 || p.B > 16 || p.t_ptr == nullptr || p.barrier == nullptr)
     return NUWA_ERR_INVALID;
-  if (p.D % 32 != 0 || p.D > 1024 || p.H <= 0 || p.H > 16 || p.dh % 8 != 0 || p.H * p.dh > 1024 || (p.H * p.dh) % 8 != 0)
+  if (p.D % 32 != 0 || p.D > 1024 || p.H <= 0 || p.H > 16 || p.dh % 8 != 0 || p.H * p.dh > 1024 || (p.H * p.dh) % 16 != 0 ||
+      (p.H * p.H) % 4 != 0)
     return NUWA_ERR_INVALID;
   if (p.kmax < p.D || p.kmax < p.H * p.dh || p.kmax % 8 != 0) return NUWA_ERR_INVALID;
   if (p.x_in == nullptr || p.y == nullptr || p.act == nullptr || p.actq == nullptr || p.norm_w == nullptr ||
       p.norm_b == nullptr)
     return NUWA_ERR_INVALID;
   if (p.w_logits != nullptr && (p.logits == nullptr || p.V <= 0)) return NUWA_ERR_INVALID;
-  if (p.j3max < 1 || p.j3max > 4096) return NUWA_ERR_INVALID;
+  if (p.j3max < 1 || p.j3max > 4096 || p.nk < 0) return NUWA_ERR_INVALID;
   p.jmax = p.j3max > p.nk + 1 ? p.j3max : p.nk + 1;
   if (p.nk > 0 && p.scores == nullptr) return NUWA_ERR_INVALID;
-  if (p.split_small != 1 && p.split_small != 2 && p.split_small != 4) p.split_small = 2;
-  if (p.split_ff != 1 && p.split_ff != 2 && p.split_ff != 4) p.split_ff = 4;
-  const DsLayout L = ds_layout(p.B, p.D, p.kmax, p.H, p.dh, p.jmax);
-  if (L.total > 200 * 1024) return NUWA_ERR_INVALID;
+  if (!valid_split(p.split_small)) p.split_small = DS_WWARPS;
+  if (!valid_split(p.split_ff)) p.split_ff = DS_WWARPS;
+  if (!valid_split(p.split_logits)) p.split_logits = DS_WWARPS;
+  const DsLayout L = ds_layout(p.B, p.D, p.kmax, p.H, p.dh, p.j3max, p.nk);
+  if (L.total > DS_SMEM_MAX) return NUWA_ERR_INVALID;
+  const void* kernel = p.B <= 8 ? (const void*)decode_stack_kernel<1> : (const void*)decode_stack_kernel<2>;
   static int max_blocks_per_sm_smem = -1, cached_smem = -1;
-  if (cudaFuncSetAttribute(decode_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total) != cudaSuccess)
-    return NUWA_ERR_CUDA;
-  if (cached_smem != L.total) {
+  static const void* cached_kernel = nullptr;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total) != cudaSuccess) return NUWA_ERR_CUDA;
+  if (cached_smem != L.total || cached_kernel != kernel) {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_stack_kernel, DS_THREADS, (size_t)L.total) != cudaSuccess)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, DS_THREADS, (size_t)L.total) != cudaSuccess)
       return NUWA_ERR_CUDA;
     max_blocks_per_sm_smem = nb;
     cached_smem = L.total;
+    cached_kernel = kernel;
   }
   if (max_blocks_per_sm_smem < 1) return NUWA_ERR_INVALID;
   int grid = device_sm_count();
   if (p.max_ctas > 0 && p.max_ctas < grid) grid = p.max_ctas;
-  if (grid < 1) return NUWA_ERR_CUDA;
+  // every sample (3DNA) / (sample, head) pair (cross attention) needs its own CTA: the K/V staging is per CTA
+  const int need = p.nk > 0 ? p.B * p.H : p.B;
+  if (grid < need) return NUWA_ERR_INVALID;
   if (cooperative) {
     void* args[] = {(void*)&p};
-    if (cudaLaunchCooperativeKernel((const void*)decode_stack_kernel, dim3(grid), dim3(DS_THREADS), args, (size_t)L.total,
-                                    stream) != cudaSuccess) {
+    if (cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(DS_THREADS), args, (size_t)L.total, stream) != cudaSuccess) {
       cudaGetLastError();
       return NUWA_ERR_CUDA;
     }
@@ -863,7 +975,8 @@ int decode_stack(const DecParams& p_in, int cooperative, cudaStream_t stream) {
     return NUWA_OK;
   }
   // plain launch: grid <= SM count and one CTA per SM, so all CTAs become resident once earlier work drains
-  decode_stack_kernel<<<grid, DS_THREADS, L.total, stream>>>(p);
+  if (p.B <= 8) decode_stack_kernel<1><<<grid, DS_THREADS, L.total, stream>>>(p);
+  else decode_stack_kernel<2><<<grid, DS_THREADS, L.total, stream>>>(p);
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
 }

@@ -375,6 +375,7 @@ class FusedDecode:
         p.kmax = kmax
         p.split_small = int(os.environ.get('NUWA_DECODE_SPLIT_SMALL', '0'))
         p.split_ff = int(os.environ.get('NUWA_DECODE_SPLIT_FF', '0'))
+        p.split_logits = int(os.environ.get('NUWA_DECODE_SPLIT_LOGITS', '0'))
         p.max_ctas = int(os.environ.get('NUWA_DECODE_MAX_CTAS', '0'))
         p.debug_flags = int(os.environ.get('NUWA_DECODE_DEBUG', '0'))
         self.params = p

@@ -57,7 +57,7 @@ with torch.no_grad():
         res[label] = dict(ms_per_sweep=round(ms, 4), us_per_barrier=round(1e3 * ms / nb, 3))
         print(label, res[label], flush=True)
     os.environ['NUWA_DECODE_DEBUG'] = '0'
-    for ctas in (148, 64, 16):
+    for ctas in (148, 96, 64):
         os.environ['NUWA_DECODE_MAX_CTAS'] = str(ctas)
         os.environ['NUWA_DECODE_DEBUG'] = '7'
         plan = engine.FusedDecode(pack, state, context, nuwa._logits_weight())

@@ -52,11 +52,11 @@ def run(label, **kw):
 
 run('fused_graph')
 run('per_kernel_graph', _use_fused=False)
-for ss, sf in ((1, 1), (1, 2), (2, 2), (2, 4), (4, 4)):
+for ss, sf in ((1, 1), (1, 7), (7, 1)):
     os.environ['NUWA_DECODE_SPLIT_SMALL'], os.environ['NUWA_DECODE_SPLIT_FF'] = str(ss), str(sf)
     run(f'fused_split_{ss}_{sf}')
 os.environ['NUWA_DECODE_SPLIT_SMALL'] = os.environ['NUWA_DECODE_SPLIT_FF'] = '0'
-for ctas in (74, 111, 132):
+for ctas in (96, 128):
     os.environ['NUWA_DECODE_MAX_CTAS'] = str(ctas)
     run(f'fused_ctas_{ctas}')
 os.environ['NUWA_DECODE_MAX_CTAS'] = '0'
