@@ -138,6 +138,11 @@ int nuwa_attn_sparse3dna(const nuwa_attn_params* p, void* vt_workspace, void* st
 /* vt_workspace: NULL, or B*H*dh*roundup(nv,16) bf16 elements of scratch; when given and the call is a full causal
  * pass over a 16-wide token grid (t0 == 0, nq == nv + 1, dh in {32,64}, H <= 8) the tensor-core kernel
  * (attention_3dna_tc.cu) runs, otherwise the generic gather kernel. */
+/* Same op on the halo-tiled tensor-core kernel (attention_3dna_halo.cu): one CTA = 4 query rows of a frame, the
+ * key rows they share staged in shared memory by TMA, banded 16x16 score / PV blocks on mma.sync.  Envelope: causal
+ * full pass (t0 == 0, nq == nv + 1), 16-wide token grid, H == 8, dh == 64, kh <= 3, <= 47 window keys, q|k|v in one
+ * row-strided buffer; returns NUWA_ERR_INVALID outside it (nothing launched) so the caller can use the gather kernel. */
+int nuwa_attn_sparse3dna_halo(const nuwa_attn_params* p, void* stream);
 /* Attention.forward core, nuwa_pytorch.py:339-378, and VQGanAttention core, vqgan_vae.py:275-282
  * (jmax = nk (+1 with a null key)) */
 int nuwa_attn_dense(const nuwa_attn_params* p, void* vt_workspace, void* stream);

@@ -114,6 +114,7 @@ SIGNATURES = {
     "nuwa_sandwich_ln": [P(LnParams), c_void_p],
     "nuwa_stable_ln": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "nuwa_attn_sparse3dna": [P(AttnParams), c_void_p, c_void_p],
+    "nuwa_attn_sparse3dna_halo": [P(AttnParams), c_void_p],
     "nuwa_attn_dense": [P(AttnParams), c_void_p, c_void_p],
     "nuwa_attn_cross2dna": [P(AttnParams), c_void_p],
     "nuwa_embed_tokens": [P(EmbedParams), c_void_p],
@@ -179,6 +180,9 @@ _lib = None
 # bumped by code that rewrites parameter storage behind autograd's back (optim.FusedAdamW): part of every packed-weight
 # cache key next to (data_ptr, _version)
 WEIGHTS_EPOCH = [0]
+
+
+NUWA_ERR_INVALID = -1  # include/nuwa_b200.h
 
 
 class NuwaB200Error(RuntimeError):

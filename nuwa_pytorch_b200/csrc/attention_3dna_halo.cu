@@ -1,0 +1,444 @@
+// Sparse3DNA attention core, halo-tiled: K/V key rows staged in shared memory by TMA, dense banded 16x16 score /
+// PV blocks on the tensor cores (causal, 16-wide token grid, 8 heads x 64).
+//
+// Reference: Sparse3DNA.forward core, nuwa_pytorch.py:523-564 (unfoldNd gather of k,v -> einsum -> mask -> softmax
+// -> talking heads -> einsum).  The reference (and attention.cu's gather kernel) reads 46 key rows PER QUERY;
+// here one CTA owns QR = 4 query rows of a frame, (f, y0 + i*dil_h, x = 0..15), chosen with the window's own row
+// dilation so that their key rows overlap: for every frame offset a of the window the CTA needs only the
+// QR + kh - 1 = 6 key rows (f_a, y0 + (r - (kh-1))*dil_h), each a [16 tokens x 64 channels] box per head that one
+// TMA instruction (SWIZZLE_128B tensor map over the q|k|v projection buffer, zero fill beyond the sequence) drops
+// into a 3-stage shared-memory ring -- 7.5 key rows per query row instead of 15 (row-per-warp) or 46 x 16 (gather).
+//
+// One warp = one query row (16 queries) and walks the heads one after the other:
+//   phase 1, head h: Q fragments (ldmatrix) x K row blocks (ldmatrix) -> mma.sync m16n8k16 -> the kw in-band
+//            diagonals of each 16x16 block go to an fp32 row buffer S[x][slot] (slot order = the reference's key
+//            order, slot 0 = bos); fp32 softmax -> P[h][q][slot] as fp16;
+//   mix:     talking heads across the 8 heads per (query, slot), fp32 math, result stored as bf16 in place;
+//   phase 3, head g: banded P'[g] blocks (A fragments gathered from P) x V row blocks (ldmatrix.trans) -> O.
+// Out-of-grid window slots keep the -FLT_MAX the row buffer is initialised with (causal: no zero-key case, D16
+// cannot occur).  Everything except the stage ring is warp-private, so the only CTA-wide sync is one
+// __syncthreads per stage hand-over.
+#include <float.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nuwa {
+
+int encode_map_bf16_sw128(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box);  // gemm_tcgen05.cu
+
+namespace {
+
+constexpr int GW = 16;                      // tokens per grid row
+constexpr int QR = 4;                       // query rows (warps) per CTA
+constexpr int NR = 6;                       // key rows per frame offset: QR + kh - 1 with kh <= 3
+constexpr int NST = 3;                      // stage ring depth
+constexpr int NH = 8, DH = 64, INNER = NH * DH;
+constexpr int BOX = GW * DH * 2;            // 2048 B: one (row, head) box
+constexpr int STAGE = NR * BOX;
+constexpr int SP = 49;                      // fp32 score row pitch
+constexpr int PP = 50;                      // fp16/bf16 probability row pitch (25 words: conflict-free across rows)
+constexpr int ZSLOT = PP - 1;               // always-zero slot
+constexpr int MAXJ = 48;
+
+constexpr int OFF_Q = NST * STAGE;
+constexpr int OFF_P = OFF_Q + QR * BOX;
+constexpr int OFF_S = OFF_P + NH * QR * GW * PP * 2;
+constexpr int OFF_BOS = OFF_S + QR * GW * SP * 4;
+constexpr int OFF_W = OFF_BOS + 2 * INNER * 2;
+constexpr int OFF_BAR = OFF_W + NH * NH * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;  // + alignment slack
+
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+struct HaloArgs {
+  int B, nv, nf, tiles;
+  int kt, kh, kw, dt, dh, dw;
+  int koff, voff;  // channel offsets of k and v relative to q inside a token row
+  int J;
+  float scale_log2e;
+  const float* talk;
+  bf16* o;
+  long long o_bs;
+  int o_rs;
+  const bf16* k0;  // k of sequence row 0 (bos), sample 0
+  const bf16* v0;
+  long long k_bs, v_bs;
+};
+
+__global__ void __launch_bounds__(QR * 32, 2)
+attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  const uint32_t sm_u = smem_u32(sm);
+  __half* P16 = reinterpret_cast<__half*>(sm + OFF_P);
+  float* S32 = reinterpret_cast<float*>(sm + OFF_S);
+  bf16* kbos = reinterpret_cast<bf16*>(sm + OFF_BOS);
+  bf16* vbos = kbos + INNER;
+  float* Wsm = reinterpret_cast<float*>(sm + OFF_W);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + OFF_BAR);  // [NST]
+  uint64_t* qbar = full + NST;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  // ---- which tile: heaviest frames first (later frames see more key frames) ----
+  const int per_f = p.tiles * p.B;
+  const int f = p.nf - 1 - (int)blockIdx.x / per_f;
+  const int rem = (int)blockIdx.x % per_f;
+  const int tile = rem / p.B, b = rem - tile * p.B;
+  int y0;
+  {
+    int r = 0, s = tile;
+    for (; r < p.dh; ++r) {
+      const int nrows = (GW - r + p.dh - 1) / p.dh;
+      const int nt = (nrows + QR - 1) / QR;
+      if (s < nt) break;
+      s -= nt;
+    }
+    y0 = r + s * QR * p.dh;
+  }
+  const int kt = p.kt, kh = p.kh, kw = p.kw;
+  const int a_lo = max(0, kt - 1 - f / p.dt);
+  const int n_a = kt - a_lo;
+  const int NS1 = NH * n_a, NS = 2 * NS1;
+  uint32_t rowmask = 0, qmask = 0;
+  for (int rr = 0; rr < QR + kh - 1; ++rr) {
+    const int yy = y0 + (rr - (kh - 1)) * p.dh;
+    if (yy >= 0 && yy < GW) rowmask |= 1u << rr;
+  }
+  for (int i = 0; i < QR; ++i)
+    if (y0 + i * p.dh < GW) qmask |= 1u << i;
+  const int yq = y0 + warp * p.dh;
+  const int vbase = (f * GW + yq) * GW;                 // video index of this warp's x = 0
+  const bool wactive = (yq < GW) && (vbase < p.nv);     // warp has at least one real query
+  const bool ok0 = wactive && (vbase + g < p.nv), ok1 = wactive && (vbase + g + 8 < p.nv);
+
+  // ---- one-time shared-memory state ----
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) mbar_init(&full[i], 1);
+    mbar_init(qbar, 1);
+    fence_barrier_init();
+  }
+  {
+    float* Sw = S32 + warp * GW * SP;
+    for (int i = lane; i < GW * SP; i += 32) Sw[i] = -FLT_MAX;
+    const int nz = PP - p.J;  // slots J .. PP-1 stay zero (pair padding + the always-zero slot)
+    for (int i = lane; i < NH * GW * nz; i += 32) {
+      const int row = i / nz, z = i - row * nz;
+      const int h = row / GW, x = row - h * GW;
+      P16[(size_t)(h * QR * GW + warp * GW + x) * PP + p.J + z] = __float2half(0.f);
+    }
+    // bos key / value rows of this sample (sequence row 0), all heads
+    const uint4* src = reinterpret_cast<const uint4*>(tid < 64 ? p.k0 + (long long)b * p.k_bs : p.v0 + (long long)b * p.v_bs);
+    reinterpret_cast<uint4*>(kbos)[tid] = __ldg(src + (tid & 63));
+    if (tid < NH * NH) Wsm[tid] = p.talk ? __ldg(p.talk + tid) : ((tid / NH) == (tid % NH) ? 1.f : 0.f);
+  }
+  __syncthreads();
+
+  // ---- producer helpers (thread 0) ----
+  auto issue_q = [&](int h) {
+    mbar_arrive_expect_tx(qbar, (uint32_t)__popc(qmask) * BOX);
+    for (int i = 0; i < QR; ++i)
+      if ((qmask >> i) & 1)
+        tma_load_3d(sm_u + OFF_Q + i * BOX, &qmap, qbar, h * DH, 1 + (f * GW + y0 + i * p.dh) * GW, b);
+  };
+  auto issue_step = [&](int s) {
+    const int ph = s >= NS1 ? 1 : 0;
+    const int r2 = s - ph * NS1;
+    const int h = r2 / n_a, a = a_lo + (r2 - h * n_a);
+    const int ff = f - (kt - 1 - a) * p.dt;
+    const int st = s % NST;
+    mbar_arrive_expect_tx(&full[st], (uint32_t)__popc(rowmask) * BOX);
+    const int chan = (ph ? p.voff : p.koff) + h * DH;
+    for (int rr = 0; rr < QR + kh - 1; ++rr)
+      if ((rowmask >> rr) & 1) {
+        const int yy = y0 + (rr - (kh - 1)) * p.dh;
+        tma_load_3d(sm_u + st * STAGE + rr * BOX, &qmap, &full[st], chan, 1 + (ff * GW + yy) * GW, b);
+      }
+  };
+  if (tid == 0) {
+    tma_prefetch_desc(&qmap);
+    issue_q(0);
+    for (int s = 0; s < NST && s < NS; ++s) issue_step(s);
+  }
+  // the bos query (sequence row 0) attends only to itself (nuwa_pytorch.py:608): copy its value row
+  if (f == 0 && y0 == 0 && warp == 0) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(p.o + (long long)b * p.o_bs);
+    for (int c = lane; c < INNER / 2; c += 32) dst[c] = reinterpret_cast<const uint32_t*>(vbos)[c];
+  }
+
+  // ---- per-lane band table: the 8 (query x, key x') pairs of a 16x16 block this lane holds, both as C fragment
+  //      (scores) and as A fragment (probabilities): idx = nt*4 + e <-> x = g + 8*(e>>1), x' = nt*8 + 2t + (e&1) ----
+  int cb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int x = g + 8 * ((i & 3) >> 1);
+    const int xp = (i >> 2) * 8 + 2 * t + (i & 1);
+    const int delta = x - xp;  // causal: key column = x - (kw-1-c)*dw
+    int c = -1;
+    if (delta >= 0 && delta % p.dw == 0 && delta / p.dw <= kw - 1) c = kw - 1 - delta / p.dw;
+    cb[i] = c;
+  }
+  // ldmatrix lane addressing inside a [16 rows x 128 B] SWIZZLE_128B box
+  const int mat = lane >> 3, l7 = lane & 7;
+  const int k_row = ((mat >> 1) << 3) + l7, k_ch = mat & 1;   // K (B operand): m0,m1 = keys 0-7 (k lo, hi); m2,m3 = keys 8-15
+  const int a_row = ((mat & 1) << 3) + l7, a_ch = mat >> 1;   // Q (A operand) and V^T: m0,m1 = rows 0-7 / 8-15 of chunk c
+  const uint32_t k_lane = k_row * 128, a_lane = a_row * 128;
+
+  float* Sw = S32 + warp * GW * SP;
+  __half* Pw = P16 + (size_t)warp * GW * PP;  // + h * QR*GW*PP
+  uint32_t qa[4][4];
+  float o[8][4];
+
+  for (int s = 0; s < NS; ++s) {
+    const int ph = s >= NS1 ? 1 : 0;
+    const int r2 = s - ph * NS1;
+    const int h = r2 / n_a, ai = r2 - h * n_a, a = a_lo + ai;
+    const int st = s % NST;
+    const uint32_t stage = sm_u + st * STAGE;
+
+    if (ph == 0 && ai == 0) {  // head start: Q fragments + bos score
+      mbar_wait(qbar, h & 1);
+      const uint32_t qb = sm_u + OFF_Q + warp * BOX;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) ldsm4(qa[ks], qb + a_lane + (((2 * ks + a_ch) ^ l7) << 4));
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t b0 = 0u, b1 = 0u;
+        if (g == 0) {
+          b0 = *reinterpret_cast<const uint32_t*>(kbos + h * DH + ks * 16 + 2 * t);
+          b1 = *reinterpret_cast<const uint32_t*>(kbos + h * DH + ks * 16 + 8 + 2 * t);
+        }
+        mma16816(c, qa[ks], b0, b1);
+      }
+      if (t == 0) {  // key column 0: c[0] (row g), c[2] (row g+8)
+        Sw[g * SP] = c[0];
+        Sw[(g + 8) * SP] = c[2];
+      }
+    }
+    if (ph == 1 && ai == 0) {
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+    }
+
+    mbar_wait(&full[st], (s / NST) & 1);
+
+    if (wactive) {
+      if (ph == 0) {
+        for (int bq = 0; bq < kh; ++bq) {
+          const int rr = warp + bq;
+          if (!((rowmask >> rr) & 1)) continue;
+          const uint32_t kb = stage + rr * BOX + k_lane;
+          float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            uint32_t r[4];
+            ldsm4(r, kb + (((2 * ks + k_ch) ^ l7) << 4));
+            mma16816(c0, qa[ks], r[0], r[1]);
+            mma16816(c1, qa[ks], r[2], r[3]);
+          }
+          const int sbase = 1 + (a * kh + bq) * kw;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int x = g + 8 * (e >> 1);
+            if (cb[e] >= 0) Sw[x * SP + sbase + cb[e]] = c0[e];
+            if (cb[4 + e] >= 0) Sw[x * SP + sbase + cb[4 + e]] = c1[e];
+          }
+        }
+      } else {
+        const unsigned short* Pg = reinterpret_cast<const unsigned short*>(Pw + (size_t)h * QR * GW * PP);
+        for (int bq = 0; bq < kh; ++bq) {
+          const int rr = warp + bq;
+          if (!((rowmask >> rr) & 1)) continue;
+          const uint32_t vb = stage + rr * BOX + a_lane;
+          const int sbase = 1 + (a * kh + bq) * kw;
+          unsigned short av[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int x = g + 8 * ((i & 3) >> 1);
+            av[i] = Pg[x * PP + (cb[i] >= 0 ? sbase + cb[i] : ZSLOT)];
+          }
+          uint32_t af[4];
+          af[0] = (uint32_t)av[0] | ((uint32_t)av[1] << 16);  // row g,   keys 2t, 2t+1
+          af[1] = (uint32_t)av[2] | ((uint32_t)av[3] << 16);  // row g+8, keys 2t, 2t+1
+          af[2] = (uint32_t)av[4] | ((uint32_t)av[5] << 16);  // row g,   keys 2t+8, 2t+9
+          af[3] = (uint32_t)av[6] | ((uint32_t)av[7] << 16);  // row g+8, keys 2t+8, 2t+9
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) {
+            uint32_t r[4];
+            ldsm4t(r, vb + (((2 * pr + a_ch) ^ l7) << 4));
+            mma16816(o[2 * pr], af, r[0], r[1]);
+            mma16816(o[2 * pr + 1], af, r[2], r[3]);
+          }
+        }
+      }
+    }
+
+    if (ph == 0 && ai == n_a - 1) {
+      // ---- head end: fp32 softmax of the 16 score rows -> P[h] (fp16); two lanes per row, interleaved slots ----
+      __syncwarp();
+      const int x = lane >> 1, half = lane & 1;
+      const float* row = Sw + x * SP;
+      float v[MAXJ / 2];
+      float m = -FLT_MAX;
+#pragma unroll
+      for (int i = 0; i < MAXJ / 2; ++i) {
+        const int j = 2 * i + half;
+        v[i] = j < p.J ? row[j] : -FLT_MAX;
+        m = fmaxf(m, v[i]);
+      }
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      float l = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXJ / 2; ++i) {
+        v[i] = exp2f((v[i] - m) * p.scale_log2e);  // masked slots: exp2(-huge) == 0
+        l += v[i];
+      }
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      const float inv = 1.0f / l;
+      __half* prow = Pw + (size_t)h * QR * GW * PP + x * PP;
+#pragma unroll
+      for (int i = 0; i < MAXJ / 2; ++i) {
+        const int j = 2 * i + half;
+        if (j < p.J) prow[j] = __float2half_rn(v[i] * inv);
+      }
+      __syncwarp();
+      if (h == NH - 1) {
+        // ---- talking heads (nuwa_pytorch.py:556-558): P'[g][x][j] = sum_h W[g][h] P[h][x][j]; slot pairs, in place ----
+        float W[NH * NH];
+#pragma unroll
+        for (int i = 0; i < NH * NH / 4; ++i) {
+          const float4 w4 = reinterpret_cast<const float4*>(Wsm)[i];
+          W[4 * i] = w4.x; W[4 * i + 1] = w4.y; W[4 * i + 2] = w4.z; W[4 * i + 3] = w4.w;
+        }
+        constexpr int NPAIR = MAXJ / 2;
+        for (int pi = lane; pi < GW * NPAIR; pi += 32) {
+          const int xx = pi / NPAIR, jp = pi - xx * NPAIR;
+          uint32_t* base = reinterpret_cast<uint32_t*>(Pw + xx * PP + 2 * jp);
+          float2 pin[NH];
+#pragma unroll
+          for (int hh = 0; hh < NH; ++hh) {
+            const uint32_t u = base[hh * (QR * GW * PP / 2)];
+            pin[hh] = __half22float2(*reinterpret_cast<const __half2*>(&u));
+          }
+#pragma unroll
+          for (int gh = 0; gh < NH; ++gh) {
+            float ax = 0.f, ay = 0.f;
+#pragma unroll
+            for (int hh = 0; hh < NH; ++hh) {
+              ax = fmaf(W[gh * NH + hh], pin[hh].x, ax);
+              ay = fmaf(W[gh * NH + hh], pin[hh].y, ay);
+            }
+            base[gh * (QR * GW * PP / 2)] = pack_bf16x2(ax, ay);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (ph == 1 && ai == n_a - 1 && wactive) {
+      // ---- output head h: add the bos value (slot 0) and store ----
+      const bf16* Pg = reinterpret_cast<const bf16*>(Pw + (size_t)h * QR * GW * PP);
+      const float pb0 = __bfloat162float(Pg[g * PP]), pb1 = __bfloat162float(Pg[(g + 8) * PP]);
+      bf16* ob = p.o + (long long)b * p.o_bs + h * DH + 2 * t;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) {
+        const float2 vb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vbos + h * DH + nd * 8 + 2 * t));
+        if (ok0)
+          *reinterpret_cast<uint32_t*>(ob + (long long)(1 + vbase + g) * p.o_rs + nd * 8) =
+              pack_bf16x2(fmaf(pb0, vb.x, o[nd][0]), fmaf(pb0, vb.y, o[nd][1]));
+        if (ok1)
+          *reinterpret_cast<uint32_t*>(ob + (long long)(1 + vbase + g + 8) * p.o_rs + nd * 8) =
+              pack_bf16x2(fmaf(pb1, vb.x, o[nd][2]), fmaf(pb1, vb.y, o[nd][3]));
+      }
+    }
+
+    __syncthreads();  // every warp is done with this stage (and, at a head start, with the Q buffer)
+    if (tid == 0) {
+      if (s + NST < NS) issue_step(s + NST);
+      if (ph == 0 && ai == 0 && h + 1 < NH) issue_q(h + 1);
+    }
+  }
+}
+
+}  // namespace
+
+// Envelope: causal full pass (t0 == 0, nq == nv + 1) over a 16-wide token grid, H == 8, dh == 64, kh <= 3,
+// window <= 47 keys, q|k|v rows sharing one token stride.  NUWA_ERR_INVALID outside it (caller falls back).
+int attn_3dna_halo(const AttnParams& p, cudaStream_t stream) {
+  if (!p.causal || p.fmap != GW || p.t0 != 0 || p.t0_ptr != nullptr) return NUWA_ERR_INVALID;
+  if (p.H != NH || p.dh != DH || p.nq != p.nv + 1 || p.nv <= 0 || p.B <= 0) return NUWA_ERR_INVALID;
+  if (p.kh > 3 || p.kt < 1 || p.kh < 1 || p.kw < 1 || p.kw > GW || 1 + p.kt * p.kh * p.kw > MAXJ) return NUWA_ERR_INVALID;
+  if (p.dt <= 0 || p.dh_ <= 0 || p.dw <= 0) return NUWA_ERR_INVALID;
+  // causal padding must equal dil*(k-1) exactly (nuwa_pytorch.py:424-428 pads 2*(dil*(k-1)//2))
+  if (((p.dt * (p.kt - 1)) & 1) || ((p.dh_ * (p.kh - 1)) & 1) || ((p.dw * (p.kw - 1)) & 1)) return NUWA_ERR_INVALID;
+  if (p.head_scale != nullptr || p.bias != nullptr || p.key_mask != nullptr || p.null_k != nullptr) return NUWA_ERR_INVALID;
+  const bf16* q = reinterpret_cast<const bf16*>(p.q);
+  const bf16* k = reinterpret_cast<const bf16*>(p.k);
+  const bf16* v = reinterpret_cast<const bf16*>(p.v);
+  const long long koff = k - q, voff = v - q;
+  if (p.k_rs != p.q_rs || p.v_rs != p.q_rs || p.k_bs != p.q_bs || p.v_bs != p.q_bs) return NUWA_ERR_INVALID;
+  if (koff < 0 || voff < 0 || koff + INNER > p.q_rs || voff + INNER > p.q_rs) return NUWA_ERR_INVALID;
+  if ((p.q_rs % 8) || (p.q_bs % 8) || (koff % 8) || (voff % 8) || (p.o_rs & 1) || (p.o_bs & 1)) return NUWA_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(p.q) & 15) || (reinterpret_cast<uintptr_t>(p.o) & 3)) return NUWA_ERR_INVALID;
+
+  CUtensorMap map;
+  const uint64_t dims[3] = {(uint64_t)p.q_rs, (uint64_t)(p.nv + 1), (uint64_t)p.B};
+  const uint64_t strides[3] = {2, (uint64_t)p.q_rs * 2, (uint64_t)p.q_bs * 2};
+  const uint32_t box[3] = {DH, GW, 1};
+  const int rc = encode_map_bf16_sw128(&map, p.q, 3, dims, strides, box);
+  if (rc != NUWA_OK) return rc;
+
+  HaloArgs a;
+  a.B = p.B; a.nv = p.nv;
+  a.nf = (p.nv + GW * GW - 1) / (GW * GW);
+  int tiles = 0;
+  for (int r = 0; r < p.dh_ && r < GW; ++r) tiles += ((GW - r + p.dh_ - 1) / p.dh_ + QR - 1) / QR;
+  a.tiles = tiles;
+  a.kt = p.kt; a.kh = p.kh; a.kw = p.kw; a.dt = p.dt; a.dh = p.dh_; a.dw = p.dw;
+  a.koff = (int)koff; a.voff = (int)voff;
+  a.J = 1 + p.kt * p.kh * p.kw;
+  a.scale_log2e = p.qscale * 1.4426950408889634f;
+  a.talk = p.talk;
+  a.o = reinterpret_cast<bf16*>(p.o); a.o_bs = p.o_bs; a.o_rs = p.o_rs;
+  a.k0 = k; a.v0 = v; a.k_bs = p.k_bs; a.v_bs = p.v_bs;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(attn_3dna_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+      return NUWA_ERR_CUDA;
+    cudaFuncSetAttribute(attn_3dna_halo_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr_set = true;
+  }
+  const int grid = a.nf * a.tiles * a.B;
+  attn_3dna_halo_kernel<<<grid, QR * 32, SMEM_BYTES, stream>>>(map, a);
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+
+}  // namespace nuwa

@@ -481,6 +481,12 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64
   return r == CUDA_SUCCESS ? NUWA_OK : NUWA_ERR_INVALID;
 }
 
+// exported for the other TMA users (attention_3dna_halo.cu)
+int encode_map_bf16_sw128(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_map(map, base, rank, dims, strides_bytes, box);
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {

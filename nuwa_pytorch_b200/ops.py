@@ -149,12 +149,13 @@ def _attn_base(q, k, v, o, B, nq, t0, H, dh, q_bs, k_bs, v_bs, o_bs, q_rs, k_rs,
 
 
 def attn_sparse3dna(qkv, o, *, B, nq, t0, npos, H, dh, talk, fmap, max_frames, nv, kernel, dilation, causal,
-                    o_bs=None, use_tc=False):
+                    o_bs=None, use_tc=False, variant='auto'):
     """qkv: bf16 buffer (B, npos, 3*H*dh) holding q|k|v rows for positions [0, npos); queries are positions
     [t0, t0+nq).  o: bf16 (B, nq, H*dh).  nv = number of video tokens present (positions 1..nv).
-    use_tc selects the banded tensor-core kernel (attention_3dna_tc.cu); measured 253-296 us vs 158-234 us for the
-    gather kernel at the cfg-3 shape (profiles/r01_attn3dna_perf.json), so it is opt-in until its softmax / mix
-    phases move off the CUDA cores."""
+    variant: 'auto' = the halo-tiled TMA + tensor-core kernel (attention_3dna_halo.cu) when the call is inside its
+    envelope (causal full pass, 16-wide grid, 8 x 64 heads), else the gather kernel; 'gather' / 'halo' pin one
+    (a pinned 'halo' outside the envelope raises).  use_tc selects the older row-per-warp tensor-core kernel
+    (attention_3dna_tc.cu; slower than both, kept for comparison)."""
     inner = H * dh
     esz = 2
     base = qkv.data_ptr()
@@ -166,6 +167,12 @@ def attn_sparse3dna(qkv, o, *, B, nq, t0, npos, H, dh, talk, fmap, max_frames, n
     p.dt, p.dh_, p.dw = dilation
     p.causal = int(bool(causal))
     p.jmax = 1 + kernel[0] * kernel[1] * kernel[2]
+    if variant in ('auto', 'halo') and not use_tc:
+        rc = lib().nuwa_attn_sparse3dna_halo(p, stream())
+        if rc == 0:
+            return
+        if variant == 'halo' or rc != _lib.NUWA_ERR_INVALID:
+            check(rc, "nuwa_attn_sparse3dna_halo")
     ws = None
     if use_tc and causal and fmap == 16 and t0 == 0 and nq == nv + 1 and dh in (32, 64) and H <= 8:
         ws = torch.empty(B * H * dh * _round_up(nv, 16), dtype=torch.bfloat16, device=qkv.device)

@@ -94,9 +94,56 @@ def test_sparse3dna_tensor_core_kernel_matches_gather_kernel(cuda_device, H, dh,
                 dilation=(dil,) * 3, causal=True)
     o_ref = torch.zeros(B, n, inner, dtype=torch.bfloat16, device=cuda_device)
     o_tc = torch.zeros(B, n, inner, dtype=torch.bfloat16, device=cuda_device)
-    ops.attn_sparse3dna(qkv, o_ref, use_tc=False, **geom)
-    ops.attn_sparse3dna(qkv, o_tc, use_tc=True, **geom)
+    ops.attn_sparse3dna(qkv, o_ref, variant='gather', **geom)
+    ops.attn_sparse3dna(qkv, o_tc, use_tc=True, variant='gather', **geom)
     r = rel(o_tc.float(), o_ref.float())
     print(f"  3dna tc vs gather H={H} dh={dh} k={kernel} d={dil} nv={nv}: rel {r:.2e}")
     assert torch.equal(o_tc[:, 0], o_ref[:, 0])  # bos row: its own value
     assert r < 8e-3  # probabilities are rounded to bf16 for the tensor-core PV
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel,dil,nv,B,talk_on", [((5, 3, 3), (1, 1, 1), 768, 2, True), ((5, 3, 3), (2, 2, 2), 1279, 2, True),
+                                                     ((5, 3, 3), (4, 4, 4), 2559, 3, True), ((5, 3, 3), (1, 2, 4), 601, 1, True),
+                                                     ((3, 3, 5), (2, 4, 2), 530, 2, False), ((3, 1, 3), (1, 1, 3), 256, 2, True),
+                                                     ((5, 3, 3), (3, 5, 2), 1024, 1, True), ((1, 3, 15), (1, 2, 1), 300, 2, True)])
+def test_sparse3dna_halo_kernel_matches_gather_kernel(cuda_device, kernel, dil, nv, B, talk_on):
+    """attention_3dna_halo.cu (TMA-staged key rows shared by 4 query rows, banded mma.sync blocks) vs the generic
+    gather kernel on identical bf16 q|k|v, incl. partial last rows / frames and mixed per-axis dilations."""
+    from nuwa_pytorch_b200 import ops
+    H, dh, fmap, maxf = 8, 64, 16, 10
+    g = gen(nv * 7 + dil[0] + 31 * kernel[2])
+    inner = H * dh
+    n = nv + 1
+    qkv = torch.randn(B, n, 3 * inner, generator=g).bfloat16().to(cuda_device)
+    talk = (torch.randn(H, H, generator=g) / 2).to(cuda_device) if talk_on else None
+    geom = dict(B=B, nq=n, t0=0, npos=n, H=H, dh=dh, talk=talk, fmap=fmap, max_frames=maxf, nv=nv, kernel=kernel,
+                dilation=dil, causal=True)
+    o_ref = torch.zeros(B, n, inner, dtype=torch.bfloat16, device=cuda_device)
+    o_halo = torch.full((B, n, inner), float('nan'), dtype=torch.bfloat16, device=cuda_device)
+    ops.attn_sparse3dna(qkv, o_ref, variant='gather', **geom)
+    ops.attn_sparse3dna(qkv, o_halo, variant='halo', **geom)
+    torch.cuda.synchronize()
+    assert torch.isfinite(o_halo.float()).all()  # every output row was written
+    r = rel(o_halo.float(), o_ref.float())
+    worst = (o_halo.float() - o_ref.float()).abs().max().item()
+    print(f"  3dna halo vs gather k={kernel} d={dil} nv={nv}: rel {r:.2e} max abs {worst:.2e}")
+    assert torch.equal(o_halo[:, 0], o_ref[:, 0])  # bos row: its own value
+    assert r < 8e-3  # probabilities are rounded to bf16 for the tensor-core PV
+
+
+@pytest.mark.gpu
+def test_sparse3dna_halo_envelope(cuda_device):
+    """Outside its envelope the halo kernel launches nothing and reports NUWA_ERR_INVALID ('auto' then falls back)."""
+    from nuwa_pytorch_b200 import ops
+    from nuwa_pytorch_b200._lib import NuwaB200Error
+    H, dh, nv = 4, 32, 64
+    qkv = torch.randn(1, nv + 1, 3 * H * dh, device=cuda_device).bfloat16()
+    o = torch.zeros(1, nv + 1, H * dh, dtype=torch.bfloat16, device=cuda_device)
+    geom = dict(B=1, nq=nv + 1, t0=0, npos=nv + 1, H=H, dh=dh, talk=None, fmap=8, max_frames=2, nv=nv, kernel=(3, 3, 3),
+                dilation=(1, 1, 1), causal=True)
+    with pytest.raises(NuwaB200Error):
+        ops.attn_sparse3dna(qkv, o, variant='halo', **geom)
+    ops.attn_sparse3dna(qkv, o, variant='auto', **geom)  # gather kernel
+    torch.cuda.synchronize()
+    assert o.float().abs().sum() > 0

@@ -18,10 +18,11 @@ talk = torch.randn(H, H, device=dev) / 2
 o = torch.empty(B, n, inner, dtype=torch.bfloat16, device=dev)
 rows = []
 for dil in (1, 2, 4):
-    for use_tc in (False, True):
+    for name in ('gather', 'tensor-core', 'halo'):
         def run():
             ops.attn_sparse3dna(qkv, o, B=B, nq=n, t0=0, npos=n, H=H, dh=dh, talk=talk, fmap=16, max_frames=10, nv=nv,
-                                kernel=(5, 3, 3), dilation=(dil,) * 3, causal=True, use_tc=use_tc)
+                                kernel=(5, 3, 3), dilation=(dil,) * 3, causal=True, use_tc=name == 'tensor-core',
+                                variant='halo' if name == 'halo' else 'gather')
         for _ in range(2):
             run()
         ts = []
@@ -36,6 +37,6 @@ for dil in (1, 2, 4):
         ts.sort()
         us = ts[2] * 1e3
         gbs = B * nv * 4096 / (us * 1e-6) / 1e9  # algorithmic bytes: 4096 B per token
-        rows.append(dict(dilation=dil, kernel='tensor-core' if use_tc else 'gather', us=round(us, 1), algorithmic_GBps=round(gbs, 1)))
+        rows.append(dict(dilation=dil, kernel=name, us=round(us, 1), algorithmic_GBps=round(gbs, 1)))
         print(rows[-1], flush=True)
 json.dump(rows, open('gpurun_out/attn3dna_perf.json', 'w'), indent=1)
