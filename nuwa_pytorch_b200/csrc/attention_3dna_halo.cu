@@ -16,8 +16,8 @@
 //   mix:     talking heads across the 8 heads per (query, slot), fp32 math, result stored as bf16 in place;
 //   phase 3, head g: banded P'[g] blocks (A fragments gathered from P) x V row blocks (ldmatrix.trans) -> O.
 // Out-of-grid window slots keep the -FLT_MAX the row buffer is initialised with (causal: no zero-key case, D16
-// cannot occur).  Everything except the stage ring is warp-private, so the only CTA-wide sync is one
-// __syncthreads per stage hand-over.
+// cannot occur).  Everything except the stage ring is warp-private; a fifth warp is the TMA producer and the ring
+// is handed over through full / empty mbarriers, so the query-row warps never wait for each other.
 #include <float.h>
 #include <cuda_fp16.h>
 
@@ -49,7 +49,7 @@ constexpr int OFF_S = OFF_P + NH * QR * GW * PP * 2;
 constexpr int OFF_BOS = OFF_S + QR * GW * SP * 4;
 constexpr int OFF_W = OFF_BOS + 2 * INNER * 2;
 constexpr int OFF_BAR = OFF_W + NH * NH * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;  // + alignment slack
+constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;  // + alignment slack
 
 __device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -89,8 +89,21 @@ struct HaloArgs {
   long long k_bs, v_bs;
 };
 
-__global__ void __launch_bounds__(QR * 32, 2)
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
+
+// Warps 0..QR-1: one query row each.  Warp QR: TMA producer (one lane).  Stage hand-over through full / empty
+// mbarriers, so the query-row warps never wait for each other.
+template <int KH>
+__global__ void __launch_bounds__((QR + 1) * 32, 2)
 attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p) {
+  constexpr int NROW = QR + KH - 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -101,7 +114,9 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
   bf16* vbos = kbos + INNER;
   float* Wsm = reinterpret_cast<float*>(sm + OFF_W);
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + OFF_BAR);  // [NST]
-  uint64_t* qbar = full + NST;
+  uint64_t* empty = full + NST;                                // [NST]
+  uint64_t* qfull = empty + NST;
+  uint64_t* qempty = qfull + 1;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -122,29 +137,22 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
     }
     y0 = r + s * QR * p.dh;
   }
-  const int kt = p.kt, kh = p.kh, kw = p.kw;
+  const int kt = p.kt, kw = p.kw;
   const int a_lo = max(0, kt - 1 - f / p.dt);
   const int n_a = kt - a_lo;
   const int NS1 = NH * n_a, NS = 2 * NS1;
-  uint32_t rowmask = 0, qmask = 0;
-  for (int rr = 0; rr < QR + kh - 1; ++rr) {
-    const int yy = y0 + (rr - (kh - 1)) * p.dh;
-    if (yy >= 0 && yy < GW) rowmask |= 1u << rr;
-  }
-  for (int i = 0; i < QR; ++i)
-    if (y0 + i * p.dh < GW) qmask |= 1u << i;
-  const int yq = y0 + warp * p.dh;
-  const int vbase = (f * GW + yq) * GW;                 // video index of this warp's x = 0
-  const bool wactive = (yq < GW) && (vbase < p.nv);     // warp has at least one real query
-  const bool ok0 = wactive && (vbase + g < p.nv), ok1 = wactive && (vbase + g + 8 < p.nv);
 
   // ---- one-time shared-memory state ----
   if (tid == 0) {
-    for (int i = 0; i < NST; ++i) mbar_init(&full[i], 1);
-    mbar_init(qbar, 1);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], QR);
+    }
+    mbar_init(qfull, 1);
+    mbar_init(qempty, QR);
     fence_barrier_init();
   }
-  {
+  if (warp < QR) {
     float* Sw = S32 + warp * GW * SP;
     for (int i = lane; i < GW * SP; i += 32) Sw[i] = -FLT_MAX;
     const int nz = PP - p.J;  // slots J .. PP-1 stay zero (pair padding + the always-zero slot)
@@ -160,31 +168,62 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
   }
   __syncthreads();
 
-  // ---- producer helpers (thread 0) ----
-  auto issue_q = [&](int h) {
-    mbar_arrive_expect_tx(qbar, (uint32_t)__popc(qmask) * BOX);
-    for (int i = 0; i < QR; ++i)
-      if ((qmask >> i) & 1)
-        tma_load_3d(sm_u + OFF_Q + i * BOX, &qmap, qbar, h * DH, 1 + (f * GW + y0 + i * p.dh) * GW, b);
-  };
-  auto issue_step = [&](int s) {
-    const int ph = s >= NS1 ? 1 : 0;
-    const int r2 = s - ph * NS1;
-    const int h = r2 / n_a, a = a_lo + (r2 - h * n_a);
-    const int ff = f - (kt - 1 - a) * p.dt;
-    const int st = s % NST;
-    mbar_arrive_expect_tx(&full[st], (uint32_t)__popc(rowmask) * BOX);
-    const int chan = (ph ? p.voff : p.koff) + h * DH;
-    for (int rr = 0; rr < QR + kh - 1; ++rr)
-      if ((rowmask >> rr) & 1) {
-        const int yy = y0 + (rr - (kh - 1)) * p.dh;
-        tma_load_3d(sm_u + st * STAGE + rr * BOX, &qmap, &full[st], chan, 1 + (ff * GW + yy) * GW, b);
-      }
-  };
-  if (tid == 0) {
+  if (warp == QR) {
+    // =============================== producer ===============================
+    if (lane != 0) return;
     tma_prefetch_desc(&qmap);
+    uint32_t qmask = 0, rowmask = 0;
+    int tok_q[QR], tok_k[NROW];
+#pragma unroll
+    for (int i = 0; i < QR; ++i) {
+      const int y = y0 + i * p.dh;
+      if (y < GW) qmask |= 1u << i;
+      tok_q[i] = 1 + (f * GW + y) * GW;
+    }
+#pragma unroll
+    for (int rr = 0; rr < NROW; ++rr) {
+      const int yy = y0 + (rr - (KH - 1)) * p.dh;
+      if (yy >= 0 && yy < GW) rowmask |= 1u << rr;
+      tok_k[rr] = 1 + yy * GW;
+    }
+    const uint32_t qbytes = (uint32_t)__popc(qmask) * BOX, kbytes = (uint32_t)__popc(rowmask) * BOX;
+    auto issue_q = [&](int h) {
+      mbar_arrive_expect_tx(qfull, qbytes);
+#pragma unroll
+      for (int i = 0; i < QR; ++i)
+        if ((qmask >> i) & 1) tma_load_3d(sm_u + OFF_Q + i * BOX, &qmap, qfull, h * DH, tok_q[i], b);
+    };
     issue_q(0);
-    for (int s = 0; s < NST && s < NS; ++s) issue_step(s);
+    int h = 0, ai = 0, ph = 0, st = 0, use = 0;
+    for (int s = 0; s < NS; ++s) {
+      if (ph == 0 && ai == 0 && h >= 1) {  // every query-row warp holds the previous head's Q fragments in registers
+        mbar_wait(qempty, (h - 1) & 1);
+        issue_q(h);
+      }
+      if (use >= 1) mbar_wait(&empty[st], (use - 1) & 1);
+      const int ff = f - (kt - 1 - (a_lo + ai)) * p.dt;
+      mbar_arrive_expect_tx(&full[st], kbytes);
+      const int chan = (ph ? p.voff : p.koff) + h * DH;
+      const int tokf = ff * GW * GW;
+#pragma unroll
+      for (int rr = 0; rr < NROW; ++rr)
+        if ((rowmask >> rr) & 1) tma_load_3d(sm_u + st * STAGE + rr * BOX, &qmap, &full[st], chan, tokf + tok_k[rr], b);
+      if (++st == NST) { st = 0; ++use; }
+      if (++ai == n_a) { ai = 0; if (++h == NH) { h = 0; ph = 1; } }
+    }
+    return;
+  }
+
+  // =============================== query-row warps ===============================
+  const int yq = y0 + warp * p.dh;
+  const int vbase = (f * GW + yq) * GW;                 // video index of this warp's x = 0
+  const bool wactive = (yq < GW) && (vbase < p.nv);     // warp has at least one real query
+  const bool ok0 = wactive && (vbase + g < p.nv), ok1 = wactive && (vbase + g + 8 < p.nv);
+  bool blk_ok[KH];
+#pragma unroll
+  for (int bq = 0; bq < KH; ++bq) {
+    const int yy = yq - (KH - 1 - bq) * p.dh;
+    blk_ok[bq] = wactive && yy >= 0;
   }
   // the bos query (sequence row 0) attends only to itself (nuwa_pytorch.py:608): copy its value row
   if (f == 0 && y0 == 0 && warp == 0) {
@@ -192,9 +231,12 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
     for (int c = lane; c < INNER / 2; c += 32) dst[c] = reinterpret_cast<const uint32_t*>(vbos)[c];
   }
 
+  float* Sw = S32 + warp * GW * SP;
+  __half* Pw = P16 + (size_t)warp * GW * PP;  // + h * QR*GW*PP
   // ---- per-lane band table: the 8 (query x, key x') pairs of a 16x16 block this lane holds, both as C fragment
-  //      (scores) and as A fragment (probabilities): idx = nt*4 + e <-> x = g + 8*(e>>1), x' = nt*8 + 2t + (e&1) ----
-  int cb[8];
+  //      (scores) and as A fragment (probabilities): idx = nt*4 + e <-> x = g + 8*(e>>1), x' = nt*8 + 2t + (e&1).
+  //      In-band entries address slot sbase + c; the others a trash slot (scores) / the always-zero slot (P). ----
+  uint32_t s_addr[8], p_addr[8], inc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int x = g + 8 * ((i & 3) >> 1);
@@ -202,31 +244,35 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
     const int delta = x - xp;  // causal: key column = x - (kw-1-c)*dw
     int c = -1;
     if (delta >= 0 && delta % p.dw == 0 && delta / p.dw <= kw - 1) c = kw - 1 - delta / p.dw;
-    cb[i] = c;
+    inc[i] = c >= 0 ? 1u : 0u;
+    s_addr[i] = smem_u32(Sw) + 4u * (x * SP + (c >= 0 ? c : SP - 1));
+    p_addr[i] = smem_u32(Pw) + 2u * (x * PP + (c >= 0 ? c : ZSLOT));
   }
   // ldmatrix lane addressing inside a [16 rows x 128 B] SWIZZLE_128B box
   const int mat = lane >> 3, l7 = lane & 7;
   const int k_row = ((mat >> 1) << 3) + l7, k_ch = mat & 1;   // K (B operand): m0,m1 = keys 0-7 (k lo, hi); m2,m3 = keys 8-15
   const int a_row = ((mat & 1) << 3) + l7, a_ch = mat >> 1;   // Q (A operand) and V^T: m0,m1 = rows 0-7 / 8-15 of chunk c
-  const uint32_t k_lane = k_row * 128, a_lane = a_row * 128;
+  uint32_t k_sw[4], a_sw[4];                                  // swizzled byte offsets of the four 32-B chunk pairs
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    k_sw[i] = k_row * 128 + (((2 * i + k_ch) ^ l7) << 4);
+    a_sw[i] = a_row * 128 + (((2 * i + a_ch) ^ l7) << 4);
+  }
 
-  float* Sw = S32 + warp * GW * SP;
-  __half* Pw = P16 + (size_t)warp * GW * PP;  // + h * QR*GW*PP
   uint32_t qa[4][4];
   float o[8][4];
-
+  int h = 0, ai = 0, ph = 0, st = 0, par = 0;
   for (int s = 0; s < NS; ++s) {
-    const int ph = s >= NS1 ? 1 : 0;
-    const int r2 = s - ph * NS1;
-    const int h = r2 / n_a, ai = r2 - h * n_a, a = a_lo + ai;
-    const int st = s % NST;
-    const uint32_t stage = sm_u + st * STAGE;
+    const uint32_t stage = sm_u + st * STAGE + warp * BOX;  // key row rr = warp + bq
+    const int sbase0 = 1 + (a_lo + ai) * KH * kw;
 
     if (ph == 0 && ai == 0) {  // head start: Q fragments + bos score
-      mbar_wait(qbar, h & 1);
+      mbar_wait(qfull, h & 1);
       const uint32_t qb = sm_u + OFF_Q + warp * BOX;
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) ldsm4(qa[ks], qb + a_lane + (((2 * ks + a_ch) ^ l7) << 4));
+      for (int ks = 0; ks < 4; ++ks) ldsm4(qa[ks], qb + a_sw[ks]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qempty);
       float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
@@ -247,87 +293,80 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
       for (int nd = 0; nd < 8; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
     }
 
-    mbar_wait(&full[st], (s / NST) & 1);
+    mbar_wait(&full[st], par);
 
-    if (wactive) {
-      if (ph == 0) {
-        for (int bq = 0; bq < kh; ++bq) {
-          const int rr = warp + bq;
-          if (!((rowmask >> rr) & 1)) continue;
-          const uint32_t kb = stage + rr * BOX + k_lane;
-          float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ph == 0) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            uint32_t r[4];
-            ldsm4(r, kb + (((2 * ks + k_ch) ^ l7) << 4));
-            mma16816(c0, qa[ks], r[0], r[1]);
-            mma16816(c1, qa[ks], r[2], r[3]);
-          }
-          const int sbase = 1 + (a * kh + bq) * kw;
+      for (int bq = 0; bq < KH; ++bq) {
+        if (!blk_ok[bq]) continue;
+        const uint32_t kb = stage + bq * BOX;
+        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int x = g + 8 * (e >> 1);
-            if (cb[e] >= 0) Sw[x * SP + sbase + cb[e]] = c0[e];
-            if (cb[4 + e] >= 0) Sw[x * SP + sbase + cb[4 + e]] = c1[e];
-          }
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t r[4];
+          ldsm4(r, kb + k_sw[ks]);
+          mma16816(c0, qa[ks], r[0], r[1]);
+          mma16816(c1, qa[ks], r[2], r[3]);
         }
-      } else {
-        const unsigned short* Pg = reinterpret_cast<const unsigned short*>(Pw + (size_t)h * QR * GW * PP);
-        for (int bq = 0; bq < kh; ++bq) {
-          const int rr = warp + bq;
-          if (!((rowmask >> rr) & 1)) continue;
-          const uint32_t vb = stage + rr * BOX + a_lane;
-          const int sbase = 1 + (a * kh + bq) * kw;
-          unsigned short av[8];
+        const uint32_t sb4 = 4u * (sbase0 + bq * kw);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int x = g + 8 * ((i & 3) >> 1);
-            av[i] = Pg[x * PP + (cb[i] >= 0 ? sbase + cb[i] : ZSLOT)];
-          }
-          uint32_t af[4];
-          af[0] = (uint32_t)av[0] | ((uint32_t)av[1] << 16);  // row g,   keys 2t, 2t+1
-          af[1] = (uint32_t)av[2] | ((uint32_t)av[3] << 16);  // row g+8, keys 2t, 2t+1
-          af[2] = (uint32_t)av[4] | ((uint32_t)av[5] << 16);  // row g,   keys 2t+8, 2t+9
-          af[3] = (uint32_t)av[6] | ((uint32_t)av[7] << 16);  // row g+8, keys 2t+8, 2t+9
+        for (int e = 0; e < 4; ++e) {
+          sts_f32(s_addr[e] + inc[e] * sb4, c0[e]);
+          sts_f32(s_addr[4 + e] + inc[4 + e] * sb4, c1[e]);
+        }
+      }
+    } else {
+      const uint32_t hoff = (uint32_t)h * (QR * GW * PP * 2);
 #pragma unroll
-          for (int pr = 0; pr < 4; ++pr) {
-            uint32_t r[4];
-            ldsm4t(r, vb + (((2 * pr + a_ch) ^ l7) << 4));
-            mma16816(o[2 * pr], af, r[0], r[1]);
-            mma16816(o[2 * pr + 1], af, r[2], r[3]);
-          }
+      for (int bq = 0; bq < KH; ++bq) {
+        if (!blk_ok[bq]) continue;
+        const uint32_t vb = stage + bq * BOX;
+        const uint32_t sb2 = 2u * (sbase0 + bq * kw);
+        uint32_t av[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) av[i] = lds_u16(p_addr[i] + hoff + inc[i] * sb2);
+        uint32_t af[4];
+        af[0] = av[0] | (av[1] << 16);  // row g,   keys 2t, 2t+1
+        af[1] = av[2] | (av[3] << 16);  // row g+8, keys 2t, 2t+1
+        af[2] = av[4] | (av[5] << 16);  // row g,   keys 2t+8, 2t+9
+        af[3] = av[6] | (av[7] << 16);  // row g+8, keys 2t+8, 2t+9
+#pragma unroll
+        for (int pr = 0; pr < 4; ++pr) {
+          uint32_t r[4];
+          ldsm4t(r, vb + a_sw[pr]);
+          mma16816(o[2 * pr], af, r[0], r[1]);
+          mma16816(o[2 * pr + 1], af, r[2], r[3]);
         }
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with the stage
 
     if (ph == 0 && ai == n_a - 1) {
-      // ---- head end: fp32 softmax of the 16 score rows -> P[h] (fp16); two lanes per row, interleaved slots ----
-      __syncwarp();
+      // ---- head end: fp32 softmax of the 16 score rows -> P[h] (fp16); two lanes per row, interleaved slots.
+      //      Slots J..47 hold the initial -FLT_MAX (never written) -> probability 0. ----
       const int x = lane >> 1, half = lane & 1;
-      const float* row = Sw + x * SP;
+      const float* row = Sw + x * SP + half;
       float v[MAXJ / 2];
       float m = -FLT_MAX;
 #pragma unroll
       for (int i = 0; i < MAXJ / 2; ++i) {
-        const int j = 2 * i + half;
-        v[i] = j < p.J ? row[j] : -FLT_MAX;
+        v[i] = row[2 * i];
         m = fmaxf(m, v[i]);
       }
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      const float mneg = -m * p.scale_log2e;
       float l = 0.f;
 #pragma unroll
       for (int i = 0; i < MAXJ / 2; ++i) {
-        v[i] = exp2f((v[i] - m) * p.scale_log2e);  // masked slots: exp2(-huge) == 0
+        v[i] = exp2f(fmaf(v[i], p.scale_log2e, mneg));  // masked slots: exp2(-huge) == 0
         l += v[i];
       }
       l += __shfl_xor_sync(0xffffffffu, l, 1);
       const float inv = 1.0f / l;
-      __half* prow = Pw + (size_t)h * QR * GW * PP + x * PP;
+      __half* prow = Pw + (size_t)h * QR * GW * PP + x * PP + half;
 #pragma unroll
-      for (int i = 0; i < MAXJ / 2; ++i) {
-        const int j = 2 * i + half;
-        if (j < p.J) prow[j] = __float2half_rn(v[i] * inv);
-      }
+      for (int i = 0; i < MAXJ / 2; ++i) prow[2 * i] = __float2half_rn(v[i] * inv);
       __syncwarp();
       if (h == NH - 1) {
         // ---- talking heads (nuwa_pytorch.py:556-558): P'[g][x][j] = sum_h W[g][h] P[h][x][j]; slot pairs, in place ----
@@ -337,27 +376,27 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
           const float4 w4 = reinterpret_cast<const float4*>(Wsm)[i];
           W[4 * i] = w4.x; W[4 * i + 1] = w4.y; W[4 * i + 2] = w4.z; W[4 * i + 3] = w4.w;
         }
-        constexpr int NPAIR = MAXJ / 2;
-        for (int pi = lane; pi < GW * NPAIR; pi += 32) {
-          const int xx = pi / NPAIR, jp = pi - xx * NPAIR;
-          uint32_t* base = reinterpret_cast<uint32_t*>(Pw + xx * PP + 2 * jp);
-          float2 pin[NH];
-#pragma unroll
-          for (int hh = 0; hh < NH; ++hh) {
-            const uint32_t u = base[hh * (QR * GW * PP / 2)];
-            pin[hh] = __half22float2(*reinterpret_cast<const __half2*>(&u));
-          }
-#pragma unroll
-          for (int gh = 0; gh < NH; ++gh) {
-            float ax = 0.f, ay = 0.f;
+        const int npair = (p.J + 1) >> 1;
+        for (int xx = lane >> 3; xx < GW; xx += 4)
+          for (int jp = lane & 7; jp < npair; jp += 8) {
+            uint32_t* base = reinterpret_cast<uint32_t*>(Pw + xx * PP + 2 * jp);
+            float2 pin[NH];
 #pragma unroll
             for (int hh = 0; hh < NH; ++hh) {
-              ax = fmaf(W[gh * NH + hh], pin[hh].x, ax);
-              ay = fmaf(W[gh * NH + hh], pin[hh].y, ay);
+              const uint32_t u = base[hh * (QR * GW * PP / 2)];
+              pin[hh] = __half22float2(*reinterpret_cast<const __half2*>(&u));
             }
-            base[gh * (QR * GW * PP / 2)] = pack_bf16x2(ax, ay);
+#pragma unroll
+            for (int gh = 0; gh < NH; ++gh) {
+              float ax = 0.f, ay = 0.f;
+#pragma unroll
+              for (int hh = 0; hh < NH; ++hh) {
+                ax = fmaf(W[gh * NH + hh], pin[hh].x, ax);
+                ay = fmaf(W[gh * NH + hh], pin[hh].y, ay);
+              }
+              base[gh * (QR * GW * PP / 2)] = pack_bf16x2(ax, ay);
+            }
           }
-        }
         __syncwarp();
       }
     }
@@ -377,12 +416,8 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
               pack_bf16x2(fmaf(pb1, vb.x, o[nd][2]), fmaf(pb1, vb.y, o[nd][3]));
       }
     }
-
-    __syncthreads();  // every warp is done with this stage (and, at a head start, with the Q buffer)
-    if (tid == 0) {
-      if (s + NST < NS) issue_step(s + NST);
-      if (ph == 0 && ai == 0 && h + 1 < NH) issue_q(h + 1);
-    }
+    if (++st == NST) { st = 0; par ^= 1; }
+    if (++ai == n_a) { ai = 0; if (++h == NH) { h = 0; ph = 1; } }
   }
 }
 
@@ -428,15 +463,23 @@ int attn_3dna_halo(const AttnParams& p, cudaStream_t stream) {
   a.o = reinterpret_cast<bf16*>(p.o); a.o_bs = p.o_bs; a.o_rs = p.o_rs;
   a.k0 = k; a.v0 = v; a.k_bs = p.k_bs; a.v_bs = p.v_bs;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_3dna_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
-      return NUWA_ERR_CUDA;
-    cudaFuncSetAttribute(attn_3dna_halo_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_set = true;
-  }
   const int grid = a.nf * a.tiles * a.B;
-  attn_3dna_halo_kernel<<<grid, QR * 32, SMEM_BYTES, stream>>>(map, a);
+  static bool attr_set[4] = {false, false, false, false};
+  auto launch = [&](void (*kern)(const CUtensorMap, const HaloArgs)) -> int {
+    if (!attr_set[p.kh]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+        return NUWA_ERR_CUDA;
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      attr_set[p.kh] = true;
+    }
+    kern<<<grid, (QR + 1) * 32, SMEM_BYTES, stream>>>(map, a);
+    return NUWA_OK;
+  };
+  int lrc;
+  if (p.kh == 1) lrc = launch(attn_3dna_halo_kernel<1>);
+  else if (p.kh == 2) lrc = launch(attn_3dna_halo_kernel<2>);
+  else lrc = launch(attn_3dna_halo_kernel<3>);
+  if (lrc != NUWA_OK) return lrc;
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
 }

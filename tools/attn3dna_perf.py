@@ -18,7 +18,7 @@ talk = torch.randn(H, H, device=dev) / 2
 o = torch.empty(B, n, inner, dtype=torch.bfloat16, device=dev)
 rows = []
 for dil in (1, 2, 4):
-    for name in ('gather', 'tensor-core', 'halo'):
+    for name in (sys.argv[1:] or ['gather', 'tensor-core', 'halo']):
         def run():
             ops.attn_sparse3dna(qkv, o, B=B, nq=n, t0=0, npos=n, H=H, dh=dh, talk=talk, fmap=16, max_frames=10, nv=nv,
                                 kernel=(5, 3, 3), dilation=(dil,) * 3, causal=True, use_tc=name == 'tensor-core',
