@@ -87,6 +87,7 @@ struct HaloArgs {
   const bf16* k0;  // k of sequence row 0 (bos), sample 0
   const bf16* v0;
   long long k_bs, v_bs;
+  long long* dbg;  // tools/halo_stamps.py: clock64 stamps of CTA 0 / warp 0 (NULL in normal use)
 };
 
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
@@ -100,7 +101,7 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 
 // Warps 0..QR-1: one query row each.  Warp QR: TMA producer (one lane).  Stage hand-over through full / empty
 // mbarriers, so the query-row warps never wait for each other.
-template <int KH>
+template <int KH, bool DBG>
 __global__ void __launch_bounds__((QR + 1) * 32, 2)
 attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p) {
   constexpr int NROW = QR + KH - 1;
@@ -120,6 +121,7 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
+  const long long t_start = clock64();
 
   // ---- which tile: heaviest frames first (later frames see more key frames) ----
   const int per_f = p.tiles * p.B;
@@ -195,12 +197,21 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
     };
     issue_q(0);
     int h = 0, ai = 0, ph = 0, st = 0, use = 0;
+    long long prod_wait = 0;
     for (int s = 0; s < NS; ++s) {
       if (ph == 0 && ai == 0 && h >= 1) {  // every query-row warp holds the previous head's Q fragments in registers
         mbar_wait(qempty, (h - 1) & 1);
         issue_q(h);
       }
-      if (use >= 1) mbar_wait(&empty[st], (use - 1) & 1);
+      if (use >= 1) {
+        if (DBG && p.dbg != nullptr && blockIdx.x == 0) {
+          const long long t0 = clock64();
+          mbar_wait(&empty[st], (use - 1) & 1);
+          prod_wait += clock64() - t0;
+        } else {
+          mbar_wait(&empty[st], (use - 1) & 1);
+        }
+      }
       const int ff = f - (kt - 1 - (a_lo + ai)) * p.dt;
       mbar_arrive_expect_tx(&full[st], kbytes);
       const int chan = (ph ? p.voff : p.koff) + h * DH;
@@ -211,6 +222,7 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
       if (++st == NST) { st = 0; ++use; }
       if (++ai == n_a) { ai = 0; if (++h == NH) { h = 0; ph = 1; } }
     }
+    if (DBG && p.dbg != nullptr && blockIdx.x == 0) p.dbg[23] = prod_wait;
     return;
   }
 
@@ -225,6 +237,7 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
     const int yy = yq - (KH - 1 - bq) * p.dh;
     blk_ok[bq] = wactive && yy >= 0;
   }
+  const bool all_ok = blk_ok[0];  // the earliest key row is in the grid -> every block is
   // the bos query (sequence row 0) attends only to itself (nuwa_pytorch.py:608): copy its value row
   if (f == 0 && y0 == 0 && warp == 0) {
     uint32_t* dst = reinterpret_cast<uint32_t*>(p.o + (long long)b * p.o_bs);
@@ -247,6 +260,8 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
     inc[i] = c >= 0 ? 1u : 0u;
     s_addr[i] = smem_u32(Sw) + 4u * (x * SP + (c >= 0 ? c : SP - 1));
     p_addr[i] = smem_u32(Pw) + 2u * (x * PP + (c >= 0 ? c : ZSLOT));
+    // keep the tables in registers (ptxas otherwise rematerialises them in every block: +15 integer ops per block)
+    asm volatile("" : "+r"(inc[i]), "+r"(s_addr[i]), "+r"(p_addr[i]));
   }
   // ldmatrix lane addressing inside a [16 rows x 128 B] SWIZZLE_128B box
   const int mat = lane >> 3, l7 = lane & 7;
@@ -257,22 +272,37 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
   for (int i = 0; i < 4; ++i) {
     k_sw[i] = k_row * 128 + (((2 * i + k_ch) ^ l7) << 4);
     a_sw[i] = a_row * 128 + (((2 * i + a_ch) ^ l7) << 4);
+    asm volatile("" : "+r"(k_sw[i]), "+r"(a_sw[i]));
   }
+  const uint32_t stage0 = sm_u + warp * BOX;  // key row rr = warp + bq of a stage
+  const int sbase_lo = 1 + a_lo * KH * kw, sbase_step = KH * kw;
 
-  uint32_t qa[4][4];
-  float o[8][4];
-  int h = 0, ai = 0, ph = 0, st = 0, par = 0;
-  for (int s = 0; s < NS; ++s) {
-    const uint32_t stage = sm_u + st * STAGE + warp * BOX;  // key row rr = warp + bq
-    const int sbase0 = 1 + (a_lo + ai) * KH * kw;
+  const bool dbg = DBG && p.dbg != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
+  long long wait_cyc[2] = {0, 0};
+  if (dbg) { p.dbg[0] = t_start; p.dbg[1] = clock64(); }
+  auto wait_full = [&](int st, int par, int ph) {
+    if (DBG && dbg) {
+      const long long t0 = clock64();
+      mbar_wait(&full[st], par);
+      wait_cyc[ph] += clock64() - t0;
+    } else {
+      mbar_wait(&full[st], par);
+    }
+  };
 
-    if (ph == 0 && ai == 0) {  // head start: Q fragments + bos score
-      mbar_wait(qfull, h & 1);
+  int st = 0, par = 0;
+  // ================= phase 1: scores + softmax, head by head =================
+  for (int h = 0; h < NH; ++h) {
+    uint32_t qa[4][4];
+    mbar_wait(qfull, h & 1);
+    {
       const uint32_t qb = sm_u + OFF_Q + warp * BOX;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) ldsm4(qa[ks], qb + a_sw[ks]);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(qempty);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(qempty);
+    {  // bos key (slot 0): a block whose only non-zero key column is 0
       float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
@@ -288,119 +318,194 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
         Sw[(g + 8) * SP] = c[2];
       }
     }
-    if (ph == 1 && ai == 0) {
+    int sbase0 = sbase_lo;
+    for (int ai = 0; ai < n_a; ++ai, sbase0 += sbase_step) {
+      const uint32_t stage = stage0 + st * STAGE;
+      wait_full(st, par, 0);
+      if (all_ok) {
+        // Hand-scheduled (the ldmatrix / mma / st.shared wrappers are volatile asm, so program order is issue
+        // order): all operand loads of the KH blocks first, then the MMAs interleaved so that dependent ones are
+        // KH issue slots apart, then the stores.  A warp issues in order; block-after-block costs a full
+        // ldmatrix + 4-deep HMMA chain latency per block.
+        uint32_t kf[KH][4][4];
 #pragma unroll
-      for (int nd = 0; nd < 8; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
-    }
-
-    mbar_wait(&full[st], par);
-
-    if (ph == 0) {
+        for (int bq = 0; bq < KH; ++bq)
 #pragma unroll
-      for (int bq = 0; bq < KH; ++bq) {
-        if (!blk_ok[bq]) continue;
-        const uint32_t kb = stage + bq * BOX;
-        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int ks = 0; ks < 4; ++ks) ldsm4(kf[bq][ks], stage + bq * BOX + k_sw[ks]);
+        float c0[KH][4], c1[KH][4];
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint32_t r[4];
-          ldsm4(r, kb + k_sw[ks]);
-          mma16816(c0, qa[ks], r[0], r[1]);
-          mma16816(c1, qa[ks], r[2], r[3]);
+        for (int bq = 0; bq < KH; ++bq)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) c0[bq][e] = c1[bq][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+          for (int bq = 0; bq < KH; ++bq) {
+            mma16816(c0[bq], qa[ks], kf[bq][ks][0], kf[bq][ks][1]);
+            mma16816(c1[bq], qa[ks], kf[bq][ks][2], kf[bq][ks][3]);
+          }
+#pragma unroll
+        for (int bq = 0; bq < KH; ++bq) {
+          const uint32_t sb4 = 4u * (sbase0 + bq * kw);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            sts_f32(s_addr[e] + inc[e] * sb4, c0[bq][e]);
+            sts_f32(s_addr[4 + e] + inc[4 + e] * sb4, c1[bq][e]);
+          }
         }
-        const uint32_t sb4 = 4u * (sbase0 + bq * kw);
+      } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          sts_f32(s_addr[e] + inc[e] * sb4, c0[e]);
-          sts_f32(s_addr[4 + e] + inc[4 + e] * sb4, c1[e]);
+        for (int bq = 0; bq < KH; ++bq) {
+          if (!blk_ok[bq]) continue;
+          const uint32_t kb = stage + bq * BOX;
+          float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            uint32_t r[4];
+            ldsm4(r, kb + k_sw[ks]);
+            mma16816(c0, qa[ks], r[0], r[1]);
+            mma16816(c1, qa[ks], r[2], r[3]);
+          }
+          const uint32_t sb4 = 4u * (sbase0 + bq * kw);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            sts_f32(s_addr[e] + inc[e] * sb4, c0[e]);
+            sts_f32(s_addr[4 + e] + inc[4 + e] * sb4, c1[e]);
+          }
         }
       }
-    } else {
-      const uint32_t hoff = (uint32_t)h * (QR * GW * PP * 2);
-#pragma unroll
-      for (int bq = 0; bq < KH; ++bq) {
-        if (!blk_ok[bq]) continue;
-        const uint32_t vb = stage + bq * BOX;
-        const uint32_t sb2 = 2u * (sbase0 + bq * kw);
-        uint32_t av[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) av[i] = lds_u16(p_addr[i] + hoff + inc[i] * sb2);
-        uint32_t af[4];
-        af[0] = av[0] | (av[1] << 16);  // row g,   keys 2t, 2t+1
-        af[1] = av[2] | (av[3] << 16);  // row g+8, keys 2t, 2t+1
-        af[2] = av[4] | (av[5] << 16);  // row g,   keys 2t+8, 2t+9
-        af[3] = av[6] | (av[7] << 16);  // row g+8, keys 2t+8, 2t+9
-#pragma unroll
-        for (int pr = 0; pr < 4; ++pr) {
-          uint32_t r[4];
-          ldsm4t(r, vb + a_sw[pr]);
-          mma16816(o[2 * pr], af, r[0], r[1]);
-          mma16816(o[2 * pr + 1], af, r[2], r[3]);
-        }
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with the stage
+      if (++st == NST) { st = 0; par ^= 1; }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with the stage
-
-    if (ph == 0 && ai == n_a - 1) {
-      // ---- head end: fp32 softmax of the 16 score rows -> P[h] (fp16); two lanes per row, interleaved slots.
-      //      Slots J..47 hold the initial -FLT_MAX (never written) -> probability 0. ----
+    // ---- head end: fp32 softmax of the 16 score rows -> P[h] (fp16); two lanes per row, interleaved slots.
+    //      Slots J..47 hold the initial -FLT_MAX (never written) -> probability 0. ----
+    {
       const int x = lane >> 1, half = lane & 1;
       const float* row = Sw + x * SP + half;
       float v[MAXJ / 2];
-      float m = -FLT_MAX;
 #pragma unroll
-      for (int i = 0; i < MAXJ / 2; ++i) {
-        v[i] = row[2 * i];
-        m = fmaxf(m, v[i]);
-      }
+      for (int i = 0; i < MAXJ / 2; ++i) v[i] = row[2 * i];
+      float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+#pragma unroll
+      for (int i = 0; i < MAXJ / 2; ++i) m4[i & 3] = fmaxf(m4[i & 3], v[i]);
+      float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
       const float mneg = -m * p.scale_log2e;
-      float l = 0.f;
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < MAXJ / 2; ++i) {
         v[i] = exp2f(fmaf(v[i], p.scale_log2e, mneg));  // masked slots: exp2(-huge) == 0
-        l += v[i];
+        l4[i & 3] += v[i];
       }
+      float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       l += __shfl_xor_sync(0xffffffffu, l, 1);
       const float inv = 1.0f / l;
       __half* prow = Pw + (size_t)h * QR * GW * PP + x * PP + half;
 #pragma unroll
       for (int i = 0; i < MAXJ / 2; ++i) prow[2 * i] = __float2half_rn(v[i] * inv);
       __syncwarp();
-      if (h == NH - 1) {
-        // ---- talking heads (nuwa_pytorch.py:556-558): P'[g][x][j] = sum_h W[g][h] P[h][x][j]; slot pairs, in place ----
-        float W[NH * NH];
-#pragma unroll
-        for (int i = 0; i < NH * NH / 4; ++i) {
-          const float4 w4 = reinterpret_cast<const float4*>(Wsm)[i];
-          W[4 * i] = w4.x; W[4 * i + 1] = w4.y; W[4 * i + 2] = w4.z; W[4 * i + 3] = w4.w;
-        }
-        const int npair = (p.J + 1) >> 1;
-        for (int xx = lane >> 3; xx < GW; xx += 4)
-          for (int jp = lane & 7; jp < npair; jp += 8) {
-            uint32_t* base = reinterpret_cast<uint32_t*>(Pw + xx * PP + 2 * jp);
-            float2 pin[NH];
-#pragma unroll
-            for (int hh = 0; hh < NH; ++hh) {
-              const uint32_t u = base[hh * (QR * GW * PP / 2)];
-              pin[hh] = __half22float2(*reinterpret_cast<const __half2*>(&u));
-            }
-#pragma unroll
-            for (int gh = 0; gh < NH; ++gh) {
-              float ax = 0.f, ay = 0.f;
-#pragma unroll
-              for (int hh = 0; hh < NH; ++hh) {
-                ax = fmaf(W[gh * NH + hh], pin[hh].x, ax);
-                ay = fmaf(W[gh * NH + hh], pin[hh].y, ay);
-              }
-              base[gh * (QR * GW * PP / 2)] = pack_bf16x2(ax, ay);
-            }
-          }
-        __syncwarp();
-      }
     }
-    if (ph == 1 && ai == n_a - 1 && wactive) {
+    if (dbg) p.dbg[2 + h] = clock64();
+  }
+
+  // ================= talking heads (nuwa_pytorch.py:556-558): P'[g][x][j] = sum_h W[g][h] P[h][x][j] =================
+  {
+    float W[NH * NH];
+#pragma unroll
+    for (int i = 0; i < NH * NH / 4; ++i) {
+      const float4 w4 = reinterpret_cast<const float4*>(Wsm)[i];
+      W[4 * i] = w4.x; W[4 * i + 1] = w4.y; W[4 * i + 2] = w4.z; W[4 * i + 3] = w4.w;
+    }
+    const int npair = (p.J + 1) >> 1;  // slot pairs, in place (each thread reads its 8 inputs before writing)
+    for (int xx = lane >> 3; xx < GW; xx += 4)
+      for (int jp = lane & 7; jp < npair; jp += 8) {
+        uint32_t* base = reinterpret_cast<uint32_t*>(Pw + xx * PP + 2 * jp);
+        float2 pin[NH];
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+          const uint32_t u = base[hh * (QR * GW * PP / 2)];
+          pin[hh] = __half22float2(*reinterpret_cast<const __half2*>(&u));
+        }
+#pragma unroll
+        for (int gh = 0; gh < NH; ++gh) {
+          float ax = 0.f, ay = 0.f;
+#pragma unroll
+          for (int hh = 0; hh < NH; ++hh) {
+            ax = fmaf(W[gh * NH + hh], pin[hh].x, ax);
+            ay = fmaf(W[gh * NH + hh], pin[hh].y, ay);
+          }
+          base[gh * (QR * GW * PP / 2)] = pack_bf16x2(ax, ay);
+        }
+      }
+    __syncwarp();
+    if (dbg) p.dbg[10] = clock64();
+  }
+
+  // ================= phase 3: O[g] = P'[g] V[g], head by head =================
+  for (int h = 0; h < NH; ++h) {
+    float o[8][4];
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+    const uint32_t hoff = (uint32_t)h * (QR * GW * PP * 2);
+    int sbase0 = sbase_lo;
+    for (int ai = 0; ai < n_a; ++ai, sbase0 += sbase_step) {
+      const uint32_t stage = stage0 + st * STAGE;
+      wait_full(st, par, 1);
+      if (all_ok) {  // hand-scheduled like phase 1: loads, then MMAs with 8 slots between dependent ones
+        uint32_t av[KH][8];
+#pragma unroll
+        for (int bq = 0; bq < KH; ++bq) {
+          const uint32_t sb2 = 2u * (sbase0 + bq * kw);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) av[bq][i] = lds_u16(p_addr[i] + hoff + inc[i] * sb2);
+        }
+        uint32_t vf[KH][4][4];
+#pragma unroll
+        for (int bq = 0; bq < KH; ++bq)
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) ldsm4t(vf[bq][pr], stage + bq * BOX + a_sw[pr]);
+#pragma unroll
+        for (int bq = 0; bq < KH; ++bq) {
+          uint32_t af[4];
+          af[0] = av[bq][0] | (av[bq][1] << 16);  // row g,   keys 2t, 2t+1
+          af[1] = av[bq][2] | (av[bq][3] << 16);  // row g+8, keys 2t, 2t+1
+          af[2] = av[bq][4] | (av[bq][5] << 16);  // row g,   keys 2t+8, 2t+9
+          af[3] = av[bq][6] | (av[bq][7] << 16);  // row g+8, keys 2t+8, 2t+9
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) {
+            mma16816(o[2 * pr], af, vf[bq][pr][0], vf[bq][pr][1]);
+            mma16816(o[2 * pr + 1], af, vf[bq][pr][2], vf[bq][pr][3]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int bq = 0; bq < KH; ++bq) {
+          if (!blk_ok[bq]) continue;
+          const uint32_t vb = stage + bq * BOX;
+          const uint32_t sb2 = 2u * (sbase0 + bq * kw);
+          uint32_t av[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) av[i] = lds_u16(p_addr[i] + hoff + inc[i] * sb2);
+          uint32_t af[4];
+          af[0] = av[0] | (av[1] << 16);
+          af[1] = av[2] | (av[3] << 16);
+          af[2] = av[4] | (av[5] << 16);
+          af[3] = av[6] | (av[7] << 16);
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) {
+            uint32_t r[4];
+            ldsm4t(r, vb + a_sw[pr]);
+            mma16816(o[2 * pr], af, r[0], r[1]);
+            mma16816(o[2 * pr + 1], af, r[2], r[3]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
+      if (++st == NST) { st = 0; par ^= 1; }
+    }
+    if (wactive) {
       // ---- output head h: add the bos value (slot 0) and store ----
       const bf16* Pg = reinterpret_cast<const bf16*>(Pw + (size_t)h * QR * GW * PP);
       const float pb0 = __bfloat162float(Pg[g * PP]), pb1 = __bfloat162float(Pg[(g + 8) * PP]);
@@ -416,12 +521,18 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
               pack_bf16x2(fmaf(pb1, vb.x, o[nd][2]), fmaf(pb1, vb.y, o[nd][3]));
       }
     }
-    if (++st == NST) { st = 0; par ^= 1; }
-    if (++ai == n_a) { ai = 0; if (++h == NH) { h = 0; ph = 1; } }
+    if (dbg) p.dbg[11 + h] = clock64();
   }
+  if (dbg) { p.dbg[19] = clock64(); p.dbg[20] = wait_cyc[0]; p.dbg[21] = wait_cyc[1]; p.dbg[22] = NS; }
 }
 
+
+long long* g_halo_dbg = nullptr;
+
 }  // namespace
+
+// measurement aid (tools/halo_stamps.py; not part of include/nuwa_b200.h): 24 int64 of device memory or NULL
+extern "C" void nuwa_debug_halo_stamps(long long* dev_ptr) { g_halo_dbg = dev_ptr; }
 
 // Envelope: causal full pass (t0 == 0, nq == nv + 1) over a 16-wide token grid, H == 8, dh == 64, kh <= 3,
 // window <= 47 keys, q|k|v rows sharing one token stride.  NUWA_ERR_INVALID outside it (caller falls back).
@@ -462,23 +573,25 @@ int attn_3dna_halo(const AttnParams& p, cudaStream_t stream) {
   a.talk = p.talk;
   a.o = reinterpret_cast<bf16*>(p.o); a.o_bs = p.o_bs; a.o_rs = p.o_rs;
   a.k0 = k; a.v0 = v; a.k_bs = p.k_bs; a.v_bs = p.v_bs;
+  a.dbg = g_halo_dbg;
 
   const int grid = a.nf * a.tiles * a.B;
-  static bool attr_set[4] = {false, false, false, false};
-  auto launch = [&](void (*kern)(const CUtensorMap, const HaloArgs)) -> int {
-    if (!attr_set[p.kh]) {
+  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+  auto launch = [&](void (*kern)(const CUtensorMap, const HaloArgs), int slot) -> int {
+    if (!attr_set[slot]) {
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
         return NUWA_ERR_CUDA;
       cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      attr_set[p.kh] = true;
+      attr_set[slot] = true;
     }
     kern<<<grid, (QR + 1) * 32, SMEM_BYTES, stream>>>(map, a);
     return NUWA_OK;
   };
   int lrc;
-  if (p.kh == 1) lrc = launch(attn_3dna_halo_kernel<1>);
-  else if (p.kh == 2) lrc = launch(attn_3dna_halo_kernel<2>);
-  else lrc = launch(attn_3dna_halo_kernel<3>);
+  if (a.dbg != nullptr && p.kh == 3) lrc = launch(attn_3dna_halo_kernel<3, true>, 4);  // tools/halo_stamps.py
+  else if (p.kh == 1) lrc = launch(attn_3dna_halo_kernel<1, false>, 1);
+  else if (p.kh == 2) lrc = launch(attn_3dna_halo_kernel<2, false>, 2);
+  else lrc = launch(attn_3dna_halo_kernel<3, false>, 3);
   if (lrc != NUWA_OK) return lrc;
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
