@@ -144,36 +144,11 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
   const int n_a = kt - a_lo;
   const int NS1 = NH * n_a, NS = 2 * NS1;
 
-  // ---- one-time shared-memory state ----
-  if (tid == 0) {
-    for (int i = 0; i < NST; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], QR);
-    }
-    mbar_init(qfull, 1);
-    mbar_init(qempty, QR);
-    fence_barrier_init();
-  }
-  if (warp < QR) {
-    float* Sw = S32 + warp * GW * SP;
-    for (int i = lane; i < GW * SP; i += 32) Sw[i] = -FLT_MAX;
-    const int nz = PP - p.J;  // slots J .. PP-1 stay zero (pair padding + the always-zero slot)
-    for (int i = lane; i < NH * GW * nz; i += 32) {
-      const int row = i / nz, z = i - row * nz;
-      const int h = row / GW, x = row - h * GW;
-      P16[(size_t)(h * QR * GW + warp * GW + x) * PP + p.J + z] = __float2half(0.f);
-    }
-    // bos key / value rows of this sample (sequence row 0), all heads
-    const uint4* src = reinterpret_cast<const uint4*>(tid < 64 ? p.k0 + (long long)b * p.k_bs : p.v0 + (long long)b * p.v_bs);
-    reinterpret_cast<uint4*>(kbos)[tid] = __ldg(src + (tid & 63));
-    if (tid < NH * NH) Wsm[tid] = p.talk ? __ldg(p.talk + tid) : ((tid / NH) == (tid % NH) ? 1.f : 0.f);
-  }
-  __syncthreads();
-
   if (warp == QR) {
     // =============================== producer ===============================
-    if (lane != 0) return;
-    tma_prefetch_desc(&qmap);
+    // Lane 0 initialises the barriers and starts the first loads BEFORE the CTA-wide sync, so the first key rows
+    // (DRAM latency: the layer's q|k|v was just written by the projection GEMM) travel while the query-row warps
+    // set up their shared-memory state.
     uint32_t qmask = 0, rowmask = 0;
     int tok_q[QR], tok_k[NROW];
 #pragma unroll
@@ -195,36 +170,70 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
       for (int i = 0; i < QR; ++i)
         if ((qmask >> i) & 1) tma_load_3d(sm_u + OFF_Q + i * BOX, &qmap, qfull, h * DH, tok_q[i], b);
     };
-    issue_q(0);
     int h = 0, ai = 0, ph = 0, st = 0, use = 0;
     long long prod_wait = 0;
-    for (int s = 0; s < NS; ++s) {
-      if (ph == 0 && ai == 0 && h >= 1) {  // every query-row warp holds the previous head's Q fragments in registers
-        mbar_wait(qempty, (h - 1) & 1);
-        issue_q(h);
-      }
-      if (use >= 1) {
-        if (DBG && p.dbg != nullptr && blockIdx.x == 0) {
-          const long long t0 = clock64();
-          mbar_wait(&empty[st], (use - 1) & 1);
-          prod_wait += clock64() - t0;
-        } else {
-          mbar_wait(&empty[st], (use - 1) & 1);
+    auto produce = [&](int s_end) {
+      for (int s = (use * NST + st); s < s_end; ++s) {
+        if (ph == 0 && ai == 0 && h >= 1) {  // every query-row warp holds the previous head's Q fragments in registers
+          mbar_wait(qempty, (h - 1) & 1);
+          issue_q(h);
         }
-      }
-      const int ff = f - (kt - 1 - (a_lo + ai)) * p.dt;
-      mbar_arrive_expect_tx(&full[st], kbytes);
-      const int chan = (ph ? p.voff : p.koff) + h * DH;
-      const int tokf = ff * GW * GW;
+        if (use >= 1) {
+          if (DBG && p.dbg != nullptr && blockIdx.x == 0) {
+            const long long t0 = clock64();
+            mbar_wait(&empty[st], (use - 1) & 1);
+            prod_wait += clock64() - t0;
+          } else {
+            mbar_wait(&empty[st], (use - 1) & 1);
+          }
+        }
+        const int ff = f - (kt - 1 - (a_lo + ai)) * p.dt;
+        mbar_arrive_expect_tx(&full[st], kbytes);
+        const int chan = (ph ? p.voff : p.koff) + h * DH;
+        const int tokf = ff * GW * GW;
 #pragma unroll
-      for (int rr = 0; rr < NROW; ++rr)
-        if ((rowmask >> rr) & 1) tma_load_3d(sm_u + st * STAGE + rr * BOX, &qmap, &full[st], chan, tokf + tok_k[rr], b);
-      if (++st == NST) { st = 0; ++use; }
-      if (++ai == n_a) { ai = 0; if (++h == NH) { h = 0; ph = 1; } }
+        for (int rr = 0; rr < NROW; ++rr)
+          if ((rowmask >> rr) & 1) tma_load_3d(sm_u + st * STAGE + rr * BOX, &qmap, &full[st], chan, tokf + tok_k[rr], b);
+        if (++st == NST) { st = 0; ++use; }
+        if (++ai == n_a) { ai = 0; if (++h == NH) { h = 0; ph = 1; } }
+      }
+    };
+    if (lane == 0) {
+      for (int i = 0; i < NST; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], QR);
+      }
+      mbar_init(qfull, 1);
+      mbar_init(qempty, QR);
+      fence_barrier_init();
+      tma_prefetch_desc(&qmap);
+      issue_q(0);
+      produce(min(NST, n_a));  // head 0 only: later heads wait for the query-row warps, which start after the sync
     }
-    if (DBG && p.dbg != nullptr && blockIdx.x == 0) p.dbg[23] = prod_wait;
+    __syncthreads();  // pairs with the query-row warps' barrier below
+    if (lane == 0) {
+      produce(NS);
+      if (DBG && p.dbg != nullptr && blockIdx.x == 0) p.dbg[23] = prod_wait;
+    }
     return;
   }
+
+  // ---- one-time shared-memory state of the query-row warps ----
+  {
+    float* Sw = S32 + warp * GW * SP;
+    for (int i = lane; i < GW * SP; i += 32) Sw[i] = -FLT_MAX;
+    const int nz = PP - p.J;  // slots J .. PP-1 stay zero (pair padding + the always-zero slot)
+    for (int i = lane; i < NH * GW * nz; i += 32) {
+      const int row = i / nz, z = i - row * nz;
+      const int h = row / GW, x = row - h * GW;
+      P16[(size_t)(h * QR * GW + warp * GW + x) * PP + p.J + z] = __float2half(0.f);
+    }
+    // bos key / value rows of this sample (sequence row 0), all heads
+    const uint4* src = reinterpret_cast<const uint4*>(tid < 64 ? p.k0 + (long long)b * p.k_bs : p.v0 + (long long)b * p.v_bs);
+    reinterpret_cast<uint4*>(kbos)[tid] = __ldg(src + (tid & 63));
+    if (tid < NH * NH) Wsm[tid] = p.talk ? __ldg(p.talk + tid) : ((tid / NH) == (tid % NH) ? 1.f : 0.f);
+  }
+  __syncthreads();  // barriers initialised (producer), shared state written
 
   // =============================== query-row warps ===============================
   const int yq = y0 + warp * p.dh;
