@@ -148,6 +148,11 @@ int nuwa_attn_sparse3dna_halo(const nuwa_attn_params* p, void* stream);
 int nuwa_attn_dense(const nuwa_attn_params* p, void* vt_workspace, void* stream);
 /* vt_workspace: NULL, or B*H*dh*roundup(nk,64) bf16 elements of scratch; when given and nk <= 256, dh in {32,64},
  * H <= 8, nq >= 8 the tensor-core (mma.sync) variant runs, otherwise the generic CUDA-core kernel. */
+/* Same op on the probability-resident kernel (attention_dense_pres.cu): 32-query tiles, the fp16 probability slab of
+ * all 8 heads kept in shared memory, K / V streamed once per tile by TMA, talking-heads mix on the tensor cores.
+ * Envelope: H == 8, dh == 64, 1 <= keys <= 256 (p->jmax minus the null slot), no bias / head_scale; returns
+ * NUWA_ERR_INVALID outside it (nothing launched). */
+int nuwa_attn_dense_pres(const nuwa_attn_params* p, void* stream);
 /* SparseCross2DNA.forward non-bos queries, nuwa_pytorch.py:851-895 (jmax = 1 + frames*ck*ck; t0 >= 1) */
 int nuwa_attn_cross2dna(const nuwa_attn_params* p, void* stream);
 

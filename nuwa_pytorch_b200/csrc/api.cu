@@ -67,6 +67,10 @@ int nuwa_attn_dense(const nuwa_attn_params* p, void* vt_workspace, void* stream)
   }
   return attn_dense(*p, S(stream));
 }
+int nuwa_attn_dense_pres(const nuwa_attn_params* p, void* stream) {
+  if (!p) return NUWA_ERR_INVALID;
+  return attn_dense_pres(*p, p->jmax - (p->null_k != nullptr ? 1 : 0), S(stream));
+}
 int nuwa_attn_cross2dna(const nuwa_attn_params* p, void* stream) { return p ? attn_cross2dna(*p, S(stream)) : NUWA_ERR_INVALID; }
 int nuwa_embed_tokens(const nuwa_embed_params* p, void* stream) { return p ? embed_tokens(*p, S(stream)) : NUWA_ERR_INVALID; }
 int nuwa_rotary_to_bf16(const float* qkv, void* out, const float* inv_freq, int rows, int n, int H, int dh, int rot,

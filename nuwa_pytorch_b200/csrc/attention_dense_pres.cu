@@ -1,0 +1,456 @@
+// Dense attention core with talking heads, probability-resident: Attention.forward core (nuwa_pytorch.py:339-378)
+// for the decoder's text cross-attention and the text encoder's self-attention: 8 heads x 64, up to 256 keys, learned
+// null key / value, key mask, talking heads.
+//
+// The talking-heads 1x1 conv (:372) mixes the NORMALISED probabilities of all heads before P.V, so no head can run
+// flash-style on its own.  attention_x64.cu answers with two passes over the keys and a register / shared-memory
+// exchange per 16-key chunk (issue bound on CUDA-core mix instructions: 272 us at cfg 3).  Here the whole probability
+// slab of a 32-query tile, P[8 heads][32 queries][257 keys] as fp16 (140 KB), stays in shared memory:
+//
+//   phase 1  warp h = head h: S = Q_h K_h^T over 32-key chunks (K boxes staged by TMA, SWIZZLE_128B, ldmatrix,
+//            mma.sync m16n8k16 with both 16-query tiles sharing the K fragments), online row maximum, p = exp2(..)
+//            stored UN-normalised as fp16 together with the maximum in force for that chunk; the exact fp32 null-key
+//            logit is folded in first.  At the end a factor cf[h][q][chunk] = exp(m_chunk - m_final) / sum turns
+//            every stored chunk into normalised probabilities.
+//   mix      on the tensor cores: for 16 (query, key) entries at a time, P'[g][e] = sum_h (W[g][h] cf[h]) P[h][e] is
+//            ONE mma.sync m16n8k16 (fp16): A = the entries x 8 heads (duplicated into k = 8..15), B = the 8 x 8 matrix
+//            W*cf split into fp16 high and low halves (k = 0..7 / 8..15), so the product keeps ~22 bits of W*cf.
+//            Written back in place as bf16.
+//   phase 3  warp g = output head g: O_g = P'_g V_g (A fragments by ldmatrix straight from the slab, V boxes by TMA,
+//            ldmatrix.trans), fp32 null value added in the epilogue.
+//
+// A ninth warp is the TMA producer (Q tile, then K chunks, then V chunks through one 2-stage ring; full / empty
+// mbarriers).  K and V are streamed once per 32 queries (16 L2 reads of the 0.5 MB K|V of a sample per 512 queries).
+#include <float.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nuwa {
+
+int encode_map_bf16_sw128(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box);  // gemm_tcgen05.cu
+
+namespace {
+
+constexpr int PQ = 32;                       // queries per CTA
+constexpr int PK = 32;                       // keys per staged chunk
+constexpr int NH = 8, DH = 64, INNER = NH * DH;
+constexpr int NSTG = 2;
+constexpr int HBOX = PK * DH * 2;            // 4096 B: one head's [32 rows x 64 channels] box
+constexpr int STAGE = NH * HBOX;             // 32 KB
+constexpr int MAXK = 256;
+constexpr int NULLJ = MAXK;                  // slot of the null key in a probability row
+constexpr int PP = 280;                      // fp16 row pitch (35 x 16 B: conflict-free ldmatrix rows)
+constexpr int HS = PQ * PP + 8;              // head stride in halves (+16 B: the mix reads 4 head pairs at once)
+constexpr int NCF = 12;                      // per (head, query): chunk maxima / final factors, 9 used
+constexpr int NTILE = (MAXK + 16) / 16;      // 17 sixteen-entry tiles per query row in the mix
+
+constexpr int OFF_P = NSTG * STAGE;
+constexpr int OFF_CF = OFF_P + NH * HS * 2;
+constexpr int OFF_SN = OFF_CF + NH * PQ * NCF * 4;
+constexpr int OFF_NULL = OFF_SN + NH * PQ * 4;
+constexpr int OFF_MASK = OFF_NULL + 2 * INNER * 4;
+constexpr int OFF_BAR = OFF_MASK + 64;
+constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;
+
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%4,%5}, {%6,%7}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ unsigned short bf16_bits(float v) {
+  const bf16 b = __float2bfloat16(v);
+  return *reinterpret_cast<const unsigned short*>(&b);
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  const __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+
+struct PresArgs {
+  int B, nq, nk, nchunk;
+  float c1;  // qscale * log2(e)
+  const float* talk;
+  const float* null_k;
+  const float* null_v;
+  const unsigned char* key_mask;
+  int mask_bs;
+  bf16* o;
+  long long o_bs;
+  int o_rs;
+};
+
+__global__ void __launch_bounds__((NH + 1) * 32, 1)
+attn_dense_pres_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
+                       const __grid_constant__ CUtensorMap vmap, const PresArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  const uint32_t sm_u = smem_u32(sm);
+  __half* P16 = reinterpret_cast<__half*>(sm + OFF_P);
+  float* CF = reinterpret_cast<float*>(sm + OFF_CF);      // [h][q][NCF]: chunk maxima, then final factors
+  float* SN = reinterpret_cast<float*>(sm + OFF_SN);      // [h][q]: raw null-key logit
+  float* nullk = reinterpret_cast<float*>(sm + OFF_NULL);
+  float* nullv = nullk + INNER;
+  uint32_t* maskw = reinterpret_cast<uint32_t*>(sm + OFF_MASK);  // [8] one bit per key: 1 = attend
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
+  uint64_t* empty = full + NSTG;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int tiles_q = (p.nq + PQ - 1) / PQ;
+  const int b = (int)blockIdx.x / tiles_q;
+  const int q0 = ((int)blockIdx.x - b * tiles_q) * PQ;
+  const int nchunk = p.nchunk;
+  const int NS = 1 + 2 * nchunk;  // Q tile, K chunks, V chunks
+  const bool has_null = p.null_k != nullptr;
+
+  if (warp == NH) {
+    // =============================== producer ===============================
+    int st = 0, use = 0;
+    auto produce = [&](int s_end) {
+      for (int s = use * NSTG + st; s < s_end; ++s) {
+        if (use >= 1) mbar_wait(&empty[st], (use - 1) & 1);
+        mbar_arrive_expect_tx(&full[st], STAGE);
+        const CUtensorMap* m = s == 0 ? &qmap : (s <= nchunk ? &kmap : &vmap);
+        const int row = s == 0 ? q0 : (s <= nchunk ? (s - 1) * PK : (s - 1 - nchunk) * PK);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) tma_load_3d(sm_u + st * STAGE + h * HBOX, m, &full[st], h * DH, row, b);
+        if (++st == NSTG) { st = 0; ++use; }
+      }
+    };
+    if (lane == 0) {
+      for (int i = 0; i < NSTG; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], NH);
+      }
+      fence_barrier_init();
+      tma_prefetch_desc(&qmap);
+      tma_prefetch_desc(&kmap);
+      tma_prefetch_desc(&vmap);
+      produce(NSTG);
+    }
+    __syncthreads();
+    if (lane == 0) produce(NS);
+    return;
+  }
+
+  // ---- one-time shared state of the 8 head warps ----
+  for (int i = tid; i < INNER; i += NH * 32) {
+    nullk[i] = has_null ? __ldg(p.null_k + i) : 0.f;
+    nullv[i] = has_null ? __ldg(p.null_v + i) : 0.f;
+  }
+  if (tid < MAXK / 32) {
+    const unsigned char* km = p.key_mask != nullptr ? p.key_mask + (long long)b * p.mask_bs : nullptr;
+    uint32_t w = 0;
+    for (int i = 0; i < 32; ++i) {
+      const int j = tid * 32 + i;
+      if (j < p.nk && (km == nullptr || km[j] != 0)) w |= 1u << i;
+    }
+    maskw[tid] = w;
+  }
+  {  // slots nk_pad .. PP-1 of this warp's head: zero (the null slot is written in phase 1)
+    __half* Ph = P16 + (size_t)warp * HS;
+    const int z0 = nchunk * PK, nz = PP - z0;
+    for (int i = lane; i < PQ * nz; i += 32) {
+      const int q = i / nz, z = i - q * nz;
+      Ph[q * PP + z0 + z] = __float2half(0.f);
+    }
+  }
+  __syncthreads();
+
+  const int h = warp;
+  const int mat = lane >> 3, l7 = lane & 7;
+  const int k_row = ((mat >> 1) << 3) + l7, k_ch = mat & 1;  // B operand (K): m0,m1 = keys 0-7 (k lo, hi); m2,m3 = keys 8-15
+  const int a_row = ((mat & 1) << 3) + l7, a_ch = mat >> 1;  // A operand (Q, P') and V^T
+  uint32_t k_sw[4], a_sw[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    k_sw[i] = k_row * 128 + (((2 * i + k_ch) ^ l7) << 4);
+    a_sw[i] = a_row * 128 + (((2 * i + a_ch) ^ l7) << 4);
+    asm volatile("" : "+r"(k_sw[i]), "+r"(a_sw[i]));
+  }
+  __half* Ph = P16 + (size_t)h * HS;
+  float* CFh = CF + h * PQ * NCF;
+  const float c1 = p.c1;
+
+  int st = 0, par = 0;
+  auto release = [&]() {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+    if (++st == NSTG) { st = 0; par ^= 1; }
+  };
+
+  // ================= phase 1: un-normalised probabilities of head h =================
+  {
+    uint32_t qa[2][4][4];
+    mbar_wait(&full[st], par);
+    const uint32_t qb = sm_u + st * STAGE + h * HBOX;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) ldsm4(qa[mt][ks], qb + mt * 2048 + a_sw[ks]);
+    if (has_null) {  // exact fp32 null-key logit of query `lane` (the learned null key is not rounded to bf16)
+      float sn = 0.f;
+      const float* nk_h = nullk + h * DH;
+#pragma unroll
+      for (int c16 = 0; c16 < 8; ++c16) {
+        uint4 u;
+        const uint32_t addr = qb + lane * 128 + ((c16 ^ (lane & 7)) << 4);
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+        const float* w = nk_h + c16 * 8;
+        sn = fmaf(f0.x, w[0], sn); sn = fmaf(f0.y, w[1], sn); sn = fmaf(f1.x, w[2], sn); sn = fmaf(f1.y, w[3], sn);
+        sn = fmaf(f2.x, w[4], sn); sn = fmaf(f2.y, w[5], sn); sn = fmaf(f3.x, w[6], sn); sn = fmaf(f3.y, w[7], sn);
+      }
+      SN[h * PQ + lane] = sn;
+      Ph[lane * PP + NULLJ] = __float2half(1.0f);  // exp(sn - m) with m = sn as the first running maximum
+      CFh[lane * NCF + 8] = sn;
+    }
+    release();
+
+    // row state: r = mt*2 + half <-> query mt*16 + g + 8*half
+    float m_run[4], l_run[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int q = (r >> 1) * 16 + g + 8 * (r & 1);
+      m_run[r] = has_null ? SN[h * PQ + q] : -FLT_MAX;
+      l_run[r] = (has_null && t == 0) ? 1.f : 0.f;
+    }
+    for (int c = 0; c < nchunk; ++c) {
+      mbar_wait(&full[st], par);
+      const uint32_t kb = sm_u + st * STAGE + h * HBOX;
+      uint32_t kf[2][4][4];  // [16-key half][ks]
+#pragma unroll
+      for (int np = 0; np < 2; ++np)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ldsm4(kf[np][ks], kb + np * 2048 + k_sw[ks]);
+      float s[2][4][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+            mma_bf16(s[mt][nt], qa[mt][ks], kf[nt >> 1][ks][(nt & 1) * 2], kf[nt >> 1][ks][(nt & 1) * 2 + 1]);
+      release();  // the K fragments are in registers
+      const uint32_t mw = maskw[c];
+      if (mw != 0xffffffffu) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (!((mw >> (nt * 8 + 2 * t + e)) & 1u)) {
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt) s[mt][nt][e] = s[mt][nt][2 + e] = -FLT_MAX;
+            }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int mt = r >> 1, hf = r & 1;
+        float cm = -FLT_MAX;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) cm = fmaxf(cm, fmaxf(s[mt][nt][2 * hf], s[mt][nt][2 * hf + 1]));
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+        const float m_new = fmaxf(m_run[r], cm);
+        const float mneg = -m_new * c1;
+        float l = l_run[r] * exp2f(fmaf(m_run[r], c1, mneg));
+        const int q = mt * 16 + g + 8 * hf;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(Ph + q * PP + c * PK + 2 * t);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const float p0 = exp2f(fmaf(s[mt][nt][2 * hf], c1, mneg));      // masked: exp2(-huge) == 0
+          const float p1 = exp2f(fmaf(s[mt][nt][2 * hf + 1], c1, mneg));
+          l += p0 + p1;
+          dst[nt * 4] = pack_h2(p0, p1);
+        }
+        m_run[r] = m_new;
+        l_run[r] = l;
+        if (t == 0) CFh[q * NCF + c] = m_new;
+      }
+    }
+    // final factors: cf[q][c] = exp(m_c - m_final) / sum   (quad lane t handles chunks t, t+4, t+8)
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float l = l_run[r];
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      const float inv = 1.0f / l, mneg = -m_run[r] * c1;
+      const int q = (r >> 1) * 16 + g + 8 * (r & 1);
+      for (int c = t; c < 9; c += 4) {
+        const bool used = c < nchunk || (c == 8 && has_null);
+        CFh[q * NCF + c] = used ? exp2f(fmaf(CFh[q * NCF + c], c1, mneg)) * inv : 0.f;
+      }
+    }
+  }
+  consumer_sync();
+
+  // ================= talking heads on the tensor cores, in place (fp16 P -> bf16 P') =================
+  {
+    const float w0 = p.talk ? __ldg(p.talk + g * NH + 2 * t) : (g == 2 * t ? 1.f : 0.f);      // W[g][2t]
+    const float w1 = p.talk ? __ldg(p.talk + g * NH + 2 * t + 1) : (g == 2 * t + 1 ? 1.f : 0.f);
+    const uint32_t pa = smem_u32(P16) + 2u * (2 * t * HS + g);  // P[2t][.][. + g]; head 2t+1 is HS halves further
+    const int ntile = 2 * nchunk + 1;                            // 16-entry tiles per query row incl. the null tile
+    for (int i = warp; i < PQ * ntile; i += NH) {
+      const int q = i / ntile, jb = i - q * ntile;
+      const int j0 = jb < 2 * nchunk ? jb * 16 : NULLJ;
+      const int c = jb < 2 * nchunk ? (jb >> 1) : 8;
+      const float f0 = w0 * CF[((2 * t) * PQ + q) * NCF + c], f1 = w1 * CF[((2 * t + 1) * PQ + q) * NCF + c];
+      const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
+      const __half2 hi = __halves2half2(h0, h1);
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&hi);
+      const uint32_t b1 = pack_h2(f0 - __half2float(h0), f1 - __half2float(h1));
+      const uint32_t a = pa + 2u * (q * PP + j0);
+      const uint32_t x00 = lds_u16(a), x01 = lds_u16(a + 2 * HS), x10 = lds_u16(a + 16), x11 = lds_u16(a + 2 * HS + 16);
+      float cacc[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_f16(cacc, x00 | (x01 << 16), x10 | (x11 << 16), b0, b1);
+      sts_u16(a, bf16_bits(cacc[0]));
+      sts_u16(a + 2 * HS, bf16_bits(cacc[1]));
+      sts_u16(a + 16, bf16_bits(cacc[2]));
+      sts_u16(a + 2 * HS + 16, bf16_bits(cacc[3]));
+    }
+  }
+  consumer_sync();
+
+  // ================= phase 3: O_h = P'_h V_h =================
+  {
+    float o[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) o[mt][nd][0] = o[mt][nd][1] = o[mt][nd][2] = o[mt][nd][3] = 0.f;
+    const uint32_t pbase = smem_u32(Ph) + 2u * (a_row * PP + a_ch * 8);
+    for (int c = 0; c < nchunk; ++c) {
+      mbar_wait(&full[st], par);
+      const uint32_t vb = sm_u + st * STAGE + h * HBOX;
+      uint32_t af[2][2][4], vf[2][4][4];
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) ldsm4(af[kk][mt], pbase + 2u * (mt * 16 * PP + c * PK + kk * 16));
+#pragma unroll
+        for (int pr = 0; pr < 4; ++pr) ldsm4t(vf[kk][pr], vb + kk * 2048 + a_sw[pr]);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) {
+            mma_bf16(o[mt][2 * pr], af[kk][mt], vf[kk][pr][0], vf[kk][pr][1]);
+            mma_bf16(o[mt][2 * pr + 1], af[kk][mt], vf[kk][pr][2], vf[kk][pr][3]);
+          }
+      release();
+    }
+    // fp32 null value + store
+    bf16* ob = p.o + (long long)b * p.o_bs + h * DH + 2 * t;
+    const bf16* Pn = reinterpret_cast<const bf16*>(Ph);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int q = mt * 16 + g + 8 * hf;
+        if (q0 + q >= p.nq) continue;
+        const float pn = has_null ? __bfloat162float(Pn[q * PP + NULLJ]) : 0.f;
+        bf16* orow = ob + (long long)(q0 + q) * p.o_rs;
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) {
+          const float nv0 = nullv[h * DH + nd * 8 + 2 * t], nv1 = nullv[h * DH + nd * 8 + 2 * t + 1];
+          *reinterpret_cast<uint32_t*>(orow + nd * 8) =
+              pack_bf16x2(fmaf(pn, nv0, o[mt][nd][2 * hf]), fmaf(pn, nv1, o[mt][nd][2 * hf + 1]));
+        }
+      }
+  }
+}
+
+}  // namespace
+
+// Envelope: H == 8, dh == 64, 1 <= nk <= 256, no additive bias / per-head scale, static positions.
+// NUWA_ERR_INVALID outside it (nothing launched; the caller falls back to attention_x64.cu / the generic kernel).
+int attn_dense_pres(const AttnParams& p, int nk, cudaStream_t stream) {
+  if (p.H != NH || p.dh != DH || p.bias != nullptr || p.head_scale != nullptr || p.t0_ptr != nullptr) return NUWA_ERR_INVALID;
+  if (nk <= 0 || nk > MAXK || p.nq <= 0 || p.B <= 0) return NUWA_ERR_INVALID;
+  if ((p.null_k == nullptr) != (p.null_v == nullptr)) return NUWA_ERR_INVALID;
+  if ((p.q_rs % 8) || (p.k_rs % 8) || (p.v_rs % 8) || (p.q_bs % 8) || (p.k_bs % 8) || (p.v_bs % 8) || (p.o_rs & 1) || (p.o_bs & 1))
+    return NUWA_ERR_INVALID;
+  if (p.q_rs < INNER || p.k_rs < INNER || p.v_rs < INNER) return NUWA_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(p.q) & 15) || (reinterpret_cast<uintptr_t>(p.k) & 15) ||
+      (reinterpret_cast<uintptr_t>(p.v) & 15) || (reinterpret_cast<uintptr_t>(p.o) & 3))
+    return NUWA_ERR_INVALID;
+
+  CUtensorMap qm, km, vm;
+  const uint32_t box[3] = {DH, PK, 1};
+  {
+    const uint64_t dims[3] = {(uint64_t)INNER, (uint64_t)p.nq, (uint64_t)p.B};
+    const uint64_t str[3] = {2, (uint64_t)p.q_rs * 2, (uint64_t)p.q_bs * 2};
+    const int rc = encode_map_bf16_sw128(&qm, p.q, 3, dims, str, box);
+    if (rc != NUWA_OK) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)INNER, (uint64_t)nk, (uint64_t)p.B};
+    const uint64_t strk[3] = {2, (uint64_t)p.k_rs * 2, (uint64_t)p.k_bs * 2};
+    const uint64_t strv[3] = {2, (uint64_t)p.v_rs * 2, (uint64_t)p.v_bs * 2};
+    int rc = encode_map_bf16_sw128(&km, p.k, 3, dims, strk, box);
+    if (rc != NUWA_OK) return rc;
+    rc = encode_map_bf16_sw128(&vm, p.v, 3, dims, strv, box);
+    if (rc != NUWA_OK) return rc;
+  }
+  PresArgs a;
+  a.B = p.B; a.nq = p.nq; a.nk = nk; a.nchunk = (nk + PK - 1) / PK;
+  a.c1 = p.qscale * 1.4426950408889634f;
+  a.talk = p.talk; a.null_k = p.null_k; a.null_v = p.null_v;
+  a.key_mask = p.key_mask; a.mask_bs = p.mask_bs;
+  a.o = reinterpret_cast<bf16*>(p.o); a.o_bs = p.o_bs; a.o_rs = p.o_rs;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(attn_dense_pres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+      return NUWA_ERR_CUDA;
+    attr = true;
+  }
+  const int grid = p.B * ((p.nq + PQ - 1) / PQ);
+  attn_dense_pres_kernel<<<grid, (NH + 1) * 32, SMEM_BYTES, stream>>>(qm, km, vm, a);
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+
+}  // namespace nuwa

@@ -61,6 +61,7 @@ int attn_3dna_tc(const AttnParams& p, void* vT_ws, cudaStream_t stream);  // att
 int attn_3dna_halo(const AttnParams& p, cudaStream_t stream);           // attention_3dna_halo.cu
 int attn_dense_mma(const AttnParams& p, int nk, void* vT_ws, cudaStream_t stream);  // attention_mma.cu
 int attn_dense_x64(const AttnParams& p, int nk, cudaStream_t stream);                // attention_x64.cu
+int attn_dense_pres(const AttnParams& p, int nk, cudaStream_t stream);               // attention_dense_pres.cu
 int attn_cross2dna(const AttnParams& p, cudaStream_t s);
 // norm.cu
 int sandwich_ln(const LnParams& p, cudaStream_t stream);

@@ -214,7 +214,8 @@ def sample_topk_gumbel_at(cond, uncond, noise_all, out_seq, t_dev, k, cond_scale
 
 
 def attn_dense(q_ptr, k_ptr, v_ptr, o, *, B, nq, nk, H, dh, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, talk=None,
-               null_k=None, null_v=None, key_mask=None, head_scale=None, bias=None, qscale=None, t0=0, use_mma=True):
+               null_k=None, null_v=None, key_mask=None, head_scale=None, bias=None, qscale=None, t0=0, use_mma=True,
+               variant='auto'):
     p = _attn_base(q_ptr, k_ptr, v_ptr, ptr(o) if torch.is_tensor(o) else o, B, nq, t0, H, dh, q_bs, k_bs, v_bs, o_bs,
                    q_rs, k_rs, v_rs, o_rs, talk)
     if qscale is not None:
@@ -227,6 +228,14 @@ def attn_dense(q_ptr, k_ptr, v_ptr, o, *, B, nq, nk, H, dh, q_bs, q_rs, k_bs, k_
     if bias is not None:
         p.bias, p.bias_nq, p.bias_nk = ptr(bias), bias.shape[1], bias.shape[2]
     p.jmax = nk + (1 if null_k is not None else 0)
+    # variant: 'auto' = probability-resident kernel (attention_dense_pres.cu) inside its envelope (8 x 64 heads, <= 256
+    # keys, >= 16 queries), else the library's own choice (attention_x64.cu / attention_mma.cu / generic); 'pres' pins it.
+    if variant == 'pres' or (variant == 'auto' and use_mma and nq >= 16):
+        rc = lib().nuwa_attn_dense_pres(p, stream())
+        if rc == 0:
+            return
+        if variant == 'pres' or rc != _lib.NUWA_ERR_INVALID:
+            check(rc, "nuwa_attn_dense_pres")
     ws = None
     if use_mma and nq >= 8 and nk <= 256 and dh in (32, 64) and H <= 8:
         dev = o.device if torch.is_tensor(o) else torch.device('cuda')

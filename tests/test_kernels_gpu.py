@@ -270,11 +270,14 @@ def test_attn_dense_tensor_core_variant(cuda_device, B, nq, nk, H, dh, null, tal
     assert r_mma < 8e-3      # additionally rounds the probabilities to bf16 for the PV tensor-core product
 
 
+@pytest.mark.parametrize("variant", ["lib", "pres"])
 @pytest.mark.parametrize("B,nq,nk,null,talk,masked", [(2, 100, 256, True, True, True), (1, 64, 50, True, True, False),
                                                        (3, 16, 12, False, True, True), (2, 257, 77, True, False, True),
-                                                       (1, 2560, 256, True, True, True)])
-def test_attn_dense_x64_two_pass_kernel(cuda_device, B, nq, nk, null, talk, masked):
-    """attention_x64.cu (8 heads x 64, 64-query tiles, statistics pass + register talking-heads mix) vs the oracle math."""
+                                                       (1, 2560, 256, True, True, True), (2, 300, 256, True, True, False),
+                                                       (2, 33, 224, False, False, False)])
+def test_attn_dense_x64_two_pass_kernel(cuda_device, B, nq, nk, null, talk, masked, variant):
+    """attention_x64.cu (8 heads x 64, 64-query tiles, statistics pass + register talking-heads mix; variant 'lib') and
+    attention_dense_pres.cu (probability slab resident in shared memory, tensor-core mix; 'pres') vs the oracle math."""
     from nuwa_pytorch_b200 import ops
     g = gen(300 + nq + nk)
     H, dh = 8, 64
@@ -309,7 +312,7 @@ def test_attn_dense_x64_two_pass_kernel(cuda_device, B, nq, nk, null, talk, mask
     ops.attn_dense(qd.data_ptr(), kvd.data_ptr(), kvd.data_ptr() + inner * 2, o, B=B, nq=nq, nk=nk, H=H, dh=dh,
                    q_bs=nq * inner, q_rs=inner, k_bs=nk * 2 * inner, k_rs=2 * inner, v_bs=nk * 2 * inner, v_rs=2 * inner,
                    o_bs=nq * inner, o_rs=inner, talk=dv(tk), null_k=dv(null_k), null_v=dv(null_v),
-                   key_mask=dv(mask.to(torch.uint8)) if masked else None)
+                   key_mask=dv(mask.to(torch.uint8)) if masked else None, variant=variant)
     r = rel(o.float(), ref)
-    print(f"  x64 dense attention B={B} nq={nq} nk={nk}: rel {r:.2e}")
+    print(f"  {variant} dense attention B={B} nq={nq} nk={nk}: rel {r:.2e}")
     assert r < 6e-3  # probabilities are rounded to bf16 for the tensor-core P'V, output stored as bf16

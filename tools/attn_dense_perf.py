@@ -13,7 +13,7 @@ flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 H, dh = 8, 64
 inner = H * dh
 rows = []
-for (B, nq, nk) in ((8, 2560, 256), (8, 256, 256), (4, 2560, 768)):
+for (B, nq, nk, variant) in ((8, 2560, 256, 'lib'), (8, 2560, 256, 'pres'), (8, 256, 256, 'lib'), (8, 256, 256, 'pres'), (4, 2560, 768, 'lib')):
     q = torch.randn(B, nq, inner, device=dev).bfloat16()
     kv = torch.randn(B, nk, 2 * inner, device=dev).bfloat16()
     talk = torch.randn(H, H, device=dev) / 2
@@ -24,7 +24,7 @@ for (B, nq, nk) in ((8, 2560, 256), (8, 256, 256), (4, 2560, 768)):
     def run():
         ops.attn_dense(q.data_ptr(), kv.data_ptr(), kv.data_ptr() + inner * 2, o, B=B, nq=nq, nk=nk, H=H, dh=dh,
                        q_bs=nq * inner, q_rs=inner, k_bs=nk * 2 * inner, k_rs=2 * inner, v_bs=nk * 2 * inner, v_rs=2 * inner,
-                       o_bs=nq * inner, o_rs=inner, talk=talk, null_k=nk_, null_v=nv_, key_mask=mask)
+                       o_bs=nq * inner, o_rs=inner, talk=talk, null_k=nk_, null_v=nv_, key_mask=mask, variant=variant)
     for _ in range(3):
         run()
     ts = []
@@ -39,6 +39,6 @@ for (B, nq, nk) in ((8, 2560, 256), (8, 256, 256), (4, 2560, 768)):
     ts.sort()
     us = ts[len(ts) // 2] * 1e3
     flops = 2 * 2 * B * H * nq * (nk + 1) * dh
-    rows.append(dict(B=B, nq=nq, nk=nk, us=round(us, 1), tflops=round(flops / us / 1e6, 1)))
+    rows.append(dict(B=B, nq=nq, nk=nk, variant=variant, us=round(us, 1), tflops=round(flops / us / 1e6, 1)))
     print(rows[-1], flush=True)
 json.dump(rows, open('gpurun_out/attn_dense_perf.json', 'w'), indent=1)
