@@ -42,7 +42,7 @@ constexpr int HBOX = PK * DH * 2;            // 4096 B: one head's [32 rows x 64
 constexpr int STAGE = NH * HBOX;             // 32 KB
 constexpr int MAXK = 256;
 constexpr int NULLJ = MAXK;                  // slot of the null key in a probability row
-constexpr int PP = 280;                      // fp16 row pitch (35 x 16 B: conflict-free ldmatrix rows)
+constexpr int PP = 280;                      // fp16 row pitch (35 x 16 B: conflict-free ldmatrix rows), >= 256 + 16
 constexpr int HS = PQ * PP + 8;              // head stride in halves (+16 B: the mix reads 4 head pairs at once)
 constexpr int NCF = 12;                      // per (head, query): chunk maxima / final factors, 9 used
 constexpr int NTILE = (MAXK + 16) / 16;      // 17 sixteen-entry tiles per query row in the mix
@@ -330,24 +330,36 @@ attn_dense_pres_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_co
     const float w0 = p.talk ? __ldg(p.talk + g * NH + 2 * t) : (g == 2 * t ? 1.f : 0.f);      // W[g][2t]
     const float w1 = p.talk ? __ldg(p.talk + g * NH + 2 * t + 1) : (g == 2 * t + 1 ? 1.f : 0.f);
     const uint32_t pa = smem_u32(P16) + 2u * (2 * t * HS + g);  // P[2t][.][. + g]; head 2t+1 is HS halves further
-    const int ntile = 2 * nchunk + 1;                            // 16-entry tiles per query row incl. the null tile
-    for (int i = warp; i < PQ * ntile; i += NH) {
-      const int q = i / ntile, jb = i - q * ntile;
-      const int j0 = jb < 2 * nchunk ? jb * 16 : NULLJ;
-      const int c = jb < 2 * nchunk ? (jb >> 1) : 8;
-      const float f0 = w0 * CF[((2 * t) * PQ + q) * NCF + c], f1 = w1 * CF[((2 * t + 1) * PQ + q) * NCF + c];
+    // warp w owns query rows w, w+8, ...; per row: 2 tiles per key chunk (one factor pair per chunk) + the null tile
+    auto mix_tile = [&](uint32_t a, float f0, float f1, bool two) {
       const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
       const __half2 hi = __halves2half2(h0, h1);
       const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&hi);
       const uint32_t b1 = pack_h2(f0 - __half2float(h0), f1 - __half2float(h1));
-      const uint32_t a = pa + 2u * (q * PP + j0);
       const uint32_t x00 = lds_u16(a), x01 = lds_u16(a + 2 * HS), x10 = lds_u16(a + 16), x11 = lds_u16(a + 2 * HS + 16);
-      float cacc[4] = {0.f, 0.f, 0.f, 0.f};
-      mma_f16(cacc, x00 | (x01 << 16), x10 | (x11 << 16), b0, b1);
-      sts_u16(a, bf16_bits(cacc[0]));
-      sts_u16(a + 2 * HS, bf16_bits(cacc[1]));
-      sts_u16(a + 16, bf16_bits(cacc[2]));
-      sts_u16(a + 2 * HS + 16, bf16_bits(cacc[3]));
+      uint32_t y00 = 0, y01 = 0, y10 = 0, y11 = 0;
+      if (two) { y00 = lds_u16(a + 32); y01 = lds_u16(a + 2 * HS + 32); y10 = lds_u16(a + 48); y11 = lds_u16(a + 2 * HS + 48); }
+      float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_f16(ca, x00 | (x01 << 16), x10 | (x11 << 16), b0, b1);
+      if (two) mma_f16(cb, y00 | (y01 << 16), y10 | (y11 << 16), b0, b1);
+      sts_u16(a, bf16_bits(ca[0]));
+      sts_u16(a + 2 * HS, bf16_bits(ca[1]));
+      sts_u16(a + 16, bf16_bits(ca[2]));
+      sts_u16(a + 2 * HS + 16, bf16_bits(ca[3]));
+      if (two) {
+        sts_u16(a + 32, bf16_bits(cb[0]));
+        sts_u16(a + 2 * HS + 32, bf16_bits(cb[1]));
+        sts_u16(a + 48, bf16_bits(cb[2]));
+        sts_u16(a + 2 * HS + 48, bf16_bits(cb[3]));
+      }
+    };
+    for (int q = warp; q < PQ; q += NH) {
+      const float* cf0 = CF + ((2 * t) * PQ + q) * NCF;
+      const float* cf1 = cf0 + PQ * NCF;
+      const uint32_t arow = pa + 2u * (q * PP);
+#pragma unroll 2
+      for (int c = 0; c < nchunk; ++c) mix_tile(arow + 2u * (c * PK), w0 * cf0[c], w1 * cf1[c], true);  // 32 entries: 2 MMAs
+      if (has_null) mix_tile(arow + 2u * NULLJ, w0 * cf0[8], w1 * cf1[8], false);  // entries 256..271: null + zero padding
     }
   }
   consumer_sync();
