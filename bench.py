@@ -242,6 +242,7 @@ def run_ours(args):
         with ClockSampler(local) as clocks:
             sec = timed(step_dev, args.steps, args.warmup, dist, None)
         n_gemm, gemm_flops, gemm_ms = _lib.gemm_prof_collect()
+        gemm_alg_bytes = _lib.gemm_prof_bytes()
         _lib.gemm_prof_enable(False)
         launches = _lib.launch_count() - launches0
         sec_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), dist, None)
@@ -251,8 +252,20 @@ def run_ours(args):
     # gemm_prof counts warm-up + timed launches alike (same shapes), so the ratio is a per-launch average.
     ach = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     peak = pk["bf16_tflops_sustained"]
+    # DRAM traffic of the same launches: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu pass
+    # (profiles/r01_vae_gemm_traffic.json, same command at --steps 1), next to the algorithmic bytes of those launches.
+    traffic, traffic_note = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_vae_gemm_traffic.json")
+    if os.path.exists(tp) and B == VAE_BATCH:
+        tj = json.load(open(tp))
+        traffic = round(tj["dram_bytes_per_launch"] / 1e9, 3)
+        traffic_note = ("GB per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum averaged over the %d launches of "
+                        "one step (profiles/r01_vae_gemm_traffic.json)" % tj["launches_per_step"])
+    alg_gb = gemm_alg_bytes / max(1, n_gemm) / 1e9
     roof = dict(bound="tensor", kernel="gemm_tcgen05_kernel (implicit-GEMM conv + GEMM)", achieved=round(ach, 1),
-                peak=peak, unit="TFLOP/s", frac=round(ach / peak, 4), traffic=None,
+                peak=peak, unit="TFLOP/s", frac=round(ach / peak, 4), traffic=traffic, traffic_unit=traffic_note,
+                algorithmic_gb_per_launch=round(alg_gb, 3),
+                flop_per_byte=round(gemm_flops / max(1.0, gemm_alg_bytes), 1),
                 peak_source=pk["source"] + ", sustained figure (kernel timed inside a long step)",
                 launches_per_step=n_gemm // (args.steps + args.warmup),
                 share_of_step=round((gemm_ms / (args.steps + args.warmup)) / (1e3 * sec / args.steps), 4),

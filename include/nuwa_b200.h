@@ -40,6 +40,9 @@ void nuwa_struct_sizes(int* out3);
  * number of launches and their summed algorithmic FLOPs and device time, then resets the counters. */
 void nuwa_gemm_prof_enable(int on);
 int nuwa_gemm_prof_collect(double* flops, float* ms);
+/* algorithmic HBM bytes (every operand read once, every output written once) of the launches the last
+ * nuwa_gemm_prof_collect summed up: the denominator for the ncu DRAM-traffic comparison in bench.py */
+double nuwa_gemm_prof_bytes(void);
 
 /* ---- dense contraction (tcgen05) ------------------------------------------------------------
  * out[M,N] = act(A[M,K] @ W[N,K]^T + bias) + residual.   A, W bf16 with K contiguous.

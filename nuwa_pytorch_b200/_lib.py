@@ -107,6 +107,7 @@ SIGNATURES = {
     "nuwa_struct_sizes": [P(c_int)],
     "nuwa_gemm_prof_enable": [c_int],
     "nuwa_gemm_prof_collect": [P(ctypes.c_double), P(c_float)],
+    "nuwa_gemm_prof_bytes": [],
     "nuwa_gemm_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                        c_void_p, c_int, c_int, c_int, c_void_p],
     "nuwa_conv2d_nhwc_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
@@ -174,7 +175,7 @@ SIGNATURES = {
     "nuwa_attn3dna_bwd_first_key_finalize": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p],
     "nuwa_struct_sizes_bwd": [P(c_int)],
 }
-_RESTYPES = {"nuwa_strerror": ctypes.c_char_p, "nuwa_launch_count": ctypes.c_ulonglong, "nuwa_struct_sizes": None,
+_RESTYPES = {"nuwa_strerror": ctypes.c_char_p, "nuwa_gemm_prof_bytes": ctypes.c_double, "nuwa_launch_count": ctypes.c_ulonglong, "nuwa_struct_sizes": None,
              "nuwa_gemm_prof_enable": None, "nuwa_struct_sizes_bwd": None, "nuwa_struct_sizes_decode": None, "nuwa_struct_sizes_optim": None}
 
 _lib = None
@@ -258,3 +259,8 @@ def gemm_prof_collect():
     fl, ms = ctypes.c_double(0), c_float(0)
     n = lib().nuwa_gemm_prof_collect(ctypes.byref(fl), ctypes.byref(ms))
     return n, fl.value, ms.value
+
+
+def gemm_prof_bytes():
+    """Algorithmic HBM bytes (operands and outputs once each) of the launches the last gemm_prof_collect() summed."""
+    return float(lib().nuwa_gemm_prof_bytes())

@@ -145,6 +145,7 @@ int nuwa_conv1x1_nhwc_to_nchw(const void* x, const float* w, const float* bias, 
 
 extern "C" void nuwa_gemm_prof_enable(int on) { gemm_prof_enable(on); }
 extern "C" int nuwa_gemm_prof_collect(double* flops, float* ms) { return gemm_prof_collect(flops, ms); }
+extern "C" double nuwa_gemm_prof_bytes(void) { return gemm_prof_bytes(); }
 
 // sizes of the parameter structs, so a foreign-language binding can verify its mirror of the layout
 extern "C" void nuwa_struct_sizes(int* out3) {

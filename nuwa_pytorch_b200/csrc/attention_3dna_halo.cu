@@ -404,7 +404,7 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
       float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < MAXJ / 2; ++i) {
-        v[i] = exp2f(fmaf(v[i], p.scale_log2e, mneg));  // masked slots: exp2(-huge) == 0
+        v[i] = fast_exp2(fmaf(v[i], p.scale_log2e, mneg));  // masked slots: exp2(-huge) == 0
         l4[i & 3] += v[i];
       }
       float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);

@@ -293,13 +293,13 @@ attn_dense_pres_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_co
         cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
         const float m_new = fmaxf(m_run[r], cm);
         const float mneg = -m_new * c1;
-        float l = l_run[r] * exp2f(fmaf(m_run[r], c1, mneg));
+        float l = l_run[r] * fast_exp2(fmaf(m_run[r], c1, mneg));
         const int q = mt * 16 + g + 8 * hf;
         uint32_t* dst = reinterpret_cast<uint32_t*>(Ph + q * PP + c * PK + 2 * t);
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-          const float p0 = exp2f(fmaf(s[mt][nt][2 * hf], c1, mneg));      // masked: exp2(-huge) == 0
-          const float p1 = exp2f(fmaf(s[mt][nt][2 * hf + 1], c1, mneg));
+          const float p0 = fast_exp2(fmaf(s[mt][nt][2 * hf], c1, mneg));      // masked: exp2(-huge) == 0
+          const float p1 = fast_exp2(fmaf(s[mt][nt][2 * hf + 1], c1, mneg));
           l += p0 + p1;
           dst[nt * 4] = pack_h2(p0, p1);
         }
@@ -319,7 +319,7 @@ attn_dense_pres_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_co
       const int q = (r >> 1) * 16 + g + 8 * (r & 1);
       for (int c = t; c < 9; c += 4) {
         const bool used = c < nchunk || (c == 8 && has_null);
-        CFh[q * NCF + c] = used ? exp2f(fmaf(CFh[q * NCF + c], c1, mneg)) * inv : 0.f;
+        CFh[q * NCF + c] = used ? fast_exp2(fmaf(CFh[q * NCF + c], c1, mneg)) * inv : 0.f;
       }
     }
   }

@@ -404,9 +404,74 @@ ce_bwd_kernel(const float* __restrict__ logits, int ld, const long long* __restr
     o[c] = __float2bfloat16(v);
   }
 }
+// Same with the row held in registers (V <= 256 * 4 * NV): one 16-byte-vectorised pass over the logits, 8-byte stores.
+template <int NV>
+__global__ void __launch_bounds__(256)
+ce_bwd_reg_kernel(const float* __restrict__ logits, int ld, const long long* __restrict__ target,
+                  const float* __restrict__ gscale, bf16* __restrict__ dl, int ld_out, int rows, int V) {
+  const int row = blockIdx.x;
+  const float4* l4 = reinterpret_cast<const float4*>(logits + (long long)row * ld);
+  const int nv4 = V >> 2;
+  __shared__ float red[2][8];
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = threadIdx.x + i * 256;
+    v[i] = c < nv4 ? __ldcs(l4 + c) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+  }
+  float m = -FLT_MAX;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0][0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[0][i]);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x = __expf(v[i].x - m); v[i].y = __expf(v[i].y - m); v[i].z = __expf(v[i].z - m); v[i].w = __expf(v[i].w - m);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[1][threadIdx.x >> 5] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[1][i];
+  const float k = (gscale != nullptr ? __ldg(gscale) : 1.0f) / (float)rows;
+  const float inv = k / tot;
+  const int tgt = (int)target[row];
+  uint2* o = reinterpret_cast<uint2*>(dl + (long long)row * ld_out);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c >= nv4) continue;
+    float a = v[i].x * inv, b = v[i].y * inv, cc = v[i].z * inv, d = v[i].w * inv;
+    if ((tgt >> 2) == c) {
+      const int e = tgt & 3;
+      if (e == 0) a -= k; else if (e == 1) b -= k; else if (e == 2) cc -= k; else d -= k;
+    }
+    uint2 u;
+    u.x = pack_bf16x2(a, b);
+    u.y = pack_bf16x2(cc, d);
+    o[c] = u;
+  }
+}
 int ce_bwd(const float* logits, int ld, const long long* target, const float* gscale, void* dlogits, int ld_out, int rows,
            int V, cudaStream_t stream) {
   if (rows <= 0 || V <= 0 || ld < V || ld_out < V) return NUWA_ERR_INVALID;
+  const bool vec = (V % 4 == 0) && (ld % 4 == 0) && (ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dlogits) & 7) == 0);
+  if (vec && V <= 256 * 4 * 8) {
+    if (V <= 256 * 4 * 2)
+      ce_bwd_reg_kernel<2><<<rows, 256, 0, stream>>>(logits, ld, target, gscale, reinterpret_cast<bf16*>(dlogits), ld_out, rows, V);
+    else
+      ce_bwd_reg_kernel<8><<<rows, 256, 0, stream>>>(logits, ld, target, gscale, reinterpret_cast<bf16*>(dlogits), ld_out, rows, V);
+    NUWA_CHECK_LAUNCH();
+    return NUWA_OK;
+  }
   ce_bwd_kernel<<<rows, 256, 0, stream>>>(logits, ld, target, gscale, reinterpret_cast<bf16*>(dlogits), ld_out, rows, V);
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;

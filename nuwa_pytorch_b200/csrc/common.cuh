@@ -41,6 +41,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// 2^x by the SFU alone (ex2.approx.ftz): exp2f() wraps the same instruction in a denormal-range rescue (FSETP + 2 FMUL
+// per call) that softmax arguments (<= 0, results flushed to 0 below 2^-126) do not need.
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float leaky01(float x) { return x > 0.f ? x : 0.1f * x; }

@@ -517,12 +517,17 @@ static std::vector<cudaEvent_t> g_prof_ev;  // start/stop pairs
 static size_t g_prof_used = 0;
 static double g_prof_flops = 0.0;
 static double g_cur_flops = 0.0;
+static double g_prof_bytes = 0.0;  // algorithmic HBM bytes: operands once + outputs once
+static double g_cur_bytes = 0.0;
+static double g_prof_bytes_last = 0.0;
 
 void gemm_prof_enable(int on) {
   g_prof_on = on != 0;
   g_prof_used = 0;
   g_prof_flops = 0.0;
+  g_prof_bytes = 0.0;
 }
+double gemm_prof_bytes() { return g_prof_bytes_last; }
 // Caller must have synchronised the stream(s).  Returns the number of timed launches.
 int gemm_prof_collect(double* flops, float* ms) {
   float total = 0.f;
@@ -532,6 +537,8 @@ int gemm_prof_collect(double* flops, float* ms) {
   }
   int n = (int)(g_prof_used / 2);
   if (flops) *flops = g_prof_flops;
+  g_prof_bytes_last = g_prof_bytes;
+  g_prof_bytes = 0.0;
   if (ms) *ms = total;
   g_prof_used = 0;
   g_prof_flops = 0.0;
@@ -576,6 +583,7 @@ static int launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, const CUten
   if (g_prof_on) {
     cudaEventRecord(prof_event(), stream);
     g_prof_flops += g_cur_flops;
+    g_prof_bytes += g_cur_bytes;
   }
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
@@ -657,6 +665,11 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   if (e) return e;
   mA[1] = mA[0]; mA[2] = mA[0]; mA[3] = mA[0];
   g_cur_flops = 2.0 * (double)M * (double)N * (double)K;
+  {
+    const double n_out = (act == ACT_GLU || act == ACT_GEGLU) ? N / 2.0 : (double)N;
+    g_cur_bytes = 2.0 * ((double)M * K + (double)N * K) + (double)M * n_out * ((out_f32 ? 4.0 : 0.0) + (out_bf16 ? 2.0 : 0.0)) +
+                  (residual ? 4.0 * M * n_out : 0.0);
+  }
   return dispatch_gemm(mA, W, p, force_bn, stream);
 }
 
@@ -738,6 +751,11 @@ int conv2d_nhwc_bf16(const void* x, const void* w, int B, int Hin, int Win, int 
       }
   }
   g_cur_flops = 2.0 * (double)p.M * (double)Cout * (double)(ntaps * Cin);  // algorithmic (un-padded) MACs x 2
+  {
+    const double n_out = (act == ACT_GLU || act == ACT_GEGLU) ? Cout / 2.0 : (double)Cout;
+    g_cur_bytes = 2.0 * ((double)B * Hin * Win * Cin + (double)Cout * ntaps * Cin) +
+                  (double)p.M * n_out * ((out_f32 ? 4.0 : 0.0) + (out_bf16 ? 2.0 : 0.0)) + (residual ? 4.0 * p.M * n_out : 0.0);
+  }
   return dispatch_gemm(mA, w, p, force_bn, stream);
 }
 

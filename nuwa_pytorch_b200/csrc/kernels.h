@@ -53,6 +53,7 @@ int conv2d_nhwc_bf16(const void* x, const void* w, int B, int Hin, int Win, int 
 
 void gemm_prof_enable(int on);
 int gemm_prof_collect(double* flops, float* ms);
+double gemm_prof_bytes();
 
 // attention.cu
 int attn_sparse3dna(const AttnParams& p, cudaStream_t s);
