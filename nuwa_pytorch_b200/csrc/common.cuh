@@ -48,8 +48,25 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// Exact-erf GELU (F.gelu default, nuwa_pytorch.py:265) with a branch-free erf: Abramowitz-Stegun 7.1.26,
+//   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2),  t = 1 / (1 + p z),  z >= 0,  |error| <= 1.5e-7,
+// i.e. gelu error <= 0.75e-7 |x| absolute -- below fp32 erff's own rounding for |x| < 2 and far below the bf16 the
+// result is stored in.  erff() is two branchy polynomial paths; in the GEGLU epilogue of the FF1 GEMM (16 outputs per
+// accumulator chunk per thread, 2 epilogue warps per scheduler) that made the epilogue, not the MMA, the critical
+// path (107 us vs 56 us for the same GEMM without the activation).  Straight-line code lets the 16 evaluations
+// interleave.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float q = fmaf(t, 1.061405429f, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  q = q * t * fast_exp2(z * z * -1.4426950408889634f);  // 1 - erf(z)
+  return 0.5f * x * (x >= 0.f ? 2.0f - q : q);
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float leaky01(float x) { return x > 0.f ? x : 0.1f * x; }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

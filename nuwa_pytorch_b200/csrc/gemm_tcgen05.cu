@@ -21,6 +21,8 @@
 //   nn.Linear  nuwa_pytorch.py:274,277,311-313,401-405,1819   nn.Conv2d  vqgan_vae.py:216-238,262-263,352-366
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -373,8 +375,54 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             // ---- TMA-store epilogue: this lane's accumulator row (32 columns) -> bias / LeakyReLU -> swizzled slab row,
             //      one elected lane hands the 32 x 32 slab to the TMA unit (bounds are clipped by the tensor map; split-K
             //      partial products use the fp32 reduce-add form) ----
-            if (lane == 0) tma_store_wait_read0();  // the previous store has finished reading the slab
-            __syncwarp();
+            // Pair activations (GLU / GEGLU): a 32-column chunk is 16 value + 16 gate columns -> 16 outputs; the two
+            // chunks of an even/odd pair (same warp: CPW is even) fill the left and right half of ONE slab.
+            const int sub = pair ? (c & 1) : 0;
+            if (sub == 0) {
+              if (lane == 0) tma_store_wait_read0();  // the previous store has finished reading the slab
+              __syncwarp();
+            }
+            if (pair) {
+              // (warp-uniform branches hoisted out of the element loops: with a branch per element the 16
+              //  activations become 16 basic blocks and their dependency chains run one after the other)
+              float o[16], g[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                o[j] = __uint_as_float(v[j]);
+                g[j] = __uint_as_float(v[16 + j]);
+              }
+              if (p.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + nc + j));
+                  const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 16 + j));
+                  o[j] += ba.x; o[j + 1] += ba.y; o[j + 2] += ba.z; o[j + 3] += ba.w;
+                  g[j] += bg.x; g[j + 1] += bg.y; g[j + 2] += bg.z; g[j + 3] += bg.w;
+                }
+              }
+              if (p.act == ACT_GLU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] *= sigmoid_f(g[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] *= gelu_erf(g[j]);
+              }
+              if (p.out_f32 != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  *reinterpret_cast<float4*>(slab + lane * 128 + (((sub * 4 + k) ^ (lane & 7)) << 4)) =
+                      make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  uint4 u;
+                  u.x = pack_bf16x2(o[8 * k], o[8 * k + 1]); u.y = pack_bf16x2(o[8 * k + 2], o[8 * k + 3]);
+                  u.z = pack_bf16x2(o[8 * k + 4], o[8 * k + 5]); u.w = pack_bf16x2(o[8 * k + 6], o[8 * k + 7]);
+                  *reinterpret_cast<uint4*>(slab + lane * 64 + (((sub * 2 + k) ^ ((lane >> 1) & 3)) << 4)) = u;
+                }
+              }
+              if (sub == 0) continue;  // the odd chunk of the pair completes the slab (N % 64 == 0, host-checked)
+            } else {
             float o[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
@@ -401,12 +449,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 *reinterpret_cast<uint4*>(slab + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = u;
               }
             }
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
               const int m0 = tc.mt * BM + q * 32;
-              if (p.tma_out == 2) tma_reduce_add_2d(&tmC, slab, nc, m0);
-              else tma_store_2d(&tmC, slab, nc, m0);
+              const int ncol = pair ? (nc - 32) / 2 : nc;
+              if (p.tma_out == 2) tma_reduce_add_2d(&tmC, slab, ncol, m0);
+              else tma_store_2d(&tmC, slab, ncol, m0);
               tma_store_commit();
             }
           } else if (nc < p.N) {  // warp-uniform
@@ -608,9 +658,13 @@ static int dispatch_gemm(const CUtensorMap* mA, const void* Wp, GemmParams& p, i
     const bool f32 = p.out_f32 != nullptr;
     const void* outp = f32 ? (const void*)p.out_f32 : (const void*)p.out_bf16;
     const size_t esz = f32 ? 4 : 2;
-    if (!p.conv && p.residual == nullptr && one_out && (p.act == ACT_NONE || p.act == ACT_LEAKY) &&
+    const bool pair = (p.act == ACT_GLU || p.act == ACT_GEGLU);
+    // pair activations: the two 32-column chunks that share a slab must belong to one epilogue warp (bn >= 128)
+    static const bool pair_tma = getenv("NUWA_PAIR_STAGED") == nullptr;  // measurement switch (tools/gemm_epi_perf.py)
+    const bool pair_ok = !pair || (pair_tma && bn >= 128 && p.N % 64 == 0 && !p.atomic_out);
+    if (!p.conv && p.residual == nullptr && one_out && pair_ok &&
         (reinterpret_cast<uintptr_t>(outp) & 15) == 0 && ((size_t)p.ld_out * esz) % 16 == 0 && (!p.atomic_out || f32)) {
-      uint64_t dimsC[2] = {(uint64_t)p.N, (uint64_t)p.M};
+      uint64_t dimsC[2] = {(uint64_t)(pair ? p.N / 2 : p.N), (uint64_t)p.M};
       uint64_t strC[2] = {esz, (uint64_t)p.ld_out * esz};
       uint32_t boxC[2] = {32, 32};
       if (encode_map(&mC, outp, 2, dimsC, strC, boxC, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
