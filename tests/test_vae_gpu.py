@@ -127,3 +127,30 @@ def test_vae_rejects_bad_input_like_reference(cuda_device):
         vae(torch.randn(1, 3, 32, 32, device=cuda_device))
     with pytest.raises(AssertionError):
         vae(torch.randn(1, 1, 64, 64, device=cuda_device))
+
+
+def test_video_index_dataset_roundtrip_on_gpu(cuda_device, tmp_path):
+    """data.convert_video_tensor_dataset_to_indices with the product VAE: rows of the int64 memmap == get_video_indices of
+    each video (batched pinned-staging path vs per-video calls), and the reader returns them."""
+    from nuwa_pytorch_b200.data import VideoIndicesDataset, convert_video_tensor_dataset_to_indices
+    from tests.helpers_data import StubVideos
+    import numpy as np
+    fx = golden("vae_small_l4.pt")
+    vae, sd = _build(fx, cuda_device)
+    size, frames = vae.image_size, 3
+    videos = StubVideos(n=5, frames=frames, channels=3, size=size, seed=3)
+    path = str(tmp_path / "idx.bin")
+    shape = convert_video_tensor_dataset_to_indices(vae=vae, raw_video_dataset=videos, num_frames=frames, path=path, batch_videos=2)
+    fm = size // 4 ** 2
+    assert shape == (5, frames * fm * fm)
+    rows = np.memmap(path, dtype=np.int64, mode="r", shape=shape)
+    with torch.no_grad():
+        for i in range(5):
+            ref = vae.get_video_indices(videos[i][1][None].to(cuda_device)).reshape(-1).cpu().numpy()
+            assert (rows[i] == ref).mean() >= 0.99  # same kernels; batch-dependent tiling may flip a near-tie
+    lab = np.memmap(str(tmp_path / "t.bin"), dtype=np.uint8, mode="w+", shape=(5, 2))
+    lab[:] = 7
+    lab.flush()
+    ds = VideoIndicesDataset(videos_memmap_path=path, text_memmap_path=str(tmp_path / "t.bin"), vae=vae, num_videos=5, num_frames=frames)
+    t, v = ds[4]
+    assert v.tolist() == rows[4].tolist() and t.tolist() == [7, 7]
