@@ -212,6 +212,7 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
     from nuwa_pytorch_b200 import _lib
