@@ -406,8 +406,20 @@ def run_ours(args):
             l0 = _lib.launch_count()
             sk_step(sketch, svideo)
             sl = _lib.launch_count() - l0
-            ssec = timed(lambda: sk_step(sketch, svideo), args.steps, args.warmup, dist, None)
-            ssec_e2e = timed(lambda: float(sk_step(h_sketch.to(dev, non_blocking=True), h_svideo.to(dev, non_blocking=True)).item()),
+            sk_mode = "eager launches" + ("" if world == 1 else " + overlapped NCCL gradient all-reduce")
+            sk_runner = sk_step
+            if world == 1:  # whole step (both VAE encodes, forward, backward) as ONE CUDA graph, like the cfg-3 leg
+                try:
+                    def sk_loss(s_, v_):
+                        return sk(sketch=s_, sketch_mask=smask.clone(), video=v_, return_loss=True)
+                    sk_runner = GraphedTrainStep(sk_loss, sparams, sketch, svideo)
+                    sk_mode = "one CUDA graph replay per step (VAE encodes + forward + backward, GraphedTrainStep)"
+                except Exception as e:  # capture is an optimisation of the launch path only
+                    print(f"[bench] NUWASketch step not captured ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
+                    torch.cuda.synchronize()
+                    sk_runner = sk_step
+            ssec = timed(lambda: sk_runner(sketch, svideo), args.steps, args.warmup, dist, None)
+            ssec_e2e = timed(lambda: float(sk_runner(h_sketch.to(dev, non_blocking=True), h_svideo.to(dev, non_blocking=True)).item()),
                              args.steps, 1, dist, None)
             stok = SB * 2560
             decoder["sketch_train"] = dict(
@@ -415,11 +427,11 @@ def run_ours(args):
                 value=round(world * stok * args.steps / ssec, 1), unit="tokens/s", ms_per_step=round(1e3 * ssec / args.steps, 3),
                 e2e=dict(value=round(world * stok * args.steps / ssec_e2e, 1), unit="tokens/s",
                          h2d_bytes_per_step=int(h_sketch.numel() * 4 + h_svideo.numel() * 4), d2h_bytes_per_step=4),
-                gpu_launches=int(sl), launch="eager launches" + ("" if world == 1 else " + overlapped NCCL gradient all-reduce"),
+                gpu_launches=int(sl), launch=sk_mode,
                 config=dict(workload="NUWASketch dim=512 sketch_enc_depth=12 (Sparse3DNA) sketch_max_video_frames=3 dec_depth=24 "
                             "(Sparse3DNA + SparseCross2DNA) max_video_frames=10, loss.backward() (BASELINE configs[4])",
                             batch_per_gpu=SB, tokens_per_sample=2560, context_tokens=768))
-            del sk, svae, vvae
+            del sk, svae, vvae, sk_runner
             torch.cuda.empty_cache()
 
     # -------- generate() (configs[3]): depth-64 reversible decoder, 5 frames = 1280 AR steps, KV-cached, --------

@@ -284,6 +284,16 @@ int nuwa_vae_attn_prep(const float* qkv, void* out, int B, int n, int inner, voi
  * euclid -> raw codebook + code_sq[Kc] = |e|^2.  out: int64 [M], first maximum wins. */
 int nuwa_vq_argmax(const float* x, const float* code, const float* code_sq, long long* out, int M, int Kc, int D,
                    int cosine, void* stream);
+/* Same arg-max with the M x Kc x D contraction on the tensor cores and an exact fp32 re-score of every code inside the
+ * provable bf16 error band of the row maximum (csrc/vae_ops.cu: vq_argmax_tc), so the result is the fp32 arg-max.
+ * code_bf16: bf16 copy of `code`; emax: DEVICE scalar holding max_j |code_j| (read by the kernel, so packing the
+ * codebook needs no host synchronisation); workspace:
+ * nuwa_vq_argmax_tc_workspace(M, Kc, D) bytes of device memory, 16-byte aligned.  Envelope: D % 8 == 0, D <= 1024,
+ * Kc % 4 == 0; NUWA_ERR_INVALID outside it. */
+unsigned long long nuwa_vq_argmax_tc_workspace(int M, int Kc, int D);
+int nuwa_vq_argmax_tc(const float* x, const float* code, const float* code_sq, const void* code_bf16, const float* emax,
+                      long long* out, int M, int Kc, int D, int cosine, void* workspace, unsigned long long workspace_bytes,
+                      void* stream);
 /* F.embedding / codebook[indices] (vqgan_vae.py:447, nuwa_pytorch.py:1910) */
 int nuwa_gather_rows(const float* table, const long long* idx, void* out_bf16, float* out_f32, long long M, int D,
                      void* stream);

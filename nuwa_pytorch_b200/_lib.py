@@ -141,6 +141,9 @@ SIGNATURES = {
     "nuwa_upsample2x_nhwc_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "nuwa_vae_attn_prep": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "nuwa_vq_argmax": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "nuwa_vq_argmax_tc_workspace": [c_int, c_int, c_int],
+    "nuwa_vq_argmax_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                          ctypes.c_ulonglong, c_void_p],
     "nuwa_gather_rows": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "nuwa_conv1x1_nhwc_to_nchw": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     # ---- training (backward) ----
@@ -175,7 +178,7 @@ SIGNATURES = {
     "nuwa_attn3dna_bwd_first_key_finalize": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p],
     "nuwa_struct_sizes_bwd": [P(c_int)],
 }
-_RESTYPES = {"nuwa_strerror": ctypes.c_char_p, "nuwa_gemm_prof_bytes": ctypes.c_double, "nuwa_launch_count": ctypes.c_ulonglong, "nuwa_struct_sizes": None,
+_RESTYPES = {"nuwa_strerror": ctypes.c_char_p, "nuwa_vq_argmax_tc_workspace": ctypes.c_ulonglong, "nuwa_gemm_prof_bytes": ctypes.c_double, "nuwa_launch_count": ctypes.c_ulonglong, "nuwa_struct_sizes": None,
              "nuwa_gemm_prof_enable": None, "nuwa_struct_sizes_bwd": None, "nuwa_struct_sizes_decode": None, "nuwa_struct_sizes_optim": None}
 
 _lib = None

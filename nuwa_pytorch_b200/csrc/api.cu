@@ -128,6 +128,12 @@ int nuwa_upsample2x_nhwc_bf16(const void* in, void* out, int B, int H, int W, in
 int nuwa_vae_attn_prep(const float* qkv, void* out, int B, int n, int inner, void* stream) {
   return vae_attn_prep(qkv, out, B, n, inner, S(stream));
 }
+unsigned long long nuwa_vq_argmax_tc_workspace(int M, int Kc, int D) { return (unsigned long long)vq_argmax_tc_workspace(M, Kc, D); }
+int nuwa_vq_argmax_tc(const float* x, const float* code, const float* code_sq, const void* code_bf16, const float* emax,
+                      long long* out, int M, int Kc, int D, int cosine, void* workspace, unsigned long long workspace_bytes,
+                      void* stream) {
+  return vq_argmax_tc(x, code, code_sq, code_bf16, emax, out, M, Kc, D, cosine, workspace, (size_t)workspace_bytes, S(stream));
+}
 int nuwa_vq_argmax(const float* x, const float* code, const float* code_sq, long long* out, int M, int Kc, int D,
                    int cosine, void* stream) {
   return vq_argmax(x, code, code_sq, out, M, Kc, D, cosine, S(stream));

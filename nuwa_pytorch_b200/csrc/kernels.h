@@ -96,6 +96,9 @@ int upsample2x_nhwc_bf16(const void* in, void* out, int B, int H, int W, int C, 
 int vae_attn_prep(const float* qkv, void* out, int B, int n, int inner, cudaStream_t stream);
 int vq_argmax(const float* x, const float* code, const float* code_sq, long long* out, int M, int Kc, int D, int cosine,
               cudaStream_t stream);
+size_t vq_argmax_tc_workspace(int M, int Kc, int D);
+int vq_argmax_tc(const float* x, const float* code, const float* code_sq, const void* code_bf16, const float* emax,
+                 long long* out, int M, int Kc, int D, int cosine, void* workspace, size_t ws_bytes, cudaStream_t stream);
 int gather_rows(const float* table, const long long* idx, void* out_bf16, float* out_f32, long long M, int D,
                 cudaStream_t stream);
 int conv1x1_nhwc_to_nchw(const void* x, const float* w, const float* bias, float* out, int B, int HW, int C, int Cout,

@@ -456,6 +456,130 @@ int vq_argmax(const float* x, const float* code, const float* code_sq, long long
   return NUWA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// VQ arg-max on the tensor cores, exact: (1) bf16 similarity GEMM (tcgen05) of all tokens against all codes,
+// (2) per token, every code whose bf16 score lies within the PROVABLE bf16 error band of the row maximum is
+// re-scored in fp32 exactly as vq_argmax_kernel does; the best exact score wins, first index on ties.
+//
+// Error band: operands rounded to bf16 (unit roundoff u = 2^-8), fp32 accumulation:
+//   |s~_j - s_j| <= (2u + u^2) sum_d |x_d e_jd| + (fp32 accumulation) <= E := 2^-7 (1 + 2^-6) |x| max_j|e_j|
+// so with t_j = s_j (cosine) or 2 s_j - |e_j|^2 (euclid: arg-max of -(|x|^2 - 2 s + |e|^2)), c = 1 resp. 2:
+//   t~_j >= max_j t~_j - 2 c E  holds for the true arg-max.  For unit vectors in 512 dimensions that is ~4-16 codes
+// of 8192 per token.  The fp32 CUDA-core kernel needs M*Kc*D FMAs (cfg 5: 14.5 ms of a 64 ms step, cfg 2: 5 ms of
+// 126 ms); this path runs the same contraction at tensor-core rate and reads the scores twice.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+vq_prep_kernel(const float* __restrict__ x, bf16* __restrict__ xb, int M, int D, int cosine) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  const float* xr = x + (long long)m * D;
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) { const float v = xr[d]; s = fmaf(v, v, s); }
+  s = warp_sum(s);
+  const float inv = cosine ? 1.0f / fmaxf(sqrtf(s), 1e-12f) : 1.0f;
+  for (int d = lane; d < D; d += 32) xb[(long long)m * D + d] = __float2bfloat16(xr[d] * inv);
+}
+
+template <int NV>  // D <= 128 * NV
+__global__ void __launch_bounds__(256)
+vq_refine_kernel(const float* __restrict__ x, const float* __restrict__ code, const float* __restrict__ code_sq,
+                 const float* __restrict__ scores, long long* __restrict__ out, int M, int Kc, int D, int cosine,
+                 const float* __restrict__ emax_ptr) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  // this lane's slice of the token row: dims lane*4 + 128*i .. +3 (scaled as vq_argmax_kernel scales it)
+  float4 xv[NV];
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int d = lane * 4 + 128 * i;
+    xv[i] = d < D ? *reinterpret_cast<const float4*>(x + (long long)m * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sq += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+  }
+  sq = warp_sum(sq);
+  float xnorm = sqrtf(sq);
+  if (cosine) {
+    const float inv = 1.0f / fmaxf(xnorm, 1e-12f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { xv[i].x *= inv; xv[i].y *= inv; xv[i].z *= inv; xv[i].w *= inv; }
+    xnorm = 1.0f;
+  }
+  const float cfac = cosine ? 1.0f : 2.0f;
+  const float emax = __ldg(emax_ptr);
+  const float band = 2.0f * cfac * 0.0079345703125f * xnorm * emax + 1e-30f;  // 2 c E,  E = 2^-7 (1 + 2^-6) |x| max|e|
+  const float* srow = scores + (long long)m * Kc;
+  // pass 1: row maximum of the bf16-operand scores
+  float tmax = -FLT_MAX;
+  for (int j = lane; j < Kc; j += 32) {
+    const float t = cosine ? srow[j] : 2.0f * srow[j] - code_sq[j];
+    tmax = fmaxf(tmax, t);
+  }
+  tmax = warp_max(tmax);
+  const float thr = tmax - band;
+  // pass 2: exact fp32 re-score of the codes inside the band, in index order
+  float best = -FLT_MAX;
+  int besti = 0x7fffffff;
+  for (int j0 = 0; j0 < Kc; j0 += 32) {
+    const int j = j0 + lane;
+    bool cand = false;
+    if (j < Kc) {
+      const float t = cosine ? srow[j] : 2.0f * srow[j] - code_sq[j];
+      cand = t >= thr;
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, cand);
+    while (mask) {
+      const int jj = j0 + (__ffs(mask) - 1);
+      mask &= mask - 1;
+      const float* cr = code + (long long)jj * D;
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int d = lane * 4 + 128 * i;
+        if (d < D) {
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(cr + d));
+          dot = fmaf(xv[i].x, c4.x, dot); dot = fmaf(xv[i].y, c4.y, dot);
+          dot = fmaf(xv[i].z, c4.z, dot); dot = fmaf(xv[i].w, c4.w, dot);
+        }
+      }
+      dot = warp_sum(dot);
+      const float sc = cosine ? dot : -(sq - 2.0f * dot + code_sq[jj]);
+      if (sc > best) { best = sc; besti = jj; }  // candidates arrive in increasing index order: first maximum wins
+    }
+  }
+  if (lane == 0) out[m] = besti;
+}
+
+// workspace: M*D bf16 (token rows, normalised for cosine) followed by M*Kc fp32 (scores), 16-byte aligned.
+// Envelope: D % 8 == 0, D <= 1024, Kc % 4 == 0; NUWA_ERR_INVALID outside it (caller uses vq_argmax).
+size_t vq_argmax_tc_workspace(int M, int Kc, int D) {
+  const size_t a = ((size_t)M * D * 2 + 255) & ~(size_t)255;
+  return a + (size_t)M * Kc * 4;
+}
+int vq_argmax_tc(const float* x, const float* code, const float* code_sq, const void* code_bf16, const float* emax,
+                 long long* out, int M, int Kc, int D, int cosine, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  if (M <= 0 || Kc <= 0 || D <= 0 || code_bf16 == nullptr || workspace == nullptr || emax == nullptr) return NUWA_ERR_INVALID;
+  if ((D % 8) || D > 1024 || (Kc % 4)) return NUWA_ERR_INVALID;
+  if (!cosine && code_sq == nullptr) return NUWA_ERR_INVALID;
+  if (ws_bytes < vq_argmax_tc_workspace(M, Kc, D)) return NUWA_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 15) || (reinterpret_cast<uintptr_t>(x) & 15) ||
+      (reinterpret_cast<uintptr_t>(code) & 15) || (reinterpret_cast<uintptr_t>(code_bf16) & 15))
+    return NUWA_ERR_INVALID;
+  bf16* xb = reinterpret_cast<bf16*>(workspace);
+  float* scores = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + (((size_t)M * D * 2 + 255) & ~(size_t)255));
+  vq_prep_kernel<<<ceil_div(M, 8), 256, 0, stream>>>(x, xb, M, D, cosine);
+  NUWA_CHECK_LAUNCH();
+  const int rc = gemm_bf16(xb, D, code_bf16, D, M, Kc, D, nullptr, nullptr, 0, scores, nullptr, Kc, ACT_NONE, 0, stream);
+  if (rc != NUWA_OK) return rc;
+  const int grid = ceil_div(M, 8);
+  if (D <= 256) vq_refine_kernel<2><<<grid, 256, 0, stream>>>(x, code, code_sq, scores, out, M, Kc, D, cosine, emax);
+  else if (D <= 512) vq_refine_kernel<4><<<grid, 256, 0, stream>>>(x, code, code_sq, scores, out, M, Kc, D, cosine, emax);
+  else vq_refine_kernel<8><<<grid, 256, 0, stream>>>(x, code, code_sq, scores, out, M, Kc, D, cosine, emax);
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+
 // gather rows of an fp32 table -> bf16 (codebook lookup feeding project_out / decode) and/or fp32
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const float* __restrict__ table, const long long* __restrict__ idx, bf16* __restrict__ out_bf16,

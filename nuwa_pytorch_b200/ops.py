@@ -360,10 +360,29 @@ def vae_attn_prep(qkv_f32, B, n, inner):
     return out
 
 
-def vq_argmax(x, code, code_sq=None, cosine=True):
+def vq_argmax(x, code, code_sq=None, cosine=True, code16=None, emax=None, variant='auto'):
+    """arg-max codebook index per row of x (M, D) fp32.  variant 'auto': the tensor-core path (bf16 similarity GEMM +
+    exact fp32 re-score of the codes inside the bf16 error band: csrc/vae_ops.cu vq_argmax_tc) when a bf16 codebook copy
+    `code16` and `emax` = max |code row| (a 1-element fp32 DEVICE tensor) are supplied and the problem is large enough to pay for the score matrix;
+    'fp32' pins the CUDA-core kernel, 'tc' the tensor-core path."""
     M, D = x.shape
+    Kc = code.shape[0]
     out = torch.empty(M, dtype=torch.int64, device=x.device)
-    check(lib().nuwa_vq_argmax(ptr(x), ptr(code), ptr(code_sq), ptr(out), M, code.shape[0], D, int(cosine), stream()),
+    want_tc = variant == 'tc' or (variant == 'auto' and code16 is not None and emax is not None and M * Kc >= (1 << 20))
+    if want_tc:
+        if code16 is None:
+            code16 = code.to(torch.bfloat16)
+        if emax is None:
+            emax = code.norm(dim=-1).max().reshape(1).float()
+        nbytes = int(lib().nuwa_vq_argmax_tc_workspace(M, Kc, D))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        rc = lib().nuwa_vq_argmax_tc(ptr(x), ptr(code), ptr(code_sq), ptr(code16), ptr(emax), ptr(out), M, Kc, D,
+                                     int(cosine), ptr(ws), nbytes, stream())
+        if rc == 0:
+            return out
+        if variant == 'tc' or rc != _lib.NUWA_ERR_INVALID:
+            check(rc, "nuwa_vq_argmax_tc")
+    check(lib().nuwa_vq_argmax(ptr(x), ptr(code), ptr(code_sq), ptr(out), M, Kc, D, int(cosine), stream()),
           "nuwa_vq_argmax")
     return out
 

@@ -275,6 +275,9 @@ class VQGanVAE(nn.Module):
         else:
             vq['code'] = vq['embed']
             vq['code_sq'] = vq['embed'].pow(2).sum(-1).contiguous()
+        # tensor-core arg-max (ops.vq_argmax 'auto'): bf16 copy of the compared codebook + its largest row norm (pack time)
+        vq['code16'] = vq['code'].to(torch.bfloat16).contiguous()
+        vq['emax'] = vq['code'].norm(dim=-1).max().reshape(1).float().contiguous()  # device scalar: no host sync
         if isinstance(self.vq.project_in, nn.Linear):
             vq['pin'] = lin_pack(self.vq.project_in.weight, self.vq.project_in.bias)
             vq['pout'] = lin_pack(self.vq.project_out.weight, self.vq.project_out.bias)
@@ -344,7 +347,7 @@ class VQGanVAE(nn.Module):
         M = B * H * W
         flat = ops.gemm(x16.view(M, C), pk['pin']['w'], bias=pk['pin']['b'], out_dtype=torch.float32) if 'pin' in pk \
             else x32.view(M, C)
-        ind = ops.vq_argmax(flat, pk['code'], pk['code_sq'], cosine=pk['cosine'])
+        ind = ops.vq_argmax(flat, pk['code'], pk['code_sq'], cosine=pk['cosine'], code16=pk['code16'], emax=pk['emax'])
         if 'pout' in pk:
             q16 = ops.gather_rows(pk['embed'], ind)
             q32, q16 = ops.gemm(q16, pk['pout']['w'], bias=pk['pout']['b'], out_dtype=torch.float32, also_bf16=True)
@@ -414,7 +417,7 @@ class VQGanVAE(nn.Module):
         B, H, W, C = x16.shape
         flat = ops.gemm(x16.view(-1, C), pk['pin']['w'], bias=pk['pin']['b'], out_dtype=torch.float32) if 'pin' in pk \
             else x32.view(-1, C)
-        ind = ops.vq_argmax(flat, pk['code'], pk['code_sq'], cosine=pk['cosine'])  # project_out is not needed here
+        ind = ops.vq_argmax(flat, pk['code'], pk['code_sq'], cosine=pk['cosine'], code16=pk['code16'], emax=pk['emax'])  # project_out is not needed here
         return ind.view(b, f, H, W)
 
     def forward(self, img, return_loss=False, return_discr_loss=False, return_recons=False, apply_grad_penalty=False):

@@ -106,7 +106,11 @@ def test_sparse3dna_tensor_core_kernel_matches_gather_kernel(cuda_device, H, dh,
 @pytest.mark.parametrize("kernel,dil,nv,B,talk_on", [((5, 3, 3), (1, 1, 1), 768, 2, True), ((5, 3, 3), (2, 2, 2), 1279, 2, True),
                                                      ((5, 3, 3), (4, 4, 4), 2559, 3, True), ((5, 3, 3), (1, 2, 4), 601, 1, True),
                                                      ((3, 3, 5), (2, 4, 2), 530, 2, False), ((3, 1, 3), (1, 1, 3), 256, 2, True),
-                                                     ((5, 3, 3), (3, 5, 2), 1024, 1, True), ((1, 3, 15), (1, 2, 1), 300, 2, True)])
+                                                     ((5, 3, 3), (3, 5, 2), 1024, 1, True), ((1, 3, 15), (1, 2, 1), 300, 2, True),
+                                                     ((5, 3, 3), (1, 1, 1), 1, 2, True), ((5, 3, 3), (1, 2, 4), 5, 1, True),
+                                                     ((5, 3, 3), (2, 2, 2), 16, 2, True), ((5, 3, 3), (1, 1, 1), 17, 1, True),
+                                                     ((3, 3, 3), (1, 1, 1), 255, 2, True), ((5, 3, 3), (4, 4, 4), 257, 3, True),
+                                                     ((5, 3, 3), (9, 9, 9), 2560, 1, True)])
 def test_sparse3dna_halo_kernel_matches_gather_kernel(cuda_device, kernel, dil, nv, B, talk_on):
     """attention_3dna_halo.cu (TMA-staged key rows shared by 4 query rows, banded mma.sync blocks) vs the generic
     gather kernel on identical bf16 q|k|v, incl. partial last rows / frames and mixed per-axis dilations."""
