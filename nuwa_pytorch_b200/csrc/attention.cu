@@ -708,15 +708,47 @@ __global__ void __launch_bounds__(1024)
 first_key_kernel(const bf16* __restrict__ q, long long q_bs, int q_rs, const bf16* __restrict__ dO, long long do_bs, int do_rs,
                  const bf16* __restrict__ dS, const bf16* __restrict__ Pp, int jp, int H, int dh, int nq, int chunk,
                  float* __restrict__ out_k, float* __restrict__ out_v, long long ok_bs) {
+  // The slot-0 weights of the chunk's queries are staged in shared memory first (they are one strided 2-byte load per
+  // (head, query): read inside the accumulation loop they put two dependent L2 round trips on every iteration), then
+  // the loop streams the q / dO rows (coalesced across the channel threads) with 8 independent loads in flight.
+  extern __shared__ float fk_w[];  // [2][H][chunk]
   const int b = blockIdx.y, c = threadIdx.x, h = c / dh;
   const int q0 = blockIdx.x * chunk, q1 = min(nq, q0 + chunk);
+  float* ws_s = fk_w;
+  float* wp_s = fk_w + H * chunk;
+  for (int i = threadIdx.x; i < H * chunk; i += blockDim.x) {
+    const int hh = i / chunk, ql = q0 + (i - hh * chunk);
+    float a = 0.f, p2 = 0.f;
+    if (ql < nq) {
+      const long long o = (((long long)b * H + hh) * nq + ql) * jp;
+      a = __bfloat162float(dS[o]);
+      p2 = __bfloat162float(Pp[o]);
+    }
+    ws_s[i] = a;
+    wp_s[i] = p2;
+  }
+  __syncthreads();
   float ak = 0.f, av = 0.f;
-  const long long hb = ((long long)b * H + h) * nq;
-  for (int ql = q0; ql < q1; ++ql) {
-    const float ws = __bfloat162float(dS[(hb + ql) * jp]);
-    const float wp = __bfloat162float(Pp[(hb + ql) * jp]);
-    ak = fmaf(ws, __bfloat162float(q[(long long)b * q_bs + (long long)ql * q_rs + c]), ak);
-    av = fmaf(wp, __bfloat162float(dO[(long long)b * do_bs + (long long)ql * do_rs + c]), av);
+  const bf16* qp = q + (long long)b * q_bs + (long long)q0 * q_rs + c;
+  const bf16* dp = dO + (long long)b * do_bs + (long long)q0 * do_rs + c;
+  const int n = q1 - q0;
+  int i = 0;
+  for (; i + 8 <= n; i += 8) {
+    float qv[8], dv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      qv[u] = __bfloat162float(qp[(long long)(i + u) * q_rs]);
+      dv[u] = __bfloat162float(dp[(long long)(i + u) * do_rs]);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      ak = fmaf(ws_s[h * chunk + i + u], qv[u], ak);
+      av = fmaf(wp_s[h * chunk + i + u], dv[u], av);
+    }
+  }
+  for (; i < n; ++i) {
+    ak = fmaf(ws_s[h * chunk + i], __bfloat162float(qp[(long long)i * q_rs]), ak);
+    av = fmaf(wp_s[h * chunk + i], __bfloat162float(dp[(long long)i * do_rs]), av);
   }
   atomicAdd(out_k + (long long)b * ok_bs + c, ak);
   atomicAdd(out_v + (long long)b * ok_bs + c, av);
@@ -896,7 +928,7 @@ int attn_bwd_first_key(const void* q, long long q_bs, int q_rs, const void* dO, 
   if (inner > 1024 || inner <= 0 || B <= 0 || nq <= 0) return NUWA_ERR_INVALID;
   const int chunk = 64;
   dim3 grid(ceil_div(nq, chunk), B);
-  first_key_kernel<<<grid, inner, 0, stream>>>(reinterpret_cast<const bf16*>(q), q_bs, q_rs, reinterpret_cast<const bf16*>(dO),
+  first_key_kernel<<<grid, inner, 2 * H * chunk * sizeof(float), stream>>>(reinterpret_cast<const bf16*>(q), q_bs, q_rs, reinterpret_cast<const bf16*>(dO),
                                                do_bs, do_rs, reinterpret_cast<const bf16*>(dS),
                                                reinterpret_cast<const bf16*>(Pp), jp, H, dh, nq, chunk, out_k, out_v, ok_bs);
   NUWA_CHECK_LAUNCH();

@@ -25,10 +25,10 @@ for it in range(2):
         p.grad = None
     torch.cuda.synchronize()
     if it == 1:
-        torch.cuda.nvtx.range_push("step")
+        torch.cuda.profiler.start()
     loss = sk(sketch=sketch, sketch_mask=mask.clone(), video=video, return_loss=True)
     loss.backward()
     torch.cuda.synchronize()
     if it == 1:
-        torch.cuda.nvtx.range_pop()
+        torch.cuda.profiler.stop()
 print(float(loss))
