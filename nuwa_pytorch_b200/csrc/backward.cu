@@ -276,11 +276,67 @@ transpose_bf16_kernel(const bf16* __restrict__ in, long long ld_in, bf16* __rest
     }
   }
 }
+// Same transpose with 32-bit shared-memory traffic: the tile is stored as bf16 PAIRS (two adjacent input columns per
+// word); a thread reads the 8 words (rows rr..rr+7, column pair cp) and splits them with byte permutes into the two
+// 16-byte output rows 2cp and 2cp+1 -- one pass, 8 LDS.32 per 16 output elements instead of 16 LDS.U16, and a warp's
+// stores cover 128 contiguous bytes of 4 output rows.  Needs ld_in % 8 == 0, ld_out % 8 == 0 (16-byte vectors).
+__global__ void __launch_bounds__(256)
+transpose_bf16_pairs_kernel(const bf16* __restrict__ in, long long ld_in, bf16* __restrict__ out, long long ld_out, int R, int C) {
+  __shared__ uint32_t tile[64][33];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int r = (tid >> 3) + 32 * pass, cc = (tid & 7) * 8;
+    const int gr = r0 + r, gc = c0 + cc;
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (gr < R && gc + 8 <= C) {
+      u = __ldg(reinterpret_cast<const uint4*>(in + (long long)gr * ld_in + gc));
+    } else if (gr < R && gc < C) {
+      unsigned short e[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) e[i] = gc + i < C ? reinterpret_cast<const unsigned short*>(in)[(long long)gr * ld_in + gc + i] : 0;
+      u.x = e[0] | ((uint32_t)e[1] << 16); u.y = e[2] | ((uint32_t)e[3] << 16);
+      u.z = e[4] | ((uint32_t)e[5] << 16); u.w = e[6] | ((uint32_t)e[7] << 16);
+    }
+    uint32_t* t = &tile[r][cc >> 1];
+    t[0] = u.x; t[1] = u.y; t[2] = u.z; t[3] = u.w;
+  }
+  __syncthreads();
+  const int cp = tid >> 3, rr = (tid & 7) * 8;  // column pair, first of 8 rows
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = tile[rr + i][cp];
+  const int gr = r0 + rr;
+  if (gr >= R) return;
+#pragma unroll
+  for (int hsel = 0; hsel < 2; ++hsel) {
+    const int gc = c0 + 2 * cp + hsel;
+    if (gc >= C) continue;
+    const uint32_t sel = hsel ? 0x7632u : 0x5410u;  // high / low halves of (a, b)
+    uint4 o;
+    o.x = __byte_perm(w[0], w[1], sel); o.y = __byte_perm(w[2], w[3], sel);
+    o.z = __byte_perm(w[4], w[5], sel); o.w = __byte_perm(w[6], w[7], sel);
+    unsigned short* dst = reinterpret_cast<unsigned short*>(out) + (long long)gc * ld_out + gr;
+    if (gr + 8 <= R) {
+      *reinterpret_cast<uint4*>(dst) = o;
+    } else {
+      const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+      for (int i = 0; i < 8 && gr + i < R; ++i) dst[i] = (unsigned short)(ow[i >> 1] >> (16 * (i & 1)));
+    }
+  }
+}
 int transpose_bf16(const void* in, long long ld_in, void* out, long long ld_out, int R, int C, cudaStream_t stream) {
   if (R <= 0 || C <= 0 || ld_in < C || ld_out < R) return NUWA_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return NUWA_ERR_INVALID;
   dim3 grid(ceil_div(C, 64), ceil_div(R, 64));
   if (grid.y > 65535) return NUWA_ERR_INVALID;
+  if ((ld_in & 7) == 0 && (ld_out & 7) == 0) {
+    transpose_bf16_pairs_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(in), ld_in, reinterpret_cast<bf16*>(out),
+                                                          ld_out, R, C);
+    NUWA_CHECK_LAUNCH();
+    return NUWA_OK;
+  }
   transpose_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(in), ld_in, reinterpret_cast<bf16*>(out),
                                                   ld_out, R, C);
   NUWA_CHECK_LAUNCH();

@@ -50,6 +50,12 @@ def test_transpose_and_splitk_gemm(cuda_device):
     x = torch.randn(203, 77, generator=g).bfloat16()
     xt = ops_bwd.transpose(x.to(cuda_device))
     assert xt.shape == (77, 203) and torch.equal(xt.cpu(), x.t())
+    # 16-byte-aligned pitches take the bf16-pair kernel: ragged rows / columns, a strided view, exact tiles
+    for (R, C, pitch) in ((203, 88, 88), (256, 128, 128), (130, 72, 96), (2048, 512, 1536), (7, 8, 8)):
+        base = torch.randn(R, pitch, generator=g).bfloat16().to(cuda_device)
+        xv = base[:, :C]
+        xt = ops_bwd.transpose(xv)
+        assert xt.shape == (C, R) and torch.equal(xt, xv.t()), (R, C, pitch)
     for (M, N, K) in ((512, 192, 5000), (96, 40, 333), (1536, 512, 20480 // 4)):
         a = torch.randn(M, K, generator=g).bfloat16()
         w = torch.randn(N, K, generator=g).bfloat16()
