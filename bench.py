@@ -201,6 +201,57 @@ def timed(fn, steps, warmup, dist, flush):
     return sec
 
 
+def attention_kernel_rooflines(dev, pk):
+    """The two attention cores of the decoder at the cfg-3 shapes, timed alone (CUDA events, L2 flushed between launches):
+    Sparse3DNA against its HBM roofline (4096 algorithmic bytes per token per layer), the text cross
+    attention against the tensor roofline.  A few ms of GPU time."""
+    from nuwa_pytorch_b200 import ops
+    B, H, dh, nv = DEC_BATCH, 8, 64, 2559
+    inner, n = H * dh, nv + 1
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev).manual_seed(7)
+    qkv = torch.randn(B, n, 3 * inner, device=dev, generator=g).bfloat16()
+    talk = torch.randn(H, H, device=dev, generator=g) / 2
+    o = torch.empty(B, n, inner, dtype=torch.bfloat16, device=dev)
+
+    def med_us(fn, iters=7):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2] * 1e3
+
+    out = dict(sparse3dna=[], cross=None)
+    for dil in (1, 2, 4):
+        us = med_us(lambda: ops.attn_sparse3dna(qkv, o, B=B, nq=n, t0=0, npos=n, H=H, dh=dh, talk=talk, fmap=16, max_frames=10,
+                                                nv=nv, kernel=(5, 3, 3), dilation=(dil,) * 3, causal=True))
+        gbs = B * nv * 4096 / (us * 1e-6) / 1e9
+        out["sparse3dna"].append(dict(dilation=dil, us_per_launch=round(us, 1), bound="hbm", achieved=round(gbs, 1),
+                                      peak=pk["hbm_gbs"], unit="GB/s", frac=round(gbs / pk["hbm_gbs"], 4),
+                                      algorithmic_bytes_per_token=4096, kernel="attn_3dna_halo_kernel"))
+    nq, nk = 2560, 256
+    q = torch.randn(B, nq, inner, device=dev, generator=g).bfloat16()
+    kv = torch.randn(B, nk, 2 * inner, device=dev, generator=g).bfloat16()
+    nk_, nv_ = torch.randn(inner, device=dev, generator=g), torch.randn(inner, device=dev, generator=g)
+    mask = torch.ones(B, nk, dtype=torch.uint8, device=dev)
+    oc = torch.empty(B, nq, inner, dtype=torch.bfloat16, device=dev)
+    us = med_us(lambda: ops.attn_dense(q.data_ptr(), kv.data_ptr(), kv.data_ptr() + inner * 2, oc, B=B, nq=nq, nk=nk, H=H, dh=dh,
+                                       q_bs=nq * inner, q_rs=inner, k_bs=nk * 2 * inner, k_rs=2 * inner, v_bs=nk * 2 * inner,
+                                       v_rs=2 * inner, o_bs=nq * inner, o_rs=inner, talk=talk, null_k=nk_, null_v=nv_, key_mask=mask))
+    fl = 2 * 2 * B * H * nq * (nk + 1) * dh
+    out["cross"] = dict(us_per_launch=round(us, 1), bound="tensor", achieved=round(fl / us / 1e6, 1), peak=pk["bf16_tflops_sustained"],
+                        unit="TFLOP/s", frac=round(fl / us / 1e6 / pk["bf16_tflops_sustained"], 4), kernel="attn_dense_pres_kernel",
+                        note="mma.sync + CUDA-core softmax at 8 warps / SM; the fraction is against the tcgen05 GEMM peak")
+    return out
+
+
 def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -370,6 +421,8 @@ def run_ours(args):
             flops=dict(mflop_per_token_fwd_bwd=3 * 104.4,
                        achieved_tflops=round(ntok * args.steps / tsec * 3 * 104.4e6 / 1e12, 1)))
         decoder["config"]["backward"] = "see 'train' (same model and batch, loss.backward() included)"
+        with torch.no_grad():
+            decoder["kernel_rooflines"] = attention_kernel_rooflines(dev, pk)
         del nuwa, tstepper
         torch.cuda.empty_cache()
 
