@@ -263,7 +263,9 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL prints its version banner / debug lines to stdout whenever NCCL_DEBUG is set in the environment (it is on
+        # the GPU boxes); rank 0 must print ONE JSON line, so NCCL's own output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
     from nuwa_pytorch_b200 import _lib
