@@ -261,11 +261,14 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
+    _saved_stdout_fd = None
     if world > 1:
         import torch.distributed as dist_mod
-        # NCCL prints its version banner / debug lines to stdout whenever NCCL_DEBUG is set in the environment (it is on
-        # the GPU boxes); rank 0 must print ONE JSON line, so NCCL's own output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints its version banner straight to stdout when NCCL_DEBUG is set in the environment (it is on the GPU
+        # boxes) -- rank 0 must print ONE JSON line, so file descriptor 1 points at stderr until that line is written
+        sys.stdout.flush()
+        _saved_stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
     from nuwa_pytorch_b200 import _lib
@@ -552,7 +555,12 @@ def run_ours(args):
                              d2h_bytes_per_step=int(host_out.numel() * 4)),
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, clocks=clocks.summary(),
                     decoder=decoder, generate=generate)
+        if _saved_stdout_fd is not None:  # give stdout back for the ONE line
+            sys.stdout.flush()
+            os.dup2(_saved_stdout_fd, 1)
         print(json.dumps(line), flush=True)
+        if _saved_stdout_fd is not None:
+            os.dup2(2, 1)  # anything the teardown prints goes to stderr again
     if dist is not None:
         dist.destroy_process_group()
 
