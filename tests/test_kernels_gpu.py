@@ -152,13 +152,18 @@ def _qkv_from(x, p, heads):
     return torch.cat([q, kv], dim=-1).bfloat16()
 
 
-@pytest.mark.parametrize("causal,kernel,dil,n", [(True, (5, 3, 3), 1, 49), (True, (5, 3, 3), 2, 30), (True, (3, 3, 3), 4, 21),
-                                                 (False, (3, 3, 3), 1, 23), (False, (5, 3, 3), 2, 48)])
-def test_attn_sparse3dna_core(cuda_device, causal, kernel, dil, n):
+@pytest.mark.parametrize("causal,kernel,dil,n,geom", [
+    (True, (5, 3, 3), 1, 49, None), (True, (5, 3, 3), 2, 30, None), (True, (3, 3, 3), 4, 21, None),
+    (False, (3, 3, 3), 1, 23, None), (False, (5, 3, 3), 2, 48, None),
+    # the model geometry (8 x 64 heads, 16-wide grid): causal full passes run attention_3dna_halo.cu -- checked here
+    # directly against the oracle math (tests/test_decode_kernels_gpu.py compares it with the gather kernel)
+    (True, (5, 3, 3), 1, 601, (1, 8, 64, 16, 3)), (True, (5, 3, 3), 2, 769, (1, 8, 64, 16, 3)),
+    (True, (3, 3, 3), 4, 1025, (1, 8, 64, 16, 5))])
+def test_attn_sparse3dna_core(cuda_device, causal, kernel, dil, n, geom):
     """Attention core only: identical bf16 q/k/v in, compare with the oracle run on those same bf16 values."""
     from nuwa_pytorch_b200 import ops
     g = gen(10 + n)
-    B, H, dh, fmap, maxf = 2, 2, 32, 4, 3
+    B, H, dh, fmap, maxf = geom if geom is not None else (2, 2, 32, 4, 3)
     inner = H * dh
     qkv = (torch.randn(B, n, 3 * inner, generator=g)).bfloat16()
     talk = torch.randn(H, H, generator=g) / 2
@@ -188,7 +193,8 @@ def test_attn_sparse3dna_core(cuda_device, causal, kernel, dil, n):
     attn = O._talking_heads(sim.softmax(-1), talk[:, :, None, None])
     out = torch.cat([vh[:, :, :1], torch.einsum('bhij,bhijd->bhid', attn, vg)], dim=2)
     ref = O._merge(out)
-    assert rel(o.float(), ref) < 4e-3  # output rounded to bf16 once
+    # output rounded to bf16 once; the halo kernel also rounds the mixed probabilities to bf16 for the tensor-core PV
+    assert rel(o.float(), ref) < (4e-3 if geom is None else 6e-3)
 
 
 def test_attn_dense_core(cuda_device):
