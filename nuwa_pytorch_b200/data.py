@@ -25,22 +25,36 @@ def _fmap_size(vae):
     return vae.image_size // (vae.num_layers ** 2)  # train_nuwa.py:67 (D5 kept)
 
 
-def convert_video_tensor_dataset_to_indices(*, vae, raw_video_dataset, num_frames, path, batch_videos=8):
+def convert_video_tensor_dataset_to_indices(*, vae, raw_video_dataset, num_frames, path, batch_videos=8, rank=0, world_size=1,
+                                            barrier=None):
     """Same contract as train_nuwa.py:56-80: `raw_video_dataset[i] -> (text, video (f, c, h, w) float)`; writes the
-    int64 memmap at `path` and returns its shape."""
+    int64 memmap at `path` and returns its shape.
+
+    Multi-GPU (one process per GPU): the videos are independent units, so rank r of `world_size` encodes the contiguous
+    slice [r * ceil(n / world), ...) with its own VAE replica and writes those rows of the SAME file -- no data-path
+    collective; `barrier` (e.g. `torch.distributed.barrier`) is called once after rank 0 has created the file and once
+    after every rank has flushed its rows."""
     try:
         device = next(vae.parameters()).device
     except StopIteration:
         device = torch.device('cpu')
     num_videos = len(raw_video_dataset)
     assert num_videos > 0, 'there must be at least 1 video'
+    assert 0 <= rank < world_size and (world_size == 1 or barrier is not None), 'multi-rank conversion needs a barrier callable'
     fmap = _fmap_size(vae)
     shape = (num_videos, num_frames * fmap * fmap)
-    out = np.memmap(path, mode='w+', dtype=np.int64, shape=shape)
+    if rank == 0:
+        out = np.memmap(path, mode='w+', dtype=np.int64, shape=shape)
+    if world_size > 1:
+        barrier()  # the file exists at full size before any other rank maps it
+    if rank != 0:
+        out = np.memmap(path, mode='r+', dtype=np.int64, shape=shape)
+    per = -(-num_videos // world_size)
+    lo, hi = min(num_videos, rank * per), min(num_videos, (rank + 1) * per)
     pinned = device.type == 'cuda'
     stage = None
-    for start in range(0, num_videos, batch_videos):
-        vids = [raw_video_dataset[i][1] for i in range(start, min(start + batch_videos, num_videos))]
+    for start in range(lo, hi, batch_videos):
+        vids = [raw_video_dataset[i][1] for i in range(start, min(start + batch_videos, hi))]
         batch = torch.stack(vids)
         if pinned:
             if stage is None or stage.shape[1:] != batch.shape[1:] or stage.dtype != batch.dtype:
@@ -54,6 +68,8 @@ def convert_video_tensor_dataset_to_indices(*, vae, raw_video_dataset, num_frame
         out[start:start + flat.shape[0]] = flat.numpy()
     out.flush()
     del out
+    if world_size > 1:
+        barrier()  # every rank's rows are on disk
     return shape
 
 

@@ -75,3 +75,36 @@ def test_two_rank_gloo_gradient_allreduce_mean():
         assert p.exitcode == 0
     want = (torch.arange(1000, dtype=torch.float32) * 1.5).tolist()   # mean of x*1 and x*2
     assert res[0][1] == want and res[1][1] == want
+
+
+def _convert_worker(rank, world, port, path, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nuwa_pytorch_b200.data import convert_video_tensor_dataset_to_indices
+    from tests.helpers_data import StubVAE, StubVideos
+    vae = StubVAE(image_size=64, num_layers=4, codebook=97)
+    videos = StubVideos(n=5, frames=3, channels=3, size=64, seed=7)
+    shape = convert_video_tensor_dataset_to_indices(vae=vae, raw_video_dataset=videos, num_frames=3, path=path, batch_videos=2,
+                                                    rank=rank, world_size=world, barrier=dist.barrier)
+    q.put((rank, tuple(shape), sum(vae.calls)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_dataset_conversion_writes_the_reference_bytes(tmp_path):
+    """data.convert_video_tensor_dataset_to_indices sharded over 2 ranks (videos are independent units, no data-path
+    collective): the shared memmap equals the file the UNMODIFIED reference writer produced (tests/golden)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    path = str(tmp_path / "idx.bin")
+    procs = [ctx.Process(target=_convert_worker, args=(r, 2, port, path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1] == (5, 48)
+    assert (res[0][2], res[1][2]) == (3, 2)  # rank 0 encoded videos 0-2, rank 1 videos 3-4
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "video_indices_small.bin")
+    assert open(path, "rb").read() == open(golden, "rb").read()
