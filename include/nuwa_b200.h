@@ -138,9 +138,8 @@ typedef struct {
 } nuwa_attn_params;
 /* Sparse3DNA.forward core, nuwa_pytorch.py:490-608 (jmax = 1 + kt*kh*kw; k/v row 0 = bos, row 1+i = video token i) */
 int nuwa_attn_sparse3dna(const nuwa_attn_params* p, void* vt_workspace, void* stream);
-/* vt_workspace: NULL, or B*H*dh*roundup(nv,16) bf16 elements of scratch; when given and the call is a full causal
- * pass over a 16-wide token grid (t0 == 0, nq == nv + 1, dh in {32,64}, H <= 8) the tensor-core kernel
- * (attention_3dna_tc.cu) runs, otherwise the generic gather kernel. */
+/* vt_workspace: unused (pass NULL); kept so the ABI of round 1 stays valid.  Generic gather kernel: any head geometry,
+ * causal or centred windows, decode steps (t0_ptr). */
 /* Same op on the halo-tiled tensor-core kernel (attention_3dna_halo.cu): one CTA = 4 query rows of a frame, the
  * key rows they share staged in shared memory by TMA, banded 16x16 score / PV blocks on mma.sync.  Envelope: causal
  * full pass (t0 == 0, nq == nv + 1), 16-wide token grid, H == 8, dh == 64, kh <= 3, <= 47 window keys, q|k|v in one
@@ -294,6 +293,17 @@ unsigned long long nuwa_vq_argmax_tc_workspace(int M, int Kc, int D);
 int nuwa_vq_argmax_tc(const float* x, const float* code, const float* code_sq, const void* code_bf16, const float* emax,
                       long long* out, int M, int Kc, int D, int cosine, void* workspace, unsigned long long workspace_bytes,
                       void* stream);
+/* fp32-faithful nn.Linear on the tensor cores: VectorQuantize.project_in (vqgan_vae.py:368-378, third-party
+ * vector_quantize_pytorch `project_in`) feeds the codebook arg-max, so its result must be the fp32 reference's, not a
+ * bf16-operand approximation.  Every fp32 operand is split exactly into three bf16 terms (x = x0 + x1 + x2) and the six
+ * products with i + j <= 2 are accumulated in fp32 by six tcgen05 GEMM launches (csrc/vae_ops.cu).
+ * nuwa_split3_f32_bf16: x[rows][K] fp32 (row stride ld) -> out[rows][3K] bf16 = [x0 | x1 | x2]; used once per weight
+ * version for W.  nuwa_linear_f32x3: out[M,N] fp32 (and, if out_bf16 != NULL, its bf16 rounding) = x[M,K] @ W^T + bias with w3 = split of W[N][K]; workspace =
+ * nuwa_linear_f32x3_workspace(M, K) bytes.  K % 8 == 0. */
+int nuwa_split3_f32_bf16(const float* x, long long ld, void* out, long long rows, int K, void* stream);
+unsigned long long nuwa_linear_f32x3_workspace(int M, int K);
+int nuwa_linear_f32x3(const float* x, long long ldx, const void* w3, int M, int N, int K, const float* bias, float* out,
+                      void* out_bf16, int ld_out, void* workspace, unsigned long long workspace_bytes, void* stream);
 /* F.embedding / codebook[indices] (vqgan_vae.py:447, nuwa_pytorch.py:1910) */
 int nuwa_gather_rows(const float* table, const long long* idx, void* out_bf16, float* out_f32, long long M, int D,
                      void* stream);
@@ -464,7 +474,12 @@ typedef struct {
   float grad_scale;    /* gradients are multiplied by this first (1 / grad_accum_every) */
   const float* sqnorm; /* device scalar: sum of squares of the UNscaled gradient buffer (nuwa_sqnorm_f32) */
   int step;            /* 1-based optimizer step, used when step_ptr == NULL */
-  const int* step_ptr; /* device-side step counter (CUDA-graph replay) or NULL */
+  const int* step_ptr; /* VQGanVAE.forward(img, return_loss=True) without the GAN / perceptual terms (use_vgg_and_gan=False): the reconstruction
+ * loss F.l1_loss (default) or F.mse_loss (l2_recon_loss=True) of vqgan_vae.py:340,502-512.  out[0] = mean |a-b| or
+ * mean (a-b)^2 over n fp32 elements; partials: nparts floats of scratch (two deterministic reduction stages). */
+int nuwa_recon_loss_f32(const float* a, const float* b, long long n, int l2, float* partials, int nparts, float* out,
+                        void* stream);
+/* device-side step counter (CUDA-graph replay) or NULL */
   int zero_grad;
 } nuwa_adamw_params;
 int nuwa_adamw_step(const nuwa_adamw_params* a, void* stream);

@@ -132,6 +132,7 @@ SIGNATURES = {
     "nuwa_struct_sizes_decode": [P(c_int)],
     "nuwa_sqnorm_f32": [c_void_p, c_ll, c_void_p, c_int, c_void_p, c_int, c_void_p],
     "nuwa_adamw_step": [P(AdamWParams), c_void_p],
+    "nuwa_recon_loss_f32": [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "nuwa_struct_sizes_optim": [P(c_int)],
     "nuwa_nchw_f32_to_nhwc_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "nuwa_nhwc_to_nchw_f32": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
@@ -143,6 +144,10 @@ SIGNATURES = {
     "nuwa_vq_argmax": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "nuwa_vq_argmax_tc_workspace": [c_int, c_int, c_int],
     "nuwa_vq_argmax_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                          ctypes.c_ulonglong, c_void_p],
+    "nuwa_split3_f32_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p],
+    "nuwa_linear_f32x3_workspace": [c_int, c_int],
+    "nuwa_linear_f32x3": [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                           ctypes.c_ulonglong, c_void_p],
     "nuwa_gather_rows": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "nuwa_conv1x1_nhwc_to_nchw": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
@@ -178,7 +183,7 @@ SIGNATURES = {
     "nuwa_attn3dna_bwd_first_key_finalize": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p],
     "nuwa_struct_sizes_bwd": [P(c_int)],
 }
-_RESTYPES = {"nuwa_strerror": ctypes.c_char_p, "nuwa_vq_argmax_tc_workspace": ctypes.c_ulonglong, "nuwa_gemm_prof_bytes": ctypes.c_double, "nuwa_launch_count": ctypes.c_ulonglong, "nuwa_struct_sizes": None,
+_RESTYPES = {"nuwa_strerror": ctypes.c_char_p, "nuwa_vq_argmax_tc_workspace": ctypes.c_ulonglong, "nuwa_linear_f32x3_workspace": ctypes.c_ulonglong, "nuwa_gemm_prof_bytes": ctypes.c_double, "nuwa_launch_count": ctypes.c_ulonglong, "nuwa_struct_sizes": None,
              "nuwa_gemm_prof_enable": None, "nuwa_struct_sizes_bwd": None, "nuwa_struct_sizes_decode": None, "nuwa_struct_sizes_optim": None}
 
 _lib = None

@@ -44,11 +44,8 @@ int nuwa_stable_ln(const float* a, const float* b2, const float* w, const float*
   return stable_ln(a, b2, w, bias, out_f32, out_bf16, rows, D, S(stream));
 }
 int nuwa_attn_sparse3dna(const nuwa_attn_params* p, void* vt_workspace, void* stream) {
+  (void)vt_workspace;  // kept in the signature for ABI stability (was the workspace of a removed kernel variant)
   if (!p) return NUWA_ERR_INVALID;
-  if (vt_workspace != nullptr) {
-    const int rc = attn_3dna_tc(*p, vt_workspace, S(stream));
-    if (rc != NUWA_ERR_INVALID) return rc;  // outside the tensor-core kernel's envelope -> generic kernel
-  }
   return attn_sparse3dna(*p, S(stream));
 }
 int nuwa_attn_sparse3dna_halo(const nuwa_attn_params* p, void* stream) {
@@ -100,6 +97,10 @@ int nuwa_decode_stack(const nuwa_decode_params* p, int cooperative, void* stream
 int nuwa_sqnorm_f32(const float* x, long long n, float* partials, int nparts, float* out, int accumulate, void* stream) {
   return sqnorm_f32(x, n, partials, nparts, out, accumulate, S(stream));
 }
+int nuwa_recon_loss_f32(const float* a, const float* b, long long n, int l2, float* partials, int nparts, float* out,
+                        void* stream) {
+  return recon_loss_f32(a, b, n, l2, partials, nparts, out, S(stream));
+}
 int nuwa_adamw_step(const nuwa_adamw_params* a, void* stream) { return a ? adamw_step(*a, S(stream)) : NUWA_ERR_INVALID; }
 void nuwa_struct_sizes_optim(int* out2) {
   out2[0] = (int)sizeof(nuwa_opt_chunk);
@@ -108,6 +109,14 @@ void nuwa_struct_sizes_optim(int* out2) {
 void nuwa_struct_sizes_decode(int* out2) {
   out2[0] = (int)sizeof(nuwa_decode_sub);
   out2[1] = (int)sizeof(nuwa_decode_params);
+}
+int nuwa_split3_f32_bf16(const float* x, long long ld, void* out, long long rows, int K, void* stream) {
+  return split3_f32_bf16(x, ld, out, rows, K, S(stream));
+}
+unsigned long long nuwa_linear_f32x3_workspace(int M, int K) { return linear_f32x3_workspace(M, K); }
+int nuwa_linear_f32x3(const float* x, long long ldx, const void* w3, int M, int N, int K, const float* bias, float* out,
+                      void* out_bf16, int ld_out, void* workspace, unsigned long long workspace_bytes, void* stream) {
+  return linear_f32x3(x, ldx, w3, M, N, K, bias, out, out_bf16, ld_out, workspace, (size_t)workspace_bytes, S(stream));
 }
 int nuwa_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, void* stream) {
   return nchw_f32_to_nhwc_bf16(in, out, B, C, H, W, S(stream));

@@ -58,7 +58,6 @@ double gemm_prof_bytes();
 // attention.cu
 int attn_sparse3dna(const AttnParams& p, cudaStream_t s);
 int attn_dense(const AttnParams& p, cudaStream_t s);
-int attn_3dna_tc(const AttnParams& p, void* vT_ws, cudaStream_t stream);  // attention_3dna_tc.cu
 int attn_3dna_halo(const AttnParams& p, cudaStream_t stream);           // attention_3dna_halo.cu
 int attn_dense_mma(const AttnParams& p, int nk, void* vT_ws, cudaStream_t stream);  // attention_mma.cu
 int attn_dense_x64(const AttnParams& p, int nk, cudaStream_t stream);                // attention_x64.cu
@@ -86,6 +85,8 @@ int decode_stack(const nuwa_decode_params& p, int cooperative, cudaStream_t stre
 // optim.cu
 int sqnorm_f32(const float* x, long long n, float* partials, int nparts, float* out, int accumulate, cudaStream_t stream);
 int adamw_step(const nuwa_adamw_params& a, cudaStream_t stream);
+int recon_loss_f32(const float* a, const float* b, long long n, int l2, float* partials, int nparts, float* out,
+                   cudaStream_t stream);
 // vae_ops.cu
 int nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, cudaStream_t stream);
 int nhwc_to_nchw_f32(const void* in, int in_is_bf16, float* out, int B, int C, int H, int W, cudaStream_t stream);
@@ -99,6 +100,10 @@ int vq_argmax(const float* x, const float* code, const float* code_sq, long long
 size_t vq_argmax_tc_workspace(int M, int Kc, int D);
 int vq_argmax_tc(const float* x, const float* code, const float* code_sq, const void* code_bf16, const float* emax,
                  long long* out, int M, int Kc, int D, int cosine, void* workspace, size_t ws_bytes, cudaStream_t stream);
+int split3_f32_bf16(const float* x, long long ld, void* out, long long rows, int K, cudaStream_t stream);
+size_t linear_f32x3_workspace(int M, int K);
+int linear_f32x3(const float* x, long long ldx, const void* w3, int M, int N, int K, const float* bias, float* out,
+                 void* out_bf16, int ld_out, void* workspace, size_t ws_bytes, cudaStream_t stream);
 int gather_rows(const float* table, const long long* idx, void* out_bf16, float* out_f32, long long M, int D,
                 cudaStream_t stream);
 int conv1x1_nhwc_to_nchw(const void* x, const float* w, const float* bias, float* out, int B, int HW, int C, int Cout,

@@ -69,6 +69,37 @@ int sqnorm_f32(const float* x, long long n, float* partials, int nparts, float* 
   return NUWA_OK;
 }
 
+// mean |a - b| (l1) or mean (a - b)^2 (l2) of two fp32 arrays: VQGanVAE.forward(return_loss=True) reconstruction loss
+// without the GAN / perceptual terms (vqgan_vae.py:340, :502-512).  Same two deterministic stages as sqnorm.
+__global__ void __launch_bounds__(OPT_THREADS) diff_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                    long long n, int l2, float* __restrict__ partials) {
+  __shared__ float red[OPT_THREADS / 32];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * OPT_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * OPT_THREADS) {
+    const float d = __ldg(a + i) - __ldg(b + i);
+    acc += l2 ? d * d : fabsf(d);
+  }
+  const float s = block_sum_256(acc, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(OPT_THREADS) mean_final_kernel(const float* __restrict__ partials, int nparts,
+                                                                  float inv_n, float* __restrict__ out) {
+  __shared__ float red[OPT_THREADS / 32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += OPT_THREADS) acc += partials[i];
+  const float s = block_sum_256(acc, red);
+  if (threadIdx.x == 0) out[0] = s * inv_n;
+}
+int recon_loss_f32(const float* a, const float* b, long long n, int l2, float* partials, int nparts, float* out,
+                   cudaStream_t stream) {
+  if (a == nullptr || b == nullptr || partials == nullptr || out == nullptr || n <= 0 || nparts <= 0) return NUWA_ERR_INVALID;
+  diff_partial_kernel<<<nparts, OPT_THREADS, 0, stream>>>(a, b, n, l2, partials);
+  NUWA_CHECK_LAUNCH();
+  mean_final_kernel<<<1, OPT_THREADS, 0, stream>>>(partials, nparts, 1.0f / (float)n, out);
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+
 // one CTA per chunk; a chunk never crosses a parameter boundary
 __global__ void __launch_bounds__(OPT_THREADS) adamw_kernel(const nuwa_adamw_params a) {
   const nuwa_opt_chunk ck = a.chunks[blockIdx.x];

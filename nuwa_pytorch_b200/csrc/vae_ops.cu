@@ -548,7 +548,8 @@ vq_refine_kernel(const float* __restrict__ x, const float* __restrict__ code, co
       if (sc > best) { best = sc; besti = jj; }  // candidates arrive in increasing index order: first maximum wins
     }
   }
-  if (lane == 0) out[m] = besti;
+  // a row holding NaN / Inf passes no threshold test: fall back to index 0 like the fp32 kernel (never out of range)
+  if (lane == 0) out[m] = besti < Kc ? besti : 0;
 }
 
 // workspace: M*D bf16 (token rows, normalised for cosine) followed by M*Kc fp32 (scores), 16-byte aligned.
@@ -577,6 +578,75 @@ int vq_argmax_tc(const float* x, const float* code, const float* code_sq, const 
   else if (D <= 512) vq_refine_kernel<4><<<grid, 256, 0, stream>>>(x, code, code_sq, scores, out, M, Kc, D, cosine, emax);
   else vq_refine_kernel<8><<<grid, 256, 0, stream>>>(x, code, code_sq, scores, out, M, Kc, D, cosine, emax);
   NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32-faithful linear on the tensor cores: VectorQuantize.project_in (vqgan_vae.py:368-378) feeds the
+// codebook arg-max, whose token ids must be the fp32 reference's ids, so its operands may not be rounded
+// to bf16.  Every fp32 value is split EXACTLY into three bf16 terms (8 + 8 + 8 mantissa bits),
+//   a = a0 + a1 + a2,   a0 = bf16(a), a1 = bf16(a - a0), a2 = bf16(a - a0 - a1),
+// and  A W^T = sum over (i + j <= 2) A_i W_j^T  runs as six tcgen05 GEMMs with fp32 accumulation, smallest
+// terms first (dropped terms are below 2^-24 relative).  Layout: [rows][3*K] = [x0 | x1 | x2].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+split3_kernel(const float* __restrict__ x, long long ld, bf16* __restrict__ out, long long rows, int K) {
+  const long long total = rows * (long long)(K / 4);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (K / 4);
+    const int c = (int)(i - r * (K / 4)) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ld + c);
+    const float a[4] = {v.x, v.y, v.z, v.w};
+    uint32_t w[3][2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float p0[2], p1[2], p2[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float t = a[2 * h + e];
+        p0[e] = __bfloat162float(__float2bfloat16(t));
+        const float r1 = t - p0[e];                       // exact (Sterbenz-style: p0 holds the leading bits of t)
+        p1[e] = __bfloat162float(__float2bfloat16(r1));
+        p2[e] = r1 - p1[e];                               // exact, <= 8 significant bits left
+      }
+      w[0][h] = pack_bf16x2(p0[0], p0[1]);
+      w[1][h] = pack_bf16x2(p1[0], p1[1]);
+      w[2][h] = pack_bf16x2(p2[0], p2[1]);
+    }
+    bf16* o = out + r * 3LL * K + c;
+    *reinterpret_cast<uint2*>(o) = make_uint2(w[0][0], w[0][1]);
+    *reinterpret_cast<uint2*>(o + K) = make_uint2(w[1][0], w[1][1]);
+    *reinterpret_cast<uint2*>(o + 2 * K) = make_uint2(w[2][0], w[2][1]);
+  }
+}
+int split3_f32_bf16(const float* x, long long ld, void* out, long long rows, int K, cudaStream_t stream) {
+  if (rows <= 0 || K <= 0 || (K % 4) || (ld % 4) || (reinterpret_cast<uintptr_t>(x) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 7))
+    return NUWA_ERR_INVALID;
+  const long long g = (rows * (K / 4) + 255) / 256;
+  split3_kernel<<<(int)(g > 148LL * 16 ? 148LL * 16 : g), 256, 0, stream>>>(x, ld, reinterpret_cast<bf16*>(out), rows, K);
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+size_t linear_f32x3_workspace(int M, int K) { return (size_t)M * 3 * K * 2; }
+// out[M,N] fp32 = x[M,K] fp32 @ W^T + bias, W given pre-split as w3 [N][3K] bf16 (split3_f32_bf16 of the fp32 weight)
+int linear_f32x3(const float* x, long long ldx, const void* w3, int M, int N, int K, const float* bias, float* out,
+                 void* out_bf16, int ld_out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 8) || out == nullptr || workspace == nullptr) return NUWA_ERR_INVALID;
+  if (ws_bytes < linear_f32x3_workspace(M, K)) return NUWA_ERR_WORKSPACE;
+  int rc = split3_f32_bf16(x, ldx, workspace, M, K, stream);
+  if (rc != NUWA_OK) return rc;
+  const bf16* xs = reinterpret_cast<const bf16*>(workspace);
+  const bf16* ws = reinterpret_cast<const bf16*>(w3);
+  // (i, j): smallest products first; each launch adds the previous partial sum as its fp32 residual (same element,
+  // same thread: in place), the last one adds the bias
+  static const int order[6][2] = {{2, 0}, {1, 1}, {0, 2}, {1, 0}, {0, 1}, {0, 0}};
+  for (int t = 0; t < 6; ++t) {
+    const int i = order[t][0], j = order[t][1];
+    rc = gemm_bf16(xs + (size_t)i * K, 3 * K, ws + (size_t)j * K, 3 * K, M, N, K, t == 5 ? bias : nullptr,
+                   t == 0 ? nullptr : out, ld_out, out, t == 5 ? out_bf16 : nullptr, ld_out, ACT_NONE, 0, stream);
+    if (rc != NUWA_OK) return rc;
+  }
   return NUWA_OK;
 }
 

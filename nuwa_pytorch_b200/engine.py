@@ -27,50 +27,82 @@ def _bf16(t):
 
 
 class SubBlock:
-    """Packed weights + static geometry of one SandwichNorm-wrapped sub-block."""
+    """Packed weights + static geometry of one SandwichNorm-wrapped sub-block.
+
+    fp32 tensors (LayerNorm weights, biases, talking heads, null k/v) alias the live parameters.  The bf16 GEMM
+    operands are COPIES; each is registered with the function that rebuilds it, so `refresh()` can re-derive every copy
+    IN PLACE after an optimizer step: addresses stay fixed for the lifetime of the parameters, which is what lets a
+    captured CUDA graph (graphs.GraphedTrainStep) keep replaying across weight updates."""
 
     def __init__(self, kind, sandwich, inner_mod, shift, read, write, **geom):
         self.kind, self.shift, self.read, self.write = kind, shift, read, write
         self.sandwich, self.mod = sandwich, inner_mod  # parameter owners (train.py maps gradients back to them)
-        self.pre =(_f32(sandwich.prenorm.weight), _f32(sandwich.prenorm.bias))
+        self.pre = (_f32(sandwich.prenorm.weight), _f32(sandwich.prenorm.bias))
         self.post = (_f32(sandwich.postnorm.weight), _f32(sandwich.postnorm.bias))
         self.__dict__.update(geom)
+        self._builders = []
+        self._bw = None
         m = inner_mod
         if kind in ('3dna', 'self'):
             self.H = m.heads
             self.inner = m.to_q.weight.shape[0]
             self.dh = self.inner // self.H
-            self.w_qkv = _bf16(torch.cat([m.to_q.weight, m.to_kv.weight], dim=0))
-            self.w_out = _bf16(m.to_out.weight)
+            self._packed('w_qkv', lambda: _bf16(torch.cat([m.to_q.weight, m.to_kv.weight], dim=0)))
+            self._packed('w_out', lambda: _bf16(m.to_out.weight))
             self.b_out = _f32(m.to_out.bias) if m.to_out.bias is not None else None
             self.talk = _f32(m.talking_heads.weight.reshape(self.H, self.H))
         if kind in ('cross', 'x2dna'):
             self.H = m.heads
             self.inner = m.to_q.weight.shape[0]
             self.dh = self.inner // self.H
-            self.w_q, self.w_kv, self.w_out = _bf16(m.to_q.weight), _bf16(m.to_kv.weight), _bf16(m.to_out.weight)
+            self._packed('w_q', lambda: _bf16(m.to_q.weight))
+            self._packed('w_kv', lambda: _bf16(m.to_kv.weight))
+            self._packed('w_out', lambda: _bf16(m.to_out.weight))
             self.talk = _f32(m.talking_heads.weight.reshape(self.H, self.H))
         if kind in ('self', 'cross', 'x2dna'):
             self.null_k, self.null_v = _f32(m.null_k.reshape(-1)), _f32(m.null_v.reshape(-1))
         if kind == 'ff':
             w1, w2 = m.net[0].weight, m.net[3].weight
             self.ff_inner = w2.shape[1]
-            self.w1 = _bf16(ops.pack_pairs(w1.detach().float()))            # (2*ip, D) pair packed
+            self._packed('w1', lambda: _bf16(ops.pack_pairs(w1.detach().float())))   # (2*ip, D) pair packed
             ip = self.w1.shape[0] // 2
-            w2p = torch.zeros(w2.shape[0], ip, dtype=torch.float32, device=w2.device)
-            w2p[:, :self.ff_inner] = w2.detach().float()
-            self.w2 = _bf16(w2p)                                             # (D, ip), zero padded K
+
+            def build_w2():
+                w2p = torch.zeros(w2.shape[0], ip, dtype=torch.float32, device=w2.device)
+                w2p[:, :self.ff_inner] = w2.detach().float()
+                return _bf16(w2p)                                                     # (D, ip), zero padded K
+            self._packed('w2', build_w2)
+
+    def _packed(self, name, build):
+        setattr(self, name, build())
+        self._builders.append((name, build))
+
+    def refresh(self):
+        """Re-derive every bf16 copy from the fp32 masters, in place (capture safe: device copies only)."""
+        for name, build in self._builders:
+            getattr(self, name).copy_(build())
+        if self._bw is not None:
+            for name, build in self._bw_builders:
+                self._bw[name].copy_(build())
 
 
 class StackPack:
-    """Everything run_stack needs, built once per weight version (see pack_stack)."""
+    """Everything run_stack needs, built once per parameter allocation (see pack_stack)."""
 
     def __init__(self, subs, norm_w, norm_b, reversible, dim):
         self.subs, self.norm_w, self.norm_b, self.reversible, self.dim = subs, norm_w, norm_b, reversible, dim
 
+    def refresh(self):
+        for s in self.subs:
+            s.refresh()
+
 
 def _signature(module):
     return (_lib.WEIGHTS_EPOCH[0],) + tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
+def _addresses(sig):
+    return tuple(a for a, _ in sig[1:])
 
 
 def pack_stack(stack):
@@ -78,6 +110,13 @@ def pack_stack(stack):
     sig = _signature(stack)
     cached = getattr(stack, '_nuwa_pack', None)
     if cached is not None and cached[0] == sig:
+        return cached[1]
+    if cached is not None and _addresses(cached[0]) == _addresses(sig):
+        # same parameter storage, new values (optimizer step): refresh the bf16 copies in place -- a captured CUDA
+        # graph holding their addresses stays valid and sees the new weights
+        with torch.no_grad():
+            cached[1].refresh()
+        stack._nuwa_pack = (sig, cached[1])
         return cached[1]
     dev = next(stack.parameters()).device
     if dev.type != 'cuda':

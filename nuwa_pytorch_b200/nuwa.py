@@ -326,9 +326,26 @@ class _VideoDecoderMixin:
     def _logits_weight(self):
         w = self.to_logits.weight
         key = (w.data_ptr(), w._version, ops._lib.WEIGHTS_EPOCH[0])
-        if getattr(self, '_logits_cache', (None,))[0] != key:
+        cache = getattr(self, '_logits_cache', None)
+        if cache is None or cache[0][0] != key[0] or cache[1].device != w.device:
             self._logits_cache = (key, w.detach().to(torch.bfloat16).contiguous())
+        elif cache[0] != key:  # same storage, new values: refresh the bf16 copy in place (address stays graph-stable)
+            with torch.no_grad():
+                cache[1].copy_(w.detach())
+            self._logits_cache = (key, cache[1])
         return self._logits_cache[1]
+
+    @torch.no_grad()
+    def refresh_packed_weights(self):
+        """Re-derive every packed bf16 GEMM operand (stack weights, their dgrad transposes, the logits weight) from
+        the fp32 parameters IN PLACE.  Device copies only, so it can be captured at the head of a CUDA graph
+        (graphs.GraphedTrainStep): a replayed step then always computes with the current weights."""
+        for name in ('text_transformer', 'sketch_transformer', 'video_transformer'):
+            stack = getattr(self, name, None)
+            if stack is not None:
+                engine.pack_stack(stack).refresh()
+        w = self._logits_weight()
+        w.copy_(self.to_logits.weight.detach())
 
     def _decoder_logits(self, frame_indices, context, return_loss):
         """Teacher-forced pass: logits for every position, optionally the mean cross entropy (:1937-1964)."""

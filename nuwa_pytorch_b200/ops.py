@@ -387,6 +387,30 @@ def vq_argmax(x, code, code_sq=None, cosine=True, code16=None, emax=None, varian
     return out
 
 
+def split3(x):
+    """fp32 (rows, K) -> bf16 (rows, 3K) = [x0 | x1 | x2] with x == x0 + x1 + x2 exactly (see nuwa_split3_f32_bf16)."""
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, K = x.shape
+    out = torch.empty(rows, 3 * K, dtype=torch.bfloat16, device=x.device)
+    check(lib().nuwa_split3_f32_bf16(ptr(x), x.stride(0), ptr(out), rows, K, stream()), "nuwa_split3_f32_bf16")
+    return out
+
+
+def linear_f32x3(x, w3, bias=None, also_bf16=False):
+    """fp32-faithful x @ W.T + bias on the tensor cores; w3 = split3(W fp32 (N, K)).  x: fp32 (M, K)."""
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1 and w3.dtype == torch.bfloat16
+    M, K = x.shape
+    N = w3.shape[0]
+    assert w3.shape[1] == 3 * K
+    out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    nbytes = int(lib().nuwa_linear_f32x3_workspace(M, K))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    o16 = torch.empty(M, N, dtype=torch.bfloat16, device=x.device) if also_bf16 else None
+    check(lib().nuwa_linear_f32x3(ptr(x), x.stride(0), ptr(w3), M, N, K, ptr(bias), ptr(out), ptr(o16), N, ptr(ws), nbytes,
+                                  stream()), "nuwa_linear_f32x3")
+    return (out, o16) if also_bf16 else out
+
+
 def gather_rows(table, idx, want_bf16=True, want_f32=False):
     M, D = idx.numel(), table.shape[1]
     o16 = torch.empty(M, D, dtype=torch.bfloat16, device=table.device) if want_bf16 else None
@@ -404,4 +428,16 @@ def conv1x1_to_nchw(x, w, b):
     out = torch.empty(B, cout, H, W, dtype=torch.float32, device=x.device)
     check(lib().nuwa_conv1x1_nhwc_to_nchw(ptr(x), ptr(w), ptr(b), ptr(out), B, H * W, C, cout, stream()),
           "nuwa_conv1x1_nhwc_to_nchw")
+    return out
+
+
+def recon_loss(a, b, l2=False):
+    """mean |a-b| (F.l1_loss) or mean (a-b)^2 (F.mse_loss) of two fp32 tensors -> 0-d fp32 device tensor."""
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape == b.shape
+    a, b = a.contiguous(), b.contiguous()
+    nparts = 4 * 148
+    partials = torch.empty(nparts, dtype=torch.float32, device=a.device)
+    out = torch.empty((), dtype=torch.float32, device=a.device)
+    check(lib().nuwa_recon_loss_f32(ptr(a), ptr(b), a.numel(), int(bool(l2)), ptr(partials), nparts, ptr(out), stream()),
+          "nuwa_recon_loss_f32")
     return out

@@ -63,31 +63,45 @@ class FusedAdamW:
 
     # ---- gradient buffer -----------------------------------------------------------------------
     def _flat_grads(self):
-        """The flat buffer the parameters' .grad tensors alias (train.GradStore layout) -- or, when the gradients
-        were produced some other way, a gathered copy."""
+        """(flat, aliased): the flat buffer the parameters' .grad tensors alias (train.GradStore layout, aliased=True) --
+        or, when the gradients were produced some other way, a gathered copy (aliased=False).
+
+        Aliasing is detected by ADDRESS: autograd's AccumulateGrad stores `grad.detach()`, which drops `._base`, so the
+        views handed out by GradStore arrive here as base-less tensors that still point into the flat buffer."""
         p0 = self.params[0]
         if p0.grad is None:
             raise _lib.NuwaB200Error('FusedAdamW.step(): no gradients (call loss.backward() first)')
-        base = p0.grad._base if p0.grad._base is not None else p0.grad
-        ok = base.dtype == torch.float32 and base.dim() == 1 and base.numel() == self.layout.flat.numel()
+        g0 = p0.grad
+        n = self.layout.flat.numel()
+        ok = g0.dtype == torch.float32 and g0.is_cuda
         if ok:
-            b0 = base.data_ptr()
-            for p, off in zip(self.params, self.layout.offsets):
-                if p.grad is None or p.grad.data_ptr() != b0 + 4 * off or not p.grad.is_contiguous():
-                    ok = False
-                    break
+            st = g0.untyped_storage()
+            b0 = g0.data_ptr()
+            ok = (b0 - st.data_ptr()) % 4 == 0 and st.data_ptr() + st.nbytes() >= b0 + 4 * n
+            if ok:
+                for p, off in zip(self.params, self.layout.offsets):
+                    g = p.grad
+                    if (g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.data_ptr() != b0 + 4 * off
+                            or g.untyped_storage().data_ptr() != st.data_ptr()):
+                        ok = False
+                        break
         if ok:
-            return base
+            flat = torch.empty(0, dtype=torch.float32, device=g0.device).set_(st, (b0 - st.data_ptr()) // 4, (n,), (1,))
+            return flat, True
         flat = self.layout.flat
         flat.zero_()
         for p, off in zip(self.params, self.layout.offsets):
             if p.grad is not None:
                 flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
-        return flat
+        return flat, False
 
     @torch.no_grad()
     def step(self, grads_flat=None, grad_scale=1.0, zero_grad=True):
-        g = grads_flat if grads_flat is not None else self._flat_grads()
+        aliased = True
+        if grads_flat is not None:
+            g = grads_flat
+        else:
+            g, aliased = self._flat_grads()
         assert g.dtype == torch.float32 and g.numel() == self.master.numel() and g.is_contiguous()
         check(lib().nuwa_sqnorm_f32(ptr(g), g.numel(), ptr(self.partials), self.nparts, ptr(self.sqnorm), 0, stream()),
               "nuwa_sqnorm_f32")
@@ -100,8 +114,23 @@ class FusedAdamW:
         a.step, a.step_ptr, a.zero_grad = 0, ptr(self.step_dev), int(bool(zero_grad))
         check(lib().nuwa_adamw_step(ctypes.byref(a), stream()), "nuwa_adamw_step")
         check(lib().nuwa_step_increment(ptr(self.step_dev), stream()), "nuwa_step_increment")
-        _lib.WEIGHTS_EPOCH[0] += 1                    # the weights changed: packed bf16 copies are rebuilt lazily
+        _lib.WEIGHTS_EPOCH[0] += 1                    # the weights changed: packed bf16 copies are refreshed lazily
+        if zero_grad and not aliased:
+            # the kernel zeroed the gathered scratch copy, not the tensors autograd accumulates into
+            for p in self.params:
+                if p.grad is not None:
+                    p.grad.zero_()
         return self.sqnorm.sqrt() * grad_scale
+
+    # ---- state (checkpointing, graph warm-up) --------------------------------------------------
+    def state_snapshot(self):
+        return tuple(t.clone() for t in (self.master, self.exp_avg, self.exp_avg_sq, self.step_dev))
+
+    def state_restore(self, snap):
+        with torch.no_grad():
+            for dst, src in zip((self.master, self.exp_avg, self.exp_avg_sq, self.step_dev), snap):
+                dst.copy_(src)
+        _lib.WEIGHTS_EPOCH[0] += 1
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:

@@ -54,16 +54,15 @@ class GradStore:
 
 
 def _bw(s):
-    """Transposed bf16 weight copies for the dgrad GEMMs (built once per weight version, cached on the SubBlock)."""
+    """Transposed bf16 weight copies for the dgrad GEMMs (built once per parameter allocation, cached on the SubBlock and
+    refreshed in place by SubBlock.refresh() whenever the weights change)."""
     if getattr(s, '_bw', None) is None:
         t = ops_bwd.transpose
-        bw = {}
-        if s.kind in ('3dna', 'self'):
-            bw['w_qkv_t'], bw['w_out_t'] = t(s.w_qkv).contiguous(), t(s.w_out).contiguous()
-        elif s.kind in ('cross', 'x2dna'):
-            bw['w_q_t'], bw['w_kv_t'], bw['w_out_t'] = t(s.w_q).contiguous(), t(s.w_kv).contiguous(), t(s.w_out).contiguous()
-        elif s.kind == 'ff':
-            bw['w1_t'], bw['w2_t'] = t(s.w1).contiguous(), t(s.w2).contiguous()
+        names = {'3dna': ('w_qkv', 'w_out'), 'self': ('w_qkv', 'w_out'), 'cross': ('w_q', 'w_kv', 'w_out'),
+                 'x2dna': ('w_q', 'w_kv', 'w_out'), 'ff': ('w1', 'w2')}[s.kind]
+        builders = [(n + '_t', (lambda n=n: t(getattr(s, n)).contiguous())) for n in names]
+        bw = {name: build() for name, build in builders}
+        if s.kind == 'ff':
             inner, ip = s.ff_inner, s.w1.shape[0] // 2
             # packed row r of w1 -> row of net[0].weight (value rows [0, inner), gate rows [inner, 2*inner)), -1 = padding
             r = torch.arange(2 * ip)
@@ -72,6 +71,7 @@ def _bw(s):
             src = torch.where(j < 16, col, col + inner)
             src = torch.where(col < inner, src, torch.full_like(src, -1))
             bw['w1_map'] = src.to(torch.int32).to(s.w1.device)
+        s._bw_builders = builders
         s._bw = bw
     return s._bw
 

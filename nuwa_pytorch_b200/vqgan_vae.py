@@ -279,8 +279,12 @@ class VQGanVAE(nn.Module):
         vq['code16'] = vq['code'].to(torch.bfloat16).contiguous()
         vq['emax'] = vq['code'].norm(dim=-1).max().reshape(1).float().contiguous()  # device scalar: no host sync
         if isinstance(self.vq.project_in, nn.Linear):
-            vq['pin'] = lin_pack(self.vq.project_in.weight, self.vq.project_in.bias)
-            vq['pout'] = lin_pack(self.vq.project_out.weight, self.vq.project_out.bias)
+            # project_in feeds the arg-max: fp32-faithful (three exact bf16 terms per fp32 weight, ops.linear_f32x3),
+            # so the token ids are those of the fp32 reference for the same pre-VQ map
+            pw = self.vq.project_in.weight.detach().float().contiguous()
+            vq['pin'] = dict(w3=ops.split3(pw), b=self.vq.project_in.bias.detach().float().contiguous())
+            po = self.vq.project_out.weight.detach().float().contiguous()
+            vq['pout'] = dict(w3=ops.split3(po), b=self.vq.project_out.bias.detach().float().contiguous())
         pk['enc'], pk['dec'], pk['vq'] = enc, dec, vq
         self._packed, self._packed_sig = pk, sig
         return pk
@@ -345,12 +349,11 @@ class VQGanVAE(nn.Module):
         pk = self._pack()['vq']
         B, H, W, C = x16.shape
         M = B * H * W
-        flat = ops.gemm(x16.view(M, C), pk['pin']['w'], bias=pk['pin']['b'], out_dtype=torch.float32) if 'pin' in pk \
-            else x32.view(M, C)
+        flat = ops.linear_f32x3(x32.view(M, C), pk['pin']['w3'], pk['pin']['b']) if 'pin' in pk else x32.view(M, C)
         ind = ops.vq_argmax(flat, pk['code'], pk['code_sq'], cosine=pk['cosine'], code16=pk['code16'], emax=pk['emax'])
         if 'pout' in pk:
-            q16 = ops.gather_rows(pk['embed'], ind)
-            q32, q16 = ops.gemm(q16, pk['pout']['w'], bias=pk['pout']['b'], out_dtype=torch.float32, also_bf16=True)
+            e32 = ops.gather_rows(pk['embed'], ind, want_bf16=False, want_f32=True)
+            q32, q16 = ops.linear_f32x3(e32, pk['pout']['w3'], pk['pout']['b'], also_bf16=True)
         else:
             q16, q32 = ops.gather_rows(pk['embed'], ind, want_bf16=True, want_f32=True)
         return q16.view(B, H, W, -1), q32.view(B, H, W, -1), ind.view(B, H, W)
@@ -415,8 +418,7 @@ class VQGanVAE(nn.Module):
         x16, x32 = self._encode_fmap_nhwc(images)
         pk = self._pack()['vq']
         B, H, W, C = x16.shape
-        flat = ops.gemm(x16.view(-1, C), pk['pin']['w'], bias=pk['pin']['b'], out_dtype=torch.float32) if 'pin' in pk \
-            else x32.view(-1, C)
+        flat = ops.linear_f32x3(x32.view(-1, C), pk['pin']['w3'], pk['pin']['b']) if 'pin' in pk else x32.view(-1, C)
         ind = ops.vq_argmax(flat, pk['code'], pk['code_sq'], cosine=pk['cosine'], code16=pk['code16'], emax=pk['emax'])  # project_out is not needed here
         return ind.view(b, f, H, W)
 
@@ -424,11 +426,19 @@ class VQGanVAE(nn.Module):
         batch, channels, height, width = img.shape
         assert height == self.image_size and width == self.image_size, 'height and width of input image must be equal to {self.image_size}'
         assert channels == self.channels, 'number of channels on image or sketch is not equal to the channels set on this VQGanVAE'
-        if return_loss or return_discr_loss:
-            raise NotImplementedError('VQGanVAE losses (vqgan_vae.py:479-548) belong to the VAE training path, which is '
-                                      'outside the B200 hot path')
         self._check_mode()
         with torch.no_grad():
             x16, x32 = self._encode_fmap_nhwc(img)
             q16, q32, _ = self._quantize_nhwc(x16, x32)
-            return self._decode_nhwc(q16, q32)
+            fmap = self._decode_nhwc(q16, q32)
+        if not return_loss and not return_discr_loss:
+            return fmap
+        assert return_loss ^ return_discr_loss, 'you should either return autoencoder loss or discriminator loss, but not both'
+        if return_discr_loss:
+            assert self.discr is not None, 'discriminator must exist to train it'
+        # reconstruction loss; without VGG / GAN the reference returns it as is (vqgan_vae.py:502-512) -- forward value
+        # only here (the VAE backward / GAN path is outside the B200 hot path, _check_mode() rejects grad mode)
+        recon_loss = ops.recon_loss(fmap, img.float(), l2=self.l2_recon_loss)
+        if return_recons:
+            return recon_loss, fmap
+        return recon_loss

@@ -54,3 +54,25 @@ def sketch_spec_from_kwargs(kw, vae_kw):
 
 def synth(fix):
     return synth_state_dict(fix['manifest'], fix['seed'])
+
+
+def assert_ids_equal_up_to_fp32_ties(got, want, x, code, cosine, tie=2e-6):
+    """VQ token ids must be EQUAL to the fp32 reference arg-max.  The only admissible difference is an fp32 tie: two
+    codes whose exact (fp64) scores differ by less than `tie` relative -- below what fp32 summation order can resolve, on
+    the CPU reference as much as on the GPU.  Every flip is printed with its fp64 margin; returns the flip count."""
+    import torch.nn.functional as F
+    got, want = got.reshape(-1).cpu(), want.reshape(-1).cpu()
+    flips = (got != want).nonzero().reshape(-1).tolist()
+    for m in flips:
+        xr, cg, cw = x[m].double(), code[got[m]].double(), code[want[m]].double()
+        if cosine:
+            xr = F.normalize(xr, dim=-1)
+            sg, sw = xr @ F.normalize(cg, dim=-1), xr @ F.normalize(cw, dim=-1)
+            scale = 1.0
+        else:
+            sg, sw = -(xr - cg).pow(2).sum(), -(xr - cw).pow(2).sum()
+            scale = float(xr.pow(2).sum() + cw.pow(2).sum())
+        margin = abs(float(sg - sw)) / scale
+        print(f"    id flip at token {m}: got {int(got[m])} want {int(want[m])}, fp64 score margin {margin:.2e}")
+        assert margin < tie, f"token {m}: ids differ ({int(got[m])} vs {int(want[m])}) with a decisive fp64 margin {margin:.3e}"
+    return len(flips)

@@ -36,7 +36,15 @@ def test_reader_and_collate_match_reference():
     text, video = ds[3]
     assert video.dtype == torch.int64 and video.shape == (48,)
     assert int(video.sum()) == meta["item3_video_sum"] and video[:8].tolist() == meta["item3_first8"]
-    assert text.tolist() == [6, 7]  # identity_digits: the label bytes (the reference's BPE tokenizer is out of scope)
+    # default encoder: digit + 1 (id 0 is NUWA's pad id and would be masked out of the conditioning -- ADVICE r1);
+    # the reference's BPE tokenizer is out of scope and can be passed as text_encode
+    assert text.tolist() == [7, 8]
+    assert all(int(t) != 0 for i in range(len(ds)) for t in ds[i][0])
+    bad = VideoIndicesDataset(videos_memmap_path=os.path.join(G, "video_indices_small.bin"),
+                              text_memmap_path=os.path.join(G, "video_indices_small_text.bin"), vae=vae, num_videos=5, num_frames=3,
+                              text_encode=lambda lab: [int(d) for d in lab])
+    with pytest.raises(AssertionError, match='padding'):
+        [bad[i] for i in range(len(bad))]   # some label holds a 0 digit -> id 0 -> rejected
     ds2 = VideoIndicesDataset(videos_memmap_path=os.path.join(G, "video_indices_small.bin"),
                               text_memmap_path=os.path.join(G, "video_indices_small_text.bin"), vae=vae, num_videos=5, num_frames=3,
                               text_encode=lambda lab: [49406] + [100 + d for d in lab] + [49407])
