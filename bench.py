@@ -123,25 +123,107 @@ def pick_cpu_threads(sd):
 def cpu_state_dict_vae(seed=0):
     """Random-init weights of the cfg-2 VAE, generated on the CPU shape-by-shape (oracle/synth.py policy)."""
     from nuwa_pytorch_b200.vqgan_vae import VQGanVAE
-    from oracle.synth import manifest_of, synth_state_dict
+    from oracle.synth import synth_state_dict
     with torch.device("meta"):
         vae = VQGanVAE(**VAE_KW)
     man = [(k, tuple(v.shape)) for k, v in vae.state_dict().items() if v.dtype == torch.float32]
     return synth_state_dict(man, seed)
 
 
+def cpu_state_dict_nuwa(seed=0, **over):
+    """Random-init weights of the cfg-3 / cfg-4 NUWA (decoder side only matters), CPU, oracle/synth.py policy."""
+    from nuwa_pytorch_b200 import NUWA, VQGanVAE
+    from oracle.synth import manifest_of, synth_state_dict
+    m = NUWA(vae=VQGanVAE(**DEC_VAE_KW), **{**DEC_KW, **over})  # CPU container (the constructor deep-copies its VAE)
+    man = [(k, shape) for k, shape in manifest_of(m.state_dict()) if not k.startswith("vae.")]
+    del m
+    return synth_state_dict(man, seed)
+
+
+def nuwa_oracle_spec(**over):
+    from oracle import nuwa_oracle as O
+    kw = {**DEC_KW, **over}
+    return O.NUWASpec(kw["dim"], 16, kw["max_video_frames"], 8192, dec_depth=kw["dec_depth"], dec_heads=kw["dec_heads"],
+                      dec_reversible=kw.get("dec_reversible", False), enc_reversible=True,
+                      kernel=kw["sparse_3dna_kernel_size"], dilation=kw["sparse_3dna_dilation"])
+
+
+def cpu_decoder_train_tokens_per_s():
+    """Reference algorithm (oracle port, PyTorch CPU fp32 autograd) on BASELINE configs[2] at B=1 (same per-sample shape:
+    256 text tokens, 2560 video tokens, 12 layers): loss + loss.backward(), one pass.  SURVEY 8(d): the full B=8 step
+    needs ~80 GB of RSS and minutes, so the per-unit rate at B=1 is the reported baseline."""
+    from oracle import nuwa_oracle as O
+    sd = cpu_state_dict_nuwa()
+    for v in sd.values():
+        v.requires_grad_(True)
+    spec = nuwa_oracle_spec()
+    g = torch.Generator().manual_seed(100)
+    text = torch.randint(1, 49408, (1, 256), generator=g)
+    video = torch.randint(0, 8192, (1, 2560), generator=g)
+    t0 = time.perf_counter()
+    _, loss = O.nuwa_logits(text, video, sd, spec)
+    t_f = time.perf_counter() - t0
+    loss.backward()
+    dt = time.perf_counter() - t0
+    return 2560 / dt, dt, 2560 / t_f, t_f
+
+
+def cpu_generate_tokens_per_s(batch=1, prefixes=(1, 129, 257)):
+    """Reference algorithm of generate() on BASELINE configs[3] (depth-64 reversible decoder): the reference recomputes
+    the whole prefix every step and runs two guidance sweeps (nuwa_pytorch.py:1870-1908).  SURVEY 8(d) method: time single
+    loop iterations at a few prefix lengths, fit step(t) = a + b t (every layer is window / 257-key attention + per-token
+    GEMMs, so the cost is linear in the prefix length) and integrate over t = 1..1280."""
+    from oracle import nuwa_oracle as O
+    sd = cpu_state_dict_nuwa(dec_depth=64, dec_reversible=True)
+    spec = nuwa_oracle_spec(dec_depth=64, dec_reversible=True)
+    g = torch.Generator().manual_seed(200)
+    text = torch.randint(1, 49408, (batch, 256), generator=g)
+    seq = torch.randint(0, 8192, (batch, max(prefixes)), generator=g)
+    pts = []
+    with torch.no_grad():
+        temb, tmask = O.nuwa_embed_text(text, sd, spec)
+        for t in prefixes:
+            t0 = time.perf_counter()
+            O.nuwa_generate_step_logits(temb, tmask, seq[:, :t - 1], sd, spec, 2.)
+            pts.append((t, time.perf_counter() - t0))
+    n = len(pts)
+    mx, my = sum(p[0] for p in pts) / n, sum(p[1] for p in pts) / n
+    b = sum((p[0] - mx) * (p[1] - my) for p in pts) / sum((p[0] - mx) ** 2 for p in pts)
+    a = my - b * mx
+    total = sum(a + b * t for t in range(1, 1281))
+    return batch * 1280 / total, pts, total
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    host_cores = os.cpu_count() or 1
     sd = cpu_state_dict_vae()
-    frames = 1
+    frames = 2  # BASELINE.md: cfg 2 at B=2 on the CPU (B=64 would take ~10 min per pass)
     cores = pick_cpu_threads(sd)  # untimed calibration pass doubles as the warm-up
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_vae_frames_per_s(sd, frames)
     dt = time.perf_counter() - t0
     fps = args.steps * frames / dt
+    del sd
+    decoder = generate = None
+    if not args.skip_decoder:
+        tps, tdt, tps_f, tdt_f = cpu_decoder_train_tokens_per_s()
+        decoder = dict(metric="3DNA decoder video-tokens/sec, forward loss + backward", value=round(tps, 2), unit="tokens/s",
+                       forward_only=dict(value=round(tps_f, 2), unit="tokens/s", seconds=round(tdt_f, 1)),
+                       cpu_baseline=dict(value=round(tps, 2), unit="tokens/s", cores=cores, host_cores=host_cores, kind="port",
+                                         sample=f"BASELINE configs[2] at B=1 (2560 video tokens, 256 text tokens, 12 layers), one "
+                                                f"forward+backward pass ({tdt:.1f} s), PyTorch CPU fp32 autograd through the oracle"))
+    if not args.skip_generate:
+        gps, pts, total = cpu_generate_tokens_per_s()
+        generate = dict(metric="generate(): sampled video-tokens/sec (AR loop)", tokens_per_s=round(gps, 4), unit="tokens/s",
+                        cpu_baseline=dict(value=round(gps, 4), unit="tokens/s", cores=cores, host_cores=host_cores, kind="port",
+                                          sample="BASELINE configs[3] (depth-64 reversible), B=1: single loop iterations (full "
+                                                 "prefix recompute, two sweeps) timed at prefix lengths %s -> %s s; step(t) = a + b t "
+                                                 "fitted and integrated over t = 1..1280 (%.0f s per 1280-token sample)"
+                                                 % ([p[0] for p in pts], [round(p[1], 2) for p in pts], total)))
     line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
@@ -149,9 +231,11 @@ def run_reference(args):
                             "vq_codebook_size=8192 encode+VQ+decode (BASELINE configs[1])", batch_per_step=frames,
                             note="reference algorithm (oracle port, PyTorch CPU fp32); the reference itself cannot be "
                                  "imported on the GPU box (two absent third-party deps, no /root/reference)"),
-                cpu_baseline=dict(value=fps, unit="frames/s", cores=cores, kind="port",
-                                  sample=f"{frames} frame(s) of the 64-frame batch per step"),
-                e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+                cpu_baseline=dict(value=fps, unit="frames/s", cores=cores, host_cores=host_cores, kind="port",
+                                  sample=f"{frames} frame(s) of the 64-frame batch per step, {cores} of {host_cores} host "
+                                         f"cores (fastest of all / half / quarter, calibrated untimed)"),
+                e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
+                decoder=decoder, generate=generate)
     print(json.dumps(line), flush=True)
 
 
@@ -376,6 +460,14 @@ def run_ours(args):
                                    backward="not included (forward loss only; autograd kernels are next-round work)"),
                        flops=dict(mflop_per_token_fwd=104.4,
                                   achieved_tflops=round(world * ntok * args.steps / dsec * 104.4e6 / 1e12 / world, 1)))
+        peak_t = pk["bf16_tflops_sustained"]
+        fwd_tf = ntok * args.steps / dsec * 104.4e6 / 1e12
+        decoder["roofline"] = dict(bound="tensor", achieved=round(fwd_tf, 1), peak=peak_t, unit="TFLOP/s",
+                                   frac=round(fwd_tf / peak_t, 4),
+                                   algorithmic="104.4 MFLOP per token forward (SURVEY 8d: 12 x 8.0 + logits 8.39) x 20480 tokens",
+                                   peak_source=pk["source"] + ", sustained figure", traffic=None,
+                                   note="whole forward step (219 launches); per-kernel rooflines of the attention cores under "
+                                        "kernel_rooflines")
         del graphed
         # ---- training step of the same config: forward loss + backward (SURVEY §8d cfg 3 timed region) ----
         from nuwa_pytorch_b200.graphs import GraphedTrainStep
@@ -425,6 +517,11 @@ def run_ours(args):
                 sum(p.numel() for p in tparams) / 1e6),
             flops=dict(mflop_per_token_fwd_bwd=3 * 104.4,
                        achieved_tflops=round(ntok * args.steps / tsec * 3 * 104.4e6 / 1e12, 1)))
+        tr_tf = ntok * args.steps / tsec * 3 * 104.4e6 / 1e12
+        decoder["train"]["roofline"] = dict(bound="tensor", achieved=round(tr_tf, 1), peak=peak_t, unit="TFLOP/s",
+                                            frac=round(tr_tf / peak_t, 4), traffic=None,
+                                            algorithmic="3 x 104.4 MFLOP per token (forward + dgrad + wgrad) x 20480 tokens",
+                                            peak_source=pk["source"] + ", sustained figure")
         decoder["config"]["backward"] = "see 'train' (same model and batch, loss.backward() included)"
         with torch.no_grad():
             decoder["kernel_rooflines"] = attention_kernel_rooflines(dev, pk)
@@ -523,7 +620,24 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t_ar, t_dec = float(tt[0]), float(tt[1])
         ntok = DEC_BATCH * frames * 256
-        generate = dict(metric="generate(): sampled video-tokens/sec (AR loop) and decoded frames/sec",
+        # algorithmic HBM bytes of ONE token step: both guidance sweeps stream every decoder weight once in bf16
+        # (data dependent, cannot share a read; 126 MB of L2 cannot hold them), + the K/V windows of the 64 3DNA layers
+        # (<= 46 keys x 2 x 512 x 2 B per layer per sample) and the cross-attention K/V (257 x 2 x 512 x 2 B) per sweep,
+        # + the bf16 logits weight twice
+        w_bytes = 2 * sum(p.numel() for n_, p in gnuwa.named_parameters()
+                          if n_.startswith("video_transformer.layers.") or n_ == "to_logits.weight")
+        n3 = sum(1 for n_, _ in gnuwa.named_parameters() if n_.endswith("fn.fn.to_kv.weight") and n_.startswith("video_transformer.layers."))
+        nx = sum(1 for n_, _ in gnuwa.named_parameters() if n_.endswith(".fn.null_k") and n_.startswith("video_transformer.layers."))
+        kv_bytes = DEC_BATCH * (n3 * 46 + nx * 257) * 2 * 512 * 2
+        step_bytes = 2 * (w_bytes + kv_bytes)
+        step_s = t_ar / (frames * 256)
+        gen_roof = dict(bound="hbm", achieved=round(step_bytes / step_s / 1e9, 1), peak=pk["hbm_gbs"], unit="GB/s",
+                        frac=round(step_bytes / step_s / 1e9 / pk["hbm_gbs"], 4), traffic=None,
+                        algorithmic_mb_per_step=round(step_bytes / 1e6, 1),
+                        algorithmic="2 sweeps x (%.1f MB bf16 decoder + logits weights + %.1f MB K/V windows) per token step at "
+                                    "batch %d" % (w_bytes / 1e6, kv_bytes / 1e6, DEC_BATCH),
+                        kernel="decode_stack_kernel (persistent, one launch per sweep)", peak_source=pk["source"])
+        generate = dict(roofline=gen_roof, metric="generate(): sampled video-tokens/sec (AR loop) and decoded frames/sec",
                         tokens_per_s=round(world * ntok / t_ar, 1), ms_per_token_step=round(1e3 * t_ar / (frames * 256), 3),
                         vae_decode_frames_per_s=round(world * DEC_BATCH * frames / t_dec, 1),
                         config=dict(workload="NUWA dim=512 dec_depth=64 dec_reversible=True, generate(num_frames=%d), "
@@ -536,12 +650,30 @@ def run_ours(args):
     # -------- CPU baseline (rank 0, N == 1 only): the reference algorithm's CPU path, bounded sample --------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
+        host_cores = os.cpu_count() or 1
         sd = cpu_state_dict_vae()
         cores = pick_cpu_threads(sd)
-        v, dt = cpu_vae_frames_per_s(sd, 1)
-        cpu = dict(value=round(v, 4), unit="frames/s", cores=cores, kind="port",
-                   sample=f"1 frame of the 64-frame batch, one pass ({dt:.1f} s), PyTorch CPU fp32 oracle port of the reference")
+        v, dt = cpu_vae_frames_per_s(sd, 2)
+        cpu = dict(value=round(v, 4), unit="frames/s", cores=cores, host_cores=host_cores, kind="port",
+                   sample=f"2 frames of the 64-frame batch, one pass ({dt:.1f} s), PyTorch CPU fp32 oracle port of the reference; "
+                          f"{cores} threads = the fastest of all / half / a quarter of the {host_cores} host cores")
         del sd
+        if decoder is not None:
+            tps, tdt, tps_f, tdt_f = cpu_decoder_train_tokens_per_s()
+            decoder["cpu_baseline"] = dict(
+                value=round(tps_f, 2), unit="tokens/s", cores=cores, host_cores=host_cores, kind="port",
+                sample=f"BASELINE configs[2] at B=1 (2560 video + 256 text tokens, 12 layers): forward loss, one pass "
+                       f"({tdt_f:.1f} s), PyTorch CPU fp32 oracle port")
+            decoder["train"]["cpu_baseline"] = dict(
+                value=round(tps, 2), unit="tokens/s", cores=cores, host_cores=host_cores, kind="port",
+                sample=f"the same pass with loss.backward() through torch autograd ({tdt:.1f} s in total)")
+        if generate is not None:
+            gps, pts, total = cpu_generate_tokens_per_s()
+            generate["cpu_baseline"] = dict(
+                value=round(gps, 4), unit="tokens/s", cores=cores, host_cores=host_cores, kind="port",
+                sample="BASELINE configs[3], B=1: single iterations of the reference loop (full prefix recompute, two sweeps) "
+                       "timed at prefix lengths %s -> %s s; step(t) = a + b t fitted and integrated over t = 1..1280 "
+                       "(%.0f s per 1280-token sample)" % ([p[0] for p in pts], [round(p[1], 2) for p in pts], total))
 
     if rank == 0:
         line = dict(metric=METRIC, value=round(fps, 2), unit="frames/s", n_gpus=world, steps=args.steps,

@@ -84,12 +84,12 @@ def test_cfg2_vae_one_frame_against_oracle(cuda_device):
           f"(fp32 ties only); quantised map rel {r_quant:.2e}; end-to-end id agreement with the all-fp32 oracle {agree:.4f}; "
           f"decoder rel {r_dec:.3e}; recon rel {r_rec:.3e}  [{time.time() - t0:.0f} s]")
     # 15 bf16-operand convolutions / GEMMs with K up to 36864 in front of the VQ, fp32 accumulate
-    assert r_pre < 1.5e-2
+    assert r_pre < 8e-3                    # measured 5.4e-3
     # fp32-faithful project_out (three-term bf16 split): the quantised map is the reference's to fp32 rounding
     assert r_quant < 1e-5
     assert agree >= 0.97
     # decoder alone on the reference's quantised map: 16 bf16-operand convolutions deep
-    assert r_dec < 2e-2
+    assert r_dec < 1.5e-2                  # measured 1.07e-2
     if agree == 1.0:
         assert r_rec < 2.5e-2
 
@@ -158,8 +158,8 @@ def test_cfg3_forward_loss_b1_against_oracle(cuda_device):
     r_emb = rel(emb, o_emb)
     print(f"  cfg3 B=1: text-encoder rel {r_emb:.3e}; loss {loss:.5f} vs oracle {o_loss.item():.5f} "
           f"(|d| {abs(loss - o_loss.item()):.2e})  [{time.time() - t0:.0f} s]")
-    assert r_emb < 1e-2                 # 6 reversible layers (12 sub-blocks), bf16 operands
-    assert abs(loss - o_loss.item()) < 5e-3   # mean CE over 2560 positions after 36 sub-blocks
+    assert r_emb < 8e-3                 # 6 reversible layers (12 sub-blocks), bf16 operands; measured 6.5e-3
+    assert abs(loss - o_loss.item()) < 1e-3   # mean CE over 2560 positions after 36 sub-blocks; measured 1.5e-5
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -191,7 +191,7 @@ def test_cfg4_depth64_reversible_generate_step_logits(cuda_device):
         worst = max(worst, r)
         print(f"  cfg4 step {t}: guided-logit rel {r:.3e}, arg-max agreement {top:.2f}")
     print(f"  cfg4: worst rel {worst:.3e}  [{time.time() - t0:.0f} s]")
-    assert worst < 4e-2  # 2 sweeps x 256 sub-blocks of bf16-operand GEMMs; guidance (x2) amplifies their difference
+    assert worst < 2e-2  # measured 1.43e-2; 2 sweeps x 256 sub-blocks of bf16-operand GEMMs; guidance (x2) amplifies their difference
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -219,5 +219,5 @@ def test_cfg5_sketch_forward_loss_b1_against_oracle(cuda_device):
     r_emb = rel(emb, o_emb)
     print(f"  cfg5 B=1: sketch-encoder (12 non-causal 3DNA layers) rel {r_emb:.3e}; loss {loss:.5f} vs oracle "
           f"{o_loss.item():.5f} (|d| {abs(loss - o_loss.item()):.2e})  [{time.time() - t0:.0f} s]")
-    assert r_emb < 1e-2
-    assert abs(loss - o_loss.item()) < 5e-3
+    assert r_emb < 8e-3                      # measured 6.5e-3
+    assert abs(loss - o_loss.item()) < 1e-3   # measured 2.8e-4

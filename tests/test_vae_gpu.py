@@ -188,7 +188,7 @@ def test_video_index_dataset_roundtrip_on_gpu(cuda_device, tmp_path):
     lab.flush()
     ds = VideoIndicesDataset(videos_memmap_path=path, text_memmap_path=str(tmp_path / "t.bin"), vae=vae, num_videos=5, num_frames=frames)
     t, v = ds[4]
-    assert v.tolist() == rows[4].tolist() and t.tolist() == [7, 7]
+    assert v.tolist() == rows[4].tolist() and t.tolist() == [8, 8]  # default text encoder: digit + 1 (0 is the pad id)
 
 
 @pytest.mark.parametrize("cosine", [True, False])
