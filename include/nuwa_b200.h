@@ -145,6 +145,14 @@ int nuwa_attn_sparse3dna(const nuwa_attn_params* p, void* vt_workspace, void* st
  * full pass (t0 == 0, nq == nv + 1), 16-wide token grid, H == 8, dh == 64, kh <= 3, <= 47 window keys, q|k|v in one
  * row-strided buffer; returns NUWA_ERR_INVALID outside it (nothing launched) so the caller can use the gather kernel. */
 int nuwa_attn_sparse3dna_halo(const nuwa_attn_params* p, void* stream);
+/* Same op on the 5th-generation tensor cores (attention_3dna_umma.cu): tcgen05.mma with TMEM accumulators.  One CTA per
+ * SM walks 128-query tiles (8 dilation-spaced grid rows x 16 columns, all heads): S = Q K^T of a (head, frame offset)
+ * unit is ONE UMMA against the <= 10 key rows the tile shares (TMA-staged), the band is extracted thread-per-query from
+ * TMEM, softmax in fp32, probabilities parked in TMEM, talking heads in fp32 registers, and P'V runs with the A operand
+ * read from tensor memory and V as MN-major B operand.  Envelope: full pass (t0 == 0, nq == nv + 1), 16-wide grid, H == 8,
+ * dh == 64, kw == 3, kh <= 3, kt <= 5, column dilation 1 / 2 / 4, causal or centred window; NUWA_ERR_INVALID outside it
+ * (nothing launched). */
+int nuwa_attn_sparse3dna_umma(const nuwa_attn_params* p, void* stream);
 /* Attention.forward core, nuwa_pytorch.py:339-378, and VQGanAttention core, vqgan_vae.py:275-282
  * (jmax = nk (+1 with a null key)) */
 int nuwa_attn_dense(const nuwa_attn_params* p, void* vt_workspace, void* stream);

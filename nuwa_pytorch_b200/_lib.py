@@ -117,6 +117,7 @@ SIGNATURES = {
     "nuwa_attn_sparse3dna": [P(AttnParams), c_void_p, c_void_p],
     "nuwa_attn_sparse3dna_halo": [P(AttnParams), c_void_p],
     "nuwa_attn_dense": [P(AttnParams), c_void_p, c_void_p],
+    "nuwa_attn_sparse3dna_umma": [P(AttnParams), c_void_p],
     "nuwa_attn_dense_pres": [P(AttnParams), c_void_p],
     "nuwa_attn_cross2dna": [P(AttnParams), c_void_p],
     "nuwa_embed_tokens": [P(EmbedParams), c_void_p],

@@ -51,6 +51,9 @@ int nuwa_attn_sparse3dna(const nuwa_attn_params* p, void* vt_workspace, void* st
 int nuwa_attn_sparse3dna_halo(const nuwa_attn_params* p, void* stream) {
   return p ? attn_3dna_halo(*p, S(stream)) : NUWA_ERR_INVALID;
 }
+int nuwa_attn_sparse3dna_umma(const nuwa_attn_params* p, void* stream) {
+  return p ? attn_3dna_umma(*p, S(stream)) : NUWA_ERR_INVALID;
+}
 int nuwa_attn_dense(const nuwa_attn_params* p, void* vt_workspace, void* stream) {
   if (!p) return NUWA_ERR_INVALID;
   if (p->nq >= 16) {  // 8 x 64 heads, learned null key / mask / talking heads: two-pass 64-query tensor-core kernel

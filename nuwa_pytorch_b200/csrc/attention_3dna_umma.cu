@@ -1,0 +1,854 @@
+// Sparse3DNA attention core on the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators, K / V key rows
+// staged by TMA, one CTA per SM walking a cost-sorted tile list.
+//
+// Reference: Sparse3DNA.forward core, nuwa_pytorch.py:523-564 (unfoldNd gather of k,v -> einsum -> mask -> softmax ->
+// talking heads -> einsum), causal (decoder) and centred (NUWASketch sketch encoder) windows.
+//
+// Work decomposition.  A TILE is 128 queries = 8 token-grid rows x 16 columns of one frame of one sample, all 8 heads.
+// The 8 rows are spaced by the window's row dilation (rows r, r+dh, r+2dh, ...; for dh >= 4 two such classes of 4 rows),
+// so the key rows the tile needs per frame offset are only 8 + kh - 1 <= 10 "slot columns" of 16 keys: the B operand of
+// ONE UMMA (N = 16 x valid slot columns <= 160), fetched by one or two TMA boxes over a 5-D view of the q|k|v buffer whose
+// row axis is split by the dilation.  A UNIT is (head, frame offset a):
+//   phase 1   S = Q_h K_{h,a}^T   M=128, N<=160, K=64, accumulator in TMEM (one S buffer per warpgroup); thread = query
+//             row: tcgen05.ld of the 64-column window holding its 3 key rows, the kw in-band entries of each go to a
+//             compact fp32 score row in shared memory (bit test + predicated store per column, immediate offsets); the
+//             bos score is a 64-term dot product per thread straight from the Q tile.  Per head: fp32 softmax ->
+//             fp16 probabilities parked in TMEM, column 8u + h = slots (2u, 2u+1) of head h
+//   mix       talking heads (nuwa_pytorch.py:556-558) ON THE TENSOR CORES: for every slot pair u one UMMA whose A operand
+//             is read from tensor memory (the 8 heads x 2 slots = K 16 just parked there) against the 16 x 16 block
+//             matrix [W 0; 0 W] split into fp16 high + low parts (two accumulating UMMAs: W to ~22 bits); the fp32 result
+//             is rounded to bf16 P' and written back in place
+//   phase 2   P'_g placed at its key position inside a dense 128 x 160 A operand that lives in TENSOR MEMORY
+//             (tcgen05.st; byte-permute placement, no shared-memory traffic), O_g += P'_g V_{g,a}: A from TMEM, B = the
+//             V key rows as MN-major operand, N=64; per head: + bos probability x bos value -> bf16 -> global
+// Warp roles: warp 0 = TMA producer, warps 2-5 / 6-9 = two warpgroups that own the even / odd heads, so extraction +
+// softmax of one head overlaps the UMMAs of the other; warp 1 / warp 10 = one MMA-issuing thread per warpgroup (a
+// tcgen05.mma costs its issuing thread ~70 cycles, the small UMMAs of this kernel are issue bound from one thread).
+// TMEM columns: P [0,184);  phase 1  S0 [192,352) S1 [352,512);  mix  D [192,512);  phase 2  A0 [192,272) A1 [272,352)
+// O0 [352,416) O1 [416,480).
+#include <float.h>
+#include <cuda_fp16.h>
+
+#include <utility>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tmem_ldst.cuh"
+
+namespace nuwa {
+
+int encode_map_bf16_sw128(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box);  // gemm_tcgen05.cu
+
+namespace {
+
+constexpr int GW = 16;                 // token grid width == height
+constexpr int NH = 8, DH = 64, INNER = NH * DH;
+constexpr int KW = 3;                  // window width (envelope: kw == 3)
+constexpr int MAXKT = 5, MAXKH = 3;
+constexpr int MAXJ = 1 + MAXKT * MAXKH * KW;   // 46
+constexpr int NU = (MAXJ - 1 + 1) / 2;         // 23 slot pairs
+constexpr int NSC = 8 + MAXKH - 1;     // slot columns of a key tile (10)
+constexpr int BOX = GW * DH * 2;       // 2048 B: 16 tokens x 64 channels of one head
+constexpr int KV_STAGE = NSC * BOX;    // 20 KB
+constexpr int NST = 5;
+constexpr int Q_BYTES = 8 * BOX;       // 16 KB
+constexpr int SPITCH = 50;             // fp32 score row pitch (words)
+
+constexpr int OFF_KV = 0;
+constexpr int OFF_Q = OFF_KV + NST * KV_STAGE;            // 4 buffers: (head pair parity, warpgroup)
+constexpr int OFF_KBOS = OFF_Q + 4 * Q_BYTES;             // [8 heads][64] fp32: bos key rows of the tile's sample
+constexpr int OFF_WB = OFF_KBOS + NH * DH * 4;            // talking-heads B operands: [hi, lo] x [16 rows x 128 B]
+constexpr int OFF_SC = OFF_WB + 2 * BOX;                  // 2 warpgroups x [128][SPITCH] fp32
+constexpr int OFF_VBOS = OFF_SC + 2 * 128 * SPITCH * 4;   // [8][64] bf16
+constexpr int OFF_PBOS = OFF_VBOS + INNER * 2;            // [8][128] fp32: probability of the bos slot
+constexpr int OFF_W = OFF_PBOS + NH * 128 * 4;            // [8][8] fp32
+constexpr int OFF_BAR = OFF_W + NH * NH * 4;
+constexpr int NBAR = 2 * NST + 2 * 4 + 6 * 2 + 3;
+constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
+
+constexpr int T_P = 0, T_S = 192, T_D = 192, T_A = 192, T_O = 352;
+constexpr int THREADS = 352;   // warp 0 producer, warp 1 / warp 10 MMA issuers of warpgroup 0 / 1, warps 2-9 warpgroups
+
+struct UmmaArgs {
+  int B, nv, nf, maxf, tpf, ntiles;    // nf = frames present, tpf = tiles per frame
+  int kt, kh, dt, dh, dw, causal;
+  int koff, voff;
+  int rows5d;                          // rows [0, rows5d) of every sample are reachable through the 5-D maps (0: none)
+  float scale_log2e;
+  const float* talk;
+  bf16* o;
+  long long o_bs;
+  int o_rs;
+  const bf16* k0;
+  const bf16* v0;
+  long long k_bs, v_bs;
+  long long* dbg;  // tools/umma_stamps.py: clock64 stamps of CTA 0 (NULL in normal use)
+};
+
+// geometry of one tile (registers only), identical in every role
+struct Tile {
+  int b, f;
+  int two;           // two classes of 4 rows (row dilation >= 4)
+  int r0, i0;        // single class: rows r0 + (i0 + i) * dh;  two classes: classes r0 and r0 + 1
+  int sc_lo, sc_hi;  // valid slot columns [sc_lo, sc_hi)
+  int real_mask;     // frame offsets a with a real key frame
+  int zero_mask;     // frame offsets whose frame lies inside the volume but beyond the sequence (visible zero keys, D16)
+  int n_real;
+};
+
+// grid row of tile row i (-1: none)
+__device__ __forceinline__ int tile_row(const UmmaArgs& p, const Tile& t, int i) {
+  if (!t.two) {
+    const int y = t.r0 + (t.i0 + i) * p.dh;
+    return y < GW ? y : -1;
+  }
+  const int r = t.r0 + (i >> 2);
+  const int y = r + (i & 3) * p.dh;
+  return (r < p.dh && y < GW) ? y : -1;
+}
+// grid row of slot column sc (-1: none); Ah = rows of the window above the query row
+__device__ __forceinline__ int slot_row(const UmmaArgs& p, const Tile& t, int sc, int Ah) {
+  if (!t.two) {
+    const int y = t.r0 + (t.i0 + sc - Ah) * p.dh;
+    return (y >= 0 && y < GW && sc < 8 + p.kh - 1) ? y : -1;
+  }
+  const int sl = sc - Ah;
+  if (sl < 0 || sl >= 8) return -1;
+  const int r = t.r0 + (sl >> 2);
+  const int y = r + (sl & 3) * p.dh;
+  return (r < p.dh && y < GW) ? y : -1;
+}
+
+__device__ __forceinline__ void make_tile(const UmmaArgs& p, int s, int Ah, Tile& t) {
+  // sorted tile index s: later frames first (causal: more key frames = more work)
+  const int per_f = p.tpf * p.B;
+  t.f = p.nf - 1 - s / per_f;
+  const int rem = s % per_f;
+  const int ti = rem / p.B;
+  t.b = rem - ti * p.B;
+  t.two = p.dh >= 4;
+  if (!t.two) {
+    int r = 0, k = ti;
+    for (; r < p.dh; ++r) {
+      const int nrows = (GW - r + p.dh - 1) / p.dh;
+      const int nt = (nrows + 7) / 8;
+      if (k < nt) break;
+      k -= nt;
+    }
+    t.r0 = r;
+    t.i0 = k * 8;
+  } else {
+    t.r0 = 2 * ti;
+    t.i0 = 0;
+  }
+  t.sc_lo = NSC; t.sc_hi = 0;
+#pragma unroll
+  for (int sc = 0; sc < NSC; ++sc)
+    if (slot_row(p, t, sc, Ah) >= 0) { t.sc_lo = min(t.sc_lo, sc); t.sc_hi = max(t.sc_hi, sc + 1); }
+  const int At = p.causal ? p.kt - 1 : (p.kt - 1) / 2;
+  t.real_mask = t.zero_mask = t.n_real = 0;
+#pragma unroll
+  for (int a = 0; a < MAXKT; ++a) {
+    const int ff = t.f + (a - At) * p.dt;
+    if (a < p.kt && ff >= 0 && ff < p.maxf) {
+      if (ff < p.nf) { t.real_mask |= 1 << a; ++t.n_real; }
+      else t.zero_mask |= 1 << a;
+    }
+  }
+}
+
+// k-th tile of CTA c under the snake deal of the cost-sorted list: rounds alternate direction
+__device__ __forceinline__ int snake(int k, int c, int G) { return k * G + ((k & 1) ? G - 1 - c : c); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+
+// Column j of a thread's 64-column window (slot column j >> 4, key column j & 15) goes to word KW * (j >> 4) +
+// (j & 15) / DW of its compact score row if bit j of the in-band mask is set: one bit test + one predicated store with an
+// immediate offset per column (true predication -- a C++ `if` around the store compiles to a divergent branch per column).
+template <int DW, int J>
+__device__ __forceinline__ void store_col(uint32_t tb, uint32_t val, uint32_t maskword) {
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .b32 t;\n and.b32 t, %2, %3;\n setp.ne.b32 p, t, 0;\n @p st.shared.b32 [%0+%4], %1;\n}\n"
+      ::"r"(tb), "r"(val), "r"(maskword), "n"(1u << (J & 31)), "n"(4 * (KW * (J >> 4) + (J & 15) / DW))
+      : "memory");
+}
+template <int DW, int... Js>
+__device__ __forceinline__ void store_band(uint32_t tb, const uint32_t (&v)[64], const uint32_t (&xm)[2],
+                                           std::integer_sequence<int, Js...>) {
+  (store_col<DW, Js>(tb, v[Js], xm[Js >> 5]), ...);
+}
+
+// key / query rows y0 + i * dh (i < n) of frame f, channels [chan, chan + 64) -> dst + i * BOX.  Rows reachable through
+// the 5-D view travel as boxes of 8 / 4 / 2 rows (one TMA instruction each); the ragged end of the sequence and
+// dilations that do not divide the grid height use one 16-token box per row on the flat view (zero fill past the end).
+__device__ __forceinline__ void load_rows(uint32_t dst, uint64_t* bar, const CUtensorMap* flat, const CUtensorMap* m8,
+                                          const CUtensorMap* m4, const CUtensorMap* m2, const UmmaArgs& p, int chan, int f,
+                                          int y0, int n, int b) {
+  const int R0 = f * GW + y0;
+  int i = 0;
+  if (R0 + (n - 1) * p.dh < p.rows5d) {
+    const int ylo = y0 % p.dh, yhi = R0 / p.dh;
+    for (; n - i >= 8; i += 8) tma_load_5d(dst + i * BOX, m8, bar, chan, 0, ylo, yhi + i, b);
+    if (n - i >= 4) { tma_load_5d(dst + i * BOX, m4, bar, chan, 0, ylo, yhi + i, b); i += 4; }
+    if (n - i >= 2) { tma_load_5d(dst + i * BOX, m2, bar, chan, 0, ylo, yhi + i, b); i += 2; }
+  }
+  for (; i < n; ++i) tma_load_3d(dst + i * BOX, flat, bar, chan, 1 + (R0 + i * p.dh) * GW, b);
+}
+
+template <int DW>
+__global__ void __launch_bounds__(THREADS, 1)
+attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap map8,
+                      const __grid_constant__ CUtensorMap map4, const __grid_constant__ CUtensorMap map2, const UmmaArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  const uint32_t sm_u = smem_u32(sm);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
+  uint64_t* full = bars;                 // [NST]  TMA -> MMA
+  uint64_t* empty = full + NST;          // [NST]  MMA commit -> TMA
+  uint64_t* qfull = empty + NST;         // [4]    Q tile of (head pair parity, warpgroup)
+  uint64_t* qempty = qfull + 4;          // [4]
+  uint64_t* sfull = qempty + 4;          // [2]    MMA commit -> warpgroup
+  uint64_t* sempty = sfull + 2;          // [2]    warpgroup (4 warps) -> MMA
+  uint64_t* afull = sempty + 2;          // [2]    warpgroup -> MMA (A operand written to TMEM)
+  uint64_t* aempty = afull + 2;          // [2]    MMA commit -> warpgroup
+  uint64_t* ofull = aempty + 2;          // [2]
+  uint64_t* oempty = ofull + 2;          // [2]
+  uint64_t* tready = oempty + 2;         // [1]    8 warps: previous tile drained, this tile's bos rows staged
+  uint64_t* mixgo = tready + 1;          // [1]    8 warps -> MMA: probabilities parked / first batch converted
+  uint64_t* mixfull = mixgo + 1;         // [1]    MMA commit -> warpgroups: a batch of mixed probabilities is in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_TMEM);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&qfull[i], 1); mbar_init(&qempty[i], 5); }  // commit + 4 warps (bos dot)
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 4);
+      mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1);
+      mbar_init(&ofull[i], 1); mbar_init(&oempty[i], 4);
+    }
+    mbar_init(tready, 8);
+    mbar_init(mixgo, 8);
+    mbar_init(mixfull, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&qmap);
+    tma_prefetch_desc(&map8);
+    tma_prefetch_desc(&map4);
+    tma_prefetch_desc(&map2);
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  // one-time shared-memory state: operand buffers zeroed (slot columns that are never loaded must hold finite values:
+  // their probabilities are exactly 0, and 0 x NaN would poison P'V), bos operand tiles, talking-heads operands
+  for (int i = tid; i < OFF_SC / 16; i += THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (tid < NH * NH) {
+    float* Wsm = reinterpret_cast<float*>(sm + OFF_W);
+    const float w = p.talk ? __ldg(p.talk + tid) : ((tid / NH) == (tid % NH) ? 1.f : 0.f);
+    Wsm[tid] = w;
+    // B[n = 2g + s'][k = 2h + s] = W[g][h] (s == s'), fp16 high and low parts; rows of 128 B, SWIZZLE_128B chunks
+    const int g = tid / NH, h = tid % NH;
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn(w - __half2float(hi));
+#pragma unroll
+    for (int sp = 0; sp < 2; ++sp) {
+      const int n = 2 * g + sp, kk = 2 * h + sp;
+      const uint32_t off = (uint32_t)n * 128u + ((((uint32_t)kk >> 3) ^ ((uint32_t)n & 7u)) << 4) + ((uint32_t)kk & 7u) * 2u;
+      *reinterpret_cast<__half*>(sm + OFF_WB + off) = hi;
+      *reinterpret_cast<__half*>(sm + OFF_WB + BOX + off) = lo;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int Ah = p.causal ? p.kh - 1 : (p.kh - 1) / 2;
+  const int At = p.causal ? p.kt - 1 : (p.kt - 1) / 2;
+  const int KHW = p.kh * KW;
+
+  if (warp == 0) {
+    // =========================================== TMA producer ===========================================
+    if (lane == 0) {
+      uint32_t it = 0, qu[4] = {0, 0, 0, 0};
+      for (int k = 0;; ++k) {
+        const int s = snake(k, cta, G);
+        if (s >= p.ntiles) break;
+        Tile t;
+        make_tile(p, s, Ah, t);
+        // row runs: queries (from tile row 0 / 4) and key slot columns (from sc_lo, or Ah / Ah + 4 for two classes)
+        int qy[2] = {0, 0}, qn[2] = {0, 0}, ky[2] = {0, 0}, kn[2] = {0, 0}, ksc[2] = {0, 0};
+        if (!t.two) {
+          qy[0] = tile_row(p, t, 0);
+          for (int i = 0; i < 8; ++i) qn[0] += tile_row(p, t, i) >= 0;
+          ksc[0] = t.sc_lo;
+          ky[0] = slot_row(p, t, t.sc_lo, Ah);
+          kn[0] = t.sc_hi - t.sc_lo;
+        } else {
+          for (int c = 0; c < 2; ++c) {
+            qy[c] = t.r0 + c;
+            for (int i = 0; i < 4; ++i) qn[c] += tile_row(p, t, 4 * c + i) >= 0;
+            ksc[c] = Ah + 4 * c;
+            ky[c] = t.r0 + c;
+            kn[c] = qn[c];
+          }
+        }
+        const uint32_t qbytes = (uint32_t)(qn[0] + qn[1]) * BOX;
+        const uint32_t kbytes = (uint32_t)(kn[0] + kn[1]) * BOX;
+        auto load_q = [&](int hp) {
+          for (int w = 0; w < 2; ++w) {
+            const int h = 2 * hp + w, qb = 2 * (hp & 1) + w;
+            mbar_wait(&qempty[qb], (qu[qb] & 1) ^ 1);
+            mbar_arrive_expect_tx(&qfull[qb], qbytes);
+            for (int c = 0; c < 2; ++c)
+              if (qn[c] > 0)
+                load_rows(sm_u + OFF_Q + qb * Q_BYTES + 4 * c * BOX, &qfull[qb], &qmap, &map8, &map4, &map2, p, h * DH, t.f,
+                          qy[c], qn[c], t.b);
+            ++qu[qb];
+          }
+        };
+        load_q(0);
+        for (int ph = 0; ph < 2; ++ph) {
+          for (int hp = 0; hp < NH / 2; ++hp) {
+            if (ph == 0 && hp + 1 < NH / 2) load_q(hp + 1);   // one head pair ahead: no bubble at the head boundary
+            for (int a = 0; a < p.kt; ++a) {
+              if (!((t.real_mask >> a) & 1)) continue;
+              const int ff = t.f + (a - At) * p.dt;
+              for (int w = 0; w < 2; ++w) {
+                const int h = 2 * hp + w;
+                const int st = it % NST;
+                mbar_wait(&empty[st], ((it / NST) & 1) ^ 1);
+                mbar_arrive_expect_tx(&full[st], kbytes);
+                const int chan = (ph ? p.voff : p.koff) + h * DH;
+                for (int c = 0; c < 2; ++c)
+                  if (kn[c] > 0)
+                    load_rows(sm_u + OFF_KV + st * KV_STAGE + ksc[c] * BOX, &full[st], &qmap, &map8, &map4, &map2, p, chan, ff,
+                              ky[c], kn[c], t.b);
+                ++it;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 || warp == 10) {
+    // ====================== MMA issuer of warpgroup w (w = 0 also issues the talking-heads UMMAs) ======================
+    if (lane == 0) {
+      const int w = warp == 1 ? 0 : 1;
+      uint32_t it = (uint32_t)w, qu[2] = {0, 0}, su = 0, au = 0, ou = 0, tile_n = 0, mg = 0;
+      const uint32_t idesc_pv = make_idesc_f16(128, DH, 1, 1, 0, 1);   // A: bf16 from TMEM, B: bf16 MN-major
+      const uint32_t idesc_mix = make_idesc_f16(128, 16, 0, 0, 0, 0);  // A: fp16 from TMEM, B: fp16 K-major
+      const uint64_t wb_hi = make_sw128_kmajor_desc(sm_u + OFF_WB), wb_lo = make_sw128_kmajor_desc(sm_u + OFF_WB + BOX);
+      const uint32_t d_s = tmem + T_S + w * 160, d_o = tmem + T_O + w * DH, a_t = tmem + T_A + w * 80;
+      for (int k = 0;; ++k) {
+        const int s = snake(k, cta, G);
+        if (s >= p.ntiles) break;
+        Tile t;
+        make_tile(p, s, Ah, t);
+        const int nsc = t.sc_hi - t.sc_lo;
+        const uint32_t idesc_qk = make_idesc_f16(128, 16 * nsc, 1, 1, 0, 0);
+        mbar_wait(tready, tile_n & 1);
+        ++tile_n;
+        tc_fence_after();
+        // ---------------- phase 1: S = Q K^T ----------------
+        for (int hp = 0; hp < NH / 2; ++hp) {
+          const int qb = 2 * (hp & 1) + w;
+          const uint64_t qdesc = make_sw128_kmajor_desc(sm_u + OFF_Q + qb * Q_BYTES);
+          mbar_wait(&qfull[qb], qu[hp & 1] & 1);
+          for (int a = 0; a < p.kt; ++a) {
+            if (!((t.real_mask >> a) & 1)) continue;
+            const int st = it % NST;
+            const uint64_t kdesc = make_sw128_kmajor_desc(sm_u + OFF_KV + st * KV_STAGE + t.sc_lo * BOX);
+            const uint32_t d = d_s + t.sc_lo * 16;
+            const bool md = p.dbg != nullptr && cta == 0 && k == 0 && w == 0 && su < 24;
+            if (md) p.dbg[320 + 4 * su] = clock64();
+            mbar_wait(&sempty[w], (su & 1) ^ 1);
+            if (md) p.dbg[320 + 4 * su + 1] = clock64();
+            mbar_wait(&full[st], (it / NST) & 1);
+            if (md) p.dbg[320 + 4 * su + 2] = clock64();
+            tc_fence_after();
+            umma_bf16(d, qdesc, kdesc, idesc_qk, 0u);
+            umma_bf16(d, qdesc + 2, kdesc + 2, idesc_qk, 1u);
+            umma_bf16(d, qdesc + 4, kdesc + 4, idesc_qk, 1u);
+            umma_bf16(d, qdesc + 6, kdesc + 6, idesc_qk, 1u);
+            umma_commit(&empty[st]);
+            umma_commit(&sfull[w]);
+            if (md) p.dbg[320 + 4 * su + 3] = clock64();
+            it += 2; ++su;
+          }
+          umma_commit(&qempty[qb]);
+          ++qu[hp & 1];
+        }
+        // ---------------- talking heads: D[q][2g + s'] = sum_h W[g][h] P[h][2u + s'] for every slot pair u ----------------
+        if (w == 0) {
+          for (int batch = 0; batch < 2; ++batch) {
+            mbar_wait(mixgo, mg & 1);
+            ++mg;
+            tc_fence_after();
+            const int u0 = batch ? 20 : 0, u1 = batch ? NU : 20;
+            for (int u = u0; u < u1; ++u) {
+              umma_f16_ts(tmem + T_D + 16 * (u - u0), tmem + T_P + 8 * u, wb_hi, idesc_mix, 0u);
+              umma_f16_ts(tmem + T_D + 16 * (u - u0), tmem + T_P + 8 * u, wb_lo, idesc_mix, 1u);
+            }
+            umma_commit(mixfull);
+          }
+        }
+        // ---------------- phase 2: O = P' V ----------------
+        for (int gp = 0; gp < NH / 2; ++gp) {
+          uint32_t acc = 0u;
+          int seen = 0;
+          for (int a = 0; a < p.kt; ++a) {
+            if (!((t.real_mask >> a) & 1)) continue;
+            ++seen;
+            const int st = it % NST;
+            const uint64_t vdesc = make_sw128_kmajor_desc(sm_u + OFF_KV + st * KV_STAGE);
+            const bool md = p.dbg != nullptr && cta == 0 && k == 0 && w == 0 && au < 24;
+            if (md) p.dbg[192 + 4 * au] = clock64();
+            mbar_wait(&full[st], (it / NST) & 1);
+            if (md) p.dbg[192 + 4 * au + 1] = clock64();
+            if (seen == 1) mbar_wait(&oempty[w], (ou & 1) ^ 1);
+            mbar_wait(&afull[w], au & 1);
+            if (md) p.dbg[192 + 4 * au + 2] = clock64();
+            tc_fence_after();
+#pragma unroll
+            for (int sc = 0; sc < NSC; ++sc)
+              if (sc >= t.sc_lo && sc < t.sc_hi) {
+                umma_f16_ts(d_o, a_t + sc * 8, vdesc + (uint64_t)(sc * (BOX >> 4)), idesc_pv, acc);
+                acc = 1u;
+              }
+            umma_commit(&empty[st]);
+            umma_commit(&aempty[w]);
+            if (seen == t.n_real) { umma_commit(&ofull[w]); ++ou; }
+            if (md) p.dbg[192 + 4 * au + 3] = clock64();
+            it += 2; ++au;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================== warpgroups ===========================================
+    const int wg = (warp - 2) >> 2;              // 0: even heads, 1: odd heads
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may touch
+    const int qrow = quarter * 32 + lane;        // query index inside the tile == TMEM lane
+    const int ti = qrow >> 4, x = qrow & 15;     // tile row, grid column
+    const int r = ti & 1;                        // row inside the warp's pair
+    const int wq = quarter;                      // window index: slot columns [2*wq, 2*wq + 4)
+    const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+    float* srow = reinterpret_cast<float*>(sm + OFF_SC) + (size_t)(wg * 128 + qrow) * SPITCH;
+    const uint32_t srow_u = smem_u32(srow);
+    const float* Wsm = reinterpret_cast<const float*>(sm + OFF_W);
+    const bf16* vbos = reinterpret_cast<const bf16*>(sm + OFF_VBOS);
+    float* pbos_s = reinterpret_cast<float*>(sm + OFF_PBOS);
+    const int Aw = p.causal ? KW - 1 : (KW - 1) / 2;
+
+    // ---- per-thread constants of the key-column geometry (x only) ----
+    bool vc[KW];
+    uint32_t sel[8];                             // PRMT selectors placing (P'_c0, P'_c1 | P'_c2, 0) at their key columns
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) sel[w8] = 0x7676u;
+#pragma unroll
+    for (int c = 0; c < KW; ++c) {
+      const int jc = x + (c - Aw) * p.dw;
+      vc[c] = jc >= 0 && jc < GW;
+      if (vc[c]) {
+        const uint32_t nib = (uint32_t)(2 * c) | ((uint32_t)(2 * c + 1) << 4);   // bytes of half-word c
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8)
+          if ((jc >> 1) == w8) sel[w8] = (jc & 1) ? ((sel[w8] & 0x00ffu) | (nib << 8)) : ((sel[w8] & 0xff00u) | nib);
+      }
+    }
+    uint32_t su = 0, au = 0, ou = 0, mf = 0, qu = 0;   // qu: uses of this warpgroup's Q buffers (same count for both parities)
+
+    for (int k = 0;; ++k) {
+      const int s = snake(k, cta, G);
+      if (s >= p.ntiles) break;
+      Tile t;
+      make_tile(p, s, Ah, t);
+      const int y = tile_row(p, t, ti);
+      const int vpos = (t.f * GW + (y >= 0 ? y : 0)) * GW + x;      // video-token index of this query
+      const bool qok = y >= 0 && vpos < p.nv;
+      // key-row validity of this thread's kernel rows, window extraction mask
+      uint32_t vb = 0;
+#pragma unroll
+      for (int b = 0; b < MAXKH; ++b) {
+        const int sc = ti + b;
+        bool ok = b < p.kh && slot_row(p, t, sc, Ah) >= 0;
+        if (t.two) { const int sl = sc - Ah; ok = ok && sl >= 0 && (sl >> 2) == (ti >> 2); }
+        vb |= (ok ? 1u : 0u) << b;
+      }
+      uint32_t xm[2] = {0u, 0u};
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const int b = (j >> 4) - r, jj = j & 15;
+        const int d = jj - x;
+        const bool inb = b >= 0 && b < MAXKH && ((vb >> (b < 0 ? 0 : (b > 2 ? 2 : b))) & 1u) && (d % DW == 0) &&
+                         (d / DW + Aw >= 0) && (d / DW + Aw < KW);
+        xm[j >> 5] |= (inb ? 1u : 0u) << (j & 31);
+      }
+      // ---- tile start: everyone has left the previous tile (its bos rows / TMEM are free), then stage this one ----
+      named_bar_sync(1, 256);
+      for (int j = 0; j < SPITCH; ++j) srow[j] = -FLT_MAX;
+      if (wg == 0) {
+        if (qrow < 64) {  // k_bos: 8 heads x 64 channels -> fp32 (read as broadcasts by the bos dot product)
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.k0 + (long long)t.b * p.k_bs) + qrow);
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+          float* dstk = reinterpret_cast<float*>(sm + OFF_KBOS) + qrow * 8;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f2 = unpack_bf16x2(w4[e]);
+            dstk[2 * e] = f2.x; dstk[2 * e + 1] = f2.y;
+          }
+        } else {
+          const int i = qrow - 64;
+          reinterpret_cast<uint4*>(sm + OFF_VBOS)[i] = __ldg(reinterpret_cast<const uint4*>(p.v0 + (long long)t.b * p.v_bs) + i);
+        }
+      }
+      // the bos query (sequence row 0) attends only to itself (nuwa_pytorch.py:608): its output is its value row
+      if (t.f == 0 && tile_row(p, t, 0) == 0 && wg == 1 && qrow < 64) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.v0 + (long long)t.b * p.v_bs) + qrow);
+        reinterpret_cast<uint4*>(p.o + (long long)t.b * p.o_bs)[qrow] = v;
+      }
+      named_bar_sync(1, 256);
+      if (lane == 0) mbar_arrive(tready);
+      const bool dbg = p.dbg != nullptr && cta == 0 && k == 0 && (warp == 2 || warp == 6) && lane == 0;
+      long long* dst_dbg = p.dbg + (warp == 6 ? 32 : 0);
+      if (dbg) dst_dbg[0] = clock64();
+
+      // ================= phase 1: band extraction + softmax =================
+      for (int hp = 0; hp < NH / 2; ++hp) {
+        const int h = 2 * hp + wg;
+        {  // bos key (slot 0): 64-term dot product of this thread's Q row (SWIZZLE_128B tile, as the UMMA reads it) with
+           // k_bos[h]; runs while the first key tile of the head is still in flight
+          const int qb = 2 * (hp & 1) + wg;
+          mbar_wait(&qfull[qb], qu & 1);
+          const uint8_t* qt = sm + OFF_Q + qb * Q_BYTES + qrow * 128;
+          const float4* kb4 = reinterpret_cast<const float4*>(sm + OFF_KBOS) + h * (DH / 4);
+          float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 qv = *reinterpret_cast<const uint4*>(qt + ((c ^ (qrow & 7)) << 4));
+            const float4 k0 = kb4[2 * c], k1 = kb4[2 * c + 1];
+            const float2 a0 = unpack_bf16x2(qv.x), a1 = unpack_bf16x2(qv.y), a2 = unpack_bf16x2(qv.z), a3 = unpack_bf16x2(qv.w);
+            d4[0] = fmaf(a0.x, k0.x, d4[0]); d4[1] = fmaf(a0.y, k0.y, d4[1]);
+            d4[2] = fmaf(a1.x, k0.z, d4[2]); d4[3] = fmaf(a1.y, k0.w, d4[3]);
+            d4[0] = fmaf(a2.x, k1.x, d4[0]); d4[1] = fmaf(a2.y, k1.y, d4[1]);
+            d4[2] = fmaf(a3.x, k1.z, d4[2]); d4[3] = fmaf(a3.y, k1.w, d4[3]);
+          }
+          srow[0] = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&qempty[qb]);
+          if (hp & 1) ++qu;
+        }
+#pragma unroll 1
+        for (int a = 0; a < p.kt; ++a) {
+          if ((t.zero_mask >> a) & 1) {
+            // in-volume key frame beyond the sequence: visible zero keys (score 0), SURVEY D16
+#pragma unroll
+            for (int b = 0; b < MAXKH; ++b)
+#pragma unroll
+              for (int c = 0; c < KW; ++c)
+                if (((vb >> b) & 1u) && vc[c]) srow[1 + a * KHW + b * KW + c] = 0.f;
+            continue;
+          }
+          if (!((t.real_mask >> a) & 1)) continue;
+          const uint32_t tb = srow_u + 4u * (uint32_t)(1 + a * KHW - r * KW - x / DW + Aw);
+          const bool ud = dbg && warp == 2 && su < 24;
+          if (ud) p.dbg[416 + 4 * su] = clock64();
+          mbar_wait(&sfull[wg], su & 1);
+          if (ud) p.dbg[416 + 4 * su + 1] = clock64();
+          tc_fence_after();
+          uint32_t v[64];
+          tmem_ld_x64(tlane + T_S + wg * 160 + wq * 32, v);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sempty[wg]);
+          if (ud) p.dbg[416 + 4 * su + 2] = clock64();
+          ++su;
+          store_band<DW>(tb, v, xm, std::make_integer_sequence<int, 64>{});
+          if (ud) p.dbg[416 + 4 * (su - 1) + 3] = clock64();
+        }
+        // ---- softmax of this head's row (fp32): bos probability -> smem (fp32), window probabilities -> fp16 pairs in
+        //      TMEM, column 8u + h = slots (1 + 2u, 2 + 2u) ----
+        {
+          float sv[MAXJ + 1];
+#pragma unroll
+          for (int i = 0; i < MAXJ / 2; ++i) {
+            const float2 f2 = *reinterpret_cast<const float2*>(srow + 2 * i);
+            sv[2 * i] = f2.x; sv[2 * i + 1] = f2.y;
+          }
+          sv[MAXJ] = -FLT_MAX;
+          float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+#pragma unroll
+          for (int i = 0; i < MAXJ; ++i) m4[i & 3] = fmaxf(m4[i & 3], sv[i]);
+          const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          const float mneg = -m * p.scale_log2e;
+          float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < MAXJ + 1; ++i) {
+            sv[i] = fast_exp2(fmaf(sv[i], p.scale_log2e, mneg));   // masked slots: exp2(-huge) == 0
+            l4[i & 3] += sv[i];
+          }
+          const float inv = 1.0f / ((l4[0] + l4[1]) + (l4[2] + l4[3]));
+          pbos_s[h * 128 + qrow] = sv[0] * inv;
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            const __half2 h2 = __floats2half2_rn(sv[1 + 2 * u] * inv, sv[2 + 2 * u] * inv);
+            uint32_t pk[1] = {*reinterpret_cast<const uint32_t*>(&h2)};
+            tmem_st_x1(tlane + T_P + 8 * u + h, pk);
+          }
+        }
+        if (dbg) dst_dbg[1 + hp] = clock64();
+      }
+      // ---- talking heads on the tensor cores: hand P to the MMA thread, convert its fp32 result to bf16 P' in place ----
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(mixgo);
+      if (dbg) dst_dbg[5] = clock64();
+#pragma unroll 1
+      for (int batch = 0; batch < 2; ++batch) {
+        mbar_wait(mixfull, mf & 1);
+        ++mf;
+        tc_fence_after();
+        const int u0 = batch ? 20 : 0, u1 = batch ? NU : 20;
+#pragma unroll 1
+        for (int u = u0 + wg; u < u1; u += 2) {
+          uint32_t d[16], o8[8];
+          tmem_ld_x16(tlane + T_D + 16 * (u - u0), d);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < NH; ++g) o8[g] = pack_bf16x2(__uint_as_float(d[2 * g]), __uint_as_float(d[2 * g + 1]));
+          tmem_st_x8(tlane + T_P + 8 * u, o8);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (batch == 0 && lane == 0) mbar_arrive(mixgo);
+      }
+      // both warpgroups are done with D: its columns become the A operands / O accumulators.  Zero this warpgroup's A
+      // buffer: only the 4-slot-column window of a lane is ever rewritten, the rest of the 160-key row must stay zero
+      named_bar_sync(1, 256);
+      tc_fence_after();
+      {
+        uint32_t z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+        for (int c = 0; c < 80; c += 16) tmem_st_x16(tlane + T_A + wg * 80 + c, z);
+        tmem_st_wait();
+      }
+      if (dbg) dst_dbg[6] = clock64();
+
+      // ================= phase 2: dense A operand rows + head epilogues =================
+      // one unit: the 9 mixed probabilities of frame offset a (halves [a*KHW, a*KHW + 9) of head g: column 8u + g,
+      // u = half / 2) -> this warp's 4-slot-column window of the dense A operand -> publish to the MMA issuer
+      auto build_unit = [&](int g, int a) {
+        const int h0 = a * KHW;
+        uint32_t c8[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          uint32_t one[1];
+          tmem_ld_x1(tlane + T_P + 8 * ((h0 >> 1) + i) + g, one);
+          c8[i] = one[0];
+        }
+        tmem_ld_wait();
+        const uint32_t sh = (uint32_t)(h0 & 1) * 16u;
+        uint32_t pr[5];                           // pairs (i0,i1) (i2,i3) (i4,i5) (i6,i7) (i8,.)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pr[i] = __funnelshift_r(c8[i], c8[i + 1], sh);
+        pr[4] = c8[4] >> sh;
+        uint32_t PA[MAXKH], PB[MAXKH];
+        PA[0] = pr[0];                       PB[0] = pr[1] & 0xffffu;
+        PA[1] = prmt(pr[1], pr[2], 0x5432u); PB[1] = pr[2] >> 16;
+        PA[2] = pr[3];                       PB[2] = pr[4] & 0xffffu;
+#pragma unroll
+        for (int b = 0; b < MAXKH; ++b)
+          if (b >= p.kh) { PA[b] = 0u; PB[b] = 0u; }   // rows beyond kh belong to the next unit
+        uint32_t win[32];
+#pragma unroll
+        for (int scw = 0; scw < 4; ++scw) {
+          // kernel row b = scw - r
+          uint32_t pa, pb;
+          if (scw == 0) { pa = r ? 0u : PA[0]; pb = r ? 0u : PB[0]; }
+          else if (scw == 3) { pa = r ? PA[2] : 0u; pb = r ? PB[2] : 0u; }
+          else { pa = r ? PA[scw - 1] : PA[scw]; pb = r ? PB[scw - 1] : PB[scw]; }
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) win[scw * 8 + w8] = prmt(pa, pb, sel[w8]);
+        }
+        mbar_wait(&aempty[wg], (au & 1) ^ 1);
+        tc_fence_after();
+        tmem_st_x32(tlane + T_A + wg * 80 + wq * 16, win);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&afull[wg]);
+        ++au;
+      };
+      const int a_first = __ffs(t.real_mask) - 1;
+      for (int gp = 0; gp < NH / 2; ++gp) {
+        const int g = 2 * gp + wg;
+#pragma unroll 1
+        for (int a = 0; a < p.kt; ++a) {
+          if (!((t.real_mask >> a) & 1)) continue;
+          if (gp > 0 && a == a_first) continue;      // published before the previous head's epilogue
+          build_unit(g, a);
+        }
+        // the next head's first unit goes out BEFORE this head's epilogue: the issuer starts it as soon as the
+        // accumulator has been read (oempty), instead of idling through the epilogue arithmetic and stores
+        if (gp + 1 < NH / 2) build_unit(g + 2, a_first);
+        // ---- head epilogue: O (fp32, TMEM) + mixed bos probability x bos value -> bf16 -> global ----
+        float pbos = 0.f;
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) pbos = fmaf(Wsm[g * NH + hh], pbos_s[hh * 128 + qrow], pbos);
+        mbar_wait(&ofull[wg], ou & 1);
+        tc_fence_after();
+        uint32_t ov[64];
+        tmem_ld_x64(tlane + T_O + wg * DH, ov);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&oempty[wg]);
+        ++ou;
+        if (qok) {
+          bf16* dst = p.o + (long long)t.b * p.o_bs + (long long)(1 + vpos) * p.o_rs + g * DH;
+#pragma unroll
+          for (int c8i = 0; c8i < 8; ++c8i) {
+            const uint4 vb4 = *reinterpret_cast<const uint4*>(vbos + g * DH + c8i * 8);
+            const uint32_t vbw[4] = {vb4.x, vb4.y, vb4.z, vb4.w};
+            uint32_t outw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 vbf = unpack_bf16x2(vbw[e]);
+              outw[e] = pack_bf16x2(fmaf(pbos, vbf.x, __uint_as_float(ov[c8i * 8 + 2 * e])),
+                                    fmaf(pbos, vbf.y, __uint_as_float(ov[c8i * 8 + 2 * e + 1])));
+            }
+            *reinterpret_cast<uint4*>(dst + c8i * 8) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+          }
+        }
+        if (dbg) dst_dbg[7 + gp] = clock64();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+long long* g_umma_dbg = nullptr;
+
+}  // namespace
+
+// measurement aid (tools/umma_stamps.py; not part of include/nuwa_b200.h): 64 int64 of device memory or NULL
+extern "C" void nuwa_debug_umma_stamps(long long* dev_ptr) { g_umma_dbg = dev_ptr; }
+
+// Envelope: full pass (t0 == 0, nq == nv + 1) over a 16-wide token grid, H == 8, dh == 64, kw == 3, kh <= 3, kt <= 5,
+// column dilation 1 / 2 / 4, q|k|v rows sharing one token stride; causal or centred windows.  NUWA_ERR_INVALID outside
+// it (nothing launched; the caller falls back to the halo / gather kernels).
+int attn_3dna_umma(const AttnParams& p, cudaStream_t stream) {
+  if (p.fmap != GW || p.t0 != 0 || p.t0_ptr != nullptr) return NUWA_ERR_INVALID;
+  if (p.H != NH || p.dh != DH || p.nq != p.nv + 1 || p.nv <= 0 || p.B <= 0) return NUWA_ERR_INVALID;
+  if (p.kw != KW || p.kh < 1 || p.kh > MAXKH || p.kt < 1 || p.kt > MAXKT) return NUWA_ERR_INVALID;
+  if (p.dt <= 0 || p.dh_ <= 0 || !(p.dw == 1 || p.dw == 2 || p.dw == 4)) return NUWA_ERR_INVALID;
+  if (!(p.kh & 1) || !(p.kt & 1)) return NUWA_ERR_INVALID;  // odd kernels (nuwa_pytorch.py:410)
+  if (p.max_frames <= 0 || p.nv > p.max_frames * GW * GW) return NUWA_ERR_INVALID;
+  if (p.head_scale != nullptr || p.bias != nullptr || p.key_mask != nullptr || p.null_k != nullptr) return NUWA_ERR_INVALID;
+  const bf16* q = reinterpret_cast<const bf16*>(p.q);
+  const bf16* k = reinterpret_cast<const bf16*>(p.k);
+  const bf16* v = reinterpret_cast<const bf16*>(p.v);
+  const long long koff = k - q, voff = v - q;
+  if (p.k_rs != p.q_rs || p.v_rs != p.q_rs || p.k_bs != p.q_bs || p.v_bs != p.q_bs) return NUWA_ERR_INVALID;
+  if (koff < 0 || voff < 0 || koff + INNER > p.q_rs || voff + INNER > p.q_rs) return NUWA_ERR_INVALID;
+  if ((p.q_rs % 8) || (p.q_bs % 8) || (koff % 8) || (voff % 8) || (p.o_rs % 8) || (p.o_bs % 8)) return NUWA_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(p.q) & 15) || (reinterpret_cast<uintptr_t>(p.o) & 15)) return NUWA_ERR_INVALID;
+
+  CUtensorMap map, map8, map4, map2;
+  const uint64_t dims[3] = {(uint64_t)p.q_rs, (uint64_t)(p.nv + 1), (uint64_t)p.B};
+  const uint64_t strides[3] = {2, (uint64_t)p.q_rs * 2, (uint64_t)p.q_bs * 2};
+  const uint32_t box[3] = {DH, GW, 1};
+  int rc = encode_map_bf16_sw128(&map, p.q, 3, dims, strides, box);
+  if (rc != NUWA_OK) return rc;
+  // 5-D view of the complete grid rows (16 tokens each, starting at sequence row 1): row R = yhi * dh + ylo, so that a box
+  // of n consecutive yhi is n key rows spaced by the row dilation.  Only when dh divides the grid height.
+  int rows5d = 0;
+  if (GW % p.dh_ == 0) {
+    const int full_rows = p.nv / GW;
+    rows5d = (full_rows / p.dh_) * p.dh_;
+  }
+  map8 = map4 = map2 = map;
+  if (rows5d > 0) {
+    const uint64_t d5[5] = {(uint64_t)p.q_rs, (uint64_t)GW, (uint64_t)p.dh_, (uint64_t)(rows5d / p.dh_), (uint64_t)p.B};
+    const uint64_t s5[5] = {2, (uint64_t)p.q_rs * 2, (uint64_t)GW * p.q_rs * 2, (uint64_t)p.dh_ * GW * p.q_rs * 2,
+                            (uint64_t)p.q_bs * 2};
+    const void* base1 = q + p.q_rs;  // sequence row 1 = video token 0
+    const uint32_t b8[5] = {DH, GW, 1, 8, 1}, b4[5] = {DH, GW, 1, 4, 1}, b2[5] = {DH, GW, 1, 2, 1};
+    if ((rc = encode_map_bf16_sw128(&map8, base1, 5, d5, s5, b8)) != NUWA_OK) return rc;
+    if ((rc = encode_map_bf16_sw128(&map4, base1, 5, d5, s5, b4)) != NUWA_OK) return rc;
+    if ((rc = encode_map_bf16_sw128(&map2, base1, 5, d5, s5, b2)) != NUWA_OK) return rc;
+  }
+
+  UmmaArgs a;
+  a.B = p.B; a.nv = p.nv;
+  a.nf = (p.nv + GW * GW - 1) / (GW * GW);
+  a.maxf = p.max_frames;
+  if (p.dh_ >= 4) {
+    a.tpf = (min(p.dh_, GW) + 1) / 2;
+  } else {
+    int tiles = 0;
+    for (int r = 0; r < p.dh_; ++r) tiles += ((GW - r + p.dh_ - 1) / p.dh_ + 7) / 8;
+    a.tpf = tiles;
+  }
+  a.ntiles = a.nf * a.tpf * a.B;
+  a.kt = p.kt; a.kh = p.kh; a.dt = p.dt; a.dh = p.dh_; a.dw = p.dw; a.causal = p.causal;
+  a.koff = (int)koff; a.voff = (int)voff;
+  a.rows5d = rows5d;
+  a.scale_log2e = p.qscale * 1.4426950408889634f;
+  a.talk = p.talk;
+  a.o = reinterpret_cast<bf16*>(p.o); a.o_bs = p.o_bs; a.o_rs = p.o_rs;
+  a.k0 = k; a.v0 = v; a.k_bs = p.k_bs; a.v_bs = p.v_bs;
+  a.dbg = g_umma_dbg;
+
+  const int grid = min(a.ntiles, device_sm_count());
+  auto launch = [&](void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const UmmaArgs)) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return NUWA_ERR_CUDA;
+    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(map, map8, map4, map2, a);
+    return NUWA_OK;
+  };
+  int lrc;
+  if (p.dw == 1) lrc = launch(attn_3dna_umma_kernel<1>);
+  else if (p.dw == 2) lrc = launch(attn_3dna_umma_kernel<2>);
+  else lrc = launch(attn_3dna_umma_kernel<4>);
+  if (lrc != NUWA_OK) return lrc;
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+
+}  // namespace nuwa

@@ -509,16 +509,17 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// rank-2..4 bf16 tensor map, innermost box 64 elements (128 B), SWIZZLE_128B, zero OOB fill.
+// rank-2..5 bf16 tensor map, innermost box 64 elements (128 B), SWIZZLE_128B, zero OOB fill.
 static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                       CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return NUWA_ERR_DRIVER;
-  cuuint64_t gdims[4];
-  cuuint64_t gstr[3];
-  cuuint32_t gbox[4];
-  cuuint32_t estr[4];
+  cuuint64_t gdims[5];
+  cuuint64_t gstr[4];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  if (rank < 2 || rank > 5) return NUWA_ERR_INVALID;
   for (int i = 0; i < rank; ++i) {
     gdims[i] = dims[i];
     gbox[i] = box[i];

@@ -59,6 +59,7 @@ double gemm_prof_bytes();
 int attn_sparse3dna(const AttnParams& p, cudaStream_t s);
 int attn_dense(const AttnParams& p, cudaStream_t s);
 int attn_3dna_halo(const AttnParams& p, cudaStream_t stream);           // attention_3dna_halo.cu
+int attn_3dna_umma(const AttnParams& p, cudaStream_t stream);           // attention_3dna_umma.cu
 int attn_dense_mma(const AttnParams& p, int nk, void* vT_ws, cudaStream_t stream);  // attention_mma.cu
 int attn_dense_x64(const AttnParams& p, int nk, cudaStream_t stream);                // attention_x64.cu
 int attn_dense_pres(const AttnParams& p, int nk, cudaStream_t stream);               // attention_dense_pres.cu

@@ -148,14 +148,19 @@ def _attn_base(q, k, v, o, B, nq, t0, H, dh, q_bs, k_bs, v_bs, o_bs, q_rs, k_rs,
     return p
 
 
+# order in which 'auto' tries the tensor-core Sparse3DNA kernels (each declines calls outside its envelope): the tcgen05
+# kernel first (causal and centred windows), then the mma.sync halo kernel (causal only), then the gather kernel
+PREFER_3DNA = ('umma', 'halo')
+
+
 def attn_sparse3dna(qkv, o, *, B, nq, t0, npos, H, dh, talk, fmap, max_frames, nv, kernel, dilation, causal,
-                    o_bs=None, use_tc=False, variant='auto'):
+                    o_bs=None, variant='auto'):
     """qkv: bf16 buffer (B, npos, 3*H*dh) holding q|k|v rows for positions [0, npos); queries are positions
     [t0, t0+nq).  o: bf16 (B, nq, H*dh).  nv = number of video tokens present (positions 1..nv).
-    variant: 'auto' = the halo-tiled TMA + tensor-core kernel (attention_3dna_halo.cu) when the call is inside its
-    envelope (causal full pass, 16-wide grid, 8 x 64 heads), else the gather kernel; 'gather' / 'halo' pin one
-    (a pinned 'halo' outside the envelope raises).  use_tc selects the older row-per-warp tensor-core kernel
-    (attention_3dna_tc.cu; slower than both, kept for comparison)."""
+    variant: 'auto' = the tcgen05 / TMEM kernel (attention_3dna_umma.cu) when the call is inside its envelope (full pass,
+    16-wide grid, 8 x 64 heads, kw == 3, causal or centred), else the halo-tiled mma.sync kernel
+    (attention_3dna_halo.cu, causal only), else the gather kernel; 'umma' / 'halo' / 'gather' pin one (a pinned kernel
+    outside its envelope raises)."""
     inner = H * dh
     esz = 2
     base = qkv.data_ptr()
@@ -167,16 +172,15 @@ def attn_sparse3dna(qkv, o, *, B, nq, t0, npos, H, dh, talk, fmap, max_frames, n
     p.dt, p.dh_, p.dw = dilation
     p.causal = int(bool(causal))
     p.jmax = 1 + kernel[0] * kernel[1] * kernel[2]
-    if variant in ('auto', 'halo') and not use_tc:
-        rc = lib().nuwa_attn_sparse3dna_halo(p, stream())
+    order = {'auto': PREFER_3DNA, 'umma': ('umma',), 'halo': ('halo',), 'gather': ()}[variant]
+    for name in order:
+        fn = lib().nuwa_attn_sparse3dna_umma if name == 'umma' else lib().nuwa_attn_sparse3dna_halo
+        rc = fn(p, stream())
         if rc == 0:
             return
-        if variant == 'halo' or rc != _lib.NUWA_ERR_INVALID:
-            check(rc, "nuwa_attn_sparse3dna_halo")
-    ws = None
-    if use_tc and causal and fmap == 16 and t0 == 0 and nq == nv + 1 and dh in (32, 64) and H <= 8:
-        ws = torch.empty(B * H * dh * _round_up(nv, 16), dtype=torch.bfloat16, device=qkv.device)
-    check(lib().nuwa_attn_sparse3dna(p, ptr(ws), stream()), "nuwa_attn_sparse3dna")
+        if variant == name or rc != _lib.NUWA_ERR_INVALID:
+            check(rc, "nuwa_attn_sparse3dna_" + name)
+    check(lib().nuwa_attn_sparse3dna(p, None, stream()), "nuwa_attn_sparse3dna")
 
 
 def attn_sparse3dna_decode(q_row, cache, o, t_dev, *, B, npos, H, dh, talk, fmap, max_frames, kernel, dilation, causal):

@@ -193,8 +193,19 @@ def test_attn_sparse3dna_core(cuda_device, causal, kernel, dil, n, geom):
     attn = O._talking_heads(sim.softmax(-1), talk[:, :, None, None])
     out = torch.cat([vh[:, :, :1], torch.einsum('bhij,bhijd->bhid', attn, vg)], dim=2)
     ref = O._merge(out)
-    # output rounded to bf16 once; the halo kernel also rounds the mixed probabilities to bf16 for the tensor-core PV
-    assert rel(o.float(), ref) < (4e-3 if geom is None else 6e-3)
+    # output rounded to bf16 once; the tensor-core kernels also round the mixed probabilities to bf16 for P'V
+    r = rel(o.float(), ref)
+    print(f"  3dna core causal={causal} k={kernel} d={dil} n={n}: rel {r:.2e} (auto variant)")
+    assert r < (4e-3 if geom is None else 3e-3)
+    if geom is not None:   # the same case on each tensor-core kernel explicitly
+        for variant in ('umma', 'halo'):
+            o2 = torch.empty_like(o)
+            ops.attn_sparse3dna(qkv.to(cuda_device), o2, B=B, nq=n, t0=0, npos=n, H=H, dh=dh, talk=talk.to(cuda_device),
+                                fmap=fmap, max_frames=maxf, nv=n - 1, kernel=kernel, dilation=(dil,) * 3, causal=causal,
+                                variant=variant)
+            r2 = rel(o2.float(), ref)
+            print(f"    {variant}: rel {r2:.2e}")
+            assert r2 < 3e-3
 
 
 def test_attn_dense_core(cuda_device):

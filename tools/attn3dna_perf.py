@@ -1,5 +1,5 @@
 """Sparse3DNA attention core at the cfg-3 shape (batch 8, 2560 video tokens, 8 heads x 64, kernel (5,3,3)):
-generic gather kernel vs the tensor-core banded-block kernel, per dilation.  CUDA events, L2 flushed."""
+gather kernel vs the halo-tiled mma.sync kernel vs the tcgen05 / TMEM kernel, per dilation.  CUDA events, L2 flushed."""
 import json
 import sys
 
@@ -10,7 +10,7 @@ from nuwa_pytorch_b200 import ops  # noqa: E402
 
 dev = torch.device('cuda')
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-B, H, dh, nv = 8, 8, 64, 2560
+B, H, dh, nv = 8, 8, 64, 2559
 inner = H * dh
 n = nv + 1
 qkv = torch.randn(B, n, 3 * inner, device=dev).bfloat16()
@@ -18,11 +18,10 @@ talk = torch.randn(H, H, device=dev) / 2
 o = torch.empty(B, n, inner, dtype=torch.bfloat16, device=dev)
 rows = []
 for dil in (1, 2, 4):
-    for name in (sys.argv[1:] or ['gather', 'tensor-core', 'halo']):
+    for name in (sys.argv[1:] or ['gather', 'halo', 'umma']):
         def run():
             ops.attn_sparse3dna(qkv, o, B=B, nq=n, t0=0, npos=n, H=H, dh=dh, talk=talk, fmap=16, max_frames=10, nv=nv,
-                                kernel=(5, 3, 3), dilation=(dil,) * 3, causal=True, use_tc=name == 'tensor-core',
-                                variant='halo' if name == 'halo' else 'gather')
+                                kernel=(5, 3, 3), dilation=(dil,) * 3, causal=True, variant=name)
         for _ in range(2):
             run()
         ts = []
