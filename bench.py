@@ -314,12 +314,15 @@ def attention_kernel_rooflines(dev, pk):
 
     out = dict(sparse3dna=[], cross=None)
     for dil in (1, 2, 4):
-        us = med_us(lambda: ops.attn_sparse3dna(qkv, o, B=B, nq=n, t0=0, npos=n, H=H, dh=dh, talk=talk, fmap=16, max_frames=10,
-                                                nv=nv, kernel=(5, 3, 3), dilation=(dil,) * 3, causal=True))
-        gbs = B * nv * 4096 / (us * 1e-6) / 1e9
-        out["sparse3dna"].append(dict(dilation=dil, us_per_launch=round(us, 1), bound="hbm", achieved=round(gbs, 1),
-                                      peak=pk["hbm_gbs"], unit="GB/s", frac=round(gbs / pk["hbm_gbs"], 4),
-                                      algorithmic_bytes_per_token=4096, kernel="attn_3dna_halo_kernel"))
+        for variant, kname in (("halo", "attn_3dna_halo_kernel (mma.sync; 'auto' choice for causal passes)"),
+                               ("umma", "attn_3dna_umma_kernel (tcgen05 / TMEM)")):
+            us = med_us(lambda: ops.attn_sparse3dna(qkv, o, B=B, nq=n, t0=0, npos=n, H=H, dh=dh, talk=talk, fmap=16,
+                                                    max_frames=10, nv=nv, kernel=(5, 3, 3), dilation=(dil,) * 3, causal=True,
+                                                    variant=variant))
+            gbs = B * nv * 4096 / (us * 1e-6) / 1e9
+            out["sparse3dna"].append(dict(dilation=dil, us_per_launch=round(us, 1), bound="hbm", achieved=round(gbs, 1),
+                                          peak=pk["hbm_gbs"], unit="GB/s", frac=round(gbs / pk["hbm_gbs"], 4),
+                                          algorithmic_bytes_per_token=4096, kernel=kname))
     nq, nk = 2560, 256
     q = torch.randn(B, nq, inner, device=dev, generator=g).bfloat16()
     kv = torch.randn(B, nk, 2 * inner, device=dev, generator=g).bfloat16()

@@ -21,7 +21,7 @@
 //   phase 2   P'_g placed at its key position inside a dense 128 x 160 A operand that lives in TENSOR MEMORY
 //             (tcgen05.st; byte-permute placement, no shared-memory traffic), O_g += P'_g V_{g,a}: A from TMEM, B = the
 //             V key rows as MN-major operand, N=64; per head: + bos probability x bos value -> bf16 -> global
-// Warp roles: warp 0 = TMA producer, warps 2-5 / 6-9 = two warpgroups that own the even / odd heads, so extraction +
+// Warp roles: warps 0 / 11 = TMA producers (one per warpgroup), warps 2-5 / 6-9 = two warpgroups that own the even / odd heads, so extraction +
 // softmax of one head overlaps the UMMAs of the other; warp 1 / warp 10 = one MMA-issuing thread per warpgroup (a
 // tcgen05.mma costs its issuing thread ~70 cycles, the small UMMAs of this kernel are issue bound from one thread).
 // TMEM columns: P [0,184);  phase 1  S0 [192,352) S1 [352,512);  mix  D [192,512);  phase 2  A0 [192,272) A1 [272,352)
@@ -51,16 +51,16 @@ constexpr int NU = (MAXJ - 1 + 1) / 2;         // 23 slot pairs
 constexpr int NSC = 8 + MAXKH - 1;     // slot columns of a key tile (10)
 constexpr int BOX = GW * DH * 2;       // 2048 B: 16 tokens x 64 channels of one head
 constexpr int KV_STAGE = NSC * BOX;    // 20 KB
-constexpr int NST = 5;
+constexpr int NST = 4;
 constexpr int Q_BYTES = 8 * BOX;       // 16 KB
-constexpr int SPITCH = 50;             // fp32 score row pitch (words)
+constexpr int DPITCH = 272;            // bytes per thread row of the window dump: 64 fp32 + a -FLT_MAX sentinel, 16-B aligned
 
 constexpr int OFF_KV = 0;
 constexpr int OFF_Q = OFF_KV + NST * KV_STAGE;            // 4 buffers: (head pair parity, warpgroup)
 constexpr int OFF_KBOS = OFF_Q + 4 * Q_BYTES;             // [8 heads][64] fp32: bos key rows of the tile's sample
 constexpr int OFF_WB = OFF_KBOS + NH * DH * 4;            // talking-heads B operands: [hi, lo] x [16 rows x 128 B]
-constexpr int OFF_SC = OFF_WB + 2 * BOX;                  // 2 warpgroups x [128][SPITCH] fp32
-constexpr int OFF_VBOS = OFF_SC + 2 * 128 * SPITCH * 4;   // [8][64] bf16
+constexpr int OFF_SC = OFF_WB + 2 * BOX;                  // 2 warpgroups x [128] window dump rows (thread private)
+constexpr int OFF_VBOS = OFF_SC + 2 * 128 * DPITCH;       // [8][64] bf16
 constexpr int OFF_PBOS = OFF_VBOS + INNER * 2;            // [8][128] fp32: probability of the bos slot
 constexpr int OFF_W = OFF_PBOS + NH * 128 * 4;            // [8][8] fp32
 constexpr int OFF_BAR = OFF_W + NH * NH * 4;
@@ -69,7 +69,7 @@ constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
 
 constexpr int T_P = 0, T_S = 192, T_D = 192, T_A = 192, T_O = 352;
-constexpr int THREADS = 352;   // warp 0 producer, warp 1 / warp 10 MMA issuers of warpgroup 0 / 1, warps 2-9 warpgroups
+constexpr int THREADS = 384;   // warps 0 / 11: TMA producers, warps 1 / 10: MMA issuers of warpgroup 0 / 1, warps 2-9: warpgroups
 
 struct UmmaArgs {
   int B, nv, nf, maxf, tpf, ntiles;    // nf = frames present, tpf = tiles per frame
@@ -184,22 +184,6 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return r;
 }
 
-// Column j of a thread's 64-column window (slot column j >> 4, key column j & 15) goes to word KW * (j >> 4) +
-// (j & 15) / DW of its compact score row if bit j of the in-band mask is set: one bit test + one predicated store with an
-// immediate offset per column (true predication -- a C++ `if` around the store compiles to a divergent branch per column).
-template <int DW, int J>
-__device__ __forceinline__ void store_col(uint32_t tb, uint32_t val, uint32_t maskword) {
-  asm volatile(
-      "{\n .reg .pred p;\n .reg .b32 t;\n and.b32 t, %2, %3;\n setp.ne.b32 p, t, 0;\n @p st.shared.b32 [%0+%4], %1;\n}\n"
-      ::"r"(tb), "r"(val), "r"(maskword), "n"(1u << (J & 31)), "n"(4 * (KW * (J >> 4) + (J & 15) / DW))
-      : "memory");
-}
-template <int DW, int... Js>
-__device__ __forceinline__ void store_band(uint32_t tb, const uint32_t (&v)[64], const uint32_t (&xm)[2],
-                                           std::integer_sequence<int, Js...>) {
-  (store_col<DW, Js>(tb, v[Js], xm[Js >> 5]), ...);
-}
-
 // key / query rows y0 + i * dh (i < n) of frame f, channels [chan, chan + 64) -> dst + i * BOX.  Rows reachable through
 // the 5-D view travel as boxes of 8 / 4 / 2 rows (one TMA instruction each); the ragged end of the sequence and
 // dilations that do not divide the grid height use one 16-token box per row on the flat view (zero fill past the end).
@@ -290,12 +274,12 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
 
   const int Ah = p.causal ? p.kh - 1 : (p.kh - 1) / 2;
   const int At = p.causal ? p.kt - 1 : (p.kt - 1) / 2;
-  const int KHW = p.kh * KW;
 
-  if (warp == 0) {
-    // =========================================== TMA producer ===========================================
+  if (warp == 0 || warp == 11) {
+    // ============ TMA producer of warpgroup w: its Q tiles and every second ring slot (its K / V tiles) ============
     if (lane == 0) {
-      uint32_t it = 0, qu[4] = {0, 0, 0, 0};
+      const int w = warp == 0 ? 0 : 1;
+      uint32_t it = (uint32_t)w, qu[2] = {0, 0};
       for (int k = 0;; ++k) {
         const int s = snake(k, cta, G);
         if (s >= p.ntiles) break;
@@ -320,43 +304,62 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
         }
         const uint32_t qbytes = (uint32_t)(qn[0] + qn[1]) * BOX;
         const uint32_t kbytes = (uint32_t)(kn[0] + kn[1]) * BOX;
+        // fast path of the key tiles (every row reachable through the 5-D view): run c = box of 8 rows + box of 2 / 4
+        // rows, coordinates precomputed up to the frame term
+        const int rpf = p.rows5d > 0 ? GW / p.dh : 0;                  // 5-D row-block coordinate advance per frame
+        int k_ylo[2], k_yhi[2], k_last[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          k_ylo[c] = p.rows5d > 0 ? ky[c] % p.dh : 0;
+          k_yhi[c] = p.rows5d > 0 ? ky[c] / p.dh : 0;
+          k_last[c] = ky[c] + (kn[c] - 1) * p.dh;                       // last row inside its frame
+        }
         auto load_q = [&](int hp) {
-          for (int w = 0; w < 2; ++w) {
-            const int h = 2 * hp + w, qb = 2 * (hp & 1) + w;
-            mbar_wait(&qempty[qb], (qu[qb] & 1) ^ 1);
-            mbar_arrive_expect_tx(&qfull[qb], qbytes);
-            for (int c = 0; c < 2; ++c)
-              if (qn[c] > 0)
-                load_rows(sm_u + OFF_Q + qb * Q_BYTES + 4 * c * BOX, &qfull[qb], &qmap, &map8, &map4, &map2, p, h * DH, t.f,
-                          qy[c], qn[c], t.b);
-            ++qu[qb];
-          }
+          const int h = 2 * hp + w, qb = 2 * (hp & 1) + w;
+          mbar_wait(&qempty[qb], (qu[hp & 1] & 1) ^ 1);
+          mbar_arrive_expect_tx(&qfull[qb], qbytes);
+          for (int c = 0; c < 2; ++c)
+            if (qn[c] > 0)
+              load_rows(sm_u + OFF_Q + qb * Q_BYTES + 4 * c * BOX, &qfull[qb], &qmap, &map8, &map4, &map2, p, h * DH, t.f,
+                        qy[c], qn[c], t.b);
+          ++qu[hp & 1];
         };
         load_q(0);
         for (int ph = 0; ph < 2; ++ph) {
           for (int hp = 0; hp < NH / 2; ++hp) {
-            if (ph == 0 && hp + 1 < NH / 2) load_q(hp + 1);   // one head pair ahead: no bubble at the head boundary
+            const int chan = (ph ? p.voff : p.koff) + (2 * hp + w) * DH;
             for (int a = 0; a < p.kt; ++a) {
               if (!((t.real_mask >> a) & 1)) continue;
               const int ff = t.f + (a - At) * p.dt;
-              for (int w = 0; w < 2; ++w) {
-                const int h = 2 * hp + w;
-                const int st = it % NST;
-                mbar_wait(&empty[st], ((it / NST) & 1) ^ 1);
-                mbar_arrive_expect_tx(&full[st], kbytes);
-                const int chan = (ph ? p.voff : p.koff) + h * DH;
-                for (int c = 0; c < 2; ++c)
-                  if (kn[c] > 0)
-                    load_rows(sm_u + OFF_KV + st * KV_STAGE + ksc[c] * BOX, &full[st], &qmap, &map8, &map4, &map2, p, chan, ff,
-                              ky[c], kn[c], t.b);
-                ++it;
+              const int st = it % NST;
+              const uint32_t dst = sm_u + OFF_KV + st * KV_STAGE;
+              mbar_wait(&empty[st], ((it / NST) & 1) ^ 1);
+              mbar_arrive_expect_tx(&full[st], kbytes);
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                if (kn[c] <= 0) continue;
+                const uint32_t d = dst + ksc[c] * BOX;
+                if (ff * GW + k_last[c] < p.rows5d && (kn[c] == 10 || kn[c] == 8 || kn[c] == 4)) {
+                  const int yhi = ff * rpf + k_yhi[c];
+                  if (kn[c] == 4) {
+                    tma_load_5d(d, &map4, &full[st], chan, 0, k_ylo[c], yhi, t.b);
+                  } else {
+                    tma_load_5d(d, &map8, &full[st], chan, 0, k_ylo[c], yhi, t.b);
+                    if (kn[c] == 10) tma_load_5d(d + 8 * BOX, &map2, &full[st], chan, 0, k_ylo[c], yhi + 8, t.b);
+                  }
+                } else {
+                  load_rows(d, &full[st], &qmap, &map8, &map4, &map2, p, chan, ff, ky[c], kn[c], t.b);
+                }
               }
+              it += 2;
             }
+            // the next head pair's Q tile goes out behind this pair's key tiles: its buffer was released a whole
+            // head pair ago, and it lands long before the issuer gets there
+            if (ph == 0 && hp + 1 < NH / 2) load_q(hp + 1);
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1 || warp == 10) {
     // ====================== MMA issuer of warpgroup w (w = 0 also issues the talking-heads UMMAs) ======================
     if (lane == 0) {
@@ -388,10 +391,8 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
             const uint32_t d = d_s + t.sc_lo * 16;
             const bool md = p.dbg != nullptr && cta == 0 && k == 0 && w == 0 && su < 24;
             if (md) p.dbg[320 + 4 * su] = clock64();
-            mbar_wait(&sempty[w], (su & 1) ^ 1);
-            if (md) p.dbg[320 + 4 * su + 1] = clock64();
-            mbar_wait(&full[st], (it / NST) & 1);
-            if (md) p.dbg[320 + 4 * su + 2] = clock64();
+            mbar_wait2(&full[st], (it / NST) & 1, &sempty[w], (su & 1) ^ 1);
+            if (md) { p.dbg[320 + 4 * su + 1] = clock64(); p.dbg[320 + 4 * su + 2] = p.dbg[320 + 4 * su + 1]; }
             tc_fence_after();
             umma_bf16(d, qdesc, kdesc, idesc_qk, 0u);
             umma_bf16(d, qdesc + 2, kdesc + 2, idesc_qk, 1u);
@@ -430,11 +431,9 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
             const uint64_t vdesc = make_sw128_kmajor_desc(sm_u + OFF_KV + st * KV_STAGE);
             const bool md = p.dbg != nullptr && cta == 0 && k == 0 && w == 0 && au < 24;
             if (md) p.dbg[192 + 4 * au] = clock64();
-            mbar_wait(&full[st], (it / NST) & 1);
-            if (md) p.dbg[192 + 4 * au + 1] = clock64();
             if (seen == 1) mbar_wait(&oempty[w], (ou & 1) ^ 1);
-            mbar_wait(&afull[w], au & 1);
-            if (md) p.dbg[192 + 4 * au + 2] = clock64();
+            mbar_wait2(&full[st], (it / NST) & 1, &afull[w], au & 1);
+            if (md) { p.dbg[192 + 4 * au + 1] = clock64(); p.dbg[192 + 4 * au + 2] = p.dbg[192 + 4 * au + 1]; }
             tc_fence_after();
 #pragma unroll
             for (int sc = 0; sc < NSC; ++sc)
@@ -461,8 +460,8 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
     const int r = ti & 1;                        // row inside the warp's pair
     const int wq = quarter;                      // window index: slot columns [2*wq, 2*wq + 4)
     const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
-    float* srow = reinterpret_cast<float*>(sm + OFF_SC) + (size_t)(wg * 128 + qrow) * SPITCH;
-    const uint32_t srow_u = smem_u32(srow);
+    const uint32_t drow_u = sm_u + OFF_SC + (uint32_t)(wg * 128 + qrow) * DPITCH;   // this thread's window dump row
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(drow_u + 256), "f"(-FLT_MAX) : "memory");  // sentinel for masked slots
     const float* Wsm = reinterpret_cast<const float*>(sm + OFF_W);
     const bf16* vbos = reinterpret_cast<const bf16*>(sm + OFF_VBOS);
     float* pbos_s = reinterpret_cast<float*>(sm + OFF_PBOS);
@@ -503,18 +502,20 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
         if (t.two) { const int sl = sc - Ah; ok = ok && sl >= 0 && (sl >> 2) == (ti >> 2); }
         vb |= (ok ? 1u : 0u) << b;
       }
-      uint32_t xm[2] = {0u, 0u};
+      // byte offsets, inside the dump row, of the 9 window entries (kernel row b, kernel column c) of this thread: window
+      // column 16 * (r + b) + x + (c - Aw) * dw; masked entries point at the -FLT_MAX sentinel.  The same for every unit.
+      uint32_t goff[MAXKH * KW];
+      uint32_t valid9 = 0;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const int b = (j >> 4) - r, jj = j & 15;
-        const int d = jj - x;
-        const bool inb = b >= 0 && b < MAXKH && ((vb >> (b < 0 ? 0 : (b > 2 ? 2 : b))) & 1u) && (d % DW == 0) &&
-                         (d / DW + Aw >= 0) && (d / DW + Aw < KW);
-        xm[j >> 5] |= (inb ? 1u : 0u) << (j & 31);
-      }
+      for (int b = 0; b < MAXKH; ++b)
+#pragma unroll
+        for (int c = 0; c < KW; ++c) {
+          const bool ok = ((vb >> b) & 1u) && vc[c];
+          goff[b * KW + c] = ok ? 4u * (uint32_t)(16 * (r + b) + x + (c - Aw) * p.dw) : 256u;
+          valid9 |= (ok ? 1u : 0u) << (b * KW + c);
+        }
       // ---- tile start: everyone has left the previous tile (its bos rows / TMEM are free), then stage this one ----
       named_bar_sync(1, 256);
-      for (int j = 0; j < SPITCH; ++j) srow[j] = -FLT_MAX;
       if (wg == 0) {
         if (qrow < 64) {  // k_bos: 8 heads x 64 channels -> fp32 (read as broadcasts by the bos dot product)
           const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.k0 + (long long)t.b * p.k_bs) + qrow);
@@ -544,6 +545,7 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
       // ================= phase 1: band extraction + softmax =================
       for (int hp = 0; hp < NH / 2; ++hp) {
         const int h = 2 * hp + wg;
+        float sv[MAXJ + 1];   // scores, then probabilities, of this thread's query for head h: bos, then 9 per frame offset
         {  // bos key (slot 0): 64-term dot product of this thread's Q row (SWIZZLE_128B tile, as the UMMA reads it) with
            // k_bos[h]; runs while the first key tile of the head is still in flight
           const int qb = 2 * (hp & 1) + wg;
@@ -561,49 +563,45 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
             d4[0] = fmaf(a2.x, k1.x, d4[0]); d4[1] = fmaf(a2.y, k1.y, d4[1]);
             d4[2] = fmaf(a3.x, k1.z, d4[2]); d4[3] = fmaf(a3.y, k1.w, d4[3]);
           }
-          srow[0] = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+          sv[0] = (d4[0] + d4[1]) + (d4[2] + d4[3]);
           __syncwarp();
           if (lane == 0) mbar_arrive(&qempty[qb]);
           if (hp & 1) ++qu;
         }
-#pragma unroll 1
-        for (int a = 0; a < p.kt; ++a) {
-          if ((t.zero_mask >> a) & 1) {
+        // window slots: unit a fills sv[1 + 9a .. 9 + 9a] (kernel row b, column c at 3b + c; rows beyond kh stay masked)
+#pragma unroll
+        for (int a = 0; a < MAXKT; ++a) {
+          if (a < p.kt && ((t.real_mask >> a) & 1)) {
+            mbar_wait(&sfull[wg], su & 1);
+            tc_fence_after();
+            uint32_t v[64];
+            tmem_ld_x64(tlane + T_S + wg * 160 + wq * 32, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sempty[wg]);
+            ++su;
+            // dump the 64-column window to this thread's private row (16 vector stores), pick the 9 in-band entries back
+            // with their precomputed offsets: ~40 instructions per unit instead of a test + predicated store per column
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(drow_u + 16 * i), "r"(v[4 * i]), "r"(v[4 * i + 1]),
+                           "r"(v[4 * i + 2]), "r"(v[4 * i + 3]) : "memory");
+#pragma unroll
+            for (int e = 0; e < MAXKH * KW; ++e)
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sv[1 + 9 * a + e]) : "r"(drow_u + goff[e]) : "memory");
+          } else if (a < p.kt && ((t.zero_mask >> a) & 1)) {
             // in-volume key frame beyond the sequence: visible zero keys (score 0), SURVEY D16
 #pragma unroll
-            for (int b = 0; b < MAXKH; ++b)
+            for (int e = 0; e < MAXKH * KW; ++e) sv[1 + 9 * a + e] = ((valid9 >> e) & 1u) ? 0.f : -FLT_MAX;
+          } else {
 #pragma unroll
-              for (int c = 0; c < KW; ++c)
-                if (((vb >> b) & 1u) && vc[c]) srow[1 + a * KHW + b * KW + c] = 0.f;
-            continue;
+            for (int e = 0; e < MAXKH * KW; ++e) sv[1 + 9 * a + e] = -FLT_MAX;
           }
-          if (!((t.real_mask >> a) & 1)) continue;
-          const uint32_t tb = srow_u + 4u * (uint32_t)(1 + a * KHW - r * KW - x / DW + Aw);
-          const bool ud = dbg && warp == 2 && su < 24;
-          if (ud) p.dbg[416 + 4 * su] = clock64();
-          mbar_wait(&sfull[wg], su & 1);
-          if (ud) p.dbg[416 + 4 * su + 1] = clock64();
-          tc_fence_after();
-          uint32_t v[64];
-          tmem_ld_x64(tlane + T_S + wg * 160 + wq * 32, v);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sempty[wg]);
-          if (ud) p.dbg[416 + 4 * su + 2] = clock64();
-          ++su;
-          store_band<DW>(tb, v, xm, std::make_integer_sequence<int, 64>{});
-          if (ud) p.dbg[416 + 4 * (su - 1) + 3] = clock64();
         }
         // ---- softmax of this head's row (fp32): bos probability -> smem (fp32), window probabilities -> fp16 pairs in
-        //      TMEM, column 8u + h = slots (1 + 2u, 2 + 2u) ----
+        //      TMEM, column 8u + h = window entries (2u, 2u + 1) ----
         {
-          float sv[MAXJ + 1];
-#pragma unroll
-          for (int i = 0; i < MAXJ / 2; ++i) {
-            const float2 f2 = *reinterpret_cast<const float2*>(srow + 2 * i);
-            sv[2 * i] = f2.x; sv[2 * i + 1] = f2.y;
-          }
           sv[MAXJ] = -FLT_MAX;
           float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
 #pragma unroll
@@ -668,10 +666,10 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
       if (dbg) dst_dbg[6] = clock64();
 
       // ================= phase 2: dense A operand rows + head epilogues =================
-      // one unit: the 9 mixed probabilities of frame offset a (halves [a*KHW, a*KHW + 9) of head g: column 8u + g,
+      // one unit: the 9 mixed probabilities of frame offset a (halves [9a, 9a + 9) of head g: column 8u + g,
       // u = half / 2) -> this warp's 4-slot-column window of the dense A operand -> publish to the MMA issuer
       auto build_unit = [&](int g, int a) {
-        const int h0 = a * KHW;
+        const int h0 = a * 9;
         uint32_t c8[5];
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
@@ -689,9 +687,6 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
         PA[0] = pr[0];                       PB[0] = pr[1] & 0xffffu;
         PA[1] = prmt(pr[1], pr[2], 0x5432u); PB[1] = pr[2] >> 16;
         PA[2] = pr[3];                       PB[2] = pr[4] & 0xffffu;
-#pragma unroll
-        for (int b = 0; b < MAXKH; ++b)
-          if (b >= p.kh) { PA[b] = 0u; PB[b] = 0u; }   // rows beyond kh belong to the next unit
         uint32_t win[32];
 #pragma unroll
         for (int scw = 0; scw < 4; ++scw) {

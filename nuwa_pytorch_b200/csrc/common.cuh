@@ -121,6 +121,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait for two mbarriers at once: the two try_wait instructions of a round are independent, so their latencies overlap
+// (a completed-barrier try_wait still costs its issuer ~100-200 cycles; two waits in sequence cost twice that).
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+  const uint32_t aa = smem_u32(bar_a), ab = smem_u32(bar_b);
+  uint32_t da = 0, db = 0;
+  long long t0 = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        " .reg .pred p, q;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5;\n"
+        " selp.u32 %0, 1, 0, p;\n"
+        " selp.u32 %1, 1, 0, q;\n"
+        "}\n"
+        : "=r"(da), "=r"(db)
+        : "r"(aa), "r"(parity_a), "r"(ab), "r"(parity_b)
+        : "memory");
+    if (da & db) break;
+    if (++spins == 64) t0 = clock64();
+    if (spins > 64 && (clock64() - t0) > 8000000000LL) __trap();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), tiled mode, completion on an mbarrier
 // ---------------------------------------------------------------------------------------------

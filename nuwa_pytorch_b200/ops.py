@@ -148,19 +148,26 @@ def _attn_base(q, k, v, o, B, nq, t0, H, dh, q_bs, k_bs, v_bs, o_bs, q_rs, k_rs,
     return p
 
 
-# order in which 'auto' tries the tensor-core Sparse3DNA kernels (each declines calls outside its envelope): the tcgen05
-# kernel first (causal and centred windows), then the mma.sync halo kernel (causal only), then the gather kernel
-PREFER_3DNA = ('umma', 'halo')
+# Which Sparse3DNA kernel 'auto' tries first (each tensor-core kernel declines calls outside its envelope, the gather
+# kernel takes everything).  Measured at the cfg-3 / cfg-5 shapes (profiles/r02_attn3dna_perf*.json):
+#   causal full pass, B=8 x 2560 tokens:  halo (mma.sync) 61 / 57 / 49 us, umma (tcgen05) 66 / 64 / 59 us, gather 233 / 199 / 158
+#   centred (sketch encoder), 768 tokens:  B=32: umma 86 / 72 / 59 us vs gather 229 / 184 / 160;  B=4: 49 / 41 / 35 us both
+#   (24 tiles of 128 queries cannot fill 148 SMs; the gather kernel spreads over every SM)
+def _prefer_3dna(causal, B, nv):
+    if causal:
+        return ('halo', 'umma')
+    tiles = B * ((nv + 255) // 256) * 2
+    return ('umma',) if tiles >= 64 else ()
 
 
 def attn_sparse3dna(qkv, o, *, B, nq, t0, npos, H, dh, talk, fmap, max_frames, nv, kernel, dilation, causal,
                     o_bs=None, variant='auto'):
     """qkv: bf16 buffer (B, npos, 3*H*dh) holding q|k|v rows for positions [0, npos); queries are positions
     [t0, t0+nq).  o: bf16 (B, nq, H*dh).  nv = number of video tokens present (positions 1..nv).
-    variant: 'auto' = the tcgen05 / TMEM kernel (attention_3dna_umma.cu) when the call is inside its envelope (full pass,
-    16-wide grid, 8 x 64 heads, kw == 3, causal or centred), else the halo-tiled mma.sync kernel
-    (attention_3dna_halo.cu, causal only), else the gather kernel; 'umma' / 'halo' / 'gather' pin one (a pinned kernel
-    outside its envelope raises)."""
+    variant: 'auto' = the fastest measured kernel whose envelope holds the call (_prefer_3dna): the halo-tiled mma.sync
+    kernel (attention_3dna_halo.cu) for causal full passes, the tcgen05 / TMEM kernel (attention_3dna_umma.cu) for
+    centred windows with enough tiles to fill the chip and for causal shapes the halo kernel declines, else the gather
+    kernel; 'umma' / 'halo' / 'gather' pin one (a pinned kernel outside its envelope raises)."""
     inner = H * dh
     esz = 2
     base = qkv.data_ptr()
@@ -172,7 +179,7 @@ def attn_sparse3dna(qkv, o, *, B, nq, t0, npos, H, dh, talk, fmap, max_frames, n
     p.dt, p.dh_, p.dw = dilation
     p.causal = int(bool(causal))
     p.jmax = 1 + kernel[0] * kernel[1] * kernel[2]
-    order = {'auto': PREFER_3DNA, 'umma': ('umma',), 'halo': ('halo',), 'gather': ()}[variant]
+    order = {'auto': _prefer_3dna(causal, B, nv), 'umma': ('umma',), 'halo': ('halo',), 'gather': ()}[variant]
     for name in order:
         fn = lib().nuwa_attn_sparse3dna_umma if name == 'umma' else lib().nuwa_attn_sparse3dna_halo
         rc = fn(p, stream())
