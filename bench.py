@@ -526,9 +526,47 @@ def run_ours(args):
                                             algorithmic="3 x 104.4 MFLOP per token (forward + dgrad + wgrad) x 20480 tokens",
                                             peak_source=pk["source"] + ", sustained figure")
         decoder["config"]["backward"] = "see 'train' (same model and batch, loss.backward() included)"
+        # ---- the whole trainer step (reference NUWATrainer.train_step, train_nuwa.py:237-258: grad_accum_every = 8
+        # micro-batches -> [N>1: NCCL mean all-reduce overlapped with the last backward] -> clip 0.5 -> AdamW -> zero_grad)
+        # through nuwa_pytorch_b200.trainer.TrainStep, captured into ONE CUDA graph when the capture succeeds ----
+        try:
+            from nuwa_pytorch_b200.trainer import TrainStep
+            del tstepper
+            for p_ in tparams:
+                p_.grad = None
+            ACC = 8
+            trainer = TrainStep(nuwa, lr=3e-4, wd=0.01, grad_accum_every=ACC, max_grad_norm=0.5, dist=dist if world > 1 else None)
+            mb = [dict(text=torch.randint(1, 49408, (DEC_BATCH, 256), device=dev, generator=gt),
+                       video=torch.randint(0, 8192, (DEC_BATCH, 10, 16, 16), device=dev, generator=gt)) for _ in range(ACC)]
+            trainer.step(mb)
+            torch.cuda.synchronize()
+            tmode = "eager launches"
+            try:
+                trainer.capture(mb)
+                tmode = "one CUDA graph replay per trainer step (8 x (forward + backward), all-reduce, clip + AdamW inside)"
+            except Exception as e:
+                print(f"[bench] trainer step not captured ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
+                torch.cuda.synchronize()
+                trainer.graph = None
+            l_first = float(trainer.step(mb)[0])
+            trsec = timed(lambda: trainer.step(mb), args.steps, args.warmup, dist, None)
+            l_last = float(trainer.step(mb)[0])
+            ttok = ACC * ntok
+            decoder["trainer_step"] = dict(
+                metric="3DNA decoder video-tokens/sec through the whole trainer step (8 micro-batches, clip, AdamW)",
+                value=round(world * ttok * args.steps / trsec, 1), unit="tokens/s", ms_per_step=round(1e3 * trsec / args.steps, 3),
+                grad_accum_every=ACC, launch=tmode, loss_first=round(l_first, 4), loss_last=round(l_last, 4),
+                collective=None if world == 1 else "all_reduce(AVG) of the flat fp32 gradient buffer once per trainer step, "
+                                                   "issued per finished sub-block during the last micro-batch's backward",
+                reference="train_nuwa.py:237-258 + optimizer.py:11-31")
+            del trainer
+        except Exception as e:
+            print(f"[bench] trainer step failed ({type(e).__name__}: {e})", file=sys.stderr)
+            decoder["trainer_step"] = dict(error=f"{type(e).__name__}: {e}")
+            tstepper = None
         with torch.no_grad():
             decoder["kernel_rooflines"] = attention_kernel_rooflines(dev, pk)
-        del nuwa, tstepper
+        del nuwa
         torch.cuda.empty_cache()
 
         # ---- NUWASketch training step (BASELINE configs[4]): 12-layer 3DNA sketch encoder over 3 sketch frames, ----

@@ -53,6 +53,17 @@ class GradStore:
         return self.offsets[min(ids)], self.offsets[max(ids) + 1]
 
 
+def _grad_store_of(model, params):
+    """(store, persistent): the model's persistent gradient accumulator (set by trainer.TrainStep; every weight-gradient
+    kernel ADDS into the flat buffer, so micro-batches accumulate without a per-parameter add) or a fresh zeroed store."""
+    store = getattr(model, '_grad_store', None)
+    if store is not None:
+        assert len(store.params) == len(params) and all(a is b for a, b in zip(store.params, params)), \
+            'the persistent gradient store was built for a different parameter list'
+        return store, True
+    return GradStore(params), False
+
+
 def _bw(s):
     """Transposed bf16 weight copies for the dgrad GEMMs (built once per parameter allocation, cached on the SubBlock and
     refreshed in place by SubBlock.refresh() whenever the weights change)."""
@@ -339,7 +350,7 @@ class NuwaStep:
 
     def backward(self, gout, reducer=None):
         m = self.model
-        g = GradStore(self.params)
+        g, persistent = _grad_store_of(m, self.params)
         on_done = None
         if reducer is not None:
             reducer.begin(g.flat)
@@ -376,7 +387,9 @@ class NuwaStep:
         self.tape_dec = self.tape_text = None
         if reducer is not None:
             reducer.finish()
-        return g.grads()
+        # a persistent store already IS every parameter's .grad (trainer.TrainStep): the kernels accumulated into it in
+        # place, handing the same views back to autograd would add them onto themselves
+        return [None] * len(self.params) if persistent else g.grads()
 
 
 class _StepFn(torch.autograd.Function):
@@ -427,7 +440,7 @@ class SketchStep(NuwaStep):
 
     def backward(self, gout, reducer=None):
         m = self.model
-        g = GradStore(self.params)
+        g, persistent = _grad_store_of(m, self.params)
         on_done = None
         if reducer is not None:
             reducer.begin(g.flat)
@@ -464,7 +477,9 @@ class SketchStep(NuwaStep):
         self.tape_dec = self.tape_ctx = None
         if reducer is not None:
             reducer.finish()
-        return g.grads()
+        # a persistent store already IS every parameter's .grad (trainer.TrainStep): the kernels accumulated into it in
+        # place, handing the same views back to autograd would add them onto themselves
+        return [None] * len(self.params) if persistent else g.grads()
 
 
 def sketch_training_loss(model, sketch_indices, tok_mask_u8, frame_indices):
