@@ -493,11 +493,15 @@ def run_ours(args):
         l0 = _lib.launch_count()
         eager_step(text, video)
         tl = _lib.launch_count() - l0
-        if world == 1:
-            tstepper = GraphedTrainStep(loss_fn, tparams, text, video)
-            launch_mode = "one CUDA graph replay per step (forward + backward, GraphedTrainStep)"
-        else:
+        if world > 1:
             nuwa._grad_reducer = GradAllReduce(dist)  # the ONE collective: fp32 gradient all-reduce (mean) over NCCL
+        try:  # whole step in ONE CUDA graph; at N > 1 the per-sub-block NCCL all-reduces are captured inside it
+            tstepper = GraphedTrainStep(loss_fn, tparams, text, video)
+            launch_mode = "one CUDA graph replay per step (forward + backward" + (
+                ", overlapped NCCL all-reduce of the flat gradient buffer inside the graph" if world > 1 else "") + ")"
+        except Exception as e:
+            print(f"[bench] training step not captured ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
+            torch.cuda.synchronize()
             tstepper = eager_step
             launch_mode = "eager launches; per-sub-block NCCL all-reduce of the flat gradient buffer overlapping the backward"
 
@@ -604,12 +608,13 @@ def run_ours(args):
             sl = _lib.launch_count() - l0
             sk_mode = "eager launches" + ("" if world == 1 else " + overlapped NCCL gradient all-reduce")
             sk_runner = sk_step
-            if world == 1:  # whole step (both VAE encodes, forward, backward) as ONE CUDA graph, like the cfg-3 leg
+            if True:  # whole step (both VAE encodes, forward, backward [, NCCL all-reduce]) as ONE CUDA graph
                 try:
                     def sk_loss(s_, v_):
                         return sk(sketch=s_, sketch_mask=smask.clone(), video=v_, return_loss=True)
                     sk_runner = GraphedTrainStep(sk_loss, sparams, sketch, svideo)
-                    sk_mode = "one CUDA graph replay per step (VAE encodes + forward + backward, GraphedTrainStep)"
+                    sk_mode = "one CUDA graph replay per step (VAE encodes + forward + backward" + (
+                        ", NCCL all-reduce inside the graph" if world > 1 else "") + ", GraphedTrainStep)"
                 except Exception as e:  # capture is an optimisation of the launch path only
                     print(f"[bench] NUWASketch step not captured ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
                     torch.cuda.synchronize()
