@@ -382,12 +382,12 @@ def run_ours(args):
         step_dev()  # builds the packed bf16 weights (one-off) outside any timed region
         torch.cuda.synchronize()
         launches0 = _lib.launch_count()
-        _lib.gemm_prof_enable(True)
-        with ClockSampler(local) as clocks:
+        prof = _lib.GemmProfiler()
+        with prof, ClockSampler(local) as clocks:
             sec = timed(step_dev, args.steps, args.warmup, dist, None)
-        n_gemm, gemm_flops, gemm_ms = _lib.gemm_prof_collect()
-        gemm_alg_bytes = _lib.gemm_prof_bytes()
-        _lib.gemm_prof_enable(False)
+        n_gemm, gemm_flops, gemm_ms = prof.collect()
+        gemm_alg_bytes = prof.bytes()
+        prof.close()
         launches = _lib.launch_count() - launches0
         sec_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), dist, None)
     fps = world * B * args.steps / sec

@@ -35,14 +35,18 @@ unsigned long long nuwa_launch_count(void);
 /* sizeof(nuwa_ln_params), sizeof(nuwa_attn_params), sizeof(nuwa_embed_params) -- lets a binding verify its struct mirror */
 void nuwa_struct_sizes(int* out3);
 
-/* Measurement aid for bench.py's roofline: while enabled, every launch of the tcgen05 GEMM/conv kernel is
- * bracketed by CUDA events on its launch stream.  nuwa_gemm_prof_collect (call after synchronising) returns the
- * number of launches and their summed algorithmic FLOPs and device time, then resets the counters. */
-void nuwa_gemm_prof_enable(int on);
-int nuwa_gemm_prof_collect(double* flops, float* ms);
-/* algorithmic HBM bytes (every operand read once, every output written once) of the launches the last
- * nuwa_gemm_prof_collect summed up: the denominator for the ncu DRAM-traffic comparison in bench.py */
-double nuwa_gemm_prof_bytes(void);
+/* Measurement aid for bench.py's roofline.  A profiler is an object, not library state: open one, ATTACH it to the calling
+ * host thread, and every launch of the tcgen05 GEMM / conv kernel made by that thread is bracketed by CUDA events on its
+ * launch stream and counted.  nuwa_gemm_prof_collect (call after synchronising) returns the number of launches and their
+ * summed algorithmic FLOPs and device time, then resets the counters; nuwa_gemm_prof_bytes returns the algorithmic HBM
+ * bytes (every operand read once, every output written once) of the launches the last collect summed up -- the
+ * denominator for the ncu DRAM-traffic comparison.  Attach NULL to detach; close destroys the events.  Threads without an
+ * attached profiler record nothing, so the library holds no global mutable state. */
+void* nuwa_gemm_prof_open(void);
+void nuwa_gemm_prof_attach(void* prof);
+int nuwa_gemm_prof_collect(void* prof, double* flops, float* ms);
+double nuwa_gemm_prof_bytes(void* prof);
+void nuwa_gemm_prof_close(void* prof);
 
 /* ---- dense contraction (tcgen05) ------------------------------------------------------------
  * out[M,N] = act(A[M,K] @ W[N,K]^T + bias) + residual.   A, W bf16 with K contiguous.
@@ -153,6 +157,12 @@ int nuwa_attn_sparse3dna_halo(const nuwa_attn_params* p, void* stream);
  * dh == 64, kw == 3, kh <= 3, kt <= 5, column dilation 1 / 2 / 4, causal or centred window; NUWA_ERR_INVALID outside it
  * (nothing launched). */
 int nuwa_attn_sparse3dna_umma(const nuwa_attn_params* p, void* stream);
+/* SparseCross2DNA.forward non-bos queries, nuwa_pytorch.py:851-895, on the same tcgen05 / TMEM kernel: p->q / p->o point at
+ * the first non-bos query (t0 == 1), slot 0 = the learned null key / value (fp32), unit a = context frame a, centred
+ * ck x ck window with dilation cdil at the query's own grid position, context mask applied to the gathered scores.
+ * Envelope: 16-wide grid, H == 8, dh == 64, ck == 3, cdil 1 / 2 / 4, 1..5 context frames, k and v rows sharing one token
+ * stride; NUWA_ERR_INVALID outside it (nothing launched; nuwa_attn_cross2dna covers the rest). */
+int nuwa_attn_cross2dna_umma(const nuwa_attn_params* p, void* stream);
 /* Attention.forward core, nuwa_pytorch.py:339-378, and VQGanAttention core, vqgan_vae.py:275-282
  * (jmax = nk (+1 with a null key)) */
 int nuwa_attn_dense(const nuwa_attn_params* p, void* vt_workspace, void* stream);

@@ -105,9 +105,11 @@ SIGNATURES = {
     "nuwa_launch_count": [],
     "nuwa_strerror": [c_int],
     "nuwa_struct_sizes": [P(c_int)],
-    "nuwa_gemm_prof_enable": [c_int],
-    "nuwa_gemm_prof_collect": [P(ctypes.c_double), P(c_float)],
-    "nuwa_gemm_prof_bytes": [],
+    "nuwa_gemm_prof_open": [],
+    "nuwa_gemm_prof_attach": [c_void_p],
+    "nuwa_gemm_prof_collect": [c_void_p, P(ctypes.c_double), P(c_float)],
+    "nuwa_gemm_prof_bytes": [c_void_p],
+    "nuwa_gemm_prof_close": [c_void_p],
     "nuwa_gemm_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                        c_void_p, c_int, c_int, c_int, c_void_p],
     "nuwa_conv2d_nhwc_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
@@ -118,6 +120,7 @@ SIGNATURES = {
     "nuwa_attn_sparse3dna_halo": [P(AttnParams), c_void_p],
     "nuwa_attn_dense": [P(AttnParams), c_void_p, c_void_p],
     "nuwa_attn_sparse3dna_umma": [P(AttnParams), c_void_p],
+    "nuwa_attn_cross2dna_umma": [P(AttnParams), c_void_p],
     "nuwa_attn_dense_pres": [P(AttnParams), c_void_p],
     "nuwa_attn_cross2dna": [P(AttnParams), c_void_p],
     "nuwa_embed_tokens": [P(EmbedParams), c_void_p],
@@ -185,7 +188,7 @@ SIGNATURES = {
     "nuwa_struct_sizes_bwd": [P(c_int)],
 }
 _RESTYPES = {"nuwa_strerror": ctypes.c_char_p, "nuwa_vq_argmax_tc_workspace": ctypes.c_ulonglong, "nuwa_linear_f32x3_workspace": ctypes.c_ulonglong, "nuwa_gemm_prof_bytes": ctypes.c_double, "nuwa_launch_count": ctypes.c_ulonglong, "nuwa_struct_sizes": None,
-             "nuwa_gemm_prof_enable": None, "nuwa_struct_sizes_bwd": None, "nuwa_struct_sizes_decode": None, "nuwa_struct_sizes_optim": None}
+             "nuwa_gemm_prof_attach": None, "nuwa_gemm_prof_close": None, "nuwa_gemm_prof_open": c_void_p, "nuwa_struct_sizes_bwd": None, "nuwa_struct_sizes_decode": None, "nuwa_struct_sizes_optim": None}
 
 _lib = None
 # bumped by code that rewrites parameter storage behind autograd's back (optim.FusedAdamW): part of every packed-weight
@@ -259,17 +262,30 @@ def launch_count():
     return int(lib().nuwa_launch_count())
 
 
-def gemm_prof_enable(on):
-    lib().nuwa_gemm_prof_enable(int(bool(on)))
+class GemmProfiler:
+    """Per-thread profiler of the tcgen05 GEMM / conv launches (context manager): events are recorded only for launches
+    made by the thread that entered it.  collect() -> (launches, algorithmic flops, device ms), call after a sync;
+    bytes() -> algorithmic HBM bytes (operands and outputs once each) of the launches the last collect() summed."""
 
+    def __init__(self):
+        self.h = lib().nuwa_gemm_prof_open()
 
-def gemm_prof_collect():
-    """(launches, algorithmic FLOPs, device ms) of the tcgen05 GEMM/conv launches since enable; call after a sync."""
-    fl, ms = ctypes.c_double(0), c_float(0)
-    n = lib().nuwa_gemm_prof_collect(ctypes.byref(fl), ctypes.byref(ms))
-    return n, fl.value, ms.value
+    def __enter__(self):
+        lib().nuwa_gemm_prof_attach(self.h)
+        return self
 
+    def __exit__(self, *a):
+        lib().nuwa_gemm_prof_attach(None)
 
-def gemm_prof_bytes():
-    """Algorithmic HBM bytes (operands and outputs once each) of the launches the last gemm_prof_collect() summed."""
-    return float(lib().nuwa_gemm_prof_bytes())
+    def collect(self):
+        fl, ms = ctypes.c_double(0.0), c_float(0.0)
+        n = lib().nuwa_gemm_prof_collect(self.h, ctypes.byref(fl), ctypes.byref(ms))
+        return int(n), float(fl.value), float(ms.value)
+
+    def bytes(self):
+        return float(lib().nuwa_gemm_prof_bytes(self.h))
+
+    def close(self):
+        if self.h:
+            lib().nuwa_gemm_prof_close(self.h)
+            self.h = None

@@ -54,6 +54,9 @@ int nuwa_attn_sparse3dna_halo(const nuwa_attn_params* p, void* stream) {
 int nuwa_attn_sparse3dna_umma(const nuwa_attn_params* p, void* stream) {
   return p ? attn_3dna_umma(*p, S(stream)) : NUWA_ERR_INVALID;
 }
+int nuwa_attn_cross2dna_umma(const nuwa_attn_params* p, void* stream) {
+  return p ? attn_cross2dna_umma(*p, S(stream)) : NUWA_ERR_INVALID;
+}
 int nuwa_attn_dense(const nuwa_attn_params* p, void* vt_workspace, void* stream) {
   if (!p) return NUWA_ERR_INVALID;
   if (p->nq >= 16) {  // 8 x 64 heads, learned null key / mask / talking heads: two-pass 64-query tensor-core kernel
@@ -161,9 +164,11 @@ int nuwa_conv1x1_nhwc_to_nchw(const void* x, const float* w, const float* bias, 
 
 }  // extern "C"
 
-extern "C" void nuwa_gemm_prof_enable(int on) { gemm_prof_enable(on); }
-extern "C" int nuwa_gemm_prof_collect(double* flops, float* ms) { return gemm_prof_collect(flops, ms); }
-extern "C" double nuwa_gemm_prof_bytes(void) { return gemm_prof_bytes(); }
+extern "C" void* nuwa_gemm_prof_open(void) { return gemm_prof_open(); }
+extern "C" void nuwa_gemm_prof_attach(void* h) { gemm_prof_attach(h); }
+extern "C" int nuwa_gemm_prof_collect(void* h, double* flops, float* ms) { return gemm_prof_collect(h, flops, ms); }
+extern "C" double nuwa_gemm_prof_bytes(void* h) { return gemm_prof_bytes(h); }
+extern "C" void nuwa_gemm_prof_close(void* h) { gemm_prof_close(h); }
 
 // sizes of the parameter structs, so a foreign-language binding can verify its mirror of the layout
 extern "C" void nuwa_struct_sizes(int* out3) {

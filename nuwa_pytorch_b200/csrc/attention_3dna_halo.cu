@@ -48,7 +48,8 @@ constexpr int OFF_P = OFF_Q + QR * BOX;
 constexpr int OFF_S = OFF_P + NH * QR * GW * PP * 2;
 constexpr int OFF_BOS = OFF_S + QR * GW * SP * 4;
 constexpr int OFF_W = OFF_BOS + 2 * INNER * 2;
-constexpr int OFF_BAR = OFF_W + NH * NH * 4;
+constexpr int OFF_TRASH = OFF_W + NH * NH * 4;     // one word per query-row lane: out-of-band score entries land here
+constexpr int OFF_BAR = OFF_TRASH + QR * 32 * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;  // + alignment slack
 
 __device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
@@ -72,6 +73,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+// The producer warp and the query-row warps meet at ONE CTA-wide barrier from two different call sites; as two
+// __syncthreads() that is a barrier in divergent code (compute-sanitizer synccheck objects), as a named barrier with an
+// explicit thread count it is well defined.
+// (__syncwarp first: the producer warp arrives right after a lane-0-only section and must be reconverged.)
+__device__ __forceinline__ void cta_bar() {
+  __syncwarp();
+  asm volatile("bar.sync 1, %0;" ::"n"((QR + 1) * 32) : "memory");
 }
 
 struct HaloArgs {
@@ -210,7 +220,7 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
       issue_q(0);
       produce(min(NST, n_a));  // head 0 only: later heads wait for the query-row warps, which start after the sync
     }
-    __syncthreads();  // pairs with the query-row warps' barrier below
+    cta_bar();  // pairs with the query-row warps' barrier below
     if (lane == 0) {
       produce(NS);
       if (DBG && p.dbg != nullptr && blockIdx.x == 0) p.dbg[23] = prod_wait;
@@ -233,7 +243,7 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
     reinterpret_cast<uint4*>(kbos)[tid] = __ldg(src + (tid & 63));
     if (tid < NH * NH) Wsm[tid] = p.talk ? __ldg(p.talk + tid) : ((tid / NH) == (tid % NH) ? 1.f : 0.f);
   }
-  __syncthreads();  // barriers initialised (producer), shared state written
+  cta_bar();  // barriers initialised (producer), shared state written
 
   // =============================== query-row warps ===============================
   const int yq = y0 + warp * p.dh;
@@ -267,7 +277,9 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
     int c = -1;
     if (delta >= 0 && delta % p.dw == 0 && delta / p.dw <= kw - 1) c = kw - 1 - delta / p.dw;
     inc[i] = c >= 0 ? 1u : 0u;
-    s_addr[i] = smem_u32(Sw) + 4u * (x * SP + (c >= 0 ? c : SP - 1));
+    // out-of-band entries go to a word private to this lane (a shared trash slot is a benign write-write race, but it
+    // drowns compute-sanitizer racecheck in reports)
+    s_addr[i] = c >= 0 ? smem_u32(Sw) + 4u * (x * SP + c) : sm_u + OFF_TRASH + 4u * (warp * 32 + lane);
     p_addr[i] = smem_u32(Pw) + 2u * (x * PP + (c >= 0 ? c : ZSLOT));
     // keep the tables in registers (ptxas otherwise rematerialises them in every block: +15 integer ops per block)
     asm volatile("" : "+r"(inc[i]), "+r"(s_addr[i]), "+r"(p_addr[i]));
@@ -585,14 +597,10 @@ int attn_3dna_halo(const AttnParams& p, cudaStream_t stream) {
   a.dbg = g_halo_dbg;
 
   const int grid = a.nf * a.tiles * a.B;
-  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
   auto launch = [&](void (*kern)(const CUtensorMap, const HaloArgs), int slot) -> int {
-    if (!attr_set[slot]) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
-        return NUWA_ERR_CUDA;
-      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      attr_set[slot] = true;
-    }
+    (void)slot;  // (attributes are set per launch: idempotent driver calls, no cached library state)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return NUWA_ERR_CUDA;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     kern<<<grid, (QR + 1) * 32, SMEM_BYTES, stream>>>(map, a);
     return NUWA_OK;
   };

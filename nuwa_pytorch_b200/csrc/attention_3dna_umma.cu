@@ -60,8 +60,8 @@ constexpr int OFF_Q = OFF_KV + NST * KV_STAGE;            // 4 buffers: (head pa
 constexpr int OFF_KBOS = OFF_Q + 4 * Q_BYTES;             // [8 heads][64] fp32: bos key rows of the tile's sample
 constexpr int OFF_WB = OFF_KBOS + NH * DH * 4;            // talking-heads B operands: [hi, lo] x [16 rows x 128 B]
 constexpr int OFF_SC = OFF_WB + 2 * BOX;                  // 2 warpgroups x [128] window dump rows (thread private)
-constexpr int OFF_VBOS = OFF_SC + 2 * 128 * DPITCH;       // [8][64] bf16
-constexpr int OFF_PBOS = OFF_VBOS + INNER * 2;            // [8][128] fp32: probability of the bos slot
+constexpr int OFF_VBOS = OFF_SC + 2 * 128 * DPITCH;       // [8][64] fp32: value of slot 0 (bos row / learned null value)
+constexpr int OFF_PBOS = OFF_VBOS + INNER * 4;            // [8][128] fp32: probability of slot 0
 constexpr int OFF_W = OFF_PBOS + NH * 128 * 4;            // [8][8] fp32
 constexpr int OFF_BAR = OFF_W + NH * NH * 4;
 constexpr int NBAR = 2 * NST + 2 * 4 + 6 * 2 + 3;
@@ -74,8 +74,14 @@ constexpr int THREADS = 384;   // warps 0 / 11: TMA producers, warps 1 / 10: MMA
 struct UmmaArgs {
   int B, nv, nf, maxf, tpf, ntiles;    // nf = frames present, tpf = tiles per frame
   int kt, kh, dt, dh, dw, causal;
-  int koff, voff;
-  int rows5d;                          // rows [0, rows5d) of every sample are reachable through the 5-D maps (0: none)
+  int koff, voff;                      // channel offsets of k / v inside a row of the key buffer
+  int q_rows5d, kv_rows5d;             // rows [0, rows5d) of every sample are reachable through the 5-D maps (0: none)
+  int q_tok0, kv_tok0;                 // token index of grid position 0 in the flat query / key views (1: a bos row first)
+  int abs_frames;                      // SparseCross2DNA: frame offset a addresses context frame a (else f + (a - At) dt)
+  const float* null_k;                 // learned null key / value [H * dh] fp32 (SparseCross2DNA) or NULL: key row 0 (bos)
+  const float* null_v;
+  const unsigned char* key_mask;       // [B][mask_bs] context-token mask or NULL
+  int mask_bs;
   float scale_log2e;
   const float* talk;
   bf16* o;
@@ -151,6 +157,10 @@ __device__ __forceinline__ void make_tile(const UmmaArgs& p, int s, int Ah, Tile
   t.real_mask = t.zero_mask = t.n_real = 0;
 #pragma unroll
   for (int a = 0; a < MAXKT; ++a) {
+    if (p.abs_frames) {                  // every context frame is a real key frame for every query frame
+      if (a < p.kt) { t.real_mask |= 1 << a; ++t.n_real; }
+      continue;
+    }
     const int ff = t.f + (a - At) * p.dt;
     if (a < p.kt && ff >= 0 && ff < p.maxf) {
       if (ff < p.nf) { t.real_mask |= 1 << a; ++t.n_real; }
@@ -187,24 +197,32 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // key / query rows y0 + i * dh (i < n) of frame f, channels [chan, chan + 64) -> dst + i * BOX.  Rows reachable through
 // the 5-D view travel as boxes of 8 / 4 / 2 rows (one TMA instruction each); the ragged end of the sequence and
 // dilations that do not divide the grid height use one 16-token box per row on the flat view (zero fill past the end).
-__device__ __forceinline__ void load_rows(uint32_t dst, uint64_t* bar, const CUtensorMap* flat, const CUtensorMap* m8,
-                                          const CUtensorMap* m4, const CUtensorMap* m2, const UmmaArgs& p, int chan, int f,
-                                          int y0, int n, int b) {
+struct MapSet {
+  const CUtensorMap* flat;
+  const CUtensorMap* m8;
+  const CUtensorMap* m4;
+  const CUtensorMap* m2;
+  int rows5d, tok0;
+};
+__device__ __forceinline__ void load_rows(uint32_t dst, uint64_t* bar, const MapSet& ms, int dh, int chan, int f, int y0, int n,
+                                          int b) {
   const int R0 = f * GW + y0;
   int i = 0;
-  if (R0 + (n - 1) * p.dh < p.rows5d) {
-    const int ylo = y0 % p.dh, yhi = R0 / p.dh;
-    for (; n - i >= 8; i += 8) tma_load_5d(dst + i * BOX, m8, bar, chan, 0, ylo, yhi + i, b);
-    if (n - i >= 4) { tma_load_5d(dst + i * BOX, m4, bar, chan, 0, ylo, yhi + i, b); i += 4; }
-    if (n - i >= 2) { tma_load_5d(dst + i * BOX, m2, bar, chan, 0, ylo, yhi + i, b); i += 2; }
+  if (R0 + (n - 1) * dh < ms.rows5d) {
+    const int ylo = y0 % dh, yhi = R0 / dh;
+    for (; n - i >= 8; i += 8) tma_load_5d(dst + i * BOX, ms.m8, bar, chan, 0, ylo, yhi + i, b);
+    if (n - i >= 4) { tma_load_5d(dst + i * BOX, ms.m4, bar, chan, 0, ylo, yhi + i, b); i += 4; }
+    if (n - i >= 2) { tma_load_5d(dst + i * BOX, ms.m2, bar, chan, 0, ylo, yhi + i, b); i += 2; }
   }
-  for (; i < n; ++i) tma_load_3d(dst + i * BOX, flat, bar, chan, 1 + (R0 + i * p.dh) * GW, b);
+  for (; i < n; ++i) tma_load_3d(dst + i * BOX, ms.flat, bar, chan, ms.tok0 + (R0 + i * dh) * GW, b);
 }
 
 template <int DW>
 __global__ void __launch_bounds__(THREADS, 1)
-attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap map8,
-                      const __grid_constant__ CUtensorMap map4, const __grid_constant__ CUtensorMap map2, const UmmaArgs p) {
+attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap qmap8,
+                      const __grid_constant__ CUtensorMap qmap4, const __grid_constant__ CUtensorMap qmap2,
+                      const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap kmap8,
+                      const __grid_constant__ CUtensorMap kmap4, const __grid_constant__ CUtensorMap kmap2, const UmmaArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -241,9 +259,10 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
     mbar_init(mixfull, 1);
     fence_barrier_init();
     tma_prefetch_desc(&qmap);
-    tma_prefetch_desc(&map8);
-    tma_prefetch_desc(&map4);
-    tma_prefetch_desc(&map2);
+    tma_prefetch_desc(&qmap8);
+    tma_prefetch_desc(&kmap);
+    tma_prefetch_desc(&kmap8);
+    tma_prefetch_desc(&kmap2);
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   // one-time shared-memory state: operand buffers zeroed (slot columns that are never loaded must hold finite values:
@@ -279,6 +298,8 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
     // ============ TMA producer of warpgroup w: its Q tiles and every second ring slot (its K / V tiles) ============
     if (lane == 0) {
       const int w = warp == 0 ? 0 : 1;
+      const MapSet qms = {&qmap, &qmap8, &qmap4, &qmap2, p.q_rows5d, p.q_tok0};
+      const MapSet kms = {&kmap, &kmap8, &kmap4, &kmap2, p.kv_rows5d, p.kv_tok0};
       uint32_t it = (uint32_t)w, qu[2] = {0, 0};
       for (int k = 0;; ++k) {
         const int s = snake(k, cta, G);
@@ -306,12 +327,12 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
         const uint32_t kbytes = (uint32_t)(kn[0] + kn[1]) * BOX;
         // fast path of the key tiles (every row reachable through the 5-D view): run c = box of 8 rows + box of 2 / 4
         // rows, coordinates precomputed up to the frame term
-        const int rpf = p.rows5d > 0 ? GW / p.dh : 0;                  // 5-D row-block coordinate advance per frame
+        const int rpf = p.kv_rows5d > 0 ? GW / p.dh : 0;               // 5-D row-block coordinate advance per frame
         int k_ylo[2], k_yhi[2], k_last[2];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          k_ylo[c] = p.rows5d > 0 ? ky[c] % p.dh : 0;
-          k_yhi[c] = p.rows5d > 0 ? ky[c] / p.dh : 0;
+          k_ylo[c] = p.kv_rows5d > 0 ? ky[c] % p.dh : 0;
+          k_yhi[c] = p.kv_rows5d > 0 ? ky[c] / p.dh : 0;
           k_last[c] = ky[c] + (kn[c] - 1) * p.dh;                       // last row inside its frame
         }
         auto load_q = [&](int hp) {
@@ -320,8 +341,7 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
           mbar_arrive_expect_tx(&qfull[qb], qbytes);
           for (int c = 0; c < 2; ++c)
             if (qn[c] > 0)
-              load_rows(sm_u + OFF_Q + qb * Q_BYTES + 4 * c * BOX, &qfull[qb], &qmap, &map8, &map4, &map2, p, h * DH, t.f,
-                        qy[c], qn[c], t.b);
+              load_rows(sm_u + OFF_Q + qb * Q_BYTES + 4 * c * BOX, &qfull[qb], qms, p.dh, h * DH, t.f, qy[c], qn[c], t.b);
           ++qu[hp & 1];
         };
         load_q(0);
@@ -330,7 +350,7 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
             const int chan = (ph ? p.voff : p.koff) + (2 * hp + w) * DH;
             for (int a = 0; a < p.kt; ++a) {
               if (!((t.real_mask >> a) & 1)) continue;
-              const int ff = t.f + (a - At) * p.dt;
+              const int ff = p.abs_frames ? a : t.f + (a - At) * p.dt;
               const int st = it % NST;
               const uint32_t dst = sm_u + OFF_KV + st * KV_STAGE;
               mbar_wait(&empty[st], ((it / NST) & 1) ^ 1);
@@ -339,16 +359,16 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
               for (int c = 0; c < 2; ++c) {
                 if (kn[c] <= 0) continue;
                 const uint32_t d = dst + ksc[c] * BOX;
-                if (ff * GW + k_last[c] < p.rows5d && (kn[c] == 10 || kn[c] == 8 || kn[c] == 4)) {
+                if (ff * GW + k_last[c] < p.kv_rows5d && (kn[c] == 10 || kn[c] == 8 || kn[c] == 4)) {
                   const int yhi = ff * rpf + k_yhi[c];
                   if (kn[c] == 4) {
-                    tma_load_5d(d, &map4, &full[st], chan, 0, k_ylo[c], yhi, t.b);
+                    tma_load_5d(d, &kmap4, &full[st], chan, 0, k_ylo[c], yhi, t.b);
                   } else {
-                    tma_load_5d(d, &map8, &full[st], chan, 0, k_ylo[c], yhi, t.b);
-                    if (kn[c] == 10) tma_load_5d(d + 8 * BOX, &map2, &full[st], chan, 0, k_ylo[c], yhi + 8, t.b);
+                    tma_load_5d(d, &kmap8, &full[st], chan, 0, k_ylo[c], yhi, t.b);
+                    if (kn[c] == 10) tma_load_5d(d + 8 * BOX, &kmap2, &full[st], chan, 0, k_ylo[c], yhi + 8, t.b);
                   }
                 } else {
-                  load_rows(d, &full[st], &qmap, &map8, &map4, &map2, p, chan, ff, ky[c], kn[c], t.b);
+                  load_rows(d, &full[st], kms, p.dh, chan, ff, ky[c], kn[c], t.b);
                 }
               }
               it += 2;
@@ -463,7 +483,7 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
     const uint32_t drow_u = sm_u + OFF_SC + (uint32_t)(wg * 128 + qrow) * DPITCH;   // this thread's window dump row
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(drow_u + 256), "f"(-FLT_MAX) : "memory");  // sentinel for masked slots
     const float* Wsm = reinterpret_cast<const float*>(sm + OFF_W);
-    const bf16* vbos = reinterpret_cast<const bf16*>(sm + OFF_VBOS);
+    const float* vbos = reinterpret_cast<const float*>(sm + OFF_VBOS);
     float* pbos_s = reinterpret_cast<float*>(sm + OFF_PBOS);
     const int Aw = p.causal ? KW - 1 : (KW - 1) / 2;
 
@@ -514,25 +534,47 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
           goff[b * KW + c] = ok ? 4u * (uint32_t)(16 * (r + b) + x + (c - Aw) * p.dw) : 256u;
           valid9 |= (ok ? 1u : 0u) << (b * KW + c);
         }
+      // context-token mask (SparseCross2DNA, nuwa_pytorch.py:878-884): the window of a query sits at the same grid position
+      // in every context frame, so its 9 mask bits per frame are tile constants
+      unsigned long long kmask = 0;      // 9 bits per frame offset
+#pragma unroll
+      for (int a = 0; a < MAXKT; ++a) {
+        uint32_t m = valid9;
+        if (p.key_mask != nullptr && a < p.kt) {
+          m = 0;
+#pragma unroll
+          for (int b = 0; b < MAXKH; ++b)
+#pragma unroll
+            for (int c = 0; c < KW; ++c)
+              if ((valid9 >> (b * KW + c)) & 1u) {
+                const int yy = slot_row(p, t, ti + b, Ah), xx = x + (c - Aw) * p.dw;   // valid9: inside the grid
+                const int tok = (a * GW + yy) * GW + xx;
+                m |= (__ldg(p.key_mask + (long long)t.b * p.mask_bs + tok) != 0 ? 1u : 0u) << (b * KW + c);
+              }
+        }
+        kmask |= (unsigned long long)m << (9 * a);
+      }
       // ---- tile start: everyone has left the previous tile (its bos rows / TMEM are free), then stage this one ----
       named_bar_sync(1, 256);
       if (wg == 0) {
-        if (qrow < 64) {  // k_bos: 8 heads x 64 channels -> fp32 (read as broadcasts by the bos dot product)
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.k0 + (long long)t.b * p.k_bs) + qrow);
+        if (p.null_k != nullptr) {   // learned null key / value (fp32 parameters), the same for every sample
+          float* dstk = reinterpret_cast<float*>(sm + OFF_KBOS);
+          float* dstv = reinterpret_cast<float*>(sm + OFF_VBOS);
+          for (int i = qrow; i < INNER; i += 128) { dstk[i] = __ldg(p.null_k + i); dstv[i] = __ldg(p.null_v + i); }
+        } else {                     // bos key / value: sequence row 0 of this sample, 8 heads x 64 channels -> fp32
+          const bf16* src = (qrow < 64 ? p.k0 + (long long)t.b * p.k_bs : p.v0 + (long long)t.b * p.v_bs);
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + (qrow & 63));
           const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-          float* dstk = reinterpret_cast<float*>(sm + OFF_KBOS) + qrow * 8;
+          float* dst8 = reinterpret_cast<float*>(sm + (qrow < 64 ? OFF_KBOS : OFF_VBOS)) + (qrow & 63) * 8;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 f2 = unpack_bf16x2(w4[e]);
-            dstk[2 * e] = f2.x; dstk[2 * e + 1] = f2.y;
+            dst8[2 * e] = f2.x; dst8[2 * e + 1] = f2.y;
           }
-        } else {
-          const int i = qrow - 64;
-          reinterpret_cast<uint4*>(sm + OFF_VBOS)[i] = __ldg(reinterpret_cast<const uint4*>(p.v0 + (long long)t.b * p.v_bs) + i);
         }
       }
       // the bos query (sequence row 0) attends only to itself (nuwa_pytorch.py:608): its output is its value row
-      if (t.f == 0 && tile_row(p, t, 0) == 0 && wg == 1 && qrow < 64) {
+      if (!p.abs_frames && t.f == 0 && tile_row(p, t, 0) == 0 && wg == 1 && qrow < 64) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.v0 + (long long)t.b * p.v_bs) + qrow);
         reinterpret_cast<uint4*>(p.o + (long long)t.b * p.o_bs)[qrow] = v;
       }
@@ -587,9 +629,11 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
             for (int i = 0; i < 16; ++i)
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(drow_u + 16 * i), "r"(v[4 * i]), "r"(v[4 * i + 1]),
                            "r"(v[4 * i + 2]), "r"(v[4 * i + 3]) : "memory");
+            const uint32_t km = (uint32_t)(kmask >> (9 * a)) & 0x1ffu;
 #pragma unroll
             for (int e = 0; e < MAXKH * KW; ++e)
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sv[1 + 9 * a + e]) : "r"(drow_u + goff[e]) : "memory");
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sv[1 + 9 * a + e])
+                           : "r"(drow_u + (((km >> e) & 1u) ? goff[e] : 256u)) : "memory");
           } else if (a < p.kt && ((t.zero_mask >> a) & 1)) {
             // in-volume key frame beyond the sequence: visible zero keys (score 0), SURVEY D16
 #pragma unroll
@@ -733,18 +777,17 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
         if (lane == 0) mbar_arrive(&oempty[wg]);
         ++ou;
         if (qok) {
-          bf16* dst = p.o + (long long)t.b * p.o_bs + (long long)(1 + vpos) * p.o_rs + g * DH;
+          bf16* dst = p.o + (long long)t.b * p.o_bs + (long long)(p.q_tok0 + vpos) * p.o_rs + g * DH;
 #pragma unroll
           for (int c8i = 0; c8i < 8; ++c8i) {
-            const uint4 vb4 = *reinterpret_cast<const uint4*>(vbos + g * DH + c8i * 8);
-            const uint32_t vbw[4] = {vb4.x, vb4.y, vb4.z, vb4.w};
+            const float4 va = *reinterpret_cast<const float4*>(vbos + g * DH + c8i * 8);
+            const float4 vb4 = *reinterpret_cast<const float4*>(vbos + g * DH + c8i * 8 + 4);
+            const float vf[8] = {va.x, va.y, va.z, va.w, vb4.x, vb4.y, vb4.z, vb4.w};
             uint32_t outw[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 vbf = unpack_bf16x2(vbw[e]);
-              outw[e] = pack_bf16x2(fmaf(pbos, vbf.x, __uint_as_float(ov[c8i * 8 + 2 * e])),
-                                    fmaf(pbos, vbf.y, __uint_as_float(ov[c8i * 8 + 2 * e + 1])));
-            }
+            for (int e = 0; e < 4; ++e)
+              outw[e] = pack_bf16x2(fmaf(pbos, vf[2 * e], __uint_as_float(ov[c8i * 8 + 2 * e])),
+                                    fmaf(pbos, vf[2 * e + 1], __uint_as_float(ov[c8i * 8 + 2 * e + 1])));
             *reinterpret_cast<uint4*>(dst + c8i * 8) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
           }
         }
@@ -764,6 +807,67 @@ long long* g_umma_dbg = nullptr;
 
 // measurement aid (tools/umma_stamps.py; not part of include/nuwa_b200.h): 64 int64 of device memory or NULL
 extern "C" void nuwa_debug_umma_stamps(long long* dev_ptr) { g_umma_dbg = dev_ptr; }
+
+namespace {
+
+struct HostMaps {
+  CUtensorMap flat, m8, m4, m2;
+  int rows5d;
+};
+
+// TMA views of one [B][tokens][row_stride] bf16 buffer: the flat token view (zero fill past `tokens`) and, when the row
+// dilation divides the grid height, the 5-D view of its complete 16-token grid rows: grid row R = yhi * dh + ylo, so a box
+// of n consecutive yhi is n rows spaced by the row dilation.  tok0 = flat token index of grid position 0.
+int build_maps(HostMaps& m, const bf16* base, int rs, long long bs, int tokens, int tok0, int dh, int B) {
+  const uint64_t dims[3] = {(uint64_t)rs, (uint64_t)tokens, (uint64_t)B};
+  const uint64_t strides[3] = {2, (uint64_t)rs * 2, (uint64_t)bs * 2};
+  const uint32_t box[3] = {DH, GW, 1};
+  int rc = encode_map_bf16_sw128(&m.flat, base, 3, dims, strides, box);
+  if (rc != NUWA_OK) return rc;
+  m.rows5d = 0;
+  if (GW % dh == 0) m.rows5d = ((tokens - tok0) / GW / dh) * dh;
+  m.m8 = m.m4 = m.m2 = m.flat;
+  if (m.rows5d > 0) {
+    const uint64_t d5[5] = {(uint64_t)rs, (uint64_t)GW, (uint64_t)dh, (uint64_t)(m.rows5d / dh), (uint64_t)B};
+    const uint64_t s5[5] = {2, (uint64_t)rs * 2, (uint64_t)GW * rs * 2, (uint64_t)dh * GW * rs * 2, (uint64_t)bs * 2};
+    const void* g0 = base + (long long)tok0 * rs;
+    const uint32_t b8[5] = {DH, GW, 1, 8, 1}, b4[5] = {DH, GW, 1, 4, 1}, b2[5] = {DH, GW, 1, 2, 1};
+    if ((rc = encode_map_bf16_sw128(&m.m8, g0, 5, d5, s5, b8)) != NUWA_OK) return rc;
+    if ((rc = encode_map_bf16_sw128(&m.m4, g0, 5, d5, s5, b4)) != NUWA_OK) return rc;
+    if ((rc = encode_map_bf16_sw128(&m.m2, g0, 5, d5, s5, b2)) != NUWA_OK) return rc;
+  }
+  return NUWA_OK;
+}
+
+int tiles_per_frame(int dh) {
+  if (dh >= 4) return (min(dh, GW) + 1) / 2;
+  int tiles = 0;
+  for (int r = 0; r < dh; ++r) tiles += ((GW - r + dh - 1) / dh + 7) / 8;
+  return tiles;
+}
+
+int launch_umma(const HostMaps& qm, const HostMaps& km, UmmaArgs& a, cudaStream_t stream) {
+  a.q_rows5d = qm.rows5d; a.kv_rows5d = km.rows5d;
+  a.tpf = tiles_per_frame(a.dh);
+  a.ntiles = a.nf * a.tpf * a.B;
+  a.dbg = g_umma_dbg;
+  const int grid = min(a.ntiles, device_sm_count());
+  auto launch = [&](void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                                 const CUtensorMap, const CUtensorMap, const CUtensorMap, const UmmaArgs)) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return NUWA_ERR_CUDA;
+    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(qm.flat, qm.m8, qm.m4, qm.m2, km.flat, km.m8, km.m4, km.m2, a);
+    return NUWA_OK;
+  };
+  int lrc;
+  if (a.dw == 1) lrc = launch(attn_3dna_umma_kernel<1>);
+  else if (a.dw == 2) lrc = launch(attn_3dna_umma_kernel<2>);
+  else lrc = launch(attn_3dna_umma_kernel<4>);
+  if (lrc != NUWA_OK) return lrc;
+  NUWA_CHECK_LAUNCH();
+  return NUWA_OK;
+}
+
+}  // namespace
 
 // Envelope: full pass (t0 == 0, nq == nv + 1) over a 16-wide token grid, H == 8, dh == 64, kw == 3, kh <= 3, kt <= 5,
 // column dilation 1 / 2 / 4, q|k|v rows sharing one token stride; causal or centred windows.  NUWA_ERR_INVALID outside
@@ -785,65 +889,68 @@ int attn_3dna_umma(const AttnParams& p, cudaStream_t stream) {
   if ((p.q_rs % 8) || (p.q_bs % 8) || (koff % 8) || (voff % 8) || (p.o_rs % 8) || (p.o_bs % 8)) return NUWA_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(p.q) & 15) || (reinterpret_cast<uintptr_t>(p.o) & 15)) return NUWA_ERR_INVALID;
 
-  CUtensorMap map, map8, map4, map2;
-  const uint64_t dims[3] = {(uint64_t)p.q_rs, (uint64_t)(p.nv + 1), (uint64_t)p.B};
-  const uint64_t strides[3] = {2, (uint64_t)p.q_rs * 2, (uint64_t)p.q_bs * 2};
-  const uint32_t box[3] = {DH, GW, 1};
-  int rc = encode_map_bf16_sw128(&map, p.q, 3, dims, strides, box);
+  HostMaps m;   // q, k and v live in one buffer: one map set serves both sides (sequence row 0 = bos, grid from row 1)
+  int rc = build_maps(m, q, p.q_rs, p.q_bs, p.nv + 1, 1, p.dh_, p.B);
   if (rc != NUWA_OK) return rc;
-  // 5-D view of the complete grid rows (16 tokens each, starting at sequence row 1): row R = yhi * dh + ylo, so that a box
-  // of n consecutive yhi is n key rows spaced by the row dilation.  Only when dh divides the grid height.
-  int rows5d = 0;
-  if (GW % p.dh_ == 0) {
-    const int full_rows = p.nv / GW;
-    rows5d = (full_rows / p.dh_) * p.dh_;
-  }
-  map8 = map4 = map2 = map;
-  if (rows5d > 0) {
-    const uint64_t d5[5] = {(uint64_t)p.q_rs, (uint64_t)GW, (uint64_t)p.dh_, (uint64_t)(rows5d / p.dh_), (uint64_t)p.B};
-    const uint64_t s5[5] = {2, (uint64_t)p.q_rs * 2, (uint64_t)GW * p.q_rs * 2, (uint64_t)p.dh_ * GW * p.q_rs * 2,
-                            (uint64_t)p.q_bs * 2};
-    const void* base1 = q + p.q_rs;  // sequence row 1 = video token 0
-    const uint32_t b8[5] = {DH, GW, 1, 8, 1}, b4[5] = {DH, GW, 1, 4, 1}, b2[5] = {DH, GW, 1, 2, 1};
-    if ((rc = encode_map_bf16_sw128(&map8, base1, 5, d5, s5, b8)) != NUWA_OK) return rc;
-    if ((rc = encode_map_bf16_sw128(&map4, base1, 5, d5, s5, b4)) != NUWA_OK) return rc;
-    if ((rc = encode_map_bf16_sw128(&map2, base1, 5, d5, s5, b2)) != NUWA_OK) return rc;
-  }
 
-  UmmaArgs a;
+  UmmaArgs a = {};
   a.B = p.B; a.nv = p.nv;
   a.nf = (p.nv + GW * GW - 1) / (GW * GW);
   a.maxf = p.max_frames;
-  if (p.dh_ >= 4) {
-    a.tpf = (min(p.dh_, GW) + 1) / 2;
-  } else {
-    int tiles = 0;
-    for (int r = 0; r < p.dh_; ++r) tiles += ((GW - r + p.dh_ - 1) / p.dh_ + 7) / 8;
-    a.tpf = tiles;
-  }
-  a.ntiles = a.nf * a.tpf * a.B;
   a.kt = p.kt; a.kh = p.kh; a.dt = p.dt; a.dh = p.dh_; a.dw = p.dw; a.causal = p.causal;
   a.koff = (int)koff; a.voff = (int)voff;
-  a.rows5d = rows5d;
+  a.q_tok0 = a.kv_tok0 = 1;
   a.scale_log2e = p.qscale * 1.4426950408889634f;
   a.talk = p.talk;
   a.o = reinterpret_cast<bf16*>(p.o); a.o_bs = p.o_bs; a.o_rs = p.o_rs;
   a.k0 = k; a.v0 = v; a.k_bs = p.k_bs; a.v_bs = p.v_bs;
-  a.dbg = g_umma_dbg;
+  return launch_umma(m, m, a, stream);
+}
 
-  const int grid = min(a.ntiles, device_sm_count());
-  auto launch = [&](void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const UmmaArgs)) -> int {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return NUWA_ERR_CUDA;
-    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(map, map8, map4, map2, a);
-    return NUWA_OK;
-  };
-  int lrc;
-  if (p.dw == 1) lrc = launch(attn_3dna_umma_kernel<1>);
-  else if (p.dw == 2) lrc = launch(attn_3dna_umma_kernel<2>);
-  else lrc = launch(attn_3dna_umma_kernel<4>);
-  if (lrc != NUWA_OK) return lrc;
-  NUWA_CHECK_LAUNCH();
-  return NUWA_OK;
+// SparseCross2DNA (nuwa_pytorch.py:851-895) on the same kernel: the nq queries at video positions 0 .. nq-1 (p.q / p.o
+// point at the first of them, i.e. past the bos row; p.t0 == 1) each see slot 0 = the learned null key / value and the
+// centred ck x ck window, dilation cdil, at their own grid position in every context frame, under the context mask.
+// Envelope: 16-wide grid, H == 8, dh == 64, ck == 3, cdil 1 / 2 / 4, <= 5 context frames, k|v rows sharing one stride.
+int attn_cross2dna_umma(const AttnParams& p, cudaStream_t stream) {
+  if (p.fmap != GW || p.t0 != 1 || p.t0_ptr != nullptr) return NUWA_ERR_INVALID;
+  if (p.H != NH || p.dh != DH || p.nq <= 0 || p.B <= 0) return NUWA_ERR_INVALID;
+  if (p.ck != KW || !(p.cdil == 1 || p.cdil == 2 || p.cdil == 4)) return NUWA_ERR_INVALID;
+  const int frames = (p.jmax - 1) / (KW * KW);
+  if (frames < 1 || frames > MAXKT || p.jmax != 1 + frames * KW * KW) return NUWA_ERR_INVALID;
+  if (p.head_scale != nullptr || p.bias != nullptr || p.null_k == nullptr || p.null_v == nullptr) return NUWA_ERR_INVALID;
+  if (p.key_mask != nullptr && p.mask_bs < frames * GW * GW) return NUWA_ERR_INVALID;
+  const bf16* q = reinterpret_cast<const bf16*>(p.q);
+  const bf16* k = reinterpret_cast<const bf16*>(p.k);
+  const bf16* v = reinterpret_cast<const bf16*>(p.v);
+  const bf16* kvbase = k < v ? k : v;
+  const long long koff = k - kvbase, voff = v - kvbase;
+  if (p.k_rs != p.v_rs || p.k_bs != p.v_bs || koff + INNER > p.k_rs || voff + INNER > p.k_rs) return NUWA_ERR_INVALID;
+  if (INNER > p.q_rs || (p.q_rs % 8) || (p.q_bs % 8) || (p.k_rs % 8) || (p.k_bs % 8) || (koff % 8) || (voff % 8) ||
+      (p.o_rs % 8) || (p.o_bs % 8))
+    return NUWA_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(p.q) & 15) || (reinterpret_cast<uintptr_t>(kvbase) & 15) ||
+      (reinterpret_cast<uintptr_t>(p.o) & 15))
+    return NUWA_ERR_INVALID;
+
+  HostMaps qm, km;
+  int rc = build_maps(qm, q, p.q_rs, p.q_bs, p.nq, 0, p.cdil, p.B);
+  if (rc != NUWA_OK) return rc;
+  if ((rc = build_maps(km, kvbase, p.k_rs, p.k_bs, frames * GW * GW, 0, p.cdil, p.B)) != NUWA_OK) return rc;
+
+  UmmaArgs a = {};
+  a.B = p.B; a.nv = p.nq;
+  a.nf = (p.nq + GW * GW - 1) / (GW * GW);
+  a.maxf = a.nf;
+  a.kt = frames; a.kh = KW; a.dt = 1; a.dh = p.cdil; a.dw = p.cdil; a.causal = 0;
+  a.koff = (int)koff; a.voff = (int)voff;
+  a.abs_frames = 1;
+  a.null_k = p.null_k; a.null_v = p.null_v;
+  a.key_mask = p.key_mask; a.mask_bs = p.mask_bs;
+  a.scale_log2e = p.qscale * 1.4426950408889634f;
+  a.talk = p.talk;
+  a.o = reinterpret_cast<bf16*>(p.o); a.o_bs = p.o_bs; a.o_rs = p.o_rs;
+  a.k0 = k; a.v0 = v; a.k_bs = p.k_bs; a.v_bs = p.v_bs;
+  return launch_umma(qm, km, a, stream);
 }
 
 }  // namespace nuwa

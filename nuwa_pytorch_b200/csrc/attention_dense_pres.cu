@@ -453,12 +453,9 @@ int attn_dense_pres(const AttnParams& p, int nk, cudaStream_t stream) {
   a.talk = p.talk; a.null_k = p.null_k; a.null_v = p.null_v;
   a.key_mask = p.key_mask; a.mask_bs = p.mask_bs;
   a.o = reinterpret_cast<bf16*>(p.o); a.o_bs = p.o_bs; a.o_rs = p.o_rs;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(attn_dense_pres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
-      return NUWA_ERR_CUDA;
-    attr = true;
-  }
+  static const cudaError_t attr_rc =   // one-time, thread-safe static initialisation, immutable afterwards
+      cudaFuncSetAttribute(attn_dense_pres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (attr_rc != cudaSuccess) return NUWA_ERR_CUDA;
   const int grid = p.B * ((p.nq + PQ - 1) / PQ);
   attn_dense_pres_kernel<<<grid, (NH + 1) * 32, SMEM_BYTES, stream>>>(qm, km, vm, a);
   NUWA_CHECK_LAUNCH();

@@ -335,12 +335,9 @@ int attn_dense_x64(const AttnParams& p, int nk, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(p.q) & 15) || (reinterpret_cast<uintptr_t>(p.k) & 15) || (reinterpret_cast<uintptr_t>(p.v) & 15))
     return NUWA_ERR_INVALID;
   const size_t smem = (size_t)(XQ + 2 * XS * XK) * XP * 2 + (size_t)2 * 4 * XH * 16 * EXP * 2 + (64 + 2 * XC + 3 * XQ * XH) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(attn_dense_x64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return NUWA_ERR_CUDA;
-    attr = true;
-  }
+  static const cudaError_t attr_rc =   // one-time, thread-safe static initialisation (smem is a compile-time constant)
+      cudaFuncSetAttribute(attn_dense_x64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (attr_rc != cudaSuccess) return NUWA_ERR_CUDA;
   const int grid = p.B * ((p.nq + XQ - 1) / XQ);
   attn_dense_x64_kernel<<<grid, XT, smem, stream>>>(p, nk);
   NUWA_CHECK_LAUNCH();

@@ -563,45 +563,53 @@ static int pick_bn(int num_m_tiles, int N, int force_bn) {
 }
 
 // ---- optional per-launch timing of this kernel (bench.py roofline): CUDA events on the launch stream ----
-static bool g_prof_on = false;
-static std::vector<cudaEvent_t> g_prof_ev;  // start/stop pairs
-static size_t g_prof_used = 0;
-static double g_prof_flops = 0.0;
-static double g_cur_flops = 0.0;
-static double g_prof_bytes = 0.0;  // algorithmic HBM bytes: operands once + outputs once
-static double g_cur_bytes = 0.0;
-static double g_prof_bytes_last = 0.0;
+// No process-global mutable state: a profiler is an object the caller opens, ATTACHES TO ITS HOST THREAD, collects from and
+// closes (nuwa_gemm_prof_* in include/nuwa_b200.h).  Launches made by a thread with no profiler attached record nothing;
+// two threads with their own profilers do not see each other.
+struct GemmProf {
+  std::vector<cudaEvent_t> ev;  // start / stop pairs
+  size_t used = 0;
+  double flops = 0.0, bytes = 0.0, bytes_last = 0.0;
+};
+static thread_local GemmProf* t_prof = nullptr;
+static thread_local double t_cur_flops = 0.0;   // algorithmic work of the call being dispatched on this thread
+static thread_local double t_cur_bytes = 0.0;   // algorithmic HBM bytes: operands once + outputs once
 
-void gemm_prof_enable(int on) {
-  g_prof_on = on != 0;
-  g_prof_used = 0;
-  g_prof_flops = 0.0;
-  g_prof_bytes = 0.0;
+void* gemm_prof_open() { return new GemmProf(); }
+void gemm_prof_attach(void* h) { t_prof = reinterpret_cast<GemmProf*>(h); }
+void gemm_prof_close(void* h) {
+  GemmProf* g = reinterpret_cast<GemmProf*>(h);
+  if (g == nullptr) return;
+  if (t_prof == g) t_prof = nullptr;
+  for (cudaEvent_t e : g->ev) cudaEventDestroy(e);
+  delete g;
 }
-double gemm_prof_bytes() { return g_prof_bytes_last; }
-// Caller must have synchronised the stream(s).  Returns the number of timed launches.
-int gemm_prof_collect(double* flops, float* ms) {
+double gemm_prof_bytes(void* h) { return h ? reinterpret_cast<GemmProf*>(h)->bytes_last : 0.0; }
+// Caller must have synchronised the stream(s).  Returns the number of timed launches and resets the counters.
+int gemm_prof_collect(void* h, double* flops, float* ms) {
+  GemmProf* g = reinterpret_cast<GemmProf*>(h);
+  if (g == nullptr) return 0;
   float total = 0.f;
-  for (size_t i = 0; i + 1 < g_prof_used; i += 2) {
+  for (size_t i = 0; i + 1 < g->used; i += 2) {
     float t = 0.f;
-    if (cudaEventElapsedTime(&t, g_prof_ev[i], g_prof_ev[i + 1]) == cudaSuccess) total += t;
+    if (cudaEventElapsedTime(&t, g->ev[i], g->ev[i + 1]) == cudaSuccess) total += t;
   }
-  int n = (int)(g_prof_used / 2);
-  if (flops) *flops = g_prof_flops;
-  g_prof_bytes_last = g_prof_bytes;
-  g_prof_bytes = 0.0;
+  const int n = (int)(g->used / 2);
+  if (flops) *flops = g->flops;
   if (ms) *ms = total;
-  g_prof_used = 0;
-  g_prof_flops = 0.0;
+  g->bytes_last = g->bytes;
+  g->bytes = 0.0;
+  g->flops = 0.0;
+  g->used = 0;
   return n;
 }
-static cudaEvent_t prof_event() {
-  if (g_prof_used == g_prof_ev.size()) {
+static cudaEvent_t prof_event(GemmProf* g) {
+  if (g->used == g->ev.size()) {
     cudaEvent_t e;
     cudaEventCreate(&e);
-    g_prof_ev.push_back(e);
+    g->ev.push_back(e);
   }
-  return g_prof_ev[g_prof_used++];
+  return g->ev[g->used++];
 }
 
 template <int BN>
@@ -609,13 +617,10 @@ static int launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, const CUten
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
-        cudaSuccess)
-      return NUWA_ERR_CUDA;
-    attr_set = true;
-  }
+  // one-time, thread-safe (C++11 static initialisation), immutable afterwards
+  static const cudaError_t attr_rc =
+      cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  if (attr_rc != cudaSuccess) return NUWA_ERR_CUDA;
   p.num_n_tiles = ceil_div(p.N, BN);
   if (p.splits <= 1) { p.splits = 1; p.kb_per_split = p.k_blocks; }
   if (p.splits > 1) {  // as many work items as keep every SM busy, every split non-empty
@@ -629,12 +634,13 @@ static int launch_gemm(const CUtensorMap* mA, const CUtensorMap& mB, const CUten
   int total = p.num_m_tiles * p.num_n_tiles * p.splits;
   int grid = total < device_sm_count() ? total : device_sm_count();
   if (grid <= 0) return NUWA_OK;
-  if (g_prof_on) cudaEventRecord(prof_event(), stream);
+  GemmProf* prof = t_prof;
+  if (prof) cudaEventRecord(prof_event(prof), stream);
   gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mA[0], mA[1], mA[2], mA[3], mB, mC, p);
-  if (g_prof_on) {
-    cudaEventRecord(prof_event(), stream);
-    g_prof_flops += g_cur_flops;
-    g_prof_bytes += g_cur_bytes;
+  if (prof) {
+    cudaEventRecord(prof_event(prof), stream);
+    prof->flops += t_cur_flops;
+    prof->bytes += t_cur_bytes;
   }
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
@@ -719,10 +725,10 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   int e = encode_map(&mA[0], A, 2, dimsA, strA, boxA);
   if (e) return e;
   mA[1] = mA[0]; mA[2] = mA[0]; mA[3] = mA[0];
-  g_cur_flops = 2.0 * (double)M * (double)N * (double)K;
+  t_cur_flops = 2.0 * (double)M * (double)N * (double)K;
   {
     const double n_out = (act == ACT_GLU || act == ACT_GEGLU) ? N / 2.0 : (double)N;
-    g_cur_bytes = 2.0 * ((double)M * K + (double)N * K) + (double)M * n_out * ((out_f32 ? 4.0 : 0.0) + (out_bf16 ? 2.0 : 0.0)) +
+    t_cur_bytes = 2.0 * ((double)M * K + (double)N * K) + (double)M * n_out * ((out_f32 ? 4.0 : 0.0) + (out_bf16 ? 2.0 : 0.0)) +
                   (residual ? 4.0 * M * n_out : 0.0);
   }
   return dispatch_gemm(mA, W, p, force_bn, stream);
@@ -805,10 +811,10 @@ int conv2d_nhwc_bf16(const void* x, const void* w, int B, int Hin, int Win, int 
         p.tap_dx[t] = (int8_t)((kw - 1 - px) / 2);
       }
   }
-  g_cur_flops = 2.0 * (double)p.M * (double)Cout * (double)(ntaps * Cin);  // algorithmic (un-padded) MACs x 2
+  t_cur_flops = 2.0 * (double)p.M * (double)Cout * (double)(ntaps * Cin);  // algorithmic (un-padded) MACs x 2
   {
     const double n_out = (act == ACT_GLU || act == ACT_GEGLU) ? Cout / 2.0 : (double)Cout;
-    g_cur_bytes = 2.0 * ((double)B * Hin * Win * Cin + (double)Cout * ntaps * Cin) +
+    t_cur_bytes = 2.0 * ((double)B * Hin * Win * Cin + (double)Cout * ntaps * Cin) +
                   (double)p.M * n_out * ((out_f32 ? 4.0 : 0.0) + (out_bf16 ? 2.0 : 0.0)) + (residual ? 4.0 * p.M * n_out : 0.0);
   }
   return dispatch_gemm(mA, w, p, force_bn, stream);

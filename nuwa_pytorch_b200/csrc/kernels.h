@@ -51,15 +51,18 @@ int conv2d_nhwc_bf16(const void* x, const void* w, int B, int Hin, int Win, int 
                      cudaStream_t stream);
 
 
-void gemm_prof_enable(int on);
-int gemm_prof_collect(double* flops, float* ms);
-double gemm_prof_bytes();
+void* gemm_prof_open();
+void gemm_prof_attach(void* h);
+int gemm_prof_collect(void* h, double* flops, float* ms);
+double gemm_prof_bytes(void* h);
+void gemm_prof_close(void* h);
 
 // attention.cu
 int attn_sparse3dna(const AttnParams& p, cudaStream_t s);
 int attn_dense(const AttnParams& p, cudaStream_t s);
 int attn_3dna_halo(const AttnParams& p, cudaStream_t stream);           // attention_3dna_halo.cu
 int attn_3dna_umma(const AttnParams& p, cudaStream_t stream);           // attention_3dna_umma.cu
+int attn_cross2dna_umma(const AttnParams& p, cudaStream_t stream);      // attention_3dna_umma.cu
 int attn_dense_mma(const AttnParams& p, int nk, void* vT_ws, cudaStream_t stream);  // attention_mma.cu
 int attn_dense_x64(const AttnParams& p, int nk, cudaStream_t stream);                // attention_x64.cu
 int attn_dense_pres(const AttnParams& p, int nk, cudaStream_t stream);               // attention_dense_pres.cu

@@ -255,7 +255,9 @@ def attn_dense(q_ptr, k_ptr, v_ptr, o, *, B, nq, nk, H, dh, q_bs, q_rs, k_bs, k_
 
 
 def attn_cross2dna(q_ptr, k_ptr, v_ptr, o_ptr, *, B, nq, t0, H, dh, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs,
-                   talk, null_k, null_v, key_mask, fmap, frames, ck, cdil):
+                   talk, null_k, null_v, key_mask, fmap, frames, ck, cdil, variant='auto'):
+    """SparseCross2DNA non-bos queries.  variant 'auto': the tcgen05 / TMEM kernel when the call is inside its envelope and
+    has enough 128-query tiles to occupy the machine, else the gather kernel; 'umma' / 'gather' force one (tests, tools)."""
     p = _attn_base(q_ptr, k_ptr, v_ptr, o_ptr, B, nq, t0, H, dh, q_bs, k_bs, v_bs, o_bs, q_rs, k_rs, v_rs, o_rs, talk)
     p.null_k, p.null_v = ptr(null_k), ptr(null_v)
     if key_mask is not None:
@@ -263,6 +265,11 @@ def attn_cross2dna(q_ptr, k_ptr, v_ptr, o_ptr, *, B, nq, t0, H, dh, q_bs, q_rs, 
         p.key_mask, p.mask_bs = ptr(key_mask), key_mask.shape[1]
     p.fmap, p.ck, p.cdil = fmap, ck, cdil
     p.jmax = 1 + frames * ck * ck
+    if variant == 'umma' or (variant == 'auto' and nq > 1 and B * ((nq + 255) // 256) * 8 >= 64):
+        rc = lib().nuwa_attn_cross2dna_umma(p, stream())
+        if rc != _lib.NUWA_ERR_INVALID or variant == 'umma':
+            check(rc, "nuwa_attn_cross2dna_umma")
+            return
     check(lib().nuwa_attn_cross2dna(p, stream()), "nuwa_attn_cross2dna")
 
 

@@ -116,6 +116,58 @@ def test_sparse3dna_umma_kernel_matches_gather_kernel(cuda_device, kernel, dil, 
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,frames,cdil,B,masked,talk_on", [
+    (2561, 3, 1, 2, True, True), (2561, 3, 2, 2, True, True), (2561, 3, 4, 2, False, True), (1281, 5, 1, 1, True, True),
+    (1000, 1, 2, 3, True, False), (258, 2, 4, 2, True, True), (2, 3, 1, 2, True, True), (17, 4, 2, 1, False, True),
+    (2561, 3, 1, 9, True, True)])
+def test_cross2dna_umma_kernel_matches_gather_kernel_and_oracle(cuda_device, n, frames, cdil, B, masked, talk_on):
+    """SparseCross2DNA (nuwa_pytorch.py:851-895) on the tcgen05 / TMEM kernel (separate query and context buffers, unit =
+    context frame, learned null key / value in slot 0, context mask on the gathered scores) vs the gather kernel on
+    identical bf16 operands, and vs the fp32 oracle of the layer core; ragged last frame, fully masked context frame,
+    one- and two-class tiles, more tiles than SMs."""
+    from nuwa_pytorch_b200 import ops
+    H, dh, fmap, ck = 8, 64, 16, 3
+    inner, nk = H * dh, frames * fmap * fmap
+    g = gen(n * 3 + frames * 17 + cdil)
+    q = torch.randn(B, n, inner, generator=g).bfloat16()
+    kv = torch.randn(B, nk, 2 * inner, generator=g).bfloat16()
+    talk = torch.randn(H, H, generator=g) / 2 if talk_on else None
+    null_k, null_v = torch.randn(inner, generator=g), torch.randn(inner, generator=g)
+    mask = None
+    if masked:
+        mask = torch.rand(B, nk, generator=g) > 0.3
+        mask[0, :fmap * fmap] = False          # a whole context frame masked
+        mask[-1, -40:] = False
+    dv_ = lambda t: None if t is None else t.to(cuda_device).contiguous()
+    qd, kvd = dv_(q), dv_(kv)
+    common = dict(B=B, nq=n - 1, t0=1, H=H, dh=dh, q_bs=n * inner, q_rs=inner, k_bs=nk * 2 * inner, k_rs=2 * inner,
+                  v_bs=nk * 2 * inner, v_rs=2 * inner, o_bs=n * inner, o_rs=inner, talk=dv_(talk), null_k=dv_(null_k),
+                  null_v=dv_(null_v), key_mask=dv_(mask.to(torch.uint8)) if masked else None, fmap=fmap, frames=frames, ck=ck,
+                  cdil=cdil)
+    outs = {}
+    for variant in ('gather', 'umma'):
+        o = torch.full((B, n, inner), float('nan'), dtype=torch.bfloat16, device=cuda_device)
+        o[:, 0] = 0  # the bos query belongs to the dense kernel
+        ops.attn_cross2dna(qd.data_ptr() + inner * 2, kvd.data_ptr(), kvd.data_ptr() + inner * 2, o.data_ptr() + inner * 2,
+                           variant=variant, **common)
+        torch.cuda.synchronize()
+        assert torch.isfinite(o.float()).all(), variant
+        outs[variant] = o.float().cpu()
+    r = rel(outs['umma'], outs['gather'])
+    print(f"  x2dna umma vs gather n={n} frames={frames} d={cdil} B={B} masked={masked}: rel {r:.2e}")
+    assert r < 4e-3  # P' is rounded to bf16 for the tensor-core PV (both outputs are bf16)
+    if B <= 3:
+        eye = torch.eye(inner)
+        tk = talk if talk_on else torch.eye(H)
+        p = {'to_q.weight': eye, 'to_kv.weight': torch.eye(2 * inner), 'to_out.weight': eye,
+             'talking_heads.weight': tk[:, :, None, None, None], 'null_k': null_k.view(H, 1, dh), 'null_v': null_v.view(H, 1, dh)}
+        ref = O.sparse_cross2dna(q.float(), p, H, kv.float(), mask, fmap, ck, cdil)
+        ro = rel(outs['umma'][:, 1:], ref[:, 1:])
+        print(f"     vs oracle: rel {ro:.2e}")
+        assert ro < 6e-3
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("kernel,dil,nv,B,talk_on", [((5, 3, 3), (1, 1, 1), 768, 2, True), ((5, 3, 3), (2, 2, 2), 1279, 2, True),
                                                      ((5, 3, 3), (4, 4, 4), 2559, 3, True), ((5, 3, 3), (1, 2, 4), 601, 1, True),
                                                      ((3, 3, 5), (2, 4, 2), 530, 2, False), ((3, 1, 3), (1, 1, 3), 256, 2, True),
