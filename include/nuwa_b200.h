@@ -339,6 +339,12 @@ int nuwa_conv1x1_nhwc_to_nchw(const void* x, const float* w, const float* bias, 
  * atomics).  The weight-gradient GEMMs dW = dY^T X have a small output and a long contraction (K = tokens). */
 int nuwa_gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out_f32,
                           int ld_out, int splits, int force_bn, void* stream);
+/* out_f32[M,N] += At^T @ Wt with BOTH operands stored contraction-major: At is [K][M] (row stride lda), Wt is [K][N] (row
+ * stride ldw), K = tokens.  This is dW = dY^T X (the weight gradient of nn.Linear under autograd, nuwa_pytorch.py:274,277,
+ * 311-313,401-405,1819) on dY and X exactly as the passes hold them: the tcgen05 instruction reads both operands MN-major
+ * from the 128-byte-swizzled tiles TMA drops (instruction-descriptor a_major = b_major = 1), no transposed copies. */
+int nuwa_gemm_bf16_tn_splitk(const void* At, int lda, const void* Wt, int ldw, int M, int N, int K, float* out_f32,
+                             int ld_out, int splits, int force_bn, void* stream);
 
 /* Batched small GEMM on mma.sync (attention backward products), see csrc/bgemm.cu.
  *   C[i1][i2] (M x N) = alpha * A(M x K) * B(K x N)  (+ C if accumulate; fp32 C only)

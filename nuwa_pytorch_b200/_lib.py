@@ -157,6 +157,8 @@ SIGNATURES = {
     "nuwa_conv1x1_nhwc_to_nchw": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     # ---- training (backward) ----
     "nuwa_gemm_bf16_splitk": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+    "nuwa_gemm_bf16_tn_splitk": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                 c_void_p],
     "nuwa_bgemm": [P(BgemmParams), c_void_p],
     "nuwa_ln_bwd_grid": [c_int],
     "nuwa_ln_bwd": [P(LnBwdParams), c_void_p],

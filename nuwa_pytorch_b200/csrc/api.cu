@@ -184,6 +184,10 @@ int nuwa_gemm_bf16_splitk(const void* A, int lda, const void* W, int ldw, int M,
   return gemm_bf16(A, lda, W, ldw, M, N, K, nullptr, nullptr, 0, out_f32, nullptr, ld_out, ACT_NONE, force_bn, S(stream),
                    splits < 2 ? 2 : splits);
 }
+int nuwa_gemm_bf16_tn_splitk(const void* At, int lda, const void* Wt, int ldw, int M, int N, int K, float* out_f32,
+                             int ld_out, int splits, int force_bn, void* stream) {
+  return gemm_bf16_tn_splitk(At, lda, Wt, ldw, M, N, K, out_f32, ld_out, splits < 2 ? 2 : splits, force_bn, S(stream));
+}
 int nuwa_bgemm(const nuwa_bgemm_params* p, void* stream) { return p ? bgemm(*p, S(stream)) : NUWA_ERR_INVALID; }
 int nuwa_ln_bwd_grid(int rows) { return ln_bwd_grid(rows); }
 int nuwa_ln_bwd(const nuwa_lnbwd_params* p, void* stream) { return p ? ln_bwd(*p, S(stream)) : NUWA_ERR_INVALID; }

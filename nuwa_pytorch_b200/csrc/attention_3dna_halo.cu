@@ -75,14 +75,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
-// The producer warp and the query-row warps meet at ONE CTA-wide barrier from two different call sites; as two
-// __syncthreads() that is a barrier in divergent code (compute-sanitizer synccheck objects), as a named barrier with an
-// explicit thread count it is well defined.
-// (__syncwarp first: the producer warp arrives right after a lane-0-only section and must be reconverged.)
-__device__ __forceinline__ void cta_bar() {
-  __syncwarp();
-  asm volatile("bar.sync 1, %0;" ::"n"((QR + 1) * 32) : "memory");
-}
+// The producer warp and the query-row warps meet at ONE CTA-wide barrier, at a single call site.
+__device__ __forceinline__ void cta_bar() { __syncthreads(); }
 
 struct HaloArgs {
   int B, nv, nf, tiles;
@@ -154,11 +148,29 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
   const int n_a = kt - a_lo;
   const int NS1 = NH * n_a, NS = 2 * NS1;
 
-  if (warp == QR) {
-    // =============================== producer ===============================
-    // Lane 0 initialises the barriers and starts the first loads BEFORE the CTA-wide sync, so the first key rows
-    // (DRAM latency: the layer's q|k|v was just written by the projection GEMM) travel while the query-row warps
-    // set up their shared-memory state.
+  // ---- one-time shared-memory state of the query-row warps ----
+  auto one_time_state = [&]() {
+    float* Sw = S32 + warp * GW * SP;
+    for (int i = lane; i < GW * SP; i += 32) Sw[i] = -FLT_MAX;
+    const int nz = PP - p.J;  // slots J .. PP-1 stay zero (pair padding + the always-zero slot)
+    for (int i = lane; i < NH * GW * nz; i += 32) {
+      const int row = i / nz, z = i - row * nz;
+      const int h = row / GW, x = row - h * GW;
+      P16[(size_t)(h * QR * GW + warp * GW + x) * PP + p.J + z] = __float2half(0.f);
+    }
+    // bos key / value rows of this sample (sequence row 0), all heads
+    const uint4* src = reinterpret_cast<const uint4*>(tid < 64 ? p.k0 + (long long)b * p.k_bs : p.v0 + (long long)b * p.v_bs);
+    reinterpret_cast<uint4*>(kbos)[tid] = __ldg(src + (tid & 63));
+    if (tid < NH * NH) Wsm[tid] = p.talk ? __ldg(p.talk + tid) : ((tid / NH) == (tid % NH) ? 1.f : 0.f);
+  };
+
+  // =============================== producer state (warp QR) ===============================
+  // Lane 0 initialises the barriers and starts the first loads BEFORE the CTA-wide sync, so the first key rows
+  // (DRAM latency: the layer's q|k|v was just written by the projection GEMM) travel while the query-row warps
+  // set up their shared-memory state.  Both roles meet at ONE barrier instruction (a single call site: the two
+  // roles arriving from different program counters is what compute-sanitizer synccheck reports as divergence).
+  const bool is_producer = warp == QR;
+  {
     uint32_t qmask = 0, rowmask = 0;
     int tok_q[QR], tok_k[NROW];
 #pragma unroll
@@ -208,7 +220,7 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
         if (++ai == n_a) { ai = 0; if (++h == NH) { h = 0; ph = 1; } }
       }
     };
-    if (lane == 0) {
+    if (is_producer && lane == 0) {
       for (int i = 0; i < NST; ++i) {
         mbar_init(&full[i], 1);
         mbar_init(&empty[i], QR);
@@ -220,30 +232,17 @@ attn_3dna_halo_kernel(const __grid_constant__ CUtensorMap qmap, const HaloArgs p
       issue_q(0);
       produce(min(NST, n_a));  // head 0 only: later heads wait for the query-row warps, which start after the sync
     }
-    cta_bar();  // pairs with the query-row warps' barrier below
-    if (lane == 0) {
-      produce(NS);
-      if (DBG && p.dbg != nullptr && blockIdx.x == 0) p.dbg[23] = prod_wait;
+    if (!is_producer) one_time_state();
+    cta_bar();  // barriers initialised (producer), shared state written (query-row warps)
+    if (is_producer) {
+      if (lane == 0) {
+        produce(NS);
+        if (DBG && p.dbg != nullptr && blockIdx.x == 0) p.dbg[23] = prod_wait;
+      }
+      return;
     }
-    return;
   }
 
-  // ---- one-time shared-memory state of the query-row warps ----
-  {
-    float* Sw = S32 + warp * GW * SP;
-    for (int i = lane; i < GW * SP; i += 32) Sw[i] = -FLT_MAX;
-    const int nz = PP - p.J;  // slots J .. PP-1 stay zero (pair padding + the always-zero slot)
-    for (int i = lane; i < NH * GW * nz; i += 32) {
-      const int row = i / nz, z = i - row * nz;
-      const int h = row / GW, x = row - h * GW;
-      P16[(size_t)(h * QR * GW + warp * GW + x) * PP + p.J + z] = __float2half(0.f);
-    }
-    // bos key / value rows of this sample (sequence row 0), all heads
-    const uint4* src = reinterpret_cast<const uint4*>(tid < 64 ? p.k0 + (long long)b * p.k_bs : p.v0 + (long long)b * p.v_bs);
-    reinterpret_cast<uint4*>(kbos)[tid] = __ldg(src + (tid & 63));
-    if (tid < NH * NH) Wsm[tid] = p.talk ? __ldg(p.talk + tid) : ((tid / NH) == (tid % NH) ? 1.f : 0.f);
-  }
-  cta_bar();  // barriers initialised (producer), shared state written
 
   // =============================== query-row warps ===============================
   const int yq = y0 + warp * p.dh;

@@ -139,7 +139,35 @@ attn_dense_pres_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_co
   const int NS = 1 + 2 * nchunk;  // Q tile, K chunks, V chunks
   const bool has_null = p.null_k != nullptr;
 
-  if (warp == NH) {
+  // ---- one-time shared state of the 8 head warps ----
+  auto head_warp_state = [&]() {
+    for (int i = tid; i < INNER; i += NH * 32) {
+      nullk[i] = has_null ? __ldg(p.null_k + i) : 0.f;
+      nullv[i] = has_null ? __ldg(p.null_v + i) : 0.f;
+    }
+    if (tid < MAXK / 32) {
+      const unsigned char* km = p.key_mask != nullptr ? p.key_mask + (long long)b * p.mask_bs : nullptr;
+      uint32_t w = 0;
+      for (int i = 0; i < 32; ++i) {
+        const int j = tid * 32 + i;
+        if (j < p.nk && (km == nullptr || km[j] != 0)) w |= 1u << i;
+      }
+      maskw[tid] = w;
+    }
+    {  // slots nk_pad .. PP-1 of this warp's head: zero (the null slot is written in phase 1)
+      __half* Ph = P16 + (size_t)warp * HS;
+      const int z0 = nchunk * PK, nz = PP - z0;
+      for (int i = lane; i < PQ * nz; i += 32) {
+        const int q = i / nz, z = i - q * nz;
+        Ph[q * PP + z0 + z] = __float2half(0.f);
+      }
+    }
+  };
+
+  // Producer (warp NH) and head warps meet at ONE barrier instruction below (a single call site: arriving from two
+  // program counters is what compute-sanitizer synccheck reports as a divergent barrier).
+  const bool is_producer = warp == NH;
+  {
     // =============================== producer ===============================
     int st = 0, use = 0;
     auto produce = [&](int s_end) {
@@ -153,7 +181,7 @@ attn_dense_pres_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_co
         if (++st == NSTG) { st = 0; ++use; }
       }
     };
-    if (lane == 0) {
+    if (is_producer && lane == 0) {
       for (int i = 0; i < NSTG; ++i) {
         mbar_init(&full[i], 1);
         mbar_init(&empty[i], NH);
@@ -164,34 +192,13 @@ attn_dense_pres_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_co
       tma_prefetch_desc(&vmap);
       produce(NSTG);
     }
+    if (!is_producer) head_warp_state();
     __syncthreads();
-    if (lane == 0) produce(NS);
-    return;
-  }
-
-  // ---- one-time shared state of the 8 head warps ----
-  for (int i = tid; i < INNER; i += NH * 32) {
-    nullk[i] = has_null ? __ldg(p.null_k + i) : 0.f;
-    nullv[i] = has_null ? __ldg(p.null_v + i) : 0.f;
-  }
-  if (tid < MAXK / 32) {
-    const unsigned char* km = p.key_mask != nullptr ? p.key_mask + (long long)b * p.mask_bs : nullptr;
-    uint32_t w = 0;
-    for (int i = 0; i < 32; ++i) {
-      const int j = tid * 32 + i;
-      if (j < p.nk && (km == nullptr || km[j] != 0)) w |= 1u << i;
-    }
-    maskw[tid] = w;
-  }
-  {  // slots nk_pad .. PP-1 of this warp's head: zero (the null slot is written in phase 1)
-    __half* Ph = P16 + (size_t)warp * HS;
-    const int z0 = nchunk * PK, nz = PP - z0;
-    for (int i = lane; i < PQ * nz; i += 32) {
-      const int q = i / nz, z = i - q * nz;
-      Ph[q * PP + z0 + z] = __float2half(0.f);
+    if (is_producer) {
+      if (lane == 0) produce(NS);
+      return;
     }
   }
-  __syncthreads();
 
   const int h = warp;
   const int mat = lane >> 3, l7 = lane & 7;

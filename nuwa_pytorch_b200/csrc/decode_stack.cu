@@ -56,7 +56,8 @@ enum { DK_NORMAL = 0, DK_MASKED = 1, DK_ZERO = 2, DK_NULL = 3 };
 // shared-memory layout (same arithmetic on host and device)
 // ------------------------------------------------------------------------------------------------
 struct DsLayout {
-  int streams, act, red, S, pm, keys, ckeys, qs, wt, part, outs, lnp, bias, shs, nullkv, desc, kvs, kv_rs3, kv_rsx, total;
+  int streams, act, red, S, S2, pm, keys, ckeys, qs, wt, part, outs, lnp, bias, shs, nullkv, desc, kvbar, kvs, kv_rs3, kv_rsx,
+      kvs_bytes, total;
 };
 __host__ __device__ inline int ds_align16(int x) { return (x + 15) & ~15; }
 __host__ __device__ inline DsLayout ds_layout(int B, int D, int kmax, int H, int dh, int j3max, int nk) {
@@ -68,6 +69,7 @@ __host__ __device__ inline DsLayout ds_layout(int B, int D, int kmax, int H, int
   L.act = o;     o += ds_align16(B * kmax * 2);             // bf16 [B][kmax] operand rows of the current product
   L.red = o;     o += ds_align16(DS_WARPS * 2 * nt * 128 * 4);  // partial 16 x 8 tiles of the K slices (value | gate)
   L.S = o;       o += ds_align16(H * jmax * 4);             // scores / probabilities [H][J]
+  L.S2 = o;      o += ds_align16(H * j3max * 4);            // talking-heads output of the 3DNA window [H][J]
   L.pm = o;      o += ds_align16(jmax * 4);                 // mixed probabilities of one head
   L.keys = o;    o += ds_align16(j3max * 4);                // 3DNA key list of this sub-block: (kind << 28) | row
   L.ckeys = o;   o += ds_align16((nk + 1) * 4);             // cross-attention key list of this CTA's sample (whole launch)
@@ -80,12 +82,14 @@ __host__ __device__ inline DsLayout ds_layout(int B, int D, int kmax, int H, int
   L.shs = o;     o += ds_align16(B * (D / 2) * 2);          // shifted channel quarters of the ShiftVideoTokens gather
   L.nullkv = o;  o += ds_align16(2 * dh * 4);               // learned null key / value of this CTA's head, fp32
   L.desc = o;    o += 4 * ds_align16((int)sizeof(nuwa_decode_sub));  // previous / current / next / next-but-one descriptor
+  L.kvbar = o;   o += 32;                                   // mbarrier of the K / V bulk copies (8 B), slot of the new token in the 3DNA window (int), mbarrier of the norm-parameter bulk copies (8 B at +16)
   // staged K | V rows: 3DNA window of one sample (all heads) or the context head slices of one (sample, head);
   // row strides padded by 16 bytes so that lanes reading consecutive rows hit different banks
   L.kv_rs3 = H * dh * 2 + 16;
-  L.kv_rsx = dh * 2 + 16;
+  L.kv_rsx = dh * 2;  // dense rows (one bulk copy per slice); readers rotate their 16-byte chunks by the row index
   const int kv3 = 2 * j3max * L.kv_rs3, kvx = nk > 0 ? 2 * nk * L.kv_rsx : 0;
-  L.kvs = o;     o += ds_align16(kv3 > kvx ? kv3 : kvx);
+  L.kvs_bytes = ds_align16(kv3 > kvx ? kv3 : kvx);
+  L.kvs = o;     o += L.kvs_bytes;
   L.total = o;
   return L;
 }
@@ -105,19 +109,26 @@ struct GridBar {
   unsigned target;
 };
 
+// Measured alternatives (tools/decode_fence_ab.py, barriers-only mode, 2.9 us per barrier): relaxed polls + one acquire
+// fence, __nanosleep between polls, red instead of atom -- all within 3 % of each other; the cost is the L2 round trips.
 __device__ __forceinline__ void grid_barrier(GridBar& g) {
   __syncthreads();
   if (threadIdx.x == DS_WORK) {  // lane 0 of the sync warp
     g.target += g.nblocks;
     // release: everything this CTA wrote (ordered before by the CTA barrier) is visible to whoever acquires the count
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(g.count) : "memory");
-    long long t0 = 0;
-    unsigned spins = 0;
-    while (ld_acquire_u32(g.count) < g.target) {
-      ++spins;
-      if (spins == 4096u) t0 = clock64();
-      // watchdog: a protocol bug becomes a launch error instead of a hung GPU (~2 s)
-      if (spins > 4096u && (spins & 4095u) == 0u && (clock64() - t0) > 4000000000LL) __trap();
+    unsigned old;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(g.count) : "memory");
+    if (old + 1u == g.target) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");  // the last arriver has nothing to wait for
+    } else {
+      long long t0 = 0;
+      unsigned spins = 0;
+      while (ld_acquire_u32(g.count) < g.target) {
+        ++spins;
+        if (spins == 4096u) t0 = clock64();
+        // watchdog: a protocol bug becomes a launch error instead of a hung GPU (~2 s)
+        if (spins > 4096u && (spins & 4095u) == 0u && (clock64() - t0) > 4000000000LL) __trap();
+      }
     }
   }
   __syncthreads();
@@ -125,6 +136,12 @@ __device__ __forceinline__ void grid_barrier(GridBar& g) {
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine, no registers, one instruction per row), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // wait until at most N of the most recently committed groups are still pending
@@ -328,45 +345,69 @@ __device__ __forceinline__ void ds_row_stats(const float4 (&v)[DS_LNV], int nv, 
   rstd = rsqrtf(q / (float)D + 1e-5f);
 }
 
-// Requested well before the barrier that precedes the norms (cp.async, L2 -> shared memory, no registers held):
+// Requested well before the barrier that precedes the norms (bulk copies L2 -> shared memory issued by ONE thread, no
+// registers held; as 16-byte cp.async pieces the request itself cost ~1.2 us of issue work per sub-block):
 // lnp[0..1] = post-norm weight / bias of `prev`, lnp[2..3] = pre-norm weight / bias of `cur` (w2 / b2 when cur is
-// NULL: the final StableLayerNorm), shs[b][0:D/2] = the two shifted channel quarters of ShiftVideoTokens, taken from the pre-norm rows of positions t - fmap and t - 1 (zeros at the grid border).
-// Commits exactly one cp.async group.
+// NULL: the final StableLayerNorm), shs[b][0:D/2] = the two shifted channel quarters of ShiftVideoTokens, taken from the
+// pre-norm rows of positions t - fmap and t - 1 (zeros at the grid border).  Completes one phase of `lnbar`.
 __device__ __forceinline__ void prefetch_norms(const DecParams& p, const DecSub* prev, const DecSub* cur, const float* w2,
-                                               const float* b2, int t, float* lnp, bf16* shs) {
-  const int D = p.D, D4 = D / 4;
-  for (int i = ds_wtid(); i < 4 * D4; i += DS_WORK) {
-    const int arr = i / D4, k = i - arr * D4;
-    const float* src = arr == 0 ? (prev ? prev->post_w : nullptr)
-                     : arr == 1 ? (prev ? prev->post_b : nullptr)
-                     : arr == 2 ? (cur ? cur->pre_w : w2)
-                                : (cur ? cur->pre_b : b2);
-    if (src != nullptr) cp_async16(lnp + arr * D + k * 4, src + k * 4);
-  }
-  if (cur != nullptr && cur->shift && t >= 1) {
+                                               const float* b2, int t, float* lnp, bf16* shs, uint64_t* lnbar) {
+  const int D = p.D;
+  const bool shift = cur != nullptr && cur->shift && t >= 1;
+  int src_h = -1, src_w = -1;
+  if (shift) {
     const int T = p.fmap * p.fmap;
     const int pos = (t - 1) % T;
     const int row = pos / p.fmap, col = pos - row * p.fmap;
-    const int src_h = row > 0 ? t - p.fmap : -1, src_w = col > 0 ? t - 1 : -1;
-    const int q4 = D / 4, qp = D / 32;  // 16-byte pieces per channel quarter (bf16)
-    const bf16* sc = reinterpret_cast<const bf16*>(cur->shift_cache);
+    src_h = row > 0 ? t - p.fmap : -1;
+    src_w = col > 0 ? t - 1 : -1;
+  }
+  const int q4 = D / 4;
+  // one bulk copy per thread of warps 0-1 (a bulk-copy instruction costs its issuing thread ~150-250 cycles: issued by
+  // one thread, the ~20 copies were 3 us on the critical path); every one of the 64 threads arrives on lnbar
+  if (threadIdx.x < 64) {
+    const int i = threadIdx.x;
+    uint32_t tx = 0;
+    if (i < 4) {
+      const float* src = i == 0 ? (prev ? prev->post_w : nullptr)
+                       : i == 1 ? (prev ? prev->post_b : nullptr)
+                       : i == 2 ? (cur ? cur->pre_w : w2)
+                                : (cur ? cur->pre_b : b2);
+      if (src != nullptr) {
+        fence_proxy_async_smem();
+        bulk_g2s(lnp + i * D, src, (uint32_t)D * 4, lnbar);
+        tx = (uint32_t)D * 4;
+      }
+    } else if (shift && i - 4 < 2 * p.B) {
+      const int b = (i - 4) >> 1, quarter = (i - 4) & 1;
+      const int src = quarter == 0 ? src_h : src_w;
+      if (src >= 0) {
+        const bf16* sc = reinterpret_cast<const bf16*>(cur->shift_cache);
+        fence_proxy_async_smem();  // the zero-filled border quarters of an earlier sub-block were generic-proxy writes
+        bulk_g2s(shs + b * (D / 2) + quarter * q4, sc + ((long long)b * p.npos + src) * D + quarter * q4, (uint32_t)q4 * 2, lnbar);
+        tx = (uint32_t)q4 * 2;
+      }
+    }
+    if (tx) mbar_arrive_expect_tx(lnbar, tx);
+    else mbar_arrive(lnbar);
+  }
+  if (shift && (src_h < 0 || src_w < 0)) {  // grid border: the shifted-in quarter is zero
+    const int qp = D / 32;  // 16-byte pieces per channel quarter (bf16)
     for (int i = ds_wtid(); i < p.B * 2 * qp; i += DS_WORK) {
       const int b = i / (2 * qp), r = i - b * 2 * qp;
       const int quarter = r / qp, k = r - quarter * qp;
-      const int src = quarter == 0 ? src_h : src_w;
-      bf16* dst = shs + b * (D / 2) + quarter * q4 + k * 8;
-      if (src >= 0) cp_async16(dst, sc + ((long long)b * p.npos + src) * D + quarter * q4 + k * 8);
-      else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+      if ((quarter == 0 ? src_h : src_w) < 0)
+        *reinterpret_cast<uint4*>(shs + b * (D / 2) + quarter * q4 + k * 8) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
-  cp_async_commit();
 }
 
 // prev != NULL:  streams[prev->write] += LayerNorm_post(y)        (SandwichNorm tail + residual)
 // cur  != NULL:  As = bf16(LayerNorm_pre(streams[cur->read])) with the ShiftVideoTokens gather
-// The norm parameters (prefetch_norms) must be the OLDEST pending cp.async group but one.
+// Waits for the phase `ln_parity` of `lnbar` (the bulk copies of prefetch_norms).
 __device__ __forceinline__ void ln_prologue(const DecParams& p, const DecSub* prev, const DecSub* cur, int t, float* streams,
-                                            bf16* As, int lda_s, const float* lnp, const bf16* shs, int warp, int lane) {
+                                            bf16* As, int lda_s, const float* lnp, const bf16* shs, int warp, int lane,
+                                            uint64_t* lnbar, uint32_t ln_parity) {
   const int D = p.D, B = p.B;
   float4 v[DS_LNV];
   int nv = 0;
@@ -379,7 +420,7 @@ __device__ __forceinline__ void ln_prologue(const DecParams& p, const DecSub* pr
       if (i < nv) v[i] = __ldcg(reinterpret_cast<const float4*>(p.y + (long long)b * D + (lane + 32 * i) * 4));
   };
   if (warp < B && prev != nullptr) load_y(warp);  // the only loads that had to wait for the barrier
-  cp_async_wait<1>();
+  mbar_wait(lnbar, ln_parity);
   __syncthreads();
   for (int b = warp; b < B; b += DS_WARPS) {
     if (prev != nullptr) {
@@ -513,76 +554,29 @@ __device__ __forceinline__ float dot8q(const float* q, const uint4& u) {
   return q0.x * a.x + q0.y * a.y + q0.z * b2.x + q0.w * b2.y + q1.x * c.x + q1.y * c.y + q1.z * d.x + q1.w * d.y;
 }
 
-// scores of heads [0, nh): S[hl*J + j] = q[hl] . K_j[hl]; key slot j is staged at Ks + j * rs (bytes); null_k fp32 (smem)
-__device__ __forceinline__ void attn_scores(const float* qs, const int* keys, const uint8_t* Ks, int rs, const float* null_k,
-                                            int nh, int dh, int J, float* S) {
-  for (int item = threadIdx.x; item < nh * J; item += DS_THREADS) {
-    const int hl = item / J, j = item - hl * J;
-    const int kind = keys[j] >> 28;
-    const float* q = qs + hl * dh;
-    float s;
-    if (kind == DK_NORMAL) {
-      const uint4* kr = reinterpret_cast<const uint4*>(Ks + (size_t)j * rs + hl * dh * 2);
-      s = 0.f;
-      for (int i = 0; i < dh / 8; ++i) s += dot8q(q + i * 8, kr[i]);
-    } else if (kind == DK_NULL) {
-      s = 0.f;
-      for (int i = 0; i < dh; ++i) s += q[i] * null_k[hl * dh + i];
-    } else {
-      s = (kind == DK_MASKED) ? -FLT_MAX : 0.f;
-    }
-    S[item] = s;
-  }
-}
-
-// in-place fp32 softmax of rows [0, nh) of S (warp per row)
-__device__ __forceinline__ void attn_softmax(float* S, int nh, int J, int warp, int lane) {
-  for (int hl = warp; hl < nh; hl += DS_WARPS) {
-    float* Sw = S + hl * J;
-    float m = -FLT_MAX;
-    for (int j = lane; j < J; j += 32) m = fmaxf(m, Sw[j]);
-    m = warp_max(m);
-    float l = 0.f;
-    for (int j = lane; j < J; j += 32) {
-      const float e = __expf(Sw[j] - m);
-      Sw[j] = e;
-      l += e;
-    }
-    l = warp_sum(l);
-    const float inv = 1.0f / l;
-    for (int j = lane; j < J; j += 32) Sw[j] *= inv;
-  }
-}
-
-// out[hl*dh + c] = sum_j P[hl*J + j] * V_j[hl*dh + c]   for heads [0, nh); V slot j staged at Vs + j * rs (bytes)
-__device__ __forceinline__ void attn_pv(const float* P, const int* keys, const uint8_t* Vs, int rs, const float* null_v,
-                                        int nh, int dh, int J, float* part, float* outs) {
-  const int npairs = nh * dh / 2;
-  const int KG = DS_THREADS / npairs;  // key groups (>= 1: H*dh <= 1024)
+// out[c] = P[0] * null_v[c] + sum_{j=1..n} P[j] * V_{j-1}[c] for one head (dh channels): every thread takes a channel pair
+// and every KG-th key, no branches (masked slots carry P = 0 and finite stale V), partial sums reduced through `part`
+__device__ __forceinline__ void attn_pv_head(const float* P, const uint8_t* Vrows, int rs, const float* null_v, int dh, int n,
+                                             float* part, float* outs) {
+  const int npairs = dh / 2;
+  const int KG = DS_THREADS / npairs;
   const int cp = threadIdx.x % npairs, kg = threadIdx.x / npairs;
   if (kg < KG) {
-    const int hl = cp / (dh / 2), c2 = cp - hl * (dh / 2);
-    const float* Ph = P + hl * J;
-    const uint8_t* vcol = Vs + (hl * dh + 2 * c2) * 2;
+    const uint8_t* vcol = Vrows + cp * 4;
     float ax = 0.f, ay = 0.f;
-#pragma unroll 4
-    for (int j = kg; j < J; j += KG) {
-      const int kind = keys[j] >> 28;
-      if (kind == DK_NORMAL) {
-        const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vcol + (size_t)j * rs));
-        ax = fmaf(Ph[j], v.x, ax);
-        ay = fmaf(Ph[j], v.y, ay);
-      } else if (kind == DK_NULL) {
-        ax = fmaf(Ph[j], null_v[hl * dh + 2 * c2], ax);
-        ay = fmaf(Ph[j], null_v[hl * dh + 2 * c2 + 1], ay);
-      }
+#pragma unroll 8
+    for (int j = kg; j < n; j += KG) {
+      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vcol + (size_t)j * rs));
+      const float pj = P[j + 1];
+      ax = fmaf(pj, v.x, ax);
+      ay = fmaf(pj, v.y, ay);
     }
     part[(kg * npairs + cp) * 2 + 0] = ax;
     part[(kg * npairs + cp) * 2 + 1] = ay;
   }
   __syncthreads();
   if (threadIdx.x < npairs) {
-    float ax = 0.f, ay = 0.f;
+    float ax = P[0] * null_v[2 * threadIdx.x], ay = P[0] * null_v[2 * threadIdx.x + 1];
     for (int g = 0; g < KG; ++g) {
       ax += part[(g * npairs + threadIdx.x) * 2 + 0];
       ay += part[(g * npairs + threadIdx.x) * 2 + 1];
@@ -593,36 +587,55 @@ __device__ __forceinline__ void attn_pv(const float* P, const int* keys, const u
   __syncthreads();
 }
 
-// K / V prefetch of a sub-block's attention (cp.async; consumed two barriers later).  Commits exactly one group.
-//   3DNA:  CTA b < B stages the window rows of sample b that earlier steps wrote (row t, the new token, comes later)
-//   cross: CTA w < B*H stages the context K and V slices of its (sample, head), the head's null key / value
-//   both:  the talking-heads matrix; 3DNA (every CTA): the to_out bias
+// K / V prefetch of a sub-block's attention (consumed two barriers later).
+//   3DNA:  CTA b < B stages the window rows of sample b that earlier steps wrote (row t, the new token, comes later):
+//          ONE bulk copy per K row and per V row (all heads: inner * 2 contiguous bytes), issued by the thread that owns
+//          the key slot -- a per-16-byte cp.async loop here was ~5 us of issue work on the critical path of every CTA
+//          that waits for these B CTAs at the next barrier
+//   cross: CTA w < B*H stages the context K and V slices of its (sample, head) (dh * 2 bytes per row), the head's
+//          null key / value
+//   both:  the talking-heads matrix; 3DNA (every CTA): the to_out bias (cp.async)
+// The bulk copies complete on the `kvbar` mbarrier (every worker thread arrives once, with the bytes it requested);
+// slots that are not loaded (masked / zero keys) keep stale but finite bf16 data: their probabilities are forced to
+// zero before PV and their scores are replaced, so the contents never matter.  Commits exactly one cp.async group.
 __device__ __forceinline__ void prefetch_kv(const DecParams& p, const DecSub* s, const DsLayout& L, uint8_t* smem, int t) {
   const int H = p.H, dh = p.dh, inner = H * dh;
+  uint64_t* kvbar = reinterpret_cast<uint64_t*>(smem + L.kvbar);
   if (s->kind == NUWA_DEC_3DNA) {
     if (s->b_out != nullptr)  // every CTA adds the to_out bias in phase 3
       for (int i = ds_wtid(); i < p.D / 4; i += DS_WORK) cp_async16(smem + L.bias + i * 16, s->b_out + i * 4);
     if ((int)blockIdx.x < p.B && t > 0) {
       const int b = blockIdx.x;
       int* keys = reinterpret_cast<int*>(smem + L.keys);
+      int* self_slot = reinterpret_cast<int*>(smem + L.kvbar + 8);
       const int J = 1 + s->kt * s->kh * s->kw;
+      if (threadIdx.x == 0) *self_slot = -1;
+      __syncthreads();
       for (int j = threadIdx.x; j < J; j += DS_THREADS) {
         int row = 0;
         const int kd = key3dna(p, *s, t, t, j, row);
         keys[j] = (kd << 28) | row;
+        if (kd == DK_NORMAL && row == t) *self_slot = j;  // the new token's own slot (at most one: offsets are distinct)
       }
       __syncthreads();
       const bf16* cb = reinterpret_cast<const bf16*>(s->cache) + (long long)b * p.npos * 3 * inner;
       uint8_t* Ks = smem + L.kvs;
       uint8_t* Vs = Ks + (size_t)J * L.kv_rs3;
-      const int pieces = inner / 8;  // 16-byte pieces per row
-      for (int i = ds_wtid(); i < J * 2 * pieces; i += DS_WORK) {
-        const int j = i / (2 * pieces), r = i - j * 2 * pieces;
-        const int kv = r / pieces, k = r - kv * pieces;
-        const int kj = keys[j];
-        const int row = kj & 0x0FFFFFFF;
-        if ((kj >> 28) == DK_NORMAL && row != t)
-          cp_async16((kv ? Vs : Ks) + (size_t)j * L.kv_rs3 + k * 16, cb + (long long)row * 3 * inner + (1 + kv) * inner + k * 8);
+      if (threadIdx.x < DS_WORK) {
+        fence_proxy_async_smem();  // earlier generic-proxy reads / writes of the staging area come before the bulk writes
+        uint32_t tx = 0;
+        for (int j = threadIdx.x; j < J; j += DS_WORK) {
+          const int kj = keys[j];
+          const int row = kj & 0x0FFFFFFF;
+          if ((kj >> 28) == DK_NORMAL && row != t) {
+            const bf16* src = cb + (long long)row * 3 * inner + inner;
+            bulk_g2s(Ks + (size_t)j * L.kv_rs3, src, (uint32_t)inner * 2, kvbar);
+            bulk_g2s(Vs + (size_t)j * L.kv_rs3, src + inner, (uint32_t)inner * 2, kvbar);
+            tx += (uint32_t)inner * 4;
+          }
+        }
+        if (tx) mbar_arrive_expect_tx(kvbar, tx);
+        else mbar_arrive(kvbar);
       }
       for (int i = ds_wtid(); i < H * H / 4; i += DS_WORK)
         cp_async16(smem + L.wt + i * 16, s->talk + i * 4);
@@ -630,16 +643,21 @@ __device__ __forceinline__ void prefetch_kv(const DecParams& p, const DecSub* s,
   } else if (s->kind == NUWA_DEC_CROSS) {
     if ((int)blockIdx.x < p.B * H) {
       const int b = blockIdx.x / H, h = blockIdx.x - b * H;
-      const int* ckeys = reinterpret_cast<const int*>(smem + L.ckeys);
-      const bf16* kv = reinterpret_cast<const bf16*>(s->cache) + (long long)b * p.nk * 2 * inner + h * dh;
+      // context K / V of this (sample, head): packed [B][H][2][nk][dh] by the host (engine.FusedDecode), so each slice is
+      // ONE contiguous bulk copy; masked rows come along (their probabilities are exactly 0)
+      const bf16* kv = reinterpret_cast<const bf16*>(s->cache) + ((long long)b * H + h) * 2 * p.nk * dh;
       uint8_t* Ks = smem + L.kvs;
       uint8_t* Vs = Ks + (size_t)p.nk * L.kv_rsx;
-      const int pieces = dh / 8;
-      for (int i = ds_wtid(); i < p.nk * 2 * pieces; i += DS_WORK) {
-        const int row = i / (2 * pieces), r = i - row * 2 * pieces;
-        const int sel = r / pieces, k = r - sel * pieces;
-        if ((ckeys[row + 1] >> 28) == DK_NORMAL)
-          cp_async16((sel ? Vs : Ks) + (size_t)row * L.kv_rsx + k * 16, kv + (long long)row * 2 * inner + sel * inner + k * 8);
+      if (threadIdx.x < DS_WORK) {
+        const uint32_t bytes = (uint32_t)p.nk * dh * 2;
+        if (threadIdx.x == 0) {
+          fence_proxy_async_smem();  // generic-proxy accesses of the staging area (made visible by the CTA barriers) first
+          bulk_g2s(Ks, kv, bytes, kvbar);
+          bulk_g2s(Vs, kv + (long long)p.nk * dh, bytes, kvbar);
+          mbar_arrive_expect_tx(kvbar, 2 * bytes);
+        } else {
+          mbar_arrive(kvbar);
+        }
       }
       float* nkv = reinterpret_cast<float*>(smem + L.nullkv);
       for (int i = ds_wtid(); i < 2 * (dh / 4); i += DS_WORK) {
@@ -659,7 +677,7 @@ __device__ __forceinline__ void prefetch_kv(const DecParams& p, const DecSub* s,
 #define DS_STAMP(id)                                                            \
   do {                                                                          \
     if (p.prof != nullptr && blockIdx.x == p.prof_cta && threadIdx.x == 0) {   \
-      p.prof[2 * nstamp] = (long long)(si * 16 + (id));                         \
+      p.prof[2 * nstamp] = (long long)(si * 32 + (id));                         \
       p.prof[2 * nstamp + 1] = clock64();                                       \
       ++nstamp;                                                                 \
     }                                                                           \
@@ -674,6 +692,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
   bf16* As = reinterpret_cast<bf16*>(ds_smem + L.act);
   float* red = reinterpret_cast<float*>(ds_smem + L.red);
   float* Ss = reinterpret_cast<float*>(ds_smem + L.S);
+  float* S2 = reinterpret_cast<float*>(ds_smem + L.S2);
   float* Pm = reinterpret_cast<float*>(ds_smem + L.pm);
   int* keys = reinterpret_cast<int*>(ds_smem + L.keys);
   int* ckeys = reinterpret_cast<int*>(ds_smem + L.ckeys);
@@ -685,6 +704,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
   bf16* shs = reinterpret_cast<bf16*>(ds_smem + L.shs);
   float* nullkv = reinterpret_cast<float*>(ds_smem + L.nullkv);
   uint8_t* kvs = ds_smem + L.kvs;
+  uint64_t* kvbar = reinterpret_cast<uint64_t*>(ds_smem + L.kvbar);
+  const int* self_slot = reinterpret_cast<const int*>(ds_smem + L.kvbar + 8);
+  uint64_t* lnbar = reinterpret_cast<uint64_t*>(ds_smem + L.kvbar + 16);
+  uint32_t kv_uses = 0, ln_uses = 0;  // phases of kvbar / lnbar consumed by this CTA
   constexpr int DESC_STRIDE = (sizeof(DecSub) + 15) & ~15;
   constexpr int DESC_WORDS = sizeof(DecSub) / 4;
   const int lda_s = p.kmax;
@@ -713,6 +736,14 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
       reinterpret_cast<uint32_t*>(ds_smem + L.desc + DESC_STRIDE)[threadIdx.x] =
           __ldg(reinterpret_cast<const uint32_t*>(p.subs + 1) + threadIdx.x);
   }
+  // the K / V staging area only ever holds bf16 data written by the bulk copies; start it from zeros so that slots
+  // that are never loaded (masked keys) read as finite values
+  for (int i = threadIdx.x; i < L.kvs_bytes / 16; i += DS_THREADS) reinterpret_cast<uint4*>(kvs)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) {
+    mbar_init(kvbar, DS_WORK);
+    mbar_init(lnbar, 64);
+    fence_barrier_init();
+  }
   if (p.nk > 0 && (int)blockIdx.x < B * H) {
     const int b = blockIdx.x / H;
     for (int j = threadIdx.x; j <= p.nk; j += DS_THREADS) {
@@ -727,7 +758,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
   __syncthreads();
   {
     const DecSub* s0 = reinterpret_cast<const DecSub*>(ds_smem + L.desc);
-    prefetch_norms(p, nullptr, s0, nullptr, nullptr, t, lnp, shs);
+    prefetch_norms(p, nullptr, s0, nullptr, nullptr, t, lnp, shs, lnbar);
   }
   DS_STAMP(0);
 
@@ -742,8 +773,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
     const int kind = s->kind;
     const bf16* Wa = reinterpret_cast<const bf16*>(s->w_a);
     const bf16* Wb = reinterpret_cast<const bf16*>(s->w_b);
-    // cp.async groups in commit order: norms(si) [during si-1], kv(si) [top of si], norms(si+1) [after the norms of si];
-    // each consumer waits with wait_group 1 = everything but the most recent group
+    // one cp.async group per sub-block (small attention parameters, committed by prefetch_kv); K / V rows and the norm
+    // parameters travel as bulk copies on their own mbarriers
     auto phase1 = [&]() {
       prefetch_kv(p, s, L, ds_smem, t);
       DS_STAMP(1);
@@ -751,10 +782,12 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
       DS_STAMP(2);
       if (has_next2)
         reinterpret_cast<uint32_t*>(ds_smem + L.desc + ((si + 2) % 4) * DESC_STRIDE)[threadIdx.x] = next_word;
-      if (!(dbg & 1)) ln_prologue(p, prev, s, t, streams, As, lda_s, lnp, shs, warp, lane);
-      else { cp_async_wait<1>(); __syncthreads(); }
+      if (!(dbg & 1)) ln_prologue(p, prev, s, t, streams, As, lda_s, lnp, shs, warp, lane, lnbar, ln_uses & 1u);
+      else { mbar_wait(lnbar, ln_uses & 1u); __syncthreads(); }
+      ++ln_uses;
+      DS_STAMP(10);
       // norm parameters of the NEXT sub-block (or of the final StableLayerNorm): >= two barriers ahead of their use
-      prefetch_norms(p, s, nxt, p.norm_w, p.norm_b, t, lnp, shs);
+      prefetch_norms(p, s, nxt, p.norm_w, p.norm_b, t, lnp, shs, lnbar);
       DS_STAMP(3);
     };
     if (kind == NUWA_DEC_3DNA) {
@@ -780,43 +813,91 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
           const int J = 1 + s->kt * s->kh * s->kw;
           uint8_t* Ks = kvs;
           uint8_t* Vs = kvs + (size_t)J * L.kv_rs3;
-          // the new token's own q, and its k / v into their window slot(s)
-          for (int c = threadIdx.x; c < inner; c += DS_THREADS)
-            qs[c] = __bfloat162float(__ldcg(cb + (long long)t * 3 * inner + c)) * qscale;
-          const int pieces = inner / 8;
-          for (int i = threadIdx.x; i < J * 2 * pieces; i += DS_THREADS) {
-            const int j = i / (2 * pieces), r = i - j * 2 * pieces;
-            const int kv = r / pieces, k = r - kv * pieces;
-            const int kj = keys[j];
-            if ((kj >> 28) == DK_NORMAL && (kj & 0x0FFFFFFF) == t)
-              *reinterpret_cast<uint4*>((kv ? Vs : Ks) + (size_t)j * L.kv_rs3 + k * 16) =
-                  __ldcg(reinterpret_cast<const uint4*>(cb + (long long)t * 3 * inner + (1 + kv) * inner + k * 8));
-          }
-          cp_async_wait<1>();
-          __syncthreads();
-          attn_scores(qs, keys, Ks, L.kv_rs3, nullptr, H, dh, J, Ss);
-          __syncthreads();
-          attn_softmax(Ss, H, J, warp, lane);
-          __syncthreads();
-          for (int j = threadIdx.x; j < J; j += DS_THREADS) {  // talking heads (:556-558)
-            float pin[16];
-            for (int h = 0; h < H; ++h) pin[h] = Ss[h * J + j];
-            for (int g = 0; g < H; ++g) {
-              float a = 0.f;
-              for (int h = 0; h < H; ++h) a = fmaf(Wt[g * H + h], pin[h], a);
-              Ss[g * J + j] = a;
+          // the new token's own q (scaled, fp32) and its k / v into their window slot: one L2 round trip
+          {
+            const int self = *self_slot;
+            const int pieces = inner / 8;
+            const bf16* rowt = cb + (long long)t * 3 * inner;
+            for (int i = threadIdx.x; i < 3 * pieces; i += DS_THREADS) {
+              const int sel = i / pieces, k = i - sel * pieces;
+              if (sel == 0) {
+                const uint4 u = __ldcg(reinterpret_cast<const uint4*>(rowt + k * 8));
+                const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+                *reinterpret_cast<float4*>(qs + k * 8) = make_float4(f0.x * qscale, f0.y * qscale, f1.x * qscale, f1.y * qscale);
+                *reinterpret_cast<float4*>(qs + k * 8 + 4) = make_float4(f2.x * qscale, f2.y * qscale, f3.x * qscale, f3.y * qscale);
+              } else if (self >= 0) {
+                *reinterpret_cast<uint4*>((sel == 2 ? Vs : Ks) + (size_t)self * L.kv_rs3 + k * 16) =
+                    __ldcg(reinterpret_cast<const uint4*>(rowt + sel * inner + k * 8));
+              }
             }
           }
+          DS_STAMP(16);
+          mbar_wait(kvbar, kv_uses & 1u);   // window rows of the earlier tokens (bulk copies)
+          cp_async_wait<0>();               // talking-heads matrix, bias
           __syncthreads();
-          attn_pv(Ss, keys, Vs, L.kv_rs3, nullptr, H, dh, J, part, outs);
-          for (int c = threadIdx.x; c < inner; c += DS_THREADS) act[(long long)b * inner + c] = __float2bfloat16(outs[c]);
+          DS_STAMP(17);
+          // scores + softmax: warp = head, lane = key slot (no CTA barrier in between; loads are unconditional, the key
+          // kind only selects the value)
+          for (int h = warp; h < H; h += DS_WARPS) {
+            const float* q = qs + h * dh;
+            float* Sh = Ss + h * J;
+            float m = -FLT_MAX;
+            for (int j = lane; j < J; j += 32) {
+              const int kind = keys[j] >> 28;
+              const uint4* kr = reinterpret_cast<const uint4*>(Ks + (size_t)j * L.kv_rs3 + h * dh * 2);
+              float sc = 0.f;
+              for (int i = 0; i < dh / 8; ++i) sc += dot8q(q + i * 8, kr[i]);
+              sc = kind == DK_NORMAL ? sc : (kind == DK_MASKED ? -FLT_MAX : 0.f);
+              Sh[j] = sc;
+              m = fmaxf(m, sc);
+            }
+            m = warp_max(m);
+            float l = 0.f;
+            for (int j = lane; j < J; j += 32) {
+              const float e = __expf(Sh[j] - m);
+              Sh[j] = e;
+              l += e;
+            }
+            l = warp_sum(l);
+            const float inv = 1.0f / l;
+            for (int j = lane; j < J; j += 32) Sh[j] *= inv;
+          }
+          __syncthreads();
+          DS_STAMP(19);
+          // talking heads (:556-558), one output per thread; slots without a real key are dropped from PV here
+          // (masked: P = 0 already; zero keys: V = 0)
+          for (int item = threadIdx.x; item < H * J; item += DS_THREADS) {
+            const int gh = item / J, j = item - gh * J;
+            float a = 0.f;
+#pragma unroll 8
+            for (int h = 0; h < H; ++h) a = fmaf(Wt[gh * H + h], Ss[h * J + j], a);
+            S2[item] = (keys[j] >> 28) == DK_NORMAL ? a : 0.f;
+          }
+          __syncthreads();
+          DS_STAMP(20);
+          // PV: thread = channel pair, branch-free over the window
+          for (int cp = threadIdx.x; cp < inner / 2; cp += DS_THREADS) {
+            const int hl = cp / (dh / 2);
+            const float* Ph = S2 + hl * J;
+            const uint8_t* vcol = Vs + cp * 4;
+            float ax = 0.f, ay = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < J; ++j) {
+              const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vcol + (size_t)j * L.kv_rs3));
+              ax = fmaf(Ph[j], v.x, ax);
+              ay = fmaf(Ph[j], v.y, ay);
+            }
+            *reinterpret_cast<uint32_t*>(act + (long long)b * inner + 2 * cp) = pack_bf16x2(ax, ay);
+          }
+          DS_STAMP(21);
         }
+        if (t > 0) ++kv_uses;
       }
       DS_STAMP(6);
       grid_barrier(bar);
       DS_STAMP(7);
       // ---- phase 3: to_out (+ bias) ----
-      cp_async_wait<1>();  // the bias (kv group); made visible by the CTA barrier inside stage_act
+      cp_async_wait<0>();  // the bias (kv group); made visible by the CTA barrier inside stage_act
       stage_act(As, lda_s, act, inner, B, inner);
       GemvOut o3{p.y, nullptr, (long long)D, s->b_out != nullptr ? reinterpret_cast<const float*>(ds_smem + L.bias) : nullptr};
       if (!(dbg & 2)) gemv_run<NT>(wb, Wb, inner, D / 16, D, inner, S16, As, lda_s, B, red, o3, gwarp, total_warps, warp, lane);
@@ -835,35 +916,63 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
       const int J = p.nk + 1;
       // slot j >= 1 of the key list is context row j - 1, staged at row j - 1 of Ks / Vs: shift the bases by one row
       const uint8_t* Ks = kvs - L.kv_rsx;
-      const uint8_t* Vs = kvs + (size_t)p.nk * L.kv_rsx - L.kv_rsx;
       const bool mine = (int)blockIdx.x < B * H;
       const int b = blockIdx.x / H, h = blockIdx.x - b * H;
-      // ---- phase 2a: scores of one (sample, head) per CTA ----
+      // ---- phase 2a: probabilities of one (sample, head) per CTA (the softmax of a head needs only that head) ----
       if (!(dbg & 4) && mine) {
         for (int c = threadIdx.x; c < dh; c += DS_THREADS)
           qs[c] = __bfloat162float(__ldcg(actq + (long long)b * inner + h * dh + c)) * qscale;
-        cp_async_wait<1>();
+        mbar_wait(kvbar, kv_uses & 1u);   // context K / V slices (bulk copies)
+        cp_async_wait<0>();               // null key / value, talking-heads matrix
         __syncthreads();
-        attn_scores(qs, ckeys, Ks, L.kv_rsx, nullkv, 1, dh, J, Ss);
+        DS_STAMP(22);
+        for (int j = threadIdx.x; j < J; j += DS_THREADS) {  // thread = key slot; unconditional loads, the kind selects
+          const int kind = ckeys[j] >> 28;
+          float sc = 0.f;
+          if (j == 0) {
+            for (int i = 0; i < dh; ++i) sc = fmaf(qs[i], nullkv[i], sc);
+          } else {
+            const uint4* kr = reinterpret_cast<const uint4*>(Ks + (size_t)j * L.kv_rsx);
+            const int nch = dh / 8;
+            for (int i = 0; i < nch; ++i) {  // dense 128-byte rows: start at chunk j so that a quarter-warp spans all banks
+              const int c = (i + j) % nch;
+              sc += dot8q(qs + c * 8, kr[c]);
+            }
+          }
+          Ss[j] = kind == DK_MASKED ? -FLT_MAX : sc;
+        }
         __syncthreads();
-        for (int j = threadIdx.x; j < J; j += DS_THREADS) p.scores[((long long)b * H + h) * J + j] = Ss[j];
+        DS_STAMP(23);
+        {  // every warp reduces the whole row (redundant, no further CTA barrier), every thread normalises its own slots
+          float m = -FLT_MAX;
+          for (int j = lane; j < J; j += 32) m = fmaxf(m, Ss[j]);
+          m = warp_max(m);
+          float l = 0.f;
+          for (int j = lane; j < J; j += 32) l += __expf(Ss[j] - m);
+          l = warp_sum(l);
+          const float inv = 1.0f / l;
+          for (int j = threadIdx.x; j < J; j += DS_THREADS) p.scores[((long long)b * H + h) * J + j] = __expf(Ss[j] - m) * inv;
+        }
       }
+      if (mine) ++kv_uses;
       DS_STAMP(6);
       grid_barrier(bar);
       DS_STAMP(7);
-      // ---- phase 2b: softmax of every head of the sample, talking-heads row h, PV of head h ----
+      // ---- phase 2b: talking-heads row h over the sample's probabilities, PV of head h ----
       if (!(dbg & 4) && mine) {
         for (int i = threadIdx.x; i < H * J; i += DS_THREADS) Ss[i] = __ldcg(p.scores + (long long)b * H * J + i);
         __syncthreads();
-        attn_softmax(Ss, H, J, warp, lane);
-        __syncthreads();
-        for (int j = threadIdx.x; j < J; j += DS_THREADS) {  // :372
+        DS_STAMP(24);
+        for (int j = threadIdx.x; j < J; j += DS_THREADS) {  // :372 (masked slots: every head's probability is exactly 0)
           float a = 0.f;
+#pragma unroll 8
           for (int hh = 0; hh < H; ++hh) a = fmaf(Wt[h * H + hh], Ss[hh * J + j], a);
           Pm[j] = a;
         }
         __syncthreads();
-        attn_pv(Pm, ckeys, Vs, L.kv_rsx, nullkv + dh, 1, dh, J, part, outs);
+        DS_STAMP(26);
+        attn_pv_head(Pm, kvs + (size_t)p.nk * L.kv_rsx, L.kv_rsx, nullkv + dh, dh, p.nk, part, outs);
+        DS_STAMP(27);
         for (int c = threadIdx.x; c < dh; c += DS_THREADS) act[(long long)b * inner + h * dh + c] = __float2bfloat16(outs[c]);
       }
       DS_STAMP(8);
@@ -897,10 +1006,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DecPa
   WPre<3, false> wl;
   const bf16* Wl = reinterpret_cast<const bf16*>(p.w_logits);
   if (Wl != nullptr) gemv_prefetch(wl, Wl, D, (p.V + 15) / 16, D, p.split_logits, gwarp, lane);
-  cp_async_commit();  // (empty) keeps the group order of ln_prologue: norms = oldest pending group but one
   grid_barrier(bar);
   DS_STAMP(13);
-  ln_prologue(p, prev, nullptr, t, streams, As, lda_s, lnp, shs, warp, lane);
+  ln_prologue(p, prev, nullptr, t, streams, As, lda_s, lnp, shs, warp, lane, lnbar, ln_uses & 1u);
   stable_ln_rows(p, streams, As, lda_s, lnp, warp, lane);
   if (Wl != nullptr) {
     GemvOut ol{p.logits, nullptr, (long long)p.V, nullptr};

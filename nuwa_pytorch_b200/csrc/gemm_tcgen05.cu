@@ -255,6 +255,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], a_bytes + Cfg::B_STAGE_BYTES);
+          if (p.mn_major) {
+            // operands stored [contraction][M] / [contraction][N]: one {64 MN elements x 64 contraction rows} box per
+            // 64-wide block -> the MN-major SWIZZLE_128B canonical layout, 8 KB per block, blocks consecutive
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * 8192, &tmA0, &full_bar[stage], tc.mt * BM + i * 64, kb * BK);
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &tmB, &full_bar[stage], n0 + i * 64, kb * BK);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           if (p.conv) {
             int tap = kb / p.cin_blocks;
             int cb = kb - tap * p.cin_blocks;
@@ -276,7 +289,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+      // MN-major operands: same instruction, a_major = b_major = 1; descriptors carry the 8 KB pitch between 64-wide
+      // blocks as the leading byte offset, and one K = 16 step advances 16 rows of 128 B (2048 B)
+      const uint32_t idesc = p.mn_major ? (make_idesc_bf16_f32(BM, BN) | (1u << 15) | (1u << 16)) : make_idesc_bf16_f32(BM, BN);
+      const uint64_t kstep = p.mn_major ? 128u : 2u;                       // in 16-byte units
+      const uint64_t mn_lbo = p.mn_major ? (((uint64_t)(8192 >> 4) << 16) - ((uint64_t)1 << 16)) : 0;  // replaces LBO = 1
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -291,12 +308,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t adesc = make_sw128_kmajor_desc(sa);
-          const uint64_t bdesc = make_sw128_kmajor_desc(sa + A_STAGE_BYTES);
+          const uint64_t adesc = make_sw128_kmajor_desc(sa) + mn_lbo;
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + A_STAGE_BYTES) + mn_lbo;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in (addr >> 4) units
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            // K-major: advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in (addr >> 4) units
+            umma_bf16(d_tmem, adesc + kstep * k, bdesc + kstep * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above retire
           if (++stage == Cfg::STAGES) {
@@ -653,6 +670,10 @@ static int dispatch_gemm(const CUtensorMap* mA, const void* Wp, GemmParams& p, i
   uint64_t dimsB[2] = {(uint64_t)p.K, (uint64_t)p.N};
   uint64_t strB[2] = {2, (uint64_t)p.ldw * 2};
   uint32_t boxB[2] = {64, (uint32_t)bn};
+  if (p.mn_major) {  // stored [K][N]: the kernel fetches {64 N elements x 64 contraction rows} boxes
+    dimsB[0] = (uint64_t)p.N; dimsB[1] = (uint64_t)p.K;
+    boxB[1] = 64;
+  }
   int e = encode_map(&mB, Wp, 2, dimsB, strB, boxB);
   if (e) return e;
   // Output through TMA stores (32 x 32 slabs) when the epilogue is "bias + optional LeakyReLU" of a plain GEMM with one
@@ -732,6 +753,36 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
                   (residual ? 4.0 * M * n_out : 0.0);
   }
   return dispatch_gemm(mA, W, p, force_bn, stream);
+}
+
+// out_f32[M][N] += At^T Wt with At stored [K][M] (row stride lda) and Wt stored [K][N] (row stride ldw), K = the long
+// contraction (tokens): the weight-gradient product dW = dY^T X on the activations as the forward / backward passes
+// hold them (no transposed copies).  Split-K partial products are reduced with fp32 reduce-adds in L2.
+int gemm_bf16_tn_splitk(const void* At, int lda, const void* Wt, int ldw, int M, int N, int K, float* out_f32, int ld_out,
+                        int splits, int force_bn, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || out_f32 == nullptr) return NUWA_ERR_INVALID;
+  if ((lda % 8) || (ldw % 8) || lda < M || ldw < N) return NUWA_ERR_INVALID;  // TMA: 16-byte row pitch
+  if ((reinterpret_cast<uintptr_t>(At) & 15) || (reinterpret_cast<uintptr_t>(Wt) & 15)) return NUWA_ERR_INVALID;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K; p.ldw = ldw;
+  p.k_blocks = ceil_div(K, BK);
+  p.num_m_tiles = ceil_div(M, BM);
+  p.out_f32 = out_f32; p.ld_out = ld_out; p.act = ACT_NONE;
+  p.splits = splits > 1 ? splits : 1;
+  p.atomic_out = 1;
+  p.mn_major = 1;
+  if (!epilogue_args_ok(p)) return NUWA_ERR_INVALID;
+  CUtensorMap mA[4];
+  uint64_t dimsA[2] = {(uint64_t)M, (uint64_t)K};
+  uint64_t strA[2] = {2, (uint64_t)lda * 2};
+  uint32_t boxA[2] = {64, 64};
+  int e = encode_map(&mA[0], At, 2, dimsA, strA, boxA);
+  if (e) return e;
+  mA[1] = mA[0]; mA[2] = mA[0]; mA[3] = mA[0];
+  t_cur_flops = 2.0 * (double)M * (double)N * (double)K;
+  t_cur_bytes = 2.0 * ((double)M * K + (double)N * K) + 4.0 * (double)M * N;
+  return dispatch_gemm(mA, Wt, p, force_bn, stream);
 }
 
 // NHWC bf16 convolution.  x: [B, Hin, Win, Cin] ; w: [Cout, KH*KW, Cin_pad] (Cin_pad = roundup(Cin,64), zero padded)

@@ -31,6 +31,9 @@ struct GemmParams {
   // split-K (weight-gradient GEMMs: small output, long contraction): item = tile * splits + split
   int splits, kb_per_split, atomic_out;
   int tma_out;  // 0: per-thread stores, 1: TMA tile stores, 2: TMA fp32 reduce-add (split-K)
+  // 1: both operands are stored with the CONTRACTION as the slow dimension (A as [K][M], W as [K][N], rows = contraction
+  // index): weight-gradient products dW = dY^T X read dY and X exactly as the forward pass left them (no transposes)
+  int mn_major;
 };
 
 typedef nuwa_attn_params AttnParams;
@@ -43,6 +46,8 @@ int device_sm_count();
 int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
               const float* residual, int ld_res, float* out_f32, void* out_bf16, int ld_out, int act, int force_bn,
               cudaStream_t stream, int splits = 1);
+int gemm_bf16_tn_splitk(const void* At, int lda, const void* Wt, int ldw, int M, int N, int K, float* out_f32, int ld_out,
+                        int splits, int force_bn, cudaStream_t stream);
 int gemm_skinny(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                 const float* residual, int ld_res, float* out_f32, void* out_bf16, int ld_out, int act,
                 cudaStream_t stream);  // gemm_skinny.cu

@@ -188,10 +188,11 @@ class Context:
     def __init__(self, ctx16, mask_u8):
         self.ctx16, self.mask = ctx16, mask_u8  # (B, nk, D) bf16 ; (B, nk) uint8 or None
         self.kv = {}
+        self.kv_packed = {}  # per-(sample, head) repack of kv for the persistent decode kernel (FusedDecode)
 
     def with_mask(self, mask_u8):
         c = Context(self.ctx16, mask_u8)
-        c.kv = self.kv  # K/V do not depend on the mask
+        c.kv, c.kv_packed = self.kv, self.kv_packed  # K/V do not depend on the mask
         return c
 
 
@@ -378,7 +379,13 @@ class FusedDecode:
                 H, dh = s.H, s.dh
                 d.w_a, d.w_b, d.talk = s.w_q.data_ptr(), s.w_out.data_ptr(), s.talk.data_ptr()
                 d.null_k, d.null_v = s.null_k.data_ptr(), s.null_v.data_ptr()
-                d.cache = context.kv[i].data_ptr()
+                # the kernel stages one (sample, head) slice per CTA: repack K|V rows [B*nk, 2*inner] as [B][H][2][nk][dh]
+                # once per generate() call so that each slice is a single contiguous bulk copy
+                packed = context.kv_packed
+                if i not in packed:
+                    nk_ = context.ctx16.shape[1]
+                    packed[i] = context.kv[i].view(B, nk_, 2, s.H, s.dh).permute(0, 3, 2, 1, 4).contiguous()
+                d.cache = packed[i].data_ptr()
             else:
                 d.w_a, d.w_b, d.ip = s.w1.data_ptr(), s.w2.data_ptr(), s.w1.shape[0] // 2
                 kmax = max(kmax, d.ip)

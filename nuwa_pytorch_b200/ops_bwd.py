@@ -38,16 +38,33 @@ def gemm_splitk(a, w, out, splits=64):
                                       force_bn, stream()), "nuwa_gemm_bf16_splitk")
 
 
-def linear_bwd(dy16, a16, w_t16, dW, want_da=True, da_residual=None, dyT=None):
+# weight gradients read dY and X contraction-major (no transposed copies); False = the transpose + K-major path, kept
+# for the A/B test (tests/test_gemm_gpu.py) and measurements
+WGRAD_TN = True
+
+
+def gemm_splitk_tn(dy, a, out, splits=64):
+    """out (N, K) fp32 += dy.T @ a ; dy (M, N), a (M, K) bf16 row-major (column slices allowed): dW = dY^T X."""
+    assert dy.dtype == torch.bfloat16 and a.dtype == torch.bfloat16 and out.dtype == torch.float32
+    assert dy.stride(1) == 1 and a.stride(1) == 1 and out.stride(1) == 1
+    M, N = dy.shape
+    K = a.shape[1]
+    assert a.shape[0] == M and out.shape == (N, K)
+    if not WGRAD_TN:
+        return gemm_splitk(transpose(dy), transpose(a), out, splits)
+    force_bn = 256 if K >= 256 else (128 if K >= 128 else 64)
+    check(lib().nuwa_gemm_bf16_tn_splitk(ptr(dy), dy.stride(0), ptr(a), a.stride(0), N, K, M, ptr(out), out.stride(0),
+                                         splits, force_bn, stream()), "nuwa_gemm_bf16_tn_splitk")
+
+
+def linear_bwd(dy16, a16, w_t16, dW, want_da=True, da_residual=None):
     """y = a @ W.T  ->  da = dy @ W (fp32, optionally + da_residual), dW += dy.T @ a.
     dy16 (M, N) bf16, a16 (M, K) bf16, w_t16 = W.T as (K, N) bf16 contiguous, dW (N, K) fp32 accumulator (or None)."""
     da = None
     if want_da:
         da = ops.gemm(dy16, w_t16, residual=da_residual, out_dtype=torch.float32)
     if dW is not None:
-        if dyT is None:
-            dyT = transpose(dy16)
-        gemm_splitk(dyT, transpose(a16), dW)
+        gemm_splitk_tn(dy16, a16, dW)
     return da
 
 

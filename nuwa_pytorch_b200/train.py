@@ -9,7 +9,7 @@ activations, without its extra forward pass.  Every weight gradient is accumulat
 
 Per sub-block  x' = x + LN_post(fn(shift(LN_pre(x_r)))):
     dy   = LN_post backward of the stream gradient                     (ln_bwd, bf16 out; bias grad = column sum)
-    da   = fn backward (GEMM dgrad on tcgen05, weight grads as split-K tcgen05 GEMMs over transposed operands,
+    da   = fn backward (GEMM dgrad on tcgen05, weight grads as split-K tcgen05 GEMMs reading dY and X contraction-major,
            attention backward kernels)
     G_r += LN_pre backward of da through the inverse token shift        (ln_bwd, accumulate)
 """
@@ -189,18 +189,17 @@ def stack_forward(stack, x, *, context=None, key_mask=None, rotary=None):
 # ------------------------------------------------------------------------------------------------
 # backward
 # ------------------------------------------------------------------------------------------------
-def _wgrad(dyT, a16_T, dst):
+def _wgrad(dy16, a16, dst):
+    """dst (N, K) fp32 += dy16 (M, N).T @ a16 (M, K)"""
     if dst is not None:
-        ops_bwd.gemm_splitk(dyT, a16_T, dst)
+        ops_bwd.gemm_splitk_tn(dy16, a16, dst)
 
 
 def _sub_backward(i, s, rec, dy16, B, nt, g, tape, dctx):
     """dy16: bf16 (M, D) gradient of the sub-block output y.  Returns da fp32 (M, D)."""
     bw = _bw(s)
     M = B * nt
-    T = ops_bwd.transpose
-    dyT = T(dy16)
-    aT = T(rec['a'])
+    a16 = rec['a']
     if s.kind == 'ff':
         m = s.mod
         D = dy16.shape[1]
@@ -209,19 +208,19 @@ def _sub_backward(i, s, rec, dy16, B, nt, g, tape, dctx):
         w2g = g(m.net[3].weight)
         if w2g is not None:
             tmp = torch.zeros(D, ip, dtype=torch.float32, device=dy16.device)
-            ops_bwd.gemm_splitk(dyT, T(rec['g']), tmp)
+            ops_bwd.gemm_splitk_tn(dy16, rec['g'], tmp)
             ops_bwd.add_rows(w2g, tmp, cols=s.ff_inner)
         dh = ops_bwd.geglu_bwd(dg, rec['h'])                                         # (M, 2*ip) pair packed
         w1g = g(m.net[0].weight)
         if w1g is not None:
             tmp = torch.zeros(2 * ip, D, dtype=torch.float32, device=dy16.device)
-            ops_bwd.gemm_splitk(T(dh), aT, tmp)
+            ops_bwd.gemm_splitk_tn(dh, a16, tmp)
             ops_bwd.add_rows(w1g, tmp, row_map=bw['w1_map'])
         return ops.gemm(dh, bw['w1_t'], out_dtype=torch.float32)
     m = s.mod
     inner, H, dh_ = s.inner, s.H, s.dh
     do = ops.gemm(dy16, bw['w_out_t'], out_dtype=torch.bfloat16)                      # (M, inner)
-    _wgrad(dyT, T(rec['o']), g(m.to_out.weight))
+    _wgrad(dy16, rec['o'], g(m.to_out.weight))
     dtalk = g(m.talking_heads.weight)
     dtalk = dtalk.view(H, H) if dtalk is not None else torch.zeros(H, H, device=dy16.device)
     if s.kind == '3dna':
@@ -269,18 +268,15 @@ def _sub_backward(i, s, rec, dy16, B, nt, g, tape, dctx):
                                                  null_v=s.null_v, dnull_k=dnk, dnull_v=dnv, key_mask=ctx.mask, fmap=s.fmap,
                                                  ck=s.ck, cdil=s.cdil)
             dq, dkv = dq.view(M, inner), dkv.view(B * nk, 2 * inner)
-        _wgrad(T(dq), aT, g(m.to_q.weight))
+        _wgrad(dq, a16, g(m.to_q.weight))
         if dctx is not None:
-            if getattr(ctx, 'ctx16_T', None) is None:
-                ctx.ctx16_T = T(ctx.ctx16.view(B * nk, -1))
-            _wgrad(T(dkv), ctx.ctx16_T, g(m.to_kv.weight))
+            _wgrad(dkv, ctx.ctx16.view(B * nk, -1), g(m.to_kv.weight))
             ops.gemm(dkv, bw['w_kv_t'], residual=dctx, out=dctx)                      # dctx += dkv @ W_kv
         return ops.gemm(dq, bw['w_q_t'], out_dtype=torch.float32)
     else:
         raise NotImplementedError(s.kind)
-    dqkvT = T(dqkv)
-    _wgrad(dqkvT[:inner], aT, g(m.to_q.weight))
-    _wgrad(dqkvT[inner:], aT, g(m.to_kv.weight))
+    _wgrad(dqkv[:, :inner], a16, g(m.to_q.weight))
+    _wgrad(dqkv[:, inner:], a16, g(m.to_kv.weight))
     return ops.gemm(dqkv, bw['w_qkv_t'], out_dtype=torch.float32)
 
 

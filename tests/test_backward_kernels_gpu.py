@@ -44,6 +44,10 @@ def test_bgemm_all_orientations(cuda_device, at, bt):
     assert rel(C, ref + 1) < 1e-5
 
 
+def _round_up8(x):
+    return (x + 7) // 8 * 8
+
+
 def test_transpose_and_splitk_gemm(cuda_device):
     from nuwa_pytorch_b200 import ops_bwd
     g = gen(20)
@@ -64,6 +68,33 @@ def test_transpose_and_splitk_gemm(cuda_device):
         ops_bwd.gemm_splitk(a_d, w_d, out)
         ref = a.float() @ w.float().t() + 1
         assert rel(out, ref) < 2e-5, (M, N, K)
+
+
+@pytest.mark.parametrize("tokens,n_out,k_in", [(5000, 512, 192), (333, 96, 40), (20480 // 4, 1536, 512), (2048, 64, 4096),
+                                               (777, 200, 520), (64, 128, 256), (4100, 2816, 512)])
+def test_weight_gradient_gemm_contraction_major(cuda_device, tokens, n_out, k_in):
+    """dW = dY^T X on the tcgen05 kernel with BOTH operands read MN-major straight from dY [tokens, n_out] and
+    X [tokens, k_in] (column-sliced views included) vs fp32 matmul, and vs the transpose + K-major path (same products,
+    same split-K reduce: equal up to the order of the fp32 reduce-adds).  Ragged tokens / n_out / k_in exercise the TMA
+    zero fill of partial 64-wide blocks and contraction rows."""
+    from nuwa_pytorch_b200 import ops_bwd
+    g = gen(tokens + n_out)
+    pitch_y, pitch_x = _round_up8(n_out) + 64, _round_up8(k_in) + 8
+    dy = torch.randn(tokens, pitch_y, generator=g).bfloat16().to(cuda_device)[:, 64:64 + n_out]   # a column slice
+    x = torch.randn(tokens, pitch_x, generator=g).bfloat16().to(cuda_device)[:, :k_in]
+    out = torch.ones(n_out, k_in, device=cuda_device)
+    ops_bwd.gemm_splitk_tn(dy, x, out)
+    ref = dy.float().t() @ x.float() + 1
+    r = rel(out, ref)
+    out2 = torch.ones(n_out, k_in, device=cuda_device)
+    ops_bwd.WGRAD_TN = False
+    try:
+        ops_bwd.gemm_splitk_tn(dy, x, out2)
+    finally:
+        ops_bwd.WGRAD_TN = True
+    print(f"  wgrad tn tokens={tokens} n_out={n_out} k_in={k_in}: rel vs fp32 {r:.2e}, vs transposed path {rel(out, out2):.2e}")
+    assert r < 2e-5
+    assert rel(out, out2) < 2e-6
 
 
 @pytest.mark.parametrize("D", [64, 512, 1024])

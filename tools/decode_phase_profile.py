@@ -70,7 +70,7 @@ with torch.no_grad():
     # ---- per-phase stamps of CTA 0 (does attention work) and of the last CTA (only products) ----
     for cta in (0, 147):
         plan = engine.FusedDecode(pack, state, context, nuwa._logits_weight())
-        prof = torch.zeros(2 * (12 * len(pack.subs) + 8), dtype=torch.int64, device=dev)
+        prof = torch.zeros(2 * (24 * len(pack.subs) + 8), dtype=torch.int64, device=dev)
         plan.params.prof, plan.params.prof_cta = prof.data_ptr(), cta
         ms = timed(plan, 5)
         v = prof.cpu().tolist()
@@ -78,7 +78,7 @@ with torch.no_grad():
         for i in range(0, len(v), 2):
             if v[i] < 0 or (i > 0 and v[i] == 0 and v[i + 1] == 0):
                 break
-            stamps.append((v[i] // 16, v[i] % 16, v[i + 1]))
+            stamps.append((v[i] // 32, v[i] % 32, v[i + 1]))
         cyc_total = stamps[-1][2] - stamps[0][2]
         ghz = cyc_total / (ms * 1e6)
         agg = collections.defaultdict(list)
