@@ -217,7 +217,9 @@ __device__ __forceinline__ void load_rows(uint32_t dst, uint64_t* bar, const Map
   for (; i < n; ++i) tma_load_3d(dst + i * BOX, ms.flat, bar, chan, ms.tok0 + (R0 + i * dh) * GW, b);
 }
 
-template <int DW>
+// X2 = SparseCross2DNA variant (absolute context frames, learned null key / value, context mask): a compile-time switch so
+// that the Sparse3DNA instantiation carries none of its per-unit work (mask selects, 64-bit mask word) or registers.
+template <int DW, bool X2>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap qmap8,
                       const __grid_constant__ CUtensorMap qmap4, const __grid_constant__ CUtensorMap qmap2,
@@ -350,7 +352,7 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
             const int chan = (ph ? p.voff : p.koff) + (2 * hp + w) * DH;
             for (int a = 0; a < p.kt; ++a) {
               if (!((t.real_mask >> a) & 1)) continue;
-              const int ff = p.abs_frames ? a : t.f + (a - At) * p.dt;
+              const int ff = X2 ? a : t.f + (a - At) * p.dt;
               const int st = it % NST;
               const uint32_t dst = sm_u + OFF_KV + st * KV_STAGE;
               mbar_wait(&empty[st], ((it / NST) & 1) ^ 1);
@@ -536,28 +538,30 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
         }
       // context-token mask (SparseCross2DNA, nuwa_pytorch.py:878-884): the window of a query sits at the same grid position
       // in every context frame, so its 9 mask bits per frame are tile constants
-      unsigned long long kmask = 0;      // 9 bits per frame offset
+      unsigned long long kmask = 0;      // 9 bits per frame offset (X2 only)
+      if constexpr (X2) {
 #pragma unroll
-      for (int a = 0; a < MAXKT; ++a) {
-        uint32_t m = valid9;
-        if (p.key_mask != nullptr && a < p.kt) {
-          m = 0;
+        for (int a = 0; a < MAXKT; ++a) {
+          uint32_t m = valid9;
+          if (p.key_mask != nullptr && a < p.kt) {
+            m = 0;
 #pragma unroll
-          for (int b = 0; b < MAXKH; ++b)
+            for (int b = 0; b < MAXKH; ++b)
 #pragma unroll
-            for (int c = 0; c < KW; ++c)
-              if ((valid9 >> (b * KW + c)) & 1u) {
-                const int yy = slot_row(p, t, ti + b, Ah), xx = x + (c - Aw) * p.dw;   // valid9: inside the grid
-                const int tok = (a * GW + yy) * GW + xx;
-                m |= (__ldg(p.key_mask + (long long)t.b * p.mask_bs + tok) != 0 ? 1u : 0u) << (b * KW + c);
-              }
+              for (int c = 0; c < KW; ++c)
+                if ((valid9 >> (b * KW + c)) & 1u) {
+                  const int yy = slot_row(p, t, ti + b, Ah), xx = x + (c - Aw) * p.dw;   // valid9: inside the grid
+                  const int tok = (a * GW + yy) * GW + xx;
+                  m |= (__ldg(p.key_mask + (long long)t.b * p.mask_bs + tok) != 0 ? 1u : 0u) << (b * KW + c);
+                }
+          }
+          kmask |= (unsigned long long)m << (9 * a);
         }
-        kmask |= (unsigned long long)m << (9 * a);
       }
       // ---- tile start: everyone has left the previous tile (its bos rows / TMEM are free), then stage this one ----
       named_bar_sync(1, 256);
       if (wg == 0) {
-        if (p.null_k != nullptr) {   // learned null key / value (fp32 parameters), the same for every sample
+        if (X2) {   // learned null key / value (fp32 parameters), the same for every sample
           float* dstk = reinterpret_cast<float*>(sm + OFF_KBOS);
           float* dstv = reinterpret_cast<float*>(sm + OFF_VBOS);
           for (int i = qrow; i < INNER; i += 128) { dstk[i] = __ldg(p.null_k + i); dstv[i] = __ldg(p.null_v + i); }
@@ -574,7 +578,7 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
         }
       }
       // the bos query (sequence row 0) attends only to itself (nuwa_pytorch.py:608): its output is its value row
-      if (!p.abs_frames && t.f == 0 && tile_row(p, t, 0) == 0 && wg == 1 && qrow < 64) {
+      if (!X2 && t.f == 0 && tile_row(p, t, 0) == 0 && wg == 1 && qrow < 64) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.v0 + (long long)t.b * p.v_bs) + qrow);
         reinterpret_cast<uint4*>(p.o + (long long)t.b * p.o_bs)[qrow] = v;
       }
@@ -629,11 +633,11 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
             for (int i = 0; i < 16; ++i)
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(drow_u + 16 * i), "r"(v[4 * i]), "r"(v[4 * i + 1]),
                            "r"(v[4 * i + 2]), "r"(v[4 * i + 3]) : "memory");
-            const uint32_t km = (uint32_t)(kmask >> (9 * a)) & 0x1ffu;
+            const uint32_t km = X2 ? (uint32_t)(kmask >> (9 * a)) & 0x1ffu : 0x1ffu;
 #pragma unroll
             for (int e = 0; e < MAXKH * KW; ++e)
               asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sv[1 + 9 * a + e])
-                           : "r"(drow_u + (((km >> e) & 1u) ? goff[e] : 256u)) : "memory");
+                           : "r"(drow_u + ((!X2 || ((km >> e) & 1u)) ? goff[e] : 256u)) : "memory");
           } else if (a < p.kt && ((t.zero_mask >> a) & 1)) {
             // in-volume key frame beyond the sequence: visible zero keys (score 0), SURVEY D16
 #pragma unroll
@@ -859,9 +863,15 @@ int launch_umma(const HostMaps& qm, const HostMaps& km, UmmaArgs& a, cudaStream_
     return NUWA_OK;
   };
   int lrc;
-  if (a.dw == 1) lrc = launch(attn_3dna_umma_kernel<1>);
-  else if (a.dw == 2) lrc = launch(attn_3dna_umma_kernel<2>);
-  else lrc = launch(attn_3dna_umma_kernel<4>);
+  if (a.abs_frames) {
+    if (a.dw == 1) lrc = launch(attn_3dna_umma_kernel<1, true>);
+    else if (a.dw == 2) lrc = launch(attn_3dna_umma_kernel<2, true>);
+    else lrc = launch(attn_3dna_umma_kernel<4, true>);
+  } else {
+    if (a.dw == 1) lrc = launch(attn_3dna_umma_kernel<1, false>);
+    else if (a.dw == 2) lrc = launch(attn_3dna_umma_kernel<2, false>);
+    else lrc = launch(attn_3dna_umma_kernel<4, false>);
+  }
   if (lrc != NUWA_OK) return lrc;
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
