@@ -866,12 +866,164 @@ __global__ void __launch_bounds__(128, 2) attn_bwd_rows_reg_kernel(const nuwa_at
   }
 }
 
+// Two warps per row (lane l of warp half w owns the key slots j = 32 w + l + 64 i, i < NJ): for 257-slot rows the
+// one-warp variant above needs P[8][9] + dP'[8][9] + 64 dW accumulators per thread and spills 768 bytes; here a thread
+// holds 5 slots per head (80 + 64 registers), twice as many warps are in flight per row, and the three row statistics
+// (max, sum, sum_j P dP) cross the warp pair through shared memory + a 64-thread named barrier.
+template <int H, int NJ>
+__global__ void __launch_bounds__(128, 2) attn_bwd_rows_pair_kernel(const nuwa_attn_rows_params p) {
+  __shared__ __align__(16) float Wt[H * H];
+  __shared__ float dW_cta[H * H];
+  __shared__ float xch[2][3][2][H];  // [pair][statistic][warp half][head]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = warp >> 1, half = warp & 1;
+  const int J = p.J, jp = p.jp;
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+    Wt[i] = p.talk != nullptr ? p.talk[i] : ((i / H) == (i % H) ? 1.0f : 0.0f);
+    dW_cta[i] = 0.f;
+  }
+  __syncthreads();
+  const uint32_t wt_u = smem_u32(Wt);
+  float dW[H * H];
+#pragma unroll
+  for (int i = 0; i < H * H; ++i) dW[i] = 0.f;
+  const long long nrows = (long long)p.B * p.nq;
+  const long long hs = (long long)p.nq * jp;  // head stride
+  bf16* Pp = reinterpret_cast<bf16*>(p.Pp);
+  bf16* dS = reinterpret_cast<bf16*>(p.dS);
+  // combine a per-head statistic over the two warps of the pair (every lane ends up with the row value)
+  auto pair_reduce = [&](float (&v)[H], int which, bool is_max) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float u = __shfl_xor_sync(0xffffffffu, v[h], o);
+        v[h] = is_max ? fmaxf(v[h], u) : v[h] + u;
+      }
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) xch[pair][which][half][h] = v[h];
+    }
+    if (pair == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+    else asm volatile("bar.sync 2, 64;" ::: "memory");
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float u = xch[pair][which][half ^ 1][h];
+      v[h] = is_max ? fmaxf(v[h], u) : v[h] + u;
+    }
+  };
+  for (long long r = blockIdx.x * 2LL + pair; r < nrows; r += (long long)gridDim.x * 2) {
+    const int b = (int)(r / p.nq), q = (int)(r - (long long)b * p.nq);
+    const long long base = ((long long)b * H * p.nq + q) * jp;
+    float P[H][NJ], G[H][NJ];
+    bool live[NJ];
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const int j = half * 32 + lane + 64 * i;
+      live[i] = j < J;
+      if (live[i] && p.key_mask != nullptr) {
+        const int key = j - p.has_null;
+        if (key >= 0 && p.key_mask[(long long)b * p.mask_bs + key] == 0) live[i] = false;
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        P[h][i] = live[i] ? p.S[base + h * hs + j] : -FLT_MAX;
+        G[h][i] = live[i] ? p.dPp[base + h * hs + j] : 0.f;
+      }
+    }
+    // ---- softmax of every head ----
+    float m[H], sum[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      m[h] = P[h][0];
+#pragma unroll
+      for (int i = 1; i < NJ; ++i) m[h] = fmaxf(m[h], P[h][i]);
+    }
+    pair_reduce(m, 0, true);
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      sum[h] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        P[h][i] = live[i] ? __expf(P[h][i] - m[h]) : 0.f;
+        sum[h] += P[h][i];
+      }
+    }
+    pair_reduce(sum, 1, false);
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float inv = 1.0f / sum[h];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) P[h][i] *= inv;
+    }
+    // ---- talking heads forward (P' -> HBM), backward (dP = W^T dP'), dW accumulation; then P .* dP row sums ----
+    float dot[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) dot[h] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const int j = half * 32 + lane + 64 * i;
+      float dp[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) dp[h] = 0.f;
+#pragma unroll
+      for (int g = 0; g < H; ++g) {
+        const float dpp = G[g][i];
+        float a = 0.f;
+        float wrow[H];  // re-read from shared memory per (slot, g): hoisted into registers the 64 weights spill
+#pragma unroll
+        for (int h4 = 0; h4 < H; h4 += 4) {
+          if constexpr (H % 4 == 0) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(wrow[h4]), "=f"(wrow[h4 + 1]), "=f"(wrow[h4 + 2]), "=f"(wrow[h4 + 3])
+                         : "r"(wt_u + (uint32_t)(g * H + h4) * 4u));
+          } else {
+            for (int h = h4; h < H && h < h4 + 4; ++h) wrow[h] = Wt[g * H + h];
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float w = wrow[h];
+          a = fmaf(w, P[h][i], a);
+          dp[h] = fmaf(w, dpp, dp[h]);
+          dW[g * H + h] = fmaf(dpp, P[h][i], dW[g * H + h]);
+        }
+        if (j < jp) Pp[base + g * hs + j] = __float2bfloat16(a);
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        G[h][i] = dp[h];
+        dot[h] = fmaf(P[h][i], dp[h], dot[h]);
+      }
+    }
+    pair_reduce(dot, 2, false);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const int j = half * 32 + lane + 64 * i;
+      if (j < jp) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) dS[base + h * hs + j] = __float2bfloat16(P[h][i] * (G[h][i] - dot[h]) * p.out_scale);
+      }
+    }
+  }
+  if (p.dtalk != nullptr) {
+#pragma unroll
+    for (int i = 0; i < H * H; ++i) {
+      const float v = warp_sum(dW[i]);
+      if (lane == 0) atomicAdd(&dW_cta[i], v);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) atomicAdd(p.dtalk + i, dW_cta[i]);
+  }
+}
+
 template <int H>
 static bool launch_rows_reg(const nuwa_attn_rows_params& p, int grid, cudaStream_t stream) {
   const int nj = ceil_div(p.J, 32);
   if (nj <= 1) attn_bwd_rows_reg_kernel<H, 1><<<grid, 128, 0, stream>>>(p);
   else if (nj <= 2) attn_bwd_rows_reg_kernel<H, 2><<<grid, 128, 0, stream>>>(p);
   else if (nj <= 4) attn_bwd_rows_reg_kernel<H, 4><<<grid, 128, 0, stream>>>(p);
+  else if (nj <= 10 && H * 5 <= 40 && H <= 32) attn_bwd_rows_pair_kernel<H, 5><<<grid, 128, 0, stream>>>(p);  // two warps per row
   else if (nj <= 9 && H * 9 <= 72) attn_bwd_rows_reg_kernel<H, 9><<<grid, 128, 0, stream>>>(p);
   else return false;
   return true;

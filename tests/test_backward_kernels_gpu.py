@@ -234,7 +234,10 @@ def test_attn_sparse3dna_bwd(cuda_device, causal, kernel, dil, n, H, dh):
 
 
 @pytest.mark.parametrize("B,nq,nk,H,dh,null,masked", [(2, 37, 12, 2, 32, True, True), (3, 70, 50, 8, 64, True, False),
-                                                       (2, 16, 16, 4, 16, False, True)])
+                                                       (2, 16, 16, 4, 16, False, True),
+                                                       (2, 45, 256, 8, 64, True, True),     # cfg-3 text context: 257 slots,
+                                                       (1, 33, 200, 8, 64, False, False),   # two warps per row kernel
+                                                       (1, 20, 300, 4, 32, True, True)])    # 301 slots
 def test_attn_dense_bwd(cuda_device, B, nq, nk, H, dh, null, masked):
     from nuwa_pytorch_b200 import ops_bwd
     g = gen(60 + nq)
