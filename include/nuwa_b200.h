@@ -458,12 +458,22 @@ int nuwa_mask_scores(float* S, const unsigned char* mask, int mask_bs, int B, in
 /* Sparse3DNA (nuwa_pytorch.py:490-608): p describes the NON-bos queries (p.t0 >= 1, p.q = first such row) */
 int nuwa_attn3dna_bwd_scores(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp,
                              int jp, void* stream);
+/* The same two tensors from the tcgen05 / TMEM kernel of nuwa_attn_sparse3dna_umma run in scores mode, twice (logits:
+ * Q = q, K = k; dP' = dO V^T: Q = dO from its own buffer, K = v): one UMMA per (head, frame offset) of a 128-query tile
+ * instead of 46 gathered key rows per query.  Same envelope as nuwa_attn_sparse3dna_umma (full pass: p->nq == p->nv,
+ * p->t0 == 1, q|k|v rows in one buffer); NUWA_ERR_INVALID outside it (nothing launched). */
+int nuwa_attn3dna_bwd_scores_umma(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp,
+                                  int jp, void* stream);
 int nuwa_attn3dna_bwd_dq(const nuwa_attn_params* p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs,
                          void* stream);
 int nuwa_attn3dna_bwd_dkdv(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, const void* dS,
                            const void* Pp, int jp, void* dk, void* dv, long long dkv_bs, int dkv_rs, void* stream);
 /* SparseCross2DNA non-bos queries (nuwa_pytorch.py:851-895): same three passes; nk = context tokens; base_k / base_v
  * (fp32 [B][nk] rows with strides base_bs / base_rs, or NULL) is added to the key gradients (the dense bos query's part) */
+/* nuwa_attnx2_bwd_scores on the tcgen05 / TMEM kernel in scores mode (envelope of nuwa_attn_cross2dna_umma; NUWA_ERR_INVALID
+ * outside it, nothing launched) */
+int nuwa_attnx2_bwd_scores_umma(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp,
+                                int jp, void* stream);
 int nuwa_attnx2_bwd_scores(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp,
                            int jp, void* stream);
 int nuwa_attnx2_bwd_dq(const nuwa_attn_params* p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs, void* stream);

@@ -229,6 +229,10 @@ int nuwa_mask_scores(float* Sc, const unsigned char* mask, int mask_bs, int B, i
                      void* stream) {
   return mask_scores(Sc, mask, mask_bs, B, H, nq, jp, nk, has_null, S(stream));
 }
+int nuwa_attn3dna_bwd_scores_umma(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* Sc, float* dPp,
+                                  int jp, void* stream) {
+  return p ? attn_3dna_umma_scores(*p, dO, do_bs, do_rs, Sc, dPp, jp, S(stream)) : NUWA_ERR_INVALID;
+}
 int nuwa_attn3dna_bwd_scores(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* Sc, float* dPp,
                              int jp, void* stream) {
   return p ? attn3dna_bwd_scores(*p, dO, do_bs, do_rs, Sc, dPp, jp, S(stream)) : NUWA_ERR_INVALID;
@@ -249,6 +253,10 @@ int nuwa_attn_bwd_first_key(const void* q, long long q_bs, int q_rs, const void*
 int nuwa_attn3dna_bwd_first_key_finalize(const float* tmp_k, const float* tmp_v, const void* dO_bos, long long do_bs,
                                          void* dqkv, long long dqkv_bs, int inner, int B, void* stream) {
   return attn3dna_bwd_first_key_finalize(tmp_k, tmp_v, dO_bos, do_bs, dqkv, dqkv_bs, inner, B, S(stream));
+}
+int nuwa_attnx2_bwd_scores_umma(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* Sc, float* dPp,
+                                int jp, void* stream) {
+  return p ? attn_cross2dna_umma_scores(*p, dO, do_bs, do_rs, Sc, dPp, jp, S(stream)) : NUWA_ERR_INVALID;
 }
 int nuwa_attnx2_bwd_scores(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* Sc, float* dPp,
                            int jp, void* stream) {

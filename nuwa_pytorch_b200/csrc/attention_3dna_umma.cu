@@ -90,6 +90,11 @@ struct UmmaArgs {
   const bf16* k0;
   const bf16* v0;
   long long k_bs, v_bs;
+  // scores mode (backward): phase 1 only, the band scores go to s_out[b][h][query][s_jp] as fp32 (slot j = 1 + (a kh + b) 3 + c,
+  // slot 0 = bos / null key), multiplied by s_scale; masked slots get s_masked
+  float* s_out;
+  int s_jp;
+  float s_scale, s_masked;
   long long* dbg;  // tools/umma_stamps.py: clock64 stamps of CTA 0 (NULL in normal use)
 };
 
@@ -219,7 +224,9 @@ __device__ __forceinline__ void load_rows(uint32_t dst, uint64_t* bar, const Map
 
 // X2 = SparseCross2DNA variant (absolute context frames, learned null key / value, context mask): a compile-time switch so
 // that the Sparse3DNA instantiation carries none of its per-unit work (mask selects, 64-bit mask word) or registers.
-template <int DW, bool X2>
+// SC = scores mode: S = Q K^T band extraction only (no softmax / mix / PV); used twice by the backward pass, for the logits
+// (Q = q, K = k) and for dP' = dO V^T (Q = dO from its own buffer, K = v).
+template <int DW, bool X2, bool SC>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap qmap8,
                       const __grid_constant__ CUtensorMap qmap4, const __grid_constant__ CUtensorMap qmap2,
@@ -347,7 +354,7 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
           ++qu[hp & 1];
         };
         load_q(0);
-        for (int ph = 0; ph < 2; ++ph) {
+        for (int ph = 0; ph < (SC ? 1 : 2); ++ph) {
           for (int hp = 0; hp < NH / 2; ++hp) {
             const int chan = (ph ? p.voff : p.koff) + (2 * hp + w) * DH;
             for (int a = 0; a < p.kt; ++a) {
@@ -428,6 +435,7 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
           umma_commit(&qempty[qb]);
           ++qu[hp & 1];
         }
+        if constexpr (SC) continue;
         // ---------------- talking heads: D[q][2g + s'] = sum_h W[g][h] P[h][2u + s'] for every slot pair u ----------------
         if (w == 0) {
           for (int batch = 0; batch < 2; ++batch) {
@@ -578,7 +586,7 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
         }
       }
       // the bos query (sequence row 0) attends only to itself (nuwa_pytorch.py:608): its output is its value row
-      if (!X2 && t.f == 0 && tile_row(p, t, 0) == 0 && wg == 1 && qrow < 64) {
+      if (!X2 && !SC && t.f == 0 && tile_row(p, t, 0) == 0 && wg == 1 && qrow < 64) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.v0 + (long long)t.b * p.v_bs) + qrow);
         reinterpret_cast<uint4*>(p.o + (long long)t.b * p.o_bs)[qrow] = v;
       }
@@ -647,6 +655,38 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
             for (int e = 0; e < MAXKH * KW; ++e) sv[1 + 9 * a + e] = -FLT_MAX;
           }
         }
+        if constexpr (SC) {
+          // scores mode: this thread's band of head h -> s_out[b][h][query][:] (fp32, 16-byte stores when the internal
+          // slot order is the external one, i.e. kernel height 3)
+          if (qok) {
+            float* So = p.s_out + (((long long)t.b * NH + h) * p.nv + vpos) * p.s_jp;
+            auto cv = [&](float v) { return v == -FLT_MAX ? p.s_masked : v * p.s_scale; };
+            if (p.kh == MAXKH && (p.s_jp & 3) == 0 && p.s_jp >= ((1 + 9 * p.kt + 3) & ~3)) {
+#pragma unroll
+              for (int i4 = 0; i4 < (MAXJ + 3) / 4; ++i4) {
+                if (4 * i4 < 1 + 9 * p.kt) {
+                  float o4[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int j = 4 * i4 + e;
+                    o4[e] = (j < MAXJ && j < 1 + 9 * p.kt) ? cv(sv[j < MAXJ ? j : 0]) : 0.f;
+                  }
+                  *reinterpret_cast<float4*>(So + 4 * i4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+                }
+              }
+            } else {
+              So[0] = cv(sv[0]);
+#pragma unroll
+              for (int a = 0; a < MAXKT; ++a)
+#pragma unroll
+                for (int b = 0; b < MAXKH; ++b)
+#pragma unroll
+                  for (int c = 0; c < KW; ++c)
+                    if (a < p.kt && b < p.kh) So[1 + (a * p.kh + b) * KW + c] = cv(sv[1 + 9 * a + 3 * b + c]);
+            }
+          }
+          continue;
+        }
         // ---- softmax of this head's row (fp32): bos probability -> smem (fp32), window probabilities -> fp16 pairs in
         //      TMEM, column 8u + h = window entries (2u, 2u + 1) ----
         {
@@ -673,6 +713,7 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
         }
         if (dbg) dst_dbg[1 + hp] = clock64();
       }
+      if constexpr (SC) continue;   // next tile
       // ---- talking heads on the tensor cores: hand P to the MMA thread, convert its fp32 result to bf16 P' in place ----
       tmem_st_wait();
       tc_fence_before();
@@ -863,14 +904,22 @@ int launch_umma(const HostMaps& qm, const HostMaps& km, UmmaArgs& a, cudaStream_
     return NUWA_OK;
   };
   int lrc;
-  if (a.abs_frames) {
-    if (a.dw == 1) lrc = launch(attn_3dna_umma_kernel<1, true>);
-    else if (a.dw == 2) lrc = launch(attn_3dna_umma_kernel<2, true>);
-    else lrc = launch(attn_3dna_umma_kernel<4, true>);
+  if (a.s_out != nullptr && a.abs_frames) {
+    if (a.dw == 1) lrc = launch(attn_3dna_umma_kernel<1, true, true>);
+    else if (a.dw == 2) lrc = launch(attn_3dna_umma_kernel<2, true, true>);
+    else lrc = launch(attn_3dna_umma_kernel<4, true, true>);
+  } else if (a.s_out != nullptr) {
+    if (a.dw == 1) lrc = launch(attn_3dna_umma_kernel<1, false, true>);
+    else if (a.dw == 2) lrc = launch(attn_3dna_umma_kernel<2, false, true>);
+    else lrc = launch(attn_3dna_umma_kernel<4, false, true>);
+  } else if (a.abs_frames) {
+    if (a.dw == 1) lrc = launch(attn_3dna_umma_kernel<1, true, false>);
+    else if (a.dw == 2) lrc = launch(attn_3dna_umma_kernel<2, true, false>);
+    else lrc = launch(attn_3dna_umma_kernel<4, true, false>);
   } else {
-    if (a.dw == 1) lrc = launch(attn_3dna_umma_kernel<1, false>);
-    else if (a.dw == 2) lrc = launch(attn_3dna_umma_kernel<2, false>);
-    else lrc = launch(attn_3dna_umma_kernel<4, false>);
+    if (a.dw == 1) lrc = launch(attn_3dna_umma_kernel<1, false, false>);
+    else if (a.dw == 2) lrc = launch(attn_3dna_umma_kernel<2, false, false>);
+    else lrc = launch(attn_3dna_umma_kernel<4, false, false>);
   }
   if (lrc != NUWA_OK) return lrc;
   NUWA_CHECK_LAUNCH();
@@ -917,11 +966,63 @@ int attn_3dna_umma(const AttnParams& p, cudaStream_t stream) {
   return launch_umma(m, m, a, stream);
 }
 
+// Backward scores of Sparse3DNA on the same kernel (phase 1 only, twice): S[b][h][q][j] = qscale q . k_j (masked slots
+// -FLT_MAX, visible zero keys 0) and dP'[b][h][q][j] = dO . v_j (0 in both cases), fp32, row pitch jp -- what
+// attn3dna_bwd_scores (gather kernel) writes.  `p` follows the backward convention: p.q = first non-bos query row, p.k / p.v =
+// row 0 (bos) of the same q|k|v buffer, p.nq = p.nv = number of video tokens, p.t0 == 1.  Same envelope as attn_3dna_umma.
+int attn_3dna_umma_scores(const AttnParams& p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp, int jp,
+                          cudaStream_t stream) {
+  if (p.fmap != GW || p.t0 != 1 || p.t0_ptr != nullptr || S == nullptr || dPp == nullptr || dO == nullptr) return NUWA_ERR_INVALID;
+  if (p.H != NH || p.dh != DH || p.nq != p.nv || p.nv <= 0 || p.B <= 0) return NUWA_ERR_INVALID;
+  if (p.kw != KW || p.kh < 1 || p.kh > MAXKH || p.kt < 1 || p.kt > MAXKT) return NUWA_ERR_INVALID;
+  if (p.dt <= 0 || p.dh_ <= 0 || !(p.dw == 1 || p.dw == 2 || p.dw == 4)) return NUWA_ERR_INVALID;
+  if (!(p.kh & 1) || !(p.kt & 1) || jp < 1 + p.kt * p.kh * KW) return NUWA_ERR_INVALID;
+  if (p.max_frames <= 0 || p.nv > p.max_frames * GW * GW) return NUWA_ERR_INVALID;
+  if (p.head_scale != nullptr || p.bias != nullptr || p.key_mask != nullptr || p.null_k != nullptr) return NUWA_ERR_INVALID;
+  const bf16* q1 = reinterpret_cast<const bf16*>(p.q);       // sequence row 1
+  const bf16* k = reinterpret_cast<const bf16*>(p.k);
+  const bf16* v = reinterpret_cast<const bf16*>(p.v);
+  const bf16* row0 = q1 - p.q_rs;                              // q of the bos row: start of the token rows
+  const long long koff = k - row0, voff = v - row0;
+  if (p.k_rs != p.q_rs || p.v_rs != p.q_rs || p.k_bs != p.q_bs || p.v_bs != p.q_bs) return NUWA_ERR_INVALID;
+  if (koff < 0 || voff < 0 || koff + INNER > p.q_rs || voff + INNER > p.q_rs) return NUWA_ERR_INVALID;
+  if ((p.q_rs % 8) || (p.q_bs % 8) || (koff % 8) || (voff % 8) || (do_rs % 8) || (do_bs % 8) || do_rs < INNER) return NUWA_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(row0) & 15) || (reinterpret_cast<uintptr_t>(dO) & 15) || (reinterpret_cast<uintptr_t>(S) & 15) ||
+      (reinterpret_cast<uintptr_t>(dPp) & 15))
+    return NUWA_ERR_INVALID;
+
+  HostMaps qm, dm, km;
+  int rc = build_maps(km, row0, p.q_rs, p.q_bs, p.nv + 1, 1, p.dh_, p.B);               // keys / values: bos row first
+  if (rc != NUWA_OK) return rc;
+  if ((rc = build_maps(qm, q1, p.q_rs, p.q_bs, p.nv, 0, p.dh_, p.B)) != NUWA_OK) return rc;   // queries from row 1
+  if ((rc = build_maps(dm, reinterpret_cast<const bf16*>(dO), do_rs, do_bs, p.nv, 0, p.dh_, p.B)) != NUWA_OK) return rc;
+
+  UmmaArgs a = {};
+  a.B = p.B; a.nv = p.nv;
+  a.nf = (p.nv + GW * GW - 1) / (GW * GW);
+  a.maxf = p.max_frames;
+  a.kt = p.kt; a.kh = p.kh; a.dt = p.dt; a.dh = p.dh_; a.dw = p.dw; a.causal = p.causal;
+  a.q_tok0 = 0; a.kv_tok0 = 1;
+  a.scale_log2e = 0.f;
+  a.k_bs = p.k_bs; a.v_bs = p.v_bs;
+  a.s_jp = jp;
+  // logits: Q = q, K = k
+  a.koff = (int)koff; a.voff = (int)koff;
+  a.k0 = k; a.v0 = k;
+  a.s_out = S; a.s_scale = p.qscale; a.s_masked = -FLT_MAX;
+  if ((rc = launch_umma(qm, km, a, stream)) != NUWA_OK) return rc;
+  // dP' = dO V^T: Q = dO, K = v
+  a.koff = (int)voff; a.voff = (int)voff;
+  a.k0 = v; a.v0 = v;
+  a.s_out = dPp; a.s_scale = 1.0f; a.s_masked = 0.0f;
+  return launch_umma(dm, km, a, stream);
+}
+
 // SparseCross2DNA (nuwa_pytorch.py:851-895) on the same kernel: the nq queries at video positions 0 .. nq-1 (p.q / p.o
 // point at the first of them, i.e. past the bos row; p.t0 == 1) each see slot 0 = the learned null key / value and the
 // centred ck x ck window, dilation cdil, at their own grid position in every context frame, under the context mask.
 // Envelope: 16-wide grid, H == 8, dh == 64, ck == 3, cdil 1 / 2 / 4, <= 5 context frames, k|v rows sharing one stride.
-int attn_cross2dna_umma(const AttnParams& p, cudaStream_t stream) {
+static int cross2dna_setup(const AttnParams& p, HostMaps& qm, HostMaps& km, UmmaArgs& a) {
   if (p.fmap != GW || p.t0 != 1 || p.t0_ptr != nullptr) return NUWA_ERR_INVALID;
   if (p.H != NH || p.dh != DH || p.nq <= 0 || p.B <= 0) return NUWA_ERR_INVALID;
   if (p.ck != KW || !(p.cdil == 1 || p.cdil == 2 || p.cdil == 4)) return NUWA_ERR_INVALID;
@@ -935,19 +1036,15 @@ int attn_cross2dna_umma(const AttnParams& p, cudaStream_t stream) {
   const bf16* kvbase = k < v ? k : v;
   const long long koff = k - kvbase, voff = v - kvbase;
   if (p.k_rs != p.v_rs || p.k_bs != p.v_bs || koff + INNER > p.k_rs || voff + INNER > p.k_rs) return NUWA_ERR_INVALID;
-  if (INNER > p.q_rs || (p.q_rs % 8) || (p.q_bs % 8) || (p.k_rs % 8) || (p.k_bs % 8) || (koff % 8) || (voff % 8) ||
-      (p.o_rs % 8) || (p.o_bs % 8))
+  if (INNER > p.q_rs || (p.q_rs % 8) || (p.q_bs % 8) || (p.k_rs % 8) || (p.k_bs % 8) || (koff % 8) || (voff % 8))
     return NUWA_ERR_INVALID;
-  if ((reinterpret_cast<uintptr_t>(p.q) & 15) || (reinterpret_cast<uintptr_t>(kvbase) & 15) ||
-      (reinterpret_cast<uintptr_t>(p.o) & 15))
-    return NUWA_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(p.q) & 15) || (reinterpret_cast<uintptr_t>(kvbase) & 15)) return NUWA_ERR_INVALID;
 
-  HostMaps qm, km;
   int rc = build_maps(qm, q, p.q_rs, p.q_bs, p.nq, 0, p.cdil, p.B);
   if (rc != NUWA_OK) return rc;
   if ((rc = build_maps(km, kvbase, p.k_rs, p.k_bs, frames * GW * GW, 0, p.cdil, p.B)) != NUWA_OK) return rc;
 
-  UmmaArgs a = {};
+  a = UmmaArgs{};
   a.B = p.B; a.nv = p.nq;
   a.nf = (p.nq + GW * GW - 1) / (GW * GW);
   a.maxf = a.nf;
@@ -958,9 +1055,43 @@ int attn_cross2dna_umma(const AttnParams& p, cudaStream_t stream) {
   a.key_mask = p.key_mask; a.mask_bs = p.mask_bs;
   a.scale_log2e = p.qscale * 1.4426950408889634f;
   a.talk = p.talk;
-  a.o = reinterpret_cast<bf16*>(p.o); a.o_bs = p.o_bs; a.o_rs = p.o_rs;
   a.k0 = k; a.v0 = v; a.k_bs = p.k_bs; a.v_bs = p.v_bs;
+  return NUWA_OK;
+}
+
+int attn_cross2dna_umma(const AttnParams& p, cudaStream_t stream) {
+  if ((p.o_rs % 8) || (p.o_bs % 8) || (reinterpret_cast<uintptr_t>(p.o) & 15)) return NUWA_ERR_INVALID;
+  HostMaps qm, km;
+  UmmaArgs a;
+  const int rc = cross2dna_setup(p, qm, km, a);
+  if (rc != NUWA_OK) return rc;
+  a.o = reinterpret_cast<bf16*>(p.o); a.o_bs = p.o_bs; a.o_rs = p.o_rs;
   return launch_umma(qm, km, a, stream);
+}
+
+// Backward scores of SparseCross2DNA (non-bos queries) in scores mode, as attn_3dna_umma_scores: S = qscale q . k_j over
+// [null key | window] with masked context tokens at -FLT_MAX, dP' = dO . v_j (null value in slot 0, 0 where masked).
+int attn_cross2dna_umma_scores(const AttnParams& p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp, int jp,
+                               cudaStream_t stream) {
+  if (S == nullptr || dPp == nullptr || dO == nullptr || jp < p.jmax) return NUWA_ERR_INVALID;
+  if ((do_rs % 8) || (do_bs % 8) || do_rs < INNER) return NUWA_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(dO) & 15) || (reinterpret_cast<uintptr_t>(S) & 15) || (reinterpret_cast<uintptr_t>(dPp) & 15))
+    return NUWA_ERR_INVALID;
+  HostMaps qm, km, dm;
+  UmmaArgs a;
+  int rc = cross2dna_setup(p, qm, km, a);
+  if (rc != NUWA_OK) return rc;
+  if ((rc = build_maps(dm, reinterpret_cast<const bf16*>(dO), do_rs, do_bs, p.nq, 0, p.cdil, p.B)) != NUWA_OK) return rc;
+  a.s_jp = jp;
+  a.voff = a.koff;
+  a.s_out = S; a.s_scale = p.qscale; a.s_masked = -FLT_MAX;
+  if ((rc = launch_umma(qm, km, a, stream)) != NUWA_OK) return rc;
+  const bf16* k = reinterpret_cast<const bf16*>(p.k);
+  const bf16* v = reinterpret_cast<const bf16*>(p.v);
+  a.koff = a.voff = (int)(v - (k < v ? k : v));
+  a.null_k = p.null_v;                 // slot 0 of dP' = dO . null_v
+  a.s_out = dPp; a.s_scale = 1.0f; a.s_masked = 0.0f;
+  return launch_umma(dm, km, a, stream);
 }
 
 }  // namespace nuwa

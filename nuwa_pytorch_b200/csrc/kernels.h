@@ -68,6 +68,10 @@ int attn_dense(const AttnParams& p, cudaStream_t s);
 int attn_3dna_halo(const AttnParams& p, cudaStream_t stream);           // attention_3dna_halo.cu
 int attn_3dna_umma(const AttnParams& p, cudaStream_t stream);           // attention_3dna_umma.cu
 int attn_cross2dna_umma(const AttnParams& p, cudaStream_t stream);      // attention_3dna_umma.cu
+int attn_cross2dna_umma_scores(const AttnParams& p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp, int jp,
+                               cudaStream_t stream);                    // attention_3dna_umma.cu
+int attn_3dna_umma_scores(const AttnParams& p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp, int jp,
+                          cudaStream_t stream);                         // attention_3dna_umma.cu
 int attn_dense_mma(const AttnParams& p, int nk, void* vT_ws, cudaStream_t stream);  // attention_mma.cu
 int attn_dense_x64(const AttnParams& p, int nk, cudaStream_t stream);                // attention_x64.cu
 int attn_dense_pres(const AttnParams& p, int nk, cudaStream_t stream);               // attention_dense_pres.cu

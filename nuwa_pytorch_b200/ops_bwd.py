@@ -176,6 +176,11 @@ def _rows(S, dPp, talk, dtalk, B, H, nq, J, jp, out_scale, key_mask=None, has_nu
     return Pp, dS
 
 
+# scores of the Sparse3DNA backward: 'auto' = tcgen05 kernel when inside its envelope and the pass has enough 128-query
+# tiles to occupy the machine, else the gather kernel; 'umma' / 'gather' force one (tests, tools)
+SCORES_VARIANT = 'auto'
+
+
 def attn_sparse3dna_bwd(qkv, do, *, B, n, H, dh, talk, dtalk, fmap, max_frames, kernel, dilation, causal):
     """Backward of ops.attn_sparse3dna over a full teacher-forced pass (positions 0..n-1, bos at 0).
     qkv: bf16 (B, n, 3*inner) saved by the forward; do: bf16 (B, n, inner) gradient of the attention output.
@@ -199,8 +204,14 @@ def attn_sparse3dna_bwd(qkv, do, *, B, n, H, dh, talk, dtalk, fmap, max_frames, 
         S = torch.empty(B, H, nq, jp, dtype=torch.float32, device=dev)
         dPp = torch.empty(B, H, nq, jp, dtype=torch.float32, device=dev)
         do_q = do.data_ptr() + inner * 2  # gradient rows of the non-bos queries
-        check(lib().nuwa_attn3dna_bwd_scores(p, do_q, n * inner, inner, ptr(S), ptr(dPp), jp, stream()),
-              "nuwa_attn3dna_bwd_scores")
+        rc = _lib.NUWA_ERR_INVALID
+        if SCORES_VARIANT == 'umma' or (SCORES_VARIANT == 'auto' and B * ((nq + 255) // 256) * 2 >= 64):
+            rc = lib().nuwa_attn3dna_bwd_scores_umma(p, do_q, n * inner, inner, ptr(S), ptr(dPp), jp, stream())
+            if rc != _lib.NUWA_ERR_INVALID or SCORES_VARIANT == 'umma':
+                check(rc, "nuwa_attn3dna_bwd_scores_umma")
+        if rc == _lib.NUWA_ERR_INVALID:
+            check(lib().nuwa_attn3dna_bwd_scores(p, do_q, n * inner, inner, ptr(S), ptr(dPp), jp, stream()),
+                  "nuwa_attn3dna_bwd_scores")
         # dS leaves the row kernel multiplied by the logit scale dh^-0.5, so dq = sum dS k and dk = sum dS q need no more
         Pp, dS = _rows(S, dPp, talk, dtalk, B, H, nq, J, jp, dh ** -0.5)
         check(lib().nuwa_attn3dna_bwd_dq(p, ptr(dS), jp, dqkv.data_ptr() + 3 * inner * 2, n * 3 * inner, 3 * inner,
@@ -297,7 +308,13 @@ def attn_cross2dna_bwd(q, kv, do, *, B, n, nk, H, dh, talk, dtalk, null_k, null_
     S = torch.empty(B, H, nq, jp, dtype=torch.float32, device=dev)
     dPp = torch.empty(B, H, nq, jp, dtype=torch.float32, device=dev)
     do_q = do.data_ptr() + inner * 2
-    check(lib().nuwa_attnx2_bwd_scores(p, do_q, n * inner, inner, ptr(S), ptr(dPp), jp, stream()), "nuwa_attnx2_bwd_scores")
+    rc = _lib.NUWA_ERR_INVALID
+    if SCORES_VARIANT == 'umma' or (SCORES_VARIANT == 'auto' and B * ((nq + 255) // 256) * 2 >= 64):
+        rc = lib().nuwa_attnx2_bwd_scores_umma(p, do_q, n * inner, inner, ptr(S), ptr(dPp), jp, stream())
+        if rc != _lib.NUWA_ERR_INVALID or SCORES_VARIANT == 'umma':
+            check(rc, "nuwa_attnx2_bwd_scores_umma")
+    if rc == _lib.NUWA_ERR_INVALID:
+        check(lib().nuwa_attnx2_bwd_scores(p, do_q, n * inner, inner, ptr(S), ptr(dPp), jp, stream()), "nuwa_attnx2_bwd_scores")
     Pp, dS = _rows(S, dPp, talk, dtalk, B, H, nq, J, jp, dh ** -0.5)  # masks already folded into S by the gather
     check(lib().nuwa_attnx2_bwd_dq(p, ptr(dS), jp, dq.data_ptr() + inner * 2, n * inner, inner, stream()),
           "nuwa_attnx2_bwd_dq")

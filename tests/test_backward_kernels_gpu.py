@@ -233,6 +233,79 @@ def test_attn_sparse3dna_bwd(cuda_device, causal, kernel, dil, n, H, dh):
         assert rel(dqkv.float()[..., part], x.grad[..., part]) < 2e-2, name
 
 
+@pytest.mark.parametrize("n,frames,cdil,B,masked", [(2561, 3, 1, 2, True), (2561, 3, 2, 2, True), (1281, 3, 4, 2, False),
+                                                    (1000, 1, 2, 3, True), (258, 2, 1, 2, True)])
+def test_cross2dna_bwd_scores_tcgen05_matches_gather(cuda_device, n, frames, cdil, B, masked):
+    """Backward of the SparseCross2DNA core with S / dP' from the tcgen05 kernel in scores mode vs the gather kernel:
+    dq, dk|dv, talking-heads and null key / value gradients; context mask incl. a fully masked frame."""
+    from nuwa_pytorch_b200 import ops_bwd
+    H, dh, fmap, ck = 8, 64, 16, 3
+    inner, nk = H * dh, frames * fmap * fmap
+    g = gen(n + 7 * frames + cdil)
+    dv_ = lambda t: None if t is None else t.to(cuda_device).contiguous()
+    q = dv_(torch.randn(B, n, inner, generator=g).bfloat16())
+    kv = dv_(torch.randn(B, nk, 2 * inner, generator=g).bfloat16())
+    do = dv_((torch.randn(B, n, inner, generator=g) / 8).bfloat16())
+    talk = dv_(torch.randn(H, H, generator=g) / 2)
+    null_k, null_v = dv_(torch.randn(inner, generator=g)), dv_(torch.randn(inner, generator=g))
+    mask = None
+    if masked:
+        mask = torch.rand(B, nk, generator=g) > 0.3
+        mask[0, :fmap * fmap] = False
+        mask = dv_(mask.to(torch.uint8))
+    outs = {}
+    for variant in ('gather', 'umma'):
+        ops_bwd.SCORES_VARIANT = variant
+        try:
+            dtalk = torch.zeros(H, H, device=cuda_device)
+            dnk, dnv = torch.zeros(inner, device=cuda_device), torch.zeros(inner, device=cuda_device)
+            dq, dkv = ops_bwd.attn_cross2dna_bwd(q, kv, do, B=B, n=n, nk=nk, H=H, dh=dh, talk=talk, dtalk=dtalk, null_k=null_k,
+                                                 null_v=null_v, dnull_k=dnk, dnull_v=dnv, key_mask=mask, fmap=fmap, ck=ck,
+                                                 cdil=cdil)
+        finally:
+            ops_bwd.SCORES_VARIANT = 'auto'
+        torch.cuda.synchronize()
+        outs[variant] = [t.float().clone() for t in (dq, dkv, dtalk, dnk, dnv)]
+    rs = [rel(a, b) for a, b in zip(outs['umma'], outs['gather'])]
+    print(f"  x2dna bwd scores tcgen05 vs gather n={n} frames={frames} d={cdil} masked={masked}: dq {rs[0]:.2e} dkv {rs[1]:.2e} "
+          f"dtalk {rs[2]:.2e} dnull {rs[3]:.2e}/{rs[4]:.2e}")
+    assert all(torch.isfinite(t).all() for t in outs['umma'])
+    assert rs[0] < 3e-3 and rs[1] < 3e-3 and rs[2] < 1e-3 and rs[3] < 1e-3 and rs[4] < 1e-3
+
+
+@pytest.mark.parametrize("causal", [True, False])
+@pytest.mark.parametrize("kernel,dil,nv,B,maxf", [((5, 3, 3), (1, 1, 1), 768, 2, 10), ((5, 3, 3), (2, 2, 2), 1279, 2, 10),
+                                                  ((5, 3, 3), (4, 4, 4), 2559, 3, 10), ((5, 3, 3), (1, 2, 4), 601, 1, 10),
+                                                  ((3, 3, 3), (2, 4, 2), 530, 2, 10), ((3, 1, 3), (1, 1, 4), 256, 2, 10),
+                                                  ((5, 3, 3), (2, 2, 2), 767, 2, 3), ((5, 3, 3), (1, 1, 1), 17, 1, 10)])
+def test_sparse3dna_bwd_scores_tcgen05_matches_gather(cuda_device, kernel, dil, nv, B, maxf, causal):
+    """Backward of the Sparse3DNA core with the logits S and dP' = dO V^T produced by the tcgen05 kernel in scores mode
+    vs by the gather kernel (same bf16 operands): dq|dk|dv (bf16) and the talking-heads gradient; causal and centred
+    windows (incl. visible zero keys past the sequence), kernel heights 1 and 3, ragged last frame."""
+    from nuwa_pytorch_b200 import ops_bwd
+    H, dh, fmap = 8, 64, 16
+    inner, n = H * dh, nv + 1
+    g = gen(nv + 13 * dil[1] + int(causal))
+    qkv = torch.randn(B, n, 3 * inner, generator=g).bfloat16().to(cuda_device)
+    do = (torch.randn(B, n, inner, generator=g) / 8).bfloat16().to(cuda_device)
+    talk = (torch.randn(H, H, generator=g) / 2).to(cuda_device)
+    outs = {}
+    for variant in ('gather', 'umma'):
+        ops_bwd.SCORES_VARIANT = variant
+        try:
+            dtalk = torch.zeros(H, H, device=cuda_device)
+            dqkv = ops_bwd.attn_sparse3dna_bwd(qkv, do, B=B, n=n, H=H, dh=dh, talk=talk, dtalk=dtalk, fmap=fmap,
+                                               max_frames=maxf, kernel=kernel, dilation=dil, causal=causal)
+        finally:
+            ops_bwd.SCORES_VARIANT = 'auto'
+        torch.cuda.synchronize()
+        outs[variant] = (dqkv.float(), dtalk.clone())
+    r, rt = rel(outs['umma'][0], outs['gather'][0]), rel(outs['umma'][1], outs['gather'][1])
+    print(f"  3dna bwd scores tcgen05 vs gather causal={causal} k={kernel} d={dil} nv={nv}: dqkv {r:.2e} dtalk {rt:.2e}")
+    assert torch.isfinite(outs['umma'][0]).all()
+    assert r < 3e-3 and rt < 1e-3   # both paths accumulate the same bf16 products in fp32; outputs are bf16-rounded
+
+
 @pytest.mark.parametrize("B,nq,nk,H,dh,null,masked", [(2, 37, 12, 2, 32, True, True), (3, 70, 50, 8, 64, True, False),
                                                        (2, 16, 16, 4, 16, False, True),
                                                        (2, 45, 256, 8, 64, True, True),     # cfg-3 text context: 257 slots,
