@@ -448,6 +448,16 @@ typedef struct {
   int mask_bs, has_null;
 } nuwa_attn_rows_params;
 int nuwa_attn_bwd_rows(const nuwa_attn_rows_params* p, void* stream);
+/* Dense attention backward (Attention core, nuwa_pytorch.py:339-378, under autograd), probability stage fused: per tile of
+ * 16 queries x 8 heads the logits S = Q K^T and dP' = dO V^T are recomputed on the tensor cores from TMA-staged K / V
+ * chunks and stay in shared memory; the softmax / talking-heads backward runs from there and writes P' (operand of
+ * dV = P'^T dO) and dS * out_scale (operand of dQ = dS K, dK = dS^T Q) as bf16 [B][8][nq][jp] (slot 0 = null key when
+ * p->null_k is set, slot has_null + j = key j, zero padding up to jp) and adds dW_talk to dtalk (fp32 [8][8], may be NULL).
+ * Replaces nuwa_bgemm (S) + nuwa_bgemm (dP') + nuwa_attn_bwd_rows and their fp32 [B][8][nq][jp] round trips through HBM.
+ * p: q / k / v pointers + strides, nq, B, qscale, talk, null_k / null_v (fp32, exact null logit as in the forward kernel),
+ * key_mask; dO: bf16 [B][nq] rows.  Envelope: H == 8, dh == 64, 1 <= nk <= 256; NUWA_ERR_INVALID outside it. */
+int nuwa_attn_dense_bwd_fused(const nuwa_attn_params* p, int nk, const void* dO, long long do_bs, int do_rs, void* Pp,
+                              void* dS, int jp, float* dtalk, float out_scale, void* stream);
 /* dense attention (nuwa_pytorch.py:339-378): K / V with the learned null slot prepended, zero padded to jp rows */
 int nuwa_kv_full_build(const void* k, const void* v, long long kv_bs, int kv_rs, const float* null_k, const float* null_v,
                        void* kfull, void* vfull, int B, int nk, int jp, int inner, void* stream);

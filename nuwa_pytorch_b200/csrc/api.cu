@@ -229,6 +229,10 @@ int nuwa_mask_scores(float* Sc, const unsigned char* mask, int mask_bs, int B, i
                      void* stream) {
   return mask_scores(Sc, mask, mask_bs, B, H, nq, jp, nk, has_null, S(stream));
 }
+int nuwa_attn_dense_bwd_fused(const nuwa_attn_params* p, int nk, const void* dO, long long do_bs, int do_rs, void* Pp,
+                              void* dS, int jp, float* dtalk, float out_scale, void* stream) {
+  return p ? attn_dense_bwd_fused(*p, nk, dO, do_bs, do_rs, Pp, dS, jp, dtalk, out_scale, S(stream)) : NUWA_ERR_INVALID;
+}
 int nuwa_attn3dna_bwd_scores_umma(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* Sc, float* dPp,
                                   int jp, void* stream) {
   return p ? attn_3dna_umma_scores(*p, dO, do_bs, do_rs, Sc, dPp, jp, S(stream)) : NUWA_ERR_INVALID;

@@ -68,6 +68,8 @@ int attn_dense(const AttnParams& p, cudaStream_t s);
 int attn_3dna_halo(const AttnParams& p, cudaStream_t stream);           // attention_3dna_halo.cu
 int attn_3dna_umma(const AttnParams& p, cudaStream_t stream);           // attention_3dna_umma.cu
 int attn_cross2dna_umma(const AttnParams& p, cudaStream_t stream);      // attention_3dna_umma.cu
+int attn_dense_bwd_fused(const AttnParams& p, int nk, const void* dO, long long do_bs, int do_rs, void* Pp, void* dS, int jp,
+                         float* dtalk, float out_scale, cudaStream_t stream);   // attention_dense_bwd.cu
 int attn_cross2dna_umma_scores(const AttnParams& p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp, int jp,
                                cudaStream_t stream);                    // attention_3dna_umma.cu
 int attn_3dna_umma_scores(const AttnParams& p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp, int jp,

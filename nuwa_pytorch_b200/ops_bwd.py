@@ -228,6 +228,16 @@ def attn_sparse3dna_bwd(qkv, do, *, B, n, H, dh, talk, dtalk, fmap, max_frames, 
     return dqkv
 
 
+# dense attention backward: True = fused probability stage (csrc/attention_dense_bwd.cu: S and dP' recomputed per 16-query
+# tile, never written to HBM); False = the materialised-logits path (two batched GEMMs + the row kernel).  Measured at the
+# cfg-3 cross-attention shape (tools/dense_bwd_perf.py): materialised 0.62 ms per layer, fused 0.69 ms -- the fused kernel
+# removes 692 MB of HBM traffic per layer but its row stage runs the two 8 x 8 head mixes and the dW products on the CUDA
+# cores (256 FMA per key slot) from shared memory with 2 warps per scheduler; until those move to mma.sync the
+# materialised path stays the default.  Gradient error vs fp32 autograd: dq 2.4e-3 / 2.9e-3, dW_talk 1.6e-4 / 1.6e-3
+# (the fused kernel keeps dP' as bf16 in shared memory).
+DENSE_BWD_FUSED = False
+
+
 def attn_dense_bwd(q_ptr, k_ptr, v_ptr, do, *, B, nq, nk, H, dh, q_bs, q_rs, kv_bs, kv_rs, talk, dtalk, null_k, null_v,
                    dnull_k, dnull_v, key_mask, dq_out, dq_bs, dq_rs, dk_ptr, dv_ptr, dkv_bs, dkv_rs, out_f32):
     """Backward of ops.attn_dense (Attention core with the learned null key, key mask and talking heads).
@@ -244,20 +254,36 @@ def attn_dense_bwd(q_ptr, k_ptr, v_ptr, do, *, B, nq, nk, H, dh, q_bs, q_rs, kv_
     vfull = torch.empty(B, jp, inner, dtype=torch.bfloat16, device=dev)
     check(lib().nuwa_kv_full_build(k_ptr, v_ptr, kv_bs, kv_rs, ptr(null_k), ptr(null_v), ptr(kfull), ptr(vfull), B, nk, jp,
                                    inner, stream()), "nuwa_kv_full_build")
-    S = torch.empty(B, H, nq, jp, dtype=torch.float32, device=dev)
-    dPp = torch.empty(B, H, nq, jp, dtype=torch.float32, device=dev)
     sc = (H * nq * jp, nq * jp)
     full_s = (jp * inner, dh)
-    bgemm(q_ptr, kfull, S, M=nq, N=jp, K=dh, a_trans=0, b_trans=0, lda=q_rs, ldb=inner, ldc=jp, batch1=B, batch2=H,
-          a_s=(q_bs, dh), b_s=full_s, c_s=sc, alpha=scale)
-    bgemm(do, vfull, dPp, M=nq, N=jp, K=dh, a_trans=0, b_trans=0, lda=inner, ldb=inner, ldc=jp, batch1=B, batch2=H,
-          a_s=(nq * inner, dh), b_s=full_s, c_s=sc)
-    fuse_mask = J <= 288  # the register-resident row kernel applies the key mask itself; the wide fallback wants it in S
-    if key_mask is not None and not fuse_mask:
-        check(lib().nuwa_mask_scores(ptr(S), ptr(key_mask), key_mask.stride(0), B, H, nq, jp, nk, has_null, stream()),
-              "nuwa_mask_scores")
-    Pp, dS = _rows(S, dPp, talk, dtalk, B, H, nq, J, jp, scale, key_mask=key_mask if fuse_mask else None, has_null=has_null)
-    del S, dPp
+    Pp = dS = None
+    if DENSE_BWD_FUSED and H == 8 and dh == 64 and nk <= 256 and nq >= 16:
+        # probability stage fused: S and dP' are recomputed on the tensor cores inside the kernel and never reach HBM
+        p = ops._attn_base(q_ptr, k_ptr, v_ptr, None, B, nq, 0, H, dh, q_bs, kv_bs, kv_bs, 0, q_rs, kv_rs, kv_rs, inner, talk)
+        p.null_k, p.null_v = ptr(null_k), ptr(null_v)
+        if key_mask is not None:
+            p.key_mask, p.mask_bs = ptr(key_mask), key_mask.stride(0)
+        Pp = torch.empty(B, H, nq, jp, dtype=torch.bfloat16, device=dev)
+        dS = torch.empty(B, H, nq, jp, dtype=torch.bfloat16, device=dev)
+        rc = lib().nuwa_attn_dense_bwd_fused(p, nk, ptr(do), nq * inner, inner, ptr(Pp), ptr(dS), jp, ptr(dtalk), scale, stream())
+        if rc == _lib.NUWA_ERR_INVALID:
+            Pp = dS = None
+        else:
+            check(rc, "nuwa_attn_dense_bwd_fused")
+    if Pp is None:
+        S = torch.empty(B, H, nq, jp, dtype=torch.float32, device=dev)
+        dPp = torch.empty(B, H, nq, jp, dtype=torch.float32, device=dev)
+        bgemm(q_ptr, kfull, S, M=nq, N=jp, K=dh, a_trans=0, b_trans=0, lda=q_rs, ldb=inner, ldc=jp, batch1=B, batch2=H,
+              a_s=(q_bs, dh), b_s=full_s, c_s=sc, alpha=scale)
+        bgemm(do, vfull, dPp, M=nq, N=jp, K=dh, a_trans=0, b_trans=0, lda=inner, ldb=inner, ldc=jp, batch1=B, batch2=H,
+              a_s=(nq * inner, dh), b_s=full_s, c_s=sc)
+        fuse_mask = J <= 288  # the register-resident row kernel applies the key mask itself; the wide fallback wants it in S
+        if key_mask is not None and not fuse_mask:
+            check(lib().nuwa_mask_scores(ptr(S), ptr(key_mask), key_mask.stride(0), B, H, nq, jp, nk, has_null, stream()),
+                  "nuwa_mask_scores")
+        Pp, dS = _rows(S, dPp, talk, dtalk, B, H, nq, J, jp, scale, key_mask=key_mask if fuse_mask else None,
+                       has_null=has_null)
+        del S, dPp
     # dQ = dS K
     bgemm(dS, kfull, dq_out, M=nq, N=dh, K=jp, a_trans=0, b_trans=1, lda=jp, ldb=inner, ldc=dq_rs, batch1=B, batch2=H,
           a_s=sc, b_s=full_s, c_s=(dq_bs, dh))

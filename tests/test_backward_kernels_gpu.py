@@ -233,6 +233,60 @@ def test_attn_sparse3dna_bwd(cuda_device, causal, kernel, dil, n, H, dh):
         assert rel(dqkv.float()[..., part], x.grad[..., part]) < 2e-2, name
 
 
+@pytest.mark.parametrize("B,nq,nk,null,masked", [(2, 2560, 256, True, True), (1, 300, 256, True, False), (3, 77, 100, True, True),
+                                                 (2, 256, 256, False, True), (1, 16, 1, True, False), (2, 50, 33, False, False)])
+def test_dense_bwd_fused_probability_stage_matches_materialised_path(cuda_device, B, nq, nk, null, masked):
+    """attention_dense_bwd.cu (S and dP' recomputed per 16-query tile on the tensor cores, softmax / talking-heads backward
+    from shared memory) vs the materialised-logits path (two batched GEMMs + row kernel) on identical bf16 operands:
+    dq, dk, dv, talking-heads and null key / value gradients.  Cfg-3 text-context shape, ragged query tiles, partial key
+    chunks, a single key, fully masked samples, with / without the null key."""
+    from nuwa_pytorch_b200 import ops_bwd
+    H, dh = 8, 64
+    inner = H * dh
+    g = gen(nq + nk + int(null))
+    dv_ = lambda t: None if t is None else t.to(cuda_device).contiguous()
+    q = dv_(torch.randn(B, nq, inner, generator=g).bfloat16())
+    kv = dv_(torch.randn(B, nk, 2 * inner, generator=g).bfloat16())
+    do = dv_((torch.randn(B, nq, inner, generator=g) / 8).bfloat16())
+    talk = dv_(torch.randn(H, H, generator=g) / 2)
+    null_k = dv_(torch.randn(inner, generator=g)) if null else None
+    null_v = dv_(torch.randn(inner, generator=g)) if null else None
+    mask = None
+    if masked:
+        mask = torch.rand(B, nk, generator=g) > 0.3
+        if null:
+            mask[0] = False          # a sample that sees only the null key
+        else:
+            mask[:, 0] = True        # without a null key every row needs one visible key
+        mask = dv_(mask.to(torch.uint8))
+    outs = {}
+    for fused in (False, True):
+        ops_bwd.DENSE_BWD_FUSED = fused
+        try:
+            dtalk = torch.zeros(H, H, device=cuda_device)
+            dnk, dnv = torch.zeros(inner, device=cuda_device), torch.zeros(inner, device=cuda_device)
+            dq = torch.empty(B, nq, inner, dtype=torch.bfloat16, device=cuda_device)
+            dkv = torch.empty(B, nk, 2 * inner, dtype=torch.bfloat16, device=cuda_device)
+            ops_bwd.attn_dense_bwd(q.data_ptr(), kv.data_ptr(), kv.data_ptr() + inner * 2, do, B=B, nq=nq, nk=nk, H=H, dh=dh,
+                                   q_bs=nq * inner, q_rs=inner, kv_bs=nk * 2 * inner, kv_rs=2 * inner, talk=talk, dtalk=dtalk,
+                                   null_k=null_k, null_v=null_v, dnull_k=dnk if null else None, dnull_v=dnv if null else None,
+                                   key_mask=mask, dq_out=dq, dq_bs=nq * inner, dq_rs=inner, dk_ptr=dkv.data_ptr(),
+                                   dv_ptr=dkv.data_ptr() + inner * 2, dkv_bs=nk * 2 * inner, dkv_rs=2 * inner, out_f32=False)
+        finally:
+            ops_bwd.DENSE_BWD_FUSED = False
+        torch.cuda.synchronize()
+        outs[fused] = [t.float().clone() for t in (dq, dkv, dtalk, dnk, dnv)]
+    rs = [rel(a, b) for a, b in zip(outs[True], outs[False])]
+    print(f"  dense bwd fused vs materialised B={B} nq={nq} nk={nk} null={null} masked={masked}: dq {rs[0]:.2e} dkv {rs[1]:.2e} "
+          f"dtalk {rs[2]:.2e} dnull {rs[3]:.2e}/{rs[4]:.2e}")
+    assert all(torch.isfinite(t).all() for t in outs[True])
+    # the fused kernel keeps dP' as bf16 and P as fp16 x fp32 factor in shared memory (the other path: fp32 in HBM) and uses
+    # the exact fp32 null-key logit like the forward kernel (the other path rounds the null key to bf16)
+    assert rs[0] < 6e-3 and rs[1] < 6e-3 and rs[2] < 6e-3
+    if null:
+        assert rs[3] < 6e-3 and rs[4] < 6e-3
+
+
 @pytest.mark.parametrize("n,frames,cdil,B,masked", [(2561, 3, 1, 2, True), (2561, 3, 2, 2, True), (1281, 3, 4, 2, False),
                                                     (1000, 1, 2, 3, True), (258, 2, 1, 2, True)])
 def test_cross2dna_bwd_scores_tcgen05_matches_gather(cuda_device, n, frames, cdil, B, masked):
