@@ -14,8 +14,8 @@
 // under autograd; the forward formulation (chunk maxima + final factors, exact fp32 null-key logit, key mask as bits)
 // is the one of attention_dense_pres.cu, so the recomputed P is the forward's P.
 //
-// Roles: warps 0-7 = heads in phases 1-2 (S / dP' chunks), = 4 warp pairs x one query row at a time in phase 3 (lane owns
-// key slots 32 half + lane + 64 i); warp 8 = TMA producer (Q|dO tile, K chunks, V chunks through a 2-stage ring).
+// Roles: warps 0-7 = heads in phases 1-2 (S / dP' chunks), = query rows w, w + 8 in phase 3 (16-slot tiles on mma.sync);
+// warp 8 = TMA producer (Q tile, dO tile, K half-chunks, V half-chunks through a 4-stage ring of 16 KB).
 #include <float.h>
 #include <cuda_fp16.h>
 
@@ -43,7 +43,6 @@ constexpr int NULLJ = MAXK;                  // slab slot of the null key
 constexpr int PP = 280;                      // slab row pitch in 16-bit elements
 constexpr int HS = BQ * PP + 8;              // head stride
 constexpr int NCF = 12;                      // per (head, query): chunk maxima / final factors (8 chunks + null at 8)
-constexpr int NJ = 5;                        // key slots per lane in phase 3: 32 half + lane + 64 i
 
 constexpr int OFF_P = NSTG * STAGE;
 constexpr int OFF_G = OFF_P + NH * HS * 2;
@@ -111,7 +110,6 @@ attn_dense_bwd_fused_kernel(const __grid_constant__ CUtensorMap qmap, const __gr
   float* nullv = nullk + INNER;
   float* Wt = reinterpret_cast<float*>(sm + OFF_W);
   float* dW_cta = reinterpret_cast<float*>(sm + OFF_DW);
-  float* xch = reinterpret_cast<float*>(sm + OFF_XCH);
   uint32_t* maskw = reinterpret_cast<uint32_t*>(sm + OFF_MASK);  // [8] one bit per key: 1 = attend
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
   uint64_t* empty = full + NSTG;
@@ -122,7 +120,7 @@ attn_dense_bwd_fused_kernel(const __grid_constant__ CUtensorMap qmap, const __gr
   const int b = (int)blockIdx.x / tiles_q;
   const int q0 = ((int)blockIdx.x - b * tiles_q) * BQ;
   const int nchunk = p.nchunk;
-  const int NS = 2 + 4 * nchunk;  // Q tile, dO tile, K half-chunks, V half-chunks
+  const int NS = 2 + 4 * nchunk;  // Q tile, dO tile, then per chunk: two K and two V half-chunks
   const bool has_null = p.has_null != 0;
 
   // ---- one-time shared state of the 8 consumer warps ----
@@ -169,9 +167,10 @@ attn_dense_bwd_fused_kernel(const __grid_constant__ CUtensorMap qmap, const __gr
 #pragma unroll
           for (int h = 0; h < NH; ++h) tma_load_3d(sm_u + st * STAGE + h * QBOX, m, &full[st], h * DH, q0, b);
         } else {
-          const int hc = s - 2;                       // half-chunk index: K halves first, then V halves
-          const CUtensorMap* m = hc < 2 * nchunk ? &kmap : &vmap;
-          const int row = (hc < 2 * nchunk ? hc : hc - 2 * nchunk) * HK;
+          const int hc = s - 2;                       // per 32-key chunk: K half 0, K half 1, V half 0, V half 1
+          const int c = hc >> 2, part = hc & 3;
+          const CUtensorMap* m = part < 2 ? &kmap : &vmap;
+          const int row = c * PK + (part & 1) * HK;
 #pragma unroll
           for (int h = 0; h < NH; ++h) tma_load_3d(sm_u + st * STAGE + h * HBOX, m, &full[st], h * DH, row, b);
         }
@@ -285,6 +284,30 @@ attn_dense_bwd_fused_kernel(const __grid_constant__ CUtensorMap qmap, const __gr
 #pragma unroll
           for (int n2 = 0; n2 < 2; ++n2) mma_bf16(s[np * 2 + n2], qa[ks], kf[ks][n2 * 2], kf[ks][n2 * 2 + 1]);
       }
+      // dP'_h chunk = dO_h V_h^T (V rows are a K-major B operand exactly like K); interleaved with the logits of the same
+      // chunk so that the two independent MMA / bookkeeping streams hide each other's latencies
+      float d[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) d[nt][0] = d[nt][1] = d[nt][2] = d[nt][3] = 0.f;
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        mbar_wait(&full[st], par);
+        const uint32_t vb = sm_u + st * STAGE + h * HBOX;
+        uint32_t vf[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ldsm4(vf[ks], vb + k_sw[ks]);
+        release();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+          for (int n2 = 0; n2 < 2; ++n2) mma_bf16(d[np * 2 + n2], da[ks], vf[ks][n2 * 2], vf[ks][n2 * 2 + 1]);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(Gh + (g + 8 * r) * PP + c * PK + 2 * t);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dst[nt * 4] = pack_bf16x2(d[nt][2 * r], d[nt][2 * r + 1]);
+      }
       const uint32_t mw = maskw[c];
       if (mw != 0xffffffffu) {
 #pragma unroll
@@ -331,142 +354,161 @@ attn_dense_bwd_fused_kernel(const __grid_constant__ CUtensorMap qmap, const __gr
         CFh[q * NCF + c] = used ? fast_exp2(fmaf(CFh[q * NCF + c], c1, mneg)) * inv : 0.f;
       }
     }
-    // ---- dP'_h = dO_h V_h^T, chunk by chunk (V rows are a K-major B operand exactly like K) ----
-    for (int c = 0; c < nchunk; ++c) {
-      float d[4][4];
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) d[nt][0] = d[nt][1] = d[nt][2] = d[nt][3] = 0.f;
-#pragma unroll
-      for (int np = 0; np < 2; ++np) {
-        mbar_wait(&full[st], par);
-        const uint32_t vb = sm_u + st * STAGE + h * HBOX;
-        uint32_t vf[4][4];
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) ldsm4(vf[ks], vb + k_sw[ks]);
-        release();
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-          for (int n2 = 0; n2 < 2; ++n2) mma_bf16(d[np * 2 + n2], da[ks], vf[ks][n2 * 2], vf[ks][n2 * 2 + 1]);
-      }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        uint32_t* dst = reinterpret_cast<uint32_t*>(Gh + (g + 8 * r) * PP + c * PK + 2 * t);
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) dst[nt * 4] = pack_bf16x2(d[nt][2 * r], d[nt][2 * r + 1]);
-      }
-    }
   }
   consumer_sync();
 
-  // ================= phase 3 (warp pair = one query row at a time): softmax / talking-heads backward =================
+  // ================= phase 3 (warp = query rows w and w + 8): softmax / talking-heads backward on the tensor cores =================
+  // Per (row, 16-slot tile) -- slots e0 .. e0 + 15 of the slab, 16 key tiles + the null tile -- with mma.sync m16n8k16:
+  //   (1) P'[e][g]  = sum_h P16[h][e] (W[g][h] cf[h])     A = slots x heads (fp16, k = 8 .. 15 repeats the heads), B = W cf as
+  //                                                        fp16 high | low halves  (the forward kernel's mix)          -> HBM
+  //   (2) dP[e][h]  = sum_g dP'[g][e] W[g][h]             A = slots x heads (bf16 dP'), B = W as bf16 high | low
+  //   (3) dW[g][h] += sum_e dP'[g][e] P[h][e]             A = dP' rows of head g (slots = contraction), B = normalised P as
+  //                                                        bf16 high + low (two MMAs), accumulated in 4 registers per lane
+  //   delta[h] = sum_e P[h][e] dP[e][h] from the C fragment of (2): lane (gq, t) holds slots gq, gq + 8 of heads 2t, 2t + 1,
+  //   exactly the P values of its A fragment in (1); reduced over gq by shuffles at the end of the row (pass A).
+  //   Pass B recomputes (2) per tile and emits dS[h][e] = P (dP - delta) dh^-0.5                                       -> HBM
   {
-    const int pair = warp >> 1, half = warp & 1;
-    float dW[NH * NH];
-#pragma unroll
-    for (int i = 0; i < NH * NH; ++i) dW[i] = 0.f;
     const long long hs = (long long)p.nq * p.jp;   // head stride of the outputs
-    const uint32_t wt_u = smem_u32(Wt);
-    // Per key slot everything but the row sums is slot-local, so P and dP' are NOT held across the row (with the 64 dW
-    // accumulators they would not fit the 168 registers a 9-warp CTA gets): pass A loads a slot's 8 + 8 values from the
-    // slabs, emits P', accumulates dW and the row sums sum_j P dP; pass B reloads the slot, recomputes dP and emits dS.
-    auto load_slot = [&](int q, int i, float (&P)[NH], float (&G)[NH], int& outj) {
-      const int j = 32 * half + lane + 64 * i;           // slab slot
-      const bool key = j < MAXK, nul = has_null && j == NULLJ;
-      outj = key ? j + p.has_null : (nul ? 0 : j);
-      if (key || nul) {
-        const int ci = key ? (j >> 5) : 8;
-#pragma unroll
-        for (int hh = 0; hh < NH; ++hh) {
-          P[hh] = __half2float(P16[(size_t)hh * HS + q * PP + j]) * CF[(hh * BQ + q) * NCF + ci];
-          G[hh] = __bfloat162float(G16[(size_t)hh * HS + q * PP + j]);
-        }
-      } else {
-#pragma unroll
-        for (int hh = 0; hh < NH; ++hh) P[hh] = G[hh] = 0.f;
-      }
+    const uint32_t pa_u = smem_u32(P16) + 2u * (2 * t * HS);    // P16[2t][.][.]; head 2t + 1 is HS elements further
+    const uint32_t ga_u = smem_u32(G16) + 2u * (2 * t * HS);
+    const uint32_t pr_u = smem_u32(P16) + 2u * (g * HS);        // rows of head g (operands of (3))
+    const uint32_t gr_u = smem_u32(G16) + 2u * (g * HS);
+    auto lds16 = [](uint32_t addr) -> uint32_t {
+      unsigned short v;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+      return v;
     };
-    for (int q = pair; q < BQ; q += 4) {
-      const bool qok = q0 + q < p.nq;   // uniform over the pair
+    auto lds32 = [](uint32_t addr) -> uint32_t {
+      uint32_t v;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+      return v;
+    };
+    auto mma_f16_dup = [](float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
+      asm volatile(
+          "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%4,%5}, {%6,%7}, {%0,%1,%2,%3};"
+          : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+          : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    };
+    auto mma_bf16_dup = [](float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
+      asm volatile(
+          "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%4,%5}, {%6,%7}, {%0,%1,%2,%3};"
+          : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+          : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    };
+    auto mma_bf16_top = [](float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {   // rows 8 .. 15 of A are zero
+      const uint32_t z = 0u;
+      asm volatile(
+          "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%5}, {%7,%8}, {%0,%1,%2,%3};"
+          : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+          : "r"(a0), "r"(z), "r"(a2), "r"(b0), "r"(b1));
+    };
+    auto split_bf16 = [](float x, float y, uint32_t& hi, uint32_t& lo) {
+      const bf16 xh = __float2bfloat16(x), yh = __float2bfloat16(y);
+      hi = pack_bf16x2(__bfloat162float(xh), __bfloat162float(yh));
+      lo = pack_bf16x2(x - __bfloat162float(xh), y - __bfloat162float(yh));
+    };
+    // B operand of (2): k = source head g' (2t, 2t + 1 | the same + 8 for the low halves), n = gq = destination head h
+    const float w2a = Wt[(2 * t) * NH + g], w2b = Wt[(2 * t + 1) * NH + g];
+    uint32_t wb_hi, wb_lo;
+    split_bf16(w2a, w2b, wb_hi, wb_lo);
+    // W[g_out = gq][h = 2t], W[gq][2t + 1] for the B operand of (1), multiplied by the chunk factors per tile
+    const float w1a = Wt[g * NH + 2 * t], w1b = Wt[g * NH + 2 * t + 1];
+    float dWc[4] = {0.f, 0.f, 0.f, 0.f};   // (3): C[g = gq][h = 2t, 2t + 1] in c0, c1
+    constexpr int NT = 17;                 // 16 key tiles + the null tile (slots 256 .. 271)
+    for (int q = warp; q < BQ; q += NH) {
+      const bool qok = q0 + q < p.nq;
       const long long base = ((long long)b * NH * p.nq + (q0 + q)) * p.jp;
-      float dot[NH];
-#pragma unroll
-      for (int hh = 0; hh < NH; ++hh) dot[hh] = 0.f;
+      const float* cfa = CF + ((2 * t) * BQ + q) * NCF;       // factors of heads 2t, 2t + 1 (A-side heads of (1), C heads of (2))
+      const float* cfb = cfa + BQ * NCF;
+      const float* cfg = CF + (g * BQ + q) * NCF;             // factors of head gq (B operand of (3))
+      const uint32_t prow = 2u * (q * PP);
+      float d0 = 0.f, d1 = 0.f;                               // partial row sums of heads 2t, 2t + 1
 #pragma unroll 1
-      for (int i = 0; i < NJ - half; ++i) {   // slots 288 .. 319 (half 1, i = 4) lie beyond every possible jp
-        float P[NH], G[NH], dp[NH];
-        int outj;
-        load_slot(q, i, P, G, outj);
-#pragma unroll
-        for (int hh = 0; hh < NH; ++hh) dp[hh] = 0.f;
-#pragma unroll
-        for (int gg = 0; gg < NH; ++gg) {
-          const float dpp = G[gg];
-          float a = 0.f;
-          float wrow[NH];   // re-read per (slot, g): held in registers the 64 weights would spill
-#pragma unroll
-          for (int h4 = 0; h4 < NH; h4 += 4)
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(wrow[h4]), "=f"(wrow[h4 + 1]), "=f"(wrow[h4 + 2]), "=f"(wrow[h4 + 3])
-                         : "r"(wt_u + (uint32_t)(gg * NH + h4) * 4u));
-#pragma unroll
-          for (int hh = 0; hh < NH; ++hh) {
-            a = fmaf(wrow[hh], P[hh], a);
-            dp[hh] = fmaf(wrow[hh], dpp, dp[hh]);
-            dW[gg * NH + hh] = fmaf(dpp, P[hh], dW[gg * NH + hh]);
+      for (int tl = 0; tl < NT; ++tl) {
+        const int e0 = tl * 16;
+        const int ci = tl < 16 ? (tl >> 1) : 8;
+        const float f0 = cfa[ci], f1 = cfb[ci], fg = cfg[ci];
+        // ---- fragments: slots gq, gq + 8 of heads 2t, 2t + 1 ----
+        const uint32_t a = prow + 2u * (e0 + g);
+        const uint32_t x00 = lds16(pa_u + a), x01 = lds16(pa_u + 2 * HS + a), x10 = lds16(pa_u + a + 16), x11 = lds16(pa_u + 2 * HS + a + 16);
+        const uint32_t y00 = lds16(ga_u + a), y01 = lds16(ga_u + 2 * HS + a), y10 = lds16(ga_u + a + 16), y11 = lds16(ga_u + 2 * HS + a + 16);
+        // (1) forward mix
+        {
+          const float b0f = w1a * f0, b1f = w1b * f1;
+          const __half h0 = __float2half_rn(b0f), h1 = __float2half_rn(b1f);
+          const __half2 hi = __halves2half2(h0, h1);
+          const uint32_t bh = *reinterpret_cast<const uint32_t*>(&hi);
+          const uint32_t bl = pack_h2(b0f - __half2float(h0), b1f - __half2float(h1));
+          float c[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_f16_dup(c, x00 | (x01 << 16), x10 | (x11 << 16), bh, bl);
+          if (qok) {   // C[e = gq (+8)][g_out = 2t, 2t + 1]
+            const int j0 = e0 + g, j1 = j0 + 8;
+            const int o0 = j0 < MAXK ? j0 + p.has_null : ((has_null && j0 == NULLJ) ? 0 : j0);
+            const int o1 = j1 < MAXK ? j1 + p.has_null : j1;
+            bf16* d = p.Pp + base + (long long)(2 * t) * hs;
+            if (o0 < p.jp) { d[o0] = __float2bfloat16(c[0]); d[hs + o0] = __float2bfloat16(c[1]); }
+            if (o1 < p.jp) { d[o1] = __float2bfloat16(c[2]); d[hs + o1] = __float2bfloat16(c[3]); }
           }
-          if (qok && outj < p.jp) p.Pp[base + gg * hs + outj] = __float2bfloat16(a);
         }
-#pragma unroll
-        for (int hh = 0; hh < NH; ++hh) dot[hh] = fmaf(P[hh], dp[hh], dot[hh]);
+        // (2) dP and the row sums
+        {
+          float c[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_bf16_dup(c, y00 | (y01 << 16), y10 | (y11 << 16), wb_hi, wb_lo);
+          const float p00 = __half2float(__ushort_as_half((unsigned short)x00)) * f0, p01 = __half2float(__ushort_as_half((unsigned short)x01)) * f1;
+          const float p10 = __half2float(__ushort_as_half((unsigned short)x10)) * f0, p11 = __half2float(__ushort_as_half((unsigned short)x11)) * f1;
+          d0 = fmaf(p00, c[0], d0); d0 = fmaf(p10, c[2], d0);
+          d1 = fmaf(p01, c[1], d1); d1 = fmaf(p11, c[3], d1);
+        }
+        // (3) dW: A = dP' rows of head gq over the 16 slots, B = normalised P of head gq (n) ... as [k = slot][n = head]
+        {
+          const uint32_t r = prow + 2u * (e0 + 2 * t);
+          const uint32_t ga0 = lds32(gr_u + r), ga2 = lds32(gr_u + r + 16);        // dP'[gq][e0 + 2t, +1], [e0 + 2t + 8, +9]
+          const uint32_t pb0 = lds32(pr_u + r), pb1 = lds32(pr_u + r + 16);        // P16[gq][same slots]
+          const __half2 q0h = *reinterpret_cast<const __half2*>(&pb0), q1h = *reinterpret_cast<const __half2*>(&pb1);
+          const float2 u0 = __half22float2(q0h), u1 = __half22float2(q1h);
+          uint32_t b0h, b0l, b1h, b1l;
+          split_bf16(u0.x * fg, u0.y * fg, b0h, b0l);
+          split_bf16(u1.x * fg, u1.y * fg, b1h, b1l);
+          mma_bf16_top(dWc, ga0, ga2, b0h, b1h);
+          mma_bf16_top(dWc, ga0, ga2, b0l, b1l);
+        }
       }
-      // row sums over the warp pair
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int hh = 0; hh < NH; ++hh) dot[hh] += __shfl_xor_sync(0xffffffffu, dot[hh], o);
-      float* xp = xch + (pair * 2) * NH;
-      if (lane == 0) {
-#pragma unroll
-        for (int hh = 0; hh < NH; ++hh) xp[half * NH + hh] = dot[hh];
-      }
-      asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory");
-#pragma unroll
-      for (int hh = 0; hh < NH; ++hh) dot[hh] += xp[(half ^ 1) * NH + hh];
-      asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory");   // both halves have read before the next row writes
-      if (qok) {
+      // row sums of heads 2t, 2t + 1 over the slots held by the 8 lanes with this t
+      d0 += __shfl_xor_sync(0xffffffffu, d0, 4);  d1 += __shfl_xor_sync(0xffffffffu, d1, 4);
+      d0 += __shfl_xor_sync(0xffffffffu, d0, 8);  d1 += __shfl_xor_sync(0xffffffffu, d1, 8);
+      d0 += __shfl_xor_sync(0xffffffffu, d0, 16); d1 += __shfl_xor_sync(0xffffffffu, d1, 16);
+      if (!qok) continue;
+      // ---- pass B: dS ----
 #pragma unroll 1
-        for (int i = 0; i < NJ - half; ++i) {
-          float P[NH], G[NH], dp[NH];
-          int outj;
-          load_slot(q, i, P, G, outj);
-          if (outj < p.jp) {
-#pragma unroll
-            for (int hh = 0; hh < NH; ++hh) dp[hh] = 0.f;
-#pragma unroll
-            for (int gg = 0; gg < NH; ++gg) {
-              float wrow[NH];
-#pragma unroll
-              for (int h4 = 0; h4 < NH; h4 += 4)
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                             : "=f"(wrow[h4]), "=f"(wrow[h4 + 1]), "=f"(wrow[h4 + 2]), "=f"(wrow[h4 + 3])
-                             : "r"(wt_u + (uint32_t)(gg * NH + h4) * 4u));
-#pragma unroll
-              for (int hh = 0; hh < NH; ++hh) dp[hh] = fmaf(wrow[hh], G[gg], dp[hh]);
-            }
-#pragma unroll
-            for (int hh = 0; hh < NH; ++hh)
-              p.dS[base + hh * hs + outj] = __float2bfloat16(P[hh] * (dp[hh] - dot[hh]) * p.out_scale);
-          }
+      for (int tl = 0; tl < NT; ++tl) {
+        const int e0 = tl * 16;
+        const int j0 = e0 + g, j1 = j0 + 8;
+        const int o0 = j0 < MAXK ? j0 + p.has_null : ((has_null && j0 == NULLJ) ? 0 : j0);
+        const int o1 = j1 < MAXK ? j1 + p.has_null : j1;
+        if (__all_sync(0xffffffffu, o0 >= p.jp && o1 >= p.jp)) continue;
+        const int ci = tl < 16 ? (tl >> 1) : 8;
+        const float f0 = cfa[ci], f1 = cfb[ci];
+        const uint32_t a = prow + 2u * (e0 + g);
+        const uint32_t x00 = lds16(pa_u + a), x01 = lds16(pa_u + 2 * HS + a), x10 = lds16(pa_u + a + 16), x11 = lds16(pa_u + 2 * HS + a + 16);
+        const uint32_t y00 = lds16(ga_u + a), y01 = lds16(ga_u + 2 * HS + a), y10 = lds16(ga_u + a + 16), y11 = lds16(ga_u + 2 * HS + a + 16);
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16_dup(c, y00 | (y01 << 16), y10 | (y11 << 16), wb_hi, wb_lo);
+        const float p00 = __half2float(__ushort_as_half((unsigned short)x00)) * f0, p01 = __half2float(__ushort_as_half((unsigned short)x01)) * f1;
+        const float p10 = __half2float(__ushort_as_half((unsigned short)x10)) * f0, p11 = __half2float(__ushort_as_half((unsigned short)x11)) * f1;
+        bf16* d = p.dS + base + (long long)(2 * t) * hs;
+        if (o0 < p.jp) {
+          d[o0] = __float2bfloat16(p00 * (c[0] - d0) * p.out_scale);
+          d[hs + o0] = __float2bfloat16(p01 * (c[1] - d1) * p.out_scale);
+        }
+        if (o1 < p.jp) {
+          d[o1] = __float2bfloat16(p10 * (c[2] - d0) * p.out_scale);
+          d[hs + o1] = __float2bfloat16(p11 * (c[3] - d1) * p.out_scale);
         }
       }
     }
     if (p.dtalk != nullptr) {
-#pragma unroll
-      for (int i = 0; i < NH * NH; ++i) {
-        const float v = warp_sum(dW[i]);
-        if (lane == 0) atomicAdd(&dW_cta[i], v);
-      }
+      atomicAdd(&dW_cta[g * NH + 2 * t], dWc[0]);       // C[g = gq][h = 2t], C[gq][2t + 1]
+      atomicAdd(&dW_cta[g * NH + 2 * t + 1], dWc[1]);
       consumer_sync();
       if (tid < NH * NH) atomicAdd(p.dtalk + tid, dW_cta[tid]);
     }

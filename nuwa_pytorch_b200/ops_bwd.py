@@ -229,13 +229,13 @@ def attn_sparse3dna_bwd(qkv, do, *, B, n, H, dh, talk, dtalk, fmap, max_frames, 
 
 
 # dense attention backward: True = fused probability stage (csrc/attention_dense_bwd.cu: S and dP' recomputed per 16-query
-# tile, never written to HBM); False = the materialised-logits path (two batched GEMMs + the row kernel).  Measured at the
-# cfg-3 cross-attention shape (tools/dense_bwd_perf.py): materialised 0.62 ms per layer, fused 0.69 ms -- the fused kernel
-# removes 692 MB of HBM traffic per layer but its row stage runs the two 8 x 8 head mixes and the dW products on the CUDA
-# cores (256 FMA per key slot) from shared memory with 2 warps per scheduler; until those move to mma.sync the
-# materialised path stays the default.  Gradient error vs fp32 autograd: dq 2.4e-3 / 2.9e-3, dW_talk 1.6e-4 / 1.6e-3
-# (the fused kernel keeps dP' as bf16 in shared memory).
-DENSE_BWD_FUSED = False
+# tile on the tensor cores, head mixes / dW on mma.sync from shared memory, nothing but P' and dS written to HBM) when the
+# call is inside its envelope; False = the materialised-logits path (two batched GEMMs + the row kernel), kept for the
+# A/B test.  Measured at the cfg-3 cross-attention shape (tools/dense_bwd_perf.py, whole attn_dense_bwd call per layer):
+# materialised 0.62 ms, fused 0.57 ms (with the head mixes on the CUDA cores it was 0.69 ms).  Gradient error vs fp32
+# autograd (materialised / fused): dq 2.4e-3 / 2.9e-3, dk|dv 2.4e-3 / 2.6e-3, dW_talk 1.6e-4 / 1.6e-3 (dP' is held as
+# bf16 in shared memory).
+DENSE_BWD_FUSED = True
 
 
 def attn_dense_bwd(q_ptr, k_ptr, v_ptr, do, *, B, nq, nk, H, dh, q_bs, q_rs, kv_bs, kv_rs, talk, dtalk, null_k, null_v,

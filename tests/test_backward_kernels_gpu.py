@@ -273,7 +273,7 @@ def test_dense_bwd_fused_probability_stage_matches_materialised_path(cuda_device
                                    key_mask=mask, dq_out=dq, dq_bs=nq * inner, dq_rs=inner, dk_ptr=dkv.data_ptr(),
                                    dv_ptr=dkv.data_ptr() + inner * 2, dkv_bs=nk * 2 * inner, dkv_rs=2 * inner, out_f32=False)
         finally:
-            ops_bwd.DENSE_BWD_FUSED = False
+            ops_bwd.DENSE_BWD_FUSED = True
         torch.cuda.synchronize()
         outs[fused] = [t.float().clone() for t in (dq, dkv, dtalk, dnk, dnv)]
     rs = [rel(a, b) for a, b in zip(outs[True], outs[False])]
