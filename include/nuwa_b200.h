@@ -474,6 +474,14 @@ int nuwa_attn3dna_bwd_scores(const nuwa_attn_params* p, const void* dO, long lon
  * p->t0 == 1, q|k|v rows in one buffer); NUWA_ERR_INVALID outside it (nothing launched). */
 int nuwa_attn3dna_bwd_scores_umma(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp,
                                   int jp, void* stream);
+/* nuwa_attn3dna_bwd_dq / nuwa_attnx2_bwd_dq on the tcgen05 / TMEM kernel in PV mode: dS (bf16, slot order) takes the place of
+ * the probabilities and V := K, so the PV stage of the forward kernel (A operand from TMEM, K tiles MN-major by TMA) yields
+ * dq = sum_j dS[j] k_j.  Kernel height 3, jp % 8 == 0, otherwise the envelopes of the forward entries; NUWA_ERR_INVALID
+ * outside (nothing launched). */
+int nuwa_attn3dna_bwd_dq_umma(const nuwa_attn_params* p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs,
+                              void* stream);
+int nuwa_attnx2_bwd_dq_umma(const nuwa_attn_params* p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs,
+                            void* stream);
 int nuwa_attn3dna_bwd_dq(const nuwa_attn_params* p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs,
                          void* stream);
 int nuwa_attn3dna_bwd_dkdv(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, const void* dS,

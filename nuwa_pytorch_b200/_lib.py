@@ -179,6 +179,8 @@ SIGNATURES = {
     "nuwa_attn3dna_bwd_scores": [P(AttnParams), c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "nuwa_attn_dense_bwd_fused": [P(AttnParams), c_int, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p, c_float,
                                   c_void_p],
+    "nuwa_attn3dna_bwd_dq_umma": [P(AttnParams), c_void_p, c_int, c_void_p, c_ll, c_int, c_void_p],
+    "nuwa_attnx2_bwd_dq_umma": [P(AttnParams), c_void_p, c_int, c_void_p, c_ll, c_int, c_void_p],
     "nuwa_attn3dna_bwd_scores_umma": [P(AttnParams), c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "nuwa_attn3dna_bwd_dq": [P(AttnParams), c_void_p, c_int, c_void_p, c_ll, c_int, c_void_p],
     "nuwa_attn3dna_bwd_dkdv": [P(AttnParams), c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll,

@@ -233,6 +233,14 @@ int nuwa_attn_dense_bwd_fused(const nuwa_attn_params* p, int nk, const void* dO,
                               void* dS, int jp, float* dtalk, float out_scale, void* stream) {
   return p ? attn_dense_bwd_fused(*p, nk, dO, do_bs, do_rs, Pp, dS, jp, dtalk, out_scale, S(stream)) : NUWA_ERR_INVALID;
 }
+int nuwa_attn3dna_bwd_dq_umma(const nuwa_attn_params* p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs,
+                              void* stream) {
+  return p ? attn_3dna_umma_dq(*p, dS, jp, dq, dq_bs, dq_rs, S(stream)) : NUWA_ERR_INVALID;
+}
+int nuwa_attnx2_bwd_dq_umma(const nuwa_attn_params* p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs,
+                            void* stream) {
+  return p ? attn_cross2dna_umma_dq(*p, dS, jp, dq, dq_bs, dq_rs, S(stream)) : NUWA_ERR_INVALID;
+}
 int nuwa_attn3dna_bwd_scores_umma(const nuwa_attn_params* p, const void* dO, long long do_bs, int do_rs, float* Sc, float* dPp,
                                   int jp, void* stream) {
   return p ? attn_3dna_umma_scores(*p, dO, do_bs, do_rs, Sc, dPp, jp, S(stream)) : NUWA_ERR_INVALID;

@@ -93,6 +93,7 @@ struct UmmaArgs {
   // scores mode (backward): phase 1 only, the band scores go to s_out[b][h][query][s_jp] as fp32 (slot j = 1 + (a kh + b) 3 + c,
   // slot 0 = bos / null key), multiplied by s_scale; masked slots get s_masked
   float* s_out;
+  const bf16* pv_in;   // PV mode: dS [B][H][nq][s_jp] (slot order, slot 0 = bos / null key)
   int s_jp;
   float s_scale, s_masked;
   long long* dbg;  // tools/umma_stamps.py: clock64 stamps of CTA 0 (NULL in normal use)
@@ -226,12 +227,16 @@ __device__ __forceinline__ void load_rows(uint32_t dst, uint64_t* bar, const Map
 // that the Sparse3DNA instantiation carries none of its per-unit work (mask selects, 64-bit mask word) or registers.
 // SC = scores mode: S = Q K^T band extraction only (no softmax / mix / PV); used twice by the backward pass, for the logits
 // (Q = q, K = k) and for dP' = dO V^T (Q = dO from its own buffer, K = v).
-template <int DW, bool X2, bool SC>
+// MODE: 0 = forward, 1 = scores (see SC above), 2 = PV only: the probabilities' place is taken by a bf16 tensor read from HBM
+// (dS of the backward pass, [B][H][nq][jp] in slot order) and V := K, so the output is dq = sum_j dS[j] k_j (slot 0 uses
+// the bos / null key); no Q tiles, no phase 1, no softmax, no mix.
+template <int DW, bool X2, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap qmap8,
                       const __grid_constant__ CUtensorMap qmap4, const __grid_constant__ CUtensorMap qmap2,
                       const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap kmap8,
                       const __grid_constant__ CUtensorMap kmap4, const __grid_constant__ CUtensorMap kmap2, const UmmaArgs p) {
+  constexpr bool SC = MODE == 1, PV = MODE == 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -353,8 +358,8 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
               load_rows(sm_u + OFF_Q + qb * Q_BYTES + 4 * c * BOX, &qfull[qb], qms, p.dh, h * DH, t.f, qy[c], qn[c], t.b);
           ++qu[hp & 1];
         };
-        load_q(0);
-        for (int ph = 0; ph < (SC ? 1 : 2); ++ph) {
+        if constexpr (!PV) load_q(0);
+        for (int ph = (PV ? 1 : 0); ph < (SC ? 1 : 2); ++ph) {
           for (int hp = 0; hp < NH / 2; ++hp) {
             const int chan = (ph ? p.voff : p.koff) + (2 * hp + w) * DH;
             for (int a = 0; a < p.kt; ++a) {
@@ -384,7 +389,7 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
             }
             // the next head pair's Q tile goes out behind this pair's key tiles: its buffer was released a whole
             // head pair ago, and it lands long before the issuer gets there
-            if (ph == 0 && hp + 1 < NH / 2) load_q(hp + 1);
+            if (!PV && ph == 0 && hp + 1 < NH / 2) load_q(hp + 1);
           }
         }
       }
@@ -409,7 +414,7 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
         ++tile_n;
         tc_fence_after();
         // ---------------- phase 1: S = Q K^T ----------------
-        for (int hp = 0; hp < NH / 2; ++hp) {
+        for (int hp = 0; hp < (PV ? 0 : NH / 2); ++hp) {
           const int qb = 2 * (hp & 1) + w;
           const uint64_t qdesc = make_sw128_kmajor_desc(sm_u + OFF_Q + qb * Q_BYTES);
           mbar_wait(&qfull[qb], qu[hp & 1] & 1);
@@ -437,7 +442,7 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
         }
         if constexpr (SC) continue;
         // ---------------- talking heads: D[q][2g + s'] = sum_h W[g][h] P[h][2u + s'] for every slot pair u ----------------
-        if (w == 0) {
+        if (!PV && w == 0) {
           for (int batch = 0; batch < 2; ++batch) {
             mbar_wait(mixgo, mg & 1);
             ++mg;
@@ -586,7 +591,7 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
         }
       }
       // the bos query (sequence row 0) attends only to itself (nuwa_pytorch.py:608): its output is its value row
-      if (!X2 && !SC && t.f == 0 && tile_row(p, t, 0) == 0 && wg == 1 && qrow < 64) {
+      if (!X2 && MODE == 0 && t.f == 0 && tile_row(p, t, 0) == 0 && wg == 1 && qrow < 64) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.v0 + (long long)t.b * p.v_bs) + qrow);
         reinterpret_cast<uint4*>(p.o + (long long)t.b * p.o_bs)[qrow] = v;
       }
@@ -596,8 +601,33 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
       long long* dst_dbg = p.dbg + (warp == 6 ? 32 : 0);
       if (dbg) dst_dbg[0] = clock64();
 
+      if constexpr (PV) {
+        // PV mode: this thread's row of dS for its warpgroup's heads -> slot-0 weight (smem, fp32) + bf16 pairs in TMEM at the
+        // columns the mix would have left P' in (column 8u + h = slots 1 + 2u, 2 + 2u)
+        for (int hp = 0; hp < NH / 2; ++hp) {
+          const int h = 2 * hp + wg;
+          uint32_t w[NU + 1];
+#pragma unroll
+          for (int i = 0; i < NU + 1; ++i) w[i] = 0u;
+          if (qok) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.pv_in + (((long long)t.b * NH + h) * p.nv + vpos) * p.s_jp);
+#pragma unroll
+            for (int i = 0; i < (NU + 1) / 4; ++i)
+              if (8 * i < p.s_jp) {
+                const uint4 v4 = __ldg(src + i);
+                w[4 * i] = v4.x; w[4 * i + 1] = v4.y; w[4 * i + 2] = v4.z; w[4 * i + 3] = v4.w;
+              }
+          }
+          pbos_s[h * 128 + qrow] = __uint_as_float(w[0] << 16);
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            uint32_t pk[1] = {__funnelshift_r(w[u], w[u + 1], 16)};   // (slot 1 + 2u, slot 2 + 2u)
+            tmem_st_x1(tlane + T_P + 8 * u + h, pk);
+          }
+        }
+      }
       // ================= phase 1: band extraction + softmax =================
-      for (int hp = 0; hp < NH / 2; ++hp) {
+      for (int hp = 0; hp < (PV ? 0 : NH / 2); ++hp) {
         const int h = 2 * hp + wg;
         float sv[MAXJ + 1];   // scores, then probabilities, of this thread's query for head h: bos, then 9 per frame offset
         {  // bos key (slot 0): 64-term dot product of this thread's Q row (SWIZZLE_128B tile, as the UMMA reads it) with
@@ -718,10 +748,10 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(mixgo);
+      if (!PV && lane == 0) mbar_arrive(mixgo);
       if (dbg) dst_dbg[5] = clock64();
 #pragma unroll 1
-      for (int batch = 0; batch < 2; ++batch) {
+      for (int batch = 0; batch < (PV ? 0 : 2); ++batch) {
         mbar_wait(mixfull, mf & 1);
         ++mf;
         tc_fence_after();
@@ -810,8 +840,12 @@ attn_3dna_umma_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_con
         if (gp + 1 < NH / 2) build_unit(g + 2, a_first);
         // ---- head epilogue: O (fp32, TMEM) + mixed bos probability x bos value -> bf16 -> global ----
         float pbos = 0.f;
+        if constexpr (PV) {
+          pbos = pbos_s[g * 128 + qrow];
+        } else {
 #pragma unroll
-        for (int hh = 0; hh < NH; ++hh) pbos = fmaf(Wsm[g * NH + hh], pbos_s[hh * 128 + qrow], pbos);
+          for (int hh = 0; hh < NH; ++hh) pbos = fmaf(Wsm[g * NH + hh], pbos_s[hh * 128 + qrow], pbos);
+        }
         mbar_wait(&ofull[wg], ou & 1);
         tc_fence_after();
         uint32_t ov[64];
@@ -904,23 +938,13 @@ int launch_umma(const HostMaps& qm, const HostMaps& km, UmmaArgs& a, cudaStream_
     return NUWA_OK;
   };
   int lrc;
-  if (a.s_out != nullptr && a.abs_frames) {
-    if (a.dw == 1) lrc = launch(attn_3dna_umma_kernel<1, true, true>);
-    else if (a.dw == 2) lrc = launch(attn_3dna_umma_kernel<2, true, true>);
-    else lrc = launch(attn_3dna_umma_kernel<4, true, true>);
-  } else if (a.s_out != nullptr) {
-    if (a.dw == 1) lrc = launch(attn_3dna_umma_kernel<1, false, true>);
-    else if (a.dw == 2) lrc = launch(attn_3dna_umma_kernel<2, false, true>);
-    else lrc = launch(attn_3dna_umma_kernel<4, false, true>);
-  } else if (a.abs_frames) {
-    if (a.dw == 1) lrc = launch(attn_3dna_umma_kernel<1, true, false>);
-    else if (a.dw == 2) lrc = launch(attn_3dna_umma_kernel<2, true, false>);
-    else lrc = launch(attn_3dna_umma_kernel<4, true, false>);
-  } else {
-    if (a.dw == 1) lrc = launch(attn_3dna_umma_kernel<1, false, false>);
-    else if (a.dw == 2) lrc = launch(attn_3dna_umma_kernel<2, false, false>);
-    else lrc = launch(attn_3dna_umma_kernel<4, false, false>);
-  }
+  const int mode = a.s_out != nullptr ? 1 : (a.pv_in != nullptr ? 2 : 0);
+#define NUWA_UMMA_DW(X2V, MODEV)                                                         \
+  (a.dw == 1 ? launch(attn_3dna_umma_kernel<1, X2V, MODEV>)                             \
+             : (a.dw == 2 ? launch(attn_3dna_umma_kernel<2, X2V, MODEV>) : launch(attn_3dna_umma_kernel<4, X2V, MODEV>)))
+  if (a.abs_frames) lrc = mode == 1 ? NUWA_UMMA_DW(true, 1) : (mode == 2 ? NUWA_UMMA_DW(true, 2) : NUWA_UMMA_DW(true, 0));
+  else lrc = mode == 1 ? NUWA_UMMA_DW(false, 1) : (mode == 2 ? NUWA_UMMA_DW(false, 2) : NUWA_UMMA_DW(false, 0));
+#undef NUWA_UMMA_DW
   if (lrc != NUWA_OK) return lrc;
   NUWA_CHECK_LAUNCH();
   return NUWA_OK;
@@ -1018,6 +1042,41 @@ int attn_3dna_umma_scores(const AttnParams& p, const void* dO, long long do_bs, 
   return launch_umma(dm, km, a, stream);
 }
 
+// dq of the Sparse3DNA backward on the same kernel in PV mode: dq[q] = sum_j dS[q][j] k_j over [bos | window] with dS (bf16,
+// [B][H][nq][jp], already multiplied by dh^-0.5) in the place of the probabilities and V := K.  `p` in the backward convention
+// (see attn_3dna_umma_scores); dq rows of the non-bos queries (dq_bs / dq_rs).  Kernel height 3 only (internal slot order ==
+// external), jp % 8 == 0; NUWA_ERR_INVALID otherwise (the gather kernel nuwa_attn3dna_bwd_dq takes those).
+int attn_3dna_umma_dq(const AttnParams& p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs, cudaStream_t stream) {
+  if (p.fmap != GW || p.t0 != 1 || p.t0_ptr != nullptr || dS == nullptr || dq == nullptr) return NUWA_ERR_INVALID;
+  if (p.H != NH || p.dh != DH || p.nq != p.nv || p.nv <= 0 || p.B <= 0) return NUWA_ERR_INVALID;
+  if (p.kw != KW || p.kh != MAXKH || p.kt < 1 || p.kt > MAXKT || !(p.kt & 1)) return NUWA_ERR_INVALID;
+  if (p.dt <= 0 || p.dh_ <= 0 || !(p.dw == 1 || p.dw == 2 || p.dw == 4)) return NUWA_ERR_INVALID;
+  if (jp < 1 + p.kt * MAXKH * KW || (jp % 8) || p.max_frames <= 0 || p.nv > p.max_frames * GW * GW) return NUWA_ERR_INVALID;
+  if (p.head_scale != nullptr || p.bias != nullptr || p.key_mask != nullptr || p.null_k != nullptr) return NUWA_ERR_INVALID;
+  const bf16* q1 = reinterpret_cast<const bf16*>(p.q);
+  const bf16* k = reinterpret_cast<const bf16*>(p.k);
+  const bf16* row0 = q1 - p.q_rs;
+  const long long koff = k - row0;
+  if (p.k_rs != p.q_rs || p.k_bs != p.q_bs || koff < 0 || koff + INNER > p.q_rs) return NUWA_ERR_INVALID;
+  if ((p.q_rs % 8) || (p.q_bs % 8) || (koff % 8) || (dq_rs % 8) || (dq_bs % 8)) return NUWA_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(row0) & 15) || (reinterpret_cast<uintptr_t>(dS) & 15) || (reinterpret_cast<uintptr_t>(dq) & 15))
+    return NUWA_ERR_INVALID;
+  HostMaps km;
+  const int rc = build_maps(km, row0, p.q_rs, p.q_bs, p.nv + 1, 1, p.dh_, p.B);
+  if (rc != NUWA_OK) return rc;
+  UmmaArgs a = {};
+  a.B = p.B; a.nv = p.nv;
+  a.nf = (p.nv + GW * GW - 1) / (GW * GW);
+  a.maxf = p.max_frames;
+  a.kt = p.kt; a.kh = p.kh; a.dt = p.dt; a.dh = p.dh_; a.dw = p.dw; a.causal = p.causal;
+  a.koff = a.voff = (int)koff;          // V := K
+  a.q_tok0 = 0; a.kv_tok0 = 1;
+  a.k0 = k; a.v0 = k; a.k_bs = p.k_bs; a.v_bs = p.k_bs;
+  a.o = reinterpret_cast<bf16*>(dq); a.o_bs = dq_bs; a.o_rs = dq_rs;
+  a.pv_in = reinterpret_cast<const bf16*>(dS); a.s_jp = jp;
+  return launch_umma(km, km, a, stream);
+}
+
 // SparseCross2DNA (nuwa_pytorch.py:851-895) on the same kernel: the nq queries at video positions 0 .. nq-1 (p.q / p.o
 // point at the first of them, i.e. past the bos row; p.t0 == 1) each see slot 0 = the learned null key / value and the
 // centred ck x ck window, dilation cdil, at their own grid position in every context frame, under the context mask.
@@ -1067,6 +1126,23 @@ int attn_cross2dna_umma(const AttnParams& p, cudaStream_t stream) {
   if (rc != NUWA_OK) return rc;
   a.o = reinterpret_cast<bf16*>(p.o); a.o_bs = p.o_bs; a.o_rs = p.o_rs;
   return launch_umma(qm, km, a, stream);
+}
+
+// dq of the SparseCross2DNA backward (non-bos queries) in PV mode, as attn_3dna_umma_dq: slot 0 multiplies the learned null key
+int attn_cross2dna_umma_dq(const AttnParams& p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs, cudaStream_t stream) {
+  if (dS == nullptr || dq == nullptr || jp < p.jmax || (jp % 8) || (dq_rs % 8) || (dq_bs % 8)) return NUWA_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(dS) & 15) || (reinterpret_cast<uintptr_t>(dq) & 15)) return NUWA_ERR_INVALID;
+  HostMaps qm, km;
+  UmmaArgs a;
+  const int rc = cross2dna_setup(p, qm, km, a);
+  if (rc != NUWA_OK) return rc;
+  a.voff = a.koff;                       // V := K
+  a.v0 = a.k0;
+  a.null_v = p.null_k;                   // slot 0: dS[0] * null key
+  a.key_mask = nullptr;                  // masked slots carry dS == 0
+  a.o = reinterpret_cast<bf16*>(dq); a.o_bs = dq_bs; a.o_rs = dq_rs;
+  a.pv_in = reinterpret_cast<const bf16*>(dS); a.s_jp = jp;
+  return launch_umma(km, km, a, stream);
 }
 
 // Backward scores of SparseCross2DNA (non-bos queries) in scores mode, as attn_3dna_umma_scores: S = qscale q . k_j over

@@ -70,6 +70,8 @@ int attn_3dna_umma(const AttnParams& p, cudaStream_t stream);           // atten
 int attn_cross2dna_umma(const AttnParams& p, cudaStream_t stream);      // attention_3dna_umma.cu
 int attn_dense_bwd_fused(const AttnParams& p, int nk, const void* dO, long long do_bs, int do_rs, void* Pp, void* dS, int jp,
                          float* dtalk, float out_scale, cudaStream_t stream);   // attention_dense_bwd.cu
+int attn_3dna_umma_dq(const AttnParams& p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs, cudaStream_t stream);
+int attn_cross2dna_umma_dq(const AttnParams& p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs, cudaStream_t stream);
 int attn_cross2dna_umma_scores(const AttnParams& p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp, int jp,
                                cudaStream_t stream);                    // attention_3dna_umma.cu
 int attn_3dna_umma_scores(const AttnParams& p, const void* dO, long long do_bs, int do_rs, float* S, float* dPp, int jp,

@@ -214,8 +214,15 @@ def attn_sparse3dna_bwd(qkv, do, *, B, n, H, dh, talk, dtalk, fmap, max_frames, 
                   "nuwa_attn3dna_bwd_scores")
         # dS leaves the row kernel multiplied by the logit scale dh^-0.5, so dq = sum dS k and dk = sum dS q need no more
         Pp, dS = _rows(S, dPp, talk, dtalk, B, H, nq, J, jp, dh ** -0.5)
-        check(lib().nuwa_attn3dna_bwd_dq(p, ptr(dS), jp, dqkv.data_ptr() + 3 * inner * 2, n * 3 * inner, 3 * inner,
-                                         stream()), "nuwa_attn3dna_bwd_dq")
+        rc = _lib.NUWA_ERR_INVALID
+        if SCORES_VARIANT == 'umma' or (SCORES_VARIANT == 'auto' and B * ((nq + 255) // 256) * 2 >= 64):
+            rc = lib().nuwa_attn3dna_bwd_dq_umma(p, ptr(dS), jp, dqkv.data_ptr() + 3 * inner * 2, n * 3 * inner, 3 * inner,
+                                                 stream())
+            if rc != _lib.NUWA_ERR_INVALID:
+                check(rc, "nuwa_attn3dna_bwd_dq_umma")
+        if rc == _lib.NUWA_ERR_INVALID:
+            check(lib().nuwa_attn3dna_bwd_dq(p, ptr(dS), jp, dqkv.data_ptr() + 3 * inner * 2, n * 3 * inner, 3 * inner,
+                                             stream()), "nuwa_attn3dna_bwd_dq")
         check(lib().nuwa_attn3dna_bwd_dkdv(p, do_q, n * inner, inner, ptr(dS), ptr(Pp), jp, dqkv.data_ptr() + inner * 2,
                                            dqkv.data_ptr() + 2 * inner * 2, n * 3 * inner, 3 * inner, stream()),
               "nuwa_attn3dna_bwd_dkdv")
@@ -342,8 +349,14 @@ def attn_cross2dna_bwd(q, kv, do, *, B, n, nk, H, dh, talk, dtalk, null_k, null_
     if rc == _lib.NUWA_ERR_INVALID:
         check(lib().nuwa_attnx2_bwd_scores(p, do_q, n * inner, inner, ptr(S), ptr(dPp), jp, stream()), "nuwa_attnx2_bwd_scores")
     Pp, dS = _rows(S, dPp, talk, dtalk, B, H, nq, J, jp, dh ** -0.5)  # masks already folded into S by the gather
-    check(lib().nuwa_attnx2_bwd_dq(p, ptr(dS), jp, dq.data_ptr() + inner * 2, n * inner, inner, stream()),
-          "nuwa_attnx2_bwd_dq")
+    rc = _lib.NUWA_ERR_INVALID
+    if SCORES_VARIANT == 'umma' or (SCORES_VARIANT == 'auto' and B * ((nq + 255) // 256) * 2 >= 64):
+        rc = lib().nuwa_attnx2_bwd_dq_umma(p, ptr(dS), jp, dq.data_ptr() + inner * 2, n * inner, inner, stream())
+        if rc != _lib.NUWA_ERR_INVALID:
+            check(rc, "nuwa_attnx2_bwd_dq_umma")
+    if rc == _lib.NUWA_ERR_INVALID:
+        check(lib().nuwa_attnx2_bwd_dq(p, ptr(dS), jp, dq.data_ptr() + inner * 2, n * inner, inner, stream()),
+              "nuwa_attnx2_bwd_dq")
     check(lib().nuwa_attnx2_bwd_dkdv(p, nk, do_q, n * inner, inner, ptr(dS), ptr(Pp), jp, ptr(base),
                                      base.data_ptr() + inner * 4, nk * 2 * inner, 2 * inner, dkv.data_ptr(),
                                      dkv.data_ptr() + inner * 2, nk * 2 * inner, 2 * inner, stream()),

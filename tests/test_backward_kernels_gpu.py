@@ -290,7 +290,8 @@ def test_dense_bwd_fused_probability_stage_matches_materialised_path(cuda_device
 @pytest.mark.parametrize("n,frames,cdil,B,masked", [(2561, 3, 1, 2, True), (2561, 3, 2, 2, True), (1281, 3, 4, 2, False),
                                                     (1000, 1, 2, 3, True), (258, 2, 1, 2, True)])
 def test_cross2dna_bwd_scores_tcgen05_matches_gather(cuda_device, n, frames, cdil, B, masked):
-    """Backward of the SparseCross2DNA core with S / dP' from the tcgen05 kernel in scores mode vs the gather kernel:
+    """Backward of the SparseCross2DNA core with S / dP' from the tcgen05 kernel in scores mode and dq in PV mode vs the
+    gather kernels:
     dq, dk|dv, talking-heads and null key / value gradients; context mask incl. a fully masked frame."""
     from nuwa_pytorch_b200 import ops_bwd
     H, dh, fmap, ck = 8, 64, 16, 3
@@ -333,8 +334,9 @@ def test_cross2dna_bwd_scores_tcgen05_matches_gather(cuda_device, n, frames, cdi
                                                   ((3, 3, 3), (2, 4, 2), 530, 2, 10), ((3, 1, 3), (1, 1, 4), 256, 2, 10),
                                                   ((5, 3, 3), (2, 2, 2), 767, 2, 3), ((5, 3, 3), (1, 1, 1), 17, 1, 10)])
 def test_sparse3dna_bwd_scores_tcgen05_matches_gather(cuda_device, kernel, dil, nv, B, maxf, causal):
-    """Backward of the Sparse3DNA core with the logits S and dP' = dO V^T produced by the tcgen05 kernel in scores mode
-    vs by the gather kernel (same bf16 operands): dq|dk|dv (bf16) and the talking-heads gradient; causal and centred
+    """Backward of the Sparse3DNA core with the logits S and dP' = dO V^T produced by the tcgen05 kernel in scores mode and
+    dq by the same kernel in PV mode (dS in the place of the probabilities, V := K; kernel height 3) vs the gather kernels
+    (same bf16 operands): dq|dk|dv (bf16) and the talking-heads gradient; causal and centred
     windows (incl. visible zero keys past the sequence), kernel heights 1 and 3, ragged last frame."""
     from nuwa_pytorch_b200 import ops_bwd
     H, dh, fmap = 8, 64, 16
