@@ -22,7 +22,7 @@ __device__ __forceinline__ void tma5(uint32_t dst, const CUtensorMap* m, uint64_
 
 template <int NST>
 __global__ void __launch_bounds__(64) bw_kernel(const __grid_constant__ CUtensorMap m8, const __grid_constant__ CUtensorMap m2,
-                                                 int tiles_per_cta, int nrow_blocks, int B, long long* cycles) {
+                                                 int tiles_per_cta, int nrow_blocks, int B, long long* cycles, int head_major) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -42,8 +42,15 @@ __global__ void __launch_bounds__(64) bw_kernel(const __grid_constant__ CUtensor
       // pseudo-random tile: (sample, head, k|v, row block)
       const unsigned u = (unsigned)(blockIdx.x * 7919 + it * 104729);
       const int b = u % B, h = (u / 7) % 8, kv = 1 + (u / 3) % 2, rb = (u / 11) % nrow_blocks;
-      tma5(smem_u32(sm) + st * 20480, &m8, &full[st], kv * 512 + h * 64, 0, 0, rb, b);
-      tma5(smem_u32(sm) + st * 20480 + 16384, &m2, &full[st], kv * 512 + h * 64, 0, 0, rb + 8, b);
+      const int c0 = head_major ? 0 : kv * 512 + h * 64, c4 = head_major ? b * 24 + kv * 8 + h : b;
+      if (head_major == 2) {
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(smem_u32(sm) + st * 20480), "l"(reinterpret_cast<uint64_t>(&m8)), "r"(smem_u32(&full[st])), "r"(0),
+                       "r"((c4 * 160 + rb) * 16) : "memory");
+        continue;
+      }
+      tma5(smem_u32(sm) + st * 20480, &m8, &full[st], c0, 0, 0, rb, c4);
+      tma5(smem_u32(sm) + st * 20480 + 16384, &m2, &full[st], c0, 0, 0, rb + 8, c4);
     }
   } else if (threadIdx.x == 32) {
     for (int it = 0; it < tiles_per_cta; ++it) {
@@ -55,6 +62,8 @@ __global__ void __launch_bounds__(64) bw_kernel(const __grid_constant__ CUtensor
   __syncthreads();
   if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
 }
+
+static int g_head_major = 0;
 
 int main() {
   const int B = 8, NTOK = 2560, ROW = 1536;
@@ -85,7 +94,7 @@ int main() {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     for (int rep = 0; rep < 3; ++rep) {
       cudaEventRecord(e0);
-      kern<<<148, 64, smem>>>(m8, m2, tiles, nrb, B, cyc);
+      kern<<<148, 64, smem>>>(m8, m2, tiles, nrb, B, cyc, g_head_major);
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);
     }
@@ -104,6 +113,34 @@ int main() {
   run(bw_kernel<4>, 4, "ring of 4 stages");
   run(bw_kernel<6>, 6, "ring of 6 stages");
   run(bw_kernel<10>, 10, "ring of 10 stages");
+  // ---- the same tiles out of a HEAD-MAJOR buffer [B][24 (q|k|v x head)][token][64]: a grid row of 16 tokens is 2 KB
+  //      contiguous (token pitch 128 B instead of 3072 B); coordinates: c0 = channel (0), c4 = b * 24 + kv * 8 + h ----
+  {
+    const cuuint64_t dimsH[5] = {64, 16, 1, (cuuint64_t)(NTOK / 16), (cuuint64_t)B * 24};
+    const cuuint64_t stridesH[4] = {128, 2048, 2048, (cuuint64_t)NTOK * 128};
+    r1 = enc(&m8, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, buf, dimsH, stridesH, b8, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    r2 = enc(&m2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, buf, dimsH, stridesH, b2, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) { printf("encode (head-major) failed %d %d\n", (int)r1, (int)r2); return 1; }
+    g_head_major = 1;
+    run(bw_kernel<2>, 2, "head-major, ring of 2 stages");
+    run(bw_kernel<4>, 4, "head-major, ring of 4 stages");
+    run(bw_kernel<10>, 10, "head-major, ring of 10 stages");
+  }
+  // ---- the same bytes as ONE 2-D box {64 channels, 160 token rows} of the head-major buffer (dilation-1 tiles are
+  //      contiguous there): is the 5-D box walk the limiter? ----
+  {
+    const cuuint64_t dims2[2] = {64, (cuuint64_t)NTOK * 24 * B};
+    const cuuint64_t strides2[1] = {128};
+    const cuuint32_t bx[2] = {64, 160}, es2[2] = {1, 1};
+    r1 = enc(&m8, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, buf, dims2, strides2, bx, es2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS) { printf("encode (2-D) failed %d\n", (int)r1); return 1; }
+    g_head_major = 2;
+    run(bw_kernel<2>, 2, "head-major 2-D box 64 x 160, ring of 2 stages");
+    run(bw_kernel<4>, 4, "head-major 2-D box 64 x 160, ring of 4 stages");
+  }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
   return 0;
