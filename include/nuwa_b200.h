@@ -448,6 +448,14 @@ typedef struct {
   int mask_bs, has_null;
 } nuwa_attn_rows_params;
 int nuwa_attn_bwd_rows(const nuwa_attn_rows_params* p, void* stream);
+/* Dense attention with ONE query per sample and no talking heads: the bos query of SparseCross2DNA.forward over
+ * [null key | every context token] (nuwa_pytorch.py:828-844) in full passes, forward and backward (under autograd).  One CTA
+ * per (sample, head).  p->q / p->o: the single row of every sample (q_bs / o_bs), p->nq == 1, dh == 64, p->talk == NULL.
+ * Backward: dO / dq one row per sample; dk, dv fp32 [B][nk] rows, WRITTEN; dnull_k / dnull_v fp32 [H*64], ADDED to.
+ * NUWA_ERR_INVALID outside the envelope (nothing launched; nuwa_attn_dense and the batched-GEMM backward cover the rest). */
+int nuwa_attn_dense_q1(const nuwa_attn_params* p, int nk, void* stream);
+int nuwa_attn_dense_q1_bwd(const nuwa_attn_params* p, int nk, const void* dO, long long do_bs, void* dq, long long dq_bs,
+                           float* dk, float* dv, long long dkv_bs, int dkv_rs, float* dnull_k, float* dnull_v, void* stream);
 /* Dense attention backward (Attention core, nuwa_pytorch.py:339-378, under autograd), probability stage fused: per tile of
  * 16 queries x 8 heads the logits S = Q K^T and dP' = dO V^T are recomputed on the tensor cores from TMA-staged K / V
  * chunks and stay in shared memory; the softmax / talking-heads backward runs from there and writes P' (operand of

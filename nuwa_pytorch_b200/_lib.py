@@ -177,6 +177,9 @@ SIGNATURES = {
                            c_int, c_int, c_int, c_int, c_void_p],
     "nuwa_mask_scores": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "nuwa_attn3dna_bwd_scores": [P(AttnParams), c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    "nuwa_attn_dense_q1": [P(AttnParams), c_int, c_void_p],
+    "nuwa_attn_dense_q1_bwd": [P(AttnParams), c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_void_p,
+                               c_void_p, c_void_p],
     "nuwa_attn_dense_bwd_fused": [P(AttnParams), c_int, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p, c_float,
                                   c_void_p],
     "nuwa_attn3dna_bwd_dq_umma": [P(AttnParams), c_void_p, c_int, c_void_p, c_ll, c_int, c_void_p],

@@ -229,6 +229,13 @@ int nuwa_mask_scores(float* Sc, const unsigned char* mask, int mask_bs, int B, i
                      void* stream) {
   return mask_scores(Sc, mask, mask_bs, B, H, nq, jp, nk, has_null, S(stream));
 }
+int nuwa_attn_dense_q1(const nuwa_attn_params* p, int nk, void* stream) {
+  return p ? attn_dense_q1(*p, nk, S(stream)) : NUWA_ERR_INVALID;
+}
+int nuwa_attn_dense_q1_bwd(const nuwa_attn_params* p, int nk, const void* dO, long long do_bs, void* dq, long long dq_bs,
+                           float* dk, float* dv, long long dkv_bs, int dkv_rs, float* dnull_k, float* dnull_v, void* stream) {
+  return p ? attn_dense_q1_bwd(*p, nk, dO, do_bs, dq, dq_bs, dk, dv, dkv_bs, dkv_rs, dnull_k, dnull_v, S(stream)) : NUWA_ERR_INVALID;
+}
 int nuwa_attn_dense_bwd_fused(const nuwa_attn_params* p, int nk, const void* dO, long long do_bs, int do_rs, void* Pp,
                               void* dS, int jp, float* dtalk, float out_scale, void* stream) {
   return p ? attn_dense_bwd_fused(*p, nk, dO, do_bs, do_rs, Pp, dS, jp, dtalk, out_scale, S(stream)) : NUWA_ERR_INVALID;

@@ -68,6 +68,9 @@ int attn_dense(const AttnParams& p, cudaStream_t s);
 int attn_3dna_halo(const AttnParams& p, cudaStream_t stream);           // attention_3dna_halo.cu
 int attn_3dna_umma(const AttnParams& p, cudaStream_t stream);           // attention_3dna_umma.cu
 int attn_cross2dna_umma(const AttnParams& p, cudaStream_t stream);      // attention_3dna_umma.cu
+int attn_dense_q1(const AttnParams& p, int nk, cudaStream_t stream);   // attention_q1.cu
+int attn_dense_q1_bwd(const AttnParams& p, int nk, const void* dO, long long do_bs, void* dq, long long dq_bs, float* dk, float* dv,
+                      long long dkv_bs, int dkv_rs, float* dnull_k, float* dnull_v, cudaStream_t stream);
 int attn_dense_bwd_fused(const AttnParams& p, int nk, const void* dO, long long do_bs, int do_rs, void* Pp, void* dS, int jp,
                          float* dtalk, float out_scale, cudaStream_t stream);   // attention_dense_bwd.cu
 int attn_3dna_umma_dq(const AttnParams& p, const void* dS, int jp, void* dq, long long dq_bs, int dq_rs, cudaStream_t stream);

@@ -239,8 +239,16 @@ def attn_dense(q_ptr, k_ptr, v_ptr, o, *, B, nq, nk, H, dh, q_bs, q_rs, k_bs, k_
     if bias is not None:
         p.bias, p.bias_nq, p.bias_nk = ptr(bias), bias.shape[1], bias.shape[2]
     p.jmax = nk + (1 if null_k is not None else 0)
+    if variant == 'auto' and nq == 1 and talk is None and dh == 64 and head_scale is None and bias is None and t0 == 0:
+        # one query per sample without talking heads (the bos query of SparseCross2DNA): one CTA per (sample, head)
+        rc = lib().nuwa_attn_dense_q1(p, nk, stream())
+        if rc == 0:
+            return
+        if rc != _lib.NUWA_ERR_INVALID:
+            check(rc, "nuwa_attn_dense_q1")
     # variant: 'auto' = probability-resident kernel (attention_dense_pres.cu) inside its envelope (8 x 64 heads, <= 256
     # keys, >= 16 queries), else the library's own choice (attention_x64.cu / attention_mma.cu / generic); 'pres' pins it.
+    # 'generic' = none of the specialised kernels (A/B tests)
     if variant == 'pres' or (variant == 'auto' and use_mma and nq >= 16):
         rc = lib().nuwa_attn_dense_pres(p, stream())
         if rc == 0:

@@ -235,6 +235,15 @@ def attn_sparse3dna_bwd(qkv, do, *, B, n, H, dh, talk, dtalk, fmap, max_frames, 
     return dqkv
 
 
+# single-query dense attention (bos query of SparseCross2DNA): dedicated kernels (csrc/attention_q1.cu); False = the generic
+# chain, kept for the A/B test
+Q1_KERNELS = True
+
+
+def key_mask_ok(key_mask):
+    return key_mask is None or (key_mask.dtype == torch.uint8 and key_mask.stride(1) == 1)
+
+
 # dense attention backward: True = fused probability stage (csrc/attention_dense_bwd.cu: S and dP' recomputed per 16-query
 # tile on the tensor cores, head mixes / dW on mma.sync from shared memory, nothing but P' and dS written to HBM) when the
 # call is inside its envelope; False = the materialised-logits path (two batched GEMMs + the row kernel), kept for the
@@ -254,6 +263,19 @@ def attn_dense_bwd(q_ptr, k_ptr, v_ptr, do, *, B, nq, nk, H, dh, q_bs, q_rs, kv_
     inner = H * dh
     dev = do.device
     has_null = int(null_k is not None)
+    if Q1_KERNELS and nq == 1 and talk is None and dh == 64 and out_f32 and key_mask_ok(key_mask):
+        # one query per sample, no talking heads (the bos query of SparseCross2DNA): a single launch instead of the K/V
+        # repack + five batched GEMMs + wide row kernel + split chain
+        p = ops._attn_base(q_ptr, k_ptr, v_ptr, None, B, 1, 0, H, dh, q_bs, kv_bs, kv_bs, 0, q_rs, kv_rs, kv_rs, inner, None)
+        p.null_k, p.null_v = ptr(null_k), ptr(null_v)
+        if key_mask is not None:
+            p.key_mask, p.mask_bs = ptr(key_mask), key_mask.stride(0)
+        dq_ptr = dq_out[1] if isinstance(dq_out, tuple) else ptr(dq_out)
+        rc = lib().nuwa_attn_dense_q1_bwd(p, nk, ptr(do), do.stride(0), dq_ptr, dq_bs, dk_ptr, dv_ptr, dkv_bs, dkv_rs,
+                                          ptr(dnull_k), ptr(dnull_v), stream())
+        if rc != _lib.NUWA_ERR_INVALID:
+            check(rc, "nuwa_attn_dense_q1_bwd")
+            return
     J = nk + has_null
     jp = _round_up(J, 8)
     scale = dh ** -0.5

@@ -287,6 +287,61 @@ def test_dense_bwd_fused_probability_stage_matches_materialised_path(cuda_device
         assert rs[3] < 6e-3 and rs[4] < 6e-3
 
 
+@pytest.mark.parametrize("B,nk,H,null,masked", [(4, 768, 8, True, True), (2, 256, 8, True, False), (3, 100, 4, False, True)])
+def test_single_query_dense_attention_kernels_match_the_generic_chain(cuda_device, B, nk, H, null, masked):
+    """attention_q1.cu (one CTA per (sample, head) for the single bos query of SparseCross2DNA, forward and backward) vs the
+    generic paths (decode kernel; K/V repack + batched GEMMs + row kernel + split) on identical bf16 operands."""
+    from nuwa_pytorch_b200 import ops, ops_bwd
+    dh = 64
+    inner = H * dh
+    g = gen(nk + H)
+    dv_ = lambda t: None if t is None else t.to(cuda_device).contiguous()
+    q = dv_(torch.randn(B, 5, inner, generator=g).bfloat16())          # the query is row 0 of a longer sequence
+    kv = dv_(torch.randn(B, nk, 2 * inner, generator=g).bfloat16())
+    do = dv_((torch.randn(B, 1, inner, generator=g) / 8).bfloat16())
+    null_k = dv_(torch.randn(inner, generator=g)) if null else None
+    null_v = dv_(torch.randn(inner, generator=g)) if null else None
+    mask = None
+    if masked:
+        mask = torch.rand(B, nk, generator=g) > 0.4
+        mask[:, 0] = True
+        if null:
+            mask[0] = False
+        mask = dv_(mask.to(torch.uint8))
+    common = dict(B=B, nq=1, nk=nk, H=H, dh=dh, q_bs=5 * inner, q_rs=inner, k_bs=nk * 2 * inner, k_rs=2 * inner,
+                  v_bs=nk * 2 * inner, v_rs=2 * inner, o_bs=inner, o_rs=inner, talk=None, null_k=null_k, null_v=null_v, key_mask=mask)
+    o_new = torch.full((B, 1, inner), float('nan'), dtype=torch.bfloat16, device=cuda_device)
+    o_ref = torch.zeros_like(o_new)
+    ops.attn_dense(q.data_ptr(), kv.data_ptr(), kv.data_ptr() + inner * 2, o_new, **common)
+    ops.attn_dense(q.data_ptr(), kv.data_ptr(), kv.data_ptr() + inner * 2, o_ref, variant='generic', **common)
+    torch.cuda.synchronize()
+    rf = rel(o_new.float(), o_ref.float())
+    outs = {}
+    for q1 in (False, True):
+        ops_bwd.Q1_KERNELS = q1
+        try:
+            dnk, dnv = torch.zeros(inner, device=cuda_device), torch.zeros(inner, device=cuda_device)
+            dq = torch.zeros(B, 5, inner, dtype=torch.bfloat16, device=cuda_device)
+            base = torch.full((B, nk, 2 * inner), float('nan'), dtype=torch.float32, device=cuda_device)
+            ops_bwd.attn_dense_bwd(q.data_ptr(), kv.data_ptr(), kv.data_ptr() + inner * 2, do, B=B, nq=1, nk=nk, H=H, dh=dh,
+                                   q_bs=5 * inner, q_rs=inner, kv_bs=nk * 2 * inner, kv_rs=2 * inner, talk=None, dtalk=None,
+                                   null_k=null_k, null_v=null_v, dnull_k=dnk if null else None, dnull_v=dnv if null else None,
+                                   key_mask=mask, dq_out=(dq, dq.data_ptr()), dq_bs=5 * inner, dq_rs=inner,
+                                   dk_ptr=base.data_ptr(), dv_ptr=base.data_ptr() + inner * 4, dkv_bs=nk * 2 * inner,
+                                   dkv_rs=2 * inner, out_f32=True)
+        finally:
+            ops_bwd.Q1_KERNELS = True
+        torch.cuda.synchronize()
+        outs[q1] = [t.float().clone() for t in (dq[:, 0], base, dnk, dnv)]
+    rs = [rel(a, b) for a, b in zip(outs[True], outs[False])]
+    print(f"  single-query dense B={B} nk={nk} H={H} null={null} masked={masked}: fwd {rf:.2e}  dq {rs[0]:.2e} dk|dv {rs[1]:.2e} "
+          f"dnull {rs[2]:.2e}/{rs[3]:.2e}")
+    assert torch.isfinite(o_new.float()).all() and all(torch.isfinite(t).all() for t in outs[True])
+    assert rf < 4e-3 and rs[0] < 6e-3 and rs[1] < 6e-3     # bf16 outputs; the generic chain rounds P' / dS / null key to bf16
+    if null:
+        assert rs[2] < 6e-3 and rs[3] < 6e-3
+
+
 @pytest.mark.parametrize("n,frames,cdil,B,masked", [(2561, 3, 1, 2, True), (2561, 3, 2, 2, True), (1281, 3, 4, 2, False),
                                                     (1000, 1, 2, 3, True), (258, 2, 1, 2, True)])
 def test_cross2dna_bwd_scores_tcgen05_matches_gather(cuda_device, n, frames, cdil, B, masked):
