@@ -39,15 +39,19 @@ class GradAllReduce:
     `finish()` reduces whatever was not announced and waits for everything.  NCCL averages in the collective
     (ReduceOp.AVG); backends without AVG (gloo, used by the CPU tests) sum and scale."""
 
-    def __init__(self, dist, group=None, max_bucket_elems=32 * 1024 * 1024):
+    def __init__(self, dist, group=None, max_bucket_elems=32 * 1024 * 1024, min_bucket_elems=4 * 1024 * 1024):
         self.dist, self.group = dist, group
         self.world = dist.get_world_size(group) if dist is not None and dist.is_initialized() else 1
         self.max_bucket = max_bucket_elems
+        # announced ranges are merged with their neighbours until a bucket holds min_bucket elements (16 MB): a decoder
+        # sub-block is 0.8-2 M parameters, and ~50 collectives of 3-8 MB per backward cost more launch / ring latency
+        # (and SM time taken from the backward kernels) than a dozen of 16-32 MB
+        self.min_bucket = min_bucket_elems
         self.avg = self.world > 1 and dist.get_backend(group) == "nccl"
-        self.flat, self.done, self.handles = None, [], []
+        self.flat, self.done, self.handles, self.pending = None, [], [], None
 
     def begin(self, flat):
-        self.flat, self.done, self.handles = flat, [], []
+        self.flat, self.done, self.handles, self.pending = flat, [], [], None
 
     def _launch(self, lo, hi):
         d = self.dist
@@ -60,11 +64,23 @@ class GradAllReduce:
         if self.world == 1 or hi <= lo:
             return
         self.done.append((lo, hi))
-        self._launch(lo, hi)
+        if self.pending is not None:
+            plo, phi = self.pending
+            if hi == plo or lo == phi:                     # adjacent (the backward finishes sub-blocks in layer order)
+                lo, hi = min(lo, plo), max(hi, phi)
+            else:
+                self._launch(plo, phi)
+        self.pending = (lo, hi)
+        if hi - lo >= self.min_bucket:
+            self._launch(lo, hi)
+            self.pending = None
 
     def finish(self):
         if self.world == 1:
             return
+        if self.pending is not None:
+            self._launch(*self.pending)
+            self.pending = None
         pos = 0
         for lo, hi in sorted(self.done):  # complement of the announced ranges
             if lo > pos:
