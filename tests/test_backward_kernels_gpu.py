@@ -343,7 +343,8 @@ def test_single_query_dense_attention_kernels_match_the_generic_chain(cuda_devic
 
 
 @pytest.mark.parametrize("n,frames,cdil,B,masked", [(2561, 3, 1, 2, True), (2561, 3, 2, 2, True), (1281, 3, 4, 2, False),
-                                                    (1000, 1, 2, 3, True), (258, 2, 1, 2, True)])
+                                                    (1000, 1, 2, 3, True), (258, 2, 1, 2, True),
+                                                    (2561, 3, 1, 9, True)])   # 180 tiles: two tiles per CTA
 def test_cross2dna_bwd_scores_tcgen05_matches_gather(cuda_device, n, frames, cdil, B, masked):
     """Backward of the SparseCross2DNA core with S / dP' from the tcgen05 kernel in scores mode and dq in PV mode vs the
     gather kernels:
@@ -387,7 +388,8 @@ def test_cross2dna_bwd_scores_tcgen05_matches_gather(cuda_device, n, frames, cdi
 @pytest.mark.parametrize("kernel,dil,nv,B,maxf", [((5, 3, 3), (1, 1, 1), 768, 2, 10), ((5, 3, 3), (2, 2, 2), 1279, 2, 10),
                                                   ((5, 3, 3), (4, 4, 4), 2559, 3, 10), ((5, 3, 3), (1, 2, 4), 601, 1, 10),
                                                   ((3, 3, 3), (2, 4, 2), 530, 2, 10), ((3, 1, 3), (1, 1, 4), 256, 2, 10),
-                                                  ((5, 3, 3), (2, 2, 2), 767, 2, 3), ((5, 3, 3), (1, 1, 1), 17, 1, 10)])
+                                                  ((5, 3, 3), (2, 2, 2), 767, 2, 3), ((5, 3, 3), (1, 1, 1), 17, 1, 10),
+                                                  ((5, 3, 3), (1, 1, 1), 2560, 9, 10)])   # 180 tiles: two tiles per CTA
 def test_sparse3dna_bwd_scores_tcgen05_matches_gather(cuda_device, kernel, dil, nv, B, maxf, causal):
     """Backward of the Sparse3DNA core with the logits S and dP' = dO V^T produced by the tcgen05 kernel in scores mode and
     dq by the same kernel in PV mode (dS in the place of the probabilities, V := K; kernel height 3) vs the gather kernels

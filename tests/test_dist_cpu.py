@@ -50,12 +50,16 @@ def _reducer_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from nuwa_pytorch_b200.parallel import GradAllReduce
     flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)      # rank-dependent "gradients"
-    red = GradAllReduce(dist, max_bucket_elems=128)                   # small buckets: exercises the chunking
+    red = GradAllReduce(dist, max_bucket_elems=128, min_bucket_elems=300)   # small buckets: chunking and merging
     red.begin(flat)
-    red.ready(700, 900)   # ranges become final in backward order, with holes that finish() must cover
-    red.ready(300, 700)
+    red.ready(700, 900)   # ranges become final in backward order, with holes that finish() must cover;
+    n0 = len(red.handles)  # 200 < min bucket: held back
+    red.ready(300, 700)   # adjacent -> merged with the pending range into one 600-element bucket (5 chunks of <= 128)
+    n1 = len(red.handles)
     red.ready(0, 0)
+    red.ready(100, 150)   # not adjacent to anything pending, below the minimum: goes out in finish()
     red.finish()
+    assert n0 == 0 and n1 == 5 and red.pending is None
     q.put((rank, flat.tolist()))
     dist.destroy_process_group()
 
