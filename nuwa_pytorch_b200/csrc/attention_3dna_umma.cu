@@ -10,8 +10,8 @@
 // ONE UMMA (N = 16 x valid slot columns <= 160), fetched by one or two TMA boxes over a 5-D view of the q|k|v buffer whose
 // row axis is split by the dilation.  A UNIT is (head, frame offset a):
 //   phase 1   S = Q_h K_{h,a}^T   M=128, N<=160, K=64, accumulator in TMEM (one S buffer per warpgroup); thread = query
-//             row: tcgen05.ld of the 64-column window holding its 3 key rows, the kw in-band entries of each go to a
-//             compact fp32 score row in shared memory (bit test + predicated store per column, immediate offsets); the
+//             row: tcgen05.ld of the 64-column window holding its 3 key rows, dumped to a thread-private shared-memory
+//             row (16 vector stores), the 9 in-band entries read back at per-tile precomputed offsets into registers; the
 //             bos score is a 64-term dot product per thread straight from the Q tile.  Per head: fp32 softmax ->
 //             fp16 probabilities parked in TMEM, column 8u + h = slots (2u, 2u+1) of head h
 //   mix       talking heads (nuwa_pytorch.py:556-558) ON THE TENSOR CORES: for every slot pair u one UMMA whose A operand
@@ -26,6 +26,11 @@
 // tcgen05.mma costs its issuing thread ~70 cycles, the small UMMAs of this kernel are issue bound from one thread).
 // TMEM columns: P [0,184);  phase 1  S0 [192,352) S1 [352,512);  mix  D [192,512);  phase 2  A0 [192,272) A1 [272,352)
 // O0 [352,416) O1 [416,480).
+//
+// Variants (compile time): X2 = SparseCross2DNA (nuwa_pytorch.py:851-895: queries and context in separate buffers, unit =
+// context frame, learned fp32 null key / value in slot 0, context mask on the gathered scores).  MODE 1 = scores only
+// (phase 1, band written to HBM as fp32: logits and dP' = dO V^T of the backward pass), MODE 2 = PV only (phase 2 with a
+// bf16 tensor from HBM in the place of P' and V := K: dq of the backward pass).
 #include <float.h>
 #include <cuda_fp16.h>
 
