@@ -189,10 +189,48 @@ def stack_forward(stack, x, *, context=None, key_mask=None, rotary=None):
 # ------------------------------------------------------------------------------------------------
 # backward
 # ------------------------------------------------------------------------------------------------
+# Weight-gradient GEMMs feed nothing in the backward chain (only the optimiser / the all-reduce), so they run on a second
+# stream: a persistent tcgen05 GEMM and the memory-bound kernels of the chain (LayerNorm backward, row kernels, GEGLU
+# backward, batched attention products) co-reside on the SMs.  The fork / join is captured like any other edge when the
+# step is a CUDA graph.  False = everything on one stream (A/B).
+WGRAD_SIDE_STREAM = True
+_side_streams = {}
+
+
+class _SideWork:
+    def __init__(self):
+        self.keep, self.stream = [], None
+
+    def run(self, fn, *keep):
+        """fn() on the side stream after everything launched so far on the current stream; `keep` = tensors fn reads (held
+        until join() so that the allocator cannot hand their memory out while the side stream still uses them)."""
+        if not WGRAD_SIDE_STREAM:
+            fn()
+            return
+        cur = torch.cuda.current_stream()
+        if self.stream is None:
+            dev = cur.device_index if hasattr(cur, 'device_index') else torch.cuda.current_device()
+            if dev not in _side_streams:
+                _side_streams[dev] = torch.cuda.Stream(device=dev)
+            self.stream = _side_streams[dev]
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.keep.append(keep)
+
+    def join(self):
+        if self.stream is not None and self.keep:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.keep.clear()
+
+
+_side = _SideWork()
+
+
 def _wgrad(dy16, a16, dst):
     """dst (N, K) fp32 += dy16 (M, N).T @ a16 (M, K)"""
     if dst is not None:
-        ops_bwd.gemm_splitk_tn(dy16, a16, dst)
+        _side.run(lambda: ops_bwd.gemm_splitk_tn(dy16, a16, dst), dy16, a16)
 
 
 def _sub_backward(i, s, rec, dy16, B, nt, g, tape, dctx):
@@ -207,15 +245,19 @@ def _sub_backward(i, s, rec, dy16, B, nt, g, tape, dctx):
         dg = ops.gemm(dy16, bw['w2_t'], out_dtype=torch.bfloat16)                     # (M, ip)
         w2g = g(m.net[3].weight)
         if w2g is not None:
-            tmp = torch.zeros(D, ip, dtype=torch.float32, device=dy16.device)
-            ops_bwd.gemm_splitk_tn(dy16, rec['g'], tmp)
-            ops_bwd.add_rows(w2g, tmp, cols=s.ff_inner)
+            def w2_grad(gact=rec['g']):
+                tmp = torch.zeros(D, ip, dtype=torch.float32, device=dy16.device)
+                ops_bwd.gemm_splitk_tn(dy16, gact, tmp)
+                ops_bwd.add_rows(w2g, tmp, cols=s.ff_inner)
+            _side.run(w2_grad, dy16, rec['g'])
         dh = ops_bwd.geglu_bwd(dg, rec['h'])                                         # (M, 2*ip) pair packed
         w1g = g(m.net[0].weight)
         if w1g is not None:
-            tmp = torch.zeros(2 * ip, D, dtype=torch.float32, device=dy16.device)
-            ops_bwd.gemm_splitk_tn(dh, a16, tmp)
-            ops_bwd.add_rows(w1g, tmp, row_map=bw['w1_map'])
+            def w1_grad():
+                tmp = torch.zeros(2 * ip, D, dtype=torch.float32, device=dy16.device)
+                ops_bwd.gemm_splitk_tn(dh, a16, tmp)
+                ops_bwd.add_rows(w1g, tmp, row_map=bw['w1_map'])
+            _side.run(w1_grad, dh, a16)
         return ops.gemm(dh, bw['w1_t'], out_dtype=torch.float32)
     m = s.mod
     inner, H, dh_ = s.inner, s.H, s.dh
@@ -305,7 +347,9 @@ def stack_backward(stack, tape, dout, g, dctx=None, on_done=None):
                        fmap=s.fmap or 0, dx_f32=G[s.read], accumulate=True)
         tape['recs'][i] = None  # free the saved activations of this sub-block
         if on_done is not None:
+            _side.join()  # the weight gradients of this sub-block are complete
             on_done(s)  # every gradient of this sub-block's parameters is final (data-parallel all-reduce can start)
+    _side.join()
     if pack.reversible:
         ops_bwd.add_rows(G[0], G[1])  # both streams start as x
     return G[0]
