@@ -255,7 +255,7 @@ DENSE_BWD_FUSED = True
 
 
 def attn_dense_bwd(q_ptr, k_ptr, v_ptr, do, *, B, nq, nk, H, dh, q_bs, q_rs, kv_bs, kv_rs, talk, dtalk, null_k, null_v,
-                   dnull_k, dnull_v, key_mask, dq_out, dq_bs, dq_rs, dk_ptr, dv_ptr, dkv_bs, dkv_rs, out_f32):
+                   dnull_k, dnull_v, key_mask, dq_out, dq_bs, dq_rs, dk_ptr, dv_ptr, dkv_bs, dkv_rs, out_f32, side=None, keep=()):
     """Backward of ops.attn_dense (Attention core with the learned null key, key mask and talking heads).
     q/k/v: bf16 device pointers with element strides; do: bf16 (B, nq, inner) contiguous.
     dq_out: (dtype donor tensor, pointer) ; dk_ptr / dv_ptr: raw pointers of the same dtype (bf16, or fp32 when out_f32).
@@ -316,16 +316,23 @@ def attn_dense_bwd(q_ptr, k_ptr, v_ptr, do, *, B, nq, nk, H, dh, q_bs, q_rs, kv_
     # dQ = dS K
     bgemm(dS, kfull, dq_out, M=nq, N=dh, K=jp, a_trans=0, b_trans=1, lda=jp, ldb=inner, ldc=dq_rs, batch1=B, batch2=H,
           a_s=sc, b_s=full_s, c_s=(dq_bs, dh))
-    # dK = dS^T Q ; dV = P'^T dO     (fp32, including the null slot and the zero pad rows)
-    dkfull = torch.empty(B, jp, inner, dtype=torch.float32, device=dev)
-    dvfull = torch.empty(B, jp, inner, dtype=torch.float32, device=dev)
-    bgemm(dS, q_ptr, dkfull, M=jp, N=dh, K=nq, a_trans=1, b_trans=1, lda=jp, ldb=q_rs, ldc=inner, batch1=B, batch2=H,
-          a_s=sc, b_s=(q_bs, dh), c_s=full_s)
-    bgemm(Pp, do, dvfull, M=jp, N=dh, K=nq, a_trans=1, b_trans=1, lda=jp, ldb=inner, ldc=inner, batch1=B, batch2=H,
-          a_s=sc, b_s=(nq * inner, dh), c_s=full_s)
-    k16, v16, k32, v32 = (None, None, dk_ptr, dv_ptr) if out_f32 else (dk_ptr, dv_ptr, None, None)
-    check(lib().nuwa_kv_full_split(ptr(dkfull), ptr(dvfull), ptr(dnull_k), ptr(dnull_v), k16, v16, k32, v32, dkv_bs, dkv_rs,
-                                   B, nk, jp, inner, stream()), "nuwa_kv_full_split")
+    # dK = dS^T Q ; dV = P'^T dO     (fp32, including the null slot and the zero pad rows).  The key / value branch feeds
+    # nothing the query branch needs: with `side` (an object with run(fn, *keep), train._SideWork) it goes to the second
+    # stream; `keep` = the tensors behind the raw q / k / v pointers
+    def key_value_branch():
+        dkfull = torch.empty(B, jp, inner, dtype=torch.float32, device=dev)
+        dvfull = torch.empty(B, jp, inner, dtype=torch.float32, device=dev)
+        bgemm(dS, q_ptr, dkfull, M=jp, N=dh, K=nq, a_trans=1, b_trans=1, lda=jp, ldb=q_rs, ldc=inner, batch1=B, batch2=H,
+              a_s=sc, b_s=(q_bs, dh), c_s=full_s)
+        bgemm(Pp, do, dvfull, M=jp, N=dh, K=nq, a_trans=1, b_trans=1, lda=jp, ldb=inner, ldc=inner, batch1=B, batch2=H,
+              a_s=sc, b_s=(nq * inner, dh), c_s=full_s)
+        k16, v16, k32, v32 = (None, None, dk_ptr, dv_ptr) if out_f32 else (dk_ptr, dv_ptr, None, None)
+        check(lib().nuwa_kv_full_split(ptr(dkfull), ptr(dvfull), ptr(dnull_k), ptr(dnull_v), k16, v16, k32, v32, dkv_bs, dkv_rs,
+                                       B, nk, jp, inner, stream()), "nuwa_kv_full_split")
+    if side is not None:
+        side.run(key_value_branch, dS, Pp, do, *keep)
+    else:
+        key_value_branch()
 
 
 def attn_cross2dna_bwd(q, kv, do, *, B, n, nk, H, dh, talk, dtalk, null_k, null_v, dnull_k, dnull_v, key_mask, fmap, ck, cdil):

@@ -303,7 +303,7 @@ def _sub_backward(i, s, rec, dy16, B, nt, g, tape, dctx):
                                    dtalk=dtalk, null_k=s.null_k, null_v=s.null_v, dnull_k=dnk, dnull_v=dnv,
                                    key_mask=ctx.mask, dq_out=dq, dq_bs=nt * inner, dq_rs=inner, dk_ptr=dkv.data_ptr(),
                                    dv_ptr=dkv.data_ptr() + inner * 2, dkv_bs=nk * 2 * inner, dkv_rs=2 * inner,
-                                   out_f32=False)
+                                   out_f32=False, side=_side, keep=(q, kv, dkv))
         else:
             dq, dkv = ops_bwd.attn_cross2dna_bwd(q.view(B, nt, inner), kv.view(B, nk, 2 * inner), do.view(B, nt, inner), B=B,
                                                  n=nt, nk=nk, H=H, dh=dh_, talk=s.talk, dtalk=dtalk, null_k=s.null_k,
@@ -313,7 +313,9 @@ def _sub_backward(i, s, rec, dy16, B, nt, g, tape, dctx):
         _wgrad(dq, a16, g(m.to_q.weight))
         if dctx is not None:
             _wgrad(dkv, ctx.ctx16.view(B * nk, -1), g(m.to_kv.weight))
-            ops.gemm(dkv, bw['w_kv_t'], residual=dctx, out=dctx)                      # dctx += dkv @ W_kv
+            # dctx += dkv @ W_kv: the context gradient is consumed after this stack's backward (text / sketch encoder), and
+            # dkv of the dense kind is produced on the second stream -> same stream, submission order
+            _side.run(lambda: ops.gemm(dkv, bw['w_kv_t'], residual=dctx, out=dctx), dkv)
         return ops.gemm(dq, bw['w_q_t'], out_dtype=torch.float32)
     else:
         raise NotImplementedError(s.kind)
