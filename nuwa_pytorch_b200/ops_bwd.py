@@ -335,7 +335,8 @@ def attn_dense_bwd(q_ptr, k_ptr, v_ptr, do, *, B, nq, nk, H, dh, q_bs, q_rs, kv_
         key_value_branch()
 
 
-def attn_cross2dna_bwd(q, kv, do, *, B, n, nk, H, dh, talk, dtalk, null_k, null_v, dnull_k, dnull_v, key_mask, fmap, ck, cdil):
+def attn_cross2dna_bwd(q, kv, do, *, B, n, nk, H, dh, talk, dtalk, null_k, null_v, dnull_k, dnull_v, key_mask, fmap, ck, cdil,
+                       side=None):
     """Backward of the SparseCross2DNA core over a full teacher-forced pass (nuwa_pytorch.py:794-901): position 0 (bos) is a
     dense query over [null] + every context token WITHOUT talking heads (:828-844), positions 1.. attend to the null key
     and the ck x ck window at their own (y, x) in every context frame (:851-895).
@@ -386,11 +387,18 @@ def attn_cross2dna_bwd(q, kv, do, *, B, n, nk, H, dh, talk, dtalk, null_k, null_
     if rc == _lib.NUWA_ERR_INVALID:
         check(lib().nuwa_attnx2_bwd_dq(p, ptr(dS), jp, dq.data_ptr() + inner * 2, n * inner, inner, stream()),
               "nuwa_attnx2_bwd_dq")
-    check(lib().nuwa_attnx2_bwd_dkdv(p, nk, do_q, n * inner, inner, ptr(dS), ptr(Pp), jp, ptr(base),
-                                     base.data_ptr() + inner * 4, nk * 2 * inner, 2 * inner, dkv.data_ptr(),
-                                     dkv.data_ptr() + inner * 2, nk * 2 * inner, 2 * inner, stream()),
-          "nuwa_attnx2_bwd_dkdv")
-    check(lib().nuwa_attn_bwd_first_key(q.data_ptr() + inner * 2, n * inner, inner, do_q, n * inner, inner, ptr(dS),
-                                        ptr(Pp), jp, B, H, dh, nq, ptr(dnull_k), ptr(dnull_v), 0, stream()),
-          "nuwa_attn_bwd_first_key")
+    # key / value branch (key-centric pass + null key / value column reduction): feeds only the to_kv weight gradient and the
+    # context gradient -> second stream when `side` is given (train._SideWork)
+    def key_value_branch():
+        check(lib().nuwa_attnx2_bwd_dkdv(p, nk, do_q, n * inner, inner, ptr(dS), ptr(Pp), jp, ptr(base),
+                                         base.data_ptr() + inner * 4, nk * 2 * inner, 2 * inner, dkv.data_ptr(),
+                                         dkv.data_ptr() + inner * 2, nk * 2 * inner, 2 * inner, stream()),
+              "nuwa_attnx2_bwd_dkdv")
+        check(lib().nuwa_attn_bwd_first_key(q.data_ptr() + inner * 2, n * inner, inner, do_q, n * inner, inner, ptr(dS),
+                                            ptr(Pp), jp, B, H, dh, nq, ptr(dnull_k), ptr(dnull_v), 0, stream()),
+              "nuwa_attn_bwd_first_key")
+    if side is not None:
+        side.run(key_value_branch, q, kv, do, dS, Pp, base, dkv, key_mask, talk)
+    else:
+        key_value_branch()
     return dq, dkv

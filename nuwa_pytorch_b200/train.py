@@ -308,7 +308,7 @@ def _sub_backward(i, s, rec, dy16, B, nt, g, tape, dctx):
             dq, dkv = ops_bwd.attn_cross2dna_bwd(q.view(B, nt, inner), kv.view(B, nk, 2 * inner), do.view(B, nt, inner), B=B,
                                                  n=nt, nk=nk, H=H, dh=dh_, talk=s.talk, dtalk=dtalk, null_k=s.null_k,
                                                  null_v=s.null_v, dnull_k=dnk, dnull_v=dnv, key_mask=ctx.mask, fmap=s.fmap,
-                                                 ck=s.ck, cdil=s.cdil)
+                                                 ck=s.ck, cdil=s.cdil, side=_side)
             dq, dkv = dq.view(M, inner), dkv.view(B * nk, 2 * inner)
         _wgrad(dq, a16, g(m.to_q.weight))
         if dctx is not None:
