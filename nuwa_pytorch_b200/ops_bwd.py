@@ -330,7 +330,7 @@ def attn_dense_bwd(q_ptr, k_ptr, v_ptr, do, *, B, nq, nk, H, dh, q_bs, q_rs, kv_
         check(lib().nuwa_kv_full_split(ptr(dkfull), ptr(dvfull), ptr(dnull_k), ptr(dnull_v), k16, v16, k32, v32, dkv_bs, dkv_rs,
                                        B, nk, jp, inner, stream()), "nuwa_kv_full_split")
     if side is not None:
-        side.run(key_value_branch, dS, Pp, do, *keep)
+        side.run(key_value_branch, dS, Pp, do, dnull_k, dnull_v, *keep)
     else:
         key_value_branch()
 
@@ -398,7 +398,7 @@ def attn_cross2dna_bwd(q, kv, do, *, B, n, nk, H, dh, talk, dtalk, null_k, null_
                                             ptr(Pp), jp, B, H, dh, nq, ptr(dnull_k), ptr(dnull_v), 0, stream()),
               "nuwa_attn_bwd_first_key")
     if side is not None:
-        side.run(key_value_branch, q, kv, do, dS, Pp, base, dkv, key_mask, talk)
+        side.run(key_value_branch, q, kv, do, dS, Pp, base, dkv, key_mask, talk, dnull_k, dnull_v)
     else:
         key_value_branch()
     return dq, dkv
