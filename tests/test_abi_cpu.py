@@ -89,3 +89,14 @@ def test_weight_packing_layouts():
     assert pc.shape == (8, 9 * 64) and pc.dtype == torch.bfloat16
     assert torch.equal(pc.view(8, 9, 64)[:, 4, :5].float(), cw[:, :, 1, 1].bfloat16().float())
     assert pc.view(8, 9, 64)[:, :, 5:].abs().sum() == 0
+
+
+def test_default_kernel_selection_switches():
+    """The A/B switches the GPU tests flip (and restore) must ship in their product positions: tensor-core / fused paths on,
+    kernel choice automatic."""
+    from nuwa_pytorch_b200 import ops_bwd, train
+    assert ops_bwd.WGRAD_TN is True            # weight gradients read dY / X contraction-major (no transposes)
+    assert ops_bwd.DENSE_BWD_FUSED is True     # dense-attention backward: probability stage fused
+    assert ops_bwd.Q1_KERNELS is True          # single-query dense attention kernels
+    assert ops_bwd.SCORES_VARIANT == 'auto'    # Sparse3DNA backward scores / dq: tcgen05 kernel inside its envelope
+    assert train.WGRAD_SIDE_STREAM is True     # weight-gradient GEMMs + key / value branches on the second stream
